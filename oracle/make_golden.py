@@ -1,0 +1,178 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/ref_shim_*.npz by executing the reference's OWN source files
+(/root/reference/signals.py, /root/reference/model.py, unmodified, imported from where
+they lie) over the torch-backed TensorFlow shim in oracle/tf_shim.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the reference checkout does not
+exist on the GPU box; the committed .npz fixtures are what travels):
+
+    python oracle/make_golden.py [--ref /root/reference] [--out tests/golden]
+
+Also writes tests/golden/kat_appendix_b.npz (SURVEY.md Appendix B known answers).
+"""
+import argparse
+import configparser
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--ref', default='/root/reference')
+    ap.add_argument('--out', default=os.path.join(os.path.dirname(HERE), 'tests', 'golden'))
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+
+    sys.path.insert(0, os.path.join(HERE, 'tf_shim'))
+    sys.path.insert(1, args.ref)
+    import tensorflow as tf          # the shim
+    import torch
+    import signals as ref_signals    # the reference, unmodified
+    import model as ref_model        # the reference, unmodified
+
+    cfg = configparser.ConfigParser()
+    cfg.read(os.path.join(args.ref, 'config'))
+    params = cfg['DEFAULT']
+    params['simulate_noise'] = 'False'          # as train.py:256 does before building the fine-tuner
+
+    rng = np.random.default_rng(20261018)
+
+    # ------------------------------------------------------------------ A. forward + tape.gradient
+    n = 192
+    oef = rng.uniform(0.04, 0.84, n)
+    dbv = rng.uniform(0.001, 0.201, n)
+    x = np.stack([oef, dbv], -1).astype(np.float32)
+    x[:4] = [[0.4, 0.12], [0.4, 0.03], [0.04, 0.001], [0.84, 0.201]]
+    g_rand = rng.standard_normal((n, 11)).astype(np.float32)
+    out = {'oef_dbv': x, 'g_rand': g_rand}
+    for full in (True, False):
+        for blood in (True, False):
+            layer = ref_signals.SignalGenerationLayer(params, full, blood)
+            key = 'f%d_b%d' % (int(full), int(blood))
+            inp = tf.convert_to_tensor(x.reshape(n, 1, 1, 1, 2))
+            with tf.GradientTape(persistent=True) as tape:
+                tape.watch(inp)
+                o = layer(inp)
+                o_w = o * tf.convert_to_tensor(g_rand.reshape(n, 1, 1, 1, 11))
+            out['signal_' + key] = o.detach().numpy().reshape(n, 11)
+            out['grad_ones_' + key] = tape.gradient(o, inp).numpy().reshape(n, 2)
+            out['grad_rand_' + key] = tape.gradient(o_w, inp).numpy().reshape(n, 2)
+            out['taus'] = layer._taus.numpy()
+    np.savez(os.path.join(args.out, 'ref_shim_forward.npz'), **out)
+    print('forward: demo input (signals.py:309) ->', out['signal_f1_b1'][0])
+
+    # ------------------------------------------------------------------ B. ELBO pieces
+    def run_elbo(tag, multi_norm, df, seed):
+        B, X, Y, Z = 2, 4, 4, 2
+        nv = B * X * Y * Z
+        r = np.random.default_rng(seed)
+        q = np.stack([r.normal(-0.3, 0.7, nv), r.normal(0.0, 0.6, nv), r.normal(-1.2, 0.7, nv),
+                      r.normal(0.0, 0.6, nv), r.normal(0.0, 0.8, nv)], -1).astype(np.float32)
+        prior = (q + r.normal(0, 0.3, (nv, 5))).astype(np.float32)
+        sigma = np.exp(r.normal(np.log(0.05), 0.2, (nv, 11))).astype(np.float32)
+        mask = (r.uniform(size=nv) > 0.25).astype(np.float32)
+        truth = np.stack([r.uniform(0.1, 0.7, nv), r.uniform(0.005, 0.15, nv)], -1).astype(np.float32)
+        sig_layer = ref_signals.SignalGenerationLayer(params, True, True)
+        data = sig_layer(tf.convert_to_tensor(truth)).numpy() * 100.0
+        data = (data * (1.0 + 0.02 * r.standard_normal((nv, 11)))).astype(np.float32)
+        data = data * mask[:, None]                                   # train.py:56 pre-masks the data
+
+        trainer = ref_model.EncoderTrainer(system_params=params, no_units=60, no_intermediate_layers=2,
+                                           student_t_df=df, initial_im_sigma=0.05,
+                                           multi_image_normalisation=multi_norm, channelwise_gating=True,
+                                           infer_inv_gamma=False, use_population_prior=False, use_mvg=True,
+                                           predict_log_data=False)
+        shp = (B, X, Y, Z)
+        q_t = tf.convert_to_tensor(q.reshape(shp + (5,)))
+        s_t = tf.convert_to_tensor(sigma.reshape(shp + (11,)))
+        m_t = tf.convert_to_tensor(mask.reshape(shp + (1,)))
+        d_t = tf.convert_to_tensor(data.reshape(shp + (11,)))
+        p_t = tf.convert_to_tensor(prior.reshape(shp + (5,)))
+        q_t.requires_grad_(True)
+        s_t.requires_grad_(True)
+        tf.random.set_seed(seed)
+        tf.random.LOG.clear()
+        sampled = ref_model.ReparamTrickLayer(trainer)((q_t, m_t))     # model.py:248
+        pred = sig_layer(sampled)                                      # model.py:273
+        y_pred = tf.concat([pred, s_t], -1)                            # model.py:276
+        y_true = tf.concat([d_t, m_t], -1)                             # train.py:58,62
+        nll = trainer.fine_tune_loss_fn(y_true, y_pred)
+        nll_map = trainer.fine_tune_loss_fn(y_true, y_pred, return_mean=False)
+        n_before_kl = len(tf.random.LOG)
+        kl = trainer.kl_loss(tf.concat([p_t, m_t], -1), q_t)           # 70 samples (model.py:654)
+        eps = tf.random.LOG[0][1].numpy().reshape(nv, 2)
+        eps_kl = np.stack([e[1].numpy().reshape(nv, 2) for e in tf.random.LOG[n_before_kl:]], 1)
+        assert eps_kl.shape == (nv, 70, 2), eps_kl.shape
+        g_nll = torch.autograd.grad(nll, [q_t, s_t], retain_graph=True)
+        g_kl = torch.autograd.grad(kl, [q_t], retain_graph=True)
+        # second, independent KL evaluation for the per-voxel map (fresh draws are recorded too)
+        n0 = len(tf.random.LOG)
+        kl_map = trainer.kl_loss(tf.concat([p_t, m_t], -1), q_t, return_mean=False, no_samples=70)
+        eps_kl2 = np.stack([e[1].numpy().reshape(nv, 2) for e in tf.random.LOG[n0:]], 1)
+        np.savez(os.path.join(args.out, 'ref_shim_elbo_%s.npz' % tag),
+                 q=q, prior=prior, sigma=sigma, mask=mask, data=data, eps=eps, eps_kl=eps_kl,
+                 sampled=sampled.detach().numpy().reshape(nv, 2), pred=pred.detach().numpy().reshape(nv, 11),
+                 nll=nll.detach().numpy(), kl=kl.detach().numpy(),
+                 nll_map=nll_map.detach().numpy().reshape(nv),
+                 grad_q_nll=g_nll[0].numpy().reshape(nv, 5), grad_sigma=g_nll[1].numpy().reshape(nv, 11),
+                 grad_q_kl=g_kl[0].numpy().reshape(nv, 5),
+                 eps_kl2=eps_kl2, kl_map2=kl_map.detach().numpy().reshape(nv),
+                 multi_image_normalisation=multi_norm, student_t_df=df, se_idx=trainer._se_idx)
+        print('elbo[%s]: nll=%.6f kl=%.6f' % (tag, float(nll), float(kl)))
+        return trainer, q
+
+    trainer, q = run_elbo('optimal', False, 200, 11)
+    run_elbo('multinorm', True, 200, 12)
+    run_elbo('studentt', False, 10, 13)
+
+    # ------------------------------------------------------------------ C. calculate_means
+    nv = q.shape[0]
+    tf.random.set_seed(5)
+    tf.random.LOG.clear()
+    q5 = tf.convert_to_tensor(q.reshape(2, 4, 4, 2, 5))
+    means, stds = trainer.calculate_means(q5, tf.ones_like(q5[:, :, :, :, :1]), include_r2p=True,
+                                          return_stds=True, no_samples=16)
+    eps_s = np.stack([e[1].numpy().reshape(nv, 2) for e in tf.random.LOG], 1)
+    np.savez(os.path.join(args.out, 'ref_shim_means.npz'), q=q, eps=eps_s,
+             means=means.numpy().reshape(nv, 3), stds=stds.numpy().reshape(nv, 3))
+
+    # ------------------------------------------------------------------ D. create_synthetic_dataset
+    for tag, uprop in (('u10', 0.1), ('u0', 0.0)):
+        p2 = configparser.ConfigParser()
+        p2.read(os.path.join(args.ref, 'config'))
+        p2 = p2['DEFAULT']
+        p2['sample_size'] = '23'                                       # 529 voxels: exercises the S^2 % 10 != 0 row drop
+        tf.random.set_seed(7)
+        tf.random.LOG.clear()
+        tx, ty = ref_signals.create_synthetic_dataset(p2, True, True, 0.0, uniform_prop=uprop)
+        log = tf.random.LOG
+        kinds = [k for k, _ in log]
+        assert kinds[:5] == ['uniform', 'normal', 'uniform', 'truncnorm_u', 'perm'], kinds[:5]
+        perm = log[4][1].numpy()
+        snr_u = np.concatenate([log[5 + 2 * i][1].numpy() for i in range(10)], 0)
+        noise = np.concatenate([log[6 + 2 * i][1].numpy() for i in range(10)], 0)
+        # marginals exactly as the reference formed them
+        ty_np = ty.numpy()
+        np.savez(os.path.join(args.out, 'ref_shim_dataset_%s.npz' % tag),
+                 train_x=tx.numpy(), train_y=ty_np, perm=perm, snr_u01=snr_u, noise_eps=noise,
+                 oef_u01=log[0][1].numpy(), oef_n01=log[1][1].numpy(), dbv_u01=log[2][1].numpy(),
+                 dbv_tn_u01=log[3][1].numpy(), uniform_prop=uprop, sample_size=23)
+        print('dataset[%s]: x %s y %s' % (tag, tuple(tx.shape), tuple(ty.shape)))
+
+    # ------------------------------------------------------------------ E. Appendix B KATs
+    np.savez(os.path.join(args.out, 'kat_appendix_b.npz'),
+             oef_dbv=np.array([[0.4, 0.12], [0.4, 0.03]]),
+             signal_fp64_0=np.array([0.37586412, 0.40909051, 0.42242562, 0.40909051, 0.37586412, 0.33616669,
+                                     0.29923692, 0.26730955, 0.23914064, 0.21358386, 0.19047615]),
+             grad_sum_0=np.array([-3.06411134, -7.29813321]),
+             signal_fp32_1=np.array([0.41349795, 0.42242014, 0.4258472, 0.42242014, 0.41349795, 0.4020199,
+                                     0.39038378, 0.3794184, 0.36889765, 0.35852298, 0.34832814]),
+             tissue_tau0=np.array(0.42698773))
+
+
+if __name__ == '__main__':
+    main()
