@@ -1,0 +1,186 @@
+/*
+ * qbold.h -- C ABI of libqbold.so: the B200-native (sm_100a) implementation of the
+ * qBOLD-VI hot path (voxel-wise ASE qBOLD forward signal model fused with the
+ * amortized-VI likelihood).
+ *
+ * The reference (wearepal/qBOLD-VI) has no FFI: the path sits behind Python/Keras
+ * objects.  Each entry point below names the reference interface it replaces
+ * (file:line in the reference checkout).  The Python host mirror in
+ * qbold_vi_b200/ binds these with ctypes and re-exposes the reference's own names
+ * (SignalGenerationLayer, create_synthetic_dataset, ReparamTrickLayer,
+ * EncoderTrainer.*); see INTEGRATION.md.
+ *
+ * Conventions
+ *   - all array pointers are DEVICE pointers owned by the caller unless the function
+ *     name ends in _host; float32, C-contiguous, last axis fastest;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous with respect to the host;
+ *   - no hidden device allocation except the *_host helpers (cached staging buffers);
+ *   - return value: 0 = ok, negative = QBOLD_E*; qbold_last_error() gives the text
+ *     (thread-local);
+ *   - QboldParams is an immutable POD; the functions are stateless and may be called
+ *     concurrently from one host thread per GPU.
+ */
+#ifndef QBOLD_H_
+#define QBOLD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QBOLD_MAX_TAU 32
+#define QBOLD_NQ 129              /* 2**7 + 1 Simpson nodes, signals.py:168 */
+#define QBOLD_NQ_PAD 132
+#define QBOLD_ABI_VERSION 1
+
+#define QBOLD_OK 0
+#define QBOLD_EINVAL (-1)         /* bad argument (the reference would assert / raise) */
+#define QBOLD_ECUDA (-2)          /* CUDA runtime error */
+#define QBOLD_EUNSUPPORTED (-3)   /* e.g. noise requested for n_tau not in {11,24}: signals.py:117-121 */
+
+/* Physics constants exactly as SignalGenerationLayer.__init__ parses them from the
+ * `config` INI (signals.py:29-46), as doubles (Python floats). */
+typedef struct QboldPhysics {
+    double gamma, b0, dchi, te, r2t, tr, ti, t1b, hct;
+} QboldPhysics;
+
+/* Likelihood options of EncoderTrainer (model.py:54-95). */
+typedef struct QboldLikelihood {
+    int32_t se_idx;                    /* model.py:95 */
+    int32_t multi_image_normalisation; /* model.py:540-545 */
+    int32_t predict_log_data;          /* model.py:547-549 */
+    int32_t reserved;
+    double student_t_df;               /* <50 -> StudentT, else Gaussian (model.py:557-561); <=0 = None */
+} QboldLikelihood;
+
+/* Resolved, device-ready parameter block (passed by value to the kernels as a
+ * __grid_constant__).  Filled by qbold_params_init(); treat as opaque + immutable. */
+typedef struct QboldParams {
+    int32_t abi_version;
+    int32_t n_tau;
+    int32_t n_cols;                    /* distinct non-zero |tau| values */
+    int32_t full_model;                /* signals.py:192 */
+    int32_t include_blood;             /* signals.py:100 */
+    int32_t se_idx;
+    int32_t multi_image_normalisation;
+    int32_t predict_log_data;
+    float student_t_df;                /* <=0 or >=50: Gaussian */
+    float student_t_logc;              /* lgamma((df+1)/2)-lgamma(df/2)-0.5*log(df*pi) */
+    float dw_k_nohct;                  /* float32((4/3) pi gamma b0 dchi)            signals.py:144 */
+    float dw_k;                        /* float32((4/3) pi gamma b0 dchi hct)        signals.py:144 */
+    float hct;
+    float e_tissue;                    /* exp(-te*r2t), float32 exp                  signals.py:172 */
+    float kappa;                       /* m_bld * nb (float32 ops)                   signals.py:105-107 */
+    float e_blood;                     /* exp(-r2b*te)                               signals.py:241 */
+    float blood_c0;                    /* (4/45) hct (1-hct)                         signals.py:239 */
+    float blood_c1;                    /* 4 pi b0 dchi                               signals.py:239 */
+    float blood_hg;                    /* 0.5 gamma^2                                signals.py:241 */
+    float blood_td2;                   /* td^2, td = 2.6^2/2 ms                      signals.py:236-238 */
+    float node0_c;                     /* true Simpson weight * g(u_0) of node 0 (value path) */
+    float pad0;
+    float tau[QBOLD_MAX_TAU];          /* tf.range(...) values, float32              signals.py:34 */
+    float blood_b[QBOLD_MAX_TAU];      /* tau-only bracket of calc_blood             signals.py:242-247 */
+    float abs_tau[QBOLD_MAX_TAU];      /* distinct non-zero |tau| (bitwise dedup)    */
+    int32_t col_of_tau[QBOLD_MAX_TAU]; /* tau index -> column, -1 for tau == 0       */
+    float norm_snr[QBOLD_MAX_TAU];     /* signals.py:119-121; all zero if undefined  */
+    float qu[QBOLD_NQ_PAD];            /* quadrature nodes u_k (tf.linspace)         signals.py:166-168 */
+    float qc[QBOLD_NQ_PAD];            /* value weights  W_k g_k, qc[0]=0 (node 0 dead in FP32), qc[128]=0 */
+    float qd[QBOLD_NQ_PAD];            /* derivative weights W_k g_k u_k (node 0 live) */
+} QboldParams;
+
+int qbold_abi_version(void);
+/* sizeof(QboldParams) as compiled into the library: bindings verify their struct layout against it. */
+int qbold_params_sizeof(void);
+const char* qbold_last_error(void);
+
+/* Replaces SignalGenerationLayer.__init__ (signals.py:18-53): resolve the physics,
+ * the tau grid (explicit float32 values) and the flags. */
+int qbold_params_init(QboldParams* out, const QboldPhysics* phys, const float* taus, int32_t n_tau,
+                      int32_t full_model, int32_t include_blood);
+/* Sets the EncoderTrainer likelihood options used by qbold_elbo_fused (model.py:54-95). */
+int qbold_params_set_likelihood(QboldParams* p, const QboldLikelihood* lik);
+
+/* Replaces SignalGenerationLayer.call with noise off (signals.py:55-114,137-140).
+ * oef_dbv [n,width], width 2 (OEF,DBV) or 3 (+Hct, variable_hct); signal [n,n_tau]. */
+int qbold_forward(const QboldParams* p, const float* oef_dbv, int32_t width, int64_t n,
+                  float* signal, void* stream);
+
+/* Forward + the vector-Jacobian product TensorFlow autodiff gives through
+ * SignalGenerationLayer.call (bessel_j0' = -bessel_j1): g_oef_dbv[n,2] =
+ * d(sum(signal*g_signal))/d(oef,dbv).  g_signal NULL means all ones (the
+ * signals.py:307-314 demo).  signal may be NULL. */
+int qbold_forward_backward(const QboldParams* p, const float* oef_dbv, const float* g_signal,
+                           int64_t n, float* signal, float* g_oef_dbv, void* stream);
+
+/* Same call with HOST buffers: chunked, double-buffered H2D -> kernel -> D2H on
+ * internal streams of the current device; returns after the results are in host memory. */
+int qbold_forward_backward_host(const QboldParams* p, const float* h_oef_dbv, const float* h_g_signal,
+                                int64_t n, float* h_signal, float* h_g_oef_dbv);
+
+/* Replaces ReparamTrickLayer.call (model.py:21-50), use_mvg branch: q [n,5] raw encoder
+ * outputs; eps [n,2] explicit N(0,1) draws, or NULL -> Philox4x32-10 keyed (seed, voxel). */
+int qbold_reparam_sample(const float* q, const float* eps, uint64_t seed, uint64_t offset,
+                         int64_t n, float* oef_dbv, void* stream);
+
+/* Column means of a [n,n_tau] signal block (the batch statistic of signals.py:126);
+ * mean is a device array [n_tau]; scratch is a device array of >= 2*n_tau doubles. */
+int qbold_column_mean(const float* signal, int64_t n, int32_t n_tau, float* mean, double* scratch,
+                      void* stream);
+
+/* Noise model (signals.py:116-128) in place: snr ~ U(50,120) * norm_snr, std = mean/snr,
+ * signal += N(0,1)*std.  snr_u01 [n] and eps [n,n_tau] are explicit draws, or both NULL ->
+ * Philox keyed by (seed, offset+voxel). */
+int qbold_add_noise(const QboldParams* p, float* signal, int64_t n, const float* mean,
+                    const float* snr_u01, const float* eps, uint64_t seed, uint64_t offset,
+                    void* stream);
+
+/* Replaces the body of create_synthetic_dataset (signals.py:270-299) for rows
+ * [first, first+count) of the shuffled OEF x DBV meshgrid: labels y3 = (OEF, DBV, R2')
+ * and the clean signal x.  perm (int64 [n_oef*n_dbv]) is an explicit shuffle, or NULL ->
+ * keyed Feistel bijection of the index space (no permutation array in HBM). */
+int qbold_generate(const QboldParams* p, const float* oefs, int64_t n_oef, const float* dbvs,
+                   int64_t n_dbv, const int64_t* perm, uint64_t seed, int64_t first, int64_t count,
+                   float* x, float* y3, void* stream);
+
+/* Fused training step of the VI likelihood: replaces ReparamTrickLayer (model.py:21-50)
+ * -> SignalGenerationLayer (signals.py:55-114) -> fine_tune_loss_fn (model.py:527-568)
+ * + kl_weight * kl_loss (model.py:654-665, 70-sample MC estimator :592-610) and the
+ * backward pass TensorFlow autodiff would run, in one kernel.
+ *   q, prior [n,5]; sigma, y [n,n_tau]; mask [n];
+ *   eps [n,2] / eps_kl [n,kl_samples,2] explicit draws or NULL -> Philox (seed, offset+voxel);
+ *   inv_mask_sum = 1/sum(mask) over the GLOBAL batch (all ranks);
+ *   outputs: grad_q [n,5], grad_sigma [n,n_tau] (d(nll + kl_weight*kl)/d.), optional
+ *   nll_map/kl_map [n], sums[4] (device doubles: sum nll*mask, sum kl, sum mask, #non-finite). */
+int qbold_elbo_fused(const QboldParams* p, const float* q, const float* sigma, const float* y,
+                     const float* mask, const float* prior, const float* eps, const float* eps_kl,
+                     uint64_t seed, uint64_t offset, int32_t kl_samples, float inv_mask_sum,
+                     float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
+                     float* kl_map, double* sums, void* stream);
+
+/* kl_loss alone (model.py:654-665 -> mvg_kl_samples :592-610): per-voxel KL(q || prior) map
+ * (zero where mask <= 0; mask may be NULL) and, optionally, grad_q[n,5] = d kl_map[v] / d q[v,:]
+ * (path-derivative estimator: stop_gradient on q inside log q, model.py:596).
+ * n_samples = 70 is the reference default; n_samples = 0 selects the closed-form KL. */
+int qbold_kl(const float* q, const float* prior, const float* mask, const float* eps_kl, uint64_t seed,
+             uint64_t offset, int32_t n_samples, int64_t n, float* kl_map, float* grad_q, void* stream);
+
+/* Replaces calculate_means(include_r2p=True, return_stds=True) (model.py:326-343):
+ * n_samples reparameterised draws per voxel -> mean3/var3 [n,3] of (OEF, DBV, R2').
+ * eps [n,n_samples,2] or NULL -> Philox. */
+int qbold_posterior_stats(const QboldParams* p, const float* q, const float* eps, uint64_t seed,
+                          uint64_t offset, int32_t n_samples, int64_t n, float* mean3, float* var3,
+                          void* stream);
+
+/* FP32 FMA micro-benchmark (roofline denominator measured in the same run): launches
+ * `iters` dependent-chain FFMA sweeps, returns achieved TFLOP/s through *tflops. */
+int qbold_fma_peak(int32_t iters, double* tflops);
+
+/* Counters: number of kernels this library launched since load (bench's gpu_launches). */
+int64_t qbold_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QBOLD_H_ */

@@ -1,0 +1,516 @@
+// K2: fused amortized-VI training step of the likelihood side.
+//
+// One kernel replaces, per voxel (reference file:line):
+//   ReparamTrickLayer.call           model.py:21-50    logit-normal reparameterised sample
+//   SignalGenerationLayer.call       signals.py:55-114 forward model (+ J1 sweep for the gradient)
+//   fine_tune_loss_fn                model.py:527-568  tau=0 normalisation, Gaussian / Student-t NLL, mask
+//   kl_loss -> mvg_kl_samples        model.py:654-665, 592-610, 376-447  MC KL(q || prior)
+// and the backward pass TensorFlow autodiff runs through all of it (stop_gradient on q inside
+// log q, identity gradient through the clip, bessel_j0' = -bessel_j1).  The predicted signal
+// never reaches HBM: only grad_q [n,5], grad_sigma [n,n_tau] and the loss partial sums are written.
+#include "qbold_core.cuh"
+#include "launch.h"
+#include "rng.cuh"
+
+namespace qb {
+
+constexpr float kOefRange = 0.8f, kMinOef = 0.04f, kDbvRange = 0.2f, kMinDbv = 0.001f;   // model.py:88-91
+constexpr float kExpM2 = 0.1353352832366127f;                                            // np.exp(-2.0), model.py:294
+constexpr float kLog2Pi = 1.8378770664093453f;                                           // model.py:390
+constexpr float kLogSqrt2Pi = 0.9189385332046727f;                                       // model.py:561
+
+__device__ __forceinline__ float sigmoidf(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// Transformed distribution parameters of one voxel (q and prior), every lane holds a copy.
+struct Dist {
+    float mu_o, mu_d, ls_o, ls_d, cov, inv_o, inv_d, inv_bl;
+};
+struct QExtra {
+    float sd_o, sd_d, dls_o, dls_d, dcov;
+};
+
+// Lanes 0..2 transform q[1], q[3], q[4]; lanes 3..5 the prior's; lanes 6/7 the off-diagonal
+// inverse factor.  One tanhf + two expf per lane instead of 6 + 8 on every lane.
+__device__ __forceinline__ void load_dists(const float* __restrict__ q, const float* __restrict__ prior,
+                                           int lane, Dist& dq, QExtra& ex, Dist& dp) {
+    const int sel = lane % 3;
+    const int idx = sel == 0 ? 1 : (sel == 1 ? 3 : 4);
+    const float* src = (lane < 3 || prior == nullptr) ? q : prior;
+    const float raw = (lane < 6) ? __ldg(src + idx) : 0.f;
+    const float th = tanhf(raw);
+    const float ls = th * 3.0f - 1.0f;                       // transform_std, model.py:288-290
+    const float e = expf(ls);
+    const float ie = expf(ls * -1.0f);                       // model.py:432-433
+    const float th1 = __shfl_sync(kFull, th, 0), th3 = __shfl_sync(kFull, th, 1), th4 = __shfl_sync(kFull, th, 2);
+    dq.mu_o = __ldg(q + 0);
+    dq.mu_d = __ldg(q + 2);
+    dq.ls_o = __shfl_sync(kFull, ls, 0);
+    dq.ls_d = __shfl_sync(kFull, ls, 1);
+    dq.cov = th4 * kExpM2;                                   // transform_offdiag, model.py:292-294
+    dq.inv_o = __shfl_sync(kFull, ie, 0);
+    dq.inv_d = __shfl_sync(kFull, ie, 1);
+    ex.sd_o = __shfl_sync(kFull, e, 0);
+    ex.sd_d = __shfl_sync(kFull, e, 1);
+    ex.dls_o = 3.0f * (1.0f - th1 * th1);
+    ex.dls_d = 3.0f * (1.0f - th3 * th3);
+    ex.dcov = kExpM2 * (1.0f - th4 * th4);
+    const float pth4 = __shfl_sync(kFull, th, 5);
+    dp.ls_o = __shfl_sync(kFull, ls, 3);
+    dp.ls_d = __shfl_sync(kFull, ls, 4);
+    dp.cov = pth4 * kExpM2;
+    dp.inv_o = __shfl_sync(kFull, ie, 3);
+    dp.inv_d = __shfl_sync(kFull, ie, 4);
+    dp.mu_o = prior ? __ldg(prior + 0) : 0.f;
+    dp.mu_d = prior ? __ldg(prior + 2) : 0.f;
+    // inv_bl = exp(-ls_o + -ls_d) * cov * -1   (model.py:434); lanes 6 (q) and 7 (prior)
+    const float a = (lane == 7) ? dp.ls_o : dq.ls_o, b = (lane == 7) ? dp.ls_d : dq.ls_d;
+    const float c = (lane == 7) ? dp.cov : dq.cov;
+    const float bl = (expf(a * -1.0f + b * -1.0f) * c) * -1.0f;
+    dq.inv_bl = __shfl_sync(kFull, bl, 6);
+    dp.inv_bl = __shfl_sync(kFull, bl, 7);
+}
+
+struct Sample {
+    float s_o, s_d, oef, dbv;
+};
+
+__device__ __forceinline__ Sample draw(const Dist& dq, const QExtra& ex, float e0, float e1) {
+    Sample r;
+    const float z_o = dq.mu_o + e0 * ex.sd_o;                                  // model.py:26-27
+    const float z_d = (dq.mu_d + e0 * dq.cov) + e1 * ex.sd_d;                  // model.py:29-31
+    r.s_o = sigmoidf(z_o);
+    r.s_d = sigmoidf(z_d);
+    r.oef = r.s_o * kOefRange + kMinOef;                                       // model.py:302-303
+    r.dbv = r.s_d * kDbvRange + kMinDbv;
+    return r;
+}
+
+// 0.5 * squared whitened residual + log-det part of the logit-MVN NLL and its gradient w.r.t.
+// the (logit-space) observation (model.py:385-390, 423-447).  The Jacobian term (model.py:398)
+// is identical in log q and log p and cancels in log q - log p, so it is not evaluated.
+__device__ __forceinline__ float mvn_nll(const Dist& d, float zh_o, float zh_d, float& g_o, float& g_d) {
+    const float r_o = zh_o - d.mu_o, r_d = zh_d - d.mu_d;
+    const float w_o = r_o * d.inv_o;
+    const float w_d = r_d * d.inv_d + r_o * d.inv_bl;
+    g_o = w_o * d.inv_o + w_d * d.inv_bl;
+    g_d = w_d * d.inv_d;
+    return kLog2Pi + 0.5f * (2.0f * (d.ls_o + d.ls_d)) + 0.5f * (w_o * w_o + w_d * w_d);
+}
+
+// KL(q || prior) of one voxel and its gradient w.r.t. the raw q parameters; warp-cooperative
+// (lanes = samples), every lane returns the same values.
+//   n_samples > 0 : the reference's Monte-Carlo estimator mean_s(log q(z_s) - log p(z_s))
+//                   (mvg_kl_samples, model.py:592-610) with its path-derivative gradient
+//                   (stop_gradient on q inside log q, model.py:596);
+//   n_samples == 0: closed-form KL of the two logit-space Gaussians (textbook formula = the
+//                   expectation of the estimator; NOT the reference's unused mvg_kl, whose trace
+//                   term has a transposed-inverse slip).
+struct KlOut {
+    float kl;
+    float g[5];
+};
+
+__device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const Dist& dp,
+                                         const float* __restrict__ eps_v, uint64_t seed, uint64_t index,
+                                         int n_samples, int lane) {
+    KlOut o;
+    if (n_samples > 0) {
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int sidx = lane; sidx < n_samples; sidx += 32) {
+            float k0, k1;
+            if (eps_v) {
+                const float2 e = __ldg(reinterpret_cast<const float2*>(eps_v) + sidx);
+                k0 = e.x;
+                k1 = e.y;
+            } else {
+                normal_pair(seed, index, kStreamKl + (uint32_t)sidx, k0, k1);
+            }
+            const Sample ks = draw(dq, ex, k0, k1);
+            // backwards_transform + clip + logit (model.py:393-396, 307-316, 10-12)
+            float x_o = (ks.oef - kMinOef) / kOefRange;
+            float x_d = (ks.dbv - kMinDbv) / kDbvRange;
+            x_o = fminf(fmaxf(x_o, 1e-6f), 1.0f - 1e-6f);
+            x_d = fminf(fmaxf(x_d, 1e-6f), 1.0f - 1e-6f);
+            const float zh_o = logf(x_o / (1.0f - x_o));
+            const float zh_d = logf(x_d / (1.0f - x_d));
+            float gq_o, gq_d, gp_o, gp_d;
+            const float nq = mvn_nll(dq, zh_o, zh_d, gq_o, gq_d);
+            const float np = mvn_nll(dp, zh_o, zh_d, gp_o, gp_d);
+            a[5] += np - nq;                                                     // log q - log p (model.py:603)
+            // d zh / d z: logit'(x) * (1/range) * range * sigmoid'(z); the clip passes the gradient (model.py:395)
+            const float dz_o = (ks.s_o * (1.0f - ks.s_o)) / (x_o * (1.0f - x_o));
+            const float dz_d = (ks.s_d * (1.0f - ks.s_d)) / (x_d * (1.0f - x_d));
+            const float hz_o = (gp_o - gq_o) * dz_o, hz_d = (gp_d - gq_d) * dz_d;
+            a[0] += hz_o;
+            a[1] += hz_o * k0;
+            a[2] += hz_d;
+            a[3] += hz_d * k1;
+            a[4] += hz_d * k0;
+        }
+        const float tot = butterfly8(a, lane);
+        const float inv_s = 1.0f / (float)n_samples;
+        o.g[0] = __shfl_sync(kFull, tot, butterfly8_src_lane(0)) * inv_s;
+        o.g[1] = __shfl_sync(kFull, tot, butterfly8_src_lane(1)) * inv_s * ex.sd_o * ex.dls_o;
+        o.g[2] = __shfl_sync(kFull, tot, butterfly8_src_lane(2)) * inv_s;
+        o.g[3] = __shfl_sync(kFull, tot, butterfly8_src_lane(3)) * inv_s * ex.sd_d * ex.dls_d;
+        o.g[4] = __shfl_sync(kFull, tot, butterfly8_src_lane(4)) * inv_s * ex.dcov;
+        o.kl = __shfl_sync(kFull, tot, butterfly8_src_lane(5)) * inv_s;
+    } else {
+        const float m00 = ex.sd_o * dp.inv_o;
+        const float m10 = (dq.cov - dp.cov * m00) * dp.inv_d;
+        const float m11 = ex.sd_d * dp.inv_d;
+        const float d_o = dp.mu_o - dq.mu_o, d_d = dp.mu_d - dq.mu_d;
+        const float w_o = d_o * dp.inv_o;
+        const float w_d = (d_d - dp.cov * w_o) * dp.inv_d;
+        o.kl = 0.5f * ((m00 * m00 + m10 * m10 + m11 * m11) + (w_o * w_o + w_d * w_d) - 2.0f +
+                       2.0f * ((dp.ls_o + dp.ls_d) - (dq.ls_o + dq.ls_d)));
+        o.g[0] = -w_o * dp.inv_o + w_d * dp.cov * dp.inv_o * dp.inv_d;
+        o.g[1] = (m00 * m00 - m10 * dp.cov * m00 * dp.inv_d - 1.0f) * ex.dls_o;
+        o.g[2] = -w_d * dp.inv_d;
+        o.g[3] = (m11 * m11 - 1.0f) * ex.dls_d;
+        o.g[4] = (m10 * dp.inv_d) * ex.dcov;
+    }
+    return o;
+}
+
+// kl_loss alone (model.py:654-665): per-voxel KL map and d kl_map[v] / d q[v,:].
+__global__ void __launch_bounds__(kThreads) k_kl(const float* __restrict__ q, const float* __restrict__ prior,
+                                                 const float* __restrict__ mask, const float* __restrict__ eps_kl,
+                                                 uint64_t seed, uint64_t offset, int n_samples, int64_t n,
+                                                 float* __restrict__ kl_map, float* __restrict__ grad_q) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t v = warp; v < n; v += nwarps) {
+        KlOut ko;
+        ko.kl = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) ko.g[i] = 0.f;
+        if (mask == nullptr || __ldg(mask + v) > 0.f) {                          // model.py:661
+            Dist dq, dp;
+            QExtra ex;
+            load_dists(q + v * 5, prior + v * 5, lane, dq, ex, dp);
+            ko = kl_term(dq, ex, dp, eps_kl ? eps_kl + v * n_samples * 2 : nullptr, seed, offset + (uint64_t)v,
+                         n_samples, lane);
+        }
+        if (lane == 0) kl_map[v] = ko.kl;
+        if (grad_q != nullptr && lane < 5)
+            grad_q[v * 5 + lane] = lane == 0 ? ko.g[0] : lane == 1 ? ko.g[1] : lane == 2 ? ko.g[2]
+                                   : lane == 3 ? ko.g[3] : ko.g[4];
+    }
+}
+
+template <bool HAS_PRIOR>
+__global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ QboldParams P,
+                                                   const float* __restrict__ q, const float* __restrict__ sigma,
+                                                   const float* __restrict__ y, const float* __restrict__ mask,
+                                                   const float* __restrict__ prior, const float* __restrict__ eps,
+                                                   const float* __restrict__ eps_kl, uint64_t seed, uint64_t offset,
+                                                   int kl_samples, float inv_mask_sum, float kl_weight, int64_t n,
+                                                   float* __restrict__ grad_q, float* __restrict__ grad_sigma,
+                                                   float* __restrict__ nll_map, float* __restrict__ kl_map,
+                                                   double* __restrict__ sums) {
+    __shared__ QuadSmem s;
+    if (P.full_model) load_quad_tables(P, s);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = lane < nt;
+    const int my_col = live ? P.col_of_tau[lane] : -1;
+    const float my_tau = live ? P.tau[lane] : 0.f;
+    const float my_b = live ? P.blood_b[lane] : 0.f;
+    const int se = P.se_idx;
+    const bool multi = P.multi_image_normalisation != 0;
+    const bool in_norm = multi ? (lane >= se - 1 && lane <= se + 1) : (lane == se);
+    const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
+    const TauCols tc0 = load_tau_cols(P, 0);
+    const float df = P.student_t_df;
+
+    double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
+    int bad = 0;
+
+    for (int64_t v = warp; v < n; v += nwarps) {
+        const float m = __ldg(mask + v);
+        if (!(m != 0.0f)) {
+            // masked voxel: nll * 0 and where(mask > 0, kl, 0) (model.py:564,661) -> zero loss and gradient
+            if (lane < 5) grad_q[v * 5 + lane] = 0.f;
+            if (live) grad_sigma[v * nt + lane] = 0.f;
+            if (lane == 0) {
+                if (nll_map) nll_map[v] = 0.f;
+                if (kl_map) kl_map[v] = 0.f;
+            }
+            continue;
+        }
+        Dist dq, dp;
+        QExtra ex;
+        load_dists(q + v * 5, HAS_PRIOR ? prior + v * 5 : nullptr, lane, dq, ex, dp);
+
+        // ---- likelihood sample
+        float e0, e1;
+        if (eps) {
+            e0 = __ldg(eps + v * 2);
+            e1 = __ldg(eps + v * 2 + 1);
+        } else {
+            normal_pair(seed, offset + (uint64_t)v, kStreamReparam, e0, e1);
+        }
+        const Sample sm = draw(dq, ex, e0, e1);
+        const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
+        float I = 0.f, D = 0.f;
+        if (P.full_model) {
+            tissue_integrals<true>(P, s, tc0, vp.dw, lane, my_col, I, D);
+            if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
+        }
+        const TauSignal ts = tau_signal<true>(P, vp, my_tau, my_b, I, D);
+
+        // ---- fine_tune_loss_fn (model.py:527-568)
+        const float yv = live ? __ldg(y + v * nt + lane) : 0.f;
+        const float sg = live ? __ldg(sigma + v * nt + lane) : 1.f;
+        const float pred = live ? ts.S : 0.f;
+        const float npd = warp_sum(in_norm ? pred * norm_w : 0.f) + 1e-3f;     // model.py:541-545
+        const float ny = warp_sum(in_norm ? yv * norm_w : 0.f) + 1e-3f;
+        float yn = yv / ny, pn = pred / npd;
+        float dpn = 1.0f;                                                       // d(pn used in residual)/d(pred/npd)
+        if (P.predict_log_data) {                                               // model.py:547-549 (mask > 0 here)
+            dpn = 1.0f / pn;
+            yn = logf(yn);
+            pn = logf(pn);
+        }
+        const float res = yn - pn;
+        const float zq = res / sg;
+        float nll_t, dnll_dres, dnll_dsg;
+        if (df > 0.f) {                                                         // StudentT(df, 0, sigma), model.py:557-559
+            const float t = zq * zq / df;
+            nll_t = -(P.student_t_logc - logf(sg) - 0.5f * (df + 1.0f) * log1pf(t));
+            const float k = (df + 1.0f) / (df + zq * zq);
+            dnll_dres = k * zq / sg;
+            dnll_dsg = 1.0f / sg - k * zq * zq / sg;
+        } else {                                                                // Gaussian, model.py:561
+            nll_t = -(-logf(sg) - kLogSqrt2Pi - 0.5f * (zq * zq));
+            dnll_dres = zq / sg;
+            dnll_dsg = 1.0f / sg - (zq * zq) / sg;
+        }
+        if (!live) nll_t = 0.f;
+        const float nll_v = warp_sum(nll_t);
+        const float scale = m * inv_mask_sum;                                   // model.py:564-566
+        if (live) grad_sigma[v * nt + lane] = dnll_dsg * scale;
+        // residual = yn - pn  =>  d/dpn = -dnll_dres
+        const float g_ratio = live ? (-dnll_dres * scale) * dpn : 0.f;          // w.r.t. pred/npd
+        float g_pred = g_ratio / npd;
+        const float g_npd = -warp_sum(g_ratio * pred) / (npd * npd);
+        if (in_norm) g_pred += g_npd * norm_w;
+        const float go = warp_sum(live ? g_pred * ts.dS_doef : 0.f);
+        const float gd = warp_sum(live ? g_pred * ts.dS_ddbv : 0.f);
+        float gz_o = go * kOefRange * sm.s_o * (1.0f - sm.s_o);
+        float gz_d = gd * kDbvRange * sm.s_d * (1.0f - sm.s_d);
+        // z -> q (model.py:26-31)
+        float g0 = gz_o, g1 = gz_o * e0 * ex.sd_o * ex.dls_o, g2 = gz_d;
+        float g3 = gz_d * e1 * ex.sd_d * ex.dls_d, g4 = gz_d * e0 * ex.dcov;
+
+        // ---- KL(q || prior), where(mask > 0) (model.py:661)
+        float kl_v = 0.f;
+        if (HAS_PRIOR && m > 0.f) {
+            const KlOut ko = kl_term(dq, ex, dp, eps_kl ? eps_kl + v * kl_samples * 2 : nullptr, seed,
+                                     offset + (uint64_t)v, kl_samples, lane);
+            kl_v = ko.kl;
+            const float w = kl_weight * inv_mask_sum;
+            g0 += w * ko.g[0];
+            g1 += w * ko.g[1];
+            g2 += w * ko.g[2];
+            g3 += w * ko.g[3];
+            g4 += w * ko.g[4];
+        }
+
+        if (lane < 5) {
+            const float gv = lane == 0 ? g0 : lane == 1 ? g1 : lane == 2 ? g2 : lane == 3 ? g3 : g4;
+            grad_q[v * 5 + lane] = gv;
+        }
+        if (lane == 0) {
+            const float nm = nll_v * m;
+            if (nll_map) nll_map[v] = nm;
+            if (kl_map) kl_map[v] = kl_v;
+            acc_nll += (double)nm;
+            acc_kl += (double)kl_v;
+            acc_mask += (double)m;
+            if (!isfinite(nm + kl_v)) bad = 1;
+        }
+    }
+    if (lane == 0 && sums != nullptr) {
+        if (acc_mask != 0.0 || bad) {
+            atomicAdd(sums + 0, acc_nll);
+            atomicAdd(sums + 1, acc_kl);
+            atomicAdd(sums + 2, acc_mask);
+            if (bad) atomicAdd(sums + 3, 1.0);
+        }
+    }
+}
+
+// ReparamTrickLayer alone (model.py:21-50): one thread per voxel.
+__global__ void __launch_bounds__(kThreads) k_reparam(const float* __restrict__ q, const float* __restrict__ eps,
+                                                      uint64_t seed, uint64_t offset, int64_t n,
+                                                      float* __restrict__ out) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const float* qv = q + v * 5;
+    float e0, e1;
+    if (eps) {
+        e0 = eps[v * 2];
+        e1 = eps[v * 2 + 1];
+    } else {
+        normal_pair(seed, offset + (uint64_t)v, kStreamReparam, e0, e1);
+    }
+    const float sd_o = expf(tanhf(qv[1]) * 3.0f - 1.0f), sd_d = expf(tanhf(qv[3]) * 3.0f - 1.0f);
+    const float cov = tanhf(qv[4]) * kExpM2;
+    const float z_o = qv[0] + e0 * sd_o;
+    const float z_d = (qv[2] + e0 * cov) + e1 * sd_d;
+    *reinterpret_cast<float2*>(out + v * 2) =
+        make_float2(sigmoidf(z_o) * kOefRange + kMinOef, sigmoidf(z_d) * kDbvRange + kMinDbv);
+}
+
+// calculate_means(include_r2p=True, return_stds=True) (model.py:326-343): one warp per voxel,
+// lanes = samples; two-pass mean / mean((s-mean)^2) exactly as the reference forms them.
+__global__ void __launch_bounds__(kThreads) k_posterior_stats(const __grid_constant__ QboldParams P,
+                                                              const float* __restrict__ q,
+                                                              const float* __restrict__ eps, uint64_t seed,
+                                                              uint64_t offset, int n_samples, int64_t n,
+                                                              float* __restrict__ mean3, float* __restrict__ var3) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    constexpr int kMaxPer = 8;   // up to 256 samples per voxel held in registers
+    const float inv_n = 1.0f / (float)n_samples;
+    for (int64_t v = warp; v < n; v += nwarps) {
+        Dist dq, dp;
+        QExtra ex;
+        load_dists(q + v * 5, nullptr, lane, dq, ex, dp);
+        float so[kMaxPer], sd[kMaxPer], sr[kMaxPer];
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+            const int sidx = lane + 32 * i;
+            so[i] = sd[i] = sr[i] = 0.f;
+            if (sidx < n_samples) {
+                float k0, k1;
+                if (eps) {
+                    const float2 e = __ldg(reinterpret_cast<const float2*>(eps) + (v * n_samples + sidx));
+                    k0 = e.x;
+                    k1 = e.y;
+                } else {
+                    normal_pair(seed, offset + (uint64_t)v, kStreamKl + (uint32_t)sidx, k0, k1);
+                }
+                const Sample ks = draw(dq, ex, k0, k1);
+                so[i] = ks.oef;
+                sd[i] = ks.dbv;
+                sr[i] = (P.dw_k * ks.oef) * ks.dbv;                              // model.py:516-525
+                a[0] += so[i];
+                a[1] += sd[i];
+                a[2] += sr[i];
+            }
+        }
+        float tot = butterfly8(a, lane);
+        const float m_o = __shfl_sync(kFull, tot, butterfly8_src_lane(0)) * inv_n;
+        const float m_d = __shfl_sync(kFull, tot, butterfly8_src_lane(1)) * inv_n;
+        const float m_r = __shfl_sync(kFull, tot, butterfly8_src_lane(2)) * inv_n;
+        float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+            if (lane + 32 * i < n_samples) {
+                b[0] += (so[i] - m_o) * (so[i] - m_o);
+                b[1] += (sd[i] - m_d) * (sd[i] - m_d);
+                b[2] += (sr[i] - m_r) * (sr[i] - m_r);
+            }
+        }
+        tot = butterfly8(b, lane);
+        const float v_o = __shfl_sync(kFull, tot, butterfly8_src_lane(0)) * inv_n;
+        const float v_d = __shfl_sync(kFull, tot, butterfly8_src_lane(1)) * inv_n;
+        const float v_r = __shfl_sync(kFull, tot, butterfly8_src_lane(2)) * inv_n;
+        if (lane < 3) {
+            mean3[v * 3 + lane] = lane == 0 ? m_o : lane == 1 ? m_d : m_r;
+            var3[v * 3 + lane] = lane == 0 ? v_o : lane == 1 ? v_d : v_r;
+        }
+    }
+}
+
+template <typename K>
+static int64_t persistent_grid(K kernel, int64_t n_warp_items) {
+    int bps = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, kThreads, 0) != cudaSuccess || bps < 1) bps = 1;
+    const int64_t want = (n_warp_items + (kThreads / 32) - 1) / (kThreads / 32);
+    int64_t grid = (int64_t)sm_count() * bps;
+    if (want < grid) grid = want;
+    return grid < 1 ? 1 : grid;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const float* sigma, const float* y,
+                                const float* mask, const float* prior, const float* eps, const float* eps_kl,
+                                uint64_t seed, uint64_t offset, int32_t kl_samples, float inv_mask_sum,
+                                float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
+                                float* kl_map, double* sums, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_elbo_fused: bad params block");
+    if (n < 0 || kl_samples < 0) return fail(QBOLD_EINVAL, "qbold_elbo_fused: negative size");
+    if (n == 0) return QBOLD_OK;
+    if (!q || !sigma || !y || !mask || !grad_q || !grad_sigma)
+        return fail(QBOLD_EINVAL, "qbold_elbo_fused: null pointer");
+    if (p->n_tau > 32) return fail(QBOLD_EINVAL, "qbold_elbo_fused: n_tau > 32");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (prior) {
+        static int64_t grid_cache = 0;
+        const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo<true>, INT64_MAX / 64));
+        const int64_t want = (n + 7) / 8;
+        k_elbo<true><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(
+            *p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, kl_weight, n, grad_q,
+            grad_sigma, nll_map, kl_map, sums);
+    } else {
+        static int64_t grid_cache = 0;
+        const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo<false>, INT64_MAX / 64));
+        const int64_t want = (n + 7) / 8;
+        k_elbo<false><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(
+            *p, q, sigma, y, mask, nullptr, eps, nullptr, seed, offset, 0, inv_mask_sum, kl_weight, n, grad_q,
+            grad_sigma, nll_map, kl_map, sums);
+    }
+    return after_launch("k_elbo");
+}
+
+extern "C" int qbold_kl(const float* q, const float* prior, const float* mask, const float* eps_kl, uint64_t seed,
+                        uint64_t offset, int32_t n_samples, int64_t n, float* kl_map, float* grad_q, void* stream) {
+    if (n < 0 || n_samples < 0 || (n > 0 && (!q || !prior || !kl_map)))
+        return fail(QBOLD_EINVAL, "qbold_kl: bad argument");
+    if (n == 0) return QBOLD_OK;
+    static int64_t grid_cache = 0;
+    const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_kl, INT64_MAX / 64));
+    const int64_t want = (n + 7) / 8;
+    k_kl<<<(unsigned)(want < grid ? want : grid), kThreads, 0, (cudaStream_t)stream>>>(q, prior, mask, eps_kl, seed,
+                                                                                      offset, n_samples, n, kl_map,
+                                                                                      grad_q);
+    return after_launch("k_kl");
+}
+
+extern "C" int qbold_reparam_sample(const float* q, const float* eps, uint64_t seed, uint64_t offset, int64_t n,
+                                    float* oef_dbv, void* stream) {
+    if (n < 0 || (n > 0 && (!q || !oef_dbv))) return fail(QBOLD_EINVAL, "qbold_reparam_sample: bad argument");
+    if (n == 0) return QBOLD_OK;
+    k_reparam<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(q, eps, seed, offset,
+                                                                                                n, oef_dbv);
+    return after_launch("k_reparam");
+}
+
+extern "C" int qbold_posterior_stats(const QboldParams* p, const float* q, const float* eps, uint64_t seed,
+                                     uint64_t offset, int32_t n_samples, int64_t n, float* mean3, float* var3,
+                                     void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_posterior_stats: bad params block");
+    if (n_samples < 1 || n_samples > 256) return fail(QBOLD_EINVAL, "qbold_posterior_stats: n_samples must be in [1,256]");
+    if (n < 0 || (n > 0 && (!q || !mean3 || !var3))) return fail(QBOLD_EINVAL, "qbold_posterior_stats: null pointer");
+    if (n == 0) return QBOLD_OK;
+    static int64_t grid_cache = 0;
+    const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_posterior_stats, INT64_MAX / 64));
+    const int64_t want = (n + 7) / 8;
+    k_posterior_stats<<<(unsigned)(want < grid ? want : grid), kThreads, 0, (cudaStream_t)stream>>>(
+        *p, q, eps, seed, offset, n_samples, n, mean3, var3);
+    return after_launch("k_posterior_stats");
+}

@@ -1,0 +1,97 @@
+// K1 / K1b: forward signal model and forward + vector-Jacobian product.
+// Replaces SignalGenerationLayer.call (reference signals.py:55-114) and what
+// tape.gradient does through it (bessel_j0' = -bessel_j1, node 0 value-dead / gradient-live).
+#include "qbold_core.cuh"
+#include "launch.h"
+
+namespace qb {
+
+// One warp per voxel (grid-stride).  BWD: also g_oef_dbv[n,2]; HCT: oef_dbv rows are (OEF,DBV,Hct).
+template <bool BWD, bool HCT>
+__global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ QboldParams P,
+                                                      const float* __restrict__ oef_dbv,
+                                                      const float* __restrict__ g_signal,
+                                                      float* __restrict__ signal,
+                                                      float* __restrict__ g_oef_dbv, int64_t n) {
+    __shared__ QuadSmem s;
+    if (P.full_model) load_quad_tables(P, s);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = lane < nt;
+    const int my_col = live ? P.col_of_tau[lane] : -1;
+    const float my_tau = live ? P.tau[lane] : 0.f;
+    const float my_b = live ? P.blood_b[lane] : 0.f;
+    constexpr int W = HCT ? 3 : 2;
+    const TauCols tc0 = load_tau_cols(P, 0);
+
+    for (int64_t v = warp; v < n; v += nwarps) {
+        const float oef = __ldg(oef_dbv + v * W);
+        const float dbv = __ldg(oef_dbv + v * W + 1);
+        const float hct = HCT ? __ldg(oef_dbv + v * W + 2) : P.hct;
+        float gs = 1.0f;
+        if (BWD && g_signal != nullptr && live) gs = __ldg(g_signal + v * nt + lane);
+        const VoxelPhys vp = voxel_phys<HCT>(P, oef, dbv, hct);
+
+        float I = 0.f, D = 0.f;
+        if (P.full_model) {
+            tissue_integrals<BWD>(P, s, tc0, vp.dw, lane, my_col, I, D);
+            if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
+        }
+        const TauSignal ts = tau_signal<BWD>(P, vp, my_tau, my_b, I, D);
+        if (live && signal != nullptr) signal[v * nt + lane] = ts.S;
+        if (BWD) {
+            float go = live ? gs * ts.dS_doef : 0.f;
+            float gd = live ? gs * ts.dS_ddbv : 0.f;
+            go = warp_sum(go);
+            gd = warp_sum(gd);
+            if (lane == 0) *reinterpret_cast<float2*>(g_oef_dbv + v * 2) = make_float2(go, gd);
+        }
+    }
+}
+
+template <bool BWD, bool HCT>
+static int launch_forward(const QboldParams* p, const float* oef_dbv, const float* g, float* signal,
+                          float* grad, int64_t n, cudaStream_t st) {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_forward<BWD, HCT>, kThreads, 0) !=
+                cudaSuccess || blocks_per_sm < 1)
+            blocks_per_sm = 1;
+    }
+    const int64_t want = (n + (kThreads / 32) - 1) / (kThreads / 32);
+    int64_t grid = (int64_t)sm_count() * blocks_per_sm;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    k_forward<BWD, HCT><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n);
+    return after_launch("k_forward");
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" int qbold_forward(const QboldParams* p, const float* oef_dbv, int32_t width, int64_t n,
+                             float* signal, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_forward: bad params block");
+    if (width != 2 && width != 3)
+        return fail(QBOLD_EINVAL, "Input should have 2 (OEF, DBV) or 3 (OEF, DBV, hct) elements in last dimension");
+    if (n < 0 || (n > 0 && (!oef_dbv || !signal))) return fail(QBOLD_EINVAL, "qbold_forward: null pointer");
+    if (n == 0) return QBOLD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    return width == 3 ? launch_forward<false, true>(p, oef_dbv, nullptr, signal, nullptr, n, st)
+                      : launch_forward<false, false>(p, oef_dbv, nullptr, signal, nullptr, n, st);
+}
+
+extern "C" int qbold_forward_backward(const QboldParams* p, const float* oef_dbv, const float* g_signal,
+                                      int64_t n, float* signal, float* g_oef_dbv, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION)
+        return fail(QBOLD_EINVAL, "qbold_forward_backward: bad params block");
+    if (n < 0 || (n > 0 && (!oef_dbv || !g_oef_dbv)))
+        return fail(QBOLD_EINVAL, "qbold_forward_backward: null pointer");
+    if (n == 0) return QBOLD_OK;
+    return launch_forward<true, false>(p, oef_dbv, g_signal, signal, g_oef_dbv, n, (cudaStream_t)stream);
+}

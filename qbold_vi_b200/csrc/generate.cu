@@ -1,0 +1,211 @@
+// K3: streaming synthetic-data path.  Replaces the body of create_synthetic_dataset
+// (reference signals.py:270-299) and the noise model of SignalGenerationLayer.call
+// (signals.py:116-128) with three device passes per chunk:
+//   k_generate     meshgrid('ij') + shuffle + forward model + labels (OEF, DBV, R2')
+//   k_column_sum   the batch statistic mean_over_chunk(signal) of signals.py:126
+//   k_add_noise    snr ~ U(50,120) * norm_snr, signal += N(0,1) * mean/snr   (HBM-bound pass)
+#include "qbold_core.cuh"
+#include "launch.h"
+#include "rng.cuh"
+
+namespace qb {
+
+// Keyed bijection of [0, n): 4-round balanced Feistel network on 2*half_bits bits with
+// cycle walking.  Stands in for tf.random.shuffle (signals.py:279) without materialising a
+// permutation array in HBM (1e9-voxel generation, BASELINE config 5).  oracle/philox.py
+// implements the identical function.
+__host__ __device__ __forceinline__ uint32_t feistel_round(uint32_t r, uint32_t key) {
+    uint32_t h = r * 0x9E3779B1u + key;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    h ^= h >> 13;
+    h *= 0xC2B2AE3Du;
+    h ^= h >> 16;
+    return h;
+}
+
+__host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t i, uint64_t n, int half_bits, uint64_t seed) {
+    const uint32_t mask = (half_bits >= 32) ? 0xffffffffu : ((1u << half_bits) - 1u);
+    uint64_t x = i;
+    do {
+        uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t key = (uint32_t)(seed >> (16 * (k & 1))) + 0x7F4A7C15u * (uint32_t)(k + 1) +
+                                 (uint32_t)(seed >> 32);
+            const uint32_t t = l ^ (feistel_round(r, key) & mask);
+            l = r;
+            r = t;
+        }
+        x = ((uint64_t)l << half_bits) | r;
+    } while (x >= n);
+    return x;
+}
+
+__global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ QboldParams P,
+                                                       const float* __restrict__ oefs, int64_t n_oef,
+                                                       const float* __restrict__ dbvs, int64_t n_dbv,
+                                                       const int64_t* __restrict__ perm, uint64_t seed,
+                                                       int half_bits, int64_t first, int64_t count,
+                                                       float* __restrict__ x, float* __restrict__ y3) {
+    __shared__ QuadSmem s;
+    if (P.full_model) load_quad_tables(P, s);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = lane < nt;
+    const int my_col = live ? P.col_of_tau[lane] : -1;
+    const float my_tau = live ? P.tau[lane] : 0.f;
+    const float my_b = live ? P.blood_b[lane] : 0.f;
+    const TauCols tc0 = load_tau_cols(P, 0);
+    const uint64_t total = (uint64_t)n_oef * (uint64_t)n_dbv;
+
+    for (int64_t v = warp; v < count; v += nwarps) {
+        const uint64_t row = (uint64_t)(first + v);
+        const uint64_t idx = perm ? (uint64_t)__ldg(perm + row) : feistel_permute(row, total, half_bits, seed);
+        const float oef = __ldg(oefs + idx / (uint64_t)n_dbv);            // meshgrid(indexing='ij'), signals.py:270
+        const float dbv = __ldg(dbvs + idx % (uint64_t)n_dbv);
+        if (y3 != nullptr && lane < 3) {
+            const float r2p = (P.dw_k * oef) * dbv;                        // signals.py:296
+            y3[v * 3 + lane] = lane == 0 ? oef : (lane == 1 ? dbv : r2p);
+        }
+        if (x == nullptr) continue;
+        const VoxelPhys vp = voxel_phys<false>(P, oef, dbv, P.hct);
+        float I = 0.f, D = 0.f;
+        if (P.full_model) {
+            tissue_integrals<false>(P, s, tc0, vp.dw, lane, my_col, I, D);
+            if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
+        }
+        const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, D);
+        if (live) x[v * nt + lane] = ts.S;
+    }
+}
+
+// Column sums of a [n, nt] block; one warp reads one 4*nt-byte row per step.
+__global__ void __launch_bounds__(kThreads) k_column_sum(const float* __restrict__ sig, int64_t n, int nt,
+                                                         double* __restrict__ sums) {
+    __shared__ float part[kThreads / 32][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + w;
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    float acc = 0.f, comp = 0.f;   // Kahan: rows per warp can reach 1e5+
+    if (lane < nt) {
+        for (int64_t r = warp; r < n; r += nwarps) {
+            const float yv = __ldg(sig + r * nt + lane) - comp;
+            const float t = acc + yv;
+            comp = (t - acc) - yv;
+            acc = t;
+        }
+    }
+    part[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && lane < nt) {
+        double tot = 0.0;
+        for (int k = 0; k < kThreads / 32; ++k) tot += (double)part[k][lane];
+        atomicAdd(sums + lane, tot);
+    }
+}
+
+__global__ void k_finish_mean(const double* __restrict__ sums, int64_t n, int nt, float* __restrict__ mean) {
+    const int t = threadIdx.x;
+    if (t < nt) mean[t] = (float)(sums[t] / (double)n);
+}
+
+// signals.py:116-128, one thread per voxel (rows stay L1-resident across the tau loop).
+__global__ void __launch_bounds__(kThreads) k_add_noise(const __grid_constant__ QboldParams P, float* __restrict__ sig,
+                                                        int64_t n, const float* __restrict__ mean,
+                                                        const float* __restrict__ snr_u01,
+                                                        const float* __restrict__ eps, uint64_t seed, uint64_t offset) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int nt = P.n_tau;
+    float u;
+    if (snr_u01) {
+        u = snr_u01[v];
+    } else {
+        const U4 r = philox4x32_10((uint32_t)(offset + v), (uint32_t)((offset + v) >> 32), kStreamSnr, 0u,
+                                   (uint32_t)seed, (uint32_t)(seed >> 32));
+        u = u01(r.x);
+    }
+    const float snr0 = u * (120.0f - 50.0f) + 50.0f;                       // tf.random.uniform(.., 50, 120), :124
+    for (int t = 0; t < nt; t += 2) {
+        float n0, n1;
+        if (eps) {
+            n0 = eps[v * nt + t];
+            n1 = (t + 1 < nt) ? eps[v * nt + t + 1] : 0.f;
+        } else {
+            normal_pair(seed, offset + (uint64_t)v, kStreamNoise + (uint32_t)(t >> 1), n0, n1);
+        }
+        const float sd0 = __ldg(mean + t) / (snr0 * P.norm_snr[t]);        // :124-126
+        sig[v * nt + t] = sig[v * nt + t] + n0 * sd0;                      // :128
+        if (t + 1 < nt) {
+            const float sd1 = __ldg(mean + t + 1) / (snr0 * P.norm_snr[t + 1]);
+            sig[v * nt + t + 1] = sig[v * nt + t + 1] + n1 * sd1;
+        }
+    }
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" int qbold_generate(const QboldParams* p, const float* oefs, int64_t n_oef, const float* dbvs,
+                              int64_t n_dbv, const int64_t* perm, uint64_t seed, int64_t first, int64_t count,
+                              float* x, float* y3, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_generate: bad params block");
+    if (!oefs || !dbvs || n_oef < 1 || n_dbv < 1) return fail(QBOLD_EINVAL, "qbold_generate: empty marginals");
+    if (first < 0 || count < 0 || first + count > n_oef * n_dbv)
+        return fail(QBOLD_EINVAL, "qbold_generate: rows [%lld,%lld) outside the %lld x %lld meshgrid",
+                    (long long)first, (long long)(first + count), (long long)n_oef, (long long)n_dbv);
+    if (count == 0) return QBOLD_OK;
+    if (!x && !y3) return fail(QBOLD_EINVAL, "qbold_generate: no output requested");
+    const uint64_t total = (uint64_t)n_oef * (uint64_t)n_dbv;
+    int bits = 1;
+    while (bits < 64 && (1ull << bits) < total) ++bits;
+    const int half_bits = (bits + 1) / 2;
+    static int bps = 0;
+    if (bps == 0 &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate, kThreads, 0) != cudaSuccess || bps < 1))
+        bps = 1;
+    int64_t grid = (int64_t)sm_count() * bps;
+    const int64_t want = (count + 7) / 8;
+    if (want < grid) grid = want;
+    k_generate<<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed,
+                                                                     half_bits, first, count, x, y3);
+    return after_launch("k_generate");
+}
+
+extern "C" int qbold_column_mean(const float* signal, int64_t n, int32_t n_tau, float* mean, double* scratch,
+                                 void* stream) {
+    if (!signal || !mean || !scratch || n < 1 || n_tau < 1 || n_tau > 32)
+        return fail(QBOLD_EINVAL, "qbold_column_mean: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cuda_check(cudaMemsetAsync(scratch, 0, sizeof(double) * n_tau, st), "cudaMemsetAsync");
+    if (rc) return rc;
+    int64_t grid = (int64_t)sm_count() * 4;
+    const int64_t want = (n + 7) / 8;
+    if (want < grid) grid = want;
+    k_column_sum<<<(unsigned)grid, kThreads, 0, st>>>(signal, n, n_tau, scratch);
+    rc = after_launch("k_column_sum");
+    if (rc) return rc;
+    k_finish_mean<<<1, 32, 0, st>>>(scratch, n, n_tau, mean);
+    return after_launch("k_finish_mean");
+}
+
+extern "C" int qbold_add_noise(const QboldParams* p, float* signal, int64_t n, const float* mean,
+                               const float* snr_u01, const float* eps, uint64_t seed, uint64_t offset,
+                               void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_add_noise: bad params block");
+    if (p->norm_snr[0] == 0.0f)
+        return fail(QBOLD_EUNSUPPORTED,
+                    "norm_snr is only defined for 11 or 24 taus (reference signals.py:117-121), got %d", p->n_tau);
+    if ((snr_u01 == nullptr) != (eps == nullptr))
+        return fail(QBOLD_EINVAL, "qbold_add_noise: pass both snr_u01 and eps, or neither");
+    if (n < 0 || (n > 0 && (!signal || !mean))) return fail(QBOLD_EINVAL, "qbold_add_noise: null pointer");
+    if (n == 0) return QBOLD_OK;
+    k_add_noise<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        *p, signal, n, mean, snr_u01, eps, seed, offset);
+    return after_launch("k_add_noise");
+}

@@ -1,0 +1,63 @@
+// Counter-based RNG shared by the kernels and (bit-for-bit on the integer side) by
+// oracle/philox.py: Philox4x32-10 keyed by the 64-bit seed, counter = (index_lo, index_hi,
+// stream, 0) where index is the GLOBAL voxel index, so results do not depend on how voxels
+// are sharded over GPUs or chunked over launches.
+//
+// TensorFlow's own Philox streams (tf.random.*, seeded by tf.random.set_seed(1),
+// reference train.py:458) cannot be reproduced offline; "identical seeds" is realised as this
+// documented scheme plus explicit-draw entry points.
+#pragma once
+#include <stdint.h>
+
+namespace qb {
+
+// stream ids
+constexpr uint32_t kStreamReparam = 0;        // ReparamTrickLayer draw of the likelihood term
+constexpr uint32_t kStreamKl = 0x100;         // + sample index (KL / posterior samples)
+constexpr uint32_t kStreamSnr = 0x10000;      // noise model: per-voxel SNR
+constexpr uint32_t kStreamNoise = 0x10001;    // + pair index: noise normals
+
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += W0;
+        k1 += W1;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+// 24-bit uniform in (0, 1): (top 24 bits + 0.5) * 2^-24 -- never 0 or 1.
+__host__ __device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-08f; }
+
+#ifdef __CUDACC__
+// Two independent N(0,1) draws from two words (Box-Muller, accurate logf/sincospif).
+__device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {
+    const float rad = sqrtf(-2.0f * logf(u01(r0)));
+    float s, c;
+    sincospif(2.0f * u01(r1), &s, &c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+
+__device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t index, uint32_t stream, float& n0, float& n1) {
+    const U4 r = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, 0u, (uint32_t)seed,
+                               (uint32_t)(seed >> 32));
+    box_muller(r.x, r.y, n0, n1);
+}
+#endif
+
+}  // namespace qb

@@ -1,0 +1,371 @@
+"""Host-side mirror of the sampling / likelihood / KL slice of the reference's ``model.py``.
+
+Reference names and signatures are kept (``ReparamTrickLayer``, ``EncoderTrainer`` with
+``transform_std``, ``forward_transform``, ``fine_tune_loss_fn(y_true, y_pred[, return_mean])``,
+``kl_loss(true, predicted[, return_mean, no_samples])``, ``calculate_means`` ...), tensors are torch
+CUDA tensors in the reference's channels-last layout ``[B, X, Y, Z, C]``.
+
+The training hot path is ``EncoderTrainer.fused_elbo`` -- one sm_100a kernel for
+sample -> forward model -> NLL (+ MC KL) -> backward (what ``build_fine_tuner`` + the two Keras loss
+closures of train.py:315-320 + autodiff do in the reference).  The stand-alone loss callables exist
+for drop-in parity of the API; small element-wise helpers (transforms, TV smoothness, the
+pre-training NLL) are torch ops and run wherever their tensors live.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import QboldLikelihood, QboldParams, check, dptr, stream_ptr
+from .signals import SignalGenerationLayer
+
+
+def logit(signal):
+    return torch.log(signal / (1.0 - signal))                                  # model.py:10-12
+
+
+def _next_seed(obj):
+    obj._calls += 1
+    return (obj._seed + 0x9E3779B97F4A7C15 * obj._calls) & 0xFFFFFFFFFFFFFFFF
+
+
+class _ReparamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, eps):
+        n = q.shape[0]
+        out = torch.empty((n, 2), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            check(_lib.lib().qbold_reparam_sample(dptr(q), dptr(eps), 0, 0, n, dptr(out), stream_ptr(q.device)))
+        ctx.save_for_backward(q, eps, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, eps, out = ctx.saved_tensors
+        th1, th3, th4 = torch.tanh(q[:, 1]), torch.tanh(q[:, 3]), torch.tanh(q[:, 4])
+        sd_o, sd_d = torch.exp(th1 * 3.0 - 1.0), torch.exp(th3 * 3.0 - 1.0)
+        s_o, s_d = (out[:, 0] - 0.04) / 0.8, (out[:, 1] - 0.001) / 0.2
+        gz_o = g[:, 0] * 0.8 * s_o * (1.0 - s_o)
+        gz_d = g[:, 1] * 0.2 * s_d * (1.0 - s_d)
+        gq = torch.stack([gz_o, gz_o * eps[:, 0] * sd_o * 3.0 * (1.0 - th1 * th1), gz_d,
+                          gz_d * eps[:, 1] * sd_d * 3.0 * (1.0 - th3 * th3),
+                          gz_d * eps[:, 0] * math.exp(-2.0) * (1.0 - th4 * th4)], -1)
+        return gq, None
+
+
+class ReparamTrickLayer:
+    """Draw samples of OEF and DBV from the predicted distributions (model.py:15-50)."""
+
+    def __init__(self, encoder_trainer):
+        self._encoder_trainer = encoder_trainer
+
+    def __call__(self, inputs, *args, **kwargs):
+        return self.call(inputs, *args, **kwargs)
+
+    def call(self, inputs, *args, eps=None, **kwargs):
+        input, mask = inputs
+        if not self._encoder_trainer._use_mvg:
+            raise NotImplementedError('diagonal (use_mvg=False) posterior: SURVEY.md 8a row a14, second priority')
+        lead = tuple(input.shape[:-1])
+        q = input.reshape(-1, 5).float().contiguous()
+        if eps is None:
+            eps = torch.randn((q.shape[0], 2), dtype=torch.float32, device=q.device)
+        eps = eps.reshape(-1, 2).float().contiguous()
+        return _ReparamFn.apply(q, eps).reshape(lead + (2,))
+
+
+class _KlFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, prior, mask, eps_kl, seed, n_samples):
+        n = pred.shape[0]
+        kl_map = torch.empty(n, dtype=torch.float32, device=pred.device)
+        grad = torch.empty((n, 5), dtype=torch.float32, device=pred.device)
+        with torch.cuda.device(pred.device):
+            check(_lib.lib().qbold_kl(dptr(pred), dptr(prior), dptr(mask, allow_none=True),
+                                      dptr(eps_kl, allow_none=True), seed, 0, n_samples, n, dptr(kl_map), dptr(grad),
+                                      stream_ptr(pred.device)))
+        ctx.save_for_backward(grad)
+        return kl_map
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g[:, None], None, None, None, None, None
+
+
+class _FusedElboFn(torch.autograd.Function):
+    """loss = nll + kl_weight * kl of one (local) batch; gradients come from the same launch."""
+
+    @staticmethod
+    def forward(ctx, q, sigma, trainer, layer, y, mask, prior, eps, eps_kl, seed, kl_samples, inv_mask_sum,
+                kl_weight, want_maps):
+        n = q.shape[0]
+        dev = q.device
+        nt = layer.n_tau
+        grad_q = torch.empty((n, 5), dtype=torch.float32, device=dev)
+        grad_sigma = torch.empty((n, nt), dtype=torch.float32, device=dev)
+        sums = torch.zeros(4, dtype=torch.float64, device=dev)
+        nll_map = torch.empty(n, dtype=torch.float32, device=dev) if want_maps else None
+        kl_map = torch.empty(n, dtype=torch.float32, device=dev) if want_maps else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().qbold_elbo_fused(
+                C.byref(trainer._params_for(layer)), dptr(q), dptr(sigma), dptr(y), dptr(mask),
+                dptr(prior, allow_none=True), dptr(eps, allow_none=True), dptr(eps_kl, allow_none=True), seed, 0,
+                kl_samples, inv_mask_sum, kl_weight, n, dptr(grad_q), dptr(grad_sigma),
+                dptr(nll_map, allow_none=True), dptr(kl_map, allow_none=True), dptr(sums, torch.float64),
+                stream_ptr(dev)))
+        ctx.save_for_backward(grad_q, grad_sigma)
+        s = sums.float()
+        nll, kl = s[0] * inv_mask_sum, s[1] * inv_mask_sum
+        ctx.mark_non_differentiable(sums)
+        if want_maps:
+            ctx.mark_non_differentiable(nll_map, kl_map)
+            return nll + kl_weight * kl, sums, nll_map, kl_map
+        return nll + kl_weight * kl, sums
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        grad_q, grad_sigma = ctx.saved_tensors
+        return (grad_q * g, grad_sigma * g) + (None,) * 12
+
+
+class EncoderTrainer:
+    """Reference model.py:53-95 (constructor signature preserved)."""
+
+    def __init__(self, system_params, no_intermediate_layers=1, no_units=10, use_layer_norm=False, dropout_rate=0.0,
+                 activation_type='gelu', student_t_df=None, initial_im_sigma=0.08, multi_image_normalisation=True,
+                 channelwise_gating=False, infer_inv_gamma=False, use_mvg=True, use_population_prior=True,
+                 mog_components=1, no_samples=1, heteroscedastic_noise=True, predict_log_data=True, seed=None):
+        self._no_intermediate_layers = no_intermediate_layers
+        self._no_units = no_units
+        self._use_layer_norm = use_layer_norm
+        self._dropout_rate = dropout_rate
+        self._activation_type = activation_type
+        self._student_t_df = student_t_df
+        self._initial_im_sigma = initial_im_sigma
+        self._multi_image_normalisation = multi_image_normalisation
+        self._system_params = system_params
+        self._channelwise_gating = channelwise_gating
+        self._infer_inv_gamma = infer_inv_gamma
+        self._use_mvg = use_mvg
+        self._use_population_prior = use_population_prior
+        self._mog_components = mog_components
+        self._no_samples = no_samples
+        self._oef_range = 0.8
+        self._min_oef = 0.04
+        self._dbv_range = 0.2
+        self._min_dbv = 0.001
+        self._heteroscedastic_noise = heteroscedastic_noise
+        self._predict_log_data = predict_log_data
+        self._se_idx = int(abs(float(system_params['tau_start']) / float(system_params['tau_step'])))   # model.py:95
+        self._seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self._calls = 0
+        self._param_cache = {}
+
+    # ------------------------------------------------------------------ transforms (model.py:288-316)
+    def transform_std(self, pred_stds):
+        return (torch.tanh(pred_stds) * 3.0) - 1.0
+
+    def transform_offdiag(self, pred_offdiag):
+        return torch.tanh(pred_offdiag) * np.exp(-2.0)
+
+    def inv_transform_std(self, std):
+        return torch.atanh((std + 1.0) / 3.0)
+
+    def forward_transform(self, logits):
+        oef, dbv = torch.split(logits, 1, -1)
+        oef = (torch.sigmoid(oef) * self._oef_range) + self._min_oef
+        dbv = (torch.sigmoid(dbv) * self._dbv_range) + self._min_dbv
+        return torch.cat([oef, dbv], -1)
+
+    def backwards_transform(self, signal, include_logit):
+        oef, dbv = torch.split(signal, 1, -1)
+        oef = (oef - self._min_oef) / self._oef_range
+        dbv = (dbv - self._min_dbv) / self._dbv_range
+        if include_logit:
+            oef, dbv = logit(oef), logit(dbv)
+        return torch.cat([oef, dbv], -1)
+
+    def calculate_dw(self, oef):
+        sp = self._system_params
+        return SignalGenerationLayer.calculate_dw_static(oef, float(sp['hct']), float(sp['gamma']), float(sp['b0']),
+                                                         float(sp['dchi']))
+
+    def calculate_r2p(self, oef, dbv):
+        return self.calculate_dw(oef) * dbv
+
+    # ------------------------------------------------------------------ parameter block with likelihood options
+    def _params_for(self, layer):
+        key = id(layer)
+        if key not in self._param_cache:
+            p = QboldParams()
+            C.memmove(C.byref(p), C.byref(layer.params), C.sizeof(QboldParams))
+            df = self._student_t_df
+            lik = QboldLikelihood(self._se_idx, int(bool(self._multi_image_normalisation)),
+                                  int(bool(self._predict_log_data)), 0, float(df) if df is not None else 0.0)
+            check(_lib.lib().qbold_params_set_likelihood(C.byref(p), C.byref(lik)))
+            self._param_cache[key] = p
+        return self._param_cache[key]
+
+    # ------------------------------------------------------------------ sampling helpers (model.py:318-343)
+    def create_samples(self, predicted_params, mask, no_samples):
+        rpl = ReparamTrickLayer(self)
+        return torch.stack([rpl([predicted_params, mask]) for _ in range(no_samples)], -1)
+
+    def calculate_means(self, predicted_params, mask, include_r2p=False, return_stds=False, no_samples=20, eps=None,
+                        signal_layer=None):
+        """Posterior means (and the reference's 'stds', which are variances: model.py:331,337)."""
+        lead = tuple(predicted_params.shape[:-1])
+        q = predicted_params.reshape(-1, 5).float().contiguous()
+        n = q.shape[0]
+        mean3 = torch.empty((n, 3), dtype=torch.float32, device=q.device)
+        var3 = torch.empty((n, 3), dtype=torch.float32, device=q.device)
+        layer = signal_layer or self._default_layer()
+        e = None if eps is None else eps.reshape(n, no_samples, 2).float().contiguous()
+        with torch.cuda.device(q.device):
+            check(_lib.lib().qbold_posterior_stats(C.byref(layer.params), dptr(q), dptr(e, allow_none=True),
+                                                   _next_seed(self), 0, no_samples, n, dptr(mean3), dptr(var3),
+                                                   stream_ptr(q.device)))
+        k = 3 if include_r2p else 2
+        means = mean3[:, :k].reshape(lead + (k,))
+        if return_stds:
+            return means, var3[:, :k].reshape(lead + (k,))
+        return means
+
+    def _default_layer(self):
+        if not hasattr(self, '_layer'):
+            sp = dict(self._system_params)
+            sp['simulate_noise'] = 'False'
+            self._layer = SignalGenerationLayer(sp, True, True)
+        return self._layer
+
+    # ------------------------------------------------------------------ likelihood (model.py:527-568)
+    def fine_tune_loss_fn(self, y_true, y_pred, return_mean=True):
+        y_true = torch.cat([y_true for _ in range(self._no_samples)], 0)
+        mask = y_true[..., -1:]
+        no_images = y_true.shape[-1] - 1
+        if self._heteroscedastic_noise:
+            y_pred, sigma = torch.split(y_pred, y_pred.shape[-1] // 2, -1)
+            sigma = sigma.reshape(-1, no_images)
+        else:
+            sigma = torch.mean(y_pred[..., -1:])
+            y_pred = y_pred[..., :-1]
+        se = self._se_idx
+        if self._multi_image_normalisation:
+            y_true = y_true / (torch.mean(y_true[..., se - 1:se + 2], -1, keepdim=True) + 1e-3)
+            y_pred = y_pred / (torch.mean(y_pred[..., se - 1:se + 2], -1, keepdim=True) + 1e-3)
+        else:
+            y_true = y_true / (torch.mean(y_true[..., se:se + 1], -1, keepdim=True) + 1e-3)
+            y_pred = y_pred / (torch.mean(y_pred[..., se:se + 1], -1, keepdim=True) + 1e-3)
+        if self._predict_log_data:
+            y_true = torch.where(mask > 0, torch.log(y_true), torch.zeros_like(y_true))
+            y_pred = torch.where(mask > 0, torch.log(y_pred), torch.zeros_like(y_pred))
+        residual = (y_true[..., :-1] - y_pred).reshape(-1, no_images)
+        mask = mask.reshape(-1, 1)
+        if self._student_t_df is not None and self._student_t_df < 50:
+            df = float(self._student_t_df)
+            c = math.lgamma(0.5 * (df + 1.0)) - math.lgamma(0.5 * df) - 0.5 * math.log(df * math.pi)
+            zq = residual / sigma
+            nll = -(c - torch.log(sigma) - 0.5 * (df + 1.0) * torch.log1p(zq * zq / df))
+        else:
+            nll = -(-torch.log(sigma) - np.log(np.sqrt(2.0 * np.pi)) - 0.5 * torch.square(residual / sigma))
+        nll = torch.sum(nll, -1, keepdim=True) * mask
+        if return_mean:
+            return torch.sum(nll) / torch.sum(mask)
+        return nll
+
+    # ------------------------------------------------------------------ KL (model.py:592-665)
+    def mvg_kl_samples(self, prior, pred, no_samples=50, eps=None):
+        prior_dist, mask = prior[..., :5], prior[..., 5:6]
+        lead = tuple(pred.shape[:-1])
+        kl = _KlFn.apply(pred.reshape(-1, 5).float().contiguous(), prior_dist.reshape(-1, 5).float().contiguous(),
+                         None, None if eps is None else eps.reshape(-1, no_samples, 2).float().contiguous(),
+                         _next_seed(self), no_samples)
+        return kl.reshape(lead + (1,))
+
+    def kl_loss(self, true, predicted, return_mean=True, no_samples=70, eps=None):
+        """KL(q || prior) by the reference's 70-sample MC estimator; ``no_samples=0`` selects the closed form."""
+        if not self._use_mvg:
+            raise NotImplementedError('diagonal / MoG KL variants: SURVEY.md 8a row a14, second priority')
+        true = torch.cat([true for _ in range(self._no_samples)], 0)
+        prior_dist, mask = true[..., :5], true[..., 5:6]
+        lead = tuple(predicted.shape[:-1])
+        m = mask.reshape(-1).float().contiguous()
+        kl = _KlFn.apply(predicted.reshape(-1, 5).float().contiguous(),
+                         prior_dist.reshape(-1, 5).float().contiguous(), m,
+                         None if eps is None else eps.reshape(-1, no_samples, 2).float().contiguous(),
+                         _next_seed(self), no_samples)
+        if return_mean:
+            return torch.sum(kl) / torch.sum(mask)
+        return kl.reshape(lead + (1,))
+
+    # ------------------------------------------------------------------ fused training objective
+    def fused_elbo(self, signal_layer, q_params, im_sigma, data, mask, prior, kl_samples=70, kl_weight=1.0,
+                   eps=None, eps_kl=None, mask_sum=None, seed=None, return_maps=False):
+        """nll + kl_weight * kl for one batch in ONE kernel launch (differentiable w.r.t. q_params, im_sigma).
+
+        q_params [...,5], im_sigma [...,n_tau], data [...,n_tau] (pre-masked, train.py:56), mask [...,1],
+        prior [...,5] raw or None.  ``mask_sum`` = global sum(mask) when the batch is sharded over ranks.
+        Returns (loss, dict(nll, kl[, nll_map, kl_map])) with the reference's normalisation (sum / sum(mask))."""
+        nt = signal_layer.n_tau
+        q = q_params.reshape(-1, 5).float().contiguous()
+        n = q.shape[0]
+        sg = im_sigma.reshape(n, nt).float().contiguous()
+        y = data.reshape(n, nt).float().contiguous()
+        m = mask.reshape(n).float().contiguous()
+        pr = None if prior is None else prior.reshape(n, 5).float().contiguous()
+        e = None if eps is None else eps.reshape(n, 2).float().contiguous()
+        ek = None if eps_kl is None else eps_kl.reshape(n, kl_samples, 2).float().contiguous()
+        if mask_sum is None:
+            mask_sum = float(m.sum().item())
+        inv = 1.0 / float(mask_sum)
+        out = _FusedElboFn.apply(q, sg, self, signal_layer, y, m, pr, e, ek,
+                                 _next_seed(self) if seed is None else seed, kl_samples if pr is not None else 0,
+                                 inv, float(kl_weight), return_maps)
+        loss, sums = out[0], out[1]
+        info = {'nll': (sums[0] * inv).float(), 'kl': (sums[1] * inv).float(), 'mask_sum': sums[2],
+                'non_finite': sums[3]}
+        if return_maps:
+            info['nll_map'], info['kl_map'] = out[2], out[3]
+        return loss, info
+
+    # ------------------------------------------------------------------ adjacent losses (torch ops)
+    def smoothness_loss(self, true_params, pred_params):
+        """Total-variation term (model.py:726-754): x/y neighbours of the forward-transformed means."""
+        true_params = torch.cat([true_params for _ in range(self._no_samples)], 0)
+        mask = true_params[..., 5:6] if self._use_mvg else true_params[..., 4:5]
+        means = torch.stack([pred_params[..., 0], pred_params[..., 2]], -1)
+        p = self.forward_transform(means) / torch.tensor([self._oef_range, self._dbv_range], device=means.device)
+        dx = p[:, :-1] - p[:, 1:]
+        dx = torch.where((mask[:, :-1] > 0.0) & (mask[:, 1:] > 0.0), dx, torch.zeros_like(dx))
+        dy = p[:, :, :-1] - p[:, :, 1:]
+        dy = torch.where((mask[:, :, :-1] > 0.0) & (mask[:, :, 1:] > 0.0), dy, torch.zeros_like(dy))
+        return (dx.abs().sum() + dy.abs().sum()) / mask.sum()
+
+    def logit_gaussian_mvg_log_prob(self, observations, predicted_params):
+        """model.py:376-400 (returns the negative log prob, as the reference does)."""
+        shape = tuple(predicted_params.shape[:-1])
+        p = predicted_params.reshape(-1, 5)
+        ls_o, ls_d = self.transform_std(p[:, 1]), self.transform_std(p[:, 3])
+        cov = self.transform_offdiag(p[:, 4])
+        x = self.backwards_transform(observations[:, 0:2], False)
+        x = x + (torch.clamp(x, 1e-6, 1.0 - 1e-6) - x).detach()              # clip_by_value_preserve_gradient
+        z = logit(x)
+        r_o, r_d = z[:, 0] - p[:, 0], z[:, 1] - p[:, 2]
+        w_o = r_o * torch.exp(-ls_o)
+        w_d = r_d * torch.exp(-ls_d) - r_o * torch.exp(-ls_o - ls_d) * cov
+        loss = math.log(2.0 * math.pi) + 0.5 * (2.0 * (ls_o + ls_d)) + 0.5 * (w_o ** 2 + w_d ** 2)
+        loss = loss + torch.sum(torch.log(x) + torch.log(1.0 - x), -1)
+        return loss.reshape(shape)
+
+    def synthetic_data_loss(self, y_true_orig, y_pred_orig, use_r2p_loss=False, inv_gamma_alpha=0.0,
+                            inv_gamma_beta=0.0):
+        """Pre-training NLL (model.py:449-514), mvg branch without the optional r2p / inverse-gamma terms."""
+        if use_r2p_loss or inv_gamma_alpha * inv_gamma_beta > 0.0 or self._infer_inv_gamma or not self._use_mvg:
+            raise NotImplementedError('only the optimal.yaml branch of synthetic_data_loss is provided')
+        y_true = y_true_orig.reshape(-1, 3)
+        return torch.mean(self.logit_gaussian_mvg_log_prob(y_true[:, :2], y_pred_orig.reshape(-1, 5)))
