@@ -1,0 +1,276 @@
+#!/usr/bin/env python3
+"""Benchmark of the qBOLD-VI hot path (BASELINE.json metric: voxel-signals/sec fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--voxels V]
+
+Workload (BASELINE config 2): batched forward model + TF-consistent gradients w.r.t. OEF/DBV on
+V = 16 777 216 voxels x the 11-tau optimal.yaml grid per GPU (full model + blood), synthetic inputs
+OEF~U(0.04,0.84), DBV~U(0.001,0.201), upstream gradient ~N(0,1).  One "step" = one pass over the
+batch = one launch of the fused forward+VJP kernel.  N>1: voxel shards, one process per GPU, no
+data-path collective (weak scaling); timing = max over ranks of the CUDA-event time.
+
+`--impl reference` times the restated reference CPU path (oracle/torch_port.py: the tensor program
+TensorFlow runs, float32, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'voxel_signals_per_sec_fwd_bwd'
+UNIT = 'voxel-signals/s'
+N_TAU = 11
+
+
+def alg_flops_per_voxel(oef, taus_abs_cols, dw_k):
+    """SURVEY.md 8(d) / BASELINE.md 3: 128*8*(28(1-f) + 107 f) + ~0.4k epilogue, with f the fraction of
+    live (column, node) pairs on the Bessel asymptotic branch |1.5*tau*dw*u| > 2, from the actual inputs."""
+    import numpy as np
+    u = 1e-5 + np.arange(128) * ((1 - 1e-5) / 128)
+    a = 1.5 * np.asarray(taus_abs_cols)[None, :] * dw_k * np.asarray(oef, dtype=np.float64)[:, None]
+    f = float(np.mean(a[:, :, None] * u[None, None, :] > 2.0))
+    ncol = len(taus_abs_cols)
+    return 128 * ncol * (28 * (1 - f) + 107 * f) + 400.0, f
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20,
+                     'hw_thermal_slowdown': 0x40, 'hw_power_brake': 0x80}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.1)
+        except Exception as exc:                                   # pragma: no cover
+            self.reasons.add('sampler_error:%s' % type(exc).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {'sm_mhz': (s[len(s) // 2] if s else None), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+def physics_and_cfg():
+    from oracle import qbold_oracle as o                           # checker side: only used by the CPU legs
+    cfg = o.default_config()
+    cfg['simulate_noise'] = 'False'
+    return o.parse_params(cfg), cfg
+
+
+def cpu_port_run(n_voxels, threads, seed=1234):
+    """Restated reference CPU path (forward + autodiff VJP) on n_voxels of the bench workload."""
+    import torch
+    from oracle import torch_port
+    ph, _ = physics_and_cfg()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand((n_voxels, 2), generator=g)
+    x[:, 0] = x[:, 0] * 0.8 + 0.04
+    x[:, 1] = x[:, 1] * 0.2 + 0.001
+    gs = torch.randn((n_voxels, N_TAU), generator=g)
+    return torch_port.timed(ph, x, gs, threads)
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: rank 0 alone times the CPU path; other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 131072
+    for _ in range(args.warmup):
+        cpu_port_run(8192, threads)
+    t = [cpu_port_run(sample, threads) for _ in range(args.steps)]
+    sec = sum(t)
+    value = sample * N_TAU * args.steps / sec
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * sec / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.voxels, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': '%d voxels x 11 tau per step, forward + autodiff VJP, float32, restated reference '
+                                   'CPU path (TensorFlow unavailable offline): oracle/torch_port.py' % sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(voxels, gpus):
+    return {'workload': 'BASELINE config 2: batched forward model + analytic (TF-autodiff-consistent) gradients '
+                        'w.r.t. OEF/DBV, %d voxels x 11-tau optimal.yaml grid per GPU, full model + blood' % voxels,
+            'voxels_per_gpu': voxels, 'n_tau': N_TAU, 'quadrature_nodes': 129,
+            'inputs': 'OEF~U(0.04,0.84), DBV~U(0.001,0.201), g_signal~N(0,1), seed 1234+rank',
+            'l2': 'inputs+outputs per step (%.0f MB) exceed the 126 MB L2; no flush needed' % (voxels * 104 / 1e6),
+            'parallelism': 'voxel shards x%d, one process per GPU, no data-path collective' % gpus}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--voxels', type=int, default=1 << 24)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import qbold_vi_b200 as qb
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the qBOLD hot path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    cfg = qb.load_system_parameters(qb.config.DEFAULT_CONFIG_PATH)
+    cfg['simulate_noise'] = 'False'
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    n = args.voxels
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.rand((n, 2), device=dev, generator=gen)
+    x[:, 0] = x[:, 0] * 0.8 + 0.04
+    x[:, 1] = x[:, 1] * 0.2 + 0.001
+    gs = torch.randn((n, N_TAU), device=dev, generator=gen)
+    sig = torch.empty((n, N_TAU), device=dev)
+    grad = torch.empty((n, 2), device=dev)
+    import ctypes as C
+    lib = qb._lib.lib()
+    P = C.byref(layer.params)
+    st = qb._lib.stream_ptr(dev)
+
+    def step():
+        qb._lib.check(lib.qbold_forward_backward(P, x.data_ptr(), gs.data_ptr(), n, sig.data_ptr(), grad.data_ptr(), st))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = qb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = qb.launch_count() - launches0
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * n * N_TAU * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host tensors, copies inside the timed region)
+    hx, hg = x.cpu().pin_memory(), gs.cpu().pin_memory()
+    hs, hgr = torch.empty_like(hg).pin_memory(), torch.empty((n, 2)).pin_memory()
+    layer.forward_backward_host(hx, hg, hs, hgr)                          # warm-up (allocates the staging slots)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        layer.forward_backward_host(hx, hg, hs, hgr)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * N_TAU * args.e2e_steps / float(e2e_s.item())
+    e2e_ok = bool(torch.equal(hs[:4096], sig[:4096].cpu()))
+
+    if rank == 0:
+        # ---- roofline of the dominant (only) kernel: FP32 CUDA-core bound, HBM reported as secondary
+        idx = torch.randint(0, n, (200000,), device=dev)
+        abs_cols = [layer.params.abs_tau[i] for i in range(layer.params.n_cols)]
+        f_alg, f_big = alg_flops_per_voxel(x[idx, 0].cpu().numpy(), abs_cols, layer.params.dw_k)
+        per_launch_s = ms_max * 1e-3 / args.steps
+        achieved_tf = n * f_alg / per_launch_s / 1e12
+        fma_tf = qb.fma_peak_tflops(8192)
+        derived_tf = 148 * 128 * 2 * 1.965e9 / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        hbm_gbs = n * 104 / per_launch_s / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(n, world),
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n * (8 + 4 * N_TAU),
+                    'd2h_bytes_per_step': n * (8 + 4 * N_TAU), 'steps': args.e2e_steps,
+                    'path': 'qbold_forward_backward_host: pinned host buffers, 3-slot H2D/kernel/D2H pipeline',
+                    'matches_device_path': e2e_ok},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'fp32', 'achieved': achieved_tf, 'peak': fma_tf, 'unit': 'TFLOP/s',
+                         'frac': achieved_tf / fma_tf, 'traffic': None,
+                         'peak_source': 'FFMA micro-benchmark (qbold_fma_peak) measured in this run; derived '
+                                        '148 SM x 128 lanes x 2 x 1.965 GHz = %.1f TFLOP/s (frac %.3f)'
+                                        % (derived_tf, achieved_tf / derived_tf),
+                         'kernel': 'k_forward<BWD=true>', 'launch_ms': per_launch_s * 1e3,
+                         'alg_flops_per_voxel': f_alg, 'asymptotic_branch_fraction_f': f_big,
+                         'alg_bytes_per_voxel': 104, 'hbm': {'achieved': hbm_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                                                             'frac': hbm_gbs / hbm_peak,
+                                                             'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = 262144
+            cpu_port_run(8192, threads)
+            sec = cpu_port_run(sample, threads)
+            line['cpu_baseline'] = {'value': sample * N_TAU / sec, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                    'sample': '%d voxels of the same workload, forward + autodiff VJP, float32, '
+                                              'restated reference CPU path (TensorFlow unavailable offline): '
+                                              'oracle/torch_port.py, %.1f s' % (sample, sec)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,349 @@
+"""GPU suite: the CUDA path (through the ctypes C-ABI) against the oracle and the golden fixtures.
+
+Tolerances are the ones BASELINE.json states: signals within 1e-5 relative (FP32), ELBO and its
+gradients within 1e-4 relative.  /root/reference is never touched here.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_elem, rel_max
+from oracle import philox
+from oracle import qbold_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+SIG_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def qb():
+    import qbold_vi_b200 as qb
+    qb._lib.lib()
+    return qb
+
+
+@pytest.fixture(scope='module')
+def dev():
+    return torch.device('cuda', 0)
+
+
+def _t(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
+
+
+def _rand_voxels(n, seed=0):
+    rng = np.random.default_rng(seed)
+    return np.stack([rng.uniform(0.04, 0.84, n), rng.uniform(0.001, 0.201, n)], -1).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------- forward
+@pytest.mark.parametrize('full', [True, False])
+@pytest.mark.parametrize('blood', [True, False])
+def test_forward_matches_oracle(qb, dev, cfg_noise_off, physics, full, blood):
+    x = _rand_voxels(4096, 1)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, full, blood)
+    s = layer(_t(x, dev)).cpu().numpy()
+    assert s.shape == (4096, 11) and s.dtype == np.float32
+    s32 = o.forward(physics, x, full, blood, np.float32)
+    s64 = o.forward(physics, x, full, blood, np.float64)
+    assert rel_elem(s, s32) < SIG_TOL, 'vs float32-emulated TF semantics'
+    assert rel_elem(s, s64) < SIG_TOL, 'vs float64 restatement (node 0 dead)'
+
+
+def test_forward_matches_reference_source_fixture(qb, dev, cfg_noise_off):
+    g = golden('ref_shim_forward.npz')
+    for full in (1, 0):
+        for blood in (1, 0):
+            layer = qb.SignalGenerationLayer(cfg_noise_off, bool(full), bool(blood), taus=g['taus'])
+            s = layer(_t(g['oef_dbv'], dev).reshape(-1, 1, 1, 1, 2))
+            assert tuple(s.shape) == (g['oef_dbv'].shape[0], 1, 1, 1, 11)          # leading shape kept (signals.py:137-140)
+            assert rel_elem(s.cpu().numpy().reshape(-1, 11), g['signal_f%d_b%d' % (full, blood)]) < SIG_TOL
+
+
+def test_appendix_b_known_answers(qb, dev, cfg_noise_off):
+    k = golden('kat_appendix_b.npz')
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    s = layer(_t(k['oef_dbv'], dev)).cpu().numpy()
+    assert np.max(np.abs(s[0] - k['signal_fp64_0'])) < 2e-6
+    assert np.max(np.abs(s[1] - k['signal_fp32_1'])) < 2e-6
+    _, g = layer.forward_backward(_t(k['oef_dbv'][:1], dev))                        # g_signal NULL = ones (signals.py:307-314 demo)
+    assert rel_elem(g.cpu().numpy()[0], k['grad_sum_0']) < GRAD_TOL
+
+
+@pytest.mark.parametrize('full', [True, False])
+@pytest.mark.parametrize('blood', [True, False])
+def test_forward_backward_matches_tf_consistent_gradient(qb, dev, cfg_noise_off, physics, full, blood):
+    x = _rand_voxels(2048, 2)
+    gs = np.random.default_rng(5).standard_normal((2048, 11)).astype(np.float32)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, full, blood)
+    s, g = layer.forward_backward(_t(x, dev), _t(gs, dev))
+    s64, g64 = o.forward_backward(physics, x, gs, full, blood, np.float64)
+    assert rel_elem(s.cpu().numpy(), s64) < SIG_TOL
+    g = g.cpu().numpy()
+    assert rel_max(g[:, 0], g64[:, 0]) < GRAD_TOL and rel_max(g[:, 1], g64[:, 1]) < GRAD_TOL
+    # element-wise, away from sign changes of the random-weighted sum
+    big = np.abs(g64) > 1e-2 * np.abs(g64).max(0, keepdims=True)
+    assert np.max(np.abs(g - g64)[big] / np.abs(g64)[big]) < 5 * GRAD_TOL
+    # the golden gradient of the reference source (tape.gradient over the TF shim)
+    gold = golden('ref_shim_forward.npz')
+    layer = qb.SignalGenerationLayer(cfg_noise_off, full, blood, taus=gold['taus'])
+    key = 'f%d_b%d' % (int(full), int(blood))
+    _, g1 = layer.forward_backward(_t(gold['oef_dbv'], dev))
+    _, g2 = layer.forward_backward(_t(gold['oef_dbv'], dev), _t(gold['g_rand'], dev))
+    assert rel_max(g1.cpu().numpy(), gold['grad_ones_' + key]) < GRAD_TOL
+    assert rel_max(g2.cpu().numpy(), gold['grad_rand_' + key]) < GRAD_TOL
+
+
+def test_autograd_through_the_layer(qb, dev, cfg_noise_off):
+    x = _t(_rand_voxels(257, 3), dev).reshape(257, 1, 2).requires_grad_(True)
+    w = torch.randn(257, 1, 11, device=dev)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    (layer(x) * w).sum().backward()
+    _, g = layer.forward_backward(x.detach(), w)
+    assert torch.equal(x.grad.reshape(-1, 2), g)
+
+
+def test_edge_cases(qb, dev, cfg_noise_off, physics):
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    assert tuple(layer(torch.zeros((0, 2), device=dev)).shape) == (0, 11)          # empty input
+    for n in (1, 7, 33, 255, 1025):                                                 # ragged sizes
+        x = _rand_voxels(n, n)
+        assert rel_elem(layer(_t(x, dev)).cpu().numpy(), o.forward(physics, x, dtype=np.float64)) < SIG_TOL
+    with pytest.raises(AssertionError):
+        layer(torch.zeros((4, 3), device=dev))
+    # corners of the admissible box and beyond it (OEF up to 1: a = 29)
+    x = np.array([[0.04, 0.001], [0.84, 0.201], [0.04, 0.201], [0.84, 0.001], [1.0, 0.3], [0.01, 0.0005]], np.float32)
+    assert rel_elem(layer(_t(x, dev)).cpu().numpy(), o.forward(physics, x, dtype=np.float32)) < SIG_TOL
+    # variable haematocrit input (signals.py:64-70)
+    xv = np.concatenate([_rand_voxels(300, 9), np.random.default_rng(1).uniform(0.25, 0.45, (300, 1))], -1).astype(np.float32)
+    lv = qb.SignalGenerationLayer(cfg_noise_off, True, True, variable_hct=True)
+    assert rel_elem(lv(_t(xv, dev)).cpu().numpy(), o.forward(physics, xv, variable_hct=True, dtype=np.float64)) < SIG_TOL
+
+
+def test_24_tau_grid(qb, dev, cfg_noise_off):
+    cfg = dict(cfg_noise_off, tau_start='-0.028', tau_end='0.065', tau_step='0.004')
+    ph = o.parse_params(cfg)
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    assert layer.params.n_cols == 16                                                # two column groups
+    x = _rand_voxels(512, 4)
+    gs = np.random.default_rng(6).standard_normal((512, 24)).astype(np.float32)
+    s, g = layer.forward_backward(_t(x, dev), _t(gs, dev))
+    s64, g64 = o.forward_backward(ph, x, gs, dtype=np.float64)
+    assert rel_elem(s.cpu().numpy(), s64) < SIG_TOL and rel_max(g.cpu().numpy(), g64) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------- sampling / likelihood / KL
+def _trainer(qb, cfg, e=None, **kw):
+    args = dict(student_t_df=200, multi_image_normalisation=False, use_mvg=True, use_population_prior=False,
+                predict_log_data=False, seed=1234)
+    args.update(kw)
+    return qb.EncoderTrainer(cfg, **args)
+
+
+def test_reparam_layer_matches_reference_source(qb, dev, cfg_noise_off):
+    e = golden('ref_shim_elbo_optimal.npz')
+    tr = _trainer(qb, cfg_noise_off)
+    q = _t(e['q'], dev).reshape(2, 4, 4, 2, 5).requires_grad_(True)
+    smp = qb.ReparamTrickLayer(tr)((q, None), eps=_t(e['eps'], dev))
+    assert tuple(smp.shape) == (2, 4, 4, 2, 2)
+    assert rel_elem(smp.detach().cpu().numpy().reshape(-1, 2), e['sampled']) < SIG_TOL
+    # its gradient against torch autograd of the same formulas
+    w = torch.randn_like(smp)
+    (smp * w).sum().backward()
+    q2 = _t(e['q'], dev).requires_grad_(True)
+    ep = _t(e['eps'], dev)
+    z_o = q2[:, 0] + ep[:, 0] * torch.exp(tr.transform_std(q2[:, 1]))
+    z_d = q2[:, 2] + ep[:, 0] * tr.transform_offdiag(q2[:, 4]) + ep[:, 1] * torch.exp(tr.transform_std(q2[:, 3]))
+    ref = tr.forward_transform(torch.stack([z_o, z_d], -1))
+    (ref * w.reshape(-1, 2)).sum().backward()
+    assert rel_max(q.grad.cpu().numpy().reshape(-1, 5), q2.grad.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('tag', ['optimal', 'multinorm', 'studentt'])
+def test_fused_elbo_matches_reference_source(qb, dev, cfg_noise_off, tag):
+    e = golden('ref_shim_elbo_%s.npz' % tag)
+    df = float(e['student_t_df'])
+    tr = _trainer(qb, cfg_noise_off, student_t_df=df, multi_image_normalisation=bool(e['multi_image_normalisation']))
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    q = _t(e['q'], dev).requires_grad_(True)
+    sg = _t(e['sigma'], dev).requires_grad_(True)
+    loss, info = tr.fused_elbo(layer, q, sg, _t(e['data'], dev), _t(e['mask'], dev), _t(e['prior'], dev),
+                               kl_samples=70, eps=_t(e['eps'], dev), eps_kl=_t(e['eps_kl'], dev), return_maps=True)
+    loss.backward()
+    assert rel_elem(info['nll'].item(), e['nll']) < GRAD_TOL
+    assert rel_elem(info['kl'].item(), e['kl']) < GRAD_TOL
+    assert rel_elem(loss.item(), e['nll'] + e['kl']) < GRAD_TOL
+    assert rel_max(info['nll_map'].cpu().numpy(), e['nll_map']) < GRAD_TOL
+    assert rel_max(q.grad.cpu().numpy(), e['grad_q_nll'] + e['grad_q_kl']) < GRAD_TOL
+    assert rel_max(sg.grad.cpu().numpy(), e['grad_sigma']) < GRAD_TOL
+    assert float(info['mask_sum']) == e['mask'].sum() and float(info['non_finite']) == 0
+    # masked voxels: exactly zero loss and gradient (model.py:564,661)
+    dead = e['mask'] == 0
+    assert np.all(q.grad.cpu().numpy()[dead] == 0) and np.all(sg.grad.cpu().numpy()[dead] == 0)
+
+
+def test_fused_elbo_matches_oracle_on_random_batch(qb, dev, cfg_noise_off, physics):
+    n, S = 1536, 70
+    r = np.random.default_rng(21)
+    q = np.stack([r.normal(-0.3, 0.7, n), r.normal(0, 0.6, n), r.normal(-1.2, 0.7, n), r.normal(0, 0.6, n),
+                  r.normal(0, 0.8, n)], -1).astype(np.float32)
+    prior = (q + r.normal(0, 0.3, (n, 5))).astype(np.float32)
+    sigma = np.exp(r.normal(np.log(0.05), 0.2, (n, 11))).astype(np.float32)
+    mask = (r.uniform(size=n) > 0.3).astype(np.float32)
+    truth = np.stack([r.uniform(0.1, 0.7, n), r.uniform(0.005, 0.15, n)], -1)
+    data = (o.forward(physics, truth, dtype=np.float64) * 100 * (1 + 0.02 * r.standard_normal((n, 11)))).astype(np.float32)
+    data *= mask[:, None]
+    eps = r.standard_normal((n, 2)).astype(np.float32)
+    eps_kl = r.standard_normal((n, S, 2)).astype(np.float32)
+    ref = o.elbo_and_grads(physics, q, sigma, data, mask, prior, eps, eps_kl, np.float64)
+    tr = _trainer(qb, cfg_noise_off)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    qt, st = _t(q, dev).requires_grad_(True), _t(sigma, dev).requires_grad_(True)
+    loss, info = tr.fused_elbo(layer, qt, st, _t(data, dev), _t(mask, dev), _t(prior, dev), kl_samples=S,
+                               eps=_t(eps, dev), eps_kl=_t(eps_kl, dev), return_maps=True)
+    loss.backward()
+    assert rel_elem(info['nll'].item(), ref['nll']) < GRAD_TOL and rel_elem(info['kl'].item(), ref['kl']) < GRAD_TOL
+    assert rel_max(info['kl_map'].cpu().numpy(), ref['kl_map']) < GRAD_TOL
+    assert rel_max(qt.grad.cpu().numpy(), ref['grad_q']) < GRAD_TOL
+    assert rel_max(st.grad.cpu().numpy(), ref['grad_sigma']) < GRAD_TOL
+    # sharding invariance: the same batch in two halves with the global mask sum gives the same gradients
+    h = n // 2
+    parts = []
+    for sl in (slice(0, h), slice(h, n)):
+        qh = _t(q[sl], dev).requires_grad_(True)
+        l, _ = tr.fused_elbo(layer, qh, _t(sigma[sl], dev), _t(data[sl], dev), _t(mask[sl], dev), _t(prior[sl], dev),
+                             kl_samples=S, eps=_t(eps[sl], dev), eps_kl=_t(eps_kl[sl], dev), mask_sum=mask.sum())
+        l.backward()
+        parts.append((l.item(), qh.grad))
+    assert abs(parts[0][0] + parts[1][0] - loss.item()) < 1e-5 * abs(loss.item())
+    assert torch.equal(torch.cat([parts[0][1], parts[1][1]]), qt.grad)
+
+
+def test_kl_loss_mc_and_closed_form(qb, dev, cfg_noise_off):
+    e = golden('ref_shim_elbo_optimal.npz')
+    tr = _trainer(qb, cfg_noise_off)
+    true = torch.cat([_t(e['prior'], dev), _t(e['mask'], dev)[:, None]], -1).reshape(2, 4, 4, 2, 6)
+    pred = _t(e['q'], dev).reshape(2, 4, 4, 2, 5).requires_grad_(True)
+    kl = tr.kl_loss(true, pred, eps=_t(e['eps_kl'], dev))
+    kl.backward()
+    assert rel_elem(kl.item(), e['kl']) < GRAD_TOL
+    assert rel_max(pred.grad.cpu().numpy().reshape(-1, 5), e['grad_q_kl']) < GRAD_TOL
+    kl_map = tr.kl_loss(true, pred.detach(), return_mean=False, eps=_t(e['eps_kl2'], dev))
+    assert tuple(kl_map.shape) == (2, 4, 4, 2, 1)
+    assert rel_max(kl_map.cpu().numpy().reshape(-1), e['kl_map2']) < GRAD_TOL
+    # closed form: value vs the textbook formula, gradient vs float64 central differences of it
+    p2 = _t(e['q'], dev).requires_grad_(True)
+    klc = tr.kl_loss(true.reshape(-1, 6), p2, return_mean=False, no_samples=0)
+    klc.sum().backward()
+    ref = np.where(e['mask'] > 0, o.closed_form_kl(e['prior'], e['q']), 0)
+    assert rel_max(klc.detach().cpu().numpy().reshape(-1), ref) < 1e-5
+    h = 1e-6
+    for j in range(5):
+        d = np.zeros(5)
+        d[j] = h
+        fd = (o.closed_form_kl(e['prior'], e['q'].astype(np.float64) + d) -
+              o.closed_form_kl(e['prior'], e['q'].astype(np.float64) - d)) / (2 * h)
+        fd = np.where(e['mask'] > 0, fd, 0)
+        assert rel_max(p2.grad.cpu().numpy()[:, j], fd) < GRAD_TOL
+
+
+def test_posterior_stats(qb, dev, cfg_noise_off, physics):
+    m = golden('ref_shim_means.npz')
+    tr = _trainer(qb, cfg_noise_off)
+    q = _t(m['q'], dev).reshape(2, 4, 4, 2, 5)
+    means, var = tr.calculate_means(q, torch.ones_like(q[..., :1]), include_r2p=True, return_stds=True, no_samples=16,
+                                    eps=_t(m['eps'], dev))
+    assert tuple(means.shape) == (2, 4, 4, 2, 3)
+    assert rel_elem(means.cpu().numpy().reshape(-1, 3), m['means']) < SIG_TOL
+    assert rel_max(var.cpu().numpy().reshape(-1, 3), m['stds']) < GRAD_TOL         # 'stds' are variances (model.py:331)
+    # in-kernel Philox draws == oracle/philox.py draws (64 samples, BASELINE config 4)
+    tr2 = _trainer(qb, cfg_noise_off, seed=77)
+    seed = (77 + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF                           # first call of this trainer
+    mp, vp = tr2.calculate_means(q, None, include_r2p=True, return_stds=True, no_samples=64)
+    eps = philox.kl_eps(seed, np.arange(64), 64)
+    mo, vo = o.posterior_stats(physics, m['q'], eps, np.float64)
+    assert rel_elem(mp.cpu().numpy().reshape(-1, 3), mo) < GRAD_TOL
+    assert rel_max(vp.cpu().numpy().reshape(-1, 3), vo) < 10 * GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------- synthetic generation
+@pytest.mark.parametrize('tag', ['u10', 'u0'])
+def test_generation_matches_reference_source(qb, dev, tag):
+    d = golden('ref_shim_dataset_%s.npz' % tag)
+    cfg = o.default_config()                                                         # noise ON, as in the INI
+    ty = d['train_y']
+    # un-shuffle the labels to recover the marginals the reference drew
+    inv = np.empty(529, dtype=np.int64)
+    inv[np.arange(529)] = d['perm']
+    grid = np.empty((529, 2), np.float32)
+    grid[d['perm']] = ty[:, :2]
+    oefs, dbvs = grid.reshape(23, 23, 2)[:, 0, 0].copy(), grid.reshape(23, 23, 2)[0, :, 1].copy()
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    snr_u01 = _t(d['snr_u01'].reshape(-1), dev)
+    x, y = qb.generate_from_marginals(layer, _t(oefs, dev), _t(dbvs, dev),
+                                      torch.as_tensor(d['perm'], device=dev).contiguous(), n_chunks=10,
+                                      snr_u01=snr_u01, noise_eps=_t(d['noise_eps'], dev))
+    assert tuple(x.shape) == (520, 11) and tuple(y.shape) == (529, 3)               # S^2 % 10 rows dropped from x only
+    assert rel_elem(y.cpu().numpy(), ty) < 1e-6
+    assert rel_elem(x.cpu().numpy(), d['train_x']) < 2 * SIG_TOL
+
+
+def test_generation_feistel_and_philox_noise(qb, dev, physics):
+    cfg = o.default_config()
+    ph = o.parse_params(cfg)
+    layer = qb.SignalGenerationLayer(cfg, True, True, seed=4242)
+    r = np.random.default_rng(8)
+    oefs = r.uniform(0.05, 0.8, 40).astype(np.float32)
+    dbvs = r.uniform(0.003, 0.195, 30).astype(np.float32)
+    x, y = qb.generate_from_marginals(layer, _t(oefs, dev), _t(dbvs, dev), None, n_chunks=10, seed=4242)
+    perm = philox.feistel_permute(np.arange(1200), 1200, 4242)
+    assert sorted(perm.tolist()) == list(range(1200))
+    snr = np.concatenate([philox.snr_u01(4242 ^ 0x5DEECE66D, np.arange(i * 120, (i + 1) * 120)) for i in range(10)])
+    eps = np.concatenate([philox.noise_eps(4242 ^ 0x5DEECE66D, np.arange(i * 120, (i + 1) * 120), 11) for i in range(10)])
+    xo, yo = o.synthetic_dataset_from_draws(ph, oefs, dbvs, perm, snr * np.float32(70) + np.float32(50), eps)
+    assert rel_elem(y.cpu().numpy(), yo) < 1e-6
+    assert rel_elem(x.cpu().numpy(), xo) < 5 * SIG_TOL
+    # public entry point: shapes, label ranges, noise level
+    cfg['sample_size'] = '100'
+    tx, ty = qb.create_synthetic_dataset(cfg, True, True, 0.0, uniform_prop=0.1, device=dev, seed=3)
+    assert tuple(tx.shape) == (10000, 11) and tuple(ty.shape) == (10000, 3)
+    ty = ty.cpu().numpy()
+    assert ty[:, 0].min() >= 0.05 - 1e-6 and ty[:, 0].max() <= 0.8 + 1e-6
+    assert ty[:, 1].min() >= 0.003 - 1e-6 and ty[:, 1].max() <= 0.195 + 1e-6
+    clean = o.forward(ph, ty[:, :2], dtype=np.float32)
+    resid = tx.cpu().numpy() - clean
+    snr_eff = clean.mean(0) / resid.std(0)
+    assert np.all(snr_eff > 40) and np.all(snr_eff < 130)                           # U(50,120) * norm_snr
+    cfg5 = dict(cfg, tau_start='0.0', tau_end='0.05', tau_step='0.01')
+    with pytest.raises(UnboundLocalError):                                          # signals.py:117-121
+        qb.SignalGenerationLayer(cfg5, True, True)(torch.rand(8, 2, device=dev) * 0.1 + 0.1)
+
+
+# ---------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_16M(qb, dev, cfg_noise_off):
+    """BASELINE config 2 size: 16 777 216 voxels.  Size-independent properties only."""
+    n = 1 << 24
+    g = torch.Generator(device=dev).manual_seed(1234)
+    x = torch.rand((n, 2), device=dev, generator=g)
+    x[:, 0] = x[:, 0] * 0.8 + 0.04
+    x[:, 1] = x[:, 1] * 0.2 + 0.001
+    tissue = qb.SignalGenerationLayer(cfg_noise_off, True, False)                    # S = (1 - dbv) * S_t
+    s = tissue(x)
+    assert torch.isfinite(s).all()
+    assert torch.equal(s[:, 0], s[:, 4]) and torch.equal(s[:, 1], s[:, 3])           # S(tau) = S(-tau)
+    e = float(np.float32(tissue.params.e_tissue))
+    assert torch.allclose(s[:, 2], (1 - x[:, 1]) * e, rtol=3e-7, atol=0)             # tau = 0: exp(-TE*R2t)
+    assert (s[:, 5:] <= s[:, 4:-1] * (1 + 1e-6)).all()                               # decays with tau
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    sl = slice(5_000_000, 5_000_000 + 4096)
+    w1 = torch.randn((n, 11), device=dev, generator=g)
+    s_full, g1 = layer.forward_backward(x, w1)
+    s_part, g_part = layer.forward_backward(x[sl].contiguous(), w1[sl].contiguous())
+    assert torch.equal(s_full[sl], s_part) and torch.equal(g1[sl], g_part)          # shard invariance, bit-exact
+    del s, s_full
+    _, g_ones = layer.forward_backward(x, None, want_signal=False)
+    _, g2 = layer.forward_backward(x, w1 + 1.0, want_signal=False)
+    err = (g2 - (g1 + g_ones)).abs().max(0).values / g2.abs().max(0).values         # the VJP is linear in g
+    assert float(err.max()) < 1e-5

@@ -1,0 +1,135 @@
+"""CPU suite, part 2: host logic and the C-ABI boundary (no compute calls: there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import qbold_oracle as o
+from oracle import philox
+
+
+@pytest.fixture(scope='module')
+def qb():
+    import qbold_vi_b200 as qb
+    if not os.path.exists(qb._lib.LIB_PATH):
+        qb.build_library()
+    return qb
+
+
+def test_library_exports_every_symbol_declared_in_the_header(qb):
+    hdr = open(os.path.join(ROOT, 'include', 'qbold.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(qbold_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 15
+    handle = C.CDLL(qb._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), 'libqbold.so does not export %s' % name
+    assert declared == set(qb._lib.EXPORTED_SYMBOLS), declared ^ set(qb._lib.EXPORTED_SYMBOLS)
+    lib = qb._lib.lib()                       # also checks ABI version and sizeof(QboldParams)
+    assert lib.qbold_abi_version() == 1
+
+
+def test_params_block_matches_the_oracle(qb):
+    cfg = o.default_config()
+    ph = o.parse_params(cfg)
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    P = layer.params
+    assert P.n_tau == 11 and P.n_cols == 8 and P.col_of_tau[2] == -1
+    assert list(P.col_of_tau)[:5] == [0, 1, -1, 1, 0]                       # tau and -tau share a column
+    assert np.array_equal(np.array(P.tau[:11], dtype=np.float32), ph.taus)
+    assert np.float32(P.dw_k) == np.float32(o.dw_const(ph))
+    assert np.float32(P.e_tissue) == o._exp(-ph.te * ph.r2t, np.float32)
+    # 1 - (2 - e1) * e2 cancels ~2 bits: a 1-ulp difference between exp implementations shows up as ~1e-7 here
+    assert abs(P.kappa - float(o.m_bld(ph, np.float64) * 0.775)) < 5e-8
+    assert abs(P.kappa - float(o.m_bld(ph, np.float32) * np.float32(0.775))) < 3e-7
+    B, _ = o.blood_b_of_tau(ph, np.float32)
+    assert np.max(np.abs(np.array(P.blood_b[:11]) - B)) < 2e-6
+    u = o.quad_nodes()
+    assert np.array_equal(np.array(P.qu[:129], dtype=np.float32), u)
+    W, _ = o.simpson_weights(u, np.float64)
+    g = (2 + u.astype(np.float64)) * np.sqrt(1 - u.astype(np.float64)) / (3 * u.astype(np.float64) ** 2)
+    c = W * g
+    assert P.qc[0] == 0.0 and P.qc[128] == 0.0                              # node 0 dead in the value
+    assert abs(P.node0_c - c[0]) / c[0] < 1e-6
+    assert np.max(np.abs(np.array(P.qc[1:128]) - c[1:128]) / c[1:128]) < 1e-6
+    assert np.max(np.abs(np.array(P.qd[0:128]) - (c * u)[0:128]) / (c * u)[0:128]) < 1e-6   # node 0 live in the derivative
+
+
+def test_tau_24_grid_and_noise_table(qb):
+    cfg = o.default_config()
+    cfg.update(tau_start='-0.028', tau_end='0.065', tau_step='0.004')
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    assert layer.n_tau == 24 and layer.params.n_cols == 16
+    ns = 1.0 - (np.abs(np.arange(-0.028, 0.065, 0.004)) * 3.0)
+    assert np.max(np.abs(np.array(layer.params.norm_snr[:24]) - ns)) < 1e-6
+    cfg.update(tau_start='0.0', tau_end='0.05', tau_step='0.01')            # 5 taus: no norm_snr (signals.py:117-121)
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    assert layer.n_tau == 5 and layer.params.norm_snr[0] == 0.0
+
+
+def test_layer_argument_handling(qb):
+    cfg = o.default_config()
+    assert qb.SignalGenerationLayer(cfg, 'True', 'False')._include_blood is False
+    with pytest.raises(ValueError):
+        qb.SignalGenerationLayer(cfg, 'yes', True)
+    with pytest.raises(NotImplementedError):
+        qb.SignalGenerationLayer(cfg, True, True, misaligned_prob=0.1)
+    import torch
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    with pytest.raises(AssertionError):
+        layer(torch.zeros(4, 3))
+    with pytest.raises(qb.QboldError):                                      # no CPU path, ever
+        qb.SignalGenerationLayer(dict(cfg, simulate_noise='False'), True, True)(torch.zeros(4, 2))
+    assert abs(qb.SignalGenerationLayer.calculate_dw_static(1.0, 0.34, 2.67513e8, 3.0, 2.64e-7) - 301.743275) < 1e-5
+
+
+def test_missing_library_fails_loudly(qb, monkeypatch, tmp_path):
+    monkeypatch.setattr(qb._lib, '_lib', None)
+    monkeypatch.setattr(qb._lib, 'LIB_PATH', str(tmp_path / 'libqbold.so'))
+    with pytest.raises(qb.QboldError, match='no CPU or PyTorch fallback'):
+        qb._lib.lib()
+
+
+def test_config_two_tier_loading(qb):
+    p = qb.load_system_parameters()
+    assert isinstance(p['gamma'], str) and float(p['gamma']) == 2.67513e8 and p['simulate_noise'] == 'True'
+    for k, v in o.default_config().items():
+        assert float(p[k]) == float(v) if k not in ('simulate_noise', 'tau_weighted') else p[k] == v
+    p['simulate_noise'] = 'False'                                            # callers mutate in place (train.py:256)
+    assert p['simulate_noise'] == 'False'
+    a = qb.optimal_arguments()
+    assert (a.no_units, a.student_t_df, a.use_mvg, a.multi_image_normalisation, a.predict_log_data) == \
+        (60, 200, True, False, False)
+    assert a.save_directory == 'optimal' and a.name == 'optimal'            # extra yaml keys are added
+    # typing rule of train.py:473-480: truthy defaults are cast, falsy defaults take the yaml value untyped
+    args = qb.apply_yaml_overrides({'a': 1, 'b': 0.0, 'c': True}, {'a': '7', 'b': '3', 'c': 0, 'new': [1]})
+    assert args == {'a': 7, 'b': '3', 'c': False, 'new': [1]}
+    t = qb.EncoderTrainer(p, student_t_df=200)
+    assert t._se_idx == 2
+
+
+def test_philox_known_answers_and_streams():
+    # Random123 kat_vectors, philox4x32-10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(*ctr, *key)
+        assert tuple(int(x) for x in got) == want
+    idx = np.arange(100000)
+    n0, n1 = philox.normal_pair(11, idx, philox.STREAM_REPARAM)
+    assert abs(n0.mean()) < 0.01 and abs(n0.std() - 1) < 0.01 and abs(np.corrcoef(n0, n1)[0, 1]) < 0.01
+    u = philox.snr_u01(11, idx)
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    # sharding invariance: the draw of voxel i does not depend on which slice it is generated in
+    a = philox.reparam_eps(5, np.arange(1000, 2000))
+    b = philox.reparam_eps(5, np.arange(0, 4000))[1000:2000]
+    assert np.array_equal(a, b)
+    for n in (1, 2, 529, 1000003):
+        m = min(n, 5000)
+        x = philox.feistel_permute(np.arange(n)[:m] if n > m else np.arange(n), n, 99)
+        assert x.min() >= 0 and x.max() < n and len(np.unique(x)) == len(x)
