@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads) k_kl(const float* __restrict__ q, co
     }
 }
 
-template <bool HAS_PRIOR>
+template <bool HAS_PRIOR, bool MULTI>
 __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ QboldParams P,
                                                    const float* __restrict__ q, const float* __restrict__ sigma,
                                                    const float* __restrict__ y, const float* __restrict__ mask,
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ Qbold
         const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
         float I = 0.f, D = 0.f;
         if (P.full_model) {
-            tissue_integrals<true>(P, s, tc0, vp.dw, lane, my_col, I, D);
+            tissue_integrals<true, MULTI>(P, s, tc0, vp.dw, lane, my_col, I, D);
             if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
         }
         const TauSignal ts = tau_signal<true>(P, vp, my_tau, my_b, I, D);
@@ -459,21 +459,22 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
         return fail(QBOLD_EINVAL, "qbold_elbo_fused: null pointer");
     if (p->n_tau > 32) return fail(QBOLD_EINVAL, "qbold_elbo_fused: n_tau > 32");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool multi = p->n_cols > kColGroup;
+    const int64_t want = (n + 7) / 8;
+#define QB_LAUNCH_ELBO(HP, MU)                                                                                       \
+    do {                                                                                                              \
+        static int64_t grid_cache = 0;                                                                                \
+        const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo<HP, MU>, INT64_MAX / 64)); \
+        k_elbo<HP, MU><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(                                  \
+            *p, q, sigma, y, mask, HP ? prior : nullptr, eps, HP ? eps_kl : nullptr, seed, offset,                    \
+            HP ? kl_samples : 0, inv_mask_sum, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums);              \
+    } while (0)
     if (prior) {
-        static int64_t grid_cache = 0;
-        const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo<true>, INT64_MAX / 64));
-        const int64_t want = (n + 7) / 8;
-        k_elbo<true><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(
-            *p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, kl_weight, n, grad_q,
-            grad_sigma, nll_map, kl_map, sums);
+        if (multi) QB_LAUNCH_ELBO(true, true); else QB_LAUNCH_ELBO(true, false);
     } else {
-        static int64_t grid_cache = 0;
-        const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo<false>, INT64_MAX / 64));
-        const int64_t want = (n + 7) / 8;
-        k_elbo<false><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(
-            *p, q, sigma, y, mask, nullptr, eps, nullptr, seed, offset, 0, inv_mask_sum, kl_weight, n, grad_q,
-            grad_sigma, nll_map, kl_map, sums);
+        if (multi) QB_LAUNCH_ELBO(false, true); else QB_LAUNCH_ELBO(false, false);
     }
+#undef QB_LAUNCH_ELBO
     return after_launch("k_elbo");
 }
 

@@ -7,7 +7,7 @@
 namespace qb {
 
 // One warp per voxel (grid-stride).  BWD: also g_oef_dbv[n,2]; HCT: oef_dbv rows are (OEF,DBV,Hct).
-template <bool BWD, bool HCT>
+template <bool BWD, bool HCT, bool MULTI>
 __global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ QboldParams P,
                                                       const float* __restrict__ oef_dbv,
                                                       const float* __restrict__ g_signal,
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ Qb
 
         float I = 0.f, D = 0.f;
         if (P.full_model) {
-            tissue_integrals<BWD>(P, s, tc0, vp.dw, lane, my_col, I, D);
+            tissue_integrals<BWD, MULTI>(P, s, tc0, vp.dw, lane, my_col, I, D);
             if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
         }
         const TauSignal ts = tau_signal<BWD>(P, vp, my_tau, my_b, I, D);
@@ -53,12 +53,12 @@ __global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ Qb
     }
 }
 
-template <bool BWD, bool HCT>
-static int launch_forward(const QboldParams* p, const float* oef_dbv, const float* g, float* signal,
+template <bool BWD, bool HCT, bool MULTI>
+static int launch_forward_t(const QboldParams* p, const float* oef_dbv, const float* g, float* signal,
                           float* grad, int64_t n, cudaStream_t st) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_forward<BWD, HCT>, kThreads, 0) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_forward<BWD, HCT, MULTI>, kThreads, 0) !=
                 cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 1;
     }
@@ -66,8 +66,15 @@ static int launch_forward(const QboldParams* p, const float* oef_dbv, const floa
     int64_t grid = (int64_t)sm_count() * blocks_per_sm;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k_forward<BWD, HCT><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n);
+    k_forward<BWD, HCT, MULTI><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n);
     return after_launch("k_forward");
+}
+
+template <bool BWD, bool HCT>
+static int launch_forward(const QboldParams* p, const float* oef_dbv, const float* g, float* signal,
+                          float* grad, int64_t n, cudaStream_t st) {
+    return p->n_cols > kColGroup ? launch_forward_t<BWD, HCT, true>(p, oef_dbv, g, signal, grad, n, st)
+                                 : launch_forward_t<BWD, HCT, false>(p, oef_dbv, g, signal, grad, n, st);
 }
 
 }  // namespace qb

@@ -42,6 +42,7 @@ __host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t i, uint64_
     return x;
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ QboldParams P,
                                                        const float* __restrict__ oefs, int64_t n_oef,
                                                        const float* __restrict__ dbvs, int64_t n_dbv,
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ Q
         const VoxelPhys vp = voxel_phys<false>(P, oef, dbv, P.hct);
         float I = 0.f, D = 0.f;
         if (P.full_model) {
-            tissue_integrals<false>(P, s, tc0, vp.dw, lane, my_col, I, D);
+            tissue_integrals<false, MULTI>(P, s, tc0, vp.dw, lane, my_col, I, D);
             if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
         }
         const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, D);
@@ -165,15 +166,23 @@ extern "C" int qbold_generate(const QboldParams* p, const float* oefs, int64_t n
     int bits = 1;
     while (bits < 64 && (1ull << bits) < total) ++bits;
     const int half_bits = (bits + 1) / 2;
-    static int bps = 0;
-    if (bps == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate, kThreads, 0) != cudaSuccess || bps < 1))
-        bps = 1;
+    const bool multi = p->n_cols > kColGroup;
+    static int bps_cache[2] = {0, 0};
+    int& bps = bps_cache[multi ? 1 : 0];
+    if (bps == 0) {
+        const cudaError_t e = multi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate<true>, kThreads, 0)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate<false>, kThreads, 0);
+        if (e != cudaSuccess || bps < 1) bps = 1;
+    }
     int64_t grid = (int64_t)sm_count() * bps;
     const int64_t want = (count + 7) / 8;
     if (want < grid) grid = want;
-    k_generate<<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed,
-                                                                     half_bits, first, count, x, y3);
+    if (multi)
+        k_generate<true><<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(*p, oefs, n_oef, dbvs, n_dbv, perm,
+                                                                               seed, half_bits, first, count, x, y3);
+    else
+        k_generate<false><<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(*p, oefs, n_oef, dbvs, n_dbv, perm,
+                                                                                seed, half_bits, first, count, x, y3);
     return after_launch("k_generate");
 }
 

@@ -112,15 +112,26 @@ __device__ __forceinline__ void tissue_group(const QuadSmem& s, const TauCols& t
     if (BWD) td = butterfly8(accD, lane);
 }
 
-template <bool BWD>
+// MULTI = false: at most 8 distinct |tau| columns (the 11-tau optimal.yaml grid): one group, nothing but
+// tc0 is read.  MULTI = true (e.g. the 24-tau grid, 16 columns): further groups are read from P.
+template <bool BWD, bool MULTI>
 __device__ __forceinline__ void tissue_integrals(const QboldParams& P, const QuadSmem& s, const TauCols& tc0,
                                                  float dw, int lane, int my_col, float& I_out, float& D_out) {
+    if (!MULTI) {
+        float ti, td;
+        tissue_group<BWD>(s, tc0, dw, lane, ti, td);
+        const int src = butterfly8_src_lane(my_col & 7);
+        const float vi = __shfl_sync(kFull, ti, src);
+        const float vd = BWD ? __shfl_sync(kFull, td, src) : 0.f;
+        I_out = (my_col >= 0) ? vi : 0.f;
+        D_out = (my_col >= 0) ? vd : 0.f;
+        return;
+    }
     I_out = 0.f;
     D_out = 0.f;
     for (int g = 0; g * kColGroup < P.n_cols; ++g) {
         float ti, td;
-        TauCols tc = tc0;
-        if (g > 0) tc = load_tau_cols(P, g);
+        const TauCols tc = load_tau_cols(P, g);
         tissue_group<BWD>(s, tc, dw, lane, ti, td);
         const int c = my_col - g * kColGroup;
         const bool mine = (c >= 0) && (c < kColGroup);

@@ -2,11 +2,12 @@
 """Fit the polynomial kernels used by the device Bessel evaluation and write
 qbold_vi_b200/csrc/bessel_coef.h.
 
-Device algorithm (qbold_vi_b200/csrc/bessel.cuh), split at X_SPLIT:
-  small |x| <= X_SPLIT : 1 - J0(x) = z * P0(z),  J1(x) = x * P1(z),  z = x^2
-                         (no cancellation: the quadrature needs 1 - J0, not J0)
-  big   |x| >  X_SPLIT : J_n(x) = rsqrt(x) * A_n(w) * cos(x - (2n+1)pi/4 + q * F_n(w)),
-                         q = 1/x, w = q^2  (modulus / phase form; A_n, F_n polynomials in w)
+Device algorithm (qbold_vi_b200/csrc/bessel.cuh), three ranges:
+  small x <= X1      : 1 - J0(x) = z * S0(z),  J1(x) = x * S1(z),  z = x^2
+                       (no cancellation: the quadrature needs 1 - J0, not J0)
+  mid   X1 < x <= X2 : 1 - J0 and J1 as polynomials in t = x - XC (XC = (X1+X2)/2)
+  big   x > X2       : J_n(x) = rsqrt(x) * A_n(w) * cos(x - (2n+1)pi/4 + q * F_n(w)),
+                       q = 1/x, w = q^2  (modulus / phase form; A_n, F_n polynomials in w)
   cos on [-pi/2, pi/2] after a 2-constant Cody-Waite reduction mod pi: polynomial in r^2.
 
 These are our own near-minimax fits (Chebyshev interpolation in float64, rounded to
@@ -20,13 +21,16 @@ import numpy as np
 import scipy.special as sp
 from numpy.polynomial import chebyshev as C, polynomial as P
 
-X_SPLIT = 3.0
-SMALL_FIT_HI = 3.25          # fit a little beyond the split
-BIG_FIT_LO = 2.75
+X1, X2 = 3.0, 9.0
+XC = 0.5 * (X1 + X2)
+SMALL_FIT_HI = 3.1           # fit a little beyond the split
+MID_FIT = (2.95, 9.05)
+BIG_FIT_LO = 8.9
 DEG_SMALL = 5
-DEG_AMP = 4
-DEG_PHASE = 4
-DEG_COS = 5                  # in r^2, |r| <= pi/2 + 0.06
+DEG_MID = 11
+DEG_AMP = 2
+DEG_PHASE = 2
+DEG_COS = 4                  # in r^2, |r| <= pi/2 + 0.02
 
 
 def cheb_fit(f, lo, hi, deg, n=6000):
@@ -77,6 +81,9 @@ def main():
     f1 = lambda z: np.where(z > 1e-10, sp.j1(np.sqrt(np.maximum(z, 0))) / np.sqrt(np.maximum(z, 1e-300)), 0.5 - z / 16)
     out['S0'] = cheb_fit(f0, 0.0, SMALL_FIT_HI ** 2, DEG_SMALL)
     out['S1'] = cheb_fit(f1, 0.0, SMALL_FIT_HI ** 2, DEG_SMALL)
+    # ---- mid
+    out['M0'] = cheb_fit(lambda t: 1 - sp.j0(t + XC), MID_FIT[0] - XC, MID_FIT[1] - XC, DEG_MID)
+    out['M1'] = cheb_fit(lambda t: sp.j1(t + XC), MID_FIT[0] - XC, MID_FIT[1] - XC, DEG_MID)
     # ---- big
     wmax = 1.0 / BIG_FIT_LO ** 2
     for order in (0, 1):
@@ -85,12 +92,12 @@ def main():
         out['A%d' % order] = cheb_fit(fa, 1e-7, wmax, DEG_AMP)
         out['F%d' % order] = cheb_fit(fp, 1e-7, wmax, DEG_PHASE)
     # ---- cos(r), |r| <= pi/2 + margin, polynomial in s = r^2
-    rmax = np.pi / 2 + 0.06
+    rmax = np.pi / 2 + 0.02
     fc = lambda s: np.cos(np.sqrt(np.maximum(s, 0)))
     out['CS'] = cheb_fit(fc, 0.0, rmax ** 2, DEG_COS)
 
     # ---- report float32 accuracy of the composed evaluation
-    x = np.linspace(1e-4, X_SPLIT, 300001).astype(np.float32)
+    x = np.linspace(1e-4, X1, 300001).astype(np.float32)
     xd = x.astype(np.float64)
     z = (x * x).astype(np.float32)
     v0 = z * horner32(out['S0'], z)
@@ -98,7 +105,12 @@ def main():
     e0 = np.abs(v0 - (1 - sp.j0(xd)))
     print('small: 1-J0 abs %.2e rel %.2e | J1 abs %.2e' % (e0.max(), (e0 / (1 - sp.j0(xd))).max(),
                                                          np.abs(v1 - sp.j1(xd)).max()))
-    x = np.linspace(X_SPLIT, 32, 600001).astype(np.float32)
+    x = np.linspace(X1, X2, 300001).astype(np.float32)
+    xd = x.astype(np.float64)
+    t = (x - np.float32(XC)).astype(np.float32)
+    print('mid  : 1-J0 abs %.2e | J1 abs %.2e' % (np.abs(horner32(out['M0'], t) - (1 - sp.j0(xd))).max(),
+                                                 np.abs(horner32(out['M1'], t) - sp.j1(xd)).max()))
+    x = np.linspace(X2, 40, 600001).astype(np.float32)
     xd = x.astype(np.float64)
     r = (1 / np.sqrt(xd)).astype(np.float32)
     q = (r * r).astype(np.float32)
@@ -125,11 +137,14 @@ def main():
     with open(path, 'w') as f:
         f.write('// GENERATED by tools/fit_bessel.py -- do not edit.\n')
         f.write('// Near-minimax float32 polynomial kernels for 1-J0 / J1 (see bessel.cuh).\n#pragma once\n')
-        f.write('#define QB_X_SPLIT %s\n' % flit(X_SPLIT))
+        f.write('namespace qb {\nnamespace coef {\n')
+        f.write('constexpr float kX1 = %s, kX2 = %s, kXC = %s;\n' % (flit(X1), flit(X2), flit(XC)))
         for name, coef in out.items():
             f.write('// %s: ascending powers, degree %d\n' % (name, len(coef) - 1))
-            for i, c in enumerate(coef):
-                f.write('#define QB_%s_%d %s\n' % (name, i, flit(c)))
+            f.write('struct %s {\n    static constexpr int N = %d;\n    __host__ __device__ static constexpr float c(int i) {\n'
+                    '        constexpr float v[%d] = {%s};\n        return v[i];\n    }\n};\n'
+                    % (name, len(coef), len(coef), ', '.join(flit(c) for c in coef)))
+        f.write('}  // namespace coef\n}  // namespace qb\n')
     print('wrote', path)
 
 
