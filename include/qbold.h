@@ -33,7 +33,10 @@ extern "C" {
 #define QBOLD_MAX_TAU 32
 #define QBOLD_NQ 129              /* 2**7 + 1 Simpson nodes, signals.py:168 */
 #define QBOLD_NQ_PAD 132
-#define QBOLD_ABI_VERSION 1
+#define QBOLD_ABI_VERSION 2
+#define QBOLD_SCHED_PHASE_LEN 4       /* chunks (warp passes) per phase of the static lane schedule */
+#define QBOLD_SCHED_MAX_PHASES 10
+#define QBOLD_SCHED_MAX_ENTRIES (QBOLD_SCHED_MAX_PHASES * QBOLD_SCHED_PHASE_LEN * 32)
 
 #define QBOLD_OK 0
 #define QBOLD_EINVAL (-1)         /* bad argument (the reference would assert / raise) */
@@ -88,6 +91,18 @@ typedef struct QboldParams {
     float qu[QBOLD_NQ_PAD];            /* quadrature nodes u_k (tf.linspace)         signals.py:166-168 */
     float qc[QBOLD_NQ_PAD];            /* value weights  W_k g_k, qc[0]=0 (node 0 dead in FP32), qc[128]=0 */
     float qd[QBOLD_NQ_PAD];            /* derivative weights W_k g_k u_k (node 0 live) */
+    /* Static lane schedule of the quadrature (n_cols <= 8; sched_phases == 0 -> column-major path).
+     * All (column j, node k>=1) pairs are dealt to the 32 lanes in passes ("chunks") ordered by
+     * m = (|tau_j|/tau_ref) * u_k, so that within one pass every lane evaluates the Bessel pair at a
+     * similar argument x = A*m (A = 1.5*tau_ref*dw) and the small/mid/large branch is warp-uniform.
+     * A lane keeps one column for a whole phase (QBOLD_SCHED_PHASE_LEN passes); see DESIGN.md 3. */
+    int32_t sched_phases;
+    float tau_ref;                                   /* max |tau| */
+    float sched_ph_min[16];                          /* min / max m over the live entries of a phase */
+    float sched_ph_max[16];
+    float sched_m[QBOLD_SCHED_MAX_ENTRIES];          /* entry [phase][pass][lane]: m */
+    float sched_w[QBOLD_SCHED_MAX_ENTRIES];          /*                            Simpson weight c_k (0 = idle) */
+    uint8_t sched_col[QBOLD_SCHED_MAX_PHASES * 32];  /* [phase][lane]: column (bits 0-2) | 0x80 = first visit */
 } QboldParams;
 
 int qbold_abi_version(void);

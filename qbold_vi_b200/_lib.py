@@ -16,7 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libqbold.so')
 MAX_TAU = 32
 NQ_PAD = 132
-ABI_VERSION = 1
+ABI_VERSION = 2
+SCHED_MAX_PHASES = 10
+SCHED_MAX_ENTRIES = SCHED_MAX_PHASES * 4 * 32
 
 
 class QboldError(RuntimeError):
@@ -40,7 +42,11 @@ class QboldParams(C.Structure):
                                           'node0_c', 'pad0')] +
                 [('tau', C.c_float * MAX_TAU), ('blood_b', C.c_float * MAX_TAU), ('abs_tau', C.c_float * MAX_TAU),
                  ('col_of_tau', C.c_int32 * MAX_TAU), ('norm_snr', C.c_float * MAX_TAU),
-                 ('qu', C.c_float * NQ_PAD), ('qc', C.c_float * NQ_PAD), ('qd', C.c_float * NQ_PAD)])
+                 ('qu', C.c_float * NQ_PAD), ('qc', C.c_float * NQ_PAD), ('qd', C.c_float * NQ_PAD),
+                 ('sched_phases', C.c_int32), ('tau_ref', C.c_float),
+                 ('sched_ph_min', C.c_float * 16), ('sched_ph_max', C.c_float * 16),
+                 ('sched_m', C.c_float * SCHED_MAX_ENTRIES), ('sched_w', C.c_float * SCHED_MAX_ENTRIES),
+                 ('sched_col', C.c_uint8 * (SCHED_MAX_PHASES * 32))])
 
 
 _P = C.POINTER

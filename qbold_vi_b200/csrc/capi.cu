@@ -48,6 +48,102 @@ int sm_count() {
 // the argument is first converted to float32, the result is the float32 nearest exp().
 static float expf_of(double x) { return (float)std::exp((double)(float)x); }
 
+// Static lane schedule (see QboldParams::sched_* in include/qbold.h and DESIGN.md 3).
+// Greedy n-way merge of the per-column node sequences by m = r_j*u_k decides, for each phase of
+// QBOLD_SCHED_PHASE_LEN passes, how many lanes each column gets (largest-remainder rounding of its
+// share of the next 4*32 entries); lanes are grouped by column, each column consumes its nodes in
+// order.  Lagging columns get more lanes in the next phase, so the m-spread inside a pass stays small.
+static void build_schedule(QboldParams& P) {
+    P.sched_phases = 0;
+    const int nc = P.n_cols, L = 32, PL = QBOLD_SCHED_PHASE_LEN, last = QBOLD_NQ - 2;   // live nodes 1..127
+    if (nc < 1 || nc > 8) return;
+    double tref = 0.0;
+    for (int j = 0; j < nc; ++j) tref = std::fmax(tref, (double)P.abs_tau[j]);
+    P.tau_ref = (float)tref;
+    double r[8];
+    int nxt[8];
+    bool seen[32][8] = {};
+    int remaining = nc * last;
+    for (int j = 0; j < nc; ++j) {
+        r[j] = (double)P.abs_tau[j] / tref;
+        nxt[j] = 1;
+    }
+    int phase = 0;
+    while (remaining > 0 && phase < QBOLD_SCHED_MAX_PHASES) {
+        int tmp[8], cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, total = 0;
+        for (int j = 0; j < nc; ++j) tmp[j] = nxt[j];
+        for (int i = 0; i < PL * L; ++i) {
+            int best = -1;
+            double bm = 0.0;
+            for (int j = 0; j < nc; ++j)
+                if (tmp[j] <= last) {
+                    const double m = r[j] * (double)P.qu[tmp[j]];
+                    if (best < 0 || m < bm) {
+                        best = j;
+                        bm = m;
+                    }
+                }
+            if (best < 0) break;
+            ++tmp[best];
+            ++cnt[best];
+            ++total;
+        }
+        int n[8], sum = 0;
+        double rem[8];
+        for (int j = 0; j < nc; ++j) {
+            const double q = (double)cnt[j] * L / (double)total;
+            n[j] = (int)std::floor(q);
+            rem[j] = cnt[j] > 0 ? q - n[j] : -1.0;
+            sum += n[j];
+        }
+        while (sum < L) {
+            int best = 0;
+            for (int j = 1; j < nc; ++j)
+                if (rem[j] > rem[best]) best = j;
+            ++n[best];
+            rem[best] = -1.0;
+            ++sum;
+        }
+        int lane_col[32], lane = 0;
+        for (int j = 0; j < nc; ++j)
+            for (int i = 0; i < n[j] && lane < L; ++i) lane_col[lane++] = j;
+        for (; lane < L; ++lane) lane_col[lane] = 0;
+        double pmin = 1e300, pmax = 0.0;
+        for (int c = 0; c < PL; ++c)
+            for (int l = 0; l < L; ++l) {
+                const int j = lane_col[l], e = (phase * PL + c) * L + l;
+                if (nxt[j] <= last) {
+                    const double m = r[j] * (double)P.qu[nxt[j]];
+                    P.sched_m[e] = (float)m;
+                    P.sched_w[e] = P.qc[nxt[j]];
+                    pmin = std::fmin(pmin, m);
+                    pmax = std::fmax(pmax, m);
+                    ++nxt[j];
+                    --remaining;
+                } else {
+                    P.sched_m[e] = 0.f;
+                    P.sched_w[e] = 0.f;
+                }
+            }
+        for (int l = 0; l < L; ++l) {
+            const int j = lane_col[l];
+            P.sched_col[phase * L + l] = (uint8_t)(j | (seen[l][j] ? 0 : 0x80));
+            seen[l][j] = true;
+        }
+        // idle entries (weight 0) take the phase's largest m, so they sit in the same argument range as the
+        // live ones (m = 0 would feed rsqrt(0) to the large-argument branch)
+        for (int c = 0; c < PL; ++c)
+            for (int l = 0; l < L; ++l) {
+                const int e = (phase * PL + c) * L + l;
+                if (P.sched_w[e] == 0.f) P.sched_m[e] = (float)pmax;
+            }
+        P.sched_ph_min[phase] = (float)(pmin > 1e200 ? 0.0 : pmin * (1.0 - 1e-6));
+        P.sched_ph_max[phase] = (float)(pmax * (1.0 + 1e-6));
+        ++phase;
+    }
+    if (remaining == 0) P.sched_phases = phase;   // else: keep 0 -> column-major fallback
+}
+
 }  // namespace qb
 
 using namespace qb;
@@ -147,6 +243,8 @@ extern "C" int qbold_params_init(QboldParams* out, const QboldPhysics* ph, const
     }
     P.node0_c = P.qc[0];
     P.qc[0] = 0.0f;   // node 0: exactly 0 in the reference's float32 value (handled by node0_value())
+
+    build_schedule(P);
 
     // ---- default likelihood: optimal.yaml (Gaussian, single-image normalisation)
     P.se_idx = 0;

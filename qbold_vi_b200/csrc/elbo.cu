@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads) k_kl(const float* __restrict__ q, co
     }
 }
 
-template <bool HAS_PRIOR, bool MULTI>
+template <bool HAS_PRIOR, int PATH>
 __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ QboldParams P,
                                                    const float* __restrict__ q, const float* __restrict__ sigma,
                                                    const float* __restrict__ y, const float* __restrict__ mask,
@@ -211,7 +211,11 @@ __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ Qbold
                                                    float* __restrict__ nll_map, float* __restrict__ kl_map,
                                                    double* __restrict__ sums) {
     __shared__ QuadSmem s;
-    if (P.full_model) load_quad_tables(P, s);
+    __shared__ SchedSmem ss;
+    if (P.full_model) {
+        if (PATH == kSched) load_sched(P, ss);
+        else load_quad_tables(P, s);
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ Qbold
     const bool multi = P.multi_image_normalisation != 0;
     const bool in_norm = multi ? (lane >= se - 1 && lane <= se + 1) : (lane == se);
     const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
-    const TauCols tc0 = load_tau_cols(P, 0);
+    const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
     const float df = P.student_t_df;
 
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
@@ -258,12 +262,9 @@ __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ Qbold
         }
         const Sample sm = draw(dq, ex, e0, e1);
         const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
-        float I = 0.f, D = 0.f;
-        if (P.full_model) {
-            tissue_integrals<true, MULTI>(P, s, tc0, vp.dw, lane, my_col, I, D);
-            if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
-        }
-        const TauSignal ts = tau_signal<true>(P, vp, my_tau, my_b, I, D);
+        float I = 0.f, dI = 0.f;
+        if (P.full_model) tissue_eval<true, PATH>(P, s, ss, qc, vp.dw, vp.dw_k, I, dI);
+        const TauSignal ts = tau_signal<true>(P, vp, my_tau, my_b, I, dI);
 
         // ---- fine_tune_loss_fn (model.py:527-568)
         const float yv = live ? __ldg(y + v * nt + lane) : 0.f;
@@ -459,7 +460,7 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
         return fail(QBOLD_EINVAL, "qbold_elbo_fused: null pointer");
     if (p->n_tau > 32) return fail(QBOLD_EINVAL, "qbold_elbo_fused: n_tau > 32");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool multi = p->n_cols > kColGroup;
+    const int path = p->sched_phases > 0 ? kSched : (p->n_cols > kColGroup ? kColsMulti : kCols);
     const int64_t want = (n + 7) / 8;
 #define QB_LAUNCH_ELBO(HP, MU)                                                                                       \
     do {                                                                                                              \
@@ -470,9 +471,13 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
             HP ? kl_samples : 0, inv_mask_sum, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums);              \
     } while (0)
     if (prior) {
-        if (multi) QB_LAUNCH_ELBO(true, true); else QB_LAUNCH_ELBO(true, false);
+        if (path == kSched) QB_LAUNCH_ELBO(true, kSched);
+        else if (path == kCols) QB_LAUNCH_ELBO(true, kCols);
+        else QB_LAUNCH_ELBO(true, kColsMulti);
     } else {
-        if (multi) QB_LAUNCH_ELBO(false, true); else QB_LAUNCH_ELBO(false, false);
+        if (path == kSched) QB_LAUNCH_ELBO(false, kSched);
+        else if (path == kCols) QB_LAUNCH_ELBO(false, kCols);
+        else QB_LAUNCH_ELBO(false, kColsMulti);
     }
 #undef QB_LAUNCH_ELBO
     return after_launch("k_elbo");

@@ -7,14 +7,18 @@
 namespace qb {
 
 // One warp per voxel (grid-stride).  BWD: also g_oef_dbv[n,2]; HCT: oef_dbv rows are (OEF,DBV,Hct).
-template <bool BWD, bool HCT, bool MULTI>
+template <bool BWD, bool HCT, int PATH>
 __global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ QboldParams P,
                                                       const float* __restrict__ oef_dbv,
                                                       const float* __restrict__ g_signal,
                                                       float* __restrict__ signal,
                                                       float* __restrict__ g_oef_dbv, int64_t n) {
     __shared__ QuadSmem s;
-    if (P.full_model) load_quad_tables(P, s);
+    __shared__ SchedSmem ss;
+    if (P.full_model) {
+        if (PATH == kSched) load_sched(P, ss);
+        else load_quad_tables(P, s);
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -26,7 +30,7 @@ __global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ Qb
     const float my_tau = live ? P.tau[lane] : 0.f;
     const float my_b = live ? P.blood_b[lane] : 0.f;
     constexpr int W = HCT ? 3 : 2;
-    const TauCols tc0 = load_tau_cols(P, 0);
+    const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
 
     for (int64_t v = warp; v < n; v += nwarps) {
         const float oef = __ldg(oef_dbv + v * W);
@@ -36,12 +40,9 @@ __global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ Qb
         if (BWD && g_signal != nullptr && live) gs = __ldg(g_signal + v * nt + lane);
         const VoxelPhys vp = voxel_phys<HCT>(P, oef, dbv, hct);
 
-        float I = 0.f, D = 0.f;
-        if (P.full_model) {
-            tissue_integrals<BWD, MULTI>(P, s, tc0, vp.dw, lane, my_col, I, D);
-            if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
-        }
-        const TauSignal ts = tau_signal<BWD>(P, vp, my_tau, my_b, I, D);
+        float I = 0.f, dI = 0.f;
+        if (P.full_model) tissue_eval<BWD, PATH>(P, s, ss, qc, vp.dw, vp.dw_k, I, dI);
+        const TauSignal ts = tau_signal<BWD>(P, vp, my_tau, my_b, I, dI);
         if (live && signal != nullptr) signal[v * nt + lane] = ts.S;
         if (BWD) {
             float go = live ? gs * ts.dS_doef : 0.f;
@@ -53,12 +54,12 @@ __global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ Qb
     }
 }
 
-template <bool BWD, bool HCT, bool MULTI>
+template <bool BWD, bool HCT, int PATH>
 static int launch_forward_t(const QboldParams* p, const float* oef_dbv, const float* g, float* signal,
                           float* grad, int64_t n, cudaStream_t st) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_forward<BWD, HCT, MULTI>, kThreads, 0) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_forward<BWD, HCT, PATH>, kThreads, 0) !=
                 cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 1;
     }
@@ -66,15 +67,16 @@ static int launch_forward_t(const QboldParams* p, const float* oef_dbv, const fl
     int64_t grid = (int64_t)sm_count() * blocks_per_sm;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k_forward<BWD, HCT, MULTI><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n);
+    k_forward<BWD, HCT, PATH><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n);
     return after_launch("k_forward");
 }
 
 template <bool BWD, bool HCT>
 static int launch_forward(const QboldParams* p, const float* oef_dbv, const float* g, float* signal,
                           float* grad, int64_t n, cudaStream_t st) {
-    return p->n_cols > kColGroup ? launch_forward_t<BWD, HCT, true>(p, oef_dbv, g, signal, grad, n, st)
-                                 : launch_forward_t<BWD, HCT, false>(p, oef_dbv, g, signal, grad, n, st);
+    if (p->sched_phases > 0) return launch_forward_t<BWD, HCT, kSched>(p, oef_dbv, g, signal, grad, n, st);
+    return p->n_cols > kColGroup ? launch_forward_t<BWD, HCT, kColsMulti>(p, oef_dbv, g, signal, grad, n, st)
+                                 : launch_forward_t<BWD, HCT, kCols>(p, oef_dbv, g, signal, grad, n, st);
 }
 
 }  // namespace qb

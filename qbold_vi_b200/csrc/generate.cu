@@ -42,7 +42,7 @@ __host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t i, uint64_
     return x;
 }
 
-template <bool MULTI>
+template <int PATH>
 __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ QboldParams P,
                                                        const float* __restrict__ oefs, int64_t n_oef,
                                                        const float* __restrict__ dbvs, int64_t n_dbv,
@@ -50,7 +50,11 @@ __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ Q
                                                        int half_bits, int64_t first, int64_t count,
                                                        float* __restrict__ x, float* __restrict__ y3) {
     __shared__ QuadSmem s;
-    if (P.full_model) load_quad_tables(P, s);
+    __shared__ SchedSmem ss;
+    if (P.full_model) {
+        if (PATH == kSched) load_sched(P, ss);
+        else load_quad_tables(P, s);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ Q
     const int my_col = live ? P.col_of_tau[lane] : -1;
     const float my_tau = live ? P.tau[lane] : 0.f;
     const float my_b = live ? P.blood_b[lane] : 0.f;
-    const TauCols tc0 = load_tau_cols(P, 0);
+    const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
     const uint64_t total = (uint64_t)n_oef * (uint64_t)n_dbv;
 
     for (int64_t v = warp; v < count; v += nwarps) {
@@ -74,12 +78,9 @@ __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ Q
         }
         if (x == nullptr) continue;
         const VoxelPhys vp = voxel_phys<false>(P, oef, dbv, P.hct);
-        float I = 0.f, D = 0.f;
-        if (P.full_model) {
-            tissue_integrals<false, MULTI>(P, s, tc0, vp.dw, lane, my_col, I, D);
-            if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
-        }
-        const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, D);
+        float I = 0.f, dI = 0.f;
+        if (P.full_model) tissue_eval<false, PATH>(P, s, ss, qc, vp.dw, vp.dw_k, I, dI);
+        const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, dI);
         if (live) x[v * nt + lane] = ts.S;
     }
 }
@@ -166,23 +167,29 @@ extern "C" int qbold_generate(const QboldParams* p, const float* oefs, int64_t n
     int bits = 1;
     while (bits < 64 && (1ull << bits) < total) ++bits;
     const int half_bits = (bits + 1) / 2;
-    const bool multi = p->n_cols > kColGroup;
-    static int bps_cache[2] = {0, 0};
-    int& bps = bps_cache[multi ? 1 : 0];
+    const int path = p->sched_phases > 0 ? kSched : (p->n_cols > kColGroup ? kColsMulti : kCols);
+    static int bps_cache[3] = {0, 0, 0};
+    int& bps = bps_cache[path];
     if (bps == 0) {
-        const cudaError_t e = multi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate<true>, kThreads, 0)
-                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate<false>, kThreads, 0);
+        cudaError_t e;
+        if (path == kSched) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate<kSched>, kThreads, 0);
+        else if (path == kCols) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate<kCols>, kThreads, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_generate<kColsMulti>, kThreads, 0);
         if (e != cudaSuccess || bps < 1) bps = 1;
     }
     int64_t grid = (int64_t)sm_count() * bps;
     const int64_t want = (count + 7) / 8;
     if (want < grid) grid = want;
-    if (multi)
-        k_generate<true><<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(*p, oefs, n_oef, dbvs, n_dbv, perm,
-                                                                               seed, half_bits, first, count, x, y3);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (path == kSched)
+        k_generate<kSched><<<(unsigned)grid, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits,
+                                                                first, count, x, y3);
+    else if (path == kCols)
+        k_generate<kCols><<<(unsigned)grid, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits,
+                                                               first, count, x, y3);
     else
-        k_generate<false><<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(*p, oefs, n_oef, dbvs, n_dbv, perm,
-                                                                                seed, half_bits, first, count, x, y3);
+        k_generate<kColsMulti><<<(unsigned)grid, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed,
+                                                                    half_bits, first, count, x, y3);
     return after_launch("k_generate");
 }
 

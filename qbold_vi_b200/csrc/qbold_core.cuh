@@ -206,16 +206,16 @@ struct TauSignal {
     float dS_ddbv;
 };
 
+// I = tissue integral of this tau, dI_doef = its derivative w.r.t. OEF (BWD).
 template <bool BWD>
 __device__ __forceinline__ TauSignal tau_signal(const QboldParams& P, const VoxelPhys& v, float tau,
-                                                float blood_b, float I, float D) {
+                                                float blood_b, float I, float dI_doef) {
     TauSignal r;
     float st, dst_doef = 0.f, dst_ddbv = 0.f;
     if (P.full_model) {
         st = expf(-v.dbv * I) * P.e_tissue;
         if (BWD) {
-            // dI/doef = D * da/doef, a = 1.5 |tau| dw
-            dst_doef = -v.dbv * st * (D * (1.5f * fabsf(tau)) * v.dw_k);
+            dst_doef = -v.dbv * st * dI_doef;
             dst_ddbv = -I * st;
         }
     } else {
@@ -246,6 +246,239 @@ __device__ __forceinline__ float node0_value(const QboldParams& P, float a) {
     const float z = __fmul_rn(x0, x0);
     const float j = __fsub_rn(1.0f, __fmul_rn(0.25f, z));
     return P.node0_c * __fsub_rn(1.0f, j);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scheduled path (n_cols <= 8): the static lane schedule of QboldParams::sched_* (built on the host).
+// Every pass hands each lane one (column, node) pair with a similar Bessel argument x = A*m, so a
+// whole phase of 4 passes is usually in ONE argument range and runs branch-free straight-line code;
+// a lane accumulates a single column per phase and flushes into its private shared-memory slot
+// [column][lane] at the phase end (first visit stores, later visits add -- no per-voxel clearing).
+enum QuadPath { kSched = 0, kCols = 1, kColsMulti = 2 };
+
+struct SchedSmem {
+    float2 mw[QBOLD_SCHED_MAX_ENTRIES];                  // (m, weight) per [phase][pass][lane]
+    unsigned char col[QBOLD_SCHED_MAX_PHASES * 32];
+    float slots[8 /*warps*/][2][8][32];                  // [warp][I|D][column][lane]
+};
+
+__device__ __forceinline__ void load_sched(const QboldParams& P, SchedSmem& s) {
+    const int n = P.sched_phases * QBOLD_SCHED_PHASE_LEN * 32;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s.mw[i] = make_float2(P.sched_m[i], P.sched_w[i]);
+    for (int i = threadIdx.x; i < P.sched_phases * 32; i += blockDim.x) s.col[i] = P.sched_col[i];
+    float* z = &s.slots[0][0][0][0];
+    for (int i = threadIdx.x; i < 8 * 2 * 8 * 32; i += blockDim.x) z[i] = 0.f;
+}
+
+// Shared-memory accesses of the scheduled path use explicit 32-bit shared addresses: one LDS/STS with a
+// register base + immediate offset, no generic-to-shared address arithmetic inside the voxel loop.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f1(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+template <bool BWD>
+__device__ __forceinline__ void acc_small(float x, float w, float& accI, float& accS) {
+    const float z = x * x;
+    const float wz = w * z;
+    accI = fmaf(wz, horner<coef::S0>(z), accI);                  // w * (1 - J0) = w z S0(z)
+    if (BWD) accS = fmaf(wz, horner<coef::S1>(z), accS);         // w * x J1 = w z S1(z)   (scaled by 1/A later)
+}
+
+template <bool BWD>
+__device__ __forceinline__ void acc_mid(float x, float2 e, float& accI, float& accB) {
+    float f0, j1 = 0.f;
+    bessel_mid<BWD>(x, f0, j1);
+    accI = fmaf(e.y, f0, accI);
+    if (BWD) accB = fmaf(e.y * e.x, j1, accB);                   // w * m * J1
+}
+
+template <bool BWD>
+__device__ __forceinline__ void acc_big(float x, float2 e, float& accI, float& accB) {
+    float f0, j1 = 0.f;
+    bessel_big<BWD>(x, f0, j1);
+    accI = fmaf(e.y, f0, accI);
+    if (BWD) accB = fmaf(e.y * e.x, j1, accB);
+}
+
+// Per-warp shared addresses of the scheduled path, computed once per kernel.
+struct SchedAddr {
+    unsigned mw;      // &mw[lane]
+    unsigned col;     // &col[lane]
+    unsigned slotI;   // &slots[warp][0][0][lane]
+    unsigned slotD;   // &slots[warp][1][0][lane]
+    unsigned redI;    // &slots[warp][0][lane >> 2][(lane & 3) * 8]
+    unsigned redD;
+};
+
+__device__ __forceinline__ SchedAddr sched_addr(const SchedSmem& s, int lane, int warp_in_cta) {
+    SchedAddr a;
+    a.mw = smem_addr(&s.mw[lane]);
+    a.col = smem_addr(&s.col[lane]);
+    a.slotI = smem_addr(&s.slots[warp_in_cta][0][0][lane]);
+    a.slotD = smem_addr(&s.slots[warp_in_cta][1][0][lane]);
+    a.redI = smem_addr(&s.slots[warp_in_cta][0][lane >> 2][(lane & 3) * 8]);
+    a.redD = smem_addr(&s.slots[warp_in_cta][1][lane >> 2][(lane & 3) * 8]);
+    return a;
+}
+
+// Returns for lane t < n_tau: I = sum_{k>=1} c_k (1 - J0(a_t u_k)) and
+// Dm = sum_{k>=1} c_k m_tk J1(a_t u_k)  (m = |tau_t|/tau_ref * u_k), so dI/dA = Dm with a_t u_k = A m.
+// ph_lo / ph_hi: this lane's phase bounds (lane p < sched_phases holds phase p), hoisted by the caller.
+template <bool BWD>
+__device__ __forceinline__ void tissue_sched(int nph, const SchedAddr& sa, float A, int lane, float ph_lo, float ph_hi,
+                                             int my_col, float& I_out, float& Dm_out) {
+    constexpr int kPassBytes = 32 * 8, kPhaseBytes = QBOLD_SCHED_PHASE_LEN * kPassBytes;
+    const bool is_ph = lane < nph;
+    const float lo = A * ph_lo, hi = A * ph_hi;
+    const unsigned PS = __ballot_sync(kFull, is_ph && hi <= coef::kX1);
+    const unsigned PM = __ballot_sync(kFull, is_ph && lo > coef::kX1 && hi <= coef::kX2);
+    const unsigned PB = __ballot_sync(kFull, is_ph && lo > coef::kX2);
+    const float invA = A > 0.f ? 1.0f / A : 0.f;
+    float accI = 0.f, accS = 0.f, accB = 0.f;
+    unsigned ea = sa.mw, ca = sa.col;
+#pragma unroll 1
+    for (int ph = 0; ph < nph; ++ph, ea += kPhaseBytes, ca += 32) {
+        const unsigned bit = 1u << ph;
+        if (PS & bit) {
+#pragma unroll
+            for (int c = 0; c < QBOLD_SCHED_PHASE_LEN; ++c) {
+                const float2 e = lds_f2(ea + c * kPassBytes);
+                acc_small<BWD>(A * e.x, e.y, accI, accS);
+            }
+        } else if (PM & bit) {
+#pragma unroll
+            for (int c = 0; c < QBOLD_SCHED_PHASE_LEN; ++c) {
+                const float2 e = lds_f2(ea + c * kPassBytes);
+                acc_mid<BWD>(A * e.x, e, accI, accB);
+            }
+        } else if (PB & bit) {
+#pragma unroll
+            for (int c = 0; c < QBOLD_SCHED_PHASE_LEN; ++c) {
+                const float2 e = lds_f2(ea + c * kPassBytes);
+                acc_big<BWD>(A * e.x, e, accI, accB);
+            }
+        } else {
+            // phase straddles a range boundary: decide per pass with warp votes (uniform branches); only the
+            // one pass that really straddles it takes the per-lane path
+#pragma unroll 1
+            for (int c = 0; c < QBOLD_SCHED_PHASE_LEN; ++c) {
+                const float2 e = lds_f2(ea + c * kPassBytes);
+                const float x = A * e.x;
+                const bool le1 = x <= coef::kX1, le2 = x <= coef::kX2;
+                if (__all_sync(kFull, le1)) {
+                    acc_small<BWD>(x, e.y, accI, accS);
+                } else if (__all_sync(kFull, !le1 && le2)) {
+                    acc_mid<BWD>(x, e, accI, accB);
+                } else if (__all_sync(kFull, !le2)) {
+                    acc_big<BWD>(x, e, accI, accB);
+                } else {
+                    if (le1) acc_small<BWD>(x, e.y, accI, accS);
+                    else if (le2) acc_mid<BWD>(x, e, accI, accB);
+                    else acc_big<BWD>(x, e, accI, accB);
+                }
+            }
+        }
+        // flush this phase's partial sums into the lane's private slot of its column
+        const unsigned cc = lds_u8(ca);
+        const unsigned off = (cc & 7u) << 7;                     // column * 32 floats
+        const bool first = cc & 0x80u;
+        float oldI = 0.f, oldD = 0.f;
+        if (!first) {
+            oldI = lds_f1(sa.slotI + off);
+            if (BWD) oldD = lds_f1(sa.slotD + off);
+        }
+        sts_f1(sa.slotI + off, oldI + accI);
+        accI = 0.f;
+        if (BWD) {
+            sts_f1(sa.slotD + off, oldD + fmaf(accS, invA, accB));
+            accS = accB = 0.f;
+        }
+    }
+    __syncwarp();
+    // column totals: the 4 lanes of column j = lane >> 2 sum the 32 per-lane slots of that column
+    const float4 a0 = lds_f4(sa.redI), a1 = lds_f4(sa.redI + 16);
+    float ti = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
+    ti += __shfl_xor_sync(kFull, ti, 1);
+    ti += __shfl_xor_sync(kFull, ti, 2);
+    float td = 0.f;
+    if (BWD) {
+        const float4 b0 = lds_f4(sa.redD), b1 = lds_f4(sa.redD + 16);
+        td = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
+        td += __shfl_xor_sync(kFull, td, 1);
+        td += __shfl_xor_sync(kFull, td, 2);
+    }
+    __syncwarp();                                        // slots are rewritten by the next voxel's first flush
+    const int src = (my_col & 7) << 2;
+    const float vi = __shfl_sync(kFull, ti, src);
+    const float vd = BWD ? __shfl_sync(kFull, td, src) : 0.f;
+    I_out = (my_col >= 0) ? vi : 0.f;
+    Dm_out = (my_col >= 0) ? vd : 0.f;
+}
+
+// One entry point for the three quadrature paths: returns (I, dI/dOEF) of this lane's tau.
+struct QuadCtx {
+    int lane, my_col, nph;
+    float my_tau, ph_lo, ph_hi;
+    float tau_ref15, node0_d;        // 1.5 * tau_ref;  qd[0] * 0.5 * u_0 * 1.5 |tau_t|  (node-0 derivative term)
+    SchedAddr sa;
+    TauCols tc0;
+};
+
+template <int PATH>
+__device__ __forceinline__ QuadCtx make_quad_ctx(const QboldParams& P, const SchedSmem& ss, int lane, int my_col,
+                                                 float my_tau) {
+    QuadCtx c;
+    c.lane = lane;
+    c.my_col = my_col;
+    c.my_tau = my_tau;
+    c.nph = P.sched_phases;
+    const bool ph = (PATH == kSched) && lane < P.sched_phases;
+    c.ph_lo = ph ? P.sched_ph_min[lane & 15] : 0.f;
+    c.ph_hi = ph ? P.sched_ph_max[lane & 15] : 0.f;
+    c.tau_ref15 = 1.5f * P.tau_ref;
+    c.node0_d = P.qd[0] * (0.5f * P.qu[0]) * (1.5f * fabsf(my_tau));
+    if (PATH == kSched) c.sa = sched_addr(ss, lane, threadIdx.x >> 5);
+    else c.tc0 = load_tau_cols(P, 0);
+    return c;
+}
+
+template <bool BWD, int PATH>
+__device__ __forceinline__ void tissue_eval(const QboldParams& P, const QuadSmem& qs, SchedSmem& ss, const QuadCtx& c,
+                                            float dw, float dw_k, float& I, float& dI_doef) {
+    if (PATH == kSched) {
+        const float A = c.tau_ref15 * dw;
+        float Dm;
+        tissue_sched<BWD>(c.nph, c.sa, A, c.lane, c.ph_lo, c.ph_hi, c.my_col, I, Dm);
+        if (BWD) {
+            // dI/dOEF = Dm * dA/dOEF + node 0 (live in the derivative only; J1(x) = x/2 for x ~ 1e-4)
+            const float a_t = 1.5f * (fabsf(c.my_tau) * dw);
+            dI_doef = (Dm * c.tau_ref15 + c.node0_d * a_t) * dw_k;
+        }
+    } else {
+        float D;
+        tissue_integrals<BWD, PATH == kColsMulti>(P, qs, c.tc0, dw, c.lane, c.my_col, I, D);
+        if (BWD) dI_doef = D * (1.5f * fabsf(c.my_tau)) * dw_k;
+    }
+    if (c.my_col >= 0) I += node0_value(P, 1.5f * (fabsf(c.my_tau) * dw));
 }
 
 }  // namespace qb

@@ -29,7 +29,7 @@ def test_library_exports_every_symbol_declared_in_the_header(qb):
         assert hasattr(handle, name), 'libqbold.so does not export %s' % name
     assert declared == set(qb._lib.EXPORTED_SYMBOLS), declared ^ set(qb._lib.EXPORTED_SYMBOLS)
     lib = qb._lib.lib()                       # also checks ABI version and sizeof(QboldParams)
-    assert lib.qbold_abi_version() == 1
+    assert lib.qbold_abi_version() == 2
 
 
 def test_params_block_matches_the_oracle(qb):
@@ -133,3 +133,42 @@ def test_philox_known_answers_and_streams():
         m = min(n, 5000)
         x = philox.feistel_permute(np.arange(n)[:m] if n > m else np.arange(n), n, 99)
         assert x.min() >= 0 and x.max() < n and len(np.unique(x)) == len(x)
+
+
+def test_static_lane_schedule_covers_every_node_once(qb):
+    """QboldParams::sched_*: every (column, node>=1) pair is dealt to exactly one (pass, lane) with its Simpson
+    weight, a lane keeps one column per phase, and the first-visit flags are consistent."""
+    cfg = o.default_config()
+    P = qb.SignalGenerationLayer(cfg, True, True).params
+    nph, PL = P.sched_phases, 4
+    assert 8 <= nph <= 10 and abs(P.tau_ref - 0.064) < 1e-7
+    m = np.array(P.sched_m[:nph * PL * 32]).reshape(nph, PL, 32)
+    w = np.array(P.sched_w[:nph * PL * 32]).reshape(nph, PL, 32)
+    col = np.array(P.sched_col[:nph * 32]).reshape(nph, 32)
+    u, c = np.array(P.qu[:129]), np.array(P.qc[:129])
+    r = np.array(P.abs_tau[:8], dtype=np.float64) / P.tau_ref
+    seen_nodes = {j: [] for j in range(8)}
+    seen_slot = set()
+    for ph in range(nph):
+        for lane in range(32):
+            j, first = int(col[ph, lane]) & 7, bool(col[ph, lane] & 0x80)
+            assert first == ((lane, j) not in seen_slot)
+            seen_slot.add((lane, j))
+            for p in range(PL):
+                if w[ph, p, lane] == 0.0:
+                    continue
+                k = int(round(m[ph, p, lane] / r[j] * 128 - 1e-5 * 128))
+                assert abs(m[ph, p, lane] - r[j] * u[k]) < 1e-7 and w[ph, p, lane] == np.float32(c[k])
+                seen_nodes[j].append(k)
+        live = w[ph] != 0
+        if live.any():
+            assert P.sched_ph_min[ph] <= m[ph][live].min() and P.sched_ph_max[ph] >= m[ph][live].max()
+    for j in range(8):
+        assert sorted(seen_nodes[j]) == list(range(1, 128))          # node 0 handled in closed form, node 128 has weight 0
+    # the point of the schedule: arguments inside one pass are close (ratio of max to min m, past the start-up phase)
+    spread = [m[ph, p][w[ph, p] != 0].max() / m[ph, p][w[ph, p] != 0].min() for ph in range(1, nph) for p in range(PL)
+              if (w[ph, p] != 0).any()]
+    assert np.median(spread) < 1.4
+    # more than 8 distinct |tau| (24-tau grid): no schedule, column-major path
+    cfg.update(tau_start='-0.028', tau_end='0.065', tau_step='0.004')
+    assert qb.SignalGenerationLayer(cfg, True, True).params.sched_phases == 0
