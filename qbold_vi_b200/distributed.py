@@ -1,0 +1,144 @@
+"""Voxel-sharded data parallelism for the hot path: one process per GPU.
+
+* forward / generation / inference: contiguous voxel shards, no communication;
+* training: every loss of the reference divides by the GLOBAL ``sum(mask)`` (model.py:566,663,753), so the mask
+  count is all-reduced first (it is an input) and handed to the fused kernel as ``inv_mask_sum``; the only
+  per-step collectives are ONE all-reduce of the flat encoder-gradient bucket (146 176 floats for optimal.yaml,
+  latency-bound over NVLink 5 / NVSwitch) and one of the 4 loss partial sums.  Replicas stay bit-identical
+  because they start from the same seed and apply the same reduced gradient.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None):
+    """torchrun-style rendezvous (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*); returns (rank, world, device)."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    use_cuda = torch.cuda.is_available()
+    device = torch.device('cuda', local) if use_cuda else torch.device('cpu')
+    if use_cuda:
+        torch.cuda.set_device(device)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29512')
+        backend = backend or ('nccl' if use_cuda else 'gloo')
+        if backend == 'nccl':
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=device)
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, device
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced shard [lo, hi) of n units (voxels or volumes) for `rank`."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_reduce_sum_(t):
+    if world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def global_mask_sum(mask):
+    """sum(mask) over all ranks, as a Python float (one tiny all-reduce; the mask is an input, so this can
+    be issued before the step)."""
+    s = mask.sum(dtype=torch.float64).reshape(1)
+    return float(all_reduce_sum_(s).item())
+
+
+class FlatGradBucket:
+    """One contiguous float32 buffer aliasing every parameter's .grad: a single all-reduce per step."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce_(self):
+        # gradients of a loss that is already normalised by the global mask count: SUM, no averaging
+        return all_reduce_sum_(self.flat)
+
+
+class LinearSchedule:
+    """LRSchedule of train.py:287-306: initial value until step 0, then linear decay to initial/100 over
+    40 x 100 steps (used for both the learning rate and the AdamW weight decay)."""
+
+    def __init__(self, initial, steps_per_epoch=100, epochs=40.0):
+        self.initial = float(initial)
+        self.rate = (self.initial / 1e2 - self.initial) / (epochs * steps_per_epoch)
+
+    def __call__(self, step):
+        return self.initial + self.rate * step if step > 0 else self.initial
+
+
+class DataParallelTrainer:
+    """Fine-tuning step of the reference (train.py:285-376) over voxel/volume shards.
+
+    loss = NLL + kl_weight * KL + smoothness_weight * TV, each normalised by the global mask count.
+    ``loss_fn(q, sigma, data, mask, prior, mask_sum) -> (loss, info)`` defaults to the fused sm_100a kernel
+    (EncoderTrainer.fused_elbo); tests of the host logic inject a stand-in."""
+
+    def __init__(self, encoder, trainer, signal_layer, ft_lr=5e-3, adamw_decay=2e-4, smoothness_weight=5.0,
+                 kl_weight=1.0, kl_samples=70, loss_fn=None):
+        self.encoder, self.trainer, self.layer = encoder, trainer, signal_layer
+        self.smoothness_weight, self.kl_weight, self.kl_samples = smoothness_weight, kl_weight, kl_samples
+        self.bucket = FlatGradBucket(encoder.parameters())
+        self.lr, self.wd = LinearSchedule(ft_lr), LinearSchedule(adamw_decay)
+        self.opt = torch.optim.Adam(self.bucket.params, lr=ft_lr, betas=(0.9, 0.9))      # beta_2 = 0.9 (train.py:310)
+        self.decay = adamw_decay > 0.0
+        self.step_no = 0
+        self.loss_fn = loss_fn or self._fused_loss
+
+    def _fused_loss(self, q, sigma, data, mask, prior, mask_sum):
+        return self.trainer.fused_elbo(self.layer, q, sigma, data, mask, prior, kl_samples=self.kl_samples,
+                                       kl_weight=self.kl_weight, mask_sum=mask_sum)
+
+    def step(self, data, mask, prior):
+        """data [B,X,Y,Z,n_tau] (pre-masked), mask [B,X,Y,Z,1], prior [B,X,Y,Z,5]: this rank's volumes."""
+        msum = global_mask_sum(mask)
+        self.bucket.zero_()
+        _, q, sigma = self.encoder(data)
+        loss, info = self.loss_fn(q, sigma, data, mask, prior, msum)
+        tv = self.trainer.smoothness_loss(torch.cat([prior, mask], -1), q) * (float(mask.sum()) / msum)
+        total = loss + self.smoothness_weight * tv
+        total.backward()
+        self.bucket.all_reduce_()
+        lr = self.lr(self.step_no)
+        for g in self.opt.param_groups:
+            g['lr'] = lr
+        if self.decay:                                    # tfa AdamW: decoupled decay var -= wd_t * var
+            with torch.no_grad():
+                self.bucket_params_mul_(1.0 - self.wd(self.step_no))
+        self.opt.step()
+        self.step_no += 1
+        stats = torch.stack([total.detach().double(), info['nll'].detach().double() if 'nll' in info else total.detach().double() * 0,
+                             info['kl'].detach().double() if 'kl' in info else total.detach().double() * 0,
+                             tv.detach().double()])
+        all_reduce_sum_(stats)
+        return {'loss': float(stats[0]), 'nll': float(stats[1]), 'kl': float(stats[2]), 'smoothness': float(stats[3]),
+                'mask_sum': msum, 'lr': lr}
+
+    def bucket_params_mul_(self, factor):
+        for p in self.bucket.params:
+            p.mul_(factor)

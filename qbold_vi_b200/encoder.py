@@ -1,0 +1,109 @@
+"""The amortization network of the reference (``EncoderTrainer.create_encoder``, model.py:122-223) in PyTorch.
+
+Adjacent to the hot path: it stays a library network (cuDNN / cuBLAS on tensor cores);
+what matters here is that it produces the tensors the fused ELBO kernel consumes -- 5 logit-normal
+parameters and ``n_tau`` heteroscedastic sigmas per voxel -- and that its 146 176 parameters (optimal.yaml)
+are what the per-step NCCL all-reduce carries.  Layout is the reference's channels-last ``[B, X, Y, Z, C]``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _he_normal_(w, fan_in):
+    # keras HeNormal: truncated normal, stddev = sqrt(2 / fan_in) / 0.87962566
+    std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
+    nn.init.trunc_normal_(w, mean=0.0, std=std, a=-2 * std, b=2 * std)
+
+
+class _Conv331(nn.Module):
+    """keras Conv3D(kernel_size=(3,3,1), padding='same') on a channels-last volume: a 2-D conv over (X, Y)
+    applied to every z slice (so z-slabs need no halo when volumes are sharded)."""
+
+    def __init__(self, c_in, c_out, std):
+        super().__init__()
+        self.conv = nn.Conv2d(c_in, c_out, 3, padding=1)
+        nn.init.normal_(self.conv.weight, std=std)
+        nn.init.zeros_(self.conv.bias)
+
+    def forward(self, x):                                   # [B, X, Y, Z, C]
+        b, nx, ny, nz, c = x.shape
+        y = x.permute(0, 3, 4, 1, 2).reshape(b * nz, c, nx, ny)
+        y = self.conv(y)
+        return y.reshape(b, nz, -1, nx, ny).permute(0, 3, 4, 1, 2)
+
+
+class _Block(nn.Module):
+    """create_block (model.py:142-174): stream-1 1x1x1 conv shared with the skip of stream 2, plus a gated
+    residual pair of 3x3x1 convs."""
+
+    def __init__(self, units, act, resid_std, channelwise_gating, gate_offset):
+        super().__init__()
+        self.act = act
+        self.gate_offset = gate_offset
+        self.pointwise = nn.Linear(units, units)
+        _he_normal_(self.pointwise.weight, units)
+        nn.init.zeros_(self.pointwise.bias)
+        self.conv_a = _Conv331(units, units, resid_std)
+        self.conv_b = _Conv331(units, units, resid_std)
+        self.gate = nn.Linear(units, units if channelwise_gating else 1)
+        nn.init.normal_(self.gate.weight, std=resid_std)
+        nn.init.zeros_(self.gate.bias)
+
+    def forward(self, net1, net2):
+        out1 = self.act(self.pointwise(net1))
+        skip = self.act(self.pointwise(net2))
+        r = self.conv_b(self.act(self.conv_a(self.act(net2))))
+        g = torch.sigmoid(self.gate(r) + self.gate_offset)
+        return out1, skip * (1.0 - g) + r * g
+
+
+class Encoder(nn.Module):
+    """outer_model of create_encoder: data [B,X,Y,Z,n_tau] -> (q_voxelwise [...,5], q_spatial [...,5], sigma [...,n_tau])."""
+
+    def __init__(self, no_units=60, no_intermediate_layers=2, activation='relu', initial_im_sigma=0.05,
+                 multi_image_normalisation=False, channelwise_gating=True, gate_offset=-3.0, resid_init_std=0.05,
+                 no_ip_images=11, se_idx=2, use_mvg=True):
+        super().__init__()
+        self.act = {'relu': F.relu, 'gelu': F.gelu, 'tanh': torch.tanh}[activation]
+        self.se_idx = se_idx
+        self.multi_image_normalisation = multi_image_normalisation
+        self.first = nn.Linear(no_ip_images, no_units)
+        _he_normal_(self.first.weight, no_ip_images)
+        nn.init.zeros_(self.first.bias)
+        self.blocks = nn.ModuleList([_Block(no_units, self.act, resid_init_std, channelwise_gating, gate_offset)
+                                     for _ in range(max(1, no_intermediate_layers))])
+        self.final = nn.Linear(no_units, 5 if use_mvg else 4)
+        _he_normal_(self.final.weight, no_units)
+        nn.init.zeros_(self.final.bias)
+        self.im_sigma = nn.Linear(no_units, no_ip_images)
+        nn.init.normal_(self.im_sigma.weight, std=resid_init_std)
+        nn.init.constant_(self.im_sigma.bias, math.log(initial_im_sigma))
+
+    def normalise_data(self, data):
+        """model.py:97-113: clip, divide by the tau=0 image (or the 3-image mean), log."""
+        d = torch.clamp(data, 1e-2, 1e8)
+        se = self.se_idx
+        ref = d[..., se - 1:se + 2] if self.multi_image_normalisation else d[..., se:se + 1]
+        return torch.log(d / ref.mean(-1, keepdim=True))
+
+    def forward(self, data):
+        h = self.act(self.first(self.normalise_data(data)))
+        net1 = net2 = h
+        for blk in self.blocks:
+            net1, net2 = blk(net1, net2)
+        return self.final(net1), self.final(net2), torch.exp(self.im_sigma(net2))
+
+
+def create_encoder_from_args(args, no_ip_images=11, se_idx=2):
+    """train.py:430-451 with an argparse/yaml namespace (config.load_arguments)."""
+    return Encoder(no_units=max(1, args.no_units), no_intermediate_layers=max(1, args.no_intermediate_layers),
+                   activation=args.activation, initial_im_sigma=args.im_loss_sigma,
+                   multi_image_normalisation=args.multi_image_normalisation,
+                   channelwise_gating=args.channelwise_gating, gate_offset=args.gate_offset,
+                   resid_init_std=args.resid_init_std, no_ip_images=no_ip_images, se_idx=se_idx,
+                   use_mvg=args.use_mvg)

@@ -1,0 +1,120 @@
+"""CPU suite, part 3: the multi-rank host logic on gloo, world_size 2.
+
+The fused CUDA loss cannot run here, so DataParallelTrainer gets a stand-in loss with the same contract
+(normalised by the GLOBAL mask count); what is under test is sharding, the global mask sum, the single
+flat-bucket all-reduce and replica consistency."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import qbold_oracle as o
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _standin_loss(q, sigma, data, mask, prior, mask_sum):
+    m = mask.reshape(-1)
+    per_voxel = ((q.reshape(-1, 5) - prior.reshape(-1, 5)) ** 2).sum(-1) + \
+        ((torch.log(sigma.reshape(m.shape[0], -1)) + 2.0) ** 2).sum(-1)
+    loss = (per_voxel * m).sum() / mask_sum
+    return loss, {'nll': loss.detach(), 'kl': loss.detach() * 0}
+
+
+def _make(seed=3):
+    import qbold_vi_b200 as qb
+    from qbold_vi_b200.encoder import Encoder
+    from qbold_vi_b200.distributed import DataParallelTrainer
+    cfg = o.default_config()
+    torch.manual_seed(seed)
+    enc = Encoder(no_units=12, no_intermediate_layers=2)
+    tr = qb.EncoderTrainer(cfg, student_t_df=200, multi_image_normalisation=False, use_mvg=True,
+                           use_population_prior=False, predict_log_data=False, seed=1)
+    return enc, DataParallelTrainer(enc, tr, None, loss_fn=_standin_loss)
+
+
+def _batch():
+    g = torch.Generator().manual_seed(11)
+    data = torch.rand((4, 6, 5, 2, 11), generator=g) + 0.5
+    mask = (torch.rand((4, 6, 5, 2, 1), generator=g) > 0.3).float()
+    prior = torch.randn((4, 6, 5, 2, 5), generator=g) * 0.3
+    return data * mask, mask, prior
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from qbold_vi_b200 import distributed as D
+    r, w, dev = D.init_distributed('gloo')
+    assert (r, w) == (rank, world) and dev.type == 'cpu'
+    enc, dp = _make()
+    data, mask, prior = _batch()
+    lo, hi = D.shard_range(data.shape[0], rank, world)
+    stats = dp.step(data[lo:hi], mask[lo:hi], prior[lo:hi])
+    out.put((rank, dp.bucket.flat.clone().numpy(), stats,
+             torch.cat([p.detach().reshape(-1) for p in enc.parameters()]).numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_is_a_balanced_partition():
+    from qbold_vi_b200.distributed import shard_range
+    for n in (0, 1, 7, 16, 1000003):
+        for w in (1, 2, 3, 8):
+            parts = [shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_step_equals_single_rank_step():
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([out.get(timeout=240) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference on the full batch
+    enc, dp = _make()
+    data, mask, prior = _batch()
+    stats = dp.step(data, mask, prior)
+    g_ref = dp.bucket.flat.numpy()
+    w_ref = torch.cat([p.detach().reshape(-1) for p in enc.parameters()]).numpy()
+    assert g_ref.shape[0] == sum(p.numel() for p in enc.parameters())
+    for rank, g, st, w in res:
+        assert np.max(np.abs(g - g_ref)) <= 1e-5 * np.max(np.abs(g_ref))       # all-reduced grads == full-batch grads
+        assert np.max(np.abs(w - w_ref)) <= 1e-6                                # replicas apply the same update
+        assert abs(st['loss'] - stats['loss']) <= 1e-5 * abs(stats['loss'])
+        assert st['mask_sum'] == stats['mask_sum'] == float(mask.sum())
+    assert np.array_equal(res[0][3], res[1][3])                                 # replicas stay bit-identical
+
+
+def test_encoder_parameter_count_matches_the_reference():
+    from qbold_vi_b200.encoder import Encoder
+    enc = Encoder()                                   # optimal.yaml: 60 units, 2 blocks, channel-wise gating
+    assert sum(p.numel() for p in enc.parameters()) == 146176
+    x = torch.rand(2, 5, 4, 3, 11) + 0.5
+    q, q2, sg = enc(x)
+    assert tuple(q.shape) == (2, 5, 4, 3, 5) and tuple(sg.shape) == (2, 5, 4, 3, 11) and bool((sg > 0).all())
+    assert abs(float(sg.mean()) - 0.05) < 0.02                                   # bias = log(im_loss_sigma)
+    # the 3x3x1 convs never mix z slices: a z-slab can be processed on its own (no halo when sharding by z)
+    assert torch.allclose(enc(x[:, :, :, 1:2])[1], q2[:, :, :, 1:2], atol=1e-6)
+
+
+def test_linear_schedule_matches_train_py():
+    from qbold_vi_b200.distributed import LinearSchedule
+    s = LinearSchedule(5e-3)
+    assert s(0) == 5e-3 and abs(s(4000) - 5e-5) < 1e-12 and abs(s(2000) - (5e-3 + 5e-5) / 2) < 1e-12

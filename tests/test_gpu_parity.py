@@ -347,3 +347,60 @@ def test_full_size_properties_16M(qb, dev, cfg_noise_off):
     _, g2 = layer.forward_backward(x, w1 + 1.0, want_signal=False)
     err = (g2 - (g1 + g_ones)).abs().max(0).values / g2.abs().max(0).values         # the VJP is linear in g
     assert float(err.max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------- training glue
+def test_fused_step_equals_unfused_layer_composition(qb, dev, cfg_noise_off):
+    """One fused launch == the reference's graph built from the separate layers (build_fine_tuner,
+    model.py:239-286 + loss closures train.py:315-320), gradients w.r.t. the encoder parameters included."""
+    from qbold_vi_b200.encoder import Encoder
+    torch.manual_seed(0)
+    enc = Encoder(no_units=16, no_intermediate_layers=1).to(dev)
+    tr = _trainer(qb, cfg_noise_off)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    g = torch.Generator(device=dev).manual_seed(5)
+    shape = (2, 6, 5, 3)
+    truth = torch.stack([torch.rand(shape, device=dev, generator=g) * 0.5 + 0.15,
+                         torch.rand(shape, device=dev, generator=g) * 0.1 + 0.01], -1)
+    mask = (torch.rand(shape + (1,), device=dev, generator=g) > 0.25).float()
+    data = layer(truth) * 100.0 * (1 + 0.02 * torch.randn(shape + (11,), device=dev, generator=g)) * mask
+    prior = torch.randn(shape + (5,), device=dev, generator=g) * 0.4
+    n = mask.numel()
+    eps = torch.randn((n, 2), device=dev, generator=g)
+    eps_kl = torch.randn((n, 70, 2), device=dev, generator=g)
+
+    _, q, sigma = enc(data)
+    loss_f, info = tr.fused_elbo(layer, q, sigma, data, mask, prior, kl_samples=70, eps=eps, eps_kl=eps_kl)
+    g_f = torch.autograd.grad(loss_f, list(enc.parameters()))
+
+    _, q, sigma = enc(data)
+    sampled = qb.ReparamTrickLayer(tr)((q, mask), eps=eps)                           # model.py:248
+    pred = layer(sampled)                                                            # model.py:273
+    nll = tr.fine_tune_loss_fn(torch.cat([data, mask], -1), torch.cat([pred, sigma], -1))
+    kl = tr.kl_loss(torch.cat([prior, mask], -1), q, eps=eps_kl)
+    g_u = torch.autograd.grad(nll + kl, list(enc.parameters()))
+    assert abs(loss_f.item() - (nll + kl).item()) < GRAD_TOL * abs(loss_f.item())
+    assert abs(info['nll'].item() - nll.item()) < GRAD_TOL * abs(nll.item())
+    for a, b in zip(g_f, g_u):
+        assert rel_max(a.cpu().numpy(), b.cpu().numpy()) < 5 * GRAD_TOL
+
+
+def test_single_gpu_training_steps_reduce_the_loss(qb, dev, cfg_noise_off):
+    from qbold_vi_b200.encoder import Encoder
+    from qbold_vi_b200.distributed import DataParallelTrainer
+    torch.manual_seed(1)
+    enc = Encoder().to(dev)
+    tr = _trainer(qb, cfg_noise_off)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    dp = DataParallelTrainer(enc, tr, layer, ft_lr=2e-3)
+    g = torch.Generator(device=dev).manual_seed(9)
+    shape = (2, 16, 16, 4)
+    truth = torch.stack([torch.rand(shape, device=dev, generator=g) * 0.4 + 0.2,
+                         torch.rand(shape, device=dev, generator=g) * 0.06 + 0.01], -1)
+    mask = torch.ones(shape + (1,), device=dev)
+    data = layer(truth) * 100.0
+    with torch.no_grad():
+        prior = enc(data)[0].clone()
+    losses = [dp.step(data, mask, prior) for _ in range(12)]
+    assert all(np.isfinite(s['loss']) for s in losses)
+    assert np.mean([s['nll'] for s in losses[-3:]]) < np.mean([s['nll'] for s in losses[:3]])

@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Multi-GPU check (run under torchrun on the GPU box): N ranks each take a shard of the same batch; the
+all-reduced encoder gradient and the loss must equal the single-GPU full-batch values, and per-voxel
+outputs of the sharded forward must be bit-identical to the unsharded ones."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qbold_vi_b200 as qb
+from qbold_vi_b200 import distributed as D
+from qbold_vi_b200.encoder import Encoder
+
+
+def main():
+    rank, world, dev = D.init_distributed()
+    cfg = qb.load_system_parameters(qb.config.DEFAULT_CONFIG_PATH)
+    cfg['simulate_noise'] = 'False'
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    tr = qb.EncoderTrainer(cfg, student_t_df=200, multi_image_normalisation=False, use_mvg=True,
+                           use_population_prior=False, predict_log_data=False, seed=7)
+    torch.manual_seed(0)
+    enc = Encoder().to(dev)
+    g = torch.Generator(device=dev).manual_seed(42)            # same data on every rank, then sharded
+    shape = (8, 24, 24, 4)
+    truth = torch.stack([torch.rand(shape, device=dev, generator=g) * 0.5 + 0.15,
+                         torch.rand(shape, device=dev, generator=g) * 0.1 + 0.01], -1)
+    mask = (torch.rand(shape + (1,), device=dev, generator=g) > 0.2).float()
+    data = layer(truth) * 100.0 * mask
+    prior = torch.randn(shape + (5,), device=dev, generator=g) * 0.3
+    n = mask.numel()
+    eps = torch.randn((n, 2), device=dev, generator=g).reshape(shape + (2,))
+    eps_kl = torch.randn((n, 70, 2), device=dev, generator=g).reshape(shape + (70, 2))
+    lo, hi = D.shard_range(shape[0], rank, world)
+    sl = slice(lo, hi)
+
+    # sharded forward == slice of the full forward, bit for bit
+    full = layer(truth)
+    assert torch.equal(layer(truth[sl].contiguous()), full[sl])
+
+    def run(sl_, msum):
+        bucket = D.FlatGradBucket(enc.parameters())
+        bucket.zero_()
+        _, q, sigma = enc(data[sl_])
+        loss, info = tr.fused_elbo(layer, q, sigma, data[sl_], mask[sl_], prior[sl_], kl_samples=70,
+                                   eps=eps[sl_], eps_kl=eps_kl[sl_], mask_sum=msum)
+        loss.backward()
+        return bucket, loss.detach().double().reshape(1)
+
+    msum = D.global_mask_sum(mask[sl])
+    assert msum == float(mask.sum())
+    bucket, loss = run(sl, msum)
+    bucket.all_reduce_()
+    D.all_reduce_sum_(loss)
+    g_sharded = bucket.flat.clone()
+    ref_bucket, ref_loss = run(slice(0, shape[0]), float(mask.sum()))
+    err = float((g_sharded - ref_bucket.flat).abs().max() / ref_bucket.flat.abs().max())
+    lerr = abs(float(loss) - float(ref_loss)) / abs(float(ref_loss))
+    if rank == 0:
+        print(json.dumps({'world': world, 'grad_rel_err': err, 'loss_rel_err': lerr, 'loss': float(ref_loss)}))
+    assert err < 1e-5 and lerr < 1e-6, (err, lerr)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
