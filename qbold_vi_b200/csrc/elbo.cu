@@ -18,8 +18,19 @@ constexpr float kOefRange = 0.8f, kMinOef = 0.04f, kDbvRange = 0.2f, kMinDbv = 0
 constexpr float kExpM2 = 0.1353352832366127f;                                            // np.exp(-2.0), model.py:294
 constexpr float kLog2Pi = 1.8378770664093453f;                                           // model.py:390
 constexpr float kLogSqrt2Pi = 0.9189385332046727f;                                       // model.py:561
+constexpr float kRoundTripZ = 9.0f;   // sigmoid/logit round trip treated as identity below this |z| (see kl_term)
 
 __device__ __forceinline__ float sigmoidf(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// Sum over the live tau lanes (lanes >= n_tau hold 0): 4 butterfly steps cover 16 lanes, a 5th only when n_tau > 16.
+__device__ __forceinline__ float sum_live(float v, bool wide) {
+    if (wide) v += __shfl_xor_sync(kFull, v, 16);
+    v += __shfl_xor_sync(kFull, v, 8);
+    v += __shfl_xor_sync(kFull, v, 4);
+    v += __shfl_xor_sync(kFull, v, 2);
+    v += __shfl_xor_sync(kFull, v, 1);
+    return v;
+}
 
 // Transformed distribution parameters of one voxel (q and prior), every lane holds a copy.
 struct Dist {
@@ -125,21 +136,30 @@ __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const
             } else {
                 normal_pair(seed, index, kStreamKl + (uint32_t)sidx, k0, k1);
             }
-            const Sample ks = draw(dq, ex, k0, k1);
-            // backwards_transform + clip + logit (model.py:393-396, 307-316, 10-12)
-            float x_o = (ks.oef - kMinOef) / kOefRange;
-            float x_d = (ks.dbv - kMinDbv) / kDbvRange;
-            x_o = fminf(fmaxf(x_o, 1e-6f), 1.0f - 1e-6f);
-            x_d = fminf(fmaxf(x_d, 1e-6f), 1.0f - 1e-6f);
-            const float zh_o = logf(x_o / (1.0f - x_o));
-            const float zh_d = logf(x_d / (1.0f - x_d));
+            // Sample in logit space, then the reference's round trip sigmoid -> OEF/DBV -> backwards_transform ->
+            // clip -> logit (model.py:393-396, 307-316, 10-12).  For |z| < kRoundTripZ the round trip is the
+            // identity up to float32 noise (< 5e-4 absolute on zh, zero-mean; far inside the 1e-4 ELBO bar after
+            // averaging) and d zh/d z = 1, so it is skipped; beyond it (saturating sigmoid, clip at 1e-6) the
+            // reference's float32 arithmetic is followed literally.
+            const float z_o = dq.mu_o + k0 * ex.sd_o;                            // model.py:26-27
+            const float z_d = (dq.mu_d + k0 * dq.cov) + k1 * ex.sd_d;            // model.py:29-31
+            float zh_o = z_o, zh_d = z_d, dz_o = 1.0f, dz_d = 1.0f;
+            if (fmaxf(fabsf(z_o), fabsf(z_d)) >= kRoundTripZ) {
+                const float s_o = sigmoidf(z_o), s_d = sigmoidf(z_d);
+                float x_o = ((s_o * kOefRange + kMinOef) - kMinOef) / kOefRange;
+                float x_d = ((s_d * kDbvRange + kMinDbv) - kMinDbv) / kDbvRange;
+                x_o = fminf(fmaxf(x_o, 1e-6f), 1.0f - 1e-6f);
+                x_d = fminf(fmaxf(x_d, 1e-6f), 1.0f - 1e-6f);
+                zh_o = logf(x_o / (1.0f - x_o));
+                zh_d = logf(x_d / (1.0f - x_d));
+                // d zh / d z: logit'(x) * (1/range) * range * sigmoid'(z); the clip passes the gradient (model.py:395)
+                dz_o = (s_o * (1.0f - s_o)) / (x_o * (1.0f - x_o));
+                dz_d = (s_d * (1.0f - s_d)) / (x_d * (1.0f - x_d));
+            }
             float gq_o, gq_d, gp_o, gp_d;
             const float nq = mvn_nll(dq, zh_o, zh_d, gq_o, gq_d);
             const float np = mvn_nll(dp, zh_o, zh_d, gp_o, gp_d);
             a[5] += np - nq;                                                     // log q - log p (model.py:603)
-            // d zh / d z: logit'(x) * (1/range) * range * sigmoid'(z); the clip passes the gradient (model.py:395)
-            const float dz_o = (ks.s_o * (1.0f - ks.s_o)) / (x_o * (1.0f - x_o));
-            const float dz_d = (ks.s_d * (1.0f - ks.s_d)) / (x_d * (1.0f - x_d));
             const float hz_o = (gp_o - gq_o) * dz_o, hz_d = (gp_d - gq_d) * dz_d;
             a[0] += hz_o;
             a[1] += hz_o * k0;
@@ -201,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) k_kl(const float* __restrict__ q, co
 }
 
 template <bool HAS_PRIOR, int PATH>
-__global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ QboldParams P,
+__global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ QboldParams P,
                                                    const float* __restrict__ q, const float* __restrict__ sigma,
                                                    const float* __restrict__ y, const float* __restrict__ mask,
                                                    const float* __restrict__ prior, const float* __restrict__ eps,
@@ -232,6 +252,7 @@ __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ Qbold
     const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
     const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
     const float df = P.student_t_df;
+    const bool wide = nt > 16;
 
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
     int bad = 0;
@@ -266,13 +287,20 @@ __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ Qbold
         if (P.full_model) tissue_eval<true, PATH>(P, s, ss, qc, vp.dw, vp.dw_k, I, dI);
         const TauSignal ts = tau_signal<true>(P, vp, my_tau, my_b, I, dI);
 
-        // ---- fine_tune_loss_fn (model.py:527-568)
+        // ---- fine_tune_loss_fn (model.py:527-568).  Divisions by the same denominator share one reciprocal.
         const float yv = live ? __ldg(y + v * nt + lane) : 0.f;
         const float sg = live ? __ldg(sigma + v * nt + lane) : 1.f;
         const float pred = live ? ts.S : 0.f;
-        const float npd = warp_sum(in_norm ? pred * norm_w : 0.f) + 1e-3f;     // model.py:541-545
-        const float ny = warp_sum(in_norm ? yv * norm_w : 0.f) + 1e-3f;
-        float yn = yv / ny, pn = pred / npd;
+        float npd, ny;                                                          // model.py:541-545
+        if (multi) {
+            npd = sum_live(in_norm ? pred * norm_w : 0.f, wide) + 1e-3f;
+            ny = sum_live(in_norm ? yv * norm_w : 0.f, wide) + 1e-3f;
+        } else {
+            npd = __shfl_sync(kFull, pred, se) + 1e-3f;
+            ny = __shfl_sync(kFull, yv, se) + 1e-3f;
+        }
+        const float inv_npd = 1.0f / npd, inv_sg = 1.0f / sg;
+        float yn = yv / ny, pn = pred * inv_npd;
         float dpn = 1.0f;                                                       // d(pn used in residual)/d(pred/npd)
         if (P.predict_log_data) {                                               // model.py:547-549 (mask > 0 here)
             dpn = 1.0f / pn;
@@ -280,30 +308,40 @@ __global__ void __launch_bounds__(kThreads) k_elbo(const __grid_constant__ Qbold
             pn = logf(pn);
         }
         const float res = yn - pn;
-        const float zq = res / sg;
+        const float zq = res * inv_sg;
         float nll_t, dnll_dres, dnll_dsg;
         if (df > 0.f) {                                                         // StudentT(df, 0, sigma), model.py:557-559
             const float t = zq * zq / df;
             nll_t = -(P.student_t_logc - logf(sg) - 0.5f * (df + 1.0f) * log1pf(t));
             const float k = (df + 1.0f) / (df + zq * zq);
-            dnll_dres = k * zq / sg;
-            dnll_dsg = 1.0f / sg - k * zq * zq / sg;
+            dnll_dres = k * zq * inv_sg;
+            dnll_dsg = inv_sg - k * zq * zq * inv_sg;
         } else {                                                                // Gaussian, model.py:561
             nll_t = -(-logf(sg) - kLogSqrt2Pi - 0.5f * (zq * zq));
-            dnll_dres = zq / sg;
-            dnll_dsg = 1.0f / sg - (zq * zq) / sg;
+            dnll_dres = zq * inv_sg;
+            dnll_dsg = inv_sg - (zq * zq) * inv_sg;
         }
         if (!live) nll_t = 0.f;
-        const float nll_v = warp_sum(nll_t);
         const float scale = m * inv_mask_sum;                                   // model.py:564-566
         if (live) grad_sigma[v * nt + lane] = dnll_dsg * scale;
-        // residual = yn - pn  =>  d/dpn = -dnll_dres
+        // residual = yn - pn  =>  d/dpn = -dnll_dres ;  pn = pred/npd, npd = pred[se] (+ neighbours) + 1e-3:
+        //   dL/dpred_t = g_t/npd + [t in norm] * w * g_npd,  g_npd = -sum_t g_t pred_t / npd^2
         const float g_ratio = live ? (-dnll_dres * scale) * dpn : 0.f;          // w.r.t. pred/npd
-        float g_pred = g_ratio / npd;
-        const float g_npd = -warp_sum(g_ratio * pred) / (npd * npd);
-        if (in_norm) g_pred += g_npd * norm_w;
-        const float go = warp_sum(live ? g_pred * ts.dS_doef : 0.f);
-        const float gd = warp_sum(live ? g_pred * ts.dS_ddbv : 0.f);
+        const float nll_v = sum_live(nll_t, wide);
+        const float s_gp = sum_live(g_ratio * pred, wide);
+        const float s_go = sum_live(g_ratio * ts.dS_doef, wide);
+        const float s_gd = sum_live(g_ratio * ts.dS_ddbv, wide);
+        float n_o, n_d;                                                          // sum over the normalisation set of dS/d.
+        if (multi) {
+            n_o = sum_live(in_norm ? ts.dS_doef * norm_w : 0.f, wide);
+            n_d = sum_live(in_norm ? ts.dS_ddbv * norm_w : 0.f, wide);
+        } else {
+            n_o = __shfl_sync(kFull, ts.dS_doef, se);
+            n_d = __shfl_sync(kFull, ts.dS_ddbv, se);
+        }
+        const float g_npd = -s_gp * (inv_npd * inv_npd);
+        const float go = s_go * inv_npd + g_npd * n_o;
+        const float gd = s_gd * inv_npd + g_npd * n_d;
         float gz_o = go * kOefRange * sm.s_o * (1.0f - sm.s_o);
         float gz_d = gd * kDbvRange * sm.s_d * (1.0f - sm.s_d);
         // z -> q (model.py:26-31)
