@@ -108,6 +108,32 @@ __device__ __forceinline__ float mvn_nll(const Dist& d, float zh_o, float zh_d, 
     return kLog2Pi + 0.5f * (2.0f * (d.ls_o + d.ls_d)) + 0.5f * (w_o * w_o + w_d * w_d);
 }
 
+// -log StudentT(df, 0, sigma).pdf(res) and its partials (model.py:557-559); cold path (optimal.yaml: df = 200).
+__device__ __forceinline__ void student_t_terms(float logc, float df, float zq, float sg, float inv_sg, float& nll,
+                                                    float& d_res, float& d_sg) {
+    const float t = zq * zq / df;
+    nll = -(logc - logf(sg) - 0.5f * (df + 1.0f) * log1pf(t));
+    const float k = (df + 1.0f) / (df + zq * zq);
+    d_res = k * zq * inv_sg;
+    d_sg = inv_sg - k * zq * zq * inv_sg;
+}
+
+// The reference's float32 round trip z -> sigmoid -> OEF/DBV -> backwards_transform -> clip -> logit
+// (model.py:302-303, 310-311, 394-396) and d zh/d z, evaluated literally.  Cold path (|z| >= kRoundTripZ).
+__device__ __forceinline__ void roundtrip_literal(float z_o, float z_d, float& zh_o, float& zh_d, float& dz_o,
+                                               float& dz_d) {
+    const float s_o = sigmoidf(z_o), s_d = sigmoidf(z_d);
+    float x_o = ((s_o * kOefRange + kMinOef) - kMinOef) / kOefRange;
+    float x_d = ((s_d * kDbvRange + kMinDbv) - kMinDbv) / kDbvRange;
+    x_o = fminf(fmaxf(x_o, 1e-6f), 1.0f - 1e-6f);
+    x_d = fminf(fmaxf(x_d, 1e-6f), 1.0f - 1e-6f);
+    zh_o = logf(x_o / (1.0f - x_o));
+    zh_d = logf(x_d / (1.0f - x_d));
+    // d zh / d z: logit'(x) * (1/range) * range * sigmoid'(z); the clip passes the gradient (model.py:395)
+    dz_o = (s_o * (1.0f - s_o)) / (x_o * (1.0f - x_o));
+    dz_d = (s_d * (1.0f - s_d)) / (x_d * (1.0f - x_d));
+}
+
 // KL(q || prior) of one voxel and its gradient w.r.t. the raw q parameters; warp-cooperative
 // (lanes = samples), every lane returns the same values.
 //   n_samples > 0 : the reference's Monte-Carlo estimator mean_s(log q(z_s) - log p(z_s))
@@ -144,18 +170,7 @@ __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const
             const float z_o = dq.mu_o + k0 * ex.sd_o;                            // model.py:26-27
             const float z_d = (dq.mu_d + k0 * dq.cov) + k1 * ex.sd_d;            // model.py:29-31
             float zh_o = z_o, zh_d = z_d, dz_o = 1.0f, dz_d = 1.0f;
-            if (fmaxf(fabsf(z_o), fabsf(z_d)) >= kRoundTripZ) {
-                const float s_o = sigmoidf(z_o), s_d = sigmoidf(z_d);
-                float x_o = ((s_o * kOefRange + kMinOef) - kMinOef) / kOefRange;
-                float x_d = ((s_d * kDbvRange + kMinDbv) - kMinDbv) / kDbvRange;
-                x_o = fminf(fmaxf(x_o, 1e-6f), 1.0f - 1e-6f);
-                x_d = fminf(fmaxf(x_d, 1e-6f), 1.0f - 1e-6f);
-                zh_o = logf(x_o / (1.0f - x_o));
-                zh_d = logf(x_d / (1.0f - x_d));
-                // d zh / d z: logit'(x) * (1/range) * range * sigmoid'(z); the clip passes the gradient (model.py:395)
-                dz_o = (s_o * (1.0f - s_o)) / (x_o * (1.0f - x_o));
-                dz_d = (s_d * (1.0f - s_d)) / (x_d * (1.0f - x_d));
-            }
+            if (fmaxf(fabsf(z_o), fabsf(z_d)) >= kRoundTripZ) roundtrip_literal(z_o, z_d, zh_o, zh_d, dz_o, dz_d);
             float gq_o, gq_d, gp_o, gp_d;
             const float nq = mvn_nll(dq, zh_o, zh_d, gq_o, gq_d);
             const float np = mvn_nll(dp, zh_o, zh_d, gp_o, gp_d);
@@ -311,11 +326,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
         const float zq = res * inv_sg;
         float nll_t, dnll_dres, dnll_dsg;
         if (df > 0.f) {                                                         // StudentT(df, 0, sigma), model.py:557-559
-            const float t = zq * zq / df;
-            nll_t = -(P.student_t_logc - logf(sg) - 0.5f * (df + 1.0f) * log1pf(t));
-            const float k = (df + 1.0f) / (df + zq * zq);
-            dnll_dres = k * zq * inv_sg;
-            dnll_dsg = inv_sg - k * zq * zq * inv_sg;
+            student_t_terms(P.student_t_logc, df, zq, sg, inv_sg, nll_t, dnll_dres, dnll_dsg);
         } else {                                                                // Gaussian, model.py:561
             nll_t = -(-logf(sg) - kLogSqrt2Pi - 0.5f * (zq * zq));
             dnll_dres = zq * inv_sg;

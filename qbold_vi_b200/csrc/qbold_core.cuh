@@ -180,6 +180,8 @@ __device__ __forceinline__ VoxelPhys voxel_phys(const QboldParams& P, float oef,
 }
 
 // Tissue signal of the log-linear model (signals.py:194-207) for one tau, with partials.
+// Cold path (full_model = False goes through k_loglinear): kept out of line so it does not bloat the
+// instruction footprint of the quadrature kernels.
 __device__ __forceinline__ void loglinear_tissue(const QboldParams& P, const VoxelPhys& v, float tau,
                                                  float& st, float& dst_doef, float& dst_ddbv) {
     const float tc = 1.0f / v.dw;
