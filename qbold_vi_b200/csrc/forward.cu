@@ -4,11 +4,15 @@
 #include "qbold_core.cuh"
 #include "launch.h"
 
+#ifndef QB_FWD_MIN_BLOCKS
+#define QB_FWD_MIN_BLOCKS 5
+#endif
+
 namespace qb {
 
 // One warp per voxel (grid-stride).  BWD: also g_oef_dbv[n,2]; HCT: oef_dbv rows are (OEF,DBV,Hct).
 template <bool BWD, bool HCT, int PATH>
-__global__ void __launch_bounds__(kThreads) k_forward(const __grid_constant__ QboldParams P,
+__global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward(const __grid_constant__ QboldParams P,
                                                       const float* __restrict__ oef_dbv,
                                                       const float* __restrict__ g_signal,
                                                       float* __restrict__ signal,
