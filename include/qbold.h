@@ -188,6 +188,13 @@ int qbold_posterior_stats(const QboldParams* p, const float* q, const float* eps
                           uint64_t offset, int32_t n_samples, int64_t n, float* mean3, float* var3,
                           void* stream);
 
+/* Posterior-predictive likelihood map of save_predictions (model.py:808-817): mean over n_samples
+ * reparameterised draws of fine_tune_loss_fn(..., return_mean=False), forward-only.  eps [n,n_samples,2] or
+ * NULL -> Philox; mask may be NULL (all ones); nll_map [n]. */
+int qbold_nll_map(const QboldParams* p, const float* q, const float* sigma, const float* y, const float* mask,
+                  const float* eps, uint64_t seed, uint64_t offset, int32_t n_samples, int64_t n, float* nll_map,
+                  void* stream);
+
 /* FP32 FMA micro-benchmark (roofline denominator measured in the same run): launches
  * `iters` dependent-chain FFMA sweeps, returns achieved TFLOP/s through *tflops. */
 int qbold_fma_peak(int32_t iters, double* tflops);

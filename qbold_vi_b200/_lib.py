@@ -71,6 +71,8 @@ _SIGNATURES = {
     'qbold_kl': (C.c_int, [_f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f, _f, C.c_void_p]),
     'qbold_posterior_stats': (C.c_int, [_P(QboldParams), _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f, _f,
                                         C.c_void_p]),
+    'qbold_nll_map': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f,
+                                C.c_void_p]),
     'qbold_fma_peak': (C.c_int, [C.c_int32, _P(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -397,6 +397,83 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
     }
 }
 
+// Posterior-predictive likelihood map (save_predictions, model.py:808-817): the reference averages
+// fine_tune_loss_fn(return_mean=False) over 100 stochastic forward passes of the fine-tuner.  Here: one warp per
+// voxel loops over n_samples reparameterised draws, runs the forward-only quadrature for each and averages the
+// masked per-voxel NLL; nothing but the [n] map is written.
+template <int PATH>
+__global__ void __launch_bounds__(kThreads, 3) k_nll_map(const __grid_constant__ QboldParams P,
+                                                         const float* __restrict__ q, const float* __restrict__ sigma,
+                                                         const float* __restrict__ y, const float* __restrict__ mask,
+                                                         const float* __restrict__ eps, uint64_t seed, uint64_t offset,
+                                                         int n_samples, int64_t n, float* __restrict__ nll_map) {
+    __shared__ QuadSmem s;
+    __shared__ SchedSmem ss;
+    if (P.full_model) {
+        if (PATH == kSched) load_sched(P, ss);
+        else load_quad_tables(P, s);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = lane < nt;
+    const int my_col = live ? P.col_of_tau[lane] : -1;
+    const float my_tau = live ? P.tau[lane] : 0.f;
+    const float my_b = live ? P.blood_b[lane] : 0.f;
+    const int se = P.se_idx;
+    const bool multi = P.multi_image_normalisation != 0;
+    const bool in_norm = multi ? (lane >= se - 1 && lane <= se + 1) : (lane == se);
+    const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
+    const bool wide = nt > 16;
+    const float df = P.student_t_df;
+    const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
+    for (int64_t v = warp; v < n; v += nwarps) {
+        const float m = mask ? __ldg(mask + v) : 1.0f;
+        if (!(m != 0.0f)) {
+            if (lane == 0) nll_map[v] = 0.f;
+            continue;
+        }
+        Dist dq, dp;
+        QExtra ex;
+        load_dists(q + v * 5, nullptr, lane, dq, ex, dp);
+        const float yv = live ? __ldg(y + v * nt + lane) : 0.f;
+        const float sg = live ? __ldg(sigma + v * nt + lane) : 1.f;
+        const float ny = (multi ? sum_live(in_norm ? yv * norm_w : 0.f, wide) : __shfl_sync(kFull, yv, se)) + 1e-3f;
+        float yn = yv / ny;
+        if (P.predict_log_data) yn = logf(yn);
+        const float inv_sg = 1.0f / sg, log_sg = logf(sg);
+        float acc = 0.f;
+        for (int sidx = 0; sidx < n_samples; ++sidx) {
+            float e0, e1;
+            if (eps) {
+                const float2 e = __ldg(reinterpret_cast<const float2*>(eps) + (v * n_samples + sidx));
+                e0 = e.x;
+                e1 = e.y;
+            } else {
+                normal_pair(seed, offset + (uint64_t)v, kStreamKl + (uint32_t)sidx, e0, e1);
+            }
+            const Sample sm = draw(dq, ex, e0, e1);
+            const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
+            float I = 0.f, dI = 0.f;
+            if (P.full_model) tissue_eval<false, PATH>(P, s, ss, qc, vp.dw, vp.dw_k, I, dI);
+            const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, dI);
+            const float pred = live ? ts.S : 0.f;
+            const float npd = (multi ? sum_live(in_norm ? pred * norm_w : 0.f, wide) : __shfl_sync(kFull, pred, se)) + 1e-3f;
+            float pn = pred / npd;
+            if (P.predict_log_data) pn = logf(pn);
+            const float zq = (yn - pn) * inv_sg;
+            float nll_t;
+            if (df > 0.f) nll_t = -(P.student_t_logc - log_sg - 0.5f * (df + 1.0f) * log1pf(zq * zq / df));
+            else nll_t = -(-log_sg - kLogSqrt2Pi - 0.5f * (zq * zq));
+            acc += live ? nll_t : 0.f;
+        }
+        const float tot = sum_live(acc, wide);
+        if (lane == 0) nll_map[v] = (tot / (float)n_samples) * m;
+    }
+}
+
 // ReparamTrickLayer alone (model.py:21-50): one thread per voxel.
 __global__ void __launch_bounds__(kThreads) k_reparam(const float* __restrict__ q, const float* __restrict__ eps,
                                                       uint64_t seed, uint64_t offset, int64_t n,
@@ -544,6 +621,30 @@ extern "C" int qbold_kl(const float* q, const float* prior, const float* mask, c
                                                                                       offset, n_samples, n, kl_map,
                                                                                       grad_q);
     return after_launch("k_kl");
+}
+
+extern "C" int qbold_nll_map(const QboldParams* p, const float* q, const float* sigma, const float* y, const float* mask,
+                             const float* eps, uint64_t seed, uint64_t offset, int32_t n_samples, int64_t n,
+                             float* nll_map, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_nll_map: bad params block");
+    if (n < 0 || n_samples < 1) return fail(QBOLD_EINVAL, "qbold_nll_map: bad size");
+    if (n == 0) return QBOLD_OK;
+    if (!q || !sigma || !y || !nll_map) return fail(QBOLD_EINVAL, "qbold_nll_map: null pointer");
+    const int path = p->sched_phases > 0 ? kSched : (p->n_cols > kColGroup ? kColsMulti : kCols);
+    const int64_t want = (n + 7) / 8;
+    cudaStream_t st = (cudaStream_t)stream;
+#define QB_LAUNCH_NLL(PA)                                                                                            \
+    do {                                                                                                              \
+        static int64_t grid_cache = 0;                                                                                \
+        const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_nll_map<PA>, INT64_MAX / 64)); \
+        k_nll_map<PA><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(*p, q, sigma, y, mask, eps, seed,  \
+                                                                                 offset, n_samples, n, nll_map);     \
+    } while (0)
+    if (path == kSched) QB_LAUNCH_NLL(kSched);
+    else if (path == kCols) QB_LAUNCH_NLL(kCols);
+    else QB_LAUNCH_NLL(kColsMulti);
+#undef QB_LAUNCH_NLL
+    return after_launch("k_nll_map");
 }
 
 extern "C" int qbold_reparam_sample(const float* q, const float* eps, uint64_t seed, uint64_t offset, int64_t n,

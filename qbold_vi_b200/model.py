@@ -333,6 +333,35 @@ class EncoderTrainer:
             info['nll_map'], info['kl_map'] = out[2], out[3]
         return loss, info
 
+    # ------------------------------------------------------------------ whole-volume inference (model.py:772-887)
+    def likelihood_map(self, signal_layer, q_params, im_sigma, data, mask=None, no_samples=100, eps=None):
+        """Average per-voxel NLL over ``no_samples`` stochastic forward passes (save_predictions, model.py:808-817)."""
+        nt = signal_layer.n_tau
+        lead = tuple(q_params.shape[:-1])
+        q = q_params.reshape(-1, 5).float().contiguous()
+        n = q.shape[0]
+        sg = im_sigma.reshape(n, nt).float().contiguous()
+        y = data.reshape(n, nt).float().contiguous()
+        m = None if mask is None else mask.reshape(n).float().contiguous()
+        e = None if eps is None else eps.reshape(n, no_samples, 2).float().contiguous()
+        out = torch.empty(n, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            check(_lib.lib().qbold_nll_map(C.byref(self._params_for(signal_layer)), dptr(q), dptr(sg), dptr(y),
+                                           dptr(m, allow_none=True), dptr(e, allow_none=True), _next_seed(self), 0,
+                                           no_samples, n, dptr(out), stream_ptr(q.device)))
+        return out.reshape(lead + (1,))
+
+    def posterior_inference(self, signal_layer, q_params, im_sigma, data, mask, prior=None, no_samples=64):
+        """BASELINE config 4: per-voxel posterior summaries of a whole volume in three launches:
+        mean / variance of OEF, DBV, R2' (calculate_means), likelihood map and KL map."""
+        means, variances = self.calculate_means(q_params, mask, include_r2p=True, return_stds=True,
+                                                no_samples=no_samples, signal_layer=signal_layer)
+        out = {'means': means, 'variances': variances,
+               'likelihood': self.likelihood_map(signal_layer, q_params, im_sigma, data, mask, no_samples)}
+        if prior is not None:
+            out['kl'] = self.kl_loss(torch.cat([prior, mask], -1), q_params, return_mean=False, no_samples=no_samples)
+        return out
+
     # ------------------------------------------------------------------ adjacent losses (torch ops)
     def smoothness_loss(self, true_params, pred_params):
         """Total-variation term (model.py:726-754): x/y neighbours of the forward-transformed means."""

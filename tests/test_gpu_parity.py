@@ -404,3 +404,34 @@ def test_single_gpu_training_steps_reduce_the_loss(qb, dev, cfg_noise_off):
     losses = [dp.step(data, mask, prior) for _ in range(12)]
     assert all(np.isfinite(s['loss']) for s in losses)
     assert np.mean([s['nll'] for s in losses[-3:]]) < np.mean([s['nll'] for s in losses[:3]])
+
+
+# ---------------------------------------------------------------------------------- whole-volume inference (config 4)
+def test_likelihood_map_and_posterior_inference(qb, dev, cfg_noise_off, physics):
+    e = golden('ref_shim_elbo_optimal.npz')
+    tr = _trainer(qb, cfg_noise_off, seed=5)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    n, S = e['q'].shape[0], 12
+    eps = np.random.default_rng(4).standard_normal((n, S, 2)).astype(np.float32)
+    got = tr.likelihood_map(layer, _t(e['q'], dev), _t(e['sigma'], dev), _t(e['data'], dev), _t(e['mask'], dev),
+                            no_samples=S, eps=_t(eps, dev)).cpu().numpy().reshape(-1)
+    yt = np.concatenate([e['data'], e['mask'][:, None]], -1)
+    ref = np.zeros(n)
+    for s in range(S):                                          # model.py:810-817, one forward pass per sample
+        smp, _ = o.reparam_sample(e['q'], eps[:, s], True, np.float64)
+        pred = o.forward(physics, smp, dtype=np.float64)
+        ref += o.fine_tune_nll(yt, pred, e['sigma'], 2, np.float64, return_mean=False).reshape(-1)
+    assert rel_max(got, ref / S) < GRAD_TOL
+    # config 4 entry point: 64 samples per voxel on a volume, in-kernel Philox draws
+    q = _t(e['q'], dev).reshape(2, 4, 4, 2, 5)
+    res = tr.posterior_inference(layer, q, _t(e['sigma'], dev).reshape(2, 4, 4, 2, 11),
+                                 _t(e['data'], dev).reshape(2, 4, 4, 2, 11), _t(e['mask'], dev).reshape(2, 4, 4, 2, 1),
+                                 prior=_t(e['prior'], dev).reshape(2, 4, 4, 2, 5), no_samples=64)
+    assert tuple(res['means'].shape) == (2, 4, 4, 2, 3) and tuple(res['variances'].shape) == (2, 4, 4, 2, 3)
+    assert tuple(res['likelihood'].shape) == (2, 4, 4, 2, 1) and tuple(res['kl'].shape) == (2, 4, 4, 2, 1)
+    for v in res.values():
+        assert torch.isfinite(v).all()
+    m = res['means'].reshape(-1, 3)
+    assert float(m[:, 0].min()) > 0.04 and float(m[:, 0].max()) < 0.84 and float(res['variances'].min()) >= 0
+    dead = _t(e['mask'], dev) == 0
+    assert float(res['likelihood'].reshape(-1)[dead].abs().max()) == 0 and float(res['kl'].reshape(-1)[dead].abs().max()) == 0
