@@ -9,10 +9,10 @@ from . import _lib
 from ._lib import QboldError, build_library, fma_peak_tflops, launch_count
 from .config import (apply_yaml_overrides, get_defaults, load_arguments, load_system_parameters,
                      optimal_arguments)
-from .model import EncoderTrainer, ReparamTrickLayer, logit
+from .model import EncoderTrainer, FineTuner, ReparamTrickLayer, logit
 from .signals import SignalGenerationLayer, create_synthetic_dataset, generate_from_marginals, make_taus
 
 __all__ = ['SignalGenerationLayer', 'create_synthetic_dataset', 'generate_from_marginals', 'make_taus',
-           'ReparamTrickLayer', 'EncoderTrainer', 'logit', 'load_system_parameters', 'get_defaults',
+           'ReparamTrickLayer', 'EncoderTrainer', 'FineTuner', 'logit', 'load_system_parameters', 'get_defaults',
            'load_arguments', 'apply_yaml_overrides', 'optimal_arguments', 'QboldError', 'build_library',
            'fma_peak_tflops', 'launch_count']

@@ -28,6 +28,14 @@ def logit(signal):
     return torch.log(signal / (1.0 - signal))                                  # model.py:10-12
 
 
+def _as_mvg(params, use_mvg):
+    """Diagonal posterior (use_mvg=False, 4 channels: model.py:33-37, 406-421, 695-708) == the Cholesky
+    parameterisation with a zero raw off-diagonal (tanh(0) = 0): pad a fifth channel so the same kernels serve it."""
+    if use_mvg:
+        return params
+    return torch.cat([params[..., :4], torch.zeros_like(params[..., :1])], -1)
+
+
 def _next_seed(obj):
     obj._calls += 1
     return (obj._seed + 0x9E3779B97F4A7C15 * obj._calls) & 0xFFFFFFFFFFFFFFFF
@@ -68,10 +76,8 @@ class ReparamTrickLayer:
 
     def call(self, inputs, *args, eps=None, **kwargs):
         input, mask = inputs
-        if not self._encoder_trainer._use_mvg:
-            raise NotImplementedError('diagonal (use_mvg=False) posterior: SURVEY.md 8a row a14, second priority')
         lead = tuple(input.shape[:-1])
-        q = input.reshape(-1, 5).float().contiguous()
+        q = _as_mvg(input, self._encoder_trainer._use_mvg).reshape(-1, 5).float().contiguous()
         if eps is None:
             eps = torch.randn((q.shape[0], 2), dtype=torch.float32, device=q.device)
         eps = eps.reshape(-1, 2).float().contiguous()
@@ -220,7 +226,7 @@ class EncoderTrainer:
                         signal_layer=None):
         """Posterior means (and the reference's 'stds', which are variances: model.py:331,337)."""
         lead = tuple(predicted_params.shape[:-1])
-        q = predicted_params.reshape(-1, 5).float().contiguous()
+        q = _as_mvg(predicted_params, self._use_mvg).reshape(-1, 5).float().contiguous()
         n = q.shape[0]
         mean3 = torch.empty((n, 3), dtype=torch.float32, device=q.device)
         var3 = torch.empty((n, 3), dtype=torch.float32, device=q.device)
@@ -289,10 +295,16 @@ class EncoderTrainer:
 
     def kl_loss(self, true, predicted, return_mean=True, no_samples=70, eps=None):
         """KL(q || prior) by the reference's 70-sample MC estimator; ``no_samples=0`` selects the closed form."""
-        if not self._use_mvg:
-            raise NotImplementedError('diagonal / MoG KL variants: SURVEY.md 8a row a14, second priority')
+        if self._use_population_prior:
+            raise NotImplementedError('population-prior / MoG KL variants (model.py:666-716) are not provided')
         true = torch.cat([true for _ in range(self._no_samples)], 0)
-        prior_dist, mask = true[..., :5], true[..., 5:6]
+        if self._use_mvg:
+            prior_dist, mask = true[..., :5], true[..., 5:6]
+        else:
+            # diagonal posterior: the reference uses the analytic LogitNormal KL (model.py:695-708) == the
+            # closed-form Gaussian KL in logit space with zero off-diagonals
+            prior_dist, mask = _as_mvg(true[..., :4], False), true[..., 4:5]
+            predicted, no_samples, eps = _as_mvg(predicted, False), 0, None
         lead = tuple(predicted.shape[:-1])
         m = mask.reshape(-1).float().contiguous()
         kl = _KlFn.apply(predicted.reshape(-1, 5).float().contiguous(),
@@ -312,6 +324,9 @@ class EncoderTrainer:
         prior [...,5] raw or None.  ``mask_sum`` = global sum(mask) when the batch is sharded over ranks.
         Returns (loss, dict(nll, kl[, nll_map, kl_map])) with the reference's normalisation (sum / sum(mask))."""
         nt = signal_layer.n_tau
+        if not self._use_mvg:
+            q_params, kl_samples = _as_mvg(q_params, False), 0          # analytic KL, as the reference (model.py:695-708)
+            prior = None if prior is None else _as_mvg(prior, False)
         q = q_params.reshape(-1, 5).float().contiguous()
         n = q.shape[0]
         sg = im_sigma.reshape(n, nt).float().contiguous()
@@ -332,6 +347,13 @@ class EncoderTrainer:
         if return_maps:
             info['nll_map'], info['kl_map'] = out[2], out[3]
         return loss, info
+
+    # ------------------------------------------------------------------ glue graph (model.py:239-286)
+    def build_fine_tuner(self, encoder_model, signal_generation_layer, input_im=None, input_mask=None):
+        """Returns the fine-tuning model: ``model(data, mask)`` gives the reference's output dict
+        {'predictions': q [...,5], 'predicted_images': concat[signal, sigma] [...,2*n_tau]} through the separate
+        layers (sample -> forward model), and ``model.fused_loss(...)`` the one-launch training objective."""
+        return FineTuner(self, encoder_model, signal_generation_layer)
 
     # ------------------------------------------------------------------ whole-volume inference (model.py:772-887)
     def likelihood_map(self, signal_layer, q_params, im_sigma, data, mask=None, no_samples=100, eps=None):
@@ -398,3 +420,25 @@ class EncoderTrainer:
             raise NotImplementedError('only the optimal.yaml branch of synthetic_data_loss is provided')
         y_true = y_true_orig.reshape(-1, 3)
         return torch.mean(self.logit_gaussian_mvg_log_prob(y_true[:, :2], y_pred_orig.reshape(-1, 5)))
+
+
+class FineTuner(torch.nn.Module):
+    """build_fine_tuner (model.py:239-286) as a module; the encoder is any callable returning
+    (q_voxelwise, q_spatial, sigma) like qbold_vi_b200.encoder.Encoder."""
+
+    def __init__(self, trainer, encoder_model, signal_generation_layer):
+        super().__init__()
+        self.trainer, self.encoder, self.layer = trainer, encoder_model, signal_generation_layer
+        self.reparam = ReparamTrickLayer(trainer)
+
+    def forward(self, data, mask, eps=None):
+        _, q, sigma = self.encoder(data)
+        k = self.trainer._no_samples
+        q_rep, sigma_rep = torch.cat([q] * k, 0), torch.cat([sigma] * k, 0)               # model.py:245-246
+        sampled = self.reparam((q_rep, mask), eps=eps)                                    # :248
+        pred = self.layer(sampled)                                                        # :273
+        return {'predictions': q_rep, 'predicted_images': torch.cat([pred, sigma_rep], -1)}   # :276,284-285
+
+    def fused_loss(self, data, mask, prior, **kw):
+        _, q, sigma = self.encoder(data)
+        return self.trainer.fused_elbo(self.layer, q, sigma, data, mask, prior, **kw)

@@ -83,9 +83,8 @@ class SignalGenerationLayer:
         self._include_blood = _as_bool(include_blood)
         self._misaligned_prob = float(misaligned_prob)
         self._variable_hct = bool(variable_hct)
-        if self._misaligned_prob > 0.0:
-            raise NotImplementedError('misalignment augmentation (signals.py:80-96) is a "next" row of the scope '
-                                      'table (SURVEY.md 8a, a8); optimal.yaml sets misalign_prob 0.0')
+        if self._misaligned_prob > 0.0 and self._variable_hct:
+            raise NotImplementedError('misalignment augmentation with variable_hct is not provided')
         self._seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self._calls = 0
 
@@ -119,9 +118,32 @@ class SignalGenerationLayer:
             signal = _ForwardFn.apply(flat, self)
         else:
             signal = self._forward_raw(flat)
+        if self._misaligned_prob > 0.0:
+            signal = self._misalign(flat, signal)
         if self._simulate_noise:
             signal = self.add_noise(signal)
         return signal.reshape(tuple(input.shape[:-1]) + (self.n_tau,))
+
+    def _misalign(self, flat, signal):
+        """Misalignment augmentation (signals.py:80-96): a Bernoulli(p) subset of voxels gets, for the images after a
+        random index in [4, n_tau-1), the signal of perturbed parameters (OEF + N(0,0.15) clipped to [0.05,0.8],
+        DBV + N(0,0.05) clipped to [0.002,0.3]).  The perturbed signals come from a second forward launch on the
+        selected voxels only; the per-image blend is the reference's mask arithmetic."""
+        n, nt = flat.shape[0], self.n_tau
+        dev = flat.device
+        misaligned = torch.rand(n, device=dev) < self._misaligned_prob                               # :82
+        from_index = torch.randint(4, nt - 1, (n,), device=dev)                                      # :84-85
+        idx = torch.nonzero(misaligned).reshape(-1)
+        if idx.numel() == 0:
+            return signal
+        sel = flat.detach()[idx]
+        pert = torch.stack([(torch.randn(idx.numel(), device=dev) * 0.15 + sel[:, 0]).clamp(0.05, 0.8),   # :92
+                            (torch.randn(idx.numel(), device=dev) * 0.05 + sel[:, 1]).clamp(0.002, 0.3)], -1)  # :93
+        s2 = self._forward_raw(pert.contiguous())
+        late = torch.arange(nt, device=dev)[None, :] > from_index[idx, None]                         # :86-88
+        out = signal.clone()
+        out[idx] = torch.where(late, s2, signal[idx])                                                # :95-96
+        return out
 
     @staticmethod
     def calculate_dw_static(oef, hct, gamma, b0, dchi):

@@ -435,3 +435,58 @@ def test_likelihood_map_and_posterior_inference(qb, dev, cfg_noise_off, physics)
     assert float(m[:, 0].min()) > 0.04 and float(m[:, 0].max()) < 0.84 and float(res['variances'].min()) >= 0
     dead = _t(e['mask'], dev) == 0
     assert float(res['likelihood'].reshape(-1)[dead].abs().max()) == 0 and float(res['kl'].reshape(-1)[dead].abs().max()) == 0
+
+
+# ---------------------------------------------------------------------------------- remaining rows of the scope table
+def test_misalignment_augmentation(qb, dev, cfg_noise_off):
+    """signals.py:80-96: images up to index 4 are never touched; a misaligned voxel's later images come from
+    perturbed OEF/DBV; probability 1 hits every voxel, the observed fraction follows the probability."""
+    x = _t(_rand_voxels(4096, 12), dev)
+    clean = qb.SignalGenerationLayer(cfg_noise_off, True, True)(x)
+    torch.manual_seed(3)
+    aug = qb.SignalGenerationLayer(cfg_noise_off, True, True, misaligned_prob=1.0)(x)
+    assert torch.equal(aug[:, :5], clean[:, :5])
+    changed = (aug != clean).any(-1)
+    assert float(changed.float().mean()) > 0.99
+    first = (aug != clean).float().argmax(-1)[changed]
+    assert int(first.min()) >= 5 and int(first.max()) <= 10              # from_index in [4, n_tau-1) -> first changed image 5..10
+    torch.manual_seed(4)
+    aug = qb.SignalGenerationLayer(cfg_noise_off, True, True, misaligned_prob=0.25)(x)
+    frac = float((aug != clean).any(-1).float().mean())
+    assert 0.2 < frac < 0.3 and torch.isfinite(aug).all()
+
+
+def test_diagonal_posterior_variant(qb, dev, cfg_noise_off):
+    """use_mvg=False (model.py:33-37, 695-708): 4 parameters per voxel, analytic KL == two 1-D Gaussian KLs."""
+    e = golden('ref_shim_elbo_optimal.npz')
+    tr = _trainer(qb, cfg_noise_off, use_mvg=False)
+    q4, p4 = e['q'][:, :4], e['prior'][:, :4]
+    smp = qb.ReparamTrickLayer(tr)((_t(q4, dev), None), eps=_t(e['eps'], dev)).cpu().numpy()
+    sd_o, sd_d = np.exp(np.tanh(q4[:, 1]) * 3 - 1), np.exp(np.tanh(q4[:, 3]) * 3 - 1)
+    z = np.stack([q4[:, 0] + e['eps'][:, 0] * sd_o, q4[:, 2] + e['eps'][:, 1] * sd_d], -1)
+    assert rel_elem(smp, o.forward_transform(z, np.float64)) < SIG_TOL
+    true = torch.cat([_t(p4, dev), _t(e['mask'], dev)[:, None]], -1)
+    kl = tr.kl_loss(true, _t(q4, dev), return_mean=False).cpu().numpy().reshape(-1)
+
+    def kl1(mq, lq, mp, lp):                                              # KL(N(mq, e^lq) || N(mp, e^lp))
+        return lp - lq + (np.exp(2 * lq) + (mq - mp) ** 2) / (2 * np.exp(2 * lp)) - 0.5
+    ls = lambda a: np.tanh(a.astype(np.float64)) * 3 - 1
+    ref = kl1(q4[:, 0], ls(q4[:, 1]), p4[:, 0], ls(p4[:, 1])) + kl1(q4[:, 2], ls(q4[:, 3]), p4[:, 2], ls(p4[:, 3]))
+    assert rel_max(kl, np.where(e['mask'] > 0, ref, 0)) < 1e-5
+
+
+def test_fine_tuner_module_outputs(qb, dev, cfg_noise_off):
+    from qbold_vi_b200.encoder import Encoder
+    torch.manual_seed(0)
+    tr = _trainer(qb, cfg_noise_off)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    ft = tr.build_fine_tuner(Encoder(no_units=8, no_intermediate_layers=1).to(dev), layer)
+    data = torch.rand(1, 5, 4, 2, 11, device=dev) + 0.5
+    mask = torch.ones(1, 5, 4, 2, 1, device=dev)
+    out = ft(data, mask)
+    assert tuple(out['predictions'].shape) == (1, 5, 4, 2, 5) and tuple(out['predicted_images'].shape) == (1, 5, 4, 2, 22)
+    nll = tr.fine_tune_loss_fn(torch.cat([data, mask], -1), out['predicted_images'])
+    nll.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ft.encoder.parameters() if p.requires_grad)
+    loss, info = ft.fused_loss(data, mask, out['predictions'].detach())
+    assert torch.isfinite(loss)

@@ -76,7 +76,7 @@ def test_layer_argument_handling(qb):
     with pytest.raises(ValueError):
         qb.SignalGenerationLayer(cfg, 'yes', True)
     with pytest.raises(NotImplementedError):
-        qb.SignalGenerationLayer(cfg, True, True, misaligned_prob=0.1)
+        qb.SignalGenerationLayer(cfg, True, True, misaligned_prob=0.1, variable_hct=True)
     import torch
     layer = qb.SignalGenerationLayer(cfg, True, True)
     with pytest.raises(AssertionError):
