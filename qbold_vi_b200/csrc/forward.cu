@@ -58,6 +58,86 @@ __global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward(const _
     }
 }
 
+// Paired variant of the scheduled path (n_tau <= 16, fixed Hct): a warp takes TWO voxels per iteration.  The two
+// quadratures still run one after the other on all 32 lanes, but everything that only needs n_tau lanes -- loads,
+// per-voxel physics, exp / blood / mixing epilogue, gradient reduction, stores -- is done once for both, voxel 0 on
+// lanes 0-15 and voxel 1 on lanes 16-31 (about 120 fewer warp instructions per voxel).
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward_pair(const __grid_constant__ QboldParams P,
+                                                                              const float* __restrict__ oef_dbv,
+                                                                              const float* __restrict__ g_signal,
+                                                                              float* __restrict__ signal,
+                                                                              float* __restrict__ g_oef_dbv, int64_t n) {
+    __shared__ SchedSmem ss;
+    load_sched(P, ss);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = t < nt;
+    const int my_col = live ? P.col_of_tau[t] : -1;
+    const float my_tau = live ? P.tau[t] : 0.f;
+    const float my_b = live ? P.blood_b[t] : 0.f;
+    const QuadCtx qc = make_quad_ctx<kSched>(P, ss, lane, my_col, my_tau);
+    const int64_t npairs = (n + 1) >> 1;
+
+    for (int64_t pr = warp; pr < npairs; pr += nwarps) {
+        const int64_t v = pr * 2 + half;
+        const bool valid = v < n;
+        float2 x = make_float2(0.f, 0.f);
+        if (valid) x = __ldg(reinterpret_cast<const float2*>(oef_dbv) + v);
+        float gs = 1.0f;
+        if (BWD && g_signal != nullptr && live && valid) gs = __ldg(g_signal + v * nt + t);
+        const VoxelPhys vp = voxel_phys<false>(P, x.x, x.y, P.hct);
+        const float A_mine = qc.tau_ref15 * vp.dw;
+        float I = 0.f, Dm = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const float A = __shfl_sync(kFull, A_mine, h << 4);
+            float vi, vd;
+            tissue_sched<BWD>(qc.nph, qc.sa, A, lane, qc.ph_lo, qc.ph_hi, my_col, vi, vd);
+            if (half == h) {
+                I = vi;
+                Dm = vd;
+            }
+        }
+        const float a_t = 1.5f * (fabsf(my_tau) * vp.dw);
+        float dI = 0.f;
+        if (BWD) dI = (Dm * qc.tau_ref15 + qc.node0_d * a_t) * vp.dw_k;
+        if (my_col >= 0) I += node0_value(P, a_t);
+        const TauSignal ts = tau_signal<BWD>(P, vp, my_tau, my_b, I, dI);
+        if (live && valid && signal != nullptr) signal[v * nt + t] = ts.S;
+        if (BWD) {
+            float go = live ? gs * ts.dS_doef : 0.f;
+            float gd = live ? gs * ts.dS_ddbv : 0.f;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                go += __shfl_xor_sync(kFull, go, o);
+                gd += __shfl_xor_sync(kFull, gd, o);
+            }
+            if (t == 0 && valid) *reinterpret_cast<float2*>(g_oef_dbv + v * 2) = make_float2(go, gd);
+        }
+    }
+}
+
+template <bool BWD>
+static int launch_forward_pair(const QboldParams* p, const float* oef_dbv, const float* g, float* signal, float* grad,
+                               int64_t n, cudaStream_t st) {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_forward_pair<BWD>, kThreads, 0) !=
+                cudaSuccess || blocks_per_sm < 1)
+            blocks_per_sm = 1;
+    }
+    const int64_t want = ((n + 1) / 2 + (kThreads / 32) - 1) / (kThreads / 32);
+    int64_t grid = (int64_t)sm_count() * blocks_per_sm;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    k_forward_pair<BWD><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n);
+    return after_launch("k_forward_pair");
+}
+
 // Log-linear branch (full_model = False, reference signals.py:194-207): ~30 FLOP per 52-104 B, i.e. HBM-bound.
 // One thread per voxel; the [256 x n_tau] signal / upstream-gradient tiles go through shared memory so that
 // every global access is a coalesced 16-byte vector (a CTA's rows are one contiguous 256*n_tau*4-byte span).
@@ -142,6 +222,8 @@ template <bool BWD, bool HCT>
 static int launch_forward(const QboldParams* p, const float* oef_dbv, const float* g, float* signal,
                           float* grad, int64_t n, cudaStream_t st) {
     if (!p->full_model && !HCT) return launch_loglinear<BWD>(p, oef_dbv, g, signal, grad, n, st);
+    if (p->sched_phases > 0 && p->full_model && !HCT && p->n_tau <= 16)
+        return launch_forward_pair<BWD>(p, oef_dbv, g, signal, grad, n, st);
     if (p->sched_phases > 0) return launch_forward_t<BWD, HCT, kSched>(p, oef_dbv, g, signal, grad, n, st);
     return p->n_cols > kColGroup ? launch_forward_t<BWD, HCT, kColsMulti>(p, oef_dbv, g, signal, grad, n, st)
                                  : launch_forward_t<BWD, HCT, kCols>(p, oef_dbv, g, signal, grad, n, st);
