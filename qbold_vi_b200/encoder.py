@@ -21,20 +21,21 @@ def _he_normal_(w, fan_in):
 
 
 class _Conv331(nn.Module):
-    """keras Conv3D(kernel_size=(3,3,1), padding='same') on a channels-last volume: a 2-D conv over (X, Y)
-    applied to every z slice (so z-slabs need no halo when volumes are sharded)."""
+    """keras Conv3D(kernel_size=(3,3,1), padding='same') on a channels-last volume.  The reference layout
+    [B, X, Y, Z, C] IS torch's channels_last_3d layout of a [B, C, X, Y, Z] tensor, so the permutes below are views
+    (no transposes hit HBM) and cuDNN runs its NDHWC kernels; the kernel never mixes z slices, so z-slabs need no
+    halo when volumes are sharded."""
 
     def __init__(self, c_in, c_out, std):
         super().__init__()
-        self.conv = nn.Conv2d(c_in, c_out, 3, padding=1)
+        self.conv = nn.Conv3d(c_in, c_out, (3, 3, 1), padding=(1, 1, 0))
         nn.init.normal_(self.conv.weight, std=std)
         nn.init.zeros_(self.conv.bias)
+        self.conv.weight.data = self.conv.weight.data.contiguous(memory_format=torch.channels_last_3d)
 
-    def forward(self, x):                                   # [B, X, Y, Z, C]
-        b, nx, ny, nz, c = x.shape
-        y = x.permute(0, 3, 4, 1, 2).reshape(b * nz, c, nx, ny)
-        y = self.conv(y)
-        return y.reshape(b, nz, -1, nx, ny).permute(0, 3, 4, 1, 2)
+    def forward(self, x):                                   # [B, X, Y, Z, C], contiguous
+        y = self.conv(x.permute(0, 4, 1, 2, 3))             # view: [B, C, X, Y, Z] in channels_last_3d strides
+        return y.permute(0, 2, 3, 4, 1)
 
 
 class _Block(nn.Module):

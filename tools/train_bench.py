@@ -24,9 +24,14 @@ def main():
     ap.add_argument('--volumes-per-gpu', type=int, default=2)
     ap.add_argument('--size', type=int, default=64)
     ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--amp', action='store_true', help='bf16 autocast for the encoder (parity runs keep fp32)')
+    ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32', 'bf16'],
+                    help='encoder arithmetic: TF32 tensor cores (default), strict fp32, or bf16 autocast; the qBOLD '
+                         'kernels are always fp32')
     a = ap.parse_args()
     rank, world, dev = D.init_distributed()
+    a.amp = a.precision == 'bf16'
+    torch.backends.cuda.matmul.allow_tf32 = a.precision != 'fp32'
+    torch.backends.cudnn.allow_tf32 = a.precision != 'fp32'
     args = qb.optimal_arguments()
     cfg = qb.load_system_parameters(qb.config.DEFAULT_CONFIG_PATH)
     cfg['simulate_noise'] = 'False'
@@ -84,8 +89,9 @@ def main():
     # where the step time goes on one rank
     def enc_only():
         dp.bucket.zero_()
-        _, q, s = enc(data)
-        (q.sum() + s.sum()).backward()
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=a.amp):
+            _, q, s = enc(data)
+        (q.float().sum() + s.float().sum()).backward()
     ms_enc = timed(enc_only, a.steps)
     with torch.no_grad():
         _, q, sigma = enc(data)
@@ -96,7 +102,7 @@ def main():
     if rank == 0:
         common = {'n_gpus': world, 'volumes_per_gpu': B, 'volume': '%d^3' % S, 'voxels_per_gpu': voxels,
                   'masked_fraction': float(mask.mean()), 'encoder_params': sum(p.numel() for p in enc.parameters()),
-                  'encoder_precision': 'bf16 autocast' if a.amp else 'fp32 (TF32 off)'}
+                  'encoder_precision': a.precision}
         print(json.dumps(dict(common, config='3/5: VI training step (encoder fwd+bwd, fused ELBO 70-sample KL, TV, '
                               'grad all-reduce, AdamW)', ms_per_step=ms_train,
                               voxel_signals_per_s=world * voxels * 11 / ms_train * 1e3,
