@@ -40,45 +40,49 @@ struct QExtra {
     float sd_o, sd_d, dls_o, dls_d, dcov;
 };
 
-// Lanes 0..2 transform q[1], q[3], q[4]; lanes 3..5 the prior's; lanes 6/7 the off-diagonal
-// inverse factor.  One tanhf + two expf per lane instead of 6 + 8 on every lane.
+// A group of W lanes (32: the whole warp, 16: one half of a paired warp) serves one voxel.  Lanes 0..2 of the
+// group transform q[1], q[3], q[4]; lanes 3..5 the prior's; lanes 6/7 the off-diagonal inverse factor.  One tanhf
+// + two expf per lane instead of 6 + 8 on every lane; shuffles broadcast inside the group.
+template <int W = 32>
 __device__ __forceinline__ void load_dists(const float* __restrict__ q, const float* __restrict__ prior,
                                            int lane, Dist& dq, QExtra& ex, Dist& dp) {
-    const int sel = lane % 3;
+    const int t = lane & (W - 1), gb = lane & ~(W - 1);
+    const int sel = t % 3;
     const int idx = sel == 0 ? 1 : (sel == 1 ? 3 : 4);
-    const float* src = (lane < 3 || prior == nullptr) ? q : prior;
-    const float raw = (lane < 6) ? __ldg(src + idx) : 0.f;
+    const float* src = (t < 3 || prior == nullptr) ? q : prior;
+    const float raw = (t < 6) ? __ldg(src + idx) : 0.f;
     const float th = tanhf(raw);
     const float ls = th * 3.0f - 1.0f;                       // transform_std, model.py:288-290
     const float e = expf(ls);
     const float ie = expf(ls * -1.0f);                       // model.py:432-433
-    const float th1 = __shfl_sync(kFull, th, 0), th3 = __shfl_sync(kFull, th, 1), th4 = __shfl_sync(kFull, th, 2);
+    const float th1 = __shfl_sync(kFull, th, gb + 0), th3 = __shfl_sync(kFull, th, gb + 1);
+    const float th4 = __shfl_sync(kFull, th, gb + 2);
     dq.mu_o = __ldg(q + 0);
     dq.mu_d = __ldg(q + 2);
-    dq.ls_o = __shfl_sync(kFull, ls, 0);
-    dq.ls_d = __shfl_sync(kFull, ls, 1);
+    dq.ls_o = __shfl_sync(kFull, ls, gb + 0);
+    dq.ls_d = __shfl_sync(kFull, ls, gb + 1);
     dq.cov = th4 * kExpM2;                                   // transform_offdiag, model.py:292-294
-    dq.inv_o = __shfl_sync(kFull, ie, 0);
-    dq.inv_d = __shfl_sync(kFull, ie, 1);
-    ex.sd_o = __shfl_sync(kFull, e, 0);
-    ex.sd_d = __shfl_sync(kFull, e, 1);
+    dq.inv_o = __shfl_sync(kFull, ie, gb + 0);
+    dq.inv_d = __shfl_sync(kFull, ie, gb + 1);
+    ex.sd_o = __shfl_sync(kFull, e, gb + 0);
+    ex.sd_d = __shfl_sync(kFull, e, gb + 1);
     ex.dls_o = 3.0f * (1.0f - th1 * th1);
     ex.dls_d = 3.0f * (1.0f - th3 * th3);
     ex.dcov = kExpM2 * (1.0f - th4 * th4);
-    const float pth4 = __shfl_sync(kFull, th, 5);
-    dp.ls_o = __shfl_sync(kFull, ls, 3);
-    dp.ls_d = __shfl_sync(kFull, ls, 4);
+    const float pth4 = __shfl_sync(kFull, th, gb + 5);
+    dp.ls_o = __shfl_sync(kFull, ls, gb + 3);
+    dp.ls_d = __shfl_sync(kFull, ls, gb + 4);
     dp.cov = pth4 * kExpM2;
-    dp.inv_o = __shfl_sync(kFull, ie, 3);
-    dp.inv_d = __shfl_sync(kFull, ie, 4);
+    dp.inv_o = __shfl_sync(kFull, ie, gb + 3);
+    dp.inv_d = __shfl_sync(kFull, ie, gb + 4);
     dp.mu_o = prior ? __ldg(prior + 0) : 0.f;
     dp.mu_d = prior ? __ldg(prior + 2) : 0.f;
-    // inv_bl = exp(-ls_o + -ls_d) * cov * -1   (model.py:434); lanes 6 (q) and 7 (prior)
-    const float a = (lane == 7) ? dp.ls_o : dq.ls_o, b = (lane == 7) ? dp.ls_d : dq.ls_d;
-    const float c = (lane == 7) ? dp.cov : dq.cov;
+    // inv_bl = exp(-ls_o + -ls_d) * cov * -1   (model.py:434); lanes 6 (q) and 7 (prior) of the group
+    const float a = (t == 7) ? dp.ls_o : dq.ls_o, b = (t == 7) ? dp.ls_d : dq.ls_d;
+    const float c = (t == 7) ? dp.cov : dq.cov;
     const float bl = (expf(a * -1.0f + b * -1.0f) * c) * -1.0f;
-    dq.inv_bl = __shfl_sync(kFull, bl, 6);
-    dp.inv_bl = __shfl_sync(kFull, bl, 7);
+    dq.inv_bl = __shfl_sync(kFull, bl, gb + 6);
+    dp.inv_bl = __shfl_sync(kFull, bl, gb + 7);
 }
 
 struct Sample {
@@ -147,13 +151,14 @@ struct KlOut {
     float g[5];
 };
 
+template <int W = 32>
 __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const Dist& dp,
                                          const float* __restrict__ eps_v, uint64_t seed, uint64_t index,
                                          int n_samples, int lane) {
     KlOut o;
     if (n_samples > 0) {
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int sidx = lane; sidx < n_samples; sidx += 32) {
+        for (int sidx = lane & (W - 1); sidx < n_samples; sidx += W) {
             float k0, k1;
             if (eps_v) {
                 const float2 e = __ldg(reinterpret_cast<const float2*>(eps_v) + sidx);
@@ -182,14 +187,28 @@ __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const
             a[3] += hz_d * k1;
             a[4] += hz_d * k0;
         }
-        const float tot = butterfly8(a, lane);
         const float inv_s = 1.0f / (float)n_samples;
-        o.g[0] = __shfl_sync(kFull, tot, butterfly8_src_lane(0)) * inv_s;
-        o.g[1] = __shfl_sync(kFull, tot, butterfly8_src_lane(1)) * inv_s * ex.sd_o * ex.dls_o;
-        o.g[2] = __shfl_sync(kFull, tot, butterfly8_src_lane(2)) * inv_s;
-        o.g[3] = __shfl_sync(kFull, tot, butterfly8_src_lane(3)) * inv_s * ex.sd_d * ex.dls_d;
-        o.g[4] = __shfl_sync(kFull, tot, butterfly8_src_lane(4)) * inv_s * ex.dcov;
-        o.kl = __shfl_sync(kFull, tot, butterfly8_src_lane(5)) * inv_s;
+        if (W == 32) {
+            const float tot = butterfly8(a, lane);
+            a[0] = __shfl_sync(kFull, tot, butterfly8_src_lane(0));
+            a[1] = __shfl_sync(kFull, tot, butterfly8_src_lane(1));
+            a[2] = __shfl_sync(kFull, tot, butterfly8_src_lane(2));
+            a[3] = __shfl_sync(kFull, tot, butterfly8_src_lane(3));
+            a[4] = __shfl_sync(kFull, tot, butterfly8_src_lane(4));
+            a[5] = __shfl_sync(kFull, tot, butterfly8_src_lane(5));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int o2 = W / 2; o2 > 0; o2 >>= 1) a[i] += __shfl_xor_sync(kFull, a[i], o2);
+            }
+        }
+        o.g[0] = a[0] * inv_s;
+        o.g[1] = a[1] * inv_s * ex.sd_o * ex.dls_o;
+        o.g[2] = a[2] * inv_s;
+        o.g[3] = a[3] * inv_s * ex.sd_d * ex.dls_d;
+        o.g[4] = a[4] * inv_s * ex.dcov;
+        o.kl = a[5] * inv_s;
     } else {
         const float m00 = ex.sd_o * dp.inv_o;
         const float m10 = (dq.cov - dp.cov * m00) * dp.inv_d;
@@ -397,6 +416,181 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
     }
 }
 
+// Paired variant of k_elbo for the scheduled path with n_tau <= 16: a warp takes TWO voxels per iteration.  Only the
+// two quadratures run on all 32 lanes (one after the other); the parameter transforms, the sample, the per-tau
+// likelihood, its reductions, the KL (lanes = samples, 16 per pass) and all loads / stores are done once for both
+// voxels, voxel 0 on lanes 0-15 and voxel 1 on lanes 16-31.
+template <bool HAS_PRIOR>
+__global__ void __launch_bounds__(kThreads, 3) k_elbo_pair(const __grid_constant__ QboldParams P,
+                                                           const float* __restrict__ q, const float* __restrict__ sigma,
+                                                           const float* __restrict__ y, const float* __restrict__ mask,
+                                                           const float* __restrict__ prior, const float* __restrict__ eps,
+                                                           const float* __restrict__ eps_kl, uint64_t seed,
+                                                           uint64_t offset, int kl_samples, float inv_mask_sum,
+                                                           float kl_weight, int64_t n, float* __restrict__ grad_q,
+                                                           float* __restrict__ grad_sigma, float* __restrict__ nll_map,
+                                                           float* __restrict__ kl_map, double* __restrict__ sums) {
+    __shared__ SchedSmem ss;
+    load_sched(P, ss);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15, gb = lane & 16;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = t < nt;
+    const int my_col = live ? P.col_of_tau[t] : -1;
+    const float my_tau = live ? P.tau[t] : 0.f;
+    const float my_b = live ? P.blood_b[t] : 0.f;
+    const int se = P.se_idx;
+    const bool multi = P.multi_image_normalisation != 0;
+    const bool in_norm = multi ? (t >= se - 1 && t <= se + 1) : (t == se);
+    const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
+    const float df = P.student_t_df;
+    const QuadCtx qc = make_quad_ctx<kSched>(P, ss, lane, my_col, my_tau);
+    const int64_t npairs = (n + 1) >> 1;
+    double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
+    int bad = 0;
+
+    for (int64_t pr = warp; pr < npairs; pr += nwarps) {
+        int64_t v = pr * 2 + half;
+        const bool valid = v < n;
+        if (!valid) v = n - 1;                               // odd tail: mirror the last voxel, store nothing
+        const float m = valid ? __ldg(mask + v) : 0.f;
+        const bool on = (m != 0.0f);
+        if (!__any_sync(kFull, on)) {
+            // both voxels masked: nll * 0 and where(mask > 0, kl, 0) (model.py:564,661) -> zero loss and gradient
+            if (valid) {
+                if (t < 5) grad_q[v * 5 + t] = 0.f;
+                if (live) grad_sigma[v * nt + t] = 0.f;
+                if (t == 0) {
+                    if (nll_map) nll_map[v] = 0.f;
+                    if (kl_map) kl_map[v] = 0.f;
+                }
+            }
+            continue;
+        }
+        Dist dq, dp;
+        QExtra ex;
+        load_dists<16>(q + v * 5, HAS_PRIOR ? prior + v * 5 : nullptr, lane, dq, ex, dp);
+        float e0, e1;
+        if (eps) {
+            e0 = __ldg(eps + v * 2);
+            e1 = __ldg(eps + v * 2 + 1);
+        } else {
+            normal_pair(seed, offset + (uint64_t)v, kStreamReparam, e0, e1);
+        }
+        const Sample sm = draw(dq, ex, e0, e1);
+        const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
+        const float A_mine = qc.tau_ref15 * vp.dw;
+        const unsigned on_mask = __ballot_sync(kFull, on);
+        float I = 0.f, Dm = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            if (!((on_mask >> (h << 4)) & 1u)) continue;     // this voxel is masked: skip its quadrature
+            const float A = __shfl_sync(kFull, A_mine, h << 4);
+            float vi, vd;
+            tissue_sched<true>(qc.nph, qc.sa, A, lane, qc.ph_lo, qc.ph_hi, my_col, vi, vd);
+            if (half == h) {
+                I = vi;
+                Dm = vd;
+            }
+        }
+        const float a_t = 1.5f * (fabsf(my_tau) * vp.dw);
+        const float dI = (Dm * qc.tau_ref15 + qc.node0_d * a_t) * vp.dw_k;
+        if (my_col >= 0) I += node0_value(P, a_t);
+        const TauSignal ts = tau_signal<true>(P, vp, my_tau, my_b, I, dI);
+
+        // ---- fine_tune_loss_fn (model.py:527-568), all reductions inside the 16-lane half
+        const float yv = live ? __ldg(y + v * nt + t) : 0.f;
+        const float sg = live ? __ldg(sigma + v * nt + t) : 1.f;
+        const float pred = live ? ts.S : 0.f;
+        float npd, ny;
+        if (multi) {
+            npd = sum_live(in_norm ? pred * norm_w : 0.f, false) + 1e-3f;
+            ny = sum_live(in_norm ? yv * norm_w : 0.f, false) + 1e-3f;
+        } else {
+            npd = __shfl_sync(kFull, pred, gb + se) + 1e-3f;
+            ny = __shfl_sync(kFull, yv, gb + se) + 1e-3f;
+        }
+        const float inv_npd = 1.0f / npd, inv_sg = 1.0f / sg;
+        float yn = yv / ny, pn = pred * inv_npd;
+        float dpn = 1.0f;
+        if (P.predict_log_data) {
+            dpn = 1.0f / pn;
+            yn = logf(yn);
+            pn = logf(pn);
+        }
+        const float zq = (yn - pn) * inv_sg;
+        float nll_t, dnll_dres, dnll_dsg;
+        if (df > 0.f) {
+            student_t_terms(P.student_t_logc, df, zq, sg, inv_sg, nll_t, dnll_dres, dnll_dsg);
+        } else {
+            nll_t = -(-logf(sg) - kLogSqrt2Pi - 0.5f * (zq * zq));
+            dnll_dres = zq * inv_sg;
+            dnll_dsg = inv_sg - (zq * zq) * inv_sg;
+        }
+        if (!live) nll_t = 0.f;
+        const float scale = m * inv_mask_sum;
+        const float g_ratio = live ? (-dnll_dres * scale) * dpn : 0.f;
+        const float nll_v = sum_live(nll_t, false);
+        const float s_gp = sum_live(g_ratio * pred, false);
+        const float s_go = sum_live(g_ratio * ts.dS_doef, false);
+        const float s_gd = sum_live(g_ratio * ts.dS_ddbv, false);
+        float n_o, n_d;
+        if (multi) {
+            n_o = sum_live(in_norm ? ts.dS_doef * norm_w : 0.f, false);
+            n_d = sum_live(in_norm ? ts.dS_ddbv * norm_w : 0.f, false);
+        } else {
+            n_o = __shfl_sync(kFull, ts.dS_doef, gb + se);
+            n_d = __shfl_sync(kFull, ts.dS_ddbv, gb + se);
+        }
+        const float g_npd = -s_gp * (inv_npd * inv_npd);
+        const float go = s_go * inv_npd + g_npd * n_o;
+        const float gd = s_gd * inv_npd + g_npd * n_d;
+        const float gz_o = go * kOefRange * sm.s_o * (1.0f - sm.s_o);
+        const float gz_d = gd * kDbvRange * sm.s_d * (1.0f - sm.s_d);
+        float g0 = gz_o, g1 = gz_o * e0 * ex.sd_o * ex.dls_o, g2 = gz_d;
+        float g3 = gz_d * e1 * ex.sd_d * ex.dls_d, g4 = gz_d * e0 * ex.dcov;
+
+        // ---- KL(q || prior): lanes of the half = samples
+        float kl_v = 0.f;
+        if (HAS_PRIOR) {
+            const KlOut ko = kl_term<16>(dq, ex, dp, eps_kl ? eps_kl + v * kl_samples * 2 : nullptr, seed,
+                                         offset + (uint64_t)v, kl_samples, lane);
+            if (m > 0.f) {                                   // model.py:661
+                kl_v = ko.kl;
+                const float w = kl_weight * inv_mask_sum;
+                g0 += w * ko.g[0];
+                g1 += w * ko.g[1];
+                g2 += w * ko.g[2];
+                g3 += w * ko.g[3];
+                g4 += w * ko.g[4];
+            }
+        }
+        if (valid) {
+            if (!on) g0 = g1 = g2 = g3 = g4 = 0.f;
+            if (live) grad_sigma[v * nt + t] = on ? dnll_dsg * scale : 0.f;
+            if (t < 5) grad_q[v * 5 + t] = t == 0 ? g0 : t == 1 ? g1 : t == 2 ? g2 : t == 3 ? g3 : g4;
+            if (t == 0) {
+                const float nm = on ? nll_v * m : 0.f;
+                if (!on) kl_v = 0.f;
+                if (nll_map) nll_map[v] = nm;
+                if (kl_map) kl_map[v] = kl_v;
+                acc_nll += (double)nm;
+                acc_kl += (double)kl_v;
+                acc_mask += (double)m;
+                if (!isfinite(nm + kl_v)) bad = 1;
+            }
+        }
+    }
+    if (t == 0 && sums != nullptr && (acc_mask != 0.0 || bad)) {
+        atomicAdd(sums + 0, acc_nll);
+        atomicAdd(sums + 1, acc_kl);
+        atomicAdd(sums + 2, acc_mask);
+        if (bad) atomicAdd(sums + 3, 1.0);
+    }
+}
+
 // Posterior-predictive likelihood map (save_predictions, model.py:808-817): the reference averages
 // fine_tune_loss_fn(return_mean=False) over 100 stochastic forward passes of the fine-tuner.  Here: one warp per
 // voxel loops over n_samples reparameterised draws, runs the forward-only quadrature for each and averages the
@@ -596,7 +790,22 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
             *p, q, sigma, y, mask, HP ? prior : nullptr, eps, HP ? eps_kl : nullptr, seed, offset,                    \
             HP ? kl_samples : 0, inv_mask_sum, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums);              \
     } while (0)
-    if (prior) {
+    if (path == kSched && p->full_model && p->n_tau <= 16) {
+        const int64_t wantp = ((n + 1) / 2 + 7) / 8;
+        if (prior) {
+            static int64_t grid_cache = 0;
+            const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<true>, INT64_MAX / 64));
+            k_elbo_pair<true><<<(unsigned)(wantp < grid ? wantp : grid), kThreads, 0, st>>>(
+                *p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, kl_weight, n, grad_q,
+                grad_sigma, nll_map, kl_map, sums);
+        } else {
+            static int64_t grid_cache = 0;
+            const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<false>, INT64_MAX / 64));
+            k_elbo_pair<false><<<(unsigned)(wantp < grid ? wantp : grid), kThreads, 0, st>>>(
+                *p, q, sigma, y, mask, nullptr, eps, nullptr, seed, offset, 0, inv_mask_sum, kl_weight, n, grad_q,
+                grad_sigma, nll_map, kl_map, sums);
+        }
+    } else if (prior) {
         if (path == kSched) QB_LAUNCH_ELBO(true, kSched);
         else if (path == kCols) QB_LAUNCH_ELBO(true, kCols);
         else QB_LAUNCH_ELBO(true, kColsMulti);
