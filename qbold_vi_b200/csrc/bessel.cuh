@@ -7,14 +7,15 @@
 //
 //   x <= 3      : 1 - J0 = z*S0(z), J1 = x*S1(z), z = x*x.  No cancellation for small x, where the
 //                 quadrature weights ~ 1/u^2 are largest (relative error 1.6e-7).
-//   3 < x <= 9  : degree-11 polynomials in t = x - 6 for 1 - J0 and J1 (23 FMA-pipe instructions for
-//                 the pair; the modulus/phase form costs twice that).
-//   x > 9       : modulus/phase form  J_n = rsqrt(x) A_n(w) cos(x - (2n+1)pi/4 + q F_n(w)),
+//   3 < x <= 9  : degree-12 polynomials in t = x - 5.5 for 1 - J0 and J1 (25 FMA-pipe instructions for
+//                 the pair; the modulus/phase form costs twice that).  Fitted on [2, 9]: a warp pass whose
+//                 arguments straddle x = 3 can run this kernel on all lanes instead of diverging.
+//   x > 9       : valid from x = 6.5 (same reason).  Modulus/phase form  J_n = rsqrt(x) A_n(w) cos(x - (2n+1)pi/4 + q F_n(w)),
 //                 q = 1/x = rsqrt(x)^2, w = q^2, one MUFU.RSQ for the pair; the cosine is a polynomial
 //                 in r^2 after a two-constant Cody-Waite reduction mod pi (n*PI_HI exact for |x| < 1e5).
 //
-// Max abs error vs float64 (float32 FMA arithmetic): 2.0e-7 / 2.2e-7 (small), 2.8e-7 / 2.0e-7 (mid),
-// 4.9e-7 / 3.9e-7 (big, x <= 40; the floor there is the float32 rounding of the phase, which the
+// Max abs error vs float64 (float32 FMA arithmetic): 2.0e-7 / 2.2e-7 (small), 4.4e-7 / 3.4e-7 (mid, on [2, 9]),
+// 4.9e-7 / 3.9e-7 (big, 6.5 <= x <= 40; the floor there is the float32 rounding of the phase, which the
 // reference's Cephes kernels share).  Error budget: the signal tolerance 1e-5 allows ~1e-5 absolute on
 // J0 at these nodes (their Simpson weights sum to < 5).
 #pragma once

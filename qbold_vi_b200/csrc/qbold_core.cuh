@@ -351,9 +351,11 @@ __device__ __forceinline__ void tissue_sched(int nph, const SchedAddr& sa, float
     constexpr int kPassBytes = 32 * 8, kPhaseBytes = QBOLD_SCHED_PHASE_LEN * kPassBytes;
     const bool is_ph = lane < nph;
     const float lo = A * ph_lo, hi = A * ph_hi;
+    // one kernel for the whole phase whenever its argument span fits the kernel's validity range
+    // (small: x <= 3, mid: [2, 9], big: x >= 6.5 -- the ranges overlap on purpose, see bessel.cuh)
     const unsigned PS = __ballot_sync(kFull, is_ph && hi <= coef::kX1);
-    const unsigned PM = __ballot_sync(kFull, is_ph && lo > coef::kX1 && hi <= coef::kX2);
-    const unsigned PB = __ballot_sync(kFull, is_ph && lo > coef::kX2);
+    const unsigned PM = __ballot_sync(kFull, is_ph && lo >= coef::kMidLo && hi <= coef::kX2);
+    const unsigned PB = __ballot_sync(kFull, is_ph && lo >= coef::kBigLo);
     const float invA = A > 0.f ? 1.0f / A : 0.f;
     float accI = 0.f, accS = 0.f, accB = 0.f;
     unsigned ea = sa.mw, ca = sa.col;
@@ -388,9 +390,9 @@ __device__ __forceinline__ void tissue_sched(int nph, const SchedAddr& sa, float
                 const bool le1 = x <= coef::kX1, le2 = x <= coef::kX2;
                 if (__all_sync(kFull, le1)) {
                     acc_small<BWD>(x, e.y, accI, accS);
-                } else if (__all_sync(kFull, !le1 && le2)) {
+                } else if (__all_sync(kFull, x >= coef::kMidLo && le2)) {
                     acc_mid<BWD>(x, e, accI, accB);
-                } else if (__all_sync(kFull, !le2)) {
+                } else if (__all_sync(kFull, x >= coef::kBigLo)) {
                     acc_big<BWD>(x, e, accI, accB);
                 } else {
                     if (le1) acc_small<BWD>(x, e.y, accI, accS);

@@ -5,8 +5,8 @@ qbold_vi_b200/csrc/bessel_coef.h.
 Device algorithm (qbold_vi_b200/csrc/bessel.cuh), three ranges:
   small x <= X1      : 1 - J0(x) = z * S0(z),  J1(x) = x * S1(z),  z = x^2
                        (no cancellation: the quadrature needs 1 - J0, not J0)
-  mid   X1 < x <= X2 : 1 - J0 and J1 as polynomials in t = x - XC (XC = (X1+X2)/2)
-  big   x > X2       : J_n(x) = rsqrt(x) * A_n(w) * cos(x - (2n+1)pi/4 + q * F_n(w)),
+  mid   X1 < x <= X2 : 1 - J0 and J1 as polynomials in t = x - XC; valid on [MID_LO, X2]
+  big   x > X2       : valid from BIG_LO;  J_n(x) = rsqrt(x) * A_n(w) * cos(x - (2n+1)pi/4 + q * F_n(w)),
                        q = 1/x, w = q^2  (modulus / phase form; A_n, F_n polynomials in w)
   cos on [-pi/2, pi/2] after a 2-constant Cody-Waite reduction mod pi: polynomial in r^2.
 
@@ -21,13 +21,15 @@ import numpy as np
 import scipy.special as sp
 from numpy.polynomial import chebyshev as C, polynomial as P
 
-X1, X2 = 3.0, 9.0
-XC = 0.5 * (X1 + X2)
+X1, X2 = 3.0, 9.0            # per-lane split points
+MID_LO, BIG_LO = 2.0, 6.5    # the mid / big kernels stay valid down to here, so a pass (or phase) that
+                             # straddles a split point can still run ONE kernel on all lanes
 SMALL_FIT_HI = 3.1           # fit a little beyond the split
-MID_FIT = (2.95, 9.05)
-BIG_FIT_LO = 8.9
+MID_FIT = (MID_LO - 0.05, X2 + 0.05)
+XC = 0.5 * (MID_FIT[0] + MID_FIT[1])
+BIG_FIT_LO = BIG_LO - 0.1
 DEG_SMALL = 5
-DEG_MID = 11
+DEG_MID = 12
 DEG_AMP = 2
 DEG_PHASE = 2
 DEG_COS = 4                  # in r^2, |r| <= pi/2 + 0.02
@@ -105,12 +107,12 @@ def main():
     e0 = np.abs(v0 - (1 - sp.j0(xd)))
     print('small: 1-J0 abs %.2e rel %.2e | J1 abs %.2e' % (e0.max(), (e0 / (1 - sp.j0(xd))).max(),
                                                          np.abs(v1 - sp.j1(xd)).max()))
-    x = np.linspace(X1, X2, 300001).astype(np.float32)
+    x = np.linspace(MID_LO, X2, 300001).astype(np.float32)
     xd = x.astype(np.float64)
     t = (x - np.float32(XC)).astype(np.float32)
     print('mid  : 1-J0 abs %.2e | J1 abs %.2e' % (np.abs(horner32(out['M0'], t) - (1 - sp.j0(xd))).max(),
                                                  np.abs(horner32(out['M1'], t) - sp.j1(xd)).max()))
-    x = np.linspace(X2, 40, 600001).astype(np.float32)
+    x = np.linspace(BIG_LO, 40, 600001).astype(np.float32)
     xd = x.astype(np.float64)
     r = (1 / np.sqrt(xd)).astype(np.float32)
     q = (r * r).astype(np.float32)
@@ -138,7 +140,8 @@ def main():
         f.write('// GENERATED by tools/fit_bessel.py -- do not edit.\n')
         f.write('// Near-minimax float32 polynomial kernels for 1-J0 / J1 (see bessel.cuh).\n#pragma once\n')
         f.write('namespace qb {\nnamespace coef {\n')
-        f.write('constexpr float kX1 = %s, kX2 = %s, kXC = %s;\n' % (flit(X1), flit(X2), flit(XC)))
+        f.write('constexpr float kX1 = %s, kX2 = %s, kXC = %s, kMidLo = %s, kBigLo = %s;\n'
+                % (flit(X1), flit(X2), flit(XC), flit(MID_LO), flit(BIG_LO)))
         for name, coef in out.items():
             f.write('// %s: ascending powers, degree %d\n' % (name, len(coef) - 1))
             f.write('struct %s {\n    static constexpr int N = %d;\n    __host__ __device__ static constexpr float c(int i) {\n'
