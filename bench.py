@@ -133,7 +133,7 @@ def workload_config(voxels, gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--voxels', type=int, default=1 << 24)
@@ -236,6 +236,12 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        traffic = None
+        try:                                             # per-voxel DRAM bytes of this kernel from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            traffic = tj['k_forward_pair_bwd']['dram_bytes_per_voxel'] * n
+        except Exception:
+            pass
         hbm_gbs = n * 104 / per_launch_s / 1e9
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -248,11 +254,13 @@ def main():
                     'matches_device_path': e2e_ok},
             'gpu_launches': launches,
             'roofline': {'bound': 'fp32', 'achieved': achieved_tf, 'peak': fma_tf, 'unit': 'TFLOP/s',
-                         'frac': achieved_tf / fma_tf, 'traffic': None,
+                         'frac': achieved_tf / fma_tf, 'traffic': traffic,
+                         'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture '
+                                         '(profiles/traffic.json), scaled to the voxels of one launch',
                          'peak_source': 'FFMA micro-benchmark (qbold_fma_peak) measured in this run; derived '
                                         '148 SM x 128 lanes x 2 x 1.965 GHz = %.1f TFLOP/s (frac %.3f)'
                                         % (derived_tf, achieved_tf / derived_tf),
-                         'kernel': 'k_forward<BWD=true>', 'launch_ms': per_launch_s * 1e3,
+                         'kernel': 'k_forward_pair<BWD=true>', 'launch_ms': per_launch_s * 1e3,
                          'alg_flops_per_voxel': f_alg, 'asymptotic_branch_fraction_f': f_big,
                          'alg_bytes_per_voxel': 104, 'hbm': {'achieved': hbm_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                                                              'frac': hbm_gbs / hbm_peak,
