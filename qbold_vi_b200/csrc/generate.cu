@@ -85,6 +85,72 @@ __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ Q
     }
 }
 
+// Paired variant (scheduled path, n_tau <= 16): two voxels per warp iteration, voxel 0 on lanes 0-15 and voxel 1 on
+// lanes 16-31 for everything but the two quadratures (see k_forward_pair).
+// idx -> (row of oefs, row of dbvs) of the 'ij' meshgrid; 32-bit division when the grid has < 2^32 points.
+__device__ __forceinline__ void mesh_index(uint64_t idx, uint64_t n_dbv, bool small, uint64_t& io, uint64_t& id) {
+    if (small) {
+        const unsigned q = (unsigned)idx / (unsigned)n_dbv;
+        io = q;
+        id = (unsigned)idx - q * (unsigned)n_dbv;
+    } else {
+        io = idx / n_dbv;
+        id = idx % n_dbv;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 5) k_generate_pair(const __grid_constant__ QboldParams P,
+                                                               const float* __restrict__ oefs, int64_t n_oef,
+                                                               const float* __restrict__ dbvs, int64_t n_dbv,
+                                                               const int64_t* __restrict__ perm, uint64_t seed,
+                                                               int half_bits, int64_t first, int64_t count,
+                                                               float* __restrict__ x, float* __restrict__ y3) {
+    __shared__ SchedSmem ss;
+    load_sched(P, ss);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = t < nt;
+    const int my_col = live ? P.col_of_tau[t] : -1;
+    const float my_tau = live ? P.tau[t] : 0.f;
+    const float my_b = live ? P.blood_b[t] : 0.f;
+    const QuadCtx qc = make_quad_ctx<kSched>(P, ss, lane, my_col, my_tau);
+    const uint64_t total = (uint64_t)n_oef * (uint64_t)n_dbv;
+    const int64_t npairs = (count + 1) >> 1;
+
+    for (int64_t pr = warp; pr < npairs; pr += nwarps) {
+        int64_t v = pr * 2 + half;
+        const bool valid = v < count;
+        if (!valid) v = count - 1;
+        const uint64_t row = (uint64_t)(first + v);
+        const uint64_t idx = perm ? (uint64_t)__ldg(perm + row) : feistel_permute(row, total, half_bits, seed);
+        uint64_t io, id;
+        mesh_index(idx, (uint64_t)n_dbv, total < (1ull << 32), io, id);
+        const float oef = __ldg(oefs + io);                               // meshgrid(indexing='ij'), signals.py:270
+        const float dbv = __ldg(dbvs + id);
+        if (y3 != nullptr && t < 3 && valid) {
+            const float r2p = (P.dw_k * oef) * dbv;                        // signals.py:296
+            y3[v * 3 + t] = t == 0 ? oef : (t == 1 ? dbv : r2p);
+        }
+        if (x == nullptr) continue;
+        const VoxelPhys vp = voxel_phys<false>(P, oef, dbv, P.hct);
+        const float A_mine = qc.tau_ref15 * vp.dw;
+        float I = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const float A = __shfl_sync(kFull, A_mine, h << 4);
+            float vi, vd;
+            tissue_sched<false>(qc.nph, qc.sa, A, lane, qc.ph_lo, qc.ph_hi, my_col, vi, vd);
+            if (half == h) I = vi;
+        }
+        if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
+        const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, 0.f);
+        if (live && valid) x[v * nt + t] = ts.S;
+    }
+}
+
 // Column sums of a [n, nt] block; one warp reads one 4*nt-byte row per step.
 __global__ void __launch_bounds__(kThreads) k_column_sum(const float* __restrict__ sig, int64_t n, int nt,
                                                          double* __restrict__ sums) {
@@ -181,7 +247,17 @@ extern "C" int qbold_generate(const QboldParams* p, const float* oefs, int64_t n
     const int64_t want = (count + 7) / 8;
     if (want < grid) grid = want;
     cudaStream_t st = (cudaStream_t)stream;
-    if (path == kSched)
+    if (path == kSched && p->full_model && p->n_tau <= 16) {
+        static int bps_pair = 0;
+        if (bps_pair == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_pair, k_generate_pair, kThreads, 0) !=
+                                  cudaSuccess || bps_pair < 1))
+            bps_pair = 1;
+        int64_t gp = (int64_t)sm_count() * bps_pair;
+        const int64_t wantp = ((count + 1) / 2 + 7) / 8;
+        if (wantp < gp) gp = wantp;
+        k_generate_pair<<<(unsigned)gp, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits, first,
+                                                           count, x, y3);
+    } else if (path == kSched)
         k_generate<kSched><<<(unsigned)grid, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits,
                                                                 first, count, x, y3);
     else if (path == kCols)
