@@ -250,7 +250,7 @@ def main():
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n * (8 + 4 * N_TAU),
                     'd2h_bytes_per_step': n * (8 + 4 * N_TAU), 'steps': args.e2e_steps,
-                    'path': 'qbold_forward_backward_host: pinned host buffers, 3-slot H2D/kernel/D2H pipeline',
+                    'path': 'qbold_forward_backward_host: pinned host buffers, 4-slot H2D/kernel/D2H pipeline, 512k-voxel chunks',
                     'matches_device_path': e2e_ok},
             'gpu_launches': launches,
             'roofline': {'bound': 'fp32', 'achieved': achieved_tf, 'peak': fma_tf, 'unit': 'TFLOP/s',

@@ -1,5 +1,5 @@
 // Host-buffer entry point: the same forward + VJP as qbold_forward_backward, fed from and
-// returning to HOST memory.  The voxel range is cut into chunks that cycle over three
+// returning to HOST memory.  The voxel range is cut into chunks that cycle over four
 // stream slots so the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of
 // chunk c-1 overlap (PCIe Gen5 full duplex).  Pinned host buffers give true asynchrony;
 // pageable ones still work (the runtime stages them).
@@ -9,8 +9,8 @@
 
 namespace qb {
 
-constexpr int kSlots = 3;
-constexpr int64_t kChunk = 1 << 20;   // voxels per chunk: 8 MB in, 52 MB g+S, 8 MB grad
+constexpr int kSlots = 4;
+constexpr int64_t kChunk = 1 << 19;   // voxels per chunk: 4 MB in, 46 MB g+S, 4 MB grad (short pipeline fill/drain)
 
 struct Slot {
     cudaStream_t stream = nullptr;
