@@ -142,3 +142,78 @@ class DataParallelTrainer:
     def bucket_params_mul_(self, factor):
         for p in self.bucket.params:
             p.mul_(factor)
+
+
+class StreamingPretrainer:
+    """Pre-training on synthetic data (create_and_train_on_synthetic_data, train.py:379-427) without materialising
+    the S x S-row dataset (6.25 M rows for the reference's config): every step generates the next slice of the
+    shuffled OEF x DBV meshgrid on the device (qbold_generate with the keyed Feistel shuffle, then the noise model),
+    feeds it to stream 1 of the encoder in the reference's [-1,10,10,5,n_tau] blocks (train.py:88) and minimises
+    synthetic_data_loss.  Ranks walk disjoint row ranges; gradients go through the same flat-bucket all-reduce."""
+
+    def __init__(self, encoder, trainer, params, full_model=True, use_blood=True, uniform_prop=0.1, lr=2e-3,
+                 weight_decay=2e-4, batch_blocks=512, seed=1, device=None):
+        import ctypes as C
+        from . import signals
+        self.encoder, self.trainer = encoder, trainer
+        self.device = torch.device(device) if device is not None else next(encoder.parameters()).device
+        self.layer = signals.SignalGenerationLayer(params, full_model, use_blood, seed=seed)
+        gen = torch.Generator(device=self.device).manual_seed(seed)
+        S = int(params['sample_size'])
+        n_u, n_n = round(S * uniform_prop), round(S * (1.0 - uniform_prop))
+        o0, o1 = float(params['oef_start']), float(params['oef_end'])
+        d0, d1 = float(params['dbv_start']), float(params['dbv_end'])
+        oefs_n = torch.randn(n_n, device=self.device, generator=gen) * float(params['oef_std']) + float(params['oef_mean'])
+        self.oefs = torch.cat([torch.rand(n_u, device=self.device, generator=gen) * (o1 - o0) + o0,
+                               oefs_n.clamp(o0, o1)]).contiguous()
+        self.dbvs = torch.cat([torch.rand(n_u, device=self.device, generator=gen) * (d1 - d0) + d0,
+                               signals._truncated_normal(n_n, float(params['dbv_mean']), float(params['dbv_std']), d0, d1,
+                                                         gen, self.device)]).contiguous()
+        self.total = self.oefs.numel() * self.dbvs.numel()
+        self.batch = batch_blocks * 500                                   # 512 blocks of 10x10x5 voxels (train.py:88,103)
+        self.seed = seed
+        rank = dist.get_rank() if world_size() > 1 else 0
+        self.cursor = rank * self.batch
+        self.stride = world_size() * self.batch
+        self.bucket = FlatGradBucket(encoder.parameters())
+        self.opt = torch.optim.Adam(self.bucket.params, lr=lr)
+        self.weight_decay = weight_decay
+        self._C = C
+
+    def next_batch(self):
+        """(x [batch, n_tau] noisy signals, y [batch, 3] labels) for this rank's next slice of the shuffled grid."""
+        from ._lib import check, dptr, lib, stream_ptr
+        C = self._C
+        nt = self.layer.n_tau
+        first = self.cursor % max(self.total - self.batch, 1)
+        self.cursor += self.stride
+        x = torch.empty((self.batch, nt), dtype=torch.float32, device=self.device)
+        y = torch.empty((self.batch, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().qbold_generate(C.byref(self.layer.params), dptr(self.oefs), self.oefs.numel(), dptr(self.dbvs),
+                                       self.dbvs.numel(), None, self.seed, first, self.batch, dptr(x), dptr(y),
+                                       stream_ptr(self.device)))
+        if self.layer._simulate_noise:
+            self.layer.add_noise(x, seed=self.seed ^ 0x5DEECE66D, offset=first, inplace=True)
+        return x, y
+
+    def step(self):
+        x, y = self.next_batch()
+        nt = self.layer.n_tau
+        self.bucket.zero_()
+        out, _, _ = self.encoder(x.reshape(-1, 10, 10, 5, nt))
+        loss = self.trainer.synthetic_data_loss(y, out) / world_size()
+        loss.backward()
+        self.bucket.all_reduce_()
+        if self.weight_decay > 0.0:
+            with torch.no_grad():
+                for p in self.bucket.params:
+                    p.mul_(1.0 - self.weight_decay)
+        self.opt.step()
+        stat = loss.detach().double().reshape(1)
+        all_reduce_sum_(stat)
+        with torch.no_grad():                                             # oef / dbv / r2p MSE metrics (model.py:345-374)
+            means = self.trainer.calculate_means(out.detach(), None, include_r2p=True, no_samples=20,
+                                                 signal_layer=self.layer).reshape(-1, 3)
+            mse = ((means - y) ** 2).mean(0)
+        return {'loss': float(stat), 'oef_mse': float(mse[0]), 'dbv_mse': float(mse[1]), 'r2p_mse': float(mse[2])}

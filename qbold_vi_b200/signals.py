@@ -290,3 +290,25 @@ def generate_from_marginals(sig_layer, oefs, dbvs, perm=None, n_chunks=10, snr_u
                                 None if noise_eps is None else noise_eps[sl].contiguous(),
                                 seed=seed ^ 0x5DEECE66D, offset=i * chunk, inplace=True)
     return train_x, train_y
+
+
+def main(argv=None):
+    """CLI of the reference (signals.py:302-332): ``python -m qbold_vi_b200.signals -f True -b True`` writes
+    synthetic_data.npz (x, y) from the ``config`` INI in the working directory (or the packaged defaults)."""
+    import argparse
+    from .config import load_system_parameters
+    parser = argparse.ArgumentParser(description='Generate ASE qBOLD signals')
+    parser.add_argument('-f', required=True, help='should the tissue contribution be calculated with the full model')
+    parser.add_argument('-b', required=True, help='should the blood contribution be included')
+    parser.add_argument('-o', default='synthetic_data', help='output .npz stem')
+    args = parser.parse_args(argv)
+    if args.f not in ['True', 'False'] or args.b not in ['True', 'False']:
+        raise ValueError('Arguments must be a valid boolean')
+    params = load_system_parameters()
+    # the reference passes misaligned_prob 0.1 here (signals.py:330)
+    train_x, train_y = create_synthetic_dataset(params, args.f, args.b, 0.1, False)
+    np.savez(args.o, x=train_x.cpu().numpy(), y=train_y.cpu().numpy())
+
+
+if __name__ == '__main__':
+    main()

@@ -490,3 +490,51 @@ def test_fine_tuner_module_outputs(qb, dev, cfg_noise_off):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ft.encoder.parameters() if p.requires_grad)
     loss, info = ft.fused_loss(data, mask, out['predictions'].detach())
     assert torch.isfinite(loss)
+
+
+# ---------------------------------------------------------------------------------- other parameter sets / tau grids
+@pytest.mark.parametrize('case', ['irregular_taus', 'other_physics', 'five_taus', 'single_column'])
+def test_other_parameter_sets(qb, dev, cfg_noise_off, case):
+    """The scheduled quadrature is built from the ACTUAL tau array and physics; exercise grids other than optimal.yaml's."""
+    cfg = dict(cfg_noise_off)
+    taus = None
+    if case == 'irregular_taus':                       # 7 taus, 6 distinct |tau| with irregular ratios
+        taus = np.array([-0.011, -0.003, 0.0, 0.003, 0.017, 0.029, 0.061], np.float32)
+    elif case == 'other_physics':
+        # keeps 1.5*tau*dw*u_0 below 3.45e-4: beyond it node 0 of the float32 reference stops being exactly dead and
+        # its value is quantisation noise of 1 - (1 - x^2/4) (SURVEY.md A.6) -- parity is ill-defined there
+        cfg.update(b0='4.0', te='0.08', r2t='20.0', hct='0.42', dchi='2.0e-7')
+    elif case == 'five_taus':
+        cfg.update(tau_start='0.0', tau_end='0.05', tau_step='0.01')
+    elif case == 'single_column':
+        taus = np.array([0.0, 0.03], np.float32)
+    ph = o.parse_params(cfg, taus=taus)
+    layer = qb.SignalGenerationLayer(cfg, True, True, taus=taus)
+    assert layer.params.sched_phases > 0
+    nt = ph.n_tau
+    x = _rand_voxels(1500, 31)
+    gs = np.random.default_rng(2).standard_normal((1500, nt)).astype(np.float32)
+    s, g = layer.forward_backward(_t(x, dev), _t(gs, dev))
+    s64, g64 = o.forward_backward(ph, x, gs, dtype=np.float64)
+    assert rel_elem(s.cpu().numpy(), s64) < SIG_TOL
+    assert rel_max(g.cpu().numpy()[:, 0], g64[:, 0]) < GRAD_TOL and rel_max(g.cpu().numpy()[:, 1], g64[:, 1]) < GRAD_TOL
+    assert rel_elem(layer(_t(x, dev)).cpu().numpy(), s64) < SIG_TOL              # forward-only kernel
+
+
+def test_streaming_pretrainer(qb, dev):
+    """train.py:379-427 with on-the-fly generation: the pre-training NLL falls and the OEF error shrinks."""
+    from qbold_vi_b200.encoder import Encoder
+    from qbold_vi_b200.distributed import StreamingPretrainer
+    cfg = o.default_config()
+    cfg['sample_size'] = '400'
+    torch.manual_seed(2)
+    enc = Encoder().to(dev)
+    tr = _trainer(qb, cfg)
+    pt = StreamingPretrainer(enc, tr, cfg, uniform_prop=0.1, lr=2e-3, batch_blocks=16, seed=5, device=dev)
+    x, y = pt.next_batch()
+    assert tuple(x.shape) == (8000, 11) and tuple(y.shape) == (8000, 3) and torch.isfinite(x).all()
+    assert float(y[:, 0].min()) >= 0.05 - 1e-6 and float(y[:, 1].max()) <= 0.195 + 1e-6
+    stats = [pt.step() for _ in range(40)]
+    assert all(np.isfinite(s['loss']) for s in stats)
+    assert np.mean([s['loss'] for s in stats[-5:]]) < np.mean([s['loss'] for s in stats[:5]]) - 0.5
+    assert np.mean([s['oef_mse'] for s in stats[-5:]]) < np.mean([s['oef_mse'] for s in stats[:5]])
