@@ -12,6 +12,10 @@
 #include "launch.h"
 #include "rng.cuh"
 
+#ifndef QB_ELBO_MIN_BLOCKS
+#define QB_ELBO_MIN_BLOCKS 3
+#endif
+
 namespace qb {
 
 constexpr float kOefRange = 0.8f, kMinOef = 0.04f, kDbvRange = 0.2f, kMinDbv = 0.001f;   // model.py:88-91
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
 // likelihood, its reductions, the KL (lanes = samples, 16 per pass) and all loads / stores are done once for both
 // voxels, voxel 0 on lanes 0-15 and voxel 1 on lanes 16-31.
 template <bool HAS_PRIOR>
-__global__ void __launch_bounds__(kThreads, 3) k_elbo_pair(const __grid_constant__ QboldParams P,
+__global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(const __grid_constant__ QboldParams P,
                                                            const float* __restrict__ q, const float* __restrict__ sigma,
                                                            const float* __restrict__ y, const float* __restrict__ mask,
                                                            const float* __restrict__ prior, const float* __restrict__ eps,

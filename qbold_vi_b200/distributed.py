@@ -132,9 +132,9 @@ class DataParallelTrainer:
                 self.bucket_params_mul_(1.0 - self.wd(self.step_no))
         self.opt.step()
         self.step_no += 1
-        stats = torch.stack([total.detach().double(), info['nll'].detach().double() if 'nll' in info else total.detach().double() * 0,
-                             info['kl'].detach().double() if 'kl' in info else total.detach().double() * 0,
-                             tv.detach().double()])
+        zero = total.detach().double() * 0
+        stats = torch.stack([total.detach().double(), info['nll'].detach().double() if 'nll' in info else zero,
+                             info['kl'].detach().double() if 'kl' in info else zero, tv.detach().double()])
         all_reduce_sum_(stats)
         return {'loss': float(stats[0]), 'nll': float(stats[1]), 'kl': float(stats[2]), 'smoothness': float(stats[3]),
                 'mask_sum': msum, 'lr': lr}

@@ -109,7 +109,9 @@ class SignalGenerationLayer:
             assert input.shape[-1] == 3, 'Input should have 3 elements in last dimension, OEF, DBV and hct'
         else:
             assert input.shape[-1] == 2, 'Input should have 2 elements in last dimension, OEF and DBV'
-        dptr(input, input.dtype) if not input.is_cuda else None      # raises: there is no CPU path
+        if not input.is_cuda:
+            raise QboldError('qbold_vi_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path'
+                             % input.device)
         flat = input.reshape(-1, width)
         if flat.dtype != torch.float32:
             flat = flat.float()
@@ -167,7 +169,8 @@ class SignalGenerationLayer:
     def forward_backward(self, oef_dbv, g_signal=None, want_signal=True):
         """Forward + VJP in one fused launch: returns (signal [N,n_tau] or None, grad [N,2])."""
         if not oef_dbv.is_cuda:
-            dptr(oef_dbv)                                             # raises: there is no CPU path
+            raise QboldError('qbold_vi_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path'
+                             % oef_dbv.device)
         flat = oef_dbv.reshape(-1, 2).contiguous()
         n = flat.shape[0]
         sig = torch.empty((n, self.n_tau), dtype=torch.float32, device=flat.device) if want_signal else None
