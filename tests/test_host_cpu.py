@@ -172,3 +172,24 @@ def test_static_lane_schedule_covers_every_node_once(qb):
     # more than 8 distinct |tau| (24-tau grid): no schedule, column-major path
     cfg.update(tau_start='-0.028', tau_end='0.065', tau_step='0.004')
     assert qb.SignalGenerationLayer(cfg, True, True).params.sched_phases == 0
+
+
+def test_dataset_plumbing_shapes(qb):
+    """prepare_dataset / prepare_synthetic_dataset semantics (train.py:17-104) on torch tensors."""
+    import torch
+    from qbold_vi_b200.data import FineTuneDataset, prepare_synthetic_dataset
+    from qbold_vi_b200.encoder import Encoder
+    torch.manual_seed(0)
+    x, y = torch.rand(6000, 11), torch.rand(6010, 3)               # x shorter than y, as signals.py:283-287 can produce
+    batches, (vx, vy) = prepare_synthetic_dataset(x, y, batch_size=4)
+    assert tuple(vx.shape) == (1, 10, 10, 5, 11) and tuple(vy.shape) == (1, 10, 10, 5, 3)
+    got = list(batches())
+    assert sum(b[0].shape[0] for b in got) == 11 and tuple(got[0][0].shape) == (4, 10, 10, 5, 11)
+    real = torch.rand(3, 70, 60, 8, 12) + 0.5
+    real[..., -1] = (real[..., -1] > 1.0).float()
+    ds = FineTuneDataset(real, Encoder(no_units=8, no_intermediate_layers=1), crop_size=25, training=True)
+    (data, mask), tgt = next(iter(ds))
+    assert tuple(data.shape) == (38, 25, 25, 8, 11) and tuple(mask.shape) == (38, 25, 25, 8, 1)      # 38*25*25*8 = 190 000 voxels
+    assert tuple(tgt['predictions'].shape) == (38, 25, 25, 8, 6) and tuple(tgt['predicted_images'].shape) == (38, 25, 25, 8, 12)
+    assert torch.equal(data, tgt['predicted_images'][..., :-1]) and bool((data[mask.expand_as(data) == 0] == 0).all())
+    assert torch.equal(tgt['predictions'][..., -1:], mask)
