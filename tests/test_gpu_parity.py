@@ -538,3 +538,60 @@ def test_streaming_pretrainer(qb, dev):
     assert all(np.isfinite(s['loss']) for s in stats)
     assert np.mean([s['loss'] for s in stats[-5:]]) < np.mean([s['loss'] for s in stats[:5]]) - 0.5
     assert np.mean([s['oef_mse'] for s in stats[-5:]]) < np.mean([s['oef_mse'] for s in stats[:5]])
+
+
+@pytest.mark.parametrize('grid', ['tau24', 'tau5', 'tau11_closed_form'])
+def test_fused_elbo_other_grids_and_closed_form(qb, dev, cfg_noise_off, grid):
+    """The unpaired / column-major ELBO kernels (24 taus: 16 columns, n_tau > 16), a 5-tau grid on the paired
+    kernel, and the closed-form KL inside the fused kernel, all against the float64 oracle."""
+    cfg = dict(cfg_noise_off)
+    S = 70
+    if grid == 'tau24':
+        cfg.update(tau_start='-0.028', tau_end='0.065', tau_step='0.004')
+    elif grid == 'tau5':
+        cfg.update(tau_start='-0.01', tau_end='0.035', tau_step='0.01')
+    ph = o.parse_params(cfg)
+    nt = ph.n_tau
+    se = int(abs(float(cfg['tau_start']) / float(cfg['tau_step'])))
+    n = 300
+    r = np.random.default_rng(33)
+    q = np.stack([r.normal(-0.3, 0.7, n), r.normal(0, 0.5, n), r.normal(-1.2, 0.7, n), r.normal(0, 0.5, n),
+                  r.normal(0, 0.8, n)], -1).astype(np.float32)
+    prior = (q + r.normal(0, 0.3, (n, 5))).astype(np.float32)
+    sigma = np.exp(r.normal(np.log(0.05), 0.2, (n, nt))).astype(np.float32)
+    mask = (r.uniform(size=n) > 0.3).astype(np.float32)
+    truth = np.stack([r.uniform(0.1, 0.7, n), r.uniform(0.005, 0.15, n)], -1)
+    data = (o.forward(ph, truth, dtype=np.float64) * 100 * (1 + 0.02 * r.standard_normal((n, nt)))).astype(np.float32)
+    data *= mask[:, None]
+    eps = r.standard_normal((n, 2)).astype(np.float32)
+    eps_kl = r.standard_normal((n, S, 2)).astype(np.float32)
+    tr = _trainer(qb, cfg)
+    assert tr._se_idx == se
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    qt, st = _t(q, dev).requires_grad_(True), _t(sigma, dev).requires_grad_(True)
+    if grid == 'tau11_closed_form':
+        ref = o.elbo_and_grads(ph, q, sigma, data, mask, prior, eps, None, np.float64, se_idx=se)
+        klc = np.where(mask > 0, o.closed_form_kl(prior, q), 0)
+        loss, info = tr.fused_elbo(layer, qt, st, _t(data, dev), _t(mask, dev), _t(prior, dev), kl_samples=0,
+                                   eps=_t(eps, dev), return_maps=True)
+        assert rel_max(info['kl_map'].cpu().numpy(), klc) < 1e-5
+        assert rel_elem(info['kl'].item(), klc.sum() / mask.sum()) < 1e-5
+        assert rel_elem(info['nll'].item(), ref['nll']) < GRAD_TOL
+        loss.backward()
+        # gradient of the closed form by float64 central differences, added to the oracle's likelihood gradient
+        g_kl = np.zeros((n, 5))
+        for j in range(5):
+            d = np.zeros(5)
+            d[j] = 1e-6
+            g_kl[:, j] = (o.closed_form_kl(prior, q.astype(np.float64) + d) - o.closed_form_kl(prior, q.astype(np.float64) - d)) / 2e-6
+        g_ref = ref['grad_q'] + np.where(mask[:, None] > 0, g_kl, 0) / mask.sum()
+        assert rel_max(qt.grad.cpu().numpy(), g_ref) < GRAD_TOL
+        return
+    ref = o.elbo_and_grads(ph, q, sigma, data, mask, prior, eps, eps_kl, np.float64, se_idx=se)
+    loss, info = tr.fused_elbo(layer, qt, st, _t(data, dev), _t(mask, dev), _t(prior, dev), kl_samples=S,
+                               eps=_t(eps, dev), eps_kl=_t(eps_kl, dev), return_maps=True)
+    loss.backward()
+    assert rel_elem(info['nll'].item(), ref['nll']) < GRAD_TOL and rel_elem(info['kl'].item(), ref['kl']) < GRAD_TOL
+    assert rel_max(info['nll_map'].cpu().numpy(), ref['nll_map']) < GRAD_TOL
+    assert rel_max(qt.grad.cpu().numpy(), ref['grad_q']) < GRAD_TOL
+    assert rel_max(st.grad.cpu().numpy(), ref['grad_sigma']) < GRAD_TOL
