@@ -672,6 +672,89 @@ __global__ void __launch_bounds__(kThreads, 3) k_nll_map(const __grid_constant__
     }
 }
 
+// Paired variant of k_nll_map (scheduled path, n_tau <= 16): one voxel per warp, TWO posterior samples per
+// iteration -- sample s on lanes 0-15, sample s+1 on lanes 16-31 for everything but the two quadratures.
+__global__ void __launch_bounds__(kThreads, 4) k_nll_map_pair(const __grid_constant__ QboldParams P,
+                                                              const float* __restrict__ q, const float* __restrict__ sigma,
+                                                              const float* __restrict__ y, const float* __restrict__ mask,
+                                                              const float* __restrict__ eps, uint64_t seed,
+                                                              uint64_t offset, int n_samples, int64_t n,
+                                                              float* __restrict__ nll_map) {
+    __shared__ SchedSmem ss;
+    load_sched(P, ss);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15, gb = lane & 16;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = t < nt;
+    const int my_col = live ? P.col_of_tau[t] : -1;
+    const float my_tau = live ? P.tau[t] : 0.f;
+    const float my_b = live ? P.blood_b[t] : 0.f;
+    const int se = P.se_idx;
+    const bool multi = P.multi_image_normalisation != 0;
+    const bool in_norm = multi ? (t >= se - 1 && t <= se + 1) : (t == se);
+    const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
+    const float df = P.student_t_df;
+    const QuadCtx qc = make_quad_ctx<kSched>(P, ss, lane, my_col, my_tau);
+    for (int64_t v = warp; v < n; v += nwarps) {
+        const float m = mask ? __ldg(mask + v) : 1.0f;
+        if (!(m != 0.0f)) {
+            if (lane == 0) nll_map[v] = 0.f;
+            continue;
+        }
+        Dist dq, dp;
+        QExtra ex;
+        load_dists(q + v * 5, nullptr, lane, dq, ex, dp);
+        const float yv = live ? __ldg(y + v * nt + t) : 0.f;
+        const float sg = live ? __ldg(sigma + v * nt + t) : 1.f;
+        const float ny = (multi ? sum_live(in_norm ? yv * norm_w : 0.f, false) : __shfl_sync(kFull, yv, gb + se)) + 1e-3f;
+        float yn = yv / ny;
+        if (P.predict_log_data) yn = logf(yn);
+        const float inv_sg = 1.0f / sg, log_sg = logf(sg);
+        float acc = 0.f;
+        for (int s0 = 0; s0 < n_samples; s0 += 2) {
+            const bool both = s0 + 1 < n_samples;
+            const int sidx = (half && both) ? s0 + 1 : s0;
+            const bool valid = (half == 0) || both;
+            float e0, e1;
+            if (eps) {
+                const float2 e = __ldg(reinterpret_cast<const float2*>(eps) + (v * n_samples + sidx));
+                e0 = e.x;
+                e1 = e.y;
+            } else {
+                normal_pair(seed, offset + (uint64_t)v, kStreamKl + (uint32_t)sidx, e0, e1);
+            }
+            const Sample sm = draw(dq, ex, e0, e1);
+            const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
+            const float A_mine = qc.tau_ref15 * vp.dw;
+            float I = 0.f;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !both) continue;
+                const float A = __shfl_sync(kFull, A_mine, h << 4);
+                float vi, vd;
+                tissue_sched<false>(qc.nph, qc.sa, A, lane, qc.ph_lo, qc.ph_hi, my_col, vi, vd);
+                if (half == h) I = vi;
+            }
+            if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
+            const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, 0.f);
+            const float pred = live ? ts.S : 0.f;
+            const float npd = (multi ? sum_live(in_norm ? pred * norm_w : 0.f, false)
+                                     : __shfl_sync(kFull, pred, gb + se)) + 1e-3f;
+            float pn = pred / npd;
+            if (P.predict_log_data) pn = logf(pn);
+            const float zq = (yn - pn) * inv_sg;
+            float nll_t;
+            if (df > 0.f) nll_t = -(P.student_t_logc - log_sg - 0.5f * (df + 1.0f) * log1pf(zq * zq / df));
+            else nll_t = -(-log_sg - kLogSqrt2Pi - 0.5f * (zq * zq));
+            acc += (live && valid) ? nll_t : 0.f;
+        }
+        const float tot = warp_sum(acc);
+        if (lane == 0) nll_map[v] = (tot / (float)n_samples) * m;
+    }
+}
+
 // ReparamTrickLayer alone (model.py:21-50): one thread per voxel.
 __global__ void __launch_bounds__(kThreads) k_reparam(const float* __restrict__ q, const float* __restrict__ eps,
                                                       uint64_t seed, uint64_t offset, int64_t n,
@@ -853,7 +936,12 @@ extern "C" int qbold_nll_map(const QboldParams* p, const float* q, const float* 
         k_nll_map<PA><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(*p, q, sigma, y, mask, eps, seed,  \
                                                                                  offset, n_samples, n, nll_map);     \
     } while (0)
-    if (path == kSched) QB_LAUNCH_NLL(kSched);
+    if (path == kSched && p->full_model && p->n_tau <= 16) {
+        static int64_t grid_cache = 0;
+        const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_nll_map_pair, INT64_MAX / 64));
+        k_nll_map_pair<<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(*p, q, sigma, y, mask, eps, seed,
+                                                                                  offset, n_samples, n, nll_map);
+    } else if (path == kSched) QB_LAUNCH_NLL(kSched);
     else if (path == kCols) QB_LAUNCH_NLL(kCols);
     else QB_LAUNCH_NLL(kColsMulti);
 #undef QB_LAUNCH_NLL

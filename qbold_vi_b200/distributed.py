@@ -69,7 +69,8 @@ class FlatGradBucket:
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # same (dense, possibly permuted) strides as the parameter, e.g. channels_last_3d conv weights
+            p.grad = self.flat[off:off + p.numel()].as_strided(p.size(), p.stride())
             off += p.numel()
 
     def zero_(self):
