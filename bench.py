@@ -253,7 +253,9 @@ def main():
                     'path': 'qbold_forward_backward_host: pinned host buffers, 4-slot H2D/kernel/D2H pipeline, 512k-voxel chunks',
                     'matches_device_path': e2e_ok},
             'gpu_launches': launches,
-            'roofline': {'bound': 'fp32', 'achieved': achieved_tf, 'peak': fma_tf, 'unit': 'TFLOP/s',
+            'roofline': {'bound': 'fp32', 'bound_note': 'FP32 CUDA-core issue (not HBM, not tensor): ~570 FLOP/B, see '
+                                                        'SURVEY.md 8(d); HBM fraction reported under "hbm"',
+                         'achieved': achieved_tf, 'peak': fma_tf, 'unit': 'TFLOP/s',
                          'frac': achieved_tf / fma_tf, 'traffic': traffic,
                          'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture '
                                          '(profiles/traffic.json), scaled to the voxels of one launch',
@@ -268,8 +270,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample = 262144
             cpu_port_run(8192, threads)
+            probe = cpu_port_run(65536, threads)                      # size the sample for ~15 s of CPU work
+            sample = int(min(1 << 22, max(1 << 17, 65536 * 15.0 / max(probe, 1e-3)))) // 8192 * 8192
             sec = cpu_port_run(sample, threads)
             line['cpu_baseline'] = {'value': sample * N_TAU / sec, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                     'sample': '%d voxels of the same workload, forward + autodiff VJP, float32, '
