@@ -174,6 +174,11 @@ int qbold_elbo_fused(const QboldParams* p, const float* q, const float* sigma, c
                      float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
                      float* kl_map, double* sums, void* stream);
 
+/* fine_tune_loss_fn alone (model.py:527-568) for predictions already in HBM: nll_map[n] = mask * sum_tau NLL,
+ * and (optional) d_pred / d_sigma [n,n_tau] = d nll_map[v] / d pred[v,:], d sigma[v,:].  mask may be NULL. */
+int qbold_nll(const QboldParams* p, const float* y, const float* pred, const float* sigma, const float* mask,
+              int64_t n, float* nll_map, float* d_pred, float* d_sigma, void* stream);
+
 /* kl_loss alone (model.py:654-665 -> mvg_kl_samples :592-610): per-voxel KL(q || prior) map
  * (zero where mask <= 0; mask may be NULL) and, optionally, grad_q[n,5] = d kl_map[v] / d q[v,:]
  * (path-derivative estimator: stop_gradient on q inside log q, model.py:596).

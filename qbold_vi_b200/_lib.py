@@ -68,6 +68,7 @@ _SIGNATURES = {
                                  _f, _f, C.c_void_p]),
     'qbold_elbo_fused': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32,
                                    C.c_float, C.c_float, C.c_int64, _f, _f, _f, _f, _f, C.c_void_p]),
+    'qbold_nll': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, C.c_int64, _f, _f, _f, C.c_void_p]),
     'qbold_kl': (C.c_int, [_f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f, _f, C.c_void_p]),
     'qbold_posterior_stats': (C.c_int, [_P(QboldParams), _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f, _f,
                                         C.c_void_p]),

@@ -755,6 +755,78 @@ __global__ void __launch_bounds__(kThreads, 4) k_nll_map_pair(const __grid_const
     }
 }
 
+// fine_tune_loss_fn alone (model.py:527-568), for predictions that already exist in HBM (the unfused graph of
+// build_fine_tuner): per-voxel masked NLL and its partial derivatives w.r.t. the predicted images and sigmas.
+// W lanes serve one voxel (W = 16: two voxels per warp when n_tau <= 16).  HBM-bound: 3 reads + 2 writes of [n,n_tau].
+template <int W>
+__global__ void __launch_bounds__(kThreads) k_nll(const __grid_constant__ QboldParams P, const float* __restrict__ y,
+                                                  const float* __restrict__ pred_in, const float* __restrict__ sigma,
+                                                  const float* __restrict__ mask, int64_t n, float* __restrict__ nll_map,
+                                                  float* __restrict__ d_pred, float* __restrict__ d_sigma) {
+    const int lane = threadIdx.x & 31, t = lane & (W - 1), gb = lane & ~(W - 1);
+    constexpr int kPer = 32 / W;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int nt = P.n_tau;
+    const bool live = t < nt;
+    const int se = P.se_idx;
+    const bool multi = P.multi_image_normalisation != 0;
+    const bool in_norm = multi ? (t >= se - 1 && t <= se + 1) : (t == se);
+    const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
+    const bool wide = (W == 32) && nt > 16;
+    const float df = P.student_t_df;
+    const int64_t ngroups = (n + kPer - 1) / kPer;
+    for (int64_t gidx = warp; gidx < ngroups; gidx += nwarps) {
+        int64_t v = gidx * kPer + (lane / W);
+        const bool valid = v < n;
+        if (!valid) v = n - 1;
+        const float m = mask ? __ldg(mask + v) : 1.0f;
+        const float yv = live ? __ldg(y + v * nt + t) : 0.f;
+        const float pred = live ? __ldg(pred_in + v * nt + t) : 0.f;
+        const float sg = live ? __ldg(sigma + v * nt + t) : 1.f;
+        float npd, ny;
+        if (multi) {
+            npd = sum_live(in_norm ? pred * norm_w : 0.f, wide) + 1e-3f;
+            ny = sum_live(in_norm ? yv * norm_w : 0.f, wide) + 1e-3f;
+        } else {
+            npd = __shfl_sync(kFull, pred, gb + se) + 1e-3f;
+            ny = __shfl_sync(kFull, yv, gb + se) + 1e-3f;
+        }
+        const float inv_npd = 1.0f / npd, inv_sg = 1.0f / sg;
+        float yn = yv / ny, pn = pred * inv_npd, dpn = 1.0f;
+        if (P.predict_log_data) {                                   // where(mask > 0, log(.), 0), model.py:547-549
+            if (m > 0.f) {
+                dpn = 1.0f / pn;
+                yn = logf(yn);
+                pn = logf(pn);
+            } else {
+                yn = pn = dpn = 0.f;
+            }
+        }
+        const float zq = (yn - pn) * inv_sg;
+        float nll_t, dnll_dres, dnll_dsg;
+        if (df > 0.f) {
+            student_t_terms(P.student_t_logc, df, zq, sg, inv_sg, nll_t, dnll_dres, dnll_dsg);
+        } else {
+            nll_t = -(-logf(sg) - kLogSqrt2Pi - 0.5f * (zq * zq));
+            dnll_dres = zq * inv_sg;
+            dnll_dsg = inv_sg - (zq * zq) * inv_sg;
+        }
+        if (!live) nll_t = 0.f;
+        const float g_ratio = live ? (-dnll_dres * m) * dpn : 0.f;
+        const float nll_v = sum_live(nll_t, wide);
+        const float s_gp = sum_live(g_ratio * pred, wide);
+        const float g_npd = -s_gp * (inv_npd * inv_npd);
+        if (valid) {
+            if (live) {
+                if (d_pred) d_pred[v * nt + t] = g_ratio * inv_npd + (in_norm ? g_npd * norm_w : 0.f);
+                if (d_sigma) d_sigma[v * nt + t] = dnll_dsg * m;
+            }
+            if (t == 0) nll_map[v] = nll_v * m;
+        }
+    }
+}
+
 // ReparamTrickLayer alone (model.py:21-50): one thread per voxel.
 __global__ void __launch_bounds__(kThreads) k_reparam(const float* __restrict__ q, const float* __restrict__ eps,
                                                       uint64_t seed, uint64_t offset, int64_t n,
@@ -946,6 +1018,25 @@ extern "C" int qbold_nll_map(const QboldParams* p, const float* q, const float* 
     else QB_LAUNCH_NLL(kColsMulti);
 #undef QB_LAUNCH_NLL
     return after_launch("k_nll_map");
+}
+
+extern "C" int qbold_nll(const QboldParams* p, const float* y, const float* pred, const float* sigma, const float* mask,
+                         int64_t n, float* nll_map, float* d_pred, float* d_sigma, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_nll: bad params block");
+    if (n < 0 || (n > 0 && (!y || !pred || !sigma || !nll_map))) return fail(QBOLD_EINVAL, "qbold_nll: bad argument");
+    if (n == 0) return QBOLD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (p->n_tau <= 16) {
+        const int64_t want = ((n + 1) / 2 + 7) / 8;
+        k_nll<16><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(*p, y, pred, sigma, mask, n, nll_map, d_pred,
+                                                                           d_sigma);
+    } else {
+        const int64_t want = (n + 7) / 8;
+        k_nll<32><<<(unsigned)(want < cap ? want : cap), kThreads, 0, st>>>(*p, y, pred, sigma, mask, n, nll_map, d_pred,
+                                                                           d_sigma);
+    }
+    return after_launch("k_nll");
 }
 
 extern "C" int qbold_reparam_sample(const float* q, const float* eps, uint64_t seed, uint64_t offset, int64_t n,

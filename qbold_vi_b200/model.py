@@ -103,6 +103,27 @@ class _KlFn(torch.autograd.Function):
         return grad * g[:, None], None, None, None, None, None
 
 
+class _NllFn(torch.autograd.Function):
+    """fine_tune_loss_fn's per-voxel map from predictions that already exist (qbold_nll); the kernel also returns
+    the partial derivatives, so backward is two multiplies."""
+
+    @staticmethod
+    def forward(ctx, pred, sigma, y, mask, params):
+        n, nt = pred.shape
+        nll = torch.empty(n, dtype=torch.float32, device=pred.device)
+        d_pred, d_sigma = torch.empty_like(pred), torch.empty_like(sigma)
+        with torch.cuda.device(pred.device):
+            check(_lib.lib().qbold_nll(C.byref(params), dptr(y), dptr(pred), dptr(sigma), dptr(mask), n, dptr(nll),
+                                       dptr(d_pred), dptr(d_sigma), stream_ptr(pred.device)))
+        ctx.save_for_backward(d_pred, d_sigma)
+        return nll
+
+    @staticmethod
+    def backward(ctx, g):
+        d_pred, d_sigma = ctx.saved_tensors
+        return d_pred * g[:, None], d_sigma * g[:, None], None, None, None
+
+
 class _FusedElboFn(torch.autograd.Function):
     """loss = nll + kl_weight * kl of one (local) batch; gradients come from the same launch."""
 
@@ -250,16 +271,37 @@ class EncoderTrainer:
         return self._layer
 
     # ------------------------------------------------------------------ likelihood (model.py:527-568)
-    def fine_tune_loss_fn(self, y_true, y_pred, return_mean=True):
+    def fine_tune_loss_fn(self, y_true, y_pred, return_mean=True, signal_layer=None):
+        """model.py:527-568.  y_true [...,n_tau+1] (last channel = mask), y_pred [...,2*n_tau] (images, sigmas)."""
         y_true = torch.cat([y_true for _ in range(self._no_samples)], 0)
+        no_images = y_true.shape[-1] - 1
+        if not self._heteroscedastic_noise:
+            return self._fine_tune_loss_homoscedastic(y_true, y_pred, return_mean)
+        if y_pred.shape[-1] != 2 * no_images:
+            raise ValueError('y_pred must hold %d predicted images followed by %d sigmas' % (no_images, no_images))
+        layer = signal_layer or self._layer_for_tau_count(no_images)
+        pred = y_pred[..., :no_images].reshape(-1, no_images).float().contiguous()
+        sigma = y_pred[..., no_images:].reshape(-1, no_images).float().contiguous()
+        y = y_true[..., :no_images].reshape(-1, no_images).float().contiguous()
+        mask = y_true[..., -1].reshape(-1).float().contiguous()
+        nll = _NllFn.apply(pred, sigma, y, mask, self._params_for(layer))
+        if return_mean:
+            return torch.sum(nll) / torch.sum(mask)
+        return nll.reshape(-1, 1)
+
+    def _layer_for_tau_count(self, no_images):
+        layer = self._default_layer()
+        if layer.n_tau != no_images:
+            raise ValueError('fine_tune_loss_fn: %d images but the system parameters define %d taus; pass signal_layer='
+                             % (no_images, layer.n_tau))
+        return layer
+
+    def _fine_tune_loss_homoscedastic(self, y_true, y_pred, return_mean):
+        """heteroscedastic_noise=False branch (model.py:535-537): a single scalar sigma; plain tensor ops."""
         mask = y_true[..., -1:]
         no_images = y_true.shape[-1] - 1
-        if self._heteroscedastic_noise:
-            y_pred, sigma = torch.split(y_pred, y_pred.shape[-1] // 2, -1)
-            sigma = sigma.reshape(-1, no_images)
-        else:
-            sigma = torch.mean(y_pred[..., -1:])
-            y_pred = y_pred[..., :-1]
+        sigma = torch.mean(y_pred[..., -1:])
+        y_pred = y_pred[..., :-1]
         se = self._se_idx
         if self._multi_image_normalisation:
             y_true = y_true / (torch.mean(y_true[..., se - 1:se + 2], -1, keepdim=True) + 1e-3)

@@ -595,3 +595,45 @@ def test_fused_elbo_other_grids_and_closed_form(qb, dev, cfg_noise_off, grid):
     assert rel_max(info['nll_map'].cpu().numpy(), ref['nll_map']) < GRAD_TOL
     assert rel_max(qt.grad.cpu().numpy(), ref['grad_q']) < GRAD_TOL
     assert rel_max(st.grad.cpu().numpy(), ref['grad_sigma']) < GRAD_TOL
+
+
+@pytest.mark.parametrize('tag', ['optimal', 'multinorm', 'studentt'])
+def test_standalone_fine_tune_loss_fn_kernel(qb, dev, cfg_noise_off, tag):
+    """fine_tune_loss_fn(y_true, y_pred) on predictions that already exist (qbold_nll) vs the reference source."""
+    e = golden('ref_shim_elbo_%s.npz' % tag)
+    tr = _trainer(qb, cfg_noise_off, student_t_df=float(e['student_t_df']),
+                  multi_image_normalisation=bool(e['multi_image_normalisation']))
+    y_true = torch.cat([_t(e['data'], dev), _t(e['mask'], dev)[:, None]], -1).reshape(2, 4, 4, 2, 12)
+    pred = _t(e['pred'], dev).requires_grad_(True)
+    sg = _t(e['sigma'], dev).requires_grad_(True)
+    y_pred = torch.cat([pred, sg], -1).reshape(2, 4, 4, 2, 22)
+    nll = tr.fine_tune_loss_fn(y_true, y_pred)
+    assert rel_elem(nll.item(), e['nll']) < GRAD_TOL
+    nll.backward()
+    assert rel_max(sg.grad.cpu().numpy(), e['grad_sigma']) < GRAD_TOL
+    m = tr.fine_tune_loss_fn(y_true, y_pred, return_mean=False)
+    assert tuple(m.shape) == (64, 1) and rel_max(m.detach().cpu().numpy().reshape(-1), e['nll_map']) < GRAD_TOL
+    # d nll / d pred against autograd of the reference formulas written with torch ops (float64)
+    p64 = _t(e['pred'], dev).double().requires_grad_(True)
+    yt, s64, mk = _t(e['data'], dev).double(), _t(e['sigma'], dev).double(), _t(e['mask'], dev).double()
+    se = 2
+    if bool(e['multi_image_normalisation']):
+        yn, pn = yt / (yt[:, se - 1:se + 2].mean(-1, keepdim=True) + 1e-3), p64 / (p64[:, se - 1:se + 2].mean(-1, keepdim=True) + 1e-3)
+    else:
+        yn, pn = yt / (yt[:, se:se + 1] + 1e-3), p64 / (p64[:, se:se + 1] + 1e-3)
+    zq = (yn - pn) / s64
+    df = float(e['student_t_df'])
+    if df < 50:
+        import math
+        c = math.lgamma(0.5 * (df + 1)) - math.lgamma(0.5 * df) - 0.5 * math.log(df * math.pi)
+        nl = -(c - torch.log(s64) - 0.5 * (df + 1) * torch.log1p(zq * zq / df))
+    else:
+        nl = torch.log(s64) + 0.5 * math_log_2pi() + 0.5 * zq * zq
+    ref = ((nl.sum(-1) * mk).sum() / mk.sum())
+    ref.backward()
+    assert rel_max(pred.grad.cpu().numpy(), p64.grad.cpu().numpy()) < GRAD_TOL
+
+
+def math_log_2pi():
+    import math
+    return math.log(2.0 * math.pi)
