@@ -200,6 +200,32 @@ int qbold_nll_map(const QboldParams* p, const float* q, const float* sigma, cons
                   const float* eps, uint64_t seed, uint64_t offset, int32_t n_samples, int64_t n, float* nll_map,
                   void* stream);
 
+/* ---- losses either side of the fused path ---------------------------------------- */
+
+/* smoothness_loss (model.py:726-754): total variation of the forward-transformed, range-rescaled means over
+ * x / y neighbours that are both inside the mask.  q [n_vol,nx,ny,nz,n_ch] (n_ch = 5 mvg / 4 diagonal; channels 0
+ * and 2 are the means), mask [n_vol,nx,ny,nz].  *tv_sum += sum |d| (double, caller zeroes; may be NULL);
+ * grad_q (same shape as q, may be NULL) = scale * d(sum |d|)/dq, so scale = weight / sum(mask). */
+int qbold_smoothness(const float* q, int32_t n_ch, const float* mask, int64_t n_vol, int32_t nx, int32_t ny,
+                     int32_t nz, float scale, double* tv_sum, float* grad_q, void* stream);
+
+/* synthetic_data_loss (model.py:449-514) per label row: logit-MVN NLL of (OEF, DBV) under the predicted
+ * distribution (use_mvg: logit_gaussian_mvg_log_prob :376-400, pred [n,5]; else logit_gaussian_log_prob :406-421,
+ * pred [n,4]) minus, when inv_gamma_alpha*inv_gamma_beta > 0, the InverseGamma log-prior of the predicted
+ * variances (:495-507).  labels [n,label_stride] (OEF, DBV first).  Outputs (each may be NULL): nll_rows [n],
+ * grad_pred = grad_scale * d nll_rows[v] / d pred[v,:], *loss_sum += sum of rows (double, caller zeroes). */
+int qbold_synth_nll(const float* labels, int32_t label_stride, const float* pred, int32_t use_mvg,
+                    double inv_gamma_alpha, double inv_gamma_beta, int64_t n, float grad_scale, float* nll_rows,
+                    float* grad_pred, double* loss_sum, void* stream);
+
+/* KL of the diagonal (use_mvg=False) branch of kl_loss (model.py:685-708): tfp LogitNormal.kl_divergence for OEF
+ * plus DBV, zero where mask <= 0 (mask may be NULL).  pred / prior rows = [mean_o, raw_std_o, mean_d, raw_std_d]
+ * at the given row strides (the population-prior layout keeps both in one 8-channel tensor, :687-689).
+ * grad_pred / grad_prior (may be NULL) = d kl_map[v] / d row, written at their own row strides. */
+int qbold_diag_kl(const float* pred, int32_t pred_stride, const float* prior, int32_t prior_stride,
+                  const float* mask, int64_t n, float* kl_map, float* grad_pred, int32_t grad_pred_stride,
+                  float* grad_prior, int32_t grad_prior_stride, void* stream);
+
 /* FP32 FMA micro-benchmark (roofline denominator measured in the same run): launches
  * `iters` dependent-chain FFMA sweeps, returns achieved TFLOP/s through *tflops. */
 int qbold_fma_peak(int32_t iters, double* tflops);

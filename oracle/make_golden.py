@@ -163,6 +163,93 @@ def main():
                  dbv_tn_u01=log[3][1].numpy(), uniform_prop=uprop, sample_size=23)
         print('dataset[%s]: x %s y %s' % (tag, tuple(tx.shape), tuple(ty.shape)))
 
+    # ------------------------------------------------------------------ F. losses either side of the path
+    def make_trainer(**kw):
+        base = dict(system_params=params, no_units=60, no_intermediate_layers=2, student_t_df=200,
+                    initial_im_sigma=0.05, multi_image_normalisation=False, channelwise_gating=True,
+                    infer_inv_gamma=False, use_population_prior=False, use_mvg=True, predict_log_data=False)
+        base.update(kw)
+        return ref_model.EncoderTrainer(**base)
+
+    r = np.random.default_rng(77)
+    shp = (2, 6, 5, 3)
+    nv = int(np.prod(shp))
+    adj = {}
+    q5 = np.stack([r.normal(-0.3, 0.9, nv), r.normal(0.0, 0.6, nv), r.normal(-1.2, 0.9, nv),
+                   r.normal(0.0, 0.6, nv), r.normal(0.0, 0.8, nv)], -1).astype(np.float32)
+    q5[7, 0] = q5[8, 0]                                      # an exact tie: |d| has zero sub-gradient there
+    prior5 = (q5 + r.normal(0, 0.3, (nv, 5))).astype(np.float32)
+    mask = (r.uniform(size=nv) > 0.3).astype(np.float32)
+    labels = np.stack([r.uniform(0.05, 0.8, nv), r.uniform(0.003, 0.195, nv), r.uniform(0.5, 20.0, nv)], -1)
+    labels = labels.astype(np.float32)
+    labels[0, :2] = [0.04, 0.201]                            # exactly on the transform bounds: exercises the clip
+    adj.update(q5=q5, prior5=prior5, mask=mask, labels=labels, shape=np.array(shp))
+
+    def t5(a, c):
+        t = tf.convert_to_tensor(a.reshape(shp + (c,)))
+        t.requires_grad_(True)
+        return t
+
+    m_t = tf.convert_to_tensor(mask.reshape(shp + (1,)))
+    # F1 smoothness (model.py:726-754), mvg and diagonal layouts
+    tr = make_trainer()
+    q_t = t5(q5, 5)
+    tv = tr.smoothness_loss(tf.concat([tf.convert_to_tensor(prior5.reshape(shp + (5,))), m_t], -1), q_t)
+    adj['tv_mvg'] = tv.detach().numpy()
+    adj['tv_mvg_grad'] = torch.autograd.grad(tv, [q_t])[0].numpy().reshape(nv, 5)
+    tr_d = make_trainer(use_mvg=False)
+    q4_t = t5(q5[:, :4], 4)
+    tv = tr_d.smoothness_loss(tf.concat([tf.convert_to_tensor(prior5[:, :4].reshape(shp + (4,))), m_t], -1), q4_t)
+    adj['tv_diag'] = tv.detach().numpy()
+    adj['tv_diag_grad'] = torch.autograd.grad(tv, [q4_t])[0].numpy().reshape(nv, 4)
+    # F2 pre-training loss (model.py:449-514): mvg / diagonal, with and without the inverse-gamma term
+    lab_t = tf.convert_to_tensor(labels.reshape(shp + (3,)))
+    for tag, trn, c, ig in (('mvg', tr, 5, (0.0, 0.0)), ('mvg_ig', tr, 5, (3.0, 0.15)),
+                            ('diag', tr_d, 4, (0.0, 0.0)), ('diag_ig', tr_d, 4, (3.0, 0.15))):
+        lab = labels.copy()
+        if c == 4:
+            lab[0, :2] = [0.3, 0.05]                         # the diagonal branch has no clip: keep labels interior
+        # With the inverse-gamma term the reference subtracts a [N] vector from the [B,X,Y,Z] loss (model.py:507),
+        # which only broadcasts for [N,1,1,1] inputs (to [N,1,1,N]; its mean = mean(loss) - mean(prior term)).
+        vshape = (nv, 1, 1, 1) if ig[0] * ig[1] > 0.0 else shp
+        q_t = tf.convert_to_tensor(q5[:, :c].reshape(vshape + (c,)))
+        q_t.requires_grad_(True)
+        loss = trn.synthetic_data_loss(tf.convert_to_tensor(lab.reshape(vshape + (3,))), q_t, False, ig[0], ig[1])
+        adj['synth_%s' % tag] = loss.detach().numpy()
+        adj['synth_%s_grad' % tag] = torch.autograd.grad(loss, [q_t])[0].numpy().reshape(nv, c)
+        adj['synth_%s_labels' % tag] = lab
+    # F2b r2p term (10 recorded reparam draws, model.py:480-494)
+    tf.random.set_seed(21)
+    tf.random.LOG.clear()
+    q_t = tf.convert_to_tensor(q5.reshape(nv, 1, 1, 1, 5))           # same broadcast constraint (model.py:490)
+    q_t.requires_grad_(True)
+    loss = tr.synthetic_data_loss(tf.convert_to_tensor(labels.reshape(nv, 1, 1, 1, 3)), q_t, True, 0.0, 0.0)
+    adj['synth_r2p'] = loss.detach().numpy()
+    adj['synth_r2p_grad'] = torch.autograd.grad(loss, [q_t])[0].numpy().reshape(nv, 5)
+    adj['synth_r2p_eps'] = np.stack([e[1].numpy().reshape(nv, 2) for e in tf.random.LOG], 1)
+    # F3 metrics (model.py:345-374): 20 recorded draws each
+    for i, name in enumerate(('oef', 'dbv', 'r2p')):
+        tf.random.set_seed(30 + i)
+        tf.random.LOG.clear()
+        val = getattr(tr, name + '_metric')(lab_t, tf.convert_to_tensor(q5.reshape(shp + (5,))))
+        adj['metric_' + name] = val.detach().numpy()
+        adj['metric_%s_eps' % name] = np.stack([e[1].numpy().reshape(nv, 2) for e in tf.random.LOG], 1)
+    # F4 diagonal KL variants (model.py:685-716): plain and population prior
+    q4_t = t5(q5[:, :4], 4)
+    kl = tr_d.kl_loss(tf.concat([tf.convert_to_tensor(prior5[:, :4].reshape(shp + (4,))), m_t], -1), q4_t)
+    adj['kl_diag'] = kl.detach().numpy()
+    adj['kl_diag_grad'] = torch.autograd.grad(kl, [q4_t])[0].numpy().reshape(nv, 4)
+    tr_p = make_trainer(use_mvg=False, use_population_prior=True)
+    pop = np.tile(np.array([[-0.2, 0.3, -1.0, 0.2]], np.float32), (nv, 1))
+    q8_t = t5(np.concatenate([q5[:, :4], pop], -1), 8)
+    kl = tr_p.kl_loss(tf.concat([tf.convert_to_tensor(prior5[:, :4].reshape(shp + (4,))), m_t], -1), q8_t)
+    adj['kl_pop'] = kl.detach().numpy()
+    adj['kl_pop_grad'] = torch.autograd.grad(kl, [q8_t])[0].numpy().reshape(nv, 8)
+    adj['kl_pop_pred'] = q8_t.detach().numpy().reshape(nv, 8)
+    np.savez(os.path.join(args.out, 'ref_shim_adjacent.npz'), **adj)
+    print('adjacent: tv=%.6f synth=%.6f kl_diag=%.6f kl_pop=%.6f' % (float(adj['tv_mvg']), float(adj['synth_mvg']),
+                                                                   float(adj['kl_diag']), float(adj['kl_pop'])))
+
     # ------------------------------------------------------------------ E. Appendix B KATs
     np.savez(os.path.join(args.out, 'kat_appendix_b.npz'),
              oef_dbv=np.array([[0.4, 0.12], [0.4, 0.03]]),

@@ -689,3 +689,112 @@ def synthetic_dataset_from_draws(ph: Physics, oefs, dbvs, perm, snr_u=None, nois
     train_x = np.concatenate(xs, 0)                                  # rows beyond 10*chunk are dropped (:283-287)
     r2p = calculate_r2p(ph, train_y[:, 0], train_y[:, 1], None, dt)  # :296
     return train_x, np.concatenate([train_y[:, :2], r2p[:, None]], -1).astype(dt)
+
+
+# --------------------------------------------------------------------------
+# losses either side of the path
+# --------------------------------------------------------------------------
+def smoothness_loss(q, mask, dt=F64):
+    """Total-variation term, model.py:726-754: x/y neighbour differences of the forward-transformed, range-rescaled
+    means, both voxels inside the mask, sum|d| / sum(mask).  q [B,X,Y,Z,C>=4] (channels 0 and 2 are the means),
+    mask [B,X,Y,Z].  Returns (value, d value / d q) -- sub-gradient sign(0) = 0 as tf.abs."""
+    q = np.asarray(q, dtype=dt)
+    mask = np.asarray(mask, dtype=dt)
+    z = np.stack([q[..., 0], q[..., 2]], -1)
+    s = _sigmoid(z, dt)
+    rng = np.array([0.8, 0.2], dtype=dt)
+    mn = np.array([0.04, 0.001], dtype=dt)
+    p = (s * rng + mn) / rng                                                     # model.py:736-738
+    g_p = np.zeros_like(p)
+    total = dt(0)
+    for axis in (1, 2):
+        lo = [slice(None)] * 5
+        hi = [slice(None)] * 5
+        lo[axis], hi[axis] = slice(None, -1), slice(1, None)
+        lo, hi = tuple(lo), tuple(hi)
+        both = ((mask[lo[:4]] > 0) & (mask[hi[:4]] > 0))[..., None]
+        d = np.where(both, p[lo] - p[hi], 0)                                     # model.py:741-747
+        total = total + np.abs(d).sum()
+        g_p[lo] += np.sign(d)
+        g_p[hi] -= np.sign(d)
+    msum = mask.sum()
+    g = np.zeros_like(q)
+    dz = g_p * (s * (1 - s)) / msum                                              # d p / d z = range * s(1-s) / range
+    g[..., 0], g[..., 2] = dz[..., 0], dz[..., 1]
+    return dt(total / msum), g
+
+
+def _lgamma(x):
+    import math as _m
+    return _m.lgamma(x)
+
+
+def synthetic_data_nll(labels, pred, use_mvg=True, inv_gamma_alpha=0.0, inv_gamma_beta=0.0, dt=F64):
+    """Per-row pre-training loss of synthetic_data_loss (model.py:449-514, without the sampled r2p term) and its
+    gradient w.r.t. the raw predictions.  labels [N,>=2] (OEF, DBV), pred [N,5] (mvg) or [N,4] (diagonal).
+    The reference's result is mean(rows) (for the inverse-gamma term: see oracle/make_golden.py, section F)."""
+    import math as _m
+    y = np.asarray(labels, dtype=dt)
+    q = np.asarray(pred, dtype=dt)
+    x = backwards_transform(y[:, :2], False, dt)                                 # model.py:393 / :416
+    th1, th3 = np.tanh(q[:, 1]), np.tanh(q[:, 3])
+    ls_o, ls_d = th1 * 3 - 1, th3 * 3 - 1
+    g = np.zeros_like(q)
+    if use_mvg:
+        x = np.clip(x, 1e-6, 1 - 1e-6)                                           # model.py:394-395
+        th4 = np.tanh(q[:, 4])
+        cov = th4 * np.exp(dt(-2.0))
+        const = _m.log(2.0 * _m.pi)
+    else:
+        cov = np.zeros_like(ls_o)
+        const = 0.0                                                              # gaussian_nll drops it (model.py:404)
+    zl = np.log(x / (1 - x))
+    r_o, r_d = zl[:, 0] - q[:, 0], zl[:, 1] - q[:, 2]
+    inv_o, inv_d, e_neg = np.exp(-ls_o), np.exp(-ls_d), np.exp(-ls_o - ls_d)
+    w_o = r_o * inv_o
+    w_d = r_d * inv_d - r_o * e_neg * cov                                        # model.py:432-439
+    loss = const + (ls_o + ls_d) + 0.5 * (w_o ** 2 + w_d ** 2)
+    loss = loss + np.log(x[:, 0]) + np.log(1 - x[:, 0]) + np.log(x[:, 1]) + np.log(1 - x[:, 1])
+    g[:, 0] = -(w_o * inv_o - w_d * e_neg * cov)
+    g[:, 2] = -w_d * inv_d
+    d_ls_o = 1 - w_o ** 2 + w_d * r_o * e_neg * cov
+    d_ls_d = 1 - w_d ** 2
+    d_cov = -w_d * r_o * e_neg
+    d_q4 = np.zeros_like(ls_o)
+    if inv_gamma_alpha * inv_gamma_beta > 0.0:                                   # model.py:495-507
+        a, b = inv_gamma_alpha, inv_gamma_beta
+        if use_mvg:
+            v_o, v_d = np.exp(ls_o) ** 2, np.exp(ls_d) ** 2 + q[:, 4] ** 2       # raw channel 4, as the reference
+            dv_d_ls, d_q4 = 2 * np.exp(ls_d) ** 2, 2 * q[:, 4]
+        else:
+            v_o, v_d = np.exp(ls_o * 2), np.exp(ls_d * 2)
+            dv_d_ls = 2 * v_d
+        lp = lambda v: a * _m.log(b) - _lgamma(a) - (a + 1) * np.log(v) - b / v  # noqa: E731
+        dlp = lambda v: -(a + 1) / v + b / v ** 2                                # noqa: E731
+        loss = loss - (lp(v_o) + lp(v_d))
+        d_ls_o = d_ls_o - dlp(v_o) * 2 * v_o
+        d_ls_d = d_ls_d - dlp(v_d) * dv_d_ls
+        d_q4 = -dlp(v_d) * d_q4
+    g[:, 1] = d_ls_o * 3 * (1 - th1 ** 2)
+    g[:, 3] = d_ls_d * 3 * (1 - th3 ** 2)
+    if use_mvg:
+        g[:, 4] = d_cov * np.exp(dt(-2.0)) * (1 - th4 ** 2) + d_q4
+    return loss.astype(dt), g.astype(dt)
+
+
+def diag_kl(prior, pred, dt=F64):
+    """KL of the diagonal (use_mvg=False) branch, model.py:685-708: tfp LogitNormal.kl_divergence = KL of the
+    underlying Normals, summed over OEF and DBV.  prior / pred [N,4] raw.  Returns (kl, d/d pred, d/d prior)."""
+    q, p = np.asarray(pred, dtype=dt), np.asarray(prior, dtype=dt)
+    kl = np.zeros(q.shape[0], dtype=dt)
+    gq, gp = np.zeros_like(q), np.zeros_like(p)
+    for m, s in ((0, 1), (2, 3)):
+        thq, thp = np.tanh(q[:, s]), np.tanh(p[:, s])
+        lq, lp = thq * 3 - 1, thp * 3 - 1
+        d = (q[:, m] - p[:, m]) * np.exp(-lp)
+        kl += 0.5 * d ** 2 + 0.5 * np.expm1(2 * (lq - lp)) - (lq - lp)
+        gq[:, m] = d * np.exp(-lp)
+        gp[:, m] = -d * np.exp(-lp)
+        gq[:, s] = (np.exp(2 * (lq - lp)) - 1) * 3 * (1 - thq ** 2)
+        gp[:, s] = (-d ** 2 - np.exp(2 * (lq - lp)) + 1) * 3 * (1 - thp ** 2)
+    return kl, gq, gp

@@ -43,5 +43,26 @@ class _StudentT:
         return c - torch.log(self.scale) - 0.5 * (df + 1.0) * torch.log1p(y * y / df)
 
 
-distributions = types.SimpleNamespace(TruncatedNormal=_TruncatedNormal, StudentT=_StudentT)
+class _LogitNormal:
+    """Only kl_divergence is used (model.py:695-698).  TFP evaluates the KL of a bijected distribution as the KL of
+    the base Normals (_kl_normal_normal): 0.5*((mu_a-mu_b)/s_b)^2 + 0.5*expm1(2*log(s_a/s_b)) - log(s_a/s_b)."""
+
+    def __init__(self, loc, scale):
+        self.loc, self.scale = loc, scale
+
+    def kl_divergence(self, other):
+        d = torch.log(self.scale) - torch.log(other.scale)
+        return 0.5 * (self.loc / other.scale - other.loc / other.scale) ** 2 + 0.5 * torch.expm1(2.0 * d) - d
+
+
+class _InverseGamma:
+    def __init__(self, concentration, scale):
+        self.a, self.b = tf._t(concentration).float(), tf._t(scale).float()
+
+    def log_prob(self, x):
+        return self.a * torch.log(self.b) - torch.lgamma(self.a) - (self.a + 1.0) * torch.log(x) - self.b / x
+
+
+distributions = types.SimpleNamespace(TruncatedNormal=_TruncatedNormal, StudentT=_StudentT, LogitNormal=_LogitNormal,
+                                      InverseGamma=_InverseGamma)
 layers = types.SimpleNamespace()

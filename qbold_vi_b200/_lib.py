@@ -74,6 +74,12 @@ _SIGNATURES = {
                                         C.c_void_p]),
     'qbold_nll_map': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f,
                                 C.c_void_p]),
+    'qbold_smoothness': (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, _f, _f,
+                                   C.c_void_p]),
+    'qbold_synth_nll': (C.c_int, [_f, C.c_int32, _f, C.c_int32, C.c_double, C.c_double, C.c_int64, C.c_float, _f, _f,
+                                  _f, C.c_void_p]),
+    'qbold_diag_kl': (C.c_int, [_f, C.c_int32, _f, C.c_int32, _f, C.c_int64, _f, _f, C.c_int32, _f, C.c_int32,
+                                C.c_void_p]),
     'qbold_fma_peak': (C.c_int, [C.c_int32, _P(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,260 @@
+// Losses either side of the fused path, each value + analytic gradient in ONE pass:
+//   k_smoothness : total-variation term on the encoder output        (reference model.py:726-754)
+//   k_synth_nll  : pre-training logit-normal NLL of the labels       (model.py:449-514, 376-421)
+//   k_diag_kl    : KL of the diagonal (use_mvg=False) branch         (model.py:685-708)
+// All three are HBM-bound elementwise / 4-neighbour stencil kernels: one thread per voxel (row), grid-stride,
+// grid = a multiple of the SM count; the neighbour reads of the stencil are served by L1/L2.
+#include <math.h>
+
+#include "launch.h"
+
+namespace qb {
+
+namespace {
+
+constexpr float kOefRange = 0.8f, kMinOef = 0.04f, kDbvRange = 0.2f, kMinDbv = 0.001f;   // model.py:88-91
+constexpr float kExpM2 = 0.1353352832366127f;                                            // np.exp(-2.0), model.py:294
+constexpr float kLog2Pi = 1.8378770664093453f;
+
+__device__ __forceinline__ float sigmoidf(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+__device__ __forceinline__ float signf(float d) { return (d > 0.f) ? 1.0f : ((d < 0.f) ? -1.0f : 0.0f); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+int64_t stream_grid(int64_t n) {
+    const int64_t want = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 16;          // 16 x 256 threads = 2 full waves of resident CTAs per SM
+    return want < cap ? want : cap;
+}
+
+struct Pq {
+    float o, d;
+};
+
+// forward_transform, then the range rescale of model.py:736-738, written as the reference evaluates it
+__device__ __forceinline__ Pq rescaled(const float* __restrict__ q, int64_t v, int n_ch, float& s_o, float& s_d) {
+    s_o = sigmoidf(__ldg(q + v * n_ch + 0));
+    s_d = sigmoidf(__ldg(q + v * n_ch + 2));
+    return Pq{(s_o * kOefRange + kMinOef) / kOefRange, (s_d * kDbvRange + kMinDbv) / kDbvRange};
+}
+
+}  // namespace
+
+// One thread per voxel of q [B,X,Y,Z,n_ch].  Value: the edges (x,x+1) and (y,y+1) it owns; gradient: all four
+// edges that touch it (sign(0) = 0 like tf.abs; an edge counts only when both ends are inside the mask).
+__global__ void __launch_bounds__(kThreads) k_smoothness(const float* __restrict__ q, int n_ch,
+                                                         const float* __restrict__ mask, int64_t n, int X, int Y,
+                                                         int Z, float scale, double* __restrict__ tv_sum,
+                                                         float* __restrict__ grad_q) {
+    const int64_t sy = Z, sx = (int64_t)Y * Z;
+    double acc = 0.0;
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += (int64_t)gridDim.x * kThreads) {
+        const int64_t r = v / Z;
+        const int y = (int)(r % Y), x = (int)((r / Y) % X);
+        float g_o = 0.f, g_d = 0.f, s_o = 0.f, s_d = 0.f;
+        if (__ldg(mask + v) > 0.f) {
+            const Pq p = rescaled(q, v, n_ch, s_o, s_d);
+            float t_o, t_d;
+            if (x + 1 < X && __ldg(mask + v + sx) > 0.f) {
+                const Pq pn = rescaled(q, v + sx, n_ch, t_o, t_d);
+                const float d_o = p.o - pn.o, d_d = p.d - pn.d;
+                acc += (double)(fabsf(d_o) + fabsf(d_d));
+                g_o += signf(d_o);
+                g_d += signf(d_d);
+            }
+            if (y + 1 < Y && __ldg(mask + v + sy) > 0.f) {
+                const Pq pn = rescaled(q, v + sy, n_ch, t_o, t_d);
+                const float d_o = p.o - pn.o, d_d = p.d - pn.d;
+                acc += (double)(fabsf(d_o) + fabsf(d_d));
+                g_o += signf(d_o);
+                g_d += signf(d_d);
+            }
+            if (x > 0 && __ldg(mask + v - sx) > 0.f) {
+                const Pq pn = rescaled(q, v - sx, n_ch, t_o, t_d);
+                g_o -= signf(pn.o - p.o);
+                g_d -= signf(pn.d - p.d);
+            }
+            if (y > 0 && __ldg(mask + v - sy) > 0.f) {
+                const Pq pn = rescaled(q, v - sy, n_ch, t_o, t_d);
+                g_o -= signf(pn.o - p.o);
+                g_d -= signf(pn.d - p.d);
+            }
+        }
+        if (grad_q != nullptr) {
+            float* g = grad_q + v * n_ch;
+            g[0] = ((g_o * scale) / kOefRange) * kOefRange * (s_o * (1.0f - s_o));
+            g[1] = 0.f;
+            g[2] = ((g_d * scale) / kDbvRange) * kDbvRange * (s_d * (1.0f - s_d));
+            g[3] = 0.f;
+            if (n_ch > 4) g[4] = 0.f;
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0 && tv_sum != nullptr && acc != 0.0) atomicAdd(tv_sum, acc);
+}
+
+struct SynthOpts {
+    int use_mvg;
+    int inv_gamma;          // 1: subtract the inverse-gamma log-prior of the predicted variances
+    float ig_alpha, ig_beta, ig_const;   // ig_const = alpha*log(beta) - lgamma(alpha)
+};
+
+// One thread per label row.  labels [n, label_stride >= 2] (OEF, DBV, ...), pred [n, 5 | 4] raw.
+__global__ void __launch_bounds__(kThreads) k_synth_nll(const float* __restrict__ labels, int label_stride,
+                                                        const float* __restrict__ pred, SynthOpts opt, int64_t n,
+                                                        float grad_scale, float* __restrict__ nll_rows,
+                                                        float* __restrict__ grad_pred,
+                                                        double* __restrict__ loss_sum) {
+    const int nc = opt.use_mvg ? 5 : 4;
+    double acc = 0.0;
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += (int64_t)gridDim.x * kThreads) {
+        const float* q = pred + v * nc;
+        const float mu_o = __ldg(q + 0), mu_d = __ldg(q + 2);
+        const float th1 = tanhf(__ldg(q + 1)), th3 = tanhf(__ldg(q + 3));
+        const float ls_o = th1 * 3.0f - 1.0f, ls_d = th3 * 3.0f - 1.0f;              // transform_std, model.py:288-290
+        float x_o = (__ldg(labels + v * label_stride + 0) - kMinOef) / kOefRange;    // backwards_transform :307-311
+        float x_d = (__ldg(labels + v * label_stride + 1) - kMinDbv) / kDbvRange;
+        float th4 = 0.f, raw4 = 0.f, cov = 0.f, konst = 0.f;
+        if (opt.use_mvg) {
+            x_o = fminf(fmaxf(x_o, 1e-6f), 1.0f - 1e-6f);                            // model.py:394-395
+            x_d = fminf(fmaxf(x_d, 1e-6f), 1.0f - 1e-6f);
+            raw4 = __ldg(q + 4);
+            th4 = tanhf(raw4);
+            cov = th4 * kExpM2;
+            konst = kLog2Pi;
+        }
+        const float r_o = logf(x_o / (1.0f - x_o)) - mu_o, r_d = logf(x_d / (1.0f - x_d)) - mu_d;
+        const float inv_o = expf(ls_o * -1.0f), inv_d = expf(ls_d * -1.0f);
+        const float e_neg = expf(ls_o * -1.0f + ls_d * -1.0f);
+        const float inv_bl = (e_neg * cov) * -1.0f;                                  // model.py:434
+        const float w_o = r_o * inv_o;
+        const float w_d = r_d * inv_d + r_o * inv_bl;
+        float loss = konst + 0.5f * (2.0f * (ls_o + ls_d)) + 0.5f * (w_o * w_o + w_d * w_d);
+        if (opt.use_mvg)
+            loss += (logf(x_o) + logf(1.0f - x_o)) + (logf(x_d) + logf(1.0f - x_d));   // model.py:398
+        else
+            loss += logf(x_o * (1.0f - x_o)) + logf(x_d * (1.0f - x_d));               // model.py:419
+        float d_ls_o = 1.0f - w_o * w_o - w_d * r_o * inv_bl;
+        float d_ls_d = 1.0f - w_d * w_d;
+        float d_raw4 = (-w_d * r_o * e_neg) * kExpM2 * (1.0f - th4 * th4);
+        if (opt.inv_gamma) {                                                         // model.py:495-507
+            const float a1 = opt.ig_alpha + 1.0f, b = opt.ig_beta;
+            const float e_o = expf(ls_o), e_d = expf(ls_d);
+            const float v_o = opt.use_mvg ? e_o * e_o : expf(ls_o * 2.0f);
+            const float vd0 = opt.use_mvg ? e_d * e_d : expf(ls_d * 2.0f);
+            const float v_d = opt.use_mvg ? vd0 + raw4 * raw4 : vd0;                 // raw channel 4 (model.py:500)
+            loss -= (opt.ig_const - a1 * logf(v_o) - b / v_o) + (opt.ig_const - a1 * logf(v_d) - b / v_d);
+            const float dl_o = a1 / v_o - b / (v_o * v_o), dl_d = a1 / v_d - b / (v_d * v_d);
+            d_ls_o += dl_o * 2.0f * v_o;
+            d_ls_d += dl_d * 2.0f * vd0;
+            d_raw4 += dl_d * 2.0f * raw4;
+        }
+        acc += (double)loss;
+        if (nll_rows != nullptr) nll_rows[v] = loss;
+        if (grad_pred != nullptr) {
+            float* g = grad_pred + v * nc;
+            g[0] = -(w_o * inv_o + w_d * inv_bl) * grad_scale;
+            g[1] = d_ls_o * (3.0f * (1.0f - th1 * th1)) * grad_scale;
+            g[2] = -(w_d * inv_d) * grad_scale;
+            g[3] = d_ls_d * (3.0f * (1.0f - th3 * th3)) * grad_scale;
+            if (opt.use_mvg) g[4] = d_raw4 * grad_scale;
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0 && loss_sum != nullptr) atomicAdd(loss_sum, acc);
+}
+
+// KL(LogitNormal q || LogitNormal p) = KL of the underlying Normals, OEF + DBV (tfp, reference model.py:695-708).
+// pred / prior rows are [mean_o, raw_std_o, mean_d, raw_std_d] at arbitrary row strides, so the population-prior
+// layout (q and p side by side in one 8-channel tensor, model.py:687-689) needs no copy.
+__global__ void __launch_bounds__(kThreads) k_diag_kl(const float* __restrict__ pred, int pred_stride,
+                                                      const float* __restrict__ prior, int prior_stride,
+                                                      const float* __restrict__ mask, int64_t n,
+                                                      float* __restrict__ kl_map, float* __restrict__ grad_pred,
+                                                      int gpred_stride, float* __restrict__ grad_prior,
+                                                      int gprior_stride) {
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += (int64_t)gridDim.x * kThreads) {
+        const bool live = mask == nullptr || __ldg(mask + v) > 0.f;                  // model.py:717
+        float kl = 0.f, gq[4] = {0.f, 0.f, 0.f, 0.f}, gp[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < 4; c += 2) {
+                const float thq = tanhf(__ldg(pred + v * pred_stride + c + 1));
+                const float thp = tanhf(__ldg(prior + v * prior_stride + c + 1));
+                const float lq = thq * 3.0f - 1.0f, lp = thp * 3.0f - 1.0f;
+                const float inv_p = expf(-lp);
+                const float d = __ldg(pred + v * pred_stride + c) * inv_p - __ldg(prior + v * prior_stride + c) * inv_p;
+                const float dl = lq - lp;
+                const float em = expm1f(2.0f * dl);
+                kl += 0.5f * (d * d) + 0.5f * em - dl;
+                gq[c] = d * inv_p;
+                gp[c] = -d * inv_p;
+                gq[c + 1] = em * (3.0f * (1.0f - thq * thq));
+                gp[c + 1] = (-(d * d) - em) * (3.0f * (1.0f - thp * thp));
+            }
+        }
+        kl_map[v] = kl;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (grad_pred != nullptr) grad_pred[v * gpred_stride + c] = gq[c];
+            if (grad_prior != nullptr) grad_prior[v * gprior_stride + c] = gp[c];
+        }
+    }
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" int qbold_smoothness(const float* q, int32_t n_ch, const float* mask, int64_t n_vol, int32_t nx,
+                                int32_t ny, int32_t nz, float scale, double* tv_sum, float* grad_q, void* stream) {
+    if ((n_ch != 4 && n_ch != 5) || n_vol < 0 || nx <= 0 || ny <= 0 || nz <= 0)
+        return fail(QBOLD_EINVAL, "qbold_smoothness: bad shape (n_ch=%d, volumes=%lld, %d x %d x %d)", n_ch,
+                    (long long)n_vol, nx, ny, nz);
+    const int64_t n = n_vol * nx * ny * nz;
+    if (n == 0) return QBOLD_OK;
+    if (!q || !mask || (!tv_sum && !grad_q)) return fail(QBOLD_EINVAL, "qbold_smoothness: null pointer");
+    k_smoothness<<<(unsigned)stream_grid(n), kThreads, 0, (cudaStream_t)stream>>>(q, n_ch, mask, n, nx, ny, nz, scale,
+                                                                                  tv_sum, grad_q);
+    return after_launch("k_smoothness");
+}
+
+extern "C" int qbold_synth_nll(const float* labels, int32_t label_stride, const float* pred, int32_t use_mvg,
+                               double inv_gamma_alpha, double inv_gamma_beta, int64_t n, float grad_scale,
+                               float* nll_rows, float* grad_pred, double* loss_sum, void* stream) {
+    if (n < 0 || label_stride < 2) return fail(QBOLD_EINVAL, "qbold_synth_nll: bad argument");
+    if (n == 0) return QBOLD_OK;
+    if (!labels || !pred || (!nll_rows && !grad_pred && !loss_sum))
+        return fail(QBOLD_EINVAL, "qbold_synth_nll: null pointer");
+    SynthOpts opt{};
+    opt.use_mvg = use_mvg ? 1 : 0;
+    if (inv_gamma_alpha * inv_gamma_beta > 0.0) {
+        opt.inv_gamma = 1;
+        opt.ig_alpha = (float)inv_gamma_alpha;
+        opt.ig_beta = (float)inv_gamma_beta;
+        opt.ig_const = (float)(inv_gamma_alpha * log(inv_gamma_beta) - lgamma(inv_gamma_alpha));
+    }
+    k_synth_nll<<<(unsigned)stream_grid(n), kThreads, 0, (cudaStream_t)stream>>>(labels, label_stride, pred, opt, n,
+                                                                                 grad_scale, nll_rows, grad_pred,
+                                                                                 loss_sum);
+    return after_launch("k_synth_nll");
+}
+
+extern "C" int qbold_diag_kl(const float* pred, int32_t pred_stride, const float* prior, int32_t prior_stride,
+                             const float* mask, int64_t n, float* kl_map, float* grad_pred, int32_t grad_pred_stride,
+                             float* grad_prior, int32_t grad_prior_stride, void* stream) {
+    if (n < 0 || pred_stride < 4 || prior_stride < 4 || (grad_pred && grad_pred_stride < 4) ||
+        (grad_prior && grad_prior_stride < 4))
+        return fail(QBOLD_EINVAL, "qbold_diag_kl: bad argument");
+    if (n == 0) return QBOLD_OK;
+    if (!pred || !prior || !kl_map) return fail(QBOLD_EINVAL, "qbold_diag_kl: null pointer");
+    k_diag_kl<<<(unsigned)stream_grid(n), kThreads, 0, (cudaStream_t)stream>>>(
+        pred, pred_stride, prior, prior_stride, mask, n, kl_map, grad_pred, grad_pred_stride, grad_prior,
+        grad_prior_stride);
+    return after_launch("k_diag_kl");
+}

@@ -98,10 +98,11 @@ class DataParallelTrainer:
 
     loss = NLL + kl_weight * KL + smoothness_weight * TV, each normalised by the global mask count.
     ``loss_fn(q, sigma, data, mask, prior, mask_sum) -> (loss, info)`` defaults to the fused sm_100a kernel
-    (EncoderTrainer.fused_elbo); tests of the host logic inject a stand-in."""
+    (EncoderTrainer.fused_elbo) and ``tv_fn(q, prior, mask, mask_sum) -> tv`` to the stencil kernel
+    (EncoderTrainer.smoothness_loss); tests of the host logic inject stand-ins."""
 
     def __init__(self, encoder, trainer, signal_layer, ft_lr=5e-3, adamw_decay=2e-4, smoothness_weight=5.0,
-                 kl_weight=1.0, kl_samples=70, loss_fn=None):
+                 kl_weight=1.0, kl_samples=70, loss_fn=None, tv_fn=None):
         self.encoder, self.trainer, self.layer = encoder, trainer, signal_layer
         self.smoothness_weight, self.kl_weight, self.kl_samples = smoothness_weight, kl_weight, kl_samples
         self.bucket = FlatGradBucket(encoder.parameters())
@@ -110,6 +111,10 @@ class DataParallelTrainer:
         self.decay = adamw_decay > 0.0
         self.step_no = 0
         self.loss_fn = loss_fn or self._fused_loss
+        self.tv_fn = tv_fn or self._tv
+
+    def _tv(self, q, prior, mask, mask_sum):
+        return self.trainer.smoothness_loss(torch.cat([prior, mask], -1), q, mask_sum=mask_sum)
 
     def _fused_loss(self, q, sigma, data, mask, prior, mask_sum):
         return self.trainer.fused_elbo(self.layer, q, sigma, data, mask, prior, kl_samples=self.kl_samples,
@@ -121,7 +126,7 @@ class DataParallelTrainer:
         self.bucket.zero_()
         _, q, sigma = self.encoder(data)
         loss, info = self.loss_fn(q, sigma, data, mask, prior, msum)
-        tv = self.trainer.smoothness_loss(torch.cat([prior, mask], -1), q) * (float(mask.sum()) / msum)
+        tv = self.tv_fn(q, prior, mask, msum)
         total = loss + self.smoothness_weight * tv
         total.backward()
         self.bucket.all_reduce_()

@@ -124,6 +124,71 @@ class _NllFn(torch.autograd.Function):
         return d_pred * g[:, None], d_sigma * g[:, None], None, None, None
 
 
+class _TvFn(torch.autograd.Function):
+    """smoothness_loss (qbold_smoothness): value and gradient from one pass over the encoder output."""
+
+    @staticmethod
+    def forward(ctx, q, mask, mask_sum):
+        q = q.float().contiguous()
+        b, x, y, z, c = q.shape
+        grad = torch.empty_like(q)
+        tv = torch.zeros(1, dtype=torch.float64, device=q.device)
+        with torch.cuda.device(q.device):
+            check(_lib.lib().qbold_smoothness(dptr(q), c, dptr(mask), b, x, y, z, 1.0 / mask_sum,
+                                              dptr(tv, torch.float64), dptr(grad), stream_ptr(q.device)))
+        ctx.save_for_backward(grad)
+        return (tv[0] / mask_sum).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.saved_tensors[0] * g, None, None
+
+
+class _SynthNllFn(torch.autograd.Function):
+    """mean over rows of the pre-training NLL (qbold_synth_nll)."""
+
+    @staticmethod
+    def forward(ctx, pred, labels, use_mvg, ig_alpha, ig_beta):
+        n = pred.shape[0]
+        grad = torch.empty_like(pred)
+        total = torch.zeros(1, dtype=torch.float64, device=pred.device)
+        with torch.cuda.device(pred.device):
+            check(_lib.lib().qbold_synth_nll(dptr(labels), labels.shape[1], dptr(pred), int(use_mvg), float(ig_alpha),
+                                             float(ig_beta), n, 1.0 / n, None, dptr(grad),
+                                             dptr(total, torch.float64), stream_ptr(pred.device)))
+        ctx.save_for_backward(grad)
+        return (total[0] / n).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.saved_tensors[0] * g, None, None, None, None
+
+
+class _DiagKlFn(torch.autograd.Function):
+    """Per-voxel KL of the diagonal branch (qbold_diag_kl).  ``both`` [n,8]: q and a trainable population prior side
+    by side (model.py:687-689); otherwise pred [n,4] with a fixed prior [n,4]."""
+
+    @staticmethod
+    def forward(ctx, pred, prior, mask):
+        n, width = pred.shape
+        kl = torch.empty(n, dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred)
+        with torch.cuda.device(pred.device):
+            if prior is None:                                   # population prior inside `pred`
+                p, g = pred.data_ptr(), grad.data_ptr()
+                check(_lib.lib().qbold_diag_kl(p, 8, p + 16, 8, dptr(mask, allow_none=True), n, dptr(kl), g, 8, g + 16,
+                                               8, stream_ptr(pred.device)))
+            else:
+                check(_lib.lib().qbold_diag_kl(dptr(pred), 4, dptr(prior), 4, dptr(mask, allow_none=True), n, dptr(kl),
+                                               dptr(grad), 4, None, 0, stream_ptr(pred.device)))
+        ctx.save_for_backward(grad)
+        return kl
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.saved_tensors[0] * g[:, None], None, None
+
+
 class _FusedElboFn(torch.autograd.Function):
     """loss = nll + kl_weight * kl of one (local) batch; gradients come from the same launch."""
 
@@ -336,25 +401,44 @@ class EncoderTrainer:
         return kl.reshape(lead + (1,))
 
     def kl_loss(self, true, predicted, return_mean=True, no_samples=70, eps=None):
-        """KL(q || prior) by the reference's 70-sample MC estimator; ``no_samples=0`` selects the closed form."""
-        if self._use_population_prior:
-            raise NotImplementedError('population-prior / MoG KL variants (model.py:666-716) are not provided')
+        """KL(q || prior), model.py:654-724.  mvg: the reference's 70-sample MC estimator (``no_samples=0`` selects
+        the closed form); diagonal: the analytic LogitNormal KL, optionally against a trainable population prior
+        carried in channels 4..7 of ``predicted`` plus its InverseGamma(1, 2) hyper-prior (:710-715)."""
         true = torch.cat([true for _ in range(self._no_samples)], 0)
         if self._use_mvg:
             prior_dist, mask = true[..., :5], true[..., 5:6]
-        else:
-            # diagonal posterior: the reference uses the analytic LogitNormal KL (model.py:695-708) == the
-            # closed-form Gaussian KL in logit space with zero off-diagonals
-            prior_dist, mask = _as_mvg(true[..., :4], False), true[..., 4:5]
-            predicted, no_samples, eps = _as_mvg(predicted, False), 0, None
+            lead = tuple(predicted.shape[:-1])
+            m = mask.reshape(-1).float().contiguous()
+            kl = _KlFn.apply(predicted.reshape(-1, 5).float().contiguous(),
+                             prior_dist.reshape(-1, 5).float().contiguous(), m,
+                             None if eps is None else eps.reshape(-1, no_samples, 2).float().contiguous(),
+                             _next_seed(self), no_samples)
+            if return_mean:
+                return torch.sum(kl) / torch.sum(mask)
+            return kl.reshape(lead + (1,))
+        if self._use_population_prior and self._mog_components > 1:
+            raise NotImplementedError('mixture-of-Gaussians population prior (model.py:666-684) is not provided')
+        mask = true[..., 4:5]
         lead = tuple(predicted.shape[:-1])
         m = mask.reshape(-1).float().contiguous()
-        kl = _KlFn.apply(predicted.reshape(-1, 5).float().contiguous(),
-                         prior_dist.reshape(-1, 5).float().contiguous(), m,
-                         None if eps is None else eps.reshape(-1, no_samples, 2).float().contiguous(),
-                         _next_seed(self), no_samples)
+        prior_cost = 0.0
+        if self._use_population_prior:
+            pred8 = predicted.reshape(-1, 8).float().contiguous()
+            kl = _DiagKlFn.apply(pred8, None, m)
+            ls = self.transform_std(predicted[..., [5, 7]])                       # p_oef_log_std, p_dbv_log_std
+            a, b = 1.0, 2.0                                                       # InverseGamma(1, 2), model.py:711
+
+            def ig_log_prob(v):
+                return a * math.log(b) - math.lgamma(a) - (a + 1.0) * torch.log(v) - b / v
+
+            prior_cost = -ig_log_prob(torch.exp(torch.mean(ls[..., 1]) * 2.0))
+            prior_cost = prior_cost - ig_log_prob(torch.exp(torch.mean(ls[..., 0]) * 2.0))
+            prior_cost = prior_cost * float(predicted.shape[0])
+        else:
+            kl = _DiagKlFn.apply(predicted.reshape(-1, 4).float().contiguous(),
+                                 true[..., :4].reshape(-1, 4).float().contiguous(), m)
         if return_mean:
-            return torch.sum(kl) / torch.sum(mask)
+            return (torch.sum(kl) + prior_cost) / torch.sum(mask)
         return kl.reshape(lead + (1,))
 
     # ------------------------------------------------------------------ fused training objective
@@ -426,18 +510,33 @@ class EncoderTrainer:
             out['kl'] = self.kl_loss(torch.cat([prior, mask], -1), q_params, return_mean=False, no_samples=no_samples)
         return out
 
-    # ------------------------------------------------------------------ adjacent losses (torch ops)
-    def smoothness_loss(self, true_params, pred_params):
-        """Total-variation term (model.py:726-754): x/y neighbours of the forward-transformed means."""
+    # ------------------------------------------------------------------ losses either side of the path
+    def smoothness_loss(self, true_params, pred_params, mask_sum=None):
+        """Total-variation term (model.py:726-754): x/y neighbours of the forward-transformed means, one stencil
+        kernel for value + gradient.  ``mask_sum``: global sum(mask) when the batch is sharded over ranks."""
         true_params = torch.cat([true_params for _ in range(self._no_samples)], 0)
-        mask = true_params[..., 5:6] if self._use_mvg else true_params[..., 4:5]
-        means = torch.stack([pred_params[..., 0], pred_params[..., 2]], -1)
-        p = self.forward_transform(means) / torch.tensor([self._oef_range, self._dbv_range], device=means.device)
-        dx = p[:, :-1] - p[:, 1:]
-        dx = torch.where((mask[:, :-1] > 0.0) & (mask[:, 1:] > 0.0), dx, torch.zeros_like(dx))
-        dy = p[:, :, :-1] - p[:, :, 1:]
-        dy = torch.where((mask[:, :, :-1] > 0.0) & (mask[:, :, 1:] > 0.0), dy, torch.zeros_like(dy))
-        return (dx.abs().sum() + dy.abs().sum()) / mask.sum()
+        c = 5 if self._use_mvg else 4
+        mask = true_params[..., c].float().contiguous()
+        if pred_params.dim() != 5 or pred_params.shape[-1] != c:
+            raise ValueError('smoothness_loss: pred_params must be [B,X,Y,Z,%d]' % c)
+        if mask_sum is None:
+            mask_sum = float(mask.sum().item())
+        return _TvFn.apply(pred_params, mask, float(mask_sum))
+
+    def oef_dbv_metrics(self, y_true, y_pred, oef_dbv_r2p=0, eps=None):
+        """MSE of the 20-sample posterior means against the labels (model.py:345-364)."""
+        means = self.calculate_means(y_pred, None, include_r2p=True, eps=eps)
+        residual = means.reshape(-1, 3) - y_true.reshape(-1, 3)
+        return torch.mean(torch.square(residual[:, min(int(oef_dbv_r2p), 2)]))
+
+    def oef_metric(self, y_true, y_pred, eps=None):
+        return self.oef_dbv_metrics(y_true, y_pred, 0, eps)
+
+    def dbv_metric(self, y_true, y_pred, eps=None):
+        return self.oef_dbv_metrics(y_true, y_pred, 1, eps)
+
+    def r2p_metric(self, y_true, y_pred, eps=None):
+        return self.oef_dbv_metrics(y_true, y_pred, 2, eps)
 
     def logit_gaussian_mvg_log_prob(self, observations, predicted_params):
         """model.py:376-400 (returns the negative log prob, as the reference does)."""
@@ -455,13 +554,35 @@ class EncoderTrainer:
         loss = loss + torch.sum(torch.log(x) + torch.log(1.0 - x), -1)
         return loss.reshape(shape)
 
+    @staticmethod
+    def gaussian_nll(obs, mean, log_std):
+        return -(-log_std - 0.5 * ((obs - mean) / torch.exp(log_std)) ** 2)                      # model.py:402-404
+
     def synthetic_data_loss(self, y_true_orig, y_pred_orig, use_r2p_loss=False, inv_gamma_alpha=0.0,
-                            inv_gamma_beta=0.0):
-        """Pre-training NLL (model.py:449-514), mvg branch without the optional r2p / inverse-gamma terms."""
-        if use_r2p_loss or inv_gamma_alpha * inv_gamma_beta > 0.0 or self._infer_inv_gamma or not self._use_mvg:
-            raise NotImplementedError('only the optimal.yaml branch of synthetic_data_loss is provided')
-        y_true = y_true_orig.reshape(-1, 3)
-        return torch.mean(self.logit_gaussian_mvg_log_prob(y_true[:, :2], y_pred_orig.reshape(-1, 5)))
+                            inv_gamma_beta=0.0, eps=None):
+        """Pre-training loss (model.py:449-514): mean over label rows of the logit-normal NLL (mvg or diagonal) minus
+        the optional InverseGamma log-prior of the predicted variances, in one kernel with its gradient.  The
+        reference adds its per-row extra terms ([N]) to a [B,X,Y,Z] loss, which only broadcasts for [N,1,1,1]
+        inputs and then averages to mean(nll) + mean(extra); that is what is returned here for any shape.
+        ``use_r2p_loss``: Gaussian NLL of the R2' label under 10 reparameterised draws (:480-494; ``eps``
+        [N,10,2] pins the draws)."""
+        if self._infer_inv_gamma:
+            raise NotImplementedError('infer_inv_gamma (learned InverseGamma parameters, model.py:497-500) is not '
+                                      'provided')
+        c = 5 if self._use_mvg else 4
+        labels = y_true_orig.reshape(-1, 3).float().contiguous()
+        pred = y_pred_orig.reshape(-1, c).float().contiguous()
+        loss = _SynthNllFn.apply(pred, labels, self._use_mvg, float(inv_gamma_alpha), float(inv_gamma_beta))
+        if use_r2p_loss:
+            n_samples = 10
+            rpl = ReparamTrickLayer(self)
+            draws = [rpl((pred, None), eps=None if eps is None else eps.reshape(-1, n_samples, 2)[:, i])
+                     for i in range(n_samples)]
+            draws = torch.stack(draws, -1)                                                       # [N,2,10]
+            r2p = self.calculate_r2p(draws[:, 0, :], draws[:, 1, :])
+            r2p_log_std = torch.log(torch.std(r2p, -1, unbiased=False))
+            loss = loss + torch.mean(self.gaussian_nll(labels[:, 2], torch.mean(r2p, -1), r2p_log_std))
+        return loss
 
 
 class FineTuner(torch.nn.Module):

@@ -29,6 +29,12 @@ def _standin_loss(q, sigma, data, mask, prior, mask_sum):
     return loss, {'nll': loss.detach(), 'kl': loss.detach() * 0}
 
 
+def _standin_tv(q, prior, mask, mask_sum):
+    p = torch.sigmoid(torch.stack([q[..., 0], q[..., 2]], -1))
+    both = (mask[:, :-1] > 0) & (mask[:, 1:] > 0)
+    return ((p[:, :-1] - p[:, 1:]).abs() * both).sum() / mask_sum
+
+
 def _make(seed=3):
     import qbold_vi_b200 as qb
     from qbold_vi_b200.encoder import Encoder
@@ -38,7 +44,7 @@ def _make(seed=3):
     enc = Encoder(no_units=12, no_intermediate_layers=2)
     tr = qb.EncoderTrainer(cfg, student_t_df=200, multi_image_normalisation=False, use_mvg=True,
                            use_population_prior=False, predict_log_data=False, seed=1)
-    return enc, DataParallelTrainer(enc, tr, None, loss_fn=_standin_loss)
+    return enc, DataParallelTrainer(enc, tr, None, loss_fn=_standin_loss, tv_fn=_standin_tv)
 
 
 def _batch():

@@ -637,3 +637,109 @@ def test_standalone_fine_tune_loss_fn_kernel(qb, dev, cfg_noise_off, tag):
 def math_log_2pi():
     import math
     return math.log(2.0 * math.pi)
+
+
+# ---------------------------------------------------------------- losses either side of the path
+def _adj():
+    a = golden('ref_shim_adjacent.npz')
+    return a, tuple(int(v) for v in a['shape'])
+
+
+@pytest.mark.parametrize('tag,c', [('mvg', 5), ('diag', 4)])
+def test_smoothness_kernel_matches_reference_source(qb, dev, cfg_noise_off, tag, c):
+    a, shp = _adj()
+    tr = _trainer(qb, cfg_noise_off, use_mvg=(c == 5))
+    q = _t(a['q5'][:, :c].reshape(shp + (c,)), dev).requires_grad_(True)
+    true = torch.cat([_t(a['prior5'][:, :c].reshape(shp + (c,)), dev), _t(a['mask'].reshape(shp + (1,)), dev)], -1)
+    tv = tr.smoothness_loss(true, q)
+    assert rel_elem(tv.item(), a['tv_' + tag]) < GRAD_TOL
+    (3.0 * tv).backward()
+    assert rel_max(q.grad.cpu().numpy().reshape(-1, c) / 3.0, a['tv_%s_grad' % tag]) < GRAD_TOL
+    val, g = o.smoothness_loss(a['q5'][:, :c].reshape(shp + (c,)), a['mask'].reshape(shp))
+    assert rel_elem(tv.item(), val) < 1e-5
+
+
+def test_smoothness_kernel_large_volume_properties(qb, dev, cfg_noise_off):
+    """64^3 volumes: against the same formula in float64 torch ops, and translation invariance of the value."""
+    tr = _trainer(qb, cfg_noise_off)
+    g = torch.Generator(device='cpu').manual_seed(3)
+    q = (torch.randn((2, 64, 64, 64, 5), generator=g) * 0.8).to(dev).requires_grad_(True)
+    mask = (torch.rand((2, 64, 64, 64, 1), generator=g) > 0.2).float().to(dev)
+    true = torch.cat([torch.zeros_like(q.detach()), mask], -1)
+    tv = tr.smoothness_loss(true, q)
+    tv.backward()
+    q64 = q.detach().double().requires_grad_(True)
+    p = torch.sigmoid(torch.stack([q64[..., 0], q64[..., 2]], -1))
+    p = (p * torch.tensor([0.8, 0.2], device=dev, dtype=torch.float64) +
+         torch.tensor([0.04, 0.001], device=dev, dtype=torch.float64)) / torch.tensor([0.8, 0.2], device=dev,
+                                                                                        dtype=torch.float64)
+    m = mask.double()
+    ref = (((p[:, :-1] - p[:, 1:]).abs() * (m[:, :-1] * m[:, 1:])).sum() +
+           ((p[:, :, :-1] - p[:, :, 1:]).abs() * (m[:, :, :-1] * m[:, :, 1:])).sum()) / m.sum()
+    ref.backward()
+    assert rel_elem(tv.item(), ref.item()) < 1e-5
+    # sign flips of |d| for float32-vs-float64 near-ties are the only legitimate difference: allow a few voxels
+    diff = (q.grad.double() - q64.grad).abs().amax(-1) > 1e-4 * q64.grad.abs().max()
+    assert diff.float().mean().item() < 1e-4
+    assert float(q.grad[..., [1, 3, 4]].abs().max()) == 0.0
+    rolled = tr.smoothness_loss(torch.roll(true, 1, 3), torch.roll(q.detach(), 1, 3))     # z has no neighbours
+    assert rel_elem(rolled.item(), tv.item()) < 1e-6
+
+
+@pytest.mark.parametrize('tag,use_mvg,ig', [('mvg', True, (0.0, 0.0)), ('mvg_ig', True, (3.0, 0.15)),
+                                            ('diag', False, (0.0, 0.0)), ('diag_ig', False, (3.0, 0.15))])
+def test_synthetic_data_loss_kernel_matches_reference_source(qb, dev, cfg_noise_off, tag, use_mvg, ig):
+    a, shp = _adj()
+    c = 5 if use_mvg else 4
+    tr = _trainer(qb, cfg_noise_off, use_mvg=use_mvg)
+    pred = _t(a['q5'][:, :c].reshape(shp + (c,)), dev).requires_grad_(True)
+    labels = _t(a['synth_%s_labels' % tag].reshape(shp + (3,)), dev)
+    loss = tr.synthetic_data_loss(labels, pred, False, ig[0], ig[1])
+    assert rel_elem(loss.item(), a['synth_' + tag]) < GRAD_TOL
+    loss.backward()
+    assert rel_max(pred.grad.cpu().numpy().reshape(-1, c), a['synth_%s_grad' % tag]) < GRAD_TOL
+    rows, g = o.synthetic_data_nll(a['synth_%s_labels' % tag], a['q5'][:, :c], use_mvg, ig[0], ig[1], dt=np.float32)
+    assert rel_max(pred.grad.cpu().numpy().reshape(-1, c), g / rows.shape[0]) < 1e-5
+
+
+def test_synthetic_data_loss_r2p_term_matches_reference_source(qb, dev, cfg_noise_off):
+    a, shp = _adj()
+    tr = _trainer(qb, cfg_noise_off)
+    pred = _t(a['q5'].reshape(shp + (5,)), dev).requires_grad_(True)
+    loss = tr.synthetic_data_loss(_t(a['labels'].reshape(shp + (3,)), dev), pred, True, 0.0, 0.0,
+                                  eps=_t(a['synth_r2p_eps'], dev))
+    assert rel_elem(loss.item(), a['synth_r2p']) < GRAD_TOL
+    loss.backward()
+    assert rel_max(pred.grad.cpu().numpy().reshape(-1, 5), a['synth_r2p_grad']) < GRAD_TOL
+
+
+@pytest.mark.parametrize('i,name', [(0, 'oef'), (1, 'dbv'), (2, 'r2p')])
+def test_pretraining_metrics_match_reference_source(qb, dev, cfg_noise_off, i, name):
+    a, shp = _adj()
+    tr = _trainer(qb, cfg_noise_off)
+    val = getattr(tr, name + '_metric')(_t(a['labels'].reshape(shp + (3,)), dev), _t(a['q5'].reshape(shp + (5,)), dev),
+                                        eps=_t(a['metric_%s_eps' % name], dev))
+    assert rel_elem(val.item(), a['metric_' + name]) < GRAD_TOL
+
+
+def test_diagonal_kl_variants_match_reference_source(qb, dev, cfg_noise_off):
+    a, shp = _adj()
+    mask = _t(a['mask'].reshape(shp + (1,)), dev)
+    true = torch.cat([_t(a['prior5'][:, :4].reshape(shp + (4,)), dev), mask], -1)
+    tr = _trainer(qb, cfg_noise_off, use_mvg=False)
+    q = _t(a['q5'][:, :4].reshape(shp + (4,)), dev).requires_grad_(True)
+    kl = tr.kl_loss(true, q)
+    assert rel_elem(kl.item(), a['kl_diag']) < GRAD_TOL
+    kl.backward()
+    assert rel_max(q.grad.cpu().numpy().reshape(-1, 4), a['kl_diag_grad']) < GRAD_TOL
+    kmap = tr.kl_loss(true, q.detach(), return_mean=False)
+    ref, _, _ = o.diag_kl(a['prior5'][:, :4], a['q5'][:, :4])
+    assert tuple(kmap.shape) == shp + (1,)
+    assert rel_max(kmap.cpu().numpy().reshape(-1), ref * (a['mask'] > 0)) < 1e-5
+    # population prior: q and the trainable prior side by side, InverseGamma(1,2) hyper-prior on its mean log-std
+    trp = _trainer(qb, cfg_noise_off, use_mvg=False, use_population_prior=True)
+    q8 = _t(a['kl_pop_pred'].reshape(shp + (8,)), dev).requires_grad_(True)
+    klp = trp.kl_loss(true, q8)
+    assert rel_elem(klp.item(), a['kl_pop']) < GRAD_TOL
+    klp.backward()
+    assert rel_max(q8.grad.cpu().numpy().reshape(-1, 8), a['kl_pop_grad']) < GRAD_TOL

@@ -153,3 +153,34 @@ def test_masked_voxels_contribute_nothing(physics):
     assert dead.any()
     assert np.all(r['grad_q'][dead] == 0) and np.all(r['grad_sigma'][dead] == 0)
     assert np.all(r['nll_map'][dead] == 0) and np.all(r['kl_map'][dead] == 0)
+
+
+# ---------------------------------------------------------------- losses either side of the path
+def test_smoothness_oracle_vs_reference_source():
+    a = golden('ref_shim_adjacent.npz')
+    shp = tuple(int(v) for v in a['shape'])
+    for tag, c in (('mvg', 5), ('diag', 4)):
+        val, g = o.smoothness_loss(a['q5'][:, :c].reshape(shp + (c,)), a['mask'].reshape(shp))
+        assert rel_elem(val, a['tv_' + tag]) < 1e-5
+        assert rel_max(g.reshape(-1, c), a['tv_%s_grad' % tag]) < 1e-4
+
+
+@pytest.mark.parametrize('tag,use_mvg,ig', [('mvg', True, (0.0, 0.0)), ('mvg_ig', True, (3.0, 0.15)),
+                                            ('diag', False, (0.0, 0.0)), ('diag_ig', False, (3.0, 0.15))])
+def test_synthetic_data_loss_oracle_vs_reference_source(tag, use_mvg, ig):
+    a = golden('ref_shim_adjacent.npz')
+    c = 5 if use_mvg else 4
+    # float32 like the reference: row 0 sits on the clip, where 1 - 1e-6 is not representable (1 - x = 1.013e-6)
+    rows, g = o.synthetic_data_nll(a['synth_%s_labels' % tag], a['q5'][:, :c], use_mvg, ig[0], ig[1], dt=np.float32)
+    assert rel_elem(rows.astype(np.float64).mean(), a['synth_' + tag]) < 1e-5
+    assert rel_max(g / rows.shape[0], a['synth_%s_grad' % tag]) < 1e-5
+    rows64, g64 = o.synthetic_data_nll(a['synth_%s_labels' % tag], a['q5'][:, :c], use_mvg, ig[0], ig[1])
+    assert rel_max(g64[1:], g[1:]) < 1e-4 and rel_max(rows64[1:], rows[1:]) < 1e-5
+
+
+def test_diag_kl_oracle_vs_reference_source():
+    a = golden('ref_shim_adjacent.npz')
+    kl, gq, _ = o.diag_kl(a['prior5'][:, :4], a['q5'][:, :4])
+    m = a['mask']
+    assert rel_elem((kl * (m > 0)).sum() / m.sum(), a['kl_diag']) < 1e-5
+    assert rel_max(gq * (m > 0)[:, None] / m.sum(), a['kl_diag_grad']) < 1e-4
