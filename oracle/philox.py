@@ -59,10 +59,26 @@ def reparam_eps(seed, index):
     return np.stack([n0, n1], -1)
 
 
+def mc_box_muller(r0, r1):
+    """Box-Muller as the kernels' Monte-Carlo draws evaluate it (rng.cuh mc_box_muller): radius from log2, angle
+    shifted by pi.  The kernel uses the SFU approximations, this is the exact value of the same expressions
+    (difference <~ 2e-6 absolute per draw; up to 6e-4 for radii < 0.04)."""
+    u1, u2 = u01(r0).astype(np.float64), u01(r1).astype(np.float64)
+    rad = np.sqrt(np.maximum(np.log2(u1) * -1.3862943611198906, 0.0))
+    x = (u2.astype(np.float32) * np.float32(6.283185307179586) + np.float32(-3.141592653589793)).astype(np.float64)
+    return (rad * -np.cos(x)).astype(np.float32), (rad * -np.sin(x)).astype(np.float32)
+
+
 def kl_eps(seed, index, n_samples):
+    """Monte-Carlo sample s of a voxel: Philox call (index, STREAM_KL + (s >> 1)), words (x, y) for even s and
+    (z, w) for odd s."""
     out = np.empty((len(index), n_samples, 2), dtype=np.float32)
-    for s in range(n_samples):
-        out[:, s, 0], out[:, s, 1] = normal_pair(seed, index, STREAM_KL + s)
+    lo, hi, k0, k1 = _words(index, seed)
+    for c in range((n_samples + 1) // 2):
+        r = philox4x32_10(lo, hi, np.uint32(STREAM_KL + c), np.uint32(0), k0, k1)
+        out[:, 2 * c, 0], out[:, 2 * c, 1] = mc_box_muller(r[0], r[1])
+        if 2 * c + 1 < n_samples:
+            out[:, 2 * c + 1, 0], out[:, 2 * c + 1, 1] = mc_box_muller(r[2], r[3])
     return out
 
 

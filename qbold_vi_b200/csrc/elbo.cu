@@ -162,34 +162,48 @@ __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const
     KlOut o;
     if (n_samples > 0) {
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int sidx = lane & (W - 1); sidx < n_samples; sidx += W) {
-            float k0, k1;
-            if (eps_v) {
-                const float2 e = __ldg(reinterpret_cast<const float2*>(eps_v) + sidx);
-                k0 = e.x;
-                k1 = e.y;
-            } else {
-                normal_pair(seed, index, kStreamKl + (uint32_t)sidx, k0, k1);
+        const int t = lane & (W - 1);
+        // Rounds of 2W samples: lane t takes the two samples of ONE Philox call (2t, 2t+1); a tail of <= W samples
+        // is spread one per lane instead (70 samples: W=16 -> 3 calls + 5 evaluations, W=32 -> 2 + 3).
+        for (int base = 0; base < n_samples; base += 2 * W) {
+            const int rem = n_samples - base;
+            const bool pairwise = rem > W;
+            const int s0 = base + (pairwise ? 2 * t : t);
+            const int cnt = pairwise ? min(2, n_samples - s0) : (t < rem ? 1 : 0);
+            U4 r = {0u, 0u, 0u, 0u};
+            if (eps_v == nullptr && cnt > 0) r = mc_words(seed, index, s0);
+#pragma unroll 1
+            for (int h = 0; h < cnt; ++h) {
+                const int sidx = s0 + h;
+                float k0, k1;
+                if (eps_v) {
+                    const float2 e = __ldg(reinterpret_cast<const float2*>(eps_v) + sidx);
+                    k0 = e.x;
+                    k1 = e.y;
+                } else {
+                    mc_normal_pair(r, sidx, k0, k1);
+                }
+                // Sample in logit space, then the reference's round trip sigmoid -> OEF/DBV -> backwards_transform ->
+                // clip -> logit (model.py:393-396, 307-316, 10-12).  For |z| < kRoundTripZ the round trip is the
+                // identity up to float32 noise (< 5e-4 absolute on zh, zero-mean; far inside the 1e-4 ELBO bar after
+                // averaging) and d zh/d z = 1, so it is skipped; beyond it (saturating sigmoid, clip at 1e-6) the
+                // reference's float32 arithmetic is followed literally.
+                const float z_o = dq.mu_o + k0 * ex.sd_o;                            // model.py:26-27
+                const float z_d = (dq.mu_d + k0 * dq.cov) + k1 * ex.sd_d;            // model.py:29-31
+                float zh_o = z_o, zh_d = z_d, dz_o = 1.0f, dz_d = 1.0f;
+                if (fmaxf(fabsf(z_o), fabsf(z_d)) >= kRoundTripZ)
+                    roundtrip_literal(z_o, z_d, zh_o, zh_d, dz_o, dz_d);
+                float gq_o, gq_d, gp_o, gp_d;
+                const float nq = mvn_nll(dq, zh_o, zh_d, gq_o, gq_d);
+                const float np = mvn_nll(dp, zh_o, zh_d, gp_o, gp_d);
+                a[5] += np - nq;                                                     // log q - log p (model.py:603)
+                const float hz_o = (gp_o - gq_o) * dz_o, hz_d = (gp_d - gq_d) * dz_d;
+                a[0] += hz_o;
+                a[1] += hz_o * k0;
+                a[2] += hz_d;
+                a[3] += hz_d * k1;
+                a[4] += hz_d * k0;
             }
-            // Sample in logit space, then the reference's round trip sigmoid -> OEF/DBV -> backwards_transform ->
-            // clip -> logit (model.py:393-396, 307-316, 10-12).  For |z| < kRoundTripZ the round trip is the
-            // identity up to float32 noise (< 5e-4 absolute on zh, zero-mean; far inside the 1e-4 ELBO bar after
-            // averaging) and d zh/d z = 1, so it is skipped; beyond it (saturating sigmoid, clip at 1e-6) the
-            // reference's float32 arithmetic is followed literally.
-            const float z_o = dq.mu_o + k0 * ex.sd_o;                            // model.py:26-27
-            const float z_d = (dq.mu_d + k0 * dq.cov) + k1 * ex.sd_d;            // model.py:29-31
-            float zh_o = z_o, zh_d = z_d, dz_o = 1.0f, dz_d = 1.0f;
-            if (fmaxf(fabsf(z_o), fabsf(z_d)) >= kRoundTripZ) roundtrip_literal(z_o, z_d, zh_o, zh_d, dz_o, dz_d);
-            float gq_o, gq_d, gp_o, gp_d;
-            const float nq = mvn_nll(dq, zh_o, zh_d, gq_o, gq_d);
-            const float np = mvn_nll(dp, zh_o, zh_d, gp_o, gp_d);
-            a[5] += np - nq;                                                     // log q - log p (model.py:603)
-            const float hz_o = (gp_o - gq_o) * dz_o, hz_d = (gp_d - gq_d) * dz_d;
-            a[0] += hz_o;
-            a[1] += hz_o * k0;
-            a[2] += hz_d;
-            a[3] += hz_d * k1;
-            a[4] += hz_d * k0;
         }
         const float inv_s = 1.0f / (float)n_samples;
         if (W == 32) {
@@ -650,7 +664,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_nll_map(const __grid_constant__
                 e0 = e.x;
                 e1 = e.y;
             } else {
-                normal_pair(seed, offset + (uint64_t)v, kStreamKl + (uint32_t)sidx, e0, e1);
+                mc_normal_pair(seed, offset + (uint64_t)v, sidx, e0, e1);
             }
             const Sample sm = draw(dq, ex, e0, e1);
             const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
@@ -723,7 +737,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_nll_map_pair(const __grid_const
                 e0 = e.x;
                 e1 = e.y;
             } else {
-                normal_pair(seed, offset + (uint64_t)v, kStreamKl + (uint32_t)sidx, e0, e1);
+                mc_normal_pair(seed, offset + (uint64_t)v, sidx, e0, e1);
             }
             const Sample sm = draw(dq, ex, e0, e1);
             const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
@@ -878,7 +892,7 @@ __global__ void __launch_bounds__(kThreads) k_posterior_stats(const __grid_const
                     k0 = e.x;
                     k1 = e.y;
                 } else {
-                    normal_pair(seed, offset + (uint64_t)v, kStreamKl + (uint32_t)sidx, k0, k1);
+                    mc_normal_pair(seed, offset + (uint64_t)v, sidx, k0, k1);
                 }
                 const Sample ks = draw(dq, ex, k0, k1);
                 so[i] = ks.oef;

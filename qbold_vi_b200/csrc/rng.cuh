@@ -13,7 +13,7 @@ namespace qb {
 
 // stream ids
 constexpr uint32_t kStreamReparam = 0;        // ReparamTrickLayer draw of the likelihood term
-constexpr uint32_t kStreamKl = 0x100;         // + sample index (KL / posterior samples)
+constexpr uint32_t kStreamKl = 0x100;         // + (sample index >> 1): Monte-Carlo samples, see mc_normal_pair
 constexpr uint32_t kStreamSnr = 0x10000;      // noise model: per-voxel SNR
 constexpr uint32_t kStreamNoise = 0x10001;    // + pair index: noise normals
 
@@ -57,6 +57,55 @@ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t index, uint3
     const U4 r = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, 0u, (uint32_t)seed,
                                (uint32_t)(seed >> 32));
     box_muller(r.x, r.y, n0, n1);
+}
+
+// ---- Monte-Carlo sample draws (KL estimator, posterior statistics, likelihood map) ----------------------------
+// Sample s of a voxel comes from Philox call (index, kStreamKl + (s >> 1)): words (x, y) for even s, (z, w) for odd
+// s, so one call serves two samples.  These draws only feed sample averages, so Box-Muller runs on the SFU
+// approximations (lg2 / sqrt / sin / cos .approx): absolute error of a draw <~ 2e-6 (up to 6e-4 for the 0.08 % of
+// draws with radius < 0.04, where the 2^-22 absolute error of lg2.approx near 1 dominates) -- far below the
+// estimators' sampling noise; four MUFU + ~8 FP32 instructions instead of ~75.  The likelihood's own reparameterisation draw and the dataset noise keep the
+// accurate logf / sincospif path above.
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sin_approx(float x) {
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float cos_approx(float x) {
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void mc_box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {
+    const float rad = sqrt_approx(fmaxf(lg2_approx(u01(r0)) * -1.3862943611198906f, 0.f));   // sqrt(-2 ln u)
+    const float x = fmaf(u01(r1), 6.283185307179586f, -3.141592653589793f);                   // angle - pi
+    n0 = rad * -cos_approx(x);                                                                // cos(x + pi) = -cos x
+    n1 = rad * -sin_approx(x);
+}
+
+__device__ __forceinline__ U4 mc_words(uint64_t seed, uint64_t index, int s) {
+    return philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), kStreamKl + (uint32_t)(s >> 1), 0u, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ void mc_normal_pair(const U4& r, int s, float& n0, float& n1) {
+    const bool odd = (s & 1) != 0;
+    mc_box_muller(odd ? r.z : r.x, odd ? r.w : r.y, n0, n1);
+}
+
+__device__ __forceinline__ void mc_normal_pair(uint64_t seed, uint64_t index, int s, float& n0, float& n1) {
+    mc_normal_pair(mc_words(seed, index, s), s, n0, n1);
 }
 #endif
 
