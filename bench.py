@@ -121,6 +121,45 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def fused_elbo_leg(qb, layer, cfg, x, sig, dev, f_alg_forward, fma_tf, voxels=1 << 22, reps=5):
+    """Secondary line (outside the timed region of the headline): the fused forward + likelihood + KL + backward
+    kernel (qbold_elbo_fused) on the first `voxels` voxels of the same inputs, CUDA-event timed, with its own
+    FP32 fraction by the SURVEY.md 8(d) FLOP convention (K1b's count + ~80 FLOP per KL sample)."""
+    import torch
+    n = min(voxels, x.shape[0])
+    tr = qb.EncoderTrainer(cfg, student_t_df=200, multi_image_normalisation=False, use_mvg=True,
+                           use_population_prior=False, predict_log_data=False, seed=1)
+    g = torch.Generator(device=dev).manual_seed(99)
+    logit = lambda p: torch.log(p / (1.0 - p))                                   # noqa: E731
+    q = torch.stack([logit((x[:n, 0] - 0.04) / 0.8).clamp(-6, 6), torch.randn(n, device=dev, generator=g) * 0.3,
+                     logit((x[:n, 1] - 0.001) / 0.2).clamp(-6, 6), torch.randn(n, device=dev, generator=g) * 0.3,
+                     torch.randn(n, device=dev, generator=g) * 0.5], -1).contiguous()
+    prior = (q + 0.3 * torch.randn((n, 5), device=dev, generator=g)).contiguous()
+    sigma = torch.exp(torch.randn((n, N_TAU), device=dev, generator=g) * 0.2 - 3.0)
+    data = (sig[:n] * 100.0).contiguous()
+    mask = torch.ones(n, device=dev)
+    out = {'kernel': 'k_elbo_pair<HAS_PRIOR=true>', 'voxels': n, 'unit': UNIT, 'peak': fma_tf,
+           'inputs': 'q centred on the headline OEF/DBV draws, raw std ~ N(0,0.3), prior = q + N(0,0.3), sigma ~ '
+                     'exp(N(-3,0.2)), all voxels inside the mask; %.0f MB in+out per launch (> L2)' % (n * 196 / 1e6)}
+    for tag, ks, extra in (('mc70', 70, 70 * 80.0), ('closed_form_kl', 0, 200.0)):
+        def run():
+            return tr.fused_elbo(layer, q, sigma, data, mask, prior, kl_samples=ks, mask_sum=float(n))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tf = n * (f_alg_forward + extra) / (ms * 1e-3) / 1e12
+        out[tag] = {'ms': ms, 'value': n * N_TAU / (ms * 1e-3), 'alg_flops_per_voxel': f_alg_forward + extra,
+                    'achieved': tf, 'frac': tf / fma_tf}
+    return out
+
+
 def workload_config(voxels, gpus):
     return {'workload': 'BASELINE config 2: batched forward model + analytic (TF-autodiff-consistent) gradients '
                         'w.r.t. OEF/DBV, %d voxels x 11-tau optimal.yaml grid per GPU, full model + blood' % voxels,
@@ -268,6 +307,8 @@ def main():
                                                              'frac': hbm_gbs / hbm_peak,
                                                              'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}},
         }
+        if world == 1:
+            line['fused_elbo'] = fused_elbo_leg(qb, layer, cfg, x, sig, dev, f_alg, fma_tf)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cpu_port_run(8192, threads)

@@ -5,7 +5,7 @@ likelihood slice of ``model.py``: same entry points, same ``config`` INI / ``opt
 parameters, arithmetic in hand-written CUDA kernels behind a C ABI (``include/qbold.h``).
 There is no CPU fallback: every compute call requires ``libqbold.so`` and CUDA tensors.
 """
-from . import _lib
+from . import _lib, nifti
 from ._lib import QboldError, build_library, fma_peak_tflops, launch_count
 from .config import (apply_yaml_overrides, get_defaults, load_arguments, load_system_parameters,
                      optimal_arguments)

@@ -510,6 +510,49 @@ class EncoderTrainer:
             out['kl'] = self.kl_loss(torch.cat([prior, mask], -1), q_params, return_mean=False, no_samples=no_samples)
         return out
 
+    def save_predictions(self, model, data, filename, transform_directory=None, use_first_op=True,
+                         fine_tuner_model=None, priors=None, affine=None):
+        """model.py:772-887: posterior maps of whole volumes as NIfTI images -- ``filename``_oef / _dbv / _r2p (means of
+        200 draws) and _logstds (their variances, as the reference), plus, when ``fine_tuner_model`` is given,
+        _likelihood (mean NLL map of 100 stochastic forward passes), _kl (100-sample KL map against ``priors``) and
+        _residual (mean absolute normalised residual of one pass).  ``data`` [S,X,Y,Z,n_tau+1], last channel = mask.
+        The FSL warp to MNI space (``transform_directory``) shells out to external binaries and is not provided."""
+        from .nifti import save_im_data
+        if transform_directory is not None:
+            raise NotImplementedError('save_predictions: the FSL applywarp / fslmerge step (model.py:846-877) needs '
+                                      'external binaries and is not provided')
+        dev = next(model.parameters()).device
+        data = torch.as_tensor(np.asarray(data, dtype=np.float32) if not torch.is_tensor(data) else data).float().to(dev)
+        images, mask = data[..., :-1].contiguous(), data[..., -1:].contiguous()
+        with torch.no_grad():
+            p1, p2, im_sigma = model(images * mask)
+            predictions = p1 if use_first_op else p2
+            ones = torch.ones_like(predictions[..., :1])
+            means, variances = self.calculate_means(predictions, ones, include_r2p=True, return_stds=True,
+                                                    no_samples=200)
+            if fine_tuner_model is not None:
+                layer = fine_tuner_model.layer
+                _, q, sigma = fine_tuner_model.encoder(images)                  # model.py:810: unmasked images
+                lik = self.likelihood_map(layer, q, sigma, images, mask, no_samples=100)
+                save_im_data(lik.cpu().numpy(), filename + '_likelihood', affine)
+                if priors is not None:
+                    pri = torch.as_tensor(np.asarray(priors, dtype=np.float32) if not torch.is_tensor(priors)
+                                          else priors).float().to(dev)
+                    kl = self.kl_loss(torch.cat([pri, mask], -1), q, return_mean=False, no_samples=100)
+                    save_im_data(kl.cpu().numpy(), filename + '_kl', affine)
+                y_pred = fine_tuner_model(images, mask)['predicted_images'][..., :images.shape[-1]]
+                se = self._se_idx
+                sl = slice(se - 1, se + 2) if self._multi_image_normalisation else slice(se, se + 1)
+                y_true = images / (images[..., sl].mean(-1, keepdim=True) + 1e-3)
+                y_pred = y_pred / (y_pred[..., sl].mean(-1, keepdim=True) + 1e-3)
+                residual = (y_true - y_pred).abs().mean(-1, keepdim=True)
+                save_im_data(residual.cpu().numpy(), filename + '_residual', affine)
+        means, variances = means.cpu().numpy(), variances.cpu().numpy()
+        for i, name in enumerate(('_oef', '_dbv', '_r2p')):
+            save_im_data(means[..., i:i + 1], filename + name, affine)
+        save_im_data(variances, filename + '_logstds', affine)
+        return {'means': means, 'variances': variances}
+
     # ------------------------------------------------------------------ losses either side of the path
     def smoothness_loss(self, true_params, pred_params, mask_sum=None):
         """Total-variation term (model.py:726-754): x/y neighbours of the forward-transformed means, one stencil

@@ -743,3 +743,36 @@ def test_diagonal_kl_variants_match_reference_source(qb, dev, cfg_noise_off):
     assert rel_elem(klp.item(), a['kl_pop']) < GRAD_TOL
     klp.backward()
     assert rel_max(q8.grad.cpu().numpy().reshape(-1, 8), a['kl_pop_grad']) < GRAD_TOL
+
+
+def test_save_predictions_writes_posterior_maps(qb, dev, cfg_noise_off, tmp_path):
+    """save_predictions (model.py:772-887): NIfTI maps of means / variances / likelihood / KL / residual."""
+    from qbold_vi_b200.encoder import Encoder
+    from qbold_vi_b200.nifti import load_nifti
+    torch.manual_seed(0)
+    tr = _trainer(qb, cfg_noise_off)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    enc = Encoder(no_units=8, no_intermediate_layers=1).to(dev)
+    ft = tr.build_fine_tuner(enc, layer)
+    g = torch.Generator().manual_seed(4)
+    truth = torch.stack([torch.rand((2, 6, 5, 3), generator=g) * 0.5 + 0.15,
+                         torch.rand((2, 6, 5, 3), generator=g) * 0.1 + 0.01], -1).to(dev)
+    images = layer(truth) * 100.0
+    mask = (torch.rand((2, 6, 5, 3, 1), generator=g) > 0.2).float().to(dev)
+    data = torch.cat([images, mask], -1).cpu().numpy()
+    with torch.no_grad():
+        priors = enc(images * mask)[0]
+    base = str(tmp_path / 'subj')
+    out = tr.save_predictions(enc, data, base, use_first_op=False, fine_tuner_model=ft, priors=priors)
+    for name, last in (('_oef', 2), ('_dbv', 2), ('_r2p', 2), ('_logstds', 6), ('_likelihood', 2), ('_kl', 2),
+                       ('_residual', 2)):
+        arr, _ = load_nifti(base + name + '.nii.gz')
+        assert arr.shape == (6, 5, 3, last), name
+        assert np.isfinite(arr).all(), name
+    oef, _ = load_nifti(base + '_oef.nii.gz')
+    assert np.array_equal(oef[..., 1], out['means'][1, ..., 0])
+    assert 0.04 <= oef.min() and oef.max() <= 0.84
+    lik, _ = load_nifti(base + '_likelihood.nii.gz')
+    assert np.all(lik[..., 0][mask[0, ..., 0].cpu().numpy() == 0] == 0.0)         # masked voxels carry no likelihood
+    with pytest.raises(NotImplementedError):
+        tr.save_predictions(enc, data, base, transform_directory='/nonexistent')

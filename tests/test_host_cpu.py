@@ -193,3 +193,26 @@ def test_dataset_plumbing_shapes(qb):
     assert tuple(tgt['predictions'].shape) == (38, 25, 25, 8, 6) and tuple(tgt['predicted_images'].shape) == (38, 25, 25, 8, 12)
     assert torch.equal(data, tgt['predicted_images'][..., :-1]) and bool((data[mask.expand_as(data) == 0] == 0).all())
     assert torch.equal(tgt['predictions'][..., -1:], mask)
+
+
+def test_nifti_round_trip_and_subject_concatenation(tmp_path):
+    """save_im_data (model.py:792-802): subjects concatenated along the last axis, NIfTI-1 single file, gzip."""
+    import gzip
+    import struct
+    from qbold_vi_b200 import nifti
+    rng = np.random.default_rng(0)
+    maps = rng.standard_normal((3, 5, 4, 2, 1)).astype(np.float32)
+    nifti.save_im_data(maps, str(tmp_path / 'oef'))
+    arr, aff = nifti.load_nifti(str(tmp_path / 'oef.nii.gz'))
+    assert arr.shape == (5, 4, 2, 3) and arr.dtype == np.float32
+    for s in range(3):
+        assert np.array_equal(arr[..., s], maps[s, ..., 0])
+    assert np.array_equal(aff, np.eye(4, dtype=np.float32))
+    raw = gzip.open(tmp_path / 'oef.nii.gz').read()
+    assert len(raw) == 352 + 4 * arr.size and raw[344:348] == b'n+1\x00'
+    assert struct.unpack_from('<8h', raw, 40)[:5] == (4, 5, 4, 2, 3) and struct.unpack_from('<h', raw, 70)[0] == 16
+    assert np.frombuffer(raw, np.float32, 2, 352).tolist() == [arr[0, 0, 0, 0], arr[1, 0, 0, 0]]   # x fastest
+    vol = rng.integers(0, 255, (4, 3, 2)).astype(np.uint8)
+    nifti.save_nifti(vol, str(tmp_path / 'm.nii'), affine=np.diag([2.0, 2.0, 3.0, 1.0]))
+    back, aff = nifti.load_nifti(str(tmp_path / 'm.nii'))
+    assert np.array_equal(back, vol) and aff[2, 2] == 3.0
