@@ -776,3 +776,71 @@ def test_save_predictions_writes_posterior_maps(qb, dev, cfg_noise_off, tmp_path
     assert np.all(lik[..., 0][mask[0, ..., 0].cpu().numpy() == 0] == 0.0)         # masked voxels carry no likelihood
     with pytest.raises(NotImplementedError):
         tr.save_predictions(enc, data, base, transform_directory='/nonexistent')
+
+
+# ---------------------------------------------------------------------------------- robustness of the C ABI
+def test_c_abi_argument_errors_and_messages(qb, dev, cfg_noise_off):
+    """Every entry point rejects bad arguments with QBOLD_EINVAL (-1) and a message, and never launches."""
+    import ctypes as C
+    lib = qb._lib.lib()
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    P = C.byref(layer.params)
+    x = torch.rand((8, 2), device=dev)
+    out = torch.empty((8, 11), device=dev)
+    before = qb.launch_count()
+    assert lib.qbold_forward(P, None, 2, 8, out.data_ptr(), None) == -1
+    assert b'qbold_forward' in lib.qbold_last_error()
+    assert lib.qbold_forward(P, x.data_ptr(), 5, 8, out.data_ptr(), None) == -1            # 2 or 3 channels only
+    assert lib.qbold_forward(P, x.data_ptr(), 2, -1, out.data_ptr(), None) == -1
+    assert lib.qbold_forward(None, x.data_ptr(), 2, 8, out.data_ptr(), None) == -1
+    assert lib.qbold_forward_backward(P, x.data_ptr(), None, 8, None, None, None) == -1
+    assert lib.qbold_kl(None, None, None, None, 0, 0, 70, 8, None, None, None) == -1
+    assert lib.qbold_smoothness(x.data_ptr(), 3, x.data_ptr(), 1, 2, 2, 2, 1.0, None, out.data_ptr(), None) == -1
+    assert lib.qbold_synth_nll(x.data_ptr(), 1, x.data_ptr(), 1, 0.0, 0.0, 8, 1.0, out.data_ptr(), None, None, None) == -1
+    assert lib.qbold_diag_kl(x.data_ptr(), 2, x.data_ptr(), 4, None, 8, out.data_ptr(), None, 0, None, 0, None) == -1
+    bad = qb._lib.QboldParams()
+    C.memmove(C.byref(bad), P, C.sizeof(bad))
+    bad.abi_version = 999
+    assert lib.qbold_forward(C.byref(bad), x.data_ptr(), 2, 8, out.data_ptr(), None) == -1
+    assert qb.launch_count() == before
+    assert lib.qbold_forward(P, x.data_ptr(), 2, 0, out.data_ptr(), None) == 0              # empty is fine
+    with pytest.raises(qb.QboldError):
+        layer(torch.rand(4, 2))                                                             # CPU tensor: no CPU path
+
+
+def test_non_default_stream_and_nan_propagation(qb, dev, cfg_noise_off, physics):
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    x = _rand_voxels(4097, 5)
+    ref = layer(_t(x, dev))
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        xt = _t(x, dev)
+        got = layer(xt)
+        sig, grad = layer.forward_backward(xt, torch.ones((4097, 11), device=dev))
+    s.synchronize()
+    assert torch.equal(got, ref) and torch.equal(sig, ref)
+    # NaN / Inf inputs propagate to that voxel only (the reference relies on TerminateOnNaN, SURVEY 8b)
+    xb = x.copy()
+    xb[10] = [np.nan, 0.05]
+    xb[20] = [0.4, np.inf]
+    out = layer(_t(xb, dev)).cpu().numpy()
+    assert np.isnan(out[10]).all() and not np.isfinite(out[20]).all()
+    keep = np.ones(4097, bool)
+    keep[[10, 20]] = False
+    assert np.array_equal(out[keep], ref.cpu().numpy()[keep])
+
+
+def test_more_than_2_31_output_elements(qb, dev, cfg_noise_off):
+    """64-bit indexing: 200 M voxels x 11 taus = 2.2e9 output elements (8.8 GB) in one launch."""
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    n = 200_000_000
+    base = _t(_rand_voxels(1 << 20, 8), dev)
+    x = base.repeat((n + (1 << 20) - 1) // (1 << 20), 1)[:n].contiguous()
+    out = layer(x)
+    assert tuple(out.shape) == (n, 11)
+    ref = layer(base)
+    tail = n - (n // (1 << 20)) * (1 << 20)
+    assert torch.equal(out[-tail:], ref[:tail])                                             # beyond element 2^31
+    assert torch.equal(out[(1 << 20) * 100:(1 << 20) * 101], ref)
+    del out, x
+    torch.cuda.empty_cache()
