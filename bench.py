@@ -160,6 +160,42 @@ def fused_elbo_leg(qb, layer, cfg, x, sig, dev, f_alg_forward, fma_tf, voxels=1 
     return out
 
 
+def streaming_leg(qb, cfg, x, dev, hbm_peak, reps=5):
+    """Secondary line: the streaming synthetic-data path (qbold_generate: shuffled OEF x DBV meshgrid -> signals +
+    labels, nothing read but the two marginals) and the HBM-bound log-linear forward (full_model=False), each with
+    its achieved HBM GB/s (algorithmic bytes: 44 B signal + 12 B labels written; 8 B read + 44 B written)."""
+    import torch
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n = x.shape[0]
+    full = qb.SignalGenerationLayer(cfg, True, True)
+    loglin = qb.SignalGenerationLayer(cfg, False, True)
+    g = torch.Generator(device=dev).manual_seed(7)
+    oefs = torch.rand(4096, device=dev, generator=g) * 0.75 + 0.05
+    dbvs = torch.rand(n // 4096, device=dev, generator=g) * 0.192 + 0.003
+    ms_gen = timed(lambda: qb.generate_from_marginals(full, oefs, dbvs, None, n_chunks=1))
+    ms_ll = timed(lambda: loglin(x))
+    return {'generate_full_model': {'voxels': n, 'ms': ms_gen, 'voxels_per_s': n / (ms_gen * 1e-3),
+                                    'hbm_gbs': n * 56 / (ms_gen * 1e-3) / 1e9,
+                                    'hbm_frac': n * 56 / (ms_gen * 1e-3) / 1e9 / hbm_peak,
+                                    'bound': 'fp32 (same quadrature as the headline kernel, forward only)'},
+            'forward_loglinear': {'voxels': n, 'ms': ms_ll, 'voxels_per_s': n / (ms_ll * 1e-3),
+                                  'hbm_gbs': n * 52 / (ms_ll * 1e-3) / 1e9,
+                                  'hbm_frac': n * 52 / (ms_ll * 1e-3) / 1e9 / hbm_peak, 'bound': 'hbm'},
+            'hbm_peak_gbs': hbm_peak}
+
+
 def workload_config(voxels, gpus):
     return {'workload': 'BASELINE config 2: batched forward model + analytic (TF-autodiff-consistent) gradients '
                         'w.r.t. OEF/DBV, %d voxels x 11-tau optimal.yaml grid per GPU, full model + blood' % voxels,
@@ -309,6 +345,7 @@ def main():
         }
         if world == 1:
             line['fused_elbo'] = fused_elbo_leg(qb, layer, cfg, x, sig, dev, f_alg, fma_tf)
+            line['streaming'] = streaming_leg(qb, cfg, x, dev, hbm_peak)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cpu_port_run(8192, threads)

@@ -184,21 +184,20 @@ __device__ __forceinline__ VoxelPhys voxel_phys(const QboldParams& P, float oef,
 // instruction footprint of the quadrature kernels.
 __device__ __forceinline__ void loglinear_tissue(const QboldParams& P, const VoxelPhys& v, float tau,
                                                  float& st, float& dst_doef, float& dst_ddbv) {
+    // One expf per element: the branch (signals.py:199-205) selects the exponent, not the exponential, so a warp
+    // whose voxels straddle |tau| = 1/dw does not evaluate both.  1/dw and 1/dbv are per-voxel (hoisted by the
+    // compiler out of the tau loop); -(0.3 rt^2)/dbv is evaluated as -(0.3 rt^2) * (1/dbv) (<= 1 ulp apart).
     const float tc = 1.0f / v.dw;
+    const float inv_dbv = 1.0f / v.dbv;
     const float r2p = v.dw * v.dbv;
     const float rt = r2p * tau;
-    if (fabsf(tau) < tc) {
-        const float e = -(0.3f * (rt * rt)) / v.dbv;
-        st = P.e_tissue * expf(e);
-        // e = -0.3 tau^2 dw^2 dbv
-        const float de_drt = -(0.3f * 2.0f * rt) / v.dbv;
-        dst_doef = st * de_drt * tau * v.dbv * v.dw_k;
-        dst_ddbv = st * (de_drt * tau * v.dw + (0.3f * (rt * rt)) / (v.dbv * v.dbv));
-    } else {
-        st = P.e_tissue * expf(v.dbv - rt);
-        dst_doef = st * (-tau * v.dbv * v.dw_k);
-        dst_ddbv = st * (1.0f - tau * v.dw);
-    }
+    const bool short_tau = fabsf(tau) < tc;
+    const float q = 0.3f * (rt * rt);
+    st = P.e_tissue * expf(short_tau ? -(q * inv_dbv) : v.dbv - rt);
+    // short: e = -0.3 tau^2 dw^2 dbv
+    const float de_drt = -(0.3f * 2.0f * rt) * inv_dbv;
+    dst_doef = short_tau ? st * de_drt * tau * v.dbv * v.dw_k : st * (-tau * v.dbv * v.dw_k);
+    dst_ddbv = short_tau ? st * (de_drt * tau * v.dw + q * (inv_dbv * inv_dbv)) : st * (1.0f - tau * v.dw);
 }
 
 // Signal of one (voxel, tau) from the tissue integral; lane-local (signals.py:98-114,169-172).

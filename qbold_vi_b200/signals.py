@@ -274,13 +274,9 @@ def generate_from_marginals(sig_layer, oefs, dbvs, perm=None, n_chunks=10, snr_u
     pptr = None if perm is None else dptr(perm, torch.int64)
     with torch.cuda.device(dev):
         st = stream_ptr(dev)
-        for i in range(n_chunks):
-            if chunk == 0:
-                break
-            xs = train_x[i * chunk:(i + 1) * chunk]
+        if n_x > 0:                 # rows are independent: the reference's chunking (:282-285) only matters for the noise
             check(lib.qbold_generate(C.byref(sig_layer.params), dptr(oefs), oefs.numel(), dptr(dbvs), dbvs.numel(),
-                                     pptr, seed, i * chunk, chunk, dptr(xs), dptr(train_y[i * chunk:(i + 1) * chunk]),
-                                     st))
+                                     pptr, seed, 0, n_x, dptr(train_x), dptr(train_y), st))
         if total > n_x:
             check(lib.qbold_generate(C.byref(sig_layer.params), dptr(oefs), oefs.numel(), dptr(dbvs), dbvs.numel(),
                                      pptr, seed, n_x, total - n_x, None, dptr(train_y[n_x:]), st))
