@@ -226,6 +226,23 @@ int qbold_diag_kl(const float* pred, int32_t pred_stride, const float* prior, in
                   const float* mask, int64_t n, float* kl_map, float* grad_pred, int32_t grad_pred_stride,
                   float* grad_prior, int32_t grad_prior_stride, void* stream);
 
+/* ---- stream 1 of the amortization network on the tensor cores ------------------------------ */
+
+/* The voxel-wise branch of create_encoder (model.py:122-223): normalise_data (:97-113) -> Dense(n_in -> H) -> ReLU ->
+ * n_mid x [Dense(H -> H) -> ReLU] -> Dense(H -> n_out), one tcgen05 (kind::tf32, fp32 accumulate in TMEM) kernel,
+ * inference only.  Limits: n_in <= 32, H <= 64, 1 <= n_mid <= 6, n_out <= 16, ReLU.
+ * qbold_encoder_mlp_pack turns torch-layout device weights ([out, in] row-major, biases [out]) into the
+ * shared-memory image (`blob`, qbold_encoder_mlp_blob_floats(n_mid) floats, device) the kernel copies verbatim;
+ * w_mid / b_mid are HOST arrays of n_mid device pointers.  qbold_encoder_mlp_forward: data [n, n_in] raw images ->
+ * q [n, n_out]; *status (device int, may be NULL) becomes non-zero if a tensor-core completion timed out. */
+int qbold_encoder_mlp_blob_floats(int32_t n_mid);
+int qbold_encoder_mlp_pack(const float* w_in, const float* b_in, const float* const* w_mid, const float* const* b_mid,
+                           const float* w_out, const float* b_out, int32_t n_in, int32_t n_hidden, int32_t n_mid,
+                           int32_t n_out, float* blob, void* stream);
+int qbold_encoder_mlp_forward(const float* data, const float* blob, int32_t n_in, int32_t n_mid, int32_t n_out,
+                              int32_t se_idx, int32_t multi_image_normalisation, int64_t n, float* q, int32_t* status,
+                              void* stream);
+
 /* FP32 FMA micro-benchmark (roofline denominator measured in the same run): launches
  * `iters` dependent-chain FFMA sweeps, returns achieved TFLOP/s through *tflops. */
 int qbold_fma_peak(int32_t iters, double* tflops);

@@ -80,6 +80,11 @@ _SIGNATURES = {
                                   _f, C.c_void_p]),
     'qbold_diag_kl': (C.c_int, [_f, C.c_int32, _f, C.c_int32, _f, C.c_int64, _f, _f, C.c_int32, _f, C.c_int32,
                                 C.c_void_p]),
+    'qbold_encoder_mlp_blob_floats': (C.c_int, [C.c_int32]),
+    'qbold_encoder_mlp_pack': (C.c_int, [_f, _f, _P(C.c_void_p), _P(C.c_void_p), _f, _f, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, _f, C.c_void_p]),
+    'qbold_encoder_mlp_forward': (C.c_int, [_f, _f, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _f,
+                                            _f, C.c_void_p]),
     'qbold_fma_peak': (C.c_int, [C.c_int32, _P(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

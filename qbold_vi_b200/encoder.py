@@ -92,6 +92,45 @@ class Encoder(nn.Module):
         ref = d[..., se - 1:se + 2] if self.multi_image_normalisation else d[..., se:se + 1]
         return torch.log(d / ref.mean(-1, keepdim=True))
 
+    @torch.no_grad()
+    def voxelwise_fused(self, data):
+        """q_voxelwise (output 0 of forward) from ONE tcgen05 kernel (qbold_encoder_mlp_forward): normalise_data, the
+        first Dense, the blocks' stream-1 Dense layers and the final Dense, TF32 tensor cores with fp32 accumulation
+        in TMEM, inference only.  Needs ReLU, no_units <= 64, n_tau <= 32."""
+        import ctypes as C
+        from . import _lib
+        from ._lib import check, dptr, stream_ptr
+        if self.act is not F.relu:
+            raise _lib.QboldError('voxelwise_fused supports the ReLU encoder (optimal.yaml) only')
+        lead = tuple(data.shape[:-1])
+        x = data.reshape(-1, data.shape[-1]).float().contiguous()
+        n, n_in = x.shape
+        n_mid, n_out, hidden = len(self.blocks), self.final.out_features, self.first.out_features
+        lib = _lib.lib()
+        n_blob = lib.qbold_encoder_mlp_blob_floats(n_mid)
+        if n_blob < 0:
+            raise _lib.QboldError('voxelwise_fused supports 1..6 blocks')
+        dev = x.device
+        blob = torch.empty(n_blob, dtype=torch.float32, device=dev)
+        q = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = [b.pointwise.weight.detach().float().contiguous() for b in self.blocks]
+        bs = [b.pointwise.bias.detach().float().contiguous() for b in self.blocks]
+        w_arr = (C.c_void_p * n_mid)(*[w.data_ptr() for w in ws])
+        b_arr = (C.c_void_p * n_mid)(*[b.data_ptr() for b in bs])
+        w_in, b_in = self.first.weight.detach().float().contiguous(), self.first.bias.detach().float().contiguous()
+        w_out, b_out = self.final.weight.detach().float().contiguous(), self.final.bias.detach().float().contiguous()
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            check(lib.qbold_encoder_mlp_pack(dptr(w_in), dptr(b_in), w_arr, b_arr, dptr(w_out), dptr(b_out), n_in, hidden,
+                                             n_mid, n_out, dptr(blob), st))
+            check(lib.qbold_encoder_mlp_forward(dptr(x), dptr(blob), n_in, n_mid, n_out, self.se_idx,
+                                                int(self.multi_image_normalisation), n, dptr(q),
+                                                dptr(status, torch.int32), st))
+        if int(status.item()) != 0:
+            raise _lib.QboldError('k_encoder_mlp: a tensor-core completion barrier timed out')
+        return q.reshape(lead + (n_out,))
+
     def forward(self, data):
         h = self.act(self.first(self.normalise_data(data)))
         net1 = net2 = h

@@ -844,3 +844,35 @@ def test_more_than_2_31_output_elements(qb, dev, cfg_noise_off):
     assert torch.equal(out[(1 << 20) * 100:(1 << 20) * 101], ref)
     del out, x
     torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------- stream-1 MLP on tcgen05
+@pytest.mark.parametrize('n_tau,units,blocks,multi,n', [(11, 60, 2, False, 5000), (11, 60, 2, True, 128),
+                                                       (24, 64, 1, False, 333), (11, 32, 3, False, 70000),
+                                                       (5, 10, 1, False, 1)])
+def test_voxelwise_encoder_tensor_core_kernel(qb, dev, n_tau, units, blocks, multi, n):
+    """qbold_encoder_mlp_forward (TF32 tcgen05, fp32 accumulate) vs the same layers in float32 torch (TF32 off)."""
+    from qbold_vi_b200.encoder import Encoder
+    torch.manual_seed(n_tau * 100 + units)
+    se = 2
+    enc = Encoder(no_units=units, no_intermediate_layers=blocks, no_ip_images=n_tau, se_idx=se,
+                  multi_image_normalisation=multi).to(dev)
+    with torch.no_grad():                                                    # non-trivial biases
+        for m in [enc.first, enc.final] + [b.pointwise for b in enc.blocks]:
+            m.bias.normal_(0.0, 0.3)
+    g = torch.Generator().manual_seed(n)
+    data = (torch.rand((n, 1, 1, 1, n_tau), generator=g) * 150.0 + 20.0).to(dev)
+    data[0, ..., 0] = 0.0                                                    # exercises the 1e-2 clip
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = enc(data)[0]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    got = enc.voxelwise_fused(data)
+    assert got.shape == ref.shape
+    # TF32 operands (10-bit mantissa), 3-4 chained layers: a few 1e-3 of the output scale
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) < 1e-2 * scale, (float((got - ref).abs().max()), scale)
+    assert float((got - ref).abs().mean()) < 2e-3 * scale
