@@ -3,7 +3,10 @@
 // sm_100a kernel on the 5th-generation tensor cores.  Forward / inference only: it produces the
 // voxel-wise posterior the fine-tuning stage uses as its prior (train.py:26-31) and save_predictions maps.
 //
-// Mapping: a CTA owns tiles of 128 voxels = the 128 TMEM lanes.  Activations (A, 128 x 64 fp32) and all layer
+// Mapping: a group of 128 threads owns tiles of 128 voxels = the 128 TMEM lanes; a CTA runs kGroups independent
+// groups (own A tile, TMEM columns, mbarrier and named barrier; the weights are shared) so that one group's
+// epilogue overlaps the others' tensor-core work -- the per-layer chain ld -> epilogue -> fence -> mma -> commit
+// is latency-, not throughput-bound.  Activations (A, 128 x 64 fp32) and all layer
 // weights (B, [out, in] = K-major, padded to 64) live in shared memory in the canonical K-major SWIZZLE_128B
 // layout; thread 0 issues tcgen05.mma kind::tf32 (fp32 bit patterns in, fp32 accumulate in TMEM), completion
 // comes back through tcgen05.commit -> mbarrier, each thread then pulls its own voxel's 64 accumulators with
@@ -20,7 +23,8 @@ constexpr int kH = 64;              // padded hidden width (N of the hidden laye
 constexpr int kNOut = 16;           // padded output width
 constexpr int kMaxMid = 6;          // hidden->hidden layers
 constexpr int kKBlock = 32;         // floats per 128-byte swizzle row
-constexpr int kTmemCols = 64;
+constexpr int kGroups = 4;          // independent 128-thread tile pipelines per CTA (1 CTA / SM: 128 + 46 KB smem)
+constexpr int kTmemCols = 64 * kGroups;
 
 constexpr int kATileFloats = 2 * kTile * kKBlock;       // 2 K-blocks x 128 rows x 32 floats = 32 KB
 constexpr int kW0Floats = kH * kKBlock;                 // 1 K-block  x 64 rows            = 8 KB
@@ -86,6 +90,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ void group_sync(int group) {        // named barrier 1 + group, 128 threads
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kTile) : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -147,6 +155,19 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The destination registers are only defined after tcgen05.wait::ld: they are bound straight to the caller's
+// floats so that no instruction touches them in between.
+__device__ __forceinline__ void tmem_ld16_nowait(unsigned taddr, float* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void sts_f4(unsigned addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -160,7 +181,7 @@ __device__ __forceinline__ unsigned a_chunk_addr(unsigned a_base, int row, int c
 }  // namespace
 
 // data [n, n_in] raw images -> q [n, n_out].  status[0] is set non-zero if a tensor-core completion never arrived.
-__global__ void __launch_bounds__(kTile) k_encoder_mlp(const float* __restrict__ data, const float* __restrict__ blob,
+__global__ void __launch_bounds__(kTile * kGroups, 1) k_encoder_mlp(const float* __restrict__ data, const float* __restrict__ blob,
                                                        int n_in, int n_mid, int n_out, int se_idx, int multi_norm,
                                                        int64_t n, float* __restrict__ q, int* __restrict__ status) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -170,14 +191,15 @@ __global__ void __launch_bounds__(kTile) k_encoder_mlp(const float* __restrict__
     const unsigned base = (raw + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - raw);
     float* sA = reinterpret_cast<float*>(sm);
-    float* sW = sA + kATileFloats;
+    float* sW = sA + kGroups * kATileFloats;
     const int wfloats = blob_floats(n_mid);
     float* sBias = sW + kW0Floats + n_mid * kWmFloats + kWoFloats;
     uint64_t* sBar = reinterpret_cast<uint64_t*>(sW + ((wfloats + 3) & ~3));
-    unsigned* sTmem = reinterpret_cast<unsigned*>(sBar + 1);
+    unsigned* sTmem = reinterpret_cast<unsigned*>(sBar + kGroups);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const unsigned a_base = base, w_base = base + kATileFloats * 4, bar = smem_u32(sBar);
+    const int warp = threadIdx.x >> 5, group = threadIdx.x / kTile, tid = threadIdx.x % kTile;
+    const unsigned a_base = base + group * (kATileFloats * 4), w_base = base + kGroups * kATileFloats * 4;
+    const unsigned bar = smem_u32(sBar + group);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)),
@@ -192,46 +214,47 @@ __global__ void __launch_bounds__(kTile) k_encoder_mlp(const float* __restrict__
     {   // weights + biases: verbatim copy of the packed image
         const float4* src = reinterpret_cast<const float4*>(blob);
         float4* dst = reinterpret_cast<float4*>(sW);
-        for (int i = tid; i < wfloats / 4; i += kTile) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < wfloats / 4; i += kTile * kGroups) dst[i] = __ldg(src + i);
     }
     fence_async_smem();
     tc_before_sync();
     __syncthreads();
     tc_after_sync();
-    const unsigned tmem = *sTmem;
-    const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16);
+    const unsigned tmem_all = *sTmem;
+    const unsigned tmem = tmem_all + group * 64;                          // this group's 64 accumulator columns
+    const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16);    // a warp reaches lanes 32 (warp % 4) ...
     const unsigned idesc_h = instr_desc(kH), idesc_o = instr_desc(kNOut);
     const int ks_in = (n_in + 7) >> 3;                                    // k-steps of 8 floats for the first layer
     unsigned phase = 0;
     bool ok = true;
 
     const int64_t tiles = (n + kTile - 1) / kTile;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int64_t tile = (int64_t)blockIdx.x * kGroups + group; tile < tiles; tile += (int64_t)gridDim.x * kGroups) {
         const int64_t v = tile * kTile + tid;
         // ---- normalise_data (model.py:97-113): clip, divide by the tau = 0 image (or the 3-image mean), log
         {
-            float x[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                x[i] = 1.0f;
-                if (i < n_in && v < n) x[i] = fminf(fmaxf(__ldg(data + v * n_in + i), 1e-2f), 1e8f);
-            }
+            const float* row = data + (v < n ? v : n - 1) * n_in;
             float ref = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const bool in = multi_norm ? (i >= se_idx - 1 && i <= se_idx + 1) : (i == se_idx);
-                if (in) ref += x[i];
+            if (multi_norm) {
+                for (int i = se_idx - 1; i <= se_idx + 1; ++i) ref += fminf(fmaxf(__ldg(row + i), 1e-2f), 1e8f);
+                ref = ref / 3.0f;
+            } else {
+                ref = fminf(fmaxf(__ldg(row + se_idx), 1e-2f), 1e8f);
             }
-            if (multi_norm) ref = ref / 3.0f;
+            for (int ks = 0; ks < ks_in; ++ks) {                       // 8 inputs = one k-step = two 16-byte chunks
+                float x[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = (i < n_in) ? logf(x[i] / ref) : 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < 2 * ks_in) sts_f4(a_chunk_addr(a_base, tid, c), x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                for (int i = 0; i < 8; ++i) {
+                    const int k = ks * 8 + i;
+                    x[i] = (k < n_in) ? logf(fminf(fmaxf(__ldg(row + k), 1e-2f), 1e8f) / ref) : 0.f;
+                }
+                sts_f4(a_chunk_addr(a_base, tid, 2 * ks), x[0], x[1], x[2], x[3]);
+                sts_f4(a_chunk_addr(a_base, tid, 2 * ks + 1), x[4], x[5], x[6], x[7]);
+            }
         }
         tc_before_sync();
         fence_async_smem();
-        __syncthreads();
+        group_sync(group);
         if (tid == 0) {
             tc_after_sync();
             for (int k = 0; k < ks_in; ++k)
@@ -245,21 +268,19 @@ __global__ void __launch_bounds__(kTile) k_encoder_mlp(const float* __restrict__
         // ---- hidden layers: bias + ReLU epilogue writes the next A tile, then 8 k-steps over the two K-blocks
         for (int l = 0; l <= n_mid; ++l) {
             const float* bias = sBias + l * kH;
+            float acc[64];
 #pragma unroll
-            for (int part = 0; part < 4; ++part) {
-                float acc[16];
-                tmem_ld16(taddr + part * 16, acc);
+            for (int part = 0; part < 4; ++part) tmem_ld16_nowait(taddr + part * 16, acc + part * 16);
+            tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int j = part * 16 + c * 4;
-                    sts_f4(a_chunk_addr(a_base, tid, part * 4 + c), fmaxf(acc[c * 4 + 0] + bias[j + 0], 0.f),
-                           fmaxf(acc[c * 4 + 1] + bias[j + 1], 0.f), fmaxf(acc[c * 4 + 2] + bias[j + 2], 0.f),
-                           fmaxf(acc[c * 4 + 3] + bias[j + 3], 0.f));
-                }
+            for (int c = 0; c < 16; ++c) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + c * 4);
+                sts_f4(a_chunk_addr(a_base, tid, c), fmaxf(acc[c * 4 + 0] + b.x, 0.f), fmaxf(acc[c * 4 + 1] + b.y, 0.f),
+                       fmaxf(acc[c * 4 + 2] + b.z, 0.f), fmaxf(acc[c * 4 + 3] + b.w, 0.f));
             }
             tc_before_sync();
             fence_async_smem();
-            __syncthreads();
+            group_sync(group);
             const bool last = (l == n_mid);
             if (tid == 0) {
                 tc_after_sync();
@@ -292,7 +313,7 @@ __global__ void __launch_bounds__(kTile) k_encoder_mlp(const float* __restrict__
     tc_before_sync();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)kTmemCols)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "r"((unsigned)kTmemCols)
                      : "memory");
     }
 }
@@ -344,13 +365,13 @@ extern "C" int qbold_encoder_mlp_forward(const float* data, const float* blob, i
         return fail(QBOLD_EINVAL, "qbold_encoder_mlp_forward: bad argument");
     if (n == 0) return QBOLD_OK;
     if (!data || !blob || !q) return fail(QBOLD_EINVAL, "qbold_encoder_mlp_forward: null pointer");
-    const size_t smem = 1024 + (size_t)(kATileFloats + ((blob_floats(n_mid) + 3) & ~3)) * 4 + 16;
+    const size_t smem = 1024 + (size_t)(kGroups * kATileFloats + ((blob_floats(n_mid) + 3) & ~3)) * 4 + 8 * kGroups + 16;
     int rc = cuda_check(cudaFuncSetAttribute(k_encoder_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                         "cudaFuncSetAttribute(k_encoder_mlp)");      // per device; cheap, so not cached
     if (rc) return rc;
-    const int64_t tiles = (n + kTile - 1) / kTile;
-    const int64_t cap = (int64_t)sm_count() * 2;
-    k_encoder_mlp<<<(unsigned)(tiles < cap ? tiles : cap), kTile, smem, (cudaStream_t)stream>>>(
+    const int64_t want = ((n + kTile - 1) / kTile + kGroups - 1) / kGroups;
+    const int64_t cap = (int64_t)sm_count();
+    k_encoder_mlp<<<(unsigned)(want < cap ? want : cap), kTile * kGroups, smem, (cudaStream_t)stream>>>(
         data, blob, n_in, n_mid, n_out, se_idx, multi_image_normalisation, n, q, status);
     return after_launch("k_encoder_mlp");
 }
