@@ -43,8 +43,10 @@ class FineTuneDataset:
         self.device = torch.device(device) if device is not None else real.device
         self.real = real.float().to(self.device).contiguous()
         self.crop = [min(crop_size, self.real.shape[1]), min(crop_size, self.real.shape[2])]
+        masked = self.real[..., :-1] * self.real[..., -1:]
         with torch.no_grad():                                                   # train.py:26-31
-            q = model(self.real[..., :-1] * self.real[..., -1:])[0]
+            can_fuse = getattr(model, 'supports_voxelwise_fused', lambda: False)()
+            q = model.voxelwise_fused(masked) if can_fuse and masked.is_cuda else model(masked)[0]
         self.prior = q[..., :5].contiguous()
         self.batch = 38 if training else 3                                      # train.py:68,70
         self.gen = torch.Generator(device='cpu').manual_seed(seed)

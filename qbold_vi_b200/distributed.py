@@ -207,7 +207,9 @@ class StreamingPretrainer:
         x, y = self.next_batch()
         nt = self.layer.n_tau
         self.bucket.zero_()
-        out, _, _ = self.encoder(x.reshape(-1, 10, 10, 5, nt))
+        blocks = x.reshape(-1, 10, 10, 5, nt)
+        fwd = getattr(self.encoder, 'forward_voxelwise', None)           # stream 1 is all the loss sees
+        out = fwd(blocks) if fwd is not None else self.encoder(blocks)[0]
         loss = self.trainer.synthetic_data_loss(y, out) / world_size()
         loss.backward()
         self.bucket.all_reduce_()

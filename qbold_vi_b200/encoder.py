@@ -92,6 +92,11 @@ class Encoder(nn.Module):
         ref = d[..., se - 1:se + 2] if self.multi_image_normalisation else d[..., se:se + 1]
         return torch.log(d / ref.mean(-1, keepdim=True))
 
+    def supports_voxelwise_fused(self):
+        """Limits of the tensor-core kernel: ReLU, <= 64 units, <= 32 input images, 1..6 blocks, <= 16 outputs."""
+        return (self.act is F.relu and self.first.out_features <= 64 and self.first.in_features <= 32 and
+                1 <= len(self.blocks) <= 6 and self.final.out_features <= 16)
+
     @torch.no_grad()
     def voxelwise_fused(self, data):
         """q_voxelwise (output 0 of forward) from ONE tcgen05 kernel (qbold_encoder_mlp_forward): normalise_data, the
@@ -130,6 +135,14 @@ class Encoder(nn.Module):
         if int(status.item()) != 0:
             raise _lib.QboldError('k_encoder_mlp: a tensor-core completion barrier timed out')
         return q.reshape(lead + (n_out,))
+
+    def forward_voxelwise(self, data):
+        """Output 0 alone through the torch layers (differentiable): the only output the pre-training loss uses
+        (train.py:402-412 compiles the model with a loss on the first output), so the 3x3x1 stream is skipped."""
+        h = self.act(self.first(self.normalise_data(data)))
+        for blk in self.blocks:
+            h = self.act(blk.pointwise(h))
+        return self.final(h)
 
     def forward(self, data):
         h = self.act(self.first(self.normalise_data(data)))

@@ -876,3 +876,26 @@ def test_voxelwise_encoder_tensor_core_kernel(qb, dev, n_tau, units, blocks, mul
     scale = float(ref.abs().max())
     assert float((got - ref).abs().max()) < 1e-2 * scale, (float((got - ref).abs().max()), scale)
     assert float((got - ref).abs().mean()) < 2e-3 * scale
+
+
+def test_fine_tune_dataset_prior_uses_the_tensor_core_branch(qb, dev):
+    """FineTuneDataset (train.py:17-72): the prior is output 0 of the pre-trained model; on CUDA it comes from the
+    one-launch tcgen05 branch and must agree with the full torch forward."""
+    from qbold_vi_b200.data import FineTuneDataset
+    from qbold_vi_b200.encoder import Encoder
+    torch.manual_seed(2)
+    enc = Encoder(no_units=60, no_intermediate_layers=2).to(dev)
+    assert enc.supports_voxelwise_fused()
+    real = torch.rand(2, 60, 50, 4, 12) * 100.0 + 20.0
+    real[..., -1] = (real[..., -1] > 60.0).float()
+    ds = FineTuneDataset(real, enc, crop_size=20, training=False, device=dev)
+    masked = ds.real[..., :-1] * ds.real[..., -1:]
+    with torch.no_grad():
+        ref = enc(masked)[0]
+    assert float((ds.prior - ref).abs().max()) < 1e-2 * float(ref.abs().max())
+    (data, mask), tgt = next(iter(ds))
+    assert tuple(data.shape) == (3, 20, 20, 4, 11) and tuple(tgt['predictions'].shape) == (3, 20, 20, 4, 6)
+    gelu = Encoder(no_units=60, no_intermediate_layers=2, activation='gelu').to(dev)
+    assert not gelu.supports_voxelwise_fused()
+    with pytest.raises(qb.QboldError):
+        gelu.voxelwise_fused(masked)
