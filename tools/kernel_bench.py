@@ -63,6 +63,22 @@ def main():
         'posterior stats, 64 samples (K4)': lambda: tr.calculate_means(q, None, include_r2p=True, return_stds=True, no_samples=64),
         'reparam sample': lambda: qb.ReparamTrickLayer(tr)((q, None)),
     }
+    pred = layer(x)
+    y_true = torch.cat([data, mask[:, None]], -1)
+    cases['fine_tune_loss_fn alone (k_nll, value + partials)'] = lambda: tr.fine_tune_loss_fn(y_true, torch.cat([pred, sigma], -1))
+    side = int(round((n // 2) ** (1.0 / 3.0)))
+    qv = q[:2 * side ** 3].reshape(2, side, side, side, 5).contiguous()
+    tv_true = torch.cat([qv, torch.ones_like(qv[..., :1])], -1)
+    cases['smoothness TV, 2 x %d^3 (k_smoothness, value + gradient)' % side] = lambda: tr.smoothness_loss(tv_true, qv)
+    labels = torch.cat([x, (x[:, :1] * x[:, 1:2]) * 301.74], -1).contiguous()
+    cases['pre-training NLL (k_synth_nll, value + gradient)'] = lambda: tr.synthetic_data_loss(labels, q)
+    trd = qb.EncoderTrainer(cfg, student_t_df=200, multi_image_normalisation=False, use_mvg=False,
+                            use_population_prior=False, predict_log_data=False, seed=1)
+    q4, true4 = q[:, :4].contiguous(), torch.cat([prior[:, :4], mask[:, None]], -1).contiguous()
+    cases['diagonal KL (k_diag_kl, value + gradient)'] = lambda: trd.kl_loss(true4, q4, return_mean=False)
+    from qbold_vi_b200.encoder import create_encoder_from_args
+    enc = create_encoder_from_args(qb.optimal_arguments()).to(dev)
+    cases['voxel-wise encoder MLP 11-60-60-60-5 (k_encoder_mlp, tcgen05 TF32)'] = lambda: enc.voxelwise_fused(data)
     oefs = torch.rand(2048, device=dev, generator=g) * 0.75 + 0.05
     dbvs = torch.rand(n // 2048, device=dev, generator=g) * 0.19 + 0.003
     cfgn = dict(cfg)
