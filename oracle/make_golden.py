@@ -246,6 +246,17 @@ def main():
     adj['kl_pop'] = kl.detach().numpy()
     adj['kl_pop_grad'] = torch.autograd.grad(kl, [q8_t])[0].numpy().reshape(nv, 8)
     adj['kl_pop_pred'] = q8_t.detach().numpy().reshape(nv, 8)
+    # F5 mixture-of-Gaussians population prior (model.py:666-684): q + 3 components, two recorded normal draws
+    tr_m = make_trainer(use_mvg=False, use_population_prior=True, mog_components=3)
+    comps = np.tile(np.array([[-0.4, 0.2, -1.3, 0.1, 0.3, -0.2, -0.8, 0.3, -1.0, 0.4, -1.6, -0.1]], np.float32), (nv, 1))
+    q16_t = t5(np.concatenate([q5[:, :4], comps], -1), 16)
+    tf.random.set_seed(41)
+    tf.random.LOG.clear()
+    kl = tr_m.kl_loss(tf.concat([tf.convert_to_tensor(prior5[:, :4].reshape(shp + (4,))), m_t], -1), q16_t)
+    adj['kl_mog'] = kl.detach().numpy()
+    adj['kl_mog_grad'] = torch.autograd.grad(kl, [q16_t])[0].numpy().reshape(nv, 16)
+    adj['kl_mog_pred'] = q16_t.detach().numpy().reshape(nv, 16)
+    adj['kl_mog_eps'] = np.stack([e[1].numpy().reshape(nv) for e in tf.random.LOG], -1)      # [nv, 2]: oef, dbv draws
     np.savez(os.path.join(args.out, 'ref_shim_adjacent.npz'), **adj)
     print('adjacent: tv=%.6f synth=%.6f kl_diag=%.6f kl_pop=%.6f' % (float(adj['tv_mvg']), float(adj['synth_mvg']),
                                                                    float(adj['kl_diag']), float(adj['kl_pop'])))

@@ -416,9 +416,10 @@ class EncoderTrainer:
             if return_mean:
                 return torch.sum(kl) / torch.sum(mask)
             return kl.reshape(lead + (1,))
-        if self._use_population_prior and self._mog_components > 1:
-            raise NotImplementedError('mixture-of-Gaussians population prior (model.py:666-684) is not provided')
         mask = true[..., 4:5]
+        if self._use_population_prior and self._mog_components > 1:
+            return self._mog_kl(predicted, mask, return_mean, eps)
+
         lead = tuple(predicted.shape[:-1])
         m = mask.reshape(-1).float().contiguous()
         prior_cost = 0.0
@@ -440,6 +441,32 @@ class EncoderTrainer:
         if return_mean:
             return (torch.sum(kl) + prior_cost) / torch.sum(mask)
         return kl.reshape(lead + (1,))
+
+    def _mog_kl(self, predicted, mask, return_mean, eps=None):
+        """Mixture-of-Gaussians population prior (model.py:666-684), a non-default branch kept as tensor ops:
+        single-sample estimate -entropy(q) + mean over components of the Gaussian NLL of one logit-space draw.
+        ``predicted`` [...,4*(M+1)]: q then M components; ``eps`` [...,2] pins the (OEF, DBV) draws."""
+        m_comp = self._mog_components
+        parts = torch.split(predicted, 4, -1)
+        q = parts[0]
+        ls_o, ls_d = self.transform_std(q[..., 1]), self.transform_std(q[..., 3])
+        if eps is None:
+            eps = torch.randn(q.shape[:-1] + (2,), dtype=q.dtype, device=q.device)
+        s_o = q[..., 0] + eps[..., 0] * torch.exp(ls_o)
+        s_d = q[..., 2] + eps[..., 1] * torch.exp(ls_d)
+
+        def nll(sample, mean, raw_std):
+            ls = self.transform_std(raw_std)
+            return -(-ls - 0.5 * ((sample - mean) / torch.exp(ls)) ** 2)
+
+        kl = (ls_o + ls_d) * -1.0
+        for i in range(m_comp):
+            c = parts[i + 1]
+            kl = kl + nll(s_o, c[..., 0], c[..., 1]) / float(m_comp) + nll(s_d, c[..., 2], c[..., 3]) / float(m_comp)
+        kl = torch.where(mask > 0, kl.unsqueeze(-1), torch.zeros_like(mask))
+        if return_mean:
+            return torch.sum(kl) / torch.sum(mask)
+        return kl
 
     # ------------------------------------------------------------------ fused training objective
     def fused_elbo(self, signal_layer, q_params, im_sigma, data, mask, prior, kl_samples=70, kl_weight=1.0,

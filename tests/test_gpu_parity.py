@@ -899,3 +899,15 @@ def test_fine_tune_dataset_prior_uses_the_tensor_core_branch(qb, dev):
     assert not gelu.supports_voxelwise_fused()
     with pytest.raises(qb.QboldError):
         gelu.voxelwise_fused(masked)
+
+
+def test_mog_population_prior_kl_matches_reference_source(qb, dev, cfg_noise_off):
+    a, shp = _adj()
+    mask = _t(a['mask'].reshape(shp + (1,)), dev)
+    true = torch.cat([_t(a['prior5'][:, :4].reshape(shp + (4,)), dev), mask], -1)
+    tr = _trainer(qb, cfg_noise_off, use_mvg=False, use_population_prior=True, mog_components=3)
+    q16 = _t(a['kl_mog_pred'].reshape(shp + (16,)), dev).requires_grad_(True)
+    kl = tr.kl_loss(true, q16, eps=_t(a['kl_mog_eps'].reshape(shp + (2,)), dev))
+    assert rel_elem(kl.item(), a['kl_mog']) < GRAD_TOL
+    kl.backward()
+    assert rel_max(q16.grad.cpu().numpy().reshape(-1, 16), a['kl_mog_grad']) < GRAD_TOL
