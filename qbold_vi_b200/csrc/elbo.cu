@@ -117,29 +117,37 @@ __device__ __forceinline__ float mvn_nll(const Dist& d, float zh_o, float zh_d, 
 }
 
 // -log StudentT(df, 0, sigma).pdf(res) and its partials (model.py:557-559); cold path (optimal.yaml: df = 200).
+// Out of line for the same reason as roundtrip_literal below.
+__device__ __noinline__ float3 student_t_terms_cold(float logc, float df, float zq, float sg, float inv_sg) {
+    const float t = zq * zq / df;
+    const float k = (df + 1.0f) / (df + zq * zq);
+    return make_float3(-(logc - logf(sg) - 0.5f * (df + 1.0f) * log1pf(t)), k * zq * inv_sg,
+                       inv_sg - k * zq * zq * inv_sg);
+}
 __device__ __forceinline__ void student_t_terms(float logc, float df, float zq, float sg, float inv_sg, float& nll,
                                                     float& d_res, float& d_sg) {
-    const float t = zq * zq / df;
-    nll = -(logc - logf(sg) - 0.5f * (df + 1.0f) * log1pf(t));
-    const float k = (df + 1.0f) / (df + zq * zq);
-    d_res = k * zq * inv_sg;
-    d_sg = inv_sg - k * zq * zq * inv_sg;
+    const float3 r = student_t_terms_cold(logc, df, zq, sg, inv_sg);
+    nll = r.x;
+    d_res = r.y;
+    d_sg = r.z;
 }
 
 // The reference's float32 round trip z -> sigmoid -> OEF/DBV -> backwards_transform -> clip -> logit
 // (model.py:302-303, 310-311, 394-396) and d zh/d z, evaluated literally.  Cold path (|z| >= kRoundTripZ).
-__device__ __forceinline__ void roundtrip_literal(float z_o, float z_d, float& zh_o, float& zh_d, float& dz_o,
-                                               float& dz_d) {
+// Kept out of line (scalar arguments, float4 result in registers): the fused kernel is instruction-cache sensitive.
+__device__ __noinline__ float4 roundtrip_literal(float z_o, float z_d) {
     const float s_o = sigmoidf(z_o), s_d = sigmoidf(z_d);
     float x_o = ((s_o * kOefRange + kMinOef) - kMinOef) / kOefRange;
     float x_d = ((s_d * kDbvRange + kMinDbv) - kMinDbv) / kDbvRange;
     x_o = fminf(fmaxf(x_o, 1e-6f), 1.0f - 1e-6f);
     x_d = fminf(fmaxf(x_d, 1e-6f), 1.0f - 1e-6f);
-    zh_o = logf(x_o / (1.0f - x_o));
-    zh_d = logf(x_d / (1.0f - x_d));
+    float4 r;
+    r.x = logf(x_o / (1.0f - x_o));                                  // zh_o
+    r.y = logf(x_d / (1.0f - x_d));                                  // zh_d
     // d zh / d z: logit'(x) * (1/range) * range * sigmoid'(z); the clip passes the gradient (model.py:395)
-    dz_o = (s_o * (1.0f - s_o)) / (x_o * (1.0f - x_o));
-    dz_d = (s_d * (1.0f - s_d)) / (x_d * (1.0f - x_d));
+    r.z = (s_o * (1.0f - s_o)) / (x_o * (1.0f - x_o));
+    r.w = (s_d * (1.0f - s_d)) / (x_d * (1.0f - x_d));
+    return r;
 }
 
 // KL(q || prior) of one voxel and its gradient w.r.t. the raw q parameters; warp-cooperative
@@ -191,8 +199,13 @@ __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const
                 const float z_o = dq.mu_o + k0 * ex.sd_o;                            // model.py:26-27
                 const float z_d = (dq.mu_d + k0 * dq.cov) + k1 * ex.sd_d;            // model.py:29-31
                 float zh_o = z_o, zh_d = z_d, dz_o = 1.0f, dz_d = 1.0f;
-                if (fmaxf(fabsf(z_o), fabsf(z_d)) >= kRoundTripZ)
-                    roundtrip_literal(z_o, z_d, zh_o, zh_d, dz_o, dz_d);
+                if (fmaxf(fabsf(z_o), fabsf(z_d)) >= kRoundTripZ) {
+                    const float4 rt = roundtrip_literal(z_o, z_d);
+                    zh_o = rt.x;
+                    zh_d = rt.y;
+                    dz_o = rt.z;
+                    dz_d = rt.w;
+                }
                 float gq_o, gq_d, gp_o, gp_d;
                 const float nq = mvn_nll(dq, zh_o, zh_d, gq_o, gq_d);
                 const float np = mvn_nll(dp, zh_o, zh_d, gp_o, gp_d);
