@@ -117,8 +117,10 @@ class DataParallelTrainer:
         return self.trainer.smoothness_loss(torch.cat([prior, mask], -1), q, mask_sum=mask_sum)
 
     def _fused_loss(self, q, sigma, data, mask, prior, mask_sum):
+        # equal-size shards (weak scaling): this rank's first global voxel, so ranks draw disjoint Philox counters
+        rank = dist.get_rank() if world_size() > 1 else 0
         return self.trainer.fused_elbo(self.layer, q, sigma, data, mask, prior, kl_samples=self.kl_samples,
-                                       kl_weight=self.kl_weight, mask_sum=mask_sum)
+                                       kl_weight=self.kl_weight, mask_sum=mask_sum, offset=rank * mask.numel())
 
     def step(self, data, mask, prior):
         """data [B,X,Y,Z,n_tau] (pre-masked), mask [B,X,Y,Z,1], prior [B,X,Y,Z,5]: this rank's volumes."""

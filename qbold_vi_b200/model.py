@@ -194,7 +194,7 @@ class _FusedElboFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, sigma, trainer, layer, y, mask, prior, eps, eps_kl, seed, kl_samples, inv_mask_sum,
-                kl_weight, want_maps):
+                kl_weight, want_maps, offset=0):
         n = q.shape[0]
         dev = q.device
         nt = layer.n_tau
@@ -206,8 +206,8 @@ class _FusedElboFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(_lib.lib().qbold_elbo_fused(
                 C.byref(trainer._params_for(layer)), dptr(q), dptr(sigma), dptr(y), dptr(mask),
-                dptr(prior, allow_none=True), dptr(eps, allow_none=True), dptr(eps_kl, allow_none=True), seed, 0,
-                kl_samples, inv_mask_sum, kl_weight, n, dptr(grad_q), dptr(grad_sigma),
+                dptr(prior, allow_none=True), dptr(eps, allow_none=True), dptr(eps_kl, allow_none=True), seed,
+                int(offset), kl_samples, inv_mask_sum, kl_weight, n, dptr(grad_q), dptr(grad_sigma),
                 dptr(nll_map, allow_none=True), dptr(kl_map, allow_none=True), dptr(sums, torch.float64),
                 stream_ptr(dev)))
         ctx.save_for_backward(grad_q, grad_sigma)
@@ -222,7 +222,7 @@ class _FusedElboFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, *unused):
         grad_q, grad_sigma = ctx.saved_tensors
-        return (grad_q * g, grad_sigma * g) + (None,) * 12
+        return (grad_q * g, grad_sigma * g) + (None,) * 13
 
 
 class EncoderTrainer:
@@ -470,8 +470,10 @@ class EncoderTrainer:
 
     # ------------------------------------------------------------------ fused training objective
     def fused_elbo(self, signal_layer, q_params, im_sigma, data, mask, prior, kl_samples=70, kl_weight=1.0,
-                   eps=None, eps_kl=None, mask_sum=None, seed=None, return_maps=False):
+                   eps=None, eps_kl=None, mask_sum=None, seed=None, return_maps=False, offset=0):
         """nll + kl_weight * kl for one batch in ONE kernel launch (differentiable w.r.t. q_params, im_sigma).
+        ``offset``: global index of this batch's first voxel -- the in-kernel Philox counter is the global voxel
+        index, so shards of one batch draw exactly what the unsharded batch would (pass it when sharding over ranks).
 
         q_params [...,5], im_sigma [...,n_tau], data [...,n_tau] (pre-masked, train.py:56), mask [...,1],
         prior [...,5] raw or None.  ``mask_sum`` = global sum(mask) when the batch is sharded over ranks.
@@ -493,7 +495,7 @@ class EncoderTrainer:
         inv = 1.0 / float(mask_sum)
         out = _FusedElboFn.apply(q, sg, self, signal_layer, y, m, pr, e, ek,
                                  _next_seed(self) if seed is None else seed, kl_samples if pr is not None else 0,
-                                 inv, float(kl_weight), return_maps)
+                                 inv, float(kl_weight), return_maps, int(offset))
         loss, sums = out[0], out[1]
         info = {'nll': (sums[0] * inv).float(), 'kl': (sums[1] * inv).float(), 'mask_sum': sums[2],
                 'non_finite': sums[3]}
