@@ -86,13 +86,14 @@ class ReparamTrickLayer:
 
 class _KlFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, prior, mask, eps_kl, seed, n_samples):
+    def forward(ctx, pred, prior, mask, eps_kl, seed, n_samples, offset=0):
         n = pred.shape[0]
         kl_map = torch.empty(n, dtype=torch.float32, device=pred.device)
         grad = torch.empty((n, 5), dtype=torch.float32, device=pred.device)
         with torch.cuda.device(pred.device):
             check(_lib.lib().qbold_kl(dptr(pred), dptr(prior), dptr(mask, allow_none=True),
-                                      dptr(eps_kl, allow_none=True), seed, 0, n_samples, n, dptr(kl_map), dptr(grad),
+                                      dptr(eps_kl, allow_none=True), seed, int(offset), n_samples, n, dptr(kl_map),
+                                      dptr(grad),
                                       stream_ptr(pred.device)))
         ctx.save_for_backward(grad)
         return kl_map
@@ -100,7 +101,7 @@ class _KlFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (grad,) = ctx.saved_tensors
-        return grad * g[:, None], None, None, None, None, None
+        return grad * g[:, None], None, None, None, None, None, None
 
 
 class _NllFn(torch.autograd.Function):
@@ -309,7 +310,7 @@ class EncoderTrainer:
         return torch.stack([rpl([predicted_params, mask]) for _ in range(no_samples)], -1)
 
     def calculate_means(self, predicted_params, mask, include_r2p=False, return_stds=False, no_samples=20, eps=None,
-                        signal_layer=None):
+                        signal_layer=None, offset=0):
         """Posterior means (and the reference's 'stds', which are variances: model.py:331,337)."""
         lead = tuple(predicted_params.shape[:-1])
         q = _as_mvg(predicted_params, self._use_mvg).reshape(-1, 5).float().contiguous()
@@ -320,7 +321,7 @@ class EncoderTrainer:
         e = None if eps is None else eps.reshape(n, no_samples, 2).float().contiguous()
         with torch.cuda.device(q.device):
             check(_lib.lib().qbold_posterior_stats(C.byref(layer.params), dptr(q), dptr(e, allow_none=True),
-                                                   _next_seed(self), 0, no_samples, n, dptr(mean3), dptr(var3),
+                                                   _next_seed(self), int(offset), no_samples, n, dptr(mean3), dptr(var3),
                                                    stream_ptr(q.device)))
         k = 3 if include_r2p else 2
         means = mean3[:, :k].reshape(lead + (k,))
@@ -400,7 +401,7 @@ class EncoderTrainer:
                          _next_seed(self), no_samples)
         return kl.reshape(lead + (1,))
 
-    def kl_loss(self, true, predicted, return_mean=True, no_samples=70, eps=None):
+    def kl_loss(self, true, predicted, return_mean=True, no_samples=70, eps=None, offset=0):
         """KL(q || prior), model.py:654-724.  mvg: the reference's 70-sample MC estimator (``no_samples=0`` selects
         the closed form); diagonal: the analytic LogitNormal KL, optionally against a trainable population prior
         carried in channels 4..7 of ``predicted`` plus its InverseGamma(1, 2) hyper-prior (:710-715)."""
@@ -412,7 +413,7 @@ class EncoderTrainer:
             kl = _KlFn.apply(predicted.reshape(-1, 5).float().contiguous(),
                              prior_dist.reshape(-1, 5).float().contiguous(), m,
                              None if eps is None else eps.reshape(-1, no_samples, 2).float().contiguous(),
-                             _next_seed(self), no_samples)
+                             _next_seed(self), no_samples, int(offset))
             if return_mean:
                 return torch.sum(kl) / torch.sum(mask)
             return kl.reshape(lead + (1,))
@@ -511,7 +512,7 @@ class EncoderTrainer:
         return FineTuner(self, encoder_model, signal_generation_layer)
 
     # ------------------------------------------------------------------ whole-volume inference (model.py:772-887)
-    def likelihood_map(self, signal_layer, q_params, im_sigma, data, mask=None, no_samples=100, eps=None):
+    def likelihood_map(self, signal_layer, q_params, im_sigma, data, mask=None, no_samples=100, eps=None, offset=0):
         """Average per-voxel NLL over ``no_samples`` stochastic forward passes (save_predictions, model.py:808-817)."""
         nt = signal_layer.n_tau
         lead = tuple(q_params.shape[:-1])
@@ -524,19 +525,22 @@ class EncoderTrainer:
         out = torch.empty(n, dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
             check(_lib.lib().qbold_nll_map(C.byref(self._params_for(signal_layer)), dptr(q), dptr(sg), dptr(y),
-                                           dptr(m, allow_none=True), dptr(e, allow_none=True), _next_seed(self), 0,
+                                           dptr(m, allow_none=True), dptr(e, allow_none=True), _next_seed(self),
+                                           int(offset),
                                            no_samples, n, dptr(out), stream_ptr(q.device)))
         return out.reshape(lead + (1,))
 
-    def posterior_inference(self, signal_layer, q_params, im_sigma, data, mask, prior=None, no_samples=64):
+    def posterior_inference(self, signal_layer, q_params, im_sigma, data, mask, prior=None, no_samples=64, offset=0):
         """BASELINE config 4: per-voxel posterior summaries of a whole volume in three launches:
         mean / variance of OEF, DBV, R2' (calculate_means), likelihood map and KL map."""
         means, variances = self.calculate_means(q_params, mask, include_r2p=True, return_stds=True,
-                                                no_samples=no_samples, signal_layer=signal_layer)
+                                                no_samples=no_samples, signal_layer=signal_layer, offset=offset)
         out = {'means': means, 'variances': variances,
-               'likelihood': self.likelihood_map(signal_layer, q_params, im_sigma, data, mask, no_samples)}
+               'likelihood': self.likelihood_map(signal_layer, q_params, im_sigma, data, mask, no_samples,
+                                                 offset=offset)}
         if prior is not None:
-            out['kl'] = self.kl_loss(torch.cat([prior, mask], -1), q_params, return_mean=False, no_samples=no_samples)
+            out['kl'] = self.kl_loss(torch.cat([prior, mask], -1), q_params, return_mean=False, no_samples=no_samples,
+                                     offset=offset)
         return out
 
     def save_predictions(self, model, data, filename, transform_directory=None, use_first_op=True,
