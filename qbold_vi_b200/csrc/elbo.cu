@@ -740,42 +740,69 @@ __global__ void __launch_bounds__(kThreads, 4) k_nll_map_pair(const __grid_const
         if (P.predict_log_data) yn = logf(yn);
         const float inv_sg = 1.0f / sg, log_sg = logf(sg);
         float acc = 0.f;
-        for (int s0 = 0; s0 < n_samples; s0 += 2) {
-            const bool both = s0 + 1 < n_samples;
-            const int sidx = (half && both) ? s0 + 1 : s0;
-            const bool valid = (half == 0) || both;
-            float e0, e1;
-            if (eps) {
-                const float2 e = __ldg(reinterpret_cast<const float2*>(eps) + (v * n_samples + sidx));
-                e0 = e.x;
-                e1 = e.y;
-            } else {
-                mc_normal_pair(seed, offset + (uint64_t)v, sidx, e0, e1);
+        // Blocks of 64 samples: every lane first draws and transforms ITS two samples (one Philox call, two
+        // Box-Muller pairs, four sigmoids -- once per voxel instead of once per lane per sample); the iterations then
+        // only fetch (OEF, DBV) of their sample from the owning lane.
+        for (int sb = 0; sb < n_samples; sb += 64) {
+            const int mine = sb + 2 * lane;
+            float o0 = 0.f, d0 = 0.f, o1 = 0.f, d1 = 0.f;
+            if (mine < n_samples) {
+                float e0, e1, f0 = 0.f, f1 = 0.f;
+                const bool second = mine + 1 < n_samples;
+                if (eps) {
+                    const float2* ev = reinterpret_cast<const float2*>(eps) + (v * n_samples + mine);
+                    const float2 a = __ldg(ev);
+                    e0 = a.x;
+                    e1 = a.y;
+                    if (second) {
+                        const float2 b = __ldg(ev + 1);
+                        f0 = b.x;
+                        f1 = b.y;
+                    }
+                } else {
+                    const U4 r = mc_words(seed, offset + (uint64_t)v, mine);
+                    mc_box_muller(r.x, r.y, e0, e1);
+                    mc_box_muller(r.z, r.w, f0, f1);
+                }
+                const Sample a = draw(dq, ex, e0, e1), b = draw(dq, ex, f0, f1);
+                o0 = a.oef;
+                d0 = a.dbv;
+                o1 = b.oef;
+                d1 = b.dbv;
             }
-            const Sample sm = draw(dq, ex, e0, e1);
-            const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
-            const float A_mine = qc.tau_ref15 * vp.dw;
-            float I = 0.f;
+            const int cnt = min(64, n_samples - sb);
+            for (int s0 = 0; s0 < cnt; s0 += 2) {
+                const bool both = s0 + 1 < cnt;
+                const bool valid = (half == 0) || both;
+                const bool odd = half && both;
+                const int src = s0 >> 1;                                  // the lane that owns samples s0, s0 + 1
+                const float oa = __shfl_sync(kFull, o0, src), ob = __shfl_sync(kFull, o1, src);
+                const float da = __shfl_sync(kFull, d0, src), db = __shfl_sync(kFull, d1, src);
+                const float oef = odd ? ob : oa, dbv = odd ? db : da;
+                const VoxelPhys vp = voxel_phys<false>(P, oef, dbv, P.hct);
+                const float A_mine = qc.tau_ref15 * vp.dw;
+                float I = 0.f;
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                if (h == 1 && !both) continue;
-                const float A = __shfl_sync(kFull, A_mine, h << 4);
-                float vi, vd;
-                tissue_sched<false>(qc.nph, qc.sa, A, lane, qc.ph_lo, qc.ph_hi, my_col, vi, vd);
-                if (half == h) I = vi;
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !both) continue;
+                    const float A = __shfl_sync(kFull, A_mine, h << 4);
+                    float vi, vd;
+                    tissue_sched<false>(qc.nph, qc.sa, A, lane, qc.ph_lo, qc.ph_hi, my_col, vi, vd);
+                    if (half == h) I = vi;
+                }
+                if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
+                const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, 0.f);
+                const float pred = live ? ts.S : 0.f;
+                const float npd = (multi ? sum_live(in_norm ? pred * norm_w : 0.f, false)
+                                         : __shfl_sync(kFull, pred, gb + se)) + 1e-3f;
+                float pn = pred / npd;
+                if (P.predict_log_data) pn = logf(pn);
+                const float zq = (yn - pn) * inv_sg;
+                float nll_t;
+                if (df > 0.f) nll_t = -(P.student_t_logc - log_sg - 0.5f * (df + 1.0f) * log1pf(zq * zq / df));
+                else nll_t = -(-log_sg - kLogSqrt2Pi - 0.5f * (zq * zq));
+                acc += (live && valid) ? nll_t : 0.f;
             }
-            if (my_col >= 0) I += node0_value(P, 1.5f * (fabsf(my_tau) * vp.dw));
-            const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, 0.f);
-            const float pred = live ? ts.S : 0.f;
-            const float npd = (multi ? sum_live(in_norm ? pred * norm_w : 0.f, false)
-                                     : __shfl_sync(kFull, pred, gb + se)) + 1e-3f;
-            float pn = pred / npd;
-            if (P.predict_log_data) pn = logf(pn);
-            const float zq = (yn - pn) * inv_sg;
-            float nll_t;
-            if (df > 0.f) nll_t = -(P.student_t_logc - log_sg - 0.5f * (df + 1.0f) * log1pf(zq * zq / df));
-            else nll_t = -(-log_sg - kLogSqrt2Pi - 0.5f * (zq * zq));
-            acc += (live && valid) ? nll_t : 0.f;
         }
         const float tot = warp_sum(acc);
         if (lane == 0) nll_map[v] = (tot / (float)n_samples) * m;

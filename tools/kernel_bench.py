@@ -79,6 +79,9 @@ def main():
     from qbold_vi_b200.encoder import create_encoder_from_args
     enc = create_encoder_from_args(qb.optimal_arguments()).to(dev)
     cases['voxel-wise encoder MLP 11-60-60-60-5 (k_encoder_mlp, tcgen05 TF32)'] = lambda: enc.voxelwise_fused(data)
+    nl = max(n // 16, 1)
+    cases['likelihood map, 64 forward passes per voxel, %d voxels (k_nll_map)' % nl] = lambda: tr.likelihood_map(
+        layer, q[:nl], sigma[:nl], data[:nl], None, no_samples=64)
     oefs = torch.rand(2048, device=dev, generator=g) * 0.75 + 0.05
     dbvs = torch.rand(n // 2048, device=dev, generator=g) * 0.19 + 0.003
     cfgn = dict(cfg)
