@@ -311,10 +311,17 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-        traffic = None
+        traffic, issue = None, None
         try:                                             # per-voxel DRAM bytes of this kernel from the committed ncu capture
             tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
             traffic = tj['k_forward_pair_bwd']['dram_bytes_per_voxel'] * n
+            # hardware-side view next to the algorithmic-FLOP fraction: executed warp instructions (ncu count per
+            # voxel x voxels of this launch) against the 4 issue slots per SM per clock at the sampled SM clock
+            wipv = tj['k_forward_pair_bwd']['warp_inst_per_voxel']
+            peak_issue = 148 * 4 * (clocks.get('sm_mhz') or 1965) * 1e6
+            issue = {'warp_inst_per_voxel': wipv, 'achieved_warp_inst_per_s': n * wipv / per_launch_s,
+                     'peak_warp_inst_per_s': peak_issue, 'frac': n * wipv / per_launch_s / peak_issue,
+                     'source': 'smsp__inst_executed.sum per voxel from profiles/traffic.json (ncu), time measured here'}
         except Exception:
             pass
         hbm_gbs = n * 104 / per_launch_s / 1e9
@@ -339,7 +346,7 @@ def main():
                                         % (derived_tf, achieved_tf / derived_tf),
                          'kernel': 'k_forward_pair<BWD=true>', 'launch_ms': per_launch_s * 1e3,
                          'alg_flops_per_voxel': f_alg, 'asymptotic_branch_fraction_f': f_big,
-                         'alg_bytes_per_voxel': 104, 'hbm': {'achieved': hbm_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'alg_bytes_per_voxel': 104, 'issue': issue, 'hbm': {'achieved': hbm_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                                                              'frac': hbm_gbs / hbm_peak,
                                                              'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}},
         }
