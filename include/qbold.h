@@ -243,6 +243,14 @@ int qbold_encoder_mlp_forward(const float* data, const float* blob, int32_t n_in
                               int32_t se_idx, int32_t multi_image_normalisation, int64_t n, float* q, int32_t* status,
                               void* stream);
 
+/* Weight / bias gradient of a per-voxel Dense layer (the 1x1x1 convolutions of create_encoder, model.py:122-223):
+ * dw[n_out,n_in] = sum_v g[v,:]^T x[v,:], db[n_out] = sum_v g[v,:] (db may be NULL); TF32 mma, fp32 accumulate,
+ * deterministic two-stage reduction.  n_out <= 64, n_in <= 63.  workspace: qbold_dense_wgrad_workspace_floats()
+ * floats of device scratch.  accumulate != 0 adds into dw / db. */
+int64_t qbold_dense_wgrad_workspace_floats(void);
+int qbold_dense_wgrad(const float* g, int32_t n_out, const float* x, int32_t n_in, int64_t n, float* dw, float* db,
+                      int32_t accumulate, float* workspace, void* stream);
+
 /* FP32 FMA micro-benchmark (roofline denominator measured in the same run): launches
  * `iters` dependent-chain FFMA sweeps, returns achieved TFLOP/s through *tflops. */
 int qbold_fma_peak(int32_t iters, double* tflops);

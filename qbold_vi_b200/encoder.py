@@ -14,6 +14,52 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+_WGRAD_WS = {}
+
+
+class _DenseFn(torch.autograd.Function):
+    """y = x W^T + b for a per-voxel Dense layer (N ~ 10^5..10^6 rows, <= 64 features).  Forward and input gradient
+    are library GEMMs; the weight / bias gradient -- a reduction over all voxels that cuBLAS serves poorly at this
+    shape -- is qbold_dense_wgrad (TF32 mma, HBM-bound, deterministic)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addmm(bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        from . import _lib
+        from ._lib import check, dptr, stream_ptr
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        gx = g @ weight if ctx.needs_input_grad[0] else None
+        dev = x.device
+        lib = _lib.lib()
+        ws = _WGRAD_WS.get(dev)
+        if ws is None:
+            ws = _WGRAD_WS[dev] = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
+        dw = torch.empty_like(weight)
+        db = torch.empty(weight.shape[0], dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.qbold_dense_wgrad(dptr(g), weight.shape[0], dptr(x), weight.shape[1], x.shape[0], dptr(dw),
+                                        dptr(db), 0, dptr(ws), stream_ptr(dev)))
+        return gx, dw, db
+
+
+def dense(layer, x):
+    """nn.Linear on the last axis; routes through _DenseFn when training on CUDA in TF32 mode with a supported
+    shape (weights contiguous float32, <= 64 outputs, <= 63 inputs), else F.linear."""
+    w, b = layer.weight, layer.bias
+    if (x.is_cuda and torch.is_grad_enabled() and w.requires_grad and b is not None and x.dtype == torch.float32
+            and torch.backends.cuda.matmul.allow_tf32 and w.shape[0] <= 64 and w.shape[1] <= 63
+            and not torch.is_autocast_enabled()):
+        lead = x.shape[:-1]
+        return _DenseFn.apply(x.reshape(-1, x.shape[-1]).contiguous(), w, b).reshape(lead + (w.shape[0],))
+    return layer(x)
+
+
 def _he_normal_(w, fan_in):
     # keras HeNormal: truncated normal, stddev = sqrt(2 / fan_in) / 0.87962566
     std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
@@ -56,10 +102,10 @@ class _Block(nn.Module):
         nn.init.zeros_(self.gate.bias)
 
     def forward(self, net1, net2):
-        out1 = self.act(self.pointwise(net1))
-        skip = self.act(self.pointwise(net2))
+        out1 = self.act(dense(self.pointwise, net1))
+        skip = self.act(dense(self.pointwise, net2))
         r = self.conv_b(self.act(self.conv_a(self.act(net2))))
-        g = torch.sigmoid(self.gate(r) + self.gate_offset)
+        g = torch.sigmoid(dense(self.gate, r) + self.gate_offset)
         return out1, skip * (1.0 - g) + r * g
 
 
@@ -139,17 +185,17 @@ class Encoder(nn.Module):
     def forward_voxelwise(self, data):
         """Output 0 alone through the torch layers (differentiable): the only output the pre-training loss uses
         (train.py:402-412 compiles the model with a loss on the first output), so the 3x3x1 stream is skipped."""
-        h = self.act(self.first(self.normalise_data(data)))
+        h = self.act(dense(self.first, self.normalise_data(data)))
         for blk in self.blocks:
-            h = self.act(blk.pointwise(h))
-        return self.final(h)
+            h = self.act(dense(blk.pointwise, h))
+        return dense(self.final, h)
 
     def forward(self, data):
-        h = self.act(self.first(self.normalise_data(data)))
+        h = self.act(dense(self.first, self.normalise_data(data)))
         net1 = net2 = h
         for blk in self.blocks:
             net1, net2 = blk(net1, net2)
-        return self.final(net1), self.final(net2), torch.exp(self.im_sigma(net2))
+        return dense(self.final, net1), dense(self.final, net2), torch.exp(dense(self.im_sigma, net2))
 
 
 def create_encoder_from_args(args, no_ip_images=11, se_idx=2):

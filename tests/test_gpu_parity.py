@@ -959,3 +959,30 @@ def test_fused_elbo_full_size_properties(qb, dev, cfg_noise_off):
                                                   return_maps=True)[1], None, None))()
     d = (info['kl_map'] - info0['kl_map'])[mask > 0].double()
     assert abs(float(d.mean())) < 5.0 * float(d.std()) / (d.numel() ** 0.5) + 1e-4 * float(info0['kl_map'].mean())
+
+
+@pytest.mark.parametrize('n,n_in,n_out', [(5000, 11, 60), (70001, 60, 60), (333, 60, 5), (31, 60, 11), (1, 63, 64)])
+def test_dense_weight_gradient_kernel(qb, dev, n, n_in, n_out):
+    """qbold_dense_wgrad (TF32 mma, fp32 accumulate) vs float64 matmul; the encoder routes its Dense layers through it."""
+    from qbold_vi_b200.encoder import _DenseFn
+    g0 = torch.Generator().manual_seed(n + n_in)
+    x = torch.randn((n, n_in), generator=g0).to(dev).requires_grad_(True)
+    w = (torch.randn((n_out, n_in), generator=g0) * 0.2).to(dev).requires_grad_(True)
+    b = torch.randn(n_out, generator=g0).to(dev).requires_grad_(True)
+    go = torch.randn((n, n_out), generator=g0).to(dev)
+    y = _DenseFn.apply(x, w, b)
+    y.backward(go)
+    dw_ref = go.double().t() @ x.detach().double()
+    db_ref = go.double().sum(0)
+    scale = float(dw_ref.abs().max())
+    # TF32 operands: 2^-11 relative per product, random signs -> ~1e-3 of the scale at most
+    assert float((w.grad.double() - dw_ref).abs().max()) < 2e-3 * max(scale, 1.0)
+    assert float((b.grad.double() - db_ref).abs().max()) < 2e-3 * max(float(db_ref.abs().max()), 1.0)
+    assert float((x.grad.double() - go.double() @ w.detach().double()).abs().max()) < 5e-3 * float(go.abs().max())
+    y2 = _DenseFn.apply(x, w, b)                               # deterministic: bit-identical on a second run
+    w.grad = None
+    y2.backward(go)
+    dw1 = w.grad.clone()
+    w.grad = None
+    _DenseFn.apply(x, w, b).backward(go)
+    assert torch.equal(dw1, w.grad)
