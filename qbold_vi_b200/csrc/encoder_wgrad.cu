@@ -45,24 +45,52 @@ __global__ void __launch_bounds__(kWgThreads) k_dense_wgrad(const float* __restr
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
     const int64_t tiles = (n + kWgTile - 1) / kWgTile;
-    // stage a tile: kWgTile rows x 64 columns, zero padded; column n_in of x holds 1 (bias gradient)
-    auto stage = [&](int buf, int64_t tile) {
-        const int64_t v0 = tile * kWgTile;
-        for (int e = tid; e < kWgTile * 64; e += kWgThreads) {
-            const int r = e >> 6, c = e & 63;
-            const int64_t v = v0 + r;
-            const bool in = v < n;
-            sg[buf][r * kWgLd + c] = (in && c < n_out) ? __ldg(g + v * n_out + c) : 0.f;
-            sx[buf][r * kWgLd + c] = in ? (c < n_in ? __ldg(x + v * n_in + c) : (c == n_in ? 1.0f : 0.f)) : 0.f;
+    // Padding is written once: columns >= n_out of g and > n_in of x stay 0, column n_in of x stays 1 (bias
+    // gradient); a tile only rewrites the live columns (16-byte cp.async when the row length allows, else scalar).
+    for (int e = tid; e < 2 * kWgTile * kWgLd; e += kWgThreads) {
+        (&sg[0][0])[e] = 0.f;
+        (&sx[0][0])[e] = ((e % kWgLd) == n_in) ? 1.0f : 0.f;
+    }
+    __syncthreads();
+    const bool vec_g = (n_out & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+    const bool vec_x = (n_in & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    auto stage_one = [&](float* dst, const float* __restrict__ src, int ncol, bool vec, int64_t v0, bool ones) {
+        const int rows = (int)((n - v0 < kWgTile) ? (n - v0) : kWgTile);
+        if (vec) {
+            const int per_row = ncol >> 2;
+            for (int e = tid; e < kWgTile * per_row; e += kWgThreads) {
+                const int r = e / per_row, c4 = e - r * per_row;
+                float* d = dst + r * kWgLd + c4 * 4;
+                if (r < rows) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (v0 + r) * ncol + c4 * 4)
+                                 : "memory");
+                } else {
+                    *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else {
+            for (int e = tid; e < kWgTile * ncol; e += kWgThreads) {
+                const int r = e / ncol, c = e - r * ncol;
+                dst[r * kWgLd + c] = (r < rows) ? __ldg(src + (v0 + r) * ncol + c) : 0.f;
+            }
         }
+        if (ones && rows < kWgTile)                                   // tail tile: rows beyond n contribute nothing
+            for (int r = rows + tid; r < kWgTile; r += kWgThreads) dst[r * kWgLd + ncol] = 0.f;
+    };
+    auto stage = [&](int b, int64_t tile_idx) {
+        stage_one(sg[b], g, n_out, vec_g, tile_idx * kWgTile, false);
+        stage_one(sx[b], x, n_in, vec_x, tile_idx * kWgTile, true);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     int buf = 0;
     int64_t tile = blockIdx.x;
     if (tile < tiles) stage(0, tile);
-    __syncthreads();
     for (; tile < tiles; tile += gridDim.x) {
         const int64_t next = tile + gridDim.x;
-        if (next < tiles) stage(buf ^ 1, next);                  // overlaps with the MMAs below (different buffer)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                             // tile `buf` landed; buffer buf^1 is free again
+        if (next < tiles) stage(buf ^ 1, next);                      // in flight while the MMAs below run
         const float* G = sg[buf];
         const float* X = sx[buf];
 #pragma unroll
@@ -87,7 +115,6 @@ __global__ void __launch_bounds__(kWgThreads) k_dense_wgrad(const float* __restr
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], a[mt], b[nt]);
         }
-        __syncthreads();
         buf ^= 1;
     }
     float* out = partial + (int64_t)blockIdx.x * 64 * 64;
