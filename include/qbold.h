@@ -251,6 +251,14 @@ int64_t qbold_dense_wgrad_workspace_floats(void);
 int qbold_dense_wgrad(const float* g, int32_t n_out, const float* x, int32_t n_in, int64_t n, float* dw, float* db,
                       int32_t accumulate, float* workspace, void* stream);
 
+/* Gated residual mix of the encoder blocks (model.py:160-172): out = skip*(1-g) + r*g, g = sigmoid(z + offset);
+ * skip, r, out [n, channels]; z [n, z_channels] with z_channels = channels (channel-wise gating) or 1.
+ * Backward: d_skip, d_r [n, channels], d_z [n, z_channels] from the upstream gradient go. */
+int qbold_gate_mix_forward(const float* skip, const float* r, const float* z, float offset, int64_t n,
+                           int32_t channels, int32_t z_channels, float* out, void* stream);
+int qbold_gate_mix_backward(const float* go, const float* skip, const float* r, const float* z, float offset, int64_t n,
+                            int32_t channels, int32_t z_channels, float* d_skip, float* d_r, float* d_z, void* stream);
+
 /* FP32 FMA micro-benchmark (roofline denominator measured in the same run): launches
  * `iters` dependent-chain FFMA sweeps, returns achieved TFLOP/s through *tflops. */
 int qbold_fma_peak(int32_t iters, double* tflops);

@@ -258,3 +258,79 @@ extern "C" int qbold_diag_kl(const float* pred, int32_t pred_stride, const float
         grad_prior_stride);
     return after_launch("k_diag_kl");
 }
+
+// ---- gated residual mix of the encoder blocks (reference model.py:160-172): out = skip * (1 - g) + r * g with
+// g = sigmoid(z + offset).  One streaming pass forward and one backward instead of ~16 elementwise launches.
+// z has `zc` channels: C (channel-wise gating) or 1 (one gate per voxel).
+namespace qb {
+
+__global__ void __launch_bounds__(kThreads) k_gate_mix_fwd(const float* __restrict__ skip, const float* __restrict__ r,
+                                                           const float* __restrict__ z, float offset, int64_t total,
+                                                           int C, int zc, float* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+        const float zz = __ldg(z + (zc == 1 ? e / C : e)) + offset;
+        const float g = 1.0f / (1.0f + expf(-zz));
+        const float s = __ldg(skip + e), rr = __ldg(r + e);
+        out[e] = s * (1.0f - g) + rr * g;
+    }
+}
+
+// d_skip = go (1 - g), d_r = go g, d_z = go (r - skip) g (1 - g)  (summed over channels when zc == 1: C <= 64 lanes
+// of consecutive threads hold one voxel, reduced with a segmented loop by the first thread of the voxel)
+__global__ void __launch_bounds__(kThreads) k_gate_mix_bwd(const float* __restrict__ go, const float* __restrict__ skip,
+                                                           const float* __restrict__ r, const float* __restrict__ z,
+                                                           float offset, int64_t total, int C, int zc,
+                                                           float* __restrict__ d_skip, float* __restrict__ d_r,
+                                                           float* __restrict__ d_z) {
+    if (zc == 1) {                                                     // one thread per voxel
+        const int64_t nvox = total / C;
+        for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * kThreads) {
+            const float g = 1.0f / (1.0f + expf(-(__ldg(z + v) + offset)));
+            float acc = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const int64_t e = v * C + c;
+                const float o = __ldg(go + e), s = __ldg(skip + e), rr = __ldg(r + e);
+                d_skip[e] = o * (1.0f - g);
+                d_r[e] = o * g;
+                acc += o * (rr - s);
+            }
+            d_z[v] = acc * (g * (1.0f - g));
+        }
+        return;
+    }
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+        const float g = 1.0f / (1.0f + expf(-(__ldg(z + e) + offset)));
+        const float o = __ldg(go + e), s = __ldg(skip + e), rr = __ldg(r + e);
+        d_skip[e] = o * (1.0f - g);
+        d_r[e] = o * g;
+        d_z[e] = o * (rr - s) * (g * (1.0f - g));
+    }
+}
+
+}  // namespace qb
+
+extern "C" int qbold_gate_mix_forward(const float* skip, const float* r, const float* z, float offset, int64_t n,
+                                      int32_t channels, int32_t z_channels, float* out, void* stream) {
+    if (n < 0 || channels < 1 || (z_channels != 1 && z_channels != channels))
+        return fail(QBOLD_EINVAL, "qbold_gate_mix_forward: bad shape");
+    if (n == 0) return QBOLD_OK;
+    if (!skip || !r || !z || !out) return fail(QBOLD_EINVAL, "qbold_gate_mix_forward: null pointer");
+    const int64_t total = n * channels;
+    k_gate_mix_fwd<<<(unsigned)stream_grid(total), kThreads, 0, (cudaStream_t)stream>>>(skip, r, z, offset, total,
+                                                                                        channels, z_channels, out);
+    return after_launch("k_gate_mix_fwd");
+}
+
+extern "C" int qbold_gate_mix_backward(const float* go, const float* skip, const float* r, const float* z, float offset,
+                                       int64_t n, int32_t channels, int32_t z_channels, float* d_skip, float* d_r,
+                                       float* d_z, void* stream) {
+    if (n < 0 || channels < 1 || (z_channels != 1 && z_channels != channels))
+        return fail(QBOLD_EINVAL, "qbold_gate_mix_backward: bad shape");
+    if (n == 0) return QBOLD_OK;
+    if (!go || !skip || !r || !z || !d_skip || !d_r || !d_z)
+        return fail(QBOLD_EINVAL, "qbold_gate_mix_backward: null pointer");
+    const int64_t total = n * channels;
+    k_gate_mix_bwd<<<(unsigned)stream_grid(z_channels == 1 ? n : total), kThreads, 0, (cudaStream_t)stream>>>(
+        go, skip, r, z, offset, total, channels, z_channels, d_skip, d_r, d_z);
+    return after_launch("k_gate_mix_bwd");
+}

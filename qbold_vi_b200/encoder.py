@@ -48,6 +48,46 @@ class _DenseFn(torch.autograd.Function):
         return gx, dw, db
 
 
+class _GateMixFn(torch.autograd.Function):
+    """skip * (1 - g) + r * g with g = sigmoid(z + offset) (model.py:160-172): one streaming kernel each way."""
+
+    @staticmethod
+    def forward(ctx, skip, r, z, offset):
+        from . import _lib
+        from ._lib import check, dptr, stream_ptr
+        skip, r, z = skip.contiguous(), r.contiguous(), z.contiguous()
+        c, zc = r.shape[-1], z.shape[-1]
+        n = r.numel() // c
+        out = torch.empty_like(r)
+        with torch.cuda.device(r.device):
+            check(_lib.lib().qbold_gate_mix_forward(dptr(skip), dptr(r), dptr(z), float(offset), n, c, zc, dptr(out),
+                                                    stream_ptr(r.device)))
+        ctx.save_for_backward(skip, r, z)
+        ctx.offset = float(offset)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        from . import _lib
+        from ._lib import check, dptr, stream_ptr
+        skip, r, z = ctx.saved_tensors
+        go = go.contiguous()
+        c, zc = r.shape[-1], z.shape[-1]
+        n = r.numel() // c
+        d_skip, d_r, d_z = torch.empty_like(skip), torch.empty_like(r), torch.empty_like(z)
+        with torch.cuda.device(r.device):
+            check(_lib.lib().qbold_gate_mix_backward(dptr(go), dptr(skip), dptr(r), dptr(z), ctx.offset, n, c, zc,
+                                                     dptr(d_skip), dptr(d_r), dptr(d_z), stream_ptr(r.device)))
+        return d_skip, d_r, d_z, None
+
+
+def gate_mix(skip, r, z, offset):
+    if r.is_cuda and r.dtype == torch.float32 and skip.dtype == torch.float32 and z.dtype == torch.float32:
+        return _GateMixFn.apply(skip, r, z, offset)
+    g = torch.sigmoid(z + offset)
+    return skip * (1.0 - g) + r * g
+
+
 def dense(layer, x):
     """nn.Linear on the last axis; routes through _DenseFn when training on CUDA in TF32 mode with a supported
     shape (weights contiguous float32, <= 64 outputs, <= 63 inputs), else F.linear."""
@@ -105,8 +145,7 @@ class _Block(nn.Module):
         out1 = self.act(dense(self.pointwise, net1))
         skip = self.act(dense(self.pointwise, net2))
         r = self.conv_b(self.act(self.conv_a(self.act(net2))))
-        g = torch.sigmoid(dense(self.gate, r) + self.gate_offset)
-        return out1, skip * (1.0 - g) + r * g
+        return out1, gate_mix(skip, r, dense(self.gate, r), self.gate_offset)
 
 
 class Encoder(nn.Module):

@@ -986,3 +986,24 @@ def test_dense_weight_gradient_kernel(qb, dev, n, n_in, n_out):
     w.grad = None
     _DenseFn.apply(x, w, b).backward(go)
     assert torch.equal(dw1, w.grad)
+
+
+@pytest.mark.parametrize('zc', [60, 1])
+def test_gate_mix_kernels(qb, dev, zc):
+    """Gated residual mix of the encoder blocks (model.py:160-172) vs the torch expression and its autograd."""
+    from qbold_vi_b200.encoder import gate_mix
+    g0 = torch.Generator().manual_seed(zc)
+    shp = (2, 7, 5, 3, 60)
+    skip, r = (torch.randn(shp, generator=g0).to(dev).requires_grad_(True) for _ in range(2))
+    z = torch.randn(shp[:-1] + (zc,), generator=g0).to(dev).requires_grad_(True)
+    go = torch.randn(shp, generator=g0).to(dev)
+    out = gate_mix(skip, r, z, -3.0)
+    out.backward(go)
+    got = [out.detach().clone(), skip.grad.clone(), r.grad.clone(), z.grad.clone()]
+    for t in (skip, r, z):
+        t.grad = None
+    g = torch.sigmoid(z.double() - 3.0)
+    ref = skip.double() * (1.0 - g) + r.double() * g
+    ref.backward(go.double())
+    for a, b in zip(got, [ref.detach(), skip.grad, r.grad, z.grad]):
+        assert float((a.double() - b.double()).abs().max()) < 1e-5 * max(float(b.abs().max()), 1.0)
