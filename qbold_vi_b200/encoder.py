@@ -23,16 +23,26 @@ class _DenseFn(torch.autograd.Function):
     shape -- is qbold_dense_wgrad (TF32 mma, HBM-bound, deterministic)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        return torch.addmm(bias, x, weight.t())
+    def forward(ctx, x, weight, bias, relu=False):
+        if relu:                                              # bias + ReLU in the GEMM epilogue (cuBLASLt)
+            y = torch._addmm_activation(bias, x, weight.t(), use_gelu=False)
+            ctx.save_for_backward(x, weight, y)
+        else:
+            y = torch.addmm(bias, x, weight.t())
+            ctx.save_for_backward(x, weight)
+        ctx.relu = relu
+        return y
 
     @staticmethod
     def backward(ctx, g):
         import ctypes as C
         from . import _lib
         from ._lib import check, dptr, stream_ptr
-        x, weight = ctx.saved_tensors
+        if ctx.relu:
+            x, weight, y = ctx.saved_tensors
+            g = torch.ops.aten.threshold_backward(g.contiguous(), y, 0.0)
+        else:
+            x, weight = ctx.saved_tensors
         g = g.contiguous()
         gx = g @ weight if ctx.needs_input_grad[0] else None
         dev = x.device
@@ -45,7 +55,7 @@ class _DenseFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib.qbold_dense_wgrad(dptr(g), weight.shape[0], dptr(x), weight.shape[1], x.shape[0], dptr(dw),
                                         dptr(db), 0, dptr(ws), stream_ptr(dev)))
-        return gx, dw, db
+        return gx, dw, db, None
 
 
 class _GateMixFn(torch.autograd.Function):
@@ -88,16 +98,16 @@ def gate_mix(skip, r, z, offset):
     return skip * (1.0 - g) + r * g
 
 
-def dense(layer, x):
-    """nn.Linear on the last axis; routes through _DenseFn when training on CUDA in TF32 mode with a supported
-    shape (weights contiguous float32, <= 64 outputs, <= 63 inputs), else F.linear."""
+def dense(layer, x, relu=False):
+    """nn.Linear on the last axis (optionally followed by ReLU); routes through _DenseFn when training on CUDA in
+    TF32 mode with a supported shape (weights contiguous float32, <= 64 outputs, <= 63 inputs), else F.linear."""
     w, b = layer.weight, layer.bias
     if (x.is_cuda and torch.is_grad_enabled() and w.requires_grad and b is not None and x.dtype == torch.float32
             and torch.backends.cuda.matmul.allow_tf32 and w.shape[0] <= 64 and w.shape[1] <= 63
             and not torch.is_autocast_enabled()):
         lead = x.shape[:-1]
-        return _DenseFn.apply(x.reshape(-1, x.shape[-1]).contiguous(), w, b).reshape(lead + (w.shape[0],))
-    return layer(x)
+        return _DenseFn.apply(x.reshape(-1, x.shape[-1]).contiguous(), w, b, relu).reshape(lead + (w.shape[0],))
+    return F.relu(layer(x)) if relu else layer(x)
 
 
 def _he_normal_(w, fan_in):
@@ -142,8 +152,9 @@ class _Block(nn.Module):
         nn.init.zeros_(self.gate.bias)
 
     def forward(self, net1, net2):
-        out1 = self.act(dense(self.pointwise, net1))
-        skip = self.act(dense(self.pointwise, net2))
+        fuse = self.act is F.relu
+        out1 = dense(self.pointwise, net1, True) if fuse else self.act(dense(self.pointwise, net1))
+        skip = dense(self.pointwise, net2, True) if fuse else self.act(dense(self.pointwise, net2))
         r = self.conv_b(self.act(self.conv_a(self.act(net2))))
         return out1, gate_mix(skip, r, dense(self.gate, r), self.gate_offset)
 
@@ -224,13 +235,16 @@ class Encoder(nn.Module):
     def forward_voxelwise(self, data):
         """Output 0 alone through the torch layers (differentiable): the only output the pre-training loss uses
         (train.py:402-412 compiles the model with a loss on the first output), so the 3x3x1 stream is skipped."""
-        h = self.act(dense(self.first, self.normalise_data(data)))
+        fuse = self.act is F.relu
+        x = self.normalise_data(data)
+        h = dense(self.first, x, True) if fuse else self.act(dense(self.first, x))
         for blk in self.blocks:
-            h = self.act(dense(blk.pointwise, h))
+            h = dense(blk.pointwise, h, True) if fuse else self.act(dense(blk.pointwise, h))
         return dense(self.final, h)
 
     def forward(self, data):
-        h = self.act(dense(self.first, self.normalise_data(data)))
+        x = self.normalise_data(data)
+        h = dense(self.first, x, True) if self.act is F.relu else self.act(dense(self.first, x))
         net1 = net2 = h
         for blk in self.blocks:
             net1, net2 = blk(net1, net2)
