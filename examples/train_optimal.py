@@ -30,6 +30,7 @@ def main():
     a = ap.parse_args()
     rank, world, dev = D.init_distributed()
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True          # let cuDNN pick the 3x3x1 kernels (fixed shapes per run)
     args = qb.optimal_arguments()                                   # configurations/optimal.yaml over train.py defaults
     params = qb.load_system_parameters(qb.config.DEFAULT_CONFIG_PATH)
     params['sample_size'] = '1000'

@@ -3,7 +3,7 @@ sys.path.insert(0, '/root/repo')
 import qbold_vi_b200 as qb
 from qbold_vi_b200 import distributed as D
 from qbold_vi_b200.encoder import create_encoder_from_args
-torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
+torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True; torch.backends.cudnn.benchmark = True
 dev = torch.device('cuda', 0)
 args = qb.optimal_arguments()
 cfg = qb.load_system_parameters(qb.config.DEFAULT_CONFIG_PATH); cfg['simulate_noise'] = 'False'

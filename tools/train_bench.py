@@ -32,6 +32,7 @@ def main():
     a.amp = a.precision == 'bf16'
     torch.backends.cuda.matmul.allow_tf32 = a.precision != 'fp32'
     torch.backends.cudnn.allow_tf32 = a.precision != 'fp32'
+    torch.backends.cudnn.benchmark = bool(int(os.environ.get("QBOLD_CUDNN_BENCHMARK", "1")))
     args = qb.optimal_arguments()
     cfg = qb.load_system_parameters(qb.config.DEFAULT_CONFIG_PATH)
     cfg['simulate_noise'] = 'False'
