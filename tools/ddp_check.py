@@ -41,12 +41,18 @@ def main():
     full = layer(truth)
     assert torch.equal(layer(truth[sl].contiguous()), full[sl])
 
-    def run(sl_, msum):
+    per_volume = mask[0].numel()
+
+    def run(sl_, msum, philox=False):
         bucket = D.FlatGradBucket(enc.parameters())
         bucket.zero_()
         _, q, sigma = enc(data[sl_])
-        loss, info = tr.fused_elbo(layer, q, sigma, data[sl_], mask[sl_], prior[sl_], kl_samples=70,
-                                   eps=eps[sl_], eps_kl=eps_kl[sl_], mask_sum=msum)
+        if philox:      # in-kernel draws: the counter is the GLOBAL voxel index, so shards reproduce the full batch
+            loss, info = tr.fused_elbo(layer, q, sigma, data[sl_], mask[sl_], prior[sl_], kl_samples=70, mask_sum=msum,
+                                       seed=1234, offset=(sl_.start or 0) * per_volume)
+        else:
+            loss, info = tr.fused_elbo(layer, q, sigma, data[sl_], mask[sl_], prior[sl_], kl_samples=70,
+                                       eps=eps[sl_], eps_kl=eps_kl[sl_], mask_sum=msum)
         loss.backward()
         return bucket, loss.detach().double().reshape(1)
 
@@ -59,9 +65,18 @@ def main():
     ref_bucket, ref_loss = run(slice(0, shape[0]), float(mask.sum()))
     err = float((g_sharded - ref_bucket.flat).abs().max() / ref_bucket.flat.abs().max())
     lerr = abs(float(loss) - float(ref_loss)) / abs(float(ref_loss))
+    bucket, loss_p = run(sl, msum, philox=True)
+    bucket.all_reduce_()
+    D.all_reduce_sum_(loss_p)
+    g_philox = bucket.flat.clone()
+    ref_bucket_p, ref_loss_p = run(slice(0, shape[0]), float(mask.sum()), philox=True)
+    err_p = float((g_philox - ref_bucket_p.flat).abs().max() / ref_bucket_p.flat.abs().max())
+    lerr_p = abs(float(loss_p) - float(ref_loss_p)) / abs(float(ref_loss_p))
     if rank == 0:
-        print(json.dumps({'world': world, 'grad_rel_err': err, 'loss_rel_err': lerr, 'loss': float(ref_loss)}))
+        print(json.dumps({'world': world, 'grad_rel_err': err, 'loss_rel_err': lerr, 'loss': float(ref_loss),
+                          'philox_grad_rel_err': err_p, 'philox_loss_rel_err': lerr_p}))
     assert err < 1e-5 and lerr < 1e-6, (err, lerr)
+    assert err_p < 1e-5 and lerr_p < 1e-6, (err_p, lerr_p)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
