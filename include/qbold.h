@@ -244,12 +244,26 @@ int qbold_encoder_mlp_forward(const float* data, const float* blob, int32_t n_in
                               void* stream);
 
 /* Weight / bias gradient of a per-voxel Dense layer (the 1x1x1 convolutions of create_encoder, model.py:122-223):
- * dw[n_out,n_in] = sum_v g[v,:]^T x[v,:], db[n_out] = sum_v g[v,:] (db may be NULL); TF32 mma, fp32 accumulate,
+ * dw[n_out,n_in] = sum_v g'[v,:]^T x[v,:], db[n_out] = sum_v g'[v,:] (db may be NULL), g' = g * [relu_mask > 0];
+ * TF32 mma, fp32 accumulate,
  * deterministic two-stage reduction.  n_out <= 64, n_in <= 63.  workspace: qbold_dense_wgrad_workspace_floats()
  * floats of device scratch.  accumulate != 0 adds into dw / db. */
 int64_t qbold_dense_wgrad_workspace_floats(void);
-int qbold_dense_wgrad(const float* g, int32_t n_out, const float* x, int32_t n_in, int64_t n, float* dw, float* db,
-                      int32_t accumulate, float* workspace, void* stream);
+int qbold_dense_wgrad(const float* g, const float* relu_mask, int32_t n_out, const float* x, int32_t n_in, int64_t n,
+                      float* dw, float* db, int32_t accumulate, float* workspace, void* stream);
+
+/* One Dense layer on the tensor cores (tcgen05 kind::tf32, fp32 accumulate) for the encoder's training passes:
+ * y[n,n_out] = act((x[n,n_in] * [relu_mask > 0]) B^T + bias).  qbold_dense_tc_pack builds the operand image
+ * (qbold_dense_tc_packed_floats() floats, device) from a row-major matrix: transpose = 0: B = w [rows, cols] with
+ * bias [rows] (forward); transpose = 1: B = w^T where w is stored [cols, rows] (input gradient, bias NULL).
+ * relu_mask (may be NULL) has the shape of x: the layer's ReLU output, fusing ReLU' into the input-gradient pass.
+ * n_in, n_out: multiples of 4 in [4, 64]; x, y, relu_mask 16-byte aligned.  relu_mask of qbold_dense_wgrad (may be
+ * NULL, shape of g) does the same for the weight gradient. */
+int qbold_dense_tc_packed_floats(void);
+int qbold_dense_tc_pack(const float* w, const float* bias, int32_t rows, int32_t cols, int32_t transpose, float* packed,
+                        void* stream);
+int qbold_dense_tc(const float* x, const float* relu_mask, const float* packed, int32_t n_in, int32_t n_out, int32_t relu,
+                   int64_t n, float* y, int32_t* status, void* stream);
 
 /* Gated residual mix of the encoder blocks (model.py:160-172): out = skip*(1-g) + r*g, g = sigmoid(z + offset);
  * skip, r, out [n, channels]; z [n, z_channels] with z_channels = channels (channel-wise gating) or 1.

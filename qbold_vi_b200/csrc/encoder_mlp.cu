@@ -379,3 +379,177 @@ extern "C" int qbold_encoder_mlp_forward(const float* data, const float* blob, i
         data, blob, n_in, n_mid, n_out, se_idx, multi_image_normalisation, n, q, status);
     return after_launch("k_encoder_mlp");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One Dense layer on the same machinery, for the TRAINING passes of the encoder:
+//     Y[n, n_out] = act( (X[n, n_in] (* [M > 0])) * B^T + bias ),   B [n_out, n_in] row-major (= K-major)
+// forward: B = W, bias, optional ReLU;  input gradient: X = dY, M = the layer's ReLU output (fuses ReLU'),
+// B = W^T (packed by k_dense_pack with transpose = 1), no bias.  n_in, n_out <= 64 and multiples of 4.
+// HBM-bound (240 B in + 240 B out per voxel for 60 channels); four tile pipelines per CTA as above.
+namespace qb {
+
+namespace {
+constexpr int kDenseWFloats = 2 * kH * kKBlock;      // one 64 x 64 weight tile, 16 KB
+}
+
+// tile[swz(64, r, k)] = transpose ? w[k * ld + r] : w[r * ld + k]   (r < rows, k < cols; rest zero); bias appended
+__global__ void k_dense_pack(const float* __restrict__ w, const float* __restrict__ bias, int rows, int cols,
+                             int transpose, float* __restrict__ tile) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int e = tid; e < kH * kH; e += nth) {
+        const int r = e >> 6, k = e & 63;
+        float v = 0.f;
+        if (r < rows && k < cols) v = transpose ? w[k * rows + r] : w[r * cols + k];
+        tile[swz(kH, r, k)] = v;
+    }
+    for (int e = tid; e < kH; e += nth) tile[kDenseWFloats + e] = (bias != nullptr && e < rows) ? bias[e] : 0.f;
+}
+
+__global__ void __launch_bounds__(kTile * kGroups, 1) k_dense_tc(const float* __restrict__ x, const float* __restrict__ relu_mask,
+                                                                 const float* __restrict__ packed, int n_in, int n_out,
+                                                                 int relu, int64_t n, float* __restrict__ y,
+                                                                 int* __restrict__ status) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const unsigned raw = smem_u32(smem_raw);
+    const unsigned base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    float* sA = reinterpret_cast<float*>(sm);
+    float* sW = sA + kGroups * kATileFloats;
+    float* sBias = sW + kDenseWFloats;
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sBias + kH);
+    unsigned* sTmem = reinterpret_cast<unsigned*>(sBar + kGroups);
+
+    const int warp = threadIdx.x >> 5, group = threadIdx.x / kTile, tid = threadIdx.x % kTile;
+    const unsigned a_base = base + group * (kATileFloats * 4), w_base = base + kGroups * kATileFloats * 4;
+    const unsigned bar = smem_u32(sBar + group);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)),
+                     "r"((unsigned)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(packed);
+        float4* dst = reinterpret_cast<float4*>(sW);
+        for (int i = threadIdx.x; i < (kDenseWFloats + kH) / 4; i += kTile * kGroups) dst[i] = __ldg(src + i);
+        float4* za = reinterpret_cast<float4*>(sA);                       // K padding of the A tiles stays zero
+        for (int i = threadIdx.x; i < kGroups * kATileFloats / 4; i += kTile * kGroups)
+            za[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_async_smem();
+    tc_before_sync();
+    __syncthreads();
+    tc_after_sync();
+    const unsigned tmem_all = *sTmem;
+    const unsigned tmem = tmem_all + group * 64;
+    const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16);
+    const unsigned idesc = instr_desc(kH);
+    const int chunks = n_in >> 2, ksteps = (n_in + 7) >> 3, ochunks = n_out >> 2;
+    unsigned phase = 0;
+    bool ok = true;
+
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    for (int64_t tile = (int64_t)blockIdx.x * kGroups + group; tile < tiles; tile += (int64_t)gridDim.x * kGroups) {
+        const int64_t v0 = tile * kTile;
+        const int rows = (int)((n - v0 < kTile) ? (n - v0) : kTile);
+        // ---- stage the A tile: coalesced 16-byte pieces of the contiguous [rows x n_in] span -> swizzled rows
+        for (int e = tid; e < kTile * chunks; e += kTile) {
+            const int r = e / chunks, c = e - r * chunks;
+            const unsigned dst = a_chunk_addr(a_base, r, c);
+            if (r < rows) {
+                const float* src = x + (v0 + r) * n_in + c * 4;
+                if (relu_mask == nullptr) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                } else {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(relu_mask + (v0 + r) * n_in + c * 4));
+                    sts_f4(dst, m.x > 0.f ? a.x : 0.f, m.y > 0.f ? a.y : 0.f, m.z > 0.f ? a.z : 0.f,
+                           m.w > 0.f ? a.w : 0.f);
+                }
+            } else {
+                sts_f4(dst, 0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        tc_before_sync();
+        fence_async_smem();
+        group_sync(group);
+        if (tid == 0) {
+            tc_after_sync();
+            for (int k = 0; k < ksteps; ++k) {
+                const unsigned ao = a_base + (k >> 2) * (kTile * 128), wo = w_base + (k >> 2) * (kH * 128);
+                umma_tf32(tmem, smem_desc(ao) + 2 * (k & 3), smem_desc(wo) + 2 * (k & 3), idesc, k > 0);
+            }
+            umma_commit(bar);
+        }
+        ok = mbar_wait(bar, phase) && ok;
+        phase ^= 1;
+        tc_after_sync();
+        // ---- epilogue: this thread's row, bias (+ ReLU), 16-byte stores
+        float acc[64];
+#pragma unroll
+        for (int part = 0; part < 4; ++part) tmem_ld16_nowait(taddr + part * 16, acc + part * 16);
+        tmem_ld_wait();
+        if (tid < rows) {
+            float* dst = y + (v0 + tid) * n_out;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < ochunks) {
+                    const float4 b = *reinterpret_cast<const float4*>(sBias + c * 4);
+                    float4 o = make_float4(acc[c * 4] + b.x, acc[c * 4 + 1] + b.y, acc[c * 4 + 2] + b.z,
+                                           acc[c * 4 + 3] + b.w);
+                    if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+                    *reinterpret_cast<float4*>(dst + c * 4) = o;
+                }
+            }
+        }
+        tc_before_sync();            // the next tile's MMA overwrites these TMEM columns: order the loads before it
+        group_sync(group);
+    }
+    if (!ok && status != nullptr) atomicExch(status, 1);
+    tc_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "r"((unsigned)kTmemCols)
+                     : "memory");
+    }
+}
+
+}  // namespace qb
+
+extern "C" int qbold_dense_tc_packed_floats(void) { return kDenseWFloats + kH; }
+
+extern "C" int qbold_dense_tc_pack(const float* w, const float* bias, int32_t rows, int32_t cols, int32_t transpose,
+                                   float* packed, void* stream) {
+    // rows / cols describe the B operand [n_out, n_in] AFTER the optional transpose of the stored matrix
+    if (rows < 1 || rows > kH || cols < 1 || cols > kH) return fail(QBOLD_EUNSUPPORTED, "qbold_dense_tc_pack: <= 64 x 64");
+    if (!w || !packed) return fail(QBOLD_EINVAL, "qbold_dense_tc_pack: null pointer");
+    k_dense_pack<<<16, 256, 0, (cudaStream_t)stream>>>(w, bias, rows, cols, transpose, packed);
+    return after_launch("k_dense_pack");
+}
+
+extern "C" int qbold_dense_tc(const float* x, const float* relu_mask, const float* packed, int32_t n_in, int32_t n_out,
+                              int32_t relu, int64_t n, float* y, int32_t* status, void* stream) {
+    if (n_in < 4 || n_in > kH || (n_in & 3) || n_out < 4 || n_out > kH || (n_out & 3) || n < 0)
+        return fail(QBOLD_EUNSUPPORTED, "qbold_dense_tc: n_in, n_out must be multiples of 4 in [4, 64] (got %d, %d)", n_in,
+                    n_out);
+    if (n == 0) return QBOLD_OK;
+    if (!x || !packed || !y) return fail(QBOLD_EINVAL, "qbold_dense_tc: null pointer");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+        (relu_mask && (reinterpret_cast<uintptr_t>(relu_mask) & 15)))
+        return fail(QBOLD_EINVAL, "qbold_dense_tc: x, y, relu_mask must be 16-byte aligned");
+    const size_t smem = 1024 + (size_t)(kGroups * kATileFloats + kDenseWFloats + kH) * 4 + 8 * kGroups + 16;
+    int rc = cuda_check(cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(k_dense_tc)");
+    if (rc) return rc;
+    const int64_t want = ((n + kTile - 1) / kTile + kGroups - 1) / kGroups;
+    const int64_t cap = (int64_t)sm_count();
+    k_dense_tc<<<(unsigned)(want < cap ? want : cap), kTile * kGroups, smem, (cudaStream_t)stream>>>(
+        x, relu_mask, packed, n_in, n_out, relu, n, y, status);
+    return after_launch("k_dense_tc");
+}

@@ -28,7 +28,8 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], 
 }  // namespace
 
 // g [n, n_out], x [n, n_in] row-major.  partial [gridDim.x, 64, 64]: partial[b][o][i] (column n_in = bias gradient).
-__global__ void __launch_bounds__(kWgThreads) k_dense_wgrad(const float* __restrict__ g, int n_out,
+__global__ void __launch_bounds__(kWgThreads) k_dense_wgrad(const float* __restrict__ g,
+                                                            const float* __restrict__ relu_mask, int n_out,
                                                             const float* __restrict__ x, int n_in, int64_t n,
                                                             float* __restrict__ partial) {
     __shared__ float sg[2][kWgTile * kWgLd];
@@ -56,7 +57,29 @@ __global__ void __launch_bounds__(kWgThreads) k_dense_wgrad(const float* __restr
     const bool vec_x = (n_in & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     auto stage_one = [&](float* dst, const float* __restrict__ src, int ncol, bool vec, int64_t v0, bool ones) {
         const int rows = (int)((n - v0 < kWgTile) ? (n - v0) : kWgTile);
-        if (vec) {
+        if (!ones && relu_mask != nullptr) {                          // g * [relu output > 0]: fuses ReLU' (model.py:152)
+            if (vec && (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0) {
+                const int per_row = ncol >> 2;
+                for (int e = tid; e < kWgTile * per_row; e += kWgThreads) {
+                    const int r = e / per_row, c4 = e - r * per_row;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < rows) {
+                        const int64_t at = (v0 + r) * ncol + c4 * 4;
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(src + at));
+                        const float4 m = __ldg(reinterpret_cast<const float4*>(relu_mask + at));
+                        o = make_float4(m.x > 0.f ? a.x : 0.f, m.y > 0.f ? a.y : 0.f, m.z > 0.f ? a.z : 0.f,
+                                        m.w > 0.f ? a.w : 0.f);
+                    }
+                    *reinterpret_cast<float4*>(dst + r * kWgLd + c4 * 4) = o;
+                }
+            } else {
+                for (int e = tid; e < kWgTile * ncol; e += kWgThreads) {
+                    const int r = e / ncol, c = e - r * ncol;
+                    const int64_t at = (v0 + r) * ncol + c;
+                    dst[r * kWgLd + c] = (r < rows && __ldg(relu_mask + at) > 0.f) ? __ldg(src + at) : 0.f;
+                }
+            }
+        } else if (vec) {
             const int per_row = ncol >> 2;
             for (int e = tid; e < kWgTile * per_row; e += kWgThreads) {
                 const int r = e / per_row, c4 = e - r * per_row;
@@ -153,8 +176,8 @@ using namespace qb;
 
 extern "C" int64_t qbold_dense_wgrad_workspace_floats(void) { return (int64_t)sm_count() * kWgCtasPerSm * 64 * 64; }
 
-extern "C" int qbold_dense_wgrad(const float* g, int32_t n_out, const float* x, int32_t n_in, int64_t n, float* dw,
-                                 float* db, int32_t accumulate, float* workspace, void* stream) {
+extern "C" int qbold_dense_wgrad(const float* g, const float* relu_mask, int32_t n_out, const float* x, int32_t n_in,
+                                 int64_t n, float* dw, float* db, int32_t accumulate, float* workspace, void* stream) {
     if (n_out < 1 || n_out > 64 || n_in < 1 || n_in > 63 || n < 0)
         return fail(QBOLD_EUNSUPPORTED, "qbold_dense_wgrad: supports n_out <= 64, n_in <= 63 (got %d, %d)", n_out, n_in);
     if (!g || !x || !dw || !workspace) return fail(QBOLD_EINVAL, "qbold_dense_wgrad: null pointer");
@@ -162,7 +185,7 @@ extern "C" int qbold_dense_wgrad(const float* g, int32_t n_out, const float* x, 
     int64_t grid = (int64_t)sm_count() * kWgCtasPerSm;
     if (tiles < grid) grid = tiles;
     if (grid < 1) grid = 1;
-    k_dense_wgrad<<<(unsigned)grid, kWgThreads, 0, (cudaStream_t)stream>>>(g, n_out, x, n_in, n, workspace);
+    k_dense_wgrad<<<(unsigned)grid, kWgThreads, 0, (cudaStream_t)stream>>>(g, relu_mask, n_out, x, n_in, n, workspace);
     int rc = after_launch("k_dense_wgrad");
     if (rc) return rc;
     k_dense_wgrad_reduce<<<16, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid, n_out, n_in, dw, db, accumulate);

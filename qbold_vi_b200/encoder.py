@@ -8,6 +8,7 @@ are what the per-step NCCL all-reduce carries.  Layout is the reference's channe
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -17,43 +18,97 @@ import torch.nn.functional as F
 _WGRAD_WS = {}
 
 
+_TC_STATUS = {}
+
+
+# The single-layer tcgen05 kernel (qbold_dense_tc) is correct but, at 16 warps per SM, latency-bound at ~75 us per
+# 524 288 x 60 layer -- level with cuBLAS (64-104 us), not ahead of it -- so the library GEMMs stay the default for the
+# forward / input-gradient passes; QBOLD_DENSE_TC=1 (or this flag) routes them through the kernel.
+USE_DENSE_TC = os.environ.get('QBOLD_DENSE_TC', '0') == '1'
+
+
+def _tc_ok(n_in, n_out, *tensors):
+    """Shapes the tcgen05 Dense kernel takes: multiples of 4 up to 64, 16-byte aligned operands."""
+    return (n_in % 4 == 0 and n_out % 4 == 0 and 4 <= n_in <= 64 and 4 <= n_out <= 64
+            and all(t.data_ptr() % 16 == 0 for t in tensors))
+
+
+def _dense_tc(x, mask, w, bias, n_in, n_out, transpose, relu):
+    """y = act((x * [mask > 0]) B^T + bias) through qbold_dense_tc; B = w (transpose=False) or w^T."""
+    from . import _lib
+    from ._lib import check, dptr, stream_ptr
+    lib = _lib.lib()
+    dev = x.device
+    packed = torch.empty(int(lib.qbold_dense_tc_packed_floats()), dtype=torch.float32, device=dev)
+    y = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=dev)
+    status = _TC_STATUS.get(dev)
+    if status is None:
+        status = _TC_STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = stream_ptr(dev)
+        check(lib.qbold_dense_tc_pack(dptr(w), dptr(bias, allow_none=True), n_out, n_in, int(transpose), dptr(packed), st))
+        check(lib.qbold_dense_tc(dptr(x), dptr(mask, allow_none=True), dptr(packed), n_in, n_out, int(relu), x.shape[0],
+                                 dptr(y), dptr(status, torch.int32), st))
+    return y
+
+
+def tensor_core_status(device):
+    """Non-zero if a tcgen05 completion barrier of the Dense kernels ever timed out on `device` (checked lazily: the
+    training loop never synchronises on it)."""
+    s = _TC_STATUS.get(torch.device(device))
+    return 0 if s is None else int(s.item())
+
+
 class _DenseFn(torch.autograd.Function):
-    """y = x W^T + b for a per-voxel Dense layer (N ~ 10^5..10^6 rows, <= 64 features).  Forward and input gradient
-    are library GEMMs; the weight / bias gradient -- a reduction over all voxels that cuBLAS serves poorly at this
-    shape -- is qbold_dense_wgrad (TF32 mma, HBM-bound, deterministic)."""
+    """y = act(x W^T + b) for a per-voxel Dense layer (N ~ 10^5..10^6 rows, <= 64 features).  Forward and input
+    gradient run on the tcgen05 kernel (qbold_dense_tc, ReLU and ReLU' fused) when the shape allows, else on library
+    GEMMs; the weight / bias gradient -- a reduction over all voxels that cuBLAS serves poorly at this shape -- is
+    qbold_dense_wgrad (TF32 mma, HBM-bound, deterministic)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, relu=False):
-        if relu:                                              # bias + ReLU in the GEMM epilogue (cuBLASLt)
+        n_out, n_in = weight.shape
+        if USE_DENSE_TC and _tc_ok(n_in, n_out, x):
+            y = _dense_tc(x, None, weight, bias, n_in, n_out, False, relu)
+        elif relu:                                            # bias + ReLU in the GEMM epilogue (cuBLASLt)
             y = torch._addmm_activation(bias, x, weight.t(), use_gelu=False)
-            ctx.save_for_backward(x, weight, y)
         else:
             y = torch.addmm(bias, x, weight.t())
+        if relu:
+            ctx.save_for_backward(x, weight, y)
+        else:
             ctx.save_for_backward(x, weight)
         ctx.relu = relu
         return y
 
     @staticmethod
     def backward(ctx, g):
-        import ctypes as C
         from . import _lib
         from ._lib import check, dptr, stream_ptr
         if ctx.relu:
             x, weight, y = ctx.saved_tensors
-            g = torch.ops.aten.threshold_backward(g.contiguous(), y, 0.0)
         else:
-            x, weight = ctx.saved_tensors
+            (x, weight), y = ctx.saved_tensors, None
         g = g.contiguous()
-        gx = g @ weight if ctx.needs_input_grad[0] else None
+        n_out, n_in = weight.shape
         dev = x.device
+        gx, mask = None, y
+        if USE_DENSE_TC and _tc_ok(n_out, n_in, g) and (y is None or y.data_ptr() % 16 == 0):
+            if ctx.needs_input_grad[0]:
+                gx = _dense_tc(g, y, weight, None, n_out, n_in, True, False)          # (g * relu') W, relu' fused
+        else:
+            if y is not None:                                 # library path: materialise g * relu' once for both uses
+                g, mask = torch.ops.aten.threshold_backward(g, y, 0.0), None
+            if ctx.needs_input_grad[0]:
+                gx = g @ weight
         lib = _lib.lib()
         ws = _WGRAD_WS.get(dev)
         if ws is None:
             ws = _WGRAD_WS[dev] = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
         dw = torch.empty_like(weight)
-        db = torch.empty(weight.shape[0], dtype=torch.float32, device=dev)
+        db = torch.empty(n_out, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib.qbold_dense_wgrad(dptr(g), weight.shape[0], dptr(x), weight.shape[1], x.shape[0], dptr(dw),
+            check(lib.qbold_dense_wgrad(dptr(g), dptr(mask, allow_none=True), n_out, dptr(x), n_in, x.shape[0], dptr(dw),
                                         dptr(db), 0, dptr(ws), stream_ptr(dev)))
         return gx, dw, db, None
 

@@ -961,6 +961,35 @@ def test_fused_elbo_full_size_properties(qb, dev, cfg_noise_off):
     assert abs(float(d.mean())) < 5.0 * float(d.std()) / (d.numel() ** 0.5) + 1e-4 * float(info0['kl_map'].mean())
 
 
+@pytest.mark.parametrize('relu', [False, True])
+@pytest.mark.parametrize('n,n_in,n_out', [(5000, 60, 60), (70001, 56, 12), (129, 8, 64), (1, 4, 4)])
+def test_dense_tensor_core_forward_and_input_gradient(qb, dev, monkeypatch, n, n_in, n_out, relu):
+    """qbold_dense_tc (tcgen05 TF32): y = act(x W^T + b) and dx = (g * relu') W vs float64."""
+    from qbold_vi_b200 import encoder as E
+    from qbold_vi_b200.encoder import _DenseFn, _tc_ok, tensor_core_status
+    monkeypatch.setattr(E, 'USE_DENSE_TC', True)
+    g0 = torch.Generator().manual_seed(n + n_out)
+    x = torch.randn((n, n_in), generator=g0).to(dev).requires_grad_(True)
+    w = (torch.randn((n_out, n_in), generator=g0) * 0.3).to(dev).requires_grad_(True)
+    b = torch.randn(n_out, generator=g0).to(dev).requires_grad_(True)
+    go = torch.randn((n, n_out), generator=g0).to(dev)
+    assert _tc_ok(n_in, n_out, x)
+    y = _DenseFn.apply(x, w, b, relu)
+    y.backward(go)
+    x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    z = x64 @ w64.t() + b64
+    ref = torch.relu(z) if relu else z
+    # the kernel decides relu' from ITS OWN output; compare gradients with the same mask (TF32 can flip near-zero z)
+    mask = (y.detach() > 0).double() if relu else torch.ones_like(z)
+    scale = float(ref.abs().max())
+    assert float((y.double() - ref).abs().max()) < 4e-3 * max(scale, 1.0)
+    gz = go.double() * mask
+    assert float((x.grad.double() - gz @ w64).abs().max()) < 4e-3 * max(float((gz @ w64).abs().max()), 1.0)
+    assert float((w.grad.double() - gz.t() @ x64).abs().max()) < 4e-3 * max(float((gz.t() @ x64).abs().max()), 1.0)
+    assert float((b.grad.double() - gz.sum(0)).abs().max()) < 4e-3 * max(float(gz.sum(0).abs().max()), 1.0)
+    assert tensor_core_status(dev) == 0
+
+
 @pytest.mark.parametrize('n,n_in,n_out', [(5000, 11, 60), (70001, 60, 60), (333, 60, 5), (31, 60, 11), (1, 63, 64)])
 def test_dense_weight_gradient_kernel(qb, dev, n, n_in, n_out):
     """qbold_dense_wgrad (TF32 mma, fp32 accumulate) vs float64 matmul; the encoder routes its Dense layers through it."""
