@@ -264,6 +264,36 @@ extern "C" int qbold_diag_kl(const float* pred, int32_t pred_stride, const float
 // z has `zc` channels: C (channel-wise gating) or 1 (one gate per voxel).
 namespace qb {
 
+__device__ __forceinline__ float gate_of(float z, float offset) { return 1.0f / (1.0f + expf(-(z + offset))); }
+
+// 16-byte variants for channel-wise gating (same shapes for all operands, total % 4 == 0, aligned pointers)
+__global__ void __launch_bounds__(kThreads) k_gate_mix_fwd4(const float4* __restrict__ skip, const float4* __restrict__ r,
+                                                            const float4* __restrict__ z, float offset, int64_t total4,
+                                                            float4* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total4; e += (int64_t)gridDim.x * kThreads) {
+        const float4 zz = __ldg(z + e), s = __ldg(skip + e), rr = __ldg(r + e);
+        const float g0 = gate_of(zz.x, offset), g1 = gate_of(zz.y, offset), g2 = gate_of(zz.z, offset),
+                    g3 = gate_of(zz.w, offset);
+        out[e] = make_float4(s.x * (1.0f - g0) + rr.x * g0, s.y * (1.0f - g1) + rr.y * g1,
+                             s.z * (1.0f - g2) + rr.z * g2, s.w * (1.0f - g3) + rr.w * g3);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_gate_mix_bwd4(const float4* __restrict__ go, const float4* __restrict__ skip,
+                                                            const float4* __restrict__ r, const float4* __restrict__ z,
+                                                            float offset, int64_t total4, float4* __restrict__ d_skip,
+                                                            float4* __restrict__ d_r, float4* __restrict__ d_z) {
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total4; e += (int64_t)gridDim.x * kThreads) {
+        const float4 zz = __ldg(z + e), s = __ldg(skip + e), rr = __ldg(r + e), o = __ldg(go + e);
+        const float g0 = gate_of(zz.x, offset), g1 = gate_of(zz.y, offset), g2 = gate_of(zz.z, offset),
+                    g3 = gate_of(zz.w, offset);
+        d_skip[e] = make_float4(o.x * (1.0f - g0), o.y * (1.0f - g1), o.z * (1.0f - g2), o.w * (1.0f - g3));
+        d_r[e] = make_float4(o.x * g0, o.y * g1, o.z * g2, o.w * g3);
+        d_z[e] = make_float4(o.x * (rr.x - s.x) * (g0 * (1.0f - g0)), o.y * (rr.y - s.y) * (g1 * (1.0f - g1)),
+                             o.z * (rr.z - s.z) * (g2 * (1.0f - g2)), o.w * (rr.w - s.w) * (g3 * (1.0f - g3)));
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_gate_mix_fwd(const float* __restrict__ skip, const float* __restrict__ r,
                                                            const float* __restrict__ z, float offset, int64_t total,
                                                            int C, int zc, float* __restrict__ out) {
@@ -316,6 +346,13 @@ extern "C" int qbold_gate_mix_forward(const float* skip, const float* r, const f
     if (n == 0) return QBOLD_OK;
     if (!skip || !r || !z || !out) return fail(QBOLD_EINVAL, "qbold_gate_mix_forward: null pointer");
     const int64_t total = n * channels;
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (z_channels == channels && (total & 3) == 0 && al(skip) && al(r) && al(z) && al(out)) {
+        k_gate_mix_fwd4<<<(unsigned)stream_grid(total / 4), kThreads, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(skip), reinterpret_cast<const float4*>(r), reinterpret_cast<const float4*>(z),
+            offset, total / 4, reinterpret_cast<float4*>(out));
+        return after_launch("k_gate_mix_fwd4");
+    }
     k_gate_mix_fwd<<<(unsigned)stream_grid(total), kThreads, 0, (cudaStream_t)stream>>>(skip, r, z, offset, total,
                                                                                         channels, z_channels, out);
     return after_launch("k_gate_mix_fwd");
@@ -330,6 +367,15 @@ extern "C" int qbold_gate_mix_backward(const float* go, const float* skip, const
     if (!go || !skip || !r || !z || !d_skip || !d_r || !d_z)
         return fail(QBOLD_EINVAL, "qbold_gate_mix_backward: null pointer");
     const int64_t total = n * channels;
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (z_channels == channels && (total & 3) == 0 && al(go) && al(skip) && al(r) && al(z) && al(d_skip) && al(d_r) &&
+        al(d_z)) {
+        k_gate_mix_bwd4<<<(unsigned)stream_grid(total / 4), kThreads, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(go), reinterpret_cast<const float4*>(skip), reinterpret_cast<const float4*>(r),
+            reinterpret_cast<const float4*>(z), offset, total / 4, reinterpret_cast<float4*>(d_skip),
+            reinterpret_cast<float4*>(d_r), reinterpret_cast<float4*>(d_z));
+        return after_launch("k_gate_mix_bwd4");
+    }
     k_gate_mix_bwd<<<(unsigned)stream_grid(z_channels == 1 ? n : total), kThreads, 0, (cudaStream_t)stream>>>(
         go, skip, r, z, offset, total, channels, z_channels, d_skip, d_r, d_z);
     return after_launch("k_gate_mix_bwd");
