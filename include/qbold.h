@@ -151,6 +151,13 @@ int qbold_add_noise(const QboldParams* p, float* signal, int64_t n, const float*
                     const float* snr_u01, const float* eps, uint64_t seed, uint64_t offset,
                     void* stream);
 
+/* The noise loop of create_synthetic_dataset (signals.py:282-285) for all chunks at once: signal [n_chunks*chunk_rows,
+ * n_tau] in place, every chunk uses ITS OWN column means, row v draws with counter offset + v.  scratch: 32*n_chunks
+ * doubles of device memory.  Same draws and arithmetic as qbold_column_mean + qbold_add_noise per chunk. */
+int qbold_add_noise_chunked(const QboldParams* p, float* signal, int64_t chunk_rows, int32_t n_chunks,
+                            const float* snr_u01, const float* eps, uint64_t seed, uint64_t offset, double* scratch,
+                            void* stream);
+
 /* Replaces the body of create_synthetic_dataset (signals.py:270-299) for rows
  * [first, first+count) of the shuffled OEF x DBV meshgrid: labels y3 = (OEF, DBV, R2')
  * and the clean signal x.  perm (int64 [n_oef*n_dbv]) is an explicit shuffle, or NULL ->

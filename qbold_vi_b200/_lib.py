@@ -64,6 +64,8 @@ _SIGNATURES = {
     'qbold_reparam_sample': (C.c_int, [_f, _f, C.c_uint64, C.c_uint64, C.c_int64, _f, C.c_void_p]),
     'qbold_column_mean': (C.c_int, [_f, C.c_int64, C.c_int32, _f, _f, C.c_void_p]),
     'qbold_add_noise': (C.c_int, [_P(QboldParams), _f, C.c_int64, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_void_p]),
+    'qbold_add_noise_chunked': (C.c_int, [_P(QboldParams), _f, C.c_int64, C.c_int32, _f, _f, C.c_uint64, C.c_uint64, _f,
+                                          C.c_void_p]),
     'qbold_generate': (C.c_int, [_P(QboldParams), _f, C.c_int64, _f, C.c_int64, _f, C.c_uint64, C.c_int64, C.c_int64,
                                  _f, _f, C.c_void_p]),
     'qbold_elbo_fused': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32,

@@ -215,9 +215,104 @@ __global__ void __launch_bounds__(kThreads) k_add_noise(const __grid_constant__ 
     }
 }
 
+// All chunks of create_synthetic_dataset's noise loop (signals.py:282-285: every chunk of S^2/10 rows is one forward
+// call, so the noise std uses THAT chunk's column means) in two launches: blockIdx.y = chunk for the column sums,
+// then one noise pass that looks its chunk's sums up.  Same per-row draws and arithmetic as k_add_noise.
+__global__ void __launch_bounds__(kThreads) k_column_sum_chunked(const float* __restrict__ sig, int64_t chunk_rows, int nt,
+                                                                 double* __restrict__ sums) {
+    __shared__ float part[kThreads / 32][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float* base = sig + (int64_t)blockIdx.y * chunk_rows * nt;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + w;
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    float acc = 0.f, comp = 0.f;
+    if (lane < nt) {
+        for (int64_t r = warp; r < chunk_rows; r += nwarps) {
+            const float yv = __ldg(base + r * nt + lane) - comp;
+            const float t = acc + yv;
+            comp = (t - acc) - yv;
+            acc = t;
+        }
+    }
+    part[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && lane < nt) {
+        double tot = 0.0;
+        for (int k = 0; k < kThreads / 32; ++k) tot += (double)part[k][lane];
+        atomicAdd(sums + blockIdx.y * 32 + lane, tot);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_add_noise_chunked(const __grid_constant__ QboldParams P,
+                                                                float* __restrict__ sig, int64_t n, int64_t chunk_rows,
+                                                                const double* __restrict__ sums,
+                                                                const float* __restrict__ snr_u01,
+                                                                const float* __restrict__ eps, uint64_t seed,
+                                                                uint64_t offset) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int nt = P.n_tau;
+    const double* cs = sums + (v / chunk_rows) * 32;
+    float u;
+    if (snr_u01) {
+        u = snr_u01[v];
+    } else {
+        const U4 r = philox4x32_10((uint32_t)(offset + v), (uint32_t)((offset + v) >> 32), kStreamSnr, 0u,
+                                   (uint32_t)seed, (uint32_t)(seed >> 32));
+        u = u01(r.x);
+    }
+    const float snr0 = u * (120.0f - 50.0f) + 50.0f;
+    for (int t = 0; t < nt; t += 2) {
+        float n0, n1;
+        if (eps) {
+            n0 = eps[v * nt + t];
+            n1 = (t + 1 < nt) ? eps[v * nt + t + 1] : 0.f;
+        } else {
+            normal_pair(seed, offset + (uint64_t)v, kStreamNoise + (uint32_t)(t >> 1), n0, n1);
+        }
+        const float m0 = (float)(cs[t] / (double)chunk_rows);
+        sig[v * nt + t] = sig[v * nt + t] + n0 * (m0 / (snr0 * P.norm_snr[t]));
+        if (t + 1 < nt) {
+            const float m1 = (float)(cs[t + 1] / (double)chunk_rows);
+            sig[v * nt + t + 1] = sig[v * nt + t + 1] + n1 * (m1 / (snr0 * P.norm_snr[t + 1]));
+        }
+    }
+}
+
 }  // namespace qb
 
 using namespace qb;
+
+extern "C" int qbold_add_noise_chunked(const QboldParams* p, float* signal, int64_t chunk_rows, int32_t n_chunks,
+                                       const float* snr_u01, const float* eps, uint64_t seed, uint64_t offset,
+                                       double* scratch, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION)
+        return fail(QBOLD_EINVAL, "qbold_add_noise_chunked: bad params block");
+    if (p->norm_snr[0] == 0.0f)
+        return fail(QBOLD_EUNSUPPORTED,
+                    "norm_snr is only defined for 11 or 24 taus (reference signals.py:117-121), got %d", p->n_tau);
+    if ((snr_u01 == nullptr) != (eps == nullptr))
+        return fail(QBOLD_EINVAL, "qbold_add_noise_chunked: pass both snr_u01 and eps, or neither");
+    if (chunk_rows < 0 || n_chunks < 0 || n_chunks > 65535)
+        return fail(QBOLD_EINVAL, "qbold_add_noise_chunked: bad chunking");
+    const int64_t n = chunk_rows * n_chunks;
+    if (n == 0) return QBOLD_OK;
+    if (!signal || !scratch) return fail(QBOLD_EINVAL, "qbold_add_noise_chunked: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cuda_check(cudaMemsetAsync(scratch, 0, sizeof(double) * 32 * n_chunks, st), "cudaMemsetAsync");
+    if (rc) return rc;
+    int64_t gx = (chunk_rows + 8 * 64 - 1) / (8 * 64);
+    const int64_t cap = ((int64_t)sm_count() * 8 + n_chunks - 1) / n_chunks;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    k_column_sum_chunked<<<dim3((unsigned)gx, (unsigned)n_chunks), kThreads, 0, st>>>(signal, chunk_rows, p->n_tau,
+                                                                                    scratch);
+    rc = after_launch("k_column_sum_chunked");
+    if (rc) return rc;
+    k_add_noise_chunked<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(*p, signal, n, chunk_rows, scratch,
+                                                                                       snr_u01, eps, seed, offset);
+    return after_launch("k_add_noise_chunked");
+}
 
 extern "C" int qbold_generate(const QboldParams* p, const float* oefs, int64_t n_oef, const float* dbvs,
                               int64_t n_dbv, const int64_t* perm, uint64_t seed, int64_t first, int64_t count,

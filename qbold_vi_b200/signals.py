@@ -280,14 +280,20 @@ def generate_from_marginals(sig_layer, oefs, dbvs, perm=None, n_chunks=10, snr_u
         if total > n_x:
             check(lib.qbold_generate(C.byref(sig_layer.params), dptr(oefs), oefs.numel(), dptr(dbvs), dbvs.numel(),
                                      pptr, seed, n_x, total - n_x, None, dptr(train_y[n_x:]), st))
-    if sig_layer._simulate_noise:
-        for i in range(n_chunks):
-            if chunk == 0:
-                break
-            sl = slice(i * chunk, (i + 1) * chunk)
-            sig_layer.add_noise(train_x[sl], None if snr_u01 is None else snr_u01[sl].contiguous(),
-                                None if noise_eps is None else noise_eps[sl].contiguous(),
-                                seed=seed ^ 0x5DEECE66D, offset=i * chunk, inplace=True)
+    if sig_layer._simulate_noise and chunk > 0:
+        # every chunk is one forward call in the reference, so its noise std uses that chunk's column means (:126)
+        if sig_layer.params.norm_snr[0] == 0.0:
+            raise UnboundLocalError("local variable 'norm_snr' referenced before assignment "
+                                    "(only 11 or 24 taus are supported, signals.py:117-121)")
+        scratch = torch.empty(32 * n_chunks, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.qbold_add_noise_chunked(C.byref(sig_layer.params), dptr(train_x), chunk, n_chunks,
+                                              dptr(None if snr_u01 is None else snr_u01[:n_x].contiguous(),
+                                                   allow_none=True),
+                                              dptr(None if noise_eps is None else noise_eps[:n_x].contiguous(),
+                                                   allow_none=True),
+                                              (seed ^ 0x5DEECE66D) & 0xFFFFFFFFFFFFFFFF, 0, dptr(scratch, torch.float64),
+                                              stream_ptr(dev)))
     return train_x, train_y
 
 
