@@ -44,6 +44,17 @@ int sm_count() {
     return cached;
 }
 
+__device__ unsigned long long g_work_counters[64];
+
+unsigned long long* next_work_counter(cudaStream_t stream) {
+    static std::atomic<unsigned> turn{0};
+    void* base = nullptr;
+    if (cudaGetSymbolAddress(&base, g_work_counters) != cudaSuccess) return nullptr;     // per current device
+    unsigned long long* c = static_cast<unsigned long long*>(base) + (turn.fetch_add(1) & 63u);
+    if (cudaMemsetAsync(c, 0, sizeof(unsigned long long), stream) != cudaSuccess) return nullptr;
+    return c;
+}
+
 // float32 exp of a Python-float argument, as tf.math.exp(<python float>) gives it:
 // the argument is first converted to float32, the result is the float32 nearest exp().
 static float expf_of(double x) { return (float)std::exp((double)(float)x); }

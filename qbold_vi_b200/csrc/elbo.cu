@@ -460,13 +460,12 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
                                                            uint64_t offset, int kl_samples, float inv_mask_sum,
                                                            float kl_weight, int64_t n, float* __restrict__ grad_q,
                                                            float* __restrict__ grad_sigma, float* __restrict__ nll_map,
-                                                           float* __restrict__ kl_map, double* __restrict__ sums) {
+                                                           float* __restrict__ kl_map, double* __restrict__ sums,
+                                                           unsigned long long* __restrict__ work) {
     __shared__ SchedSmem ss;
     load_sched(P, ss);
     __syncthreads();
     const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15, gb = lane & 16;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
     const int nt = P.n_tau;
     const bool live = t < nt;
     const int my_col = live ? P.col_of_tau[t] : -1;
@@ -482,7 +481,9 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
     int bad = 0;
 
-    for (int64_t pr = warp; pr < npairs; pr += nwarps) {
+    // pairs come from the device work counter (masked volumes: see next_unit); the next index is fetched early
+    for (int64_t pr = next_unit(work, lane), nxt; pr < npairs; pr = nxt) {
+        nxt = next_unit(work, lane);
         int64_t v = pr * 2 + half;
         const bool valid = v < n;
         if (!valid) v = n - 1;                               // odd tail: mirror the last voxel, store nothing
@@ -706,13 +707,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_nll_map_pair(const __grid_const
                                                               const float* __restrict__ y, const float* __restrict__ mask,
                                                               const float* __restrict__ eps, uint64_t seed,
                                                               uint64_t offset, int n_samples, int64_t n,
-                                                              float* __restrict__ nll_map) {
+                                                              float* __restrict__ nll_map,
+                                                              unsigned long long* __restrict__ work) {
     __shared__ SchedSmem ss;
     load_sched(P, ss);
     __syncthreads();
     const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15, gb = lane & 16;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
     const int nt = P.n_tau;
     const bool live = t < nt;
     const int my_col = live ? P.col_of_tau[t] : -1;
@@ -724,7 +724,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_nll_map_pair(const __grid_const
     const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
     const float df = P.student_t_df;
     const QuadCtx qc = make_quad_ctx<kSched>(P, ss, lane, my_col, my_tau);
-    for (int64_t v = warp; v < n; v += nwarps) {
+    // one voxel (n_samples forward passes) per grab; the next index is fetched before the current voxel is processed
+    for (int64_t v = next_unit(work, lane), nxt; v < n; v = nxt) {
+        nxt = next_unit(work, lane);
         const float m = mask ? __ldg(mask + v) : 1.0f;
         if (!(m != 0.0f)) {
             if (lane == 0) nll_map[v] = 0.f;
@@ -1005,18 +1007,20 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
     } while (0)
     if (path == kSched && p->full_model && p->n_tau <= 16) {
         const int64_t wantp = ((n + 1) / 2 + 7) / 8;
+        unsigned long long* work = next_work_counter(st);
+        if (!work) return fail(QBOLD_ECUDA, "qbold_elbo_fused: work counter unavailable");
         if (prior) {
             static int64_t grid_cache = 0;
             const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<true>, INT64_MAX / 64));
             k_elbo_pair<true><<<(unsigned)(wantp < grid ? wantp : grid), kThreads, 0, st>>>(
                 *p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, kl_weight, n, grad_q,
-                grad_sigma, nll_map, kl_map, sums);
+                grad_sigma, nll_map, kl_map, sums, work);
         } else {
             static int64_t grid_cache = 0;
             const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<false>, INT64_MAX / 64));
             k_elbo_pair<false><<<(unsigned)(wantp < grid ? wantp : grid), kThreads, 0, st>>>(
                 *p, q, sigma, y, mask, nullptr, eps, nullptr, seed, offset, 0, inv_mask_sum, kl_weight, n, grad_q,
-                grad_sigma, nll_map, kl_map, sums);
+                grad_sigma, nll_map, kl_map, sums, work);
         }
     } else if (prior) {
         if (path == kSched) QB_LAUNCH_ELBO(true, kSched);
@@ -1065,8 +1069,10 @@ extern "C" int qbold_nll_map(const QboldParams* p, const float* q, const float* 
     if (path == kSched && p->full_model && p->n_tau <= 16) {
         static int64_t grid_cache = 0;
         const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_nll_map_pair, INT64_MAX / 64));
+        unsigned long long* work = next_work_counter(st);
+        if (!work) return fail(QBOLD_ECUDA, "qbold_nll_map: work counter unavailable");
         k_nll_map_pair<<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(*p, q, sigma, y, mask, eps, seed,
-                                                                                  offset, n_samples, n, nll_map);
+                                                                                  offset, n_samples, n, nll_map, work);
     } else if (path == kSched) QB_LAUNCH_NLL(kSched);
     else if (path == kCols) QB_LAUNCH_NLL(kCols);
     else QB_LAUNCH_NLL(kColsMulti);

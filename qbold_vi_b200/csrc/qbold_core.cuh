@@ -238,6 +238,15 @@ __device__ __forceinline__ TauSignal tau_signal(const QboldParams& P, const Voxe
     return r;
 }
 
+// Dynamic work distribution for kernels with uneven per-unit cost (a masked voxel costs nothing, a live one tens of
+// microseconds; with a static warp stride that is a multiple of the volume's z extent whole warps only ever see
+// voxels outside the mask).  Lane 0 takes the next unit from a device counter, the warp follows.
+__device__ __forceinline__ int64_t next_unit(unsigned long long* counter, int lane) {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(counter, 1ull);
+    return (int64_t)__shfl_sync(kFull, v, 0);
+}
+
 // FP32 artefact of the reference at quadrature node 0: TensorFlow evaluates
 // 1 - j0f(x0) with the Cephes tiny-argument branch 1 - 0.25 x0^2, which rounds to exactly 1
 // (so the node contributes 0) for every admissible voxel.  Reproduced literally so that
