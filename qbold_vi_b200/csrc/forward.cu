@@ -67,13 +67,12 @@ __global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward_pair(co
                                                                               const float* __restrict__ oef_dbv,
                                                                               const float* __restrict__ g_signal,
                                                                               float* __restrict__ signal,
-                                                                              float* __restrict__ g_oef_dbv, int64_t n) {
+                                                                              float* __restrict__ g_oef_dbv, int64_t n,
+                                                                              unsigned long long* __restrict__ work) {
     __shared__ SchedSmem ss;
     load_sched(P, ss);
     __syncthreads();
     const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
     const int nt = P.n_tau;
     const bool live = t < nt;
     const int my_col = live ? P.col_of_tau[t] : -1;
@@ -82,7 +81,10 @@ __global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward_pair(co
     const QuadCtx qc = make_quad_ctx<kSched>(P, ss, lane, my_col, my_tau);
     const int64_t npairs = (n + 1) >> 1;
 
-    for (int64_t pr = warp; pr < npairs; pr += nwarps) {
+    // pairs come from a device work counter (next index fetched before the current pair is processed): warps that
+    // run ahead simply take more pairs, which evens out SM-to-SM rate differences and the tail of the launch
+    for (int64_t pr = next_unit(work, lane), nxt; pr < npairs; pr = nxt) {
+        nxt = next_unit(work, lane);
         const int64_t v = pr * 2 + half;
         const bool valid = v < n;
         float2 x = make_float2(0.f, 0.f);
@@ -134,7 +136,9 @@ static int launch_forward_pair(const QboldParams* p, const float* oef_dbv, const
     int64_t grid = (int64_t)sm_count() * blocks_per_sm;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k_forward_pair<BWD><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n);
+    unsigned long long* work = next_work_counter(st);
+    if (!work) return fail(QBOLD_ECUDA, "qbold_forward: work counter unavailable");
+    k_forward_pair<BWD><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n, work);
     return after_launch("k_forward_pair");
 }
 
