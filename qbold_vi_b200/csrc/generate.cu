@@ -104,13 +104,12 @@ __global__ void __launch_bounds__(kThreads, 5) k_generate_pair(const __grid_cons
                                                                const float* __restrict__ dbvs, int64_t n_dbv,
                                                                const int64_t* __restrict__ perm, uint64_t seed,
                                                                int half_bits, int64_t first, int64_t count,
-                                                               float* __restrict__ x, float* __restrict__ y3) {
+                                                               float* __restrict__ x, float* __restrict__ y3,
+                                                               unsigned long long* __restrict__ work) {
     __shared__ SchedSmem ss;
     load_sched(P, ss);
     __syncthreads();
     const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
     const int nt = P.n_tau;
     const bool live = t < nt;
     const int my_col = live ? P.col_of_tau[t] : -1;
@@ -120,7 +119,8 @@ __global__ void __launch_bounds__(kThreads, 5) k_generate_pair(const __grid_cons
     const uint64_t total = (uint64_t)n_oef * (uint64_t)n_dbv;
     const int64_t npairs = (count + 1) >> 1;
 
-    for (int64_t pr = warp; pr < npairs; pr += nwarps) {
+    for (int64_t pr = next_unit(work, lane), nxt; pr < npairs; pr = nxt) {   // dynamic pairs, see k_forward_pair
+        nxt = next_unit(work, lane);
         int64_t v = pr * 2 + half;
         const bool valid = v < count;
         if (!valid) v = count - 1;
@@ -350,8 +350,10 @@ extern "C" int qbold_generate(const QboldParams* p, const float* oefs, int64_t n
         int64_t gp = (int64_t)sm_count() * bps_pair;
         const int64_t wantp = ((count + 1) / 2 + 7) / 8;
         if (wantp < gp) gp = wantp;
+        unsigned long long* work = next_work_counter(st);
+        if (!work) return fail(QBOLD_ECUDA, "qbold_generate: work counter unavailable");
         k_generate_pair<<<(unsigned)gp, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits, first,
-                                                           count, x, y3);
+                                                           count, x, y3, work);
     } else if (path == kSched)
         k_generate<kSched><<<(unsigned)grid, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits,
                                                                 first, count, x, y3);
