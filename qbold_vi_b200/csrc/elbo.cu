@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
                                                    int kl_samples, float inv_mask_sum, float kl_weight, int64_t n,
                                                    float* __restrict__ grad_q, float* __restrict__ grad_sigma,
                                                    float* __restrict__ nll_map, float* __restrict__ kl_map,
-                                                   double* __restrict__ sums) {
+                                                   double* __restrict__ sums, unsigned long long* __restrict__ work) {
     __shared__ QuadSmem s;
     __shared__ SchedSmem ss;
     if (P.full_model) {
@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
     int bad = 0;
 
-    for (int64_t v = warp; v < n; v += nwarps) {
+    for (int64_t v = next_unit(work, lane), nxt_unit; v < n; v = nxt_unit) {   // dynamic units, see next_unit
+        nxt_unit = next_unit(work, lane);
         const float m = __ldg(mask + v);
         if (!(m != 0.0f)) {
             // masked voxel: nll * 0 and where(mask > 0, kl, 0) (model.py:564,661) -> zero loss and gradient
@@ -632,7 +633,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_nll_map(const __grid_constant__
                                                          const float* __restrict__ q, const float* __restrict__ sigma,
                                                          const float* __restrict__ y, const float* __restrict__ mask,
                                                          const float* __restrict__ eps, uint64_t seed, uint64_t offset,
-                                                         int n_samples, int64_t n, float* __restrict__ nll_map) {
+                                                         int n_samples, int64_t n, float* __restrict__ nll_map,
+                                                         unsigned long long* __restrict__ work) {
     __shared__ QuadSmem s;
     __shared__ SchedSmem ss;
     if (P.full_model) {
@@ -655,7 +657,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_nll_map(const __grid_constant__
     const bool wide = nt > 16;
     const float df = P.student_t_df;
     const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
-    for (int64_t v = warp; v < n; v += nwarps) {
+    for (int64_t v = next_unit(work, lane), nxt_unit; v < n; v = nxt_unit) {   // dynamic units, see next_unit
+        nxt_unit = next_unit(work, lane);
         const float m = mask ? __ldg(mask + v) : 1.0f;
         if (!(m != 0.0f)) {
             if (lane == 0) nll_map[v] = 0.f;
@@ -997,18 +1000,18 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const int path = p->sched_phases > 0 ? kSched : (p->n_cols > kColGroup ? kColsMulti : kCols);
     const int64_t want = (n + 7) / 8;
+    unsigned long long* work = next_work_counter(st);
+    if (!work) return fail(QBOLD_ECUDA, "qbold_elbo_fused: work counter unavailable");
 #define QB_LAUNCH_ELBO(HP, MU)                                                                                       \
     do {                                                                                                              \
         static int64_t grid_cache = 0;                                                                                \
         const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo<HP, MU>, INT64_MAX / 64)); \
         k_elbo<HP, MU><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(                                  \
             *p, q, sigma, y, mask, HP ? prior : nullptr, eps, HP ? eps_kl : nullptr, seed, offset,                    \
-            HP ? kl_samples : 0, inv_mask_sum, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums);              \
+            HP ? kl_samples : 0, inv_mask_sum, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, work);        \
     } while (0)
     if (path == kSched && p->full_model && p->n_tau <= 16) {
         const int64_t wantp = ((n + 1) / 2 + 7) / 8;
-        unsigned long long* work = next_work_counter(st);
-        if (!work) return fail(QBOLD_ECUDA, "qbold_elbo_fused: work counter unavailable");
         if (prior) {
             static int64_t grid_cache = 0;
             const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<true>, INT64_MAX / 64));
@@ -1059,18 +1062,18 @@ extern "C" int qbold_nll_map(const QboldParams* p, const float* q, const float* 
     const int path = p->sched_phases > 0 ? kSched : (p->n_cols > kColGroup ? kColsMulti : kCols);
     const int64_t want = (n + 7) / 8;
     cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* work = next_work_counter(st);
+    if (!work) return fail(QBOLD_ECUDA, "qbold_nll_map: work counter unavailable");
 #define QB_LAUNCH_NLL(PA)                                                                                            \
     do {                                                                                                              \
         static int64_t grid_cache = 0;                                                                                \
         const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_nll_map<PA>, INT64_MAX / 64)); \
         k_nll_map<PA><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(*p, q, sigma, y, mask, eps, seed,  \
-                                                                                 offset, n_samples, n, nll_map);     \
+                                                                                 offset, n_samples, n, nll_map, work); \
     } while (0)
     if (path == kSched && p->full_model && p->n_tau <= 16) {
         static int64_t grid_cache = 0;
         const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_nll_map_pair, INT64_MAX / 64));
-        unsigned long long* work = next_work_counter(st);
-        if (!work) return fail(QBOLD_ECUDA, "qbold_nll_map: work counter unavailable");
         k_nll_map_pair<<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(*p, q, sigma, y, mask, eps, seed,
                                                                                   offset, n_samples, n, nll_map, work);
     } else if (path == kSched) QB_LAUNCH_NLL(kSched);

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward(const _
                                                       const float* __restrict__ oef_dbv,
                                                       const float* __restrict__ g_signal,
                                                       float* __restrict__ signal,
-                                                      float* __restrict__ g_oef_dbv, int64_t n) {
+                                                      float* __restrict__ g_oef_dbv, int64_t n,
+                                                      unsigned long long* __restrict__ work) {
     __shared__ QuadSmem s;
     __shared__ SchedSmem ss;
     if (P.full_model) {
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward(const _
     constexpr int W = HCT ? 3 : 2;
     const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
 
-    for (int64_t v = warp; v < n; v += nwarps) {
+    for (int64_t v = next_unit(work, lane), nxt_unit; v < n; v = nxt_unit) {   // dynamic units, see next_unit
+        nxt_unit = next_unit(work, lane);
         const float oef = __ldg(oef_dbv + v * W);
         const float dbv = __ldg(oef_dbv + v * W + 1);
         const float hct = HCT ? __ldg(oef_dbv + v * W + 2) : P.hct;
@@ -218,7 +220,9 @@ static int launch_forward_t(const QboldParams* p, const float* oef_dbv, const fl
     int64_t grid = (int64_t)sm_count() * blocks_per_sm;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k_forward<BWD, HCT, PATH><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n);
+    unsigned long long* work = next_work_counter(st);
+    if (!work) return fail(QBOLD_ECUDA, "qbold_forward: work counter unavailable");
+    k_forward<BWD, HCT, PATH><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, g, signal, grad, n, work);
     return after_launch("k_forward");
 }
 

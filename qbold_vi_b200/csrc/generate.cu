@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ Q
                                                        const float* __restrict__ dbvs, int64_t n_dbv,
                                                        const int64_t* __restrict__ perm, uint64_t seed,
                                                        int half_bits, int64_t first, int64_t count,
-                                                       float* __restrict__ x, float* __restrict__ y3) {
+                                                       float* __restrict__ x, float* __restrict__ y3,
+                                                       unsigned long long* __restrict__ work) {
     __shared__ QuadSmem s;
     __shared__ SchedSmem ss;
     if (P.full_model) {
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ Q
     const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
     const uint64_t total = (uint64_t)n_oef * (uint64_t)n_dbv;
 
-    for (int64_t v = warp; v < count; v += nwarps) {
+    for (int64_t v = next_unit(work, lane), nxt_unit; v < count; v = nxt_unit) {   // dynamic units, see next_unit
+        nxt_unit = next_unit(work, lane);
         const uint64_t row = (uint64_t)(first + v);
         const uint64_t idx = perm ? (uint64_t)__ldg(perm + row) : feistel_permute(row, total, half_bits, seed);
         const float oef = __ldg(oefs + idx / (uint64_t)n_dbv);            // meshgrid(indexing='ij'), signals.py:270
@@ -342,6 +344,8 @@ extern "C" int qbold_generate(const QboldParams* p, const float* oefs, int64_t n
     const int64_t want = (count + 7) / 8;
     if (want < grid) grid = want;
     cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* gwork = next_work_counter(st);
+    if (!gwork) return fail(QBOLD_ECUDA, "qbold_generate: work counter unavailable");
     if (path == kSched && p->full_model && p->n_tau <= 16) {
         static int bps_pair = 0;
         if (bps_pair == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_pair, k_generate_pair, kThreads, 0) !=
@@ -350,19 +354,18 @@ extern "C" int qbold_generate(const QboldParams* p, const float* oefs, int64_t n
         int64_t gp = (int64_t)sm_count() * bps_pair;
         const int64_t wantp = ((count + 1) / 2 + 7) / 8;
         if (wantp < gp) gp = wantp;
-        unsigned long long* work = next_work_counter(st);
-        if (!work) return fail(QBOLD_ECUDA, "qbold_generate: work counter unavailable");
+        unsigned long long* work = gwork;
         k_generate_pair<<<(unsigned)gp, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits, first,
                                                            count, x, y3, work);
     } else if (path == kSched)
         k_generate<kSched><<<(unsigned)grid, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits,
-                                                                first, count, x, y3);
+                                                                first, count, x, y3, gwork);
     else if (path == kCols)
         k_generate<kCols><<<(unsigned)grid, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed, half_bits,
-                                                               first, count, x, y3);
+                                                               first, count, x, y3, gwork);
     else
         k_generate<kColsMulti><<<(unsigned)grid, kThreads, 0, st>>>(*p, oefs, n_oef, dbvs, n_dbv, perm, seed,
-                                                                    half_bits, first, count, x, y3);
+                                                                    half_bits, first, count, x, y3, gwork);
     return after_launch("k_generate");
 }
 
