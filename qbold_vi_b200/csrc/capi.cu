@@ -44,13 +44,16 @@ int sm_count() {
     return cached;
 }
 
-__device__ unsigned long long g_work_counters[64];
+// Ring size bounds how many launches may be in flight at once ACROSS streams before a counter is reused (launches on
+// one stream are ordered with the memset that re-arms their counter, so a single stream can never collide).
+constexpr unsigned kWorkCounters = 1024;
+__device__ unsigned long long g_work_counters[kWorkCounters];
 
 unsigned long long* next_work_counter(cudaStream_t stream) {
     static std::atomic<unsigned> turn{0};
     void* base = nullptr;
     if (cudaGetSymbolAddress(&base, g_work_counters) != cudaSuccess) return nullptr;     // per current device
-    unsigned long long* c = static_cast<unsigned long long*>(base) + (turn.fetch_add(1) & 63u);
+    unsigned long long* c = static_cast<unsigned long long*>(base) + (turn.fetch_add(1) & (kWorkCounters - 1));
     if (cudaMemsetAsync(c, 0, sizeof(unsigned long long), stream) != cudaSuccess) return nullptr;
     return c;
 }

@@ -1,9 +1,12 @@
 """The amortization network of the reference (``EncoderTrainer.create_encoder``, model.py:122-223) in PyTorch.
 
-Adjacent to the hot path: it stays a library network (cuDNN / cuBLAS on tensor cores);
-what matters here is that it produces the tensors the fused ELBO kernel consumes -- 5 logit-normal
-parameters and ``n_tau`` heteroscedastic sigmas per voxel -- and that its 146 176 parameters (optimal.yaml)
-are what the per-step NCCL all-reduce carries.  Layout is the reference's channels-last ``[B, X, Y, Z, C]``.
+Adjacent to the hot path.  It produces the tensors the fused ELBO kernel consumes -- 5 logit-normal
+parameters and ``n_tau`` heteroscedastic sigmas per voxel -- and its 146 176 parameters (optimal.yaml) are what the
+per-step NCCL all-reduce carries.  Layout is the reference's channels-last ``[B, X, Y, Z, C]``.  The 3x3x1
+convolutions and the forward / input-gradient GEMMs of the per-voxel layers are library kernels (cuDNN / cuBLAS on
+tensor cores); hand-written here: the weight / bias gradients of the per-voxel layers (``qbold_dense_wgrad``), the gated
+residual mix (``qbold_gate_mix_*``), the whole voxel-wise branch as one tcgen05 kernel for inference
+(``voxelwise_fused``) and, opt-in, the single-layer tcgen05 GEMMs (``QBOLD_DENSE_TC=1``).
 """
 from __future__ import annotations
 
