@@ -18,9 +18,6 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-_WGRAD_WS = {}
-
-
 _TC_STATUS = {}
 
 
@@ -105,9 +102,8 @@ class _DenseFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 gx = g @ weight
         lib = _lib.lib()
-        ws = _WGRAD_WS.get(dev)
-        if ws is None:
-            ws = _WGRAD_WS[dev] = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
+        # per-call scratch from the caching allocator (stream-ordered, so concurrent backward passes cannot share it)
+        ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
         dw = torch.empty_like(weight)
         db = torch.empty(n_out, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
