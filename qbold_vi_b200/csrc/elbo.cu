@@ -262,11 +262,14 @@ __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const
 __global__ void __launch_bounds__(kThreads) k_kl(const float* __restrict__ q, const float* __restrict__ prior,
                                                  const float* __restrict__ mask, const float* __restrict__ eps_kl,
                                                  uint64_t seed, uint64_t offset, int n_samples, int64_t n,
-                                                 float* __restrict__ kl_map, float* __restrict__ grad_q) {
+                                                 float* __restrict__ kl_map, float* __restrict__ grad_q,
+                                                 unsigned long long* __restrict__ work) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
-    for (int64_t v = warp; v < n; v += nwarps) {
+    // four voxels per grab from the device work counter (see next_unit)
+    for (int64_t b = next_unit(work, lane), nb; b * 4 < n; b = nb) {
+      nb = next_unit(work, lane);
+      const int64_t v_end = (b + 1) * 4 < n ? (b + 1) * 4 : n;
+      for (int64_t v = b * 4; v < v_end; ++v) {
         KlOut ko;
         ko.kl = 0.f;
 #pragma unroll
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(kThreads) k_kl(const float* __restrict__ q, co
         if (grad_q != nullptr && lane < 5)
             grad_q[v * 5 + lane] = lane == 0 ? ko.g[0] : lane == 1 ? ko.g[1] : lane == 2 ? ko.g[2]
                                    : lane == 3 ? ko.g[3] : ko.g[4];
+      }
     }
 }
 
@@ -914,13 +918,15 @@ __global__ void __launch_bounds__(kThreads) k_posterior_stats(const __grid_const
                                                               const float* __restrict__ q,
                                                               const float* __restrict__ eps, uint64_t seed,
                                                               uint64_t offset, int n_samples, int64_t n,
-                                                              float* __restrict__ mean3, float* __restrict__ var3) {
+                                                              float* __restrict__ mean3, float* __restrict__ var3,
+                                                              unsigned long long* __restrict__ work) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
     constexpr int kMaxPer = 8;   // up to 256 samples per voxel held in registers
     const float inv_n = 1.0f / (float)n_samples;
-    for (int64_t v = warp; v < n; v += nwarps) {
+    for (int64_t bt = next_unit(work, lane), nbt; bt * 4 < n; bt = nbt) {        // four voxels per grab
+      nbt = next_unit(work, lane);
+      const int64_t v_end = (bt + 1) * 4 < n ? (bt + 1) * 4 : n;
+      for (int64_t v = bt * 4; v < v_end; ++v) {
         Dist dq, dp;
         QExtra ex;
         load_dists(q + v * 5, nullptr, lane, dq, ex, dp);
@@ -969,6 +975,7 @@ __global__ void __launch_bounds__(kThreads) k_posterior_stats(const __grid_const
             mean3[v * 3 + lane] = lane == 0 ? m_o : lane == 1 ? m_d : m_r;
             var3[v * 3 + lane] = lane == 0 ? v_o : lane == 1 ? v_d : v_r;
         }
+      }
     }
 }
 
@@ -1046,9 +1053,11 @@ extern "C" int qbold_kl(const float* q, const float* prior, const float* mask, c
     static int64_t grid_cache = 0;
     const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_kl, INT64_MAX / 64));
     const int64_t want = (n + 7) / 8;
+    unsigned long long* work = next_work_counter((cudaStream_t)stream);
+    if (!work) return fail(QBOLD_ECUDA, "qbold_kl: work counter unavailable");
     k_kl<<<(unsigned)(want < grid ? want : grid), kThreads, 0, (cudaStream_t)stream>>>(q, prior, mask, eps_kl, seed,
                                                                                       offset, n_samples, n, kl_map,
-                                                                                      grad_q);
+                                                                                      grad_q, work);
     return after_launch("k_kl");
 }
 
@@ -1121,7 +1130,9 @@ extern "C" int qbold_posterior_stats(const QboldParams* p, const float* q, const
     static int64_t grid_cache = 0;
     const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_posterior_stats, INT64_MAX / 64));
     const int64_t want = (n + 7) / 8;
+    unsigned long long* work = next_work_counter((cudaStream_t)stream);
+    if (!work) return fail(QBOLD_ECUDA, "qbold_posterior_stats: work counter unavailable");
     k_posterior_stats<<<(unsigned)(want < grid ? want : grid), kThreads, 0, (cudaStream_t)stream>>>(
-        *p, q, eps, seed, offset, n_samples, n, mean3, var3);
+        *p, q, eps, seed, offset, n_samples, n, mean3, var3, work);
     return after_launch("k_posterior_stats");
 }
