@@ -1036,3 +1036,27 @@ def test_gate_mix_kernels(qb, dev, zc):
     ref.backward(go.double())
     for a, b in zip(got, [ref.detach(), skip.grad, r.grad, z.grad]):
         assert float((a.double() - b.double()).abs().max()) < 1e-5 * max(float(b.abs().max()), 1.0)
+
+
+def test_concurrent_streams_share_no_work_counter(qb, dev, cfg_noise_off):
+    """Every launch takes its own device work counter (a ring, re-armed on the launch's stream): kernels overlapping
+    on different streams, and > ring-size launches on one stream, must each cover all of their voxels exactly once."""
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    xs = [_t(_rand_voxels(200_003 + 17 * i, 40 + i), dev) for i in range(4)]
+    refs = [layer(x) for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    outs = [[] for _ in range(4)]
+    for rep in range(6):
+        for i, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                outs[i].append(layer(xs[i]))
+    torch.cuda.synchronize()
+    for i in range(4):
+        for o_ in outs[i]:
+            assert torch.equal(o_, refs[i])
+    small = _t(_rand_voxels(33, 3), dev)
+    ref_small = layer(small)
+    for _ in range(1100):                                   # wraps the 1024-entry ring on one stream
+        got = layer(small)
+    assert torch.equal(got, ref_small)
