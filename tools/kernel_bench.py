@@ -66,7 +66,7 @@ def main():
     pred = layer(x)
     y_true = torch.cat([data, mask[:, None]], -1)
     cases['fine_tune_loss_fn alone (k_nll, value + partials)'] = lambda: tr.fine_tune_loss_fn(y_true, torch.cat([pred, sigma], -1))
-    side = int(round((n // 2) ** (1.0 / 3.0)))
+    side = int((n // 2) ** (1.0 / 3.0) + 1e-6)               # largest cube that fits: 2 x side^3 <= n
     qv = q[:2 * side ** 3].reshape(2, side, side, side, 5).contiguous()
     tv_true = torch.cat([qv, torch.ones_like(qv[..., :1])], -1)
     cases['smoothness TV, 2 x %d^3 (k_smoothness, value + gradient)' % side] = lambda: tr.smoothness_loss(tv_true, qv)
