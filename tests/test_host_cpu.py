@@ -216,3 +216,26 @@ def test_nifti_round_trip_and_subject_concatenation(tmp_path):
     nifti.save_nifti(vol, str(tmp_path / 'm.nii'), affine=np.diag([2.0, 2.0, 3.0, 1.0]))
     back, aff = nifti.load_nifti(str(tmp_path / 'm.nii'))
     assert np.array_equal(back, vol) and aff[2, 2] == 3.0
+
+
+def test_encoder_host_paths_on_cpu(qb):
+    """The encoder's routing helpers leave CPU tensors on the plain torch layers (the kernels are CUDA-only), and the
+    stream-1-only forward used by pre-training equals output 0 of the full forward."""
+    import torch
+    from qbold_vi_b200.encoder import Encoder, dense, gate_mix
+    torch.manual_seed(0)
+    enc = Encoder(no_units=12, no_intermediate_layers=2)
+    x = torch.rand(2, 5, 4, 3, 11) * 100.0 + 10.0
+    full = enc(x)
+    assert tuple(full[0].shape) == (2, 5, 4, 3, 5) and tuple(full[2].shape) == (2, 5, 4, 3, 11)
+    assert torch.allclose(enc.forward_voxelwise(x), full[0], atol=1e-6)
+    assert enc.supports_voxelwise_fused() and not Encoder(activation='gelu').supports_voxelwise_fused()
+    assert not Encoder(no_units=80).supports_voxelwise_fused()
+    h = torch.randn(7, 12, requires_grad=True)
+    y = dense(enc.blocks[0].pointwise, h, relu=True)
+    assert torch.allclose(y, torch.relu(enc.blocks[0].pointwise(h)))
+    skip, r, z = torch.randn(3, 12), torch.randn(3, 12), torch.randn(3, 12)
+    g = torch.sigmoid(z - 3.0)
+    assert torch.allclose(gate_mix(skip, r, z, -3.0), skip * (1 - g) + r * g)
+    # parameter count of the optimal.yaml encoder (what the gradient all-reduce carries)
+    assert sum(p.numel() for p in Encoder(no_units=60, no_intermediate_layers=2).parameters()) == 146176
