@@ -1090,3 +1090,22 @@ def test_cuda_graph_capture_and_replay(qb, dev, cfg_noise_off):
         torch.cuda.synchronize()
         s_ref, g_ref = layer.forward_backward(x, g)
         assert torch.equal(sig, s_ref) and torch.equal(grad, g_ref)
+
+
+def test_c_abi_from_plain_c(qb, dev, tmp_path):
+    """examples/c_abi_demo.c: the library driven from C (no Python, no torch) reproduces the Appendix B known answers."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available on this box')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, 'qbold_vi_b200')
+    exe = str(tmp_path / 'c_abi_demo')
+    subprocess.run([nvcc, '-Wno-deprecated-gpu-targets', '-x', 'c', os.path.join(root, 'examples', 'c_abi_demo.c'), '-I',
+                    os.path.join(root, 'include'), '-L', libdir, '-lqbold', '-Xlinker', '-rpath=' + libdir, '-o', exe],
+                   check=True, capture_output=True, timeout=300)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'max relative deviation' in out.stdout
