@@ -148,8 +148,7 @@ class DataParallelTrainer:
                 'mask_sum': msum, 'lr': lr}
 
     def bucket_params_mul_(self, factor):
-        for p in self.bucket.params:
-            p.mul_(factor)
+        torch._foreach_mul_(self.bucket.params, factor)
 
 
 class StreamingPretrainer:
@@ -205,7 +204,7 @@ class StreamingPretrainer:
             self.layer.add_noise(x, seed=self.seed ^ 0x5DEECE66D, offset=first, inplace=True)
         return x, y
 
-    def step(self):
+    def step(self, with_metrics=True):
         x, y = self.next_batch()
         nt = self.layer.n_tau
         self.bucket.zero_()
@@ -217,13 +216,15 @@ class StreamingPretrainer:
         self.bucket.all_reduce_()
         if self.weight_decay > 0.0:
             with torch.no_grad():
-                for p in self.bucket.params:
-                    p.mul_(1.0 - self.weight_decay)
+                torch._foreach_mul_(self.bucket.params, 1.0 - self.weight_decay)
         self.opt.step()
         stat = loss.detach().double().reshape(1)
         all_reduce_sum_(stat)
+        if not with_metrics:
+            return {'loss': float(stat)}
         with torch.no_grad():                                             # oef / dbv / r2p MSE metrics (model.py:345-374)
             means = self.trainer.calculate_means(out.detach(), None, include_r2p=True, no_samples=20,
                                                  signal_layer=self.layer).reshape(-1, 3)
             mse = ((means - y) ** 2).mean(0)
-        return {'loss': float(stat), 'oef_mse': float(mse[0]), 'dbv_mse': float(mse[1]), 'r2p_mse': float(mse[2])}
+            vals = torch.cat([stat, mse.double()]).tolist()               # one device -> host read per step
+        return {'loss': vals[0], 'oef_mse': vals[1], 'dbv_mse': vals[2], 'r2p_mse': vals[3]}
