@@ -59,6 +59,17 @@ def global_mask_sum(mask):
     return float(all_reduce_sum_(s).item())
 
 
+def _adam(params, **kw):
+    """Adam with the single-kernel (fused) update on CUDA parameters; the multi-tensor default elsewhere (CPU tests)."""
+    params = list(params)
+    if params and all(p.is_cuda for p in params):
+        try:
+            return torch.optim.Adam(params, fused=True, **kw)
+        except (RuntimeError, TypeError):
+            pass
+    return torch.optim.Adam(params, **kw)
+
+
 class FlatGradBucket:
     """One contiguous float32 buffer aliasing every parameter's .grad: a single all-reduce per step."""
 
@@ -107,7 +118,7 @@ class DataParallelTrainer:
         self.smoothness_weight, self.kl_weight, self.kl_samples = smoothness_weight, kl_weight, kl_samples
         self.bucket = FlatGradBucket(encoder.parameters())
         self.lr, self.wd = LinearSchedule(ft_lr), LinearSchedule(adamw_decay)
-        self.opt = torch.optim.Adam(self.bucket.params, lr=ft_lr, betas=(0.9, 0.9))      # beta_2 = 0.9 (train.py:310)
+        self.opt = _adam(self.bucket.params, lr=ft_lr, betas=(0.9, 0.9))                 # beta_2 = 0.9 (train.py:310)
         self.decay = adamw_decay > 0.0
         self.step_no = 0
         self.loss_fn = loss_fn or self._fused_loss
@@ -183,7 +194,7 @@ class StreamingPretrainer:
         self.cursor = rank * self.batch
         self.stride = world_size() * self.batch
         self.bucket = FlatGradBucket(encoder.parameters())
-        self.opt = torch.optim.Adam(self.bucket.params, lr=lr)
+        self.opt = _adam(self.bucket.params, lr=lr)
         self.weight_decay = weight_decay
         self._C = C
 
