@@ -259,6 +259,14 @@ int64_t qbold_dense_wgrad_workspace_floats(void);
 int qbold_dense_wgrad(const float* g, const float* relu_mask, int32_t n_out, const float* x, int32_t n_in, int64_t n,
                       float* dw, float* db, int32_t accumulate, float* workspace, void* stream);
 
+/* Skinny Dense layers (the encoder's heads, n_out <= 16: 60 -> 5 posterior parameters, 60 -> 11 sigmas) as streaming
+ * FP32 passes: y[n,n_out] = x[n,n_in] w^T + bias and dx[n,n_in] = g[n,n_out] w, w [n_out,n_in] row-major; n_in a multiple
+ * of 4 up to 64; x / w / y / dx 16-byte aligned. */
+int qbold_dense_small_forward(const float* x, const float* w, const float* bias, int32_t n_in, int32_t n_out, int64_t n,
+                              float* y, void* stream);
+int qbold_dense_small_dgrad(const float* g, const float* w, int32_t n_in, int32_t n_out, int64_t n, float* dx,
+                            void* stream);
+
 /* One Dense layer on the tensor cores (tcgen05 kind::tf32, fp32 accumulate) for the encoder's training passes:
  * y[n,n_out] = act((x[n,n_in] * [relu_mask > 0]) B^T + bias).  qbold_dense_tc_pack builds the operand image
  * (qbold_dense_tc_packed_floats() floats, device) from a row-major matrix: transpose = 0: B = w [rows, cols] with

@@ -89,6 +89,8 @@ _SIGNATURES = {
                                             _f, C.c_void_p]),
     'qbold_dense_wgrad_workspace_floats': (C.c_int64, []),
     'qbold_dense_wgrad': (C.c_int, [_f, _f, C.c_int32, _f, C.c_int32, C.c_int64, _f, _f, C.c_int32, _f, C.c_void_p]),
+    'qbold_dense_small_forward': (C.c_int, [_f, _f, _f, C.c_int32, C.c_int32, C.c_int64, _f, C.c_void_p]),
+    'qbold_dense_small_dgrad': (C.c_int, [_f, _f, C.c_int32, C.c_int32, C.c_int64, _f, C.c_void_p]),
     'qbold_dense_tc_packed_floats': (C.c_int, []),
     'qbold_dense_tc_pack': (C.c_int, [_f, _f, C.c_int32, C.c_int32, C.c_int32, _f, C.c_void_p]),
     'qbold_dense_tc': (C.c_int, [_f, _f, _f, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _f, _f, C.c_void_p]),

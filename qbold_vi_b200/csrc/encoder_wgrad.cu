@@ -191,3 +191,109 @@ extern "C" int qbold_dense_wgrad(const float* g, const float* relu_mask, int32_t
     k_dense_wgrad_reduce<<<16, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid, n_out, n_in, dw, db, accumulate);
     return after_launch("k_dense_wgrad_reduce");
 }
+
+// ---- skinny Dense layers (the encoder's heads: 60 -> 5 posterior parameters, 60 -> 11 sigmas) --------------------------
+// y[v, o] = b[o] + sum_i x[v, i] W[o, i]  and  dx[v, i] = sum_o g[v, o] W[o, i]  for n_out <= 16.  With so few outputs the
+// GEMM is a streaming pass over x (or dx): one thread per voxel, W in shared memory read as broadcast float4, ~25 us of
+// HBM time per 524 288 voxels where the library's tensor-op kernels take 100-130 us on this shape.
+namespace qb {
+
+constexpr int kSmallOut = 16, kSmallIn = 64;
+
+__global__ void __launch_bounds__(256) k_dense_small_fwd(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ b, int n_in, int n_out, int64_t n,
+                                                         float* __restrict__ y) {
+    __shared__ float4 sw[kSmallOut][kSmallIn / 4];
+    __shared__ float sb[kSmallOut];
+    const int chunks = n_in >> 2;
+    for (int e = threadIdx.x; e < kSmallOut * (kSmallIn / 4); e += blockDim.x) {
+        const int o = e / (kSmallIn / 4), c = e % (kSmallIn / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < n_out && c < chunks) v = *reinterpret_cast<const float4*>(w + o * n_in + c * 4);
+        sw[o][c] = v;
+    }
+    if (threadIdx.x < kSmallOut) sb[threadIdx.x] = threadIdx.x < n_out ? b[threadIdx.x] : 0.f;
+    __syncthreads();
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        float acc[kSmallOut];
+#pragma unroll
+        for (int o = 0; o < kSmallOut; ++o) acc[o] = sb[o];
+        const float4* row = reinterpret_cast<const float4*>(x + v * n_in);
+        for (int c = 0; c < chunks; ++c) {
+            const float4 a = __ldg(row + c);
+#pragma unroll
+            for (int o = 0; o < kSmallOut; ++o) {
+                const float4 ww = sw[o][c];
+                acc[o] = fmaf(a.x, ww.x, fmaf(a.y, ww.y, fmaf(a.z, ww.z, fmaf(a.w, ww.w, acc[o]))));
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kSmallOut; ++o)
+            if (o < n_out) y[v * n_out + o] = acc[o];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dense_small_dgrad(const float* __restrict__ g, const float* __restrict__ w,
+                                                           int n_in, int n_out, int64_t n, float* __restrict__ dx) {
+    __shared__ float4 sw[kSmallOut][kSmallIn / 4];
+    const int chunks = n_in >> 2;
+    for (int e = threadIdx.x; e < kSmallOut * (kSmallIn / 4); e += blockDim.x) {
+        const int o = e / (kSmallIn / 4), c = e % (kSmallIn / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < n_out && c < chunks) v = *reinterpret_cast<const float4*>(w + o * n_in + c * 4);
+        sw[o][c] = v;
+    }
+    __syncthreads();
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        float gv[kSmallOut];
+#pragma unroll
+        for (int o = 0; o < kSmallOut; ++o) gv[o] = o < n_out ? __ldg(g + v * n_out + o) : 0.f;
+        float4* row = reinterpret_cast<float4*>(dx + v * n_in);
+        for (int c = 0; c < chunks; ++c) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int o = 0; o < kSmallOut; ++o) {
+                const float4 ww = sw[o][c];
+                a.x = fmaf(gv[o], ww.x, a.x);
+                a.y = fmaf(gv[o], ww.y, a.y);
+                a.z = fmaf(gv[o], ww.z, a.z);
+                a.w = fmaf(gv[o], ww.w, a.w);
+            }
+            row[c] = a;
+        }
+    }
+}
+
+}  // namespace qb
+
+static int small_dense_args_ok(const void* a, const void* w, const void* out, int n_in, int n_out, int64_t n) {
+    return a && w && out && n >= 0 && n_out >= 1 && n_out <= kSmallOut && n_in >= 4 && n_in <= kSmallIn && (n_in & 3) == 0 &&
+           (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+
+extern "C" int qbold_dense_small_forward(const float* x, const float* w, const float* bias, int32_t n_in, int32_t n_out,
+                                         int64_t n, float* y, void* stream) {
+    if (!small_dense_args_ok(x, w, y, n_in, n_out, n) || !bias)
+        return fail(QBOLD_EUNSUPPORTED, "qbold_dense_small_forward: needs n_out <= 16, n_in a multiple of 4 up to 64, "
+                                        "16-byte aligned x / w / y");
+    if (n == 0) return QBOLD_OK;
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    k_dense_small_fwd<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, n_in, n_out, n, y);
+    return after_launch("k_dense_small_fwd");
+}
+
+extern "C" int qbold_dense_small_dgrad(const float* g, const float* w, int32_t n_in, int32_t n_out, int64_t n, float* dx,
+                                       void* stream) {
+    if (!small_dense_args_ok(dx, w, dx, n_in, n_out, n) || !g)
+        return fail(QBOLD_EUNSUPPORTED, "qbold_dense_small_dgrad: needs n_out <= 16, n_in a multiple of 4 up to 64, "
+                                        "16-byte aligned w / dx");
+    if (n == 0) return QBOLD_OK;
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    k_dense_small_dgrad<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(g, w, n_in, n_out, n, dx);
+    return after_launch("k_dense_small_dgrad");
+}

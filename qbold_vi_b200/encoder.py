@@ -33,6 +33,12 @@ def _tc_ok(n_in, n_out, *tensors):
             and all(t.data_ptr() % 16 == 0 for t in tensors))
 
 
+def _small_ok(n_in, n_out, *tensors):
+    """The skinny-layer kernels (qbold_dense_small_*): <= 16 outputs, inputs a multiple of 4 up to 64, aligned."""
+    return (n_out <= 16 and n_in % 4 == 0 and 4 <= n_in <= 64 and all(t.is_contiguous() and t.data_ptr() % 16 == 0
+                                                                      for t in tensors))
+
+
 def _dense_tc(x, mask, w, bias, n_in, n_out, transpose, relu):
     """y = act((x * [mask > 0]) B^T + bias) through qbold_dense_tc; B = w (transpose=False) or w^T."""
     from . import _lib
@@ -68,7 +74,14 @@ class _DenseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu=False):
         n_out, n_in = weight.shape
-        if USE_DENSE_TC and _tc_ok(n_in, n_out, x):
+        if not relu and _small_ok(n_in, n_out, x, weight):
+            from . import _lib
+            from ._lib import check, dptr, stream_ptr
+            y = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                check(_lib.lib().qbold_dense_small_forward(dptr(x), dptr(weight), dptr(bias), n_in, n_out, x.shape[0],
+                                                           dptr(y), stream_ptr(x.device)))
+        elif USE_DENSE_TC and _tc_ok(n_in, n_out, x):
             y = _dense_tc(x, None, weight, bias, n_in, n_out, False, relu)
         elif relu:                                            # bias + ReLU in the GEMM epilogue (cuBLASLt)
             y = torch._addmm_activation(bias, x, weight.t(), use_gelu=False)
@@ -93,7 +106,13 @@ class _DenseFn(torch.autograd.Function):
         n_out, n_in = weight.shape
         dev = x.device
         gx, mask = None, y
-        if USE_DENSE_TC and _tc_ok(n_out, n_in, g) and (y is None or y.data_ptr() % 16 == 0):
+        if y is None and _small_ok(n_in, n_out, weight):
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty((x.shape[0], n_in), dtype=torch.float32, device=dev)
+                with torch.cuda.device(dev):
+                    check(_lib.lib().qbold_dense_small_dgrad(dptr(g), dptr(weight), n_in, n_out, x.shape[0], dptr(gx),
+                                                             stream_ptr(dev)))
+        elif USE_DENSE_TC and _tc_ok(n_out, n_in, g) and (y is None or y.data_ptr() % 16 == 0):
             if ctx.needs_input_grad[0]:
                 gx = _dense_tc(g, y, weight, None, n_out, n_in, True, False)          # (g * relu') W, relu' fused
         else:
