@@ -1,5 +1,6 @@
+"""Kernel-level breakdown (torch profiler) of the fine-tuning step on 2 x 64^3 unmasked volumes."""
 import os, sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import qbold_vi_b200 as qb
 from qbold_vi_b200 import distributed as D
 from qbold_vi_b200.encoder import create_encoder_from_args
