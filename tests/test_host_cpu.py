@@ -239,3 +239,22 @@ def test_encoder_host_paths_on_cpu(qb):
     assert torch.allclose(gate_mix(skip, r, z, -3.0), skip * (1 - g) + r * g)
     # parameter count of the optimal.yaml encoder (what the gradient all-reduce carries)
     assert sum(p.numel() for p in Encoder(no_units=60, no_intermediate_layers=2).parameters()) == 146176
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup',
+                          '0'], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'impl', 'cpu_baseline', 'e2e', 'gpu_launches'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['unit'] == 'voxel-signals/s' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and 'workload' in line['config']
