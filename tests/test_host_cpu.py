@@ -258,3 +258,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['impl'] == 'reference' and line['unit'] == 'voxel-signals/s' and line['higher_is_better'] is True
     assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and 'workload' in line['config']
+
+
+def test_bench_fails_loudly_without_a_gpu():
+    """The product arm has no CPU fallback: without CUDA it must stop with a clear message, not print a number."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1'], capture_output=True, text=True,
+                         timeout=300, cwd=root)
+    assert out.returncode != 0 and 'no CPU fallback' in (out.stderr + out.stdout)
+    assert '"value"' not in out.stdout
