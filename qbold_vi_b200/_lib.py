@@ -13,7 +13,8 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libqbold.so')
+# QBOLD_LIB: kernel-variant A/B runs (tools/ab_variants.sh); the product library is the in-tree one
+LIB_PATH = os.environ.get('QBOLD_LIB') or os.path.join(_HERE, 'libqbold.so')
 MAX_TAU = 32
 NQ_PAD = 132
 ABI_VERSION = 2

@@ -86,6 +86,104 @@ __device__ __forceinline__ void bessel_big(float x, float& omj0, float& j1) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Packed FP32 (sm_100a fma/mul/add.rn.f32x2 -> SASS FFMA2 / FMUL2 / FADD2): one instruction evaluates the same
+// Horner step for TWO quadrature entries held in an aligned register pair.  The polynomial coefficients stay
+// 32-bit immediates (FFMA2 broadcasts them), pack/unpack of the two halves is free (they are the two registers
+// of the pair), so the MUFU.RSQ and the sign-bit fix-up of the large-argument form stay scalar on each half.
+// Same IEEE round-to-nearest arithmetic per half as the scalar kernels above.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk1(float v) { return pk2(v, v); }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float hsum2(f32x2 v) {
+    float lo, hi;
+    upk2(v, lo, hi);
+    return lo + hi;
+}
+
+template <class P>
+__device__ __forceinline__ f32x2 horner2(f32x2 t) {
+    f32x2 acc = pk1(P::c(P::N - 1));
+#pragma unroll
+    for (int i = P::N - 2; i >= 0; --i) acc = fma2(acc, t, pk1(P::c(i)));
+    return acc;
+}
+
+// amp * cos(theta) on both halves (see amp_cos)
+__device__ __forceinline__ f32x2 amp_cos2(f32x2 amp, f32x2 theta) {
+    const f32x2 t = fma2(theta, pk1(kInvPi), pk1(kMagic));
+    const f32x2 n = add2(t, pk1(-kMagic));
+    f32x2 r = fma2(n, pk1(-kPiHi), theta);
+    r = fma2(n, pk1(-kPiLo), r);
+    const f32x2 c = horner2<coef::CS>(mul2(r, r));
+    float t0, t1, a0, a1;
+    upk2(t, t0, t1);
+    upk2(amp, a0, a1);
+    a0 = __uint_as_float(__float_as_uint(a0) ^ (__float_as_uint(t0) << 31));
+    a1 = __uint_as_float(__float_as_uint(a1) ^ (__float_as_uint(t1) << 31));
+    return mul2(pk2(a0, a1), c);
+}
+
+// Packed accumulation steps of the scheduled quadrature: x = A*m (both halves), w = Simpson weights.
+//   small:  accI += w z S0(z),  accS += w z S1(z)        (accS is scaled by 1/A at the flush: w x J1 / A = w m J1)
+//   mid/big: accI += w (1 - J0),  accB += (w m) J1
+template <bool BWD>
+__device__ __forceinline__ void acc_small2(f32x2 x, f32x2 w, f32x2& accI, f32x2& accS) {
+    const f32x2 z = mul2(x, x);
+    const f32x2 wz = mul2(w, z);
+    accI = fma2(wz, horner2<coef::S0>(z), accI);
+    if (BWD) accS = fma2(wz, horner2<coef::S1>(z), accS);
+}
+
+template <bool BWD>
+__device__ __forceinline__ void acc_mid2(f32x2 x, f32x2 m, f32x2 w, f32x2& accI, f32x2& accB) {
+    const f32x2 t = add2(x, pk1(-coef::kXC));
+    accI = fma2(w, horner2<coef::M0>(t), accI);
+    if (BWD) accB = fma2(mul2(w, m), horner2<coef::M1>(t), accB);
+}
+
+template <bool BWD>
+__device__ __forceinline__ void acc_big2(f32x2 x, f32x2 m, f32x2 w, f32x2& accI, f32x2& accB) {
+    float x0, x1;
+    upk2(x, x0, x1);
+    const f32x2 r = pk2(rsqrt_pos(x0), rsqrt_pos(x1));
+    const f32x2 q = mul2(r, r);
+    const f32x2 v = mul2(q, q);
+    const f32x2 a0 = mul2(r, horner2<coef::A0>(v));
+    const f32x2 th0 = fma2(q, horner2<coef::F0>(v), add2(x, pk1(-kPiO4)));
+    const f32x2 omj0 = fma2(amp_cos2(a0, th0), pk1(-1.0f), pk1(1.0f));
+    accI = fma2(w, omj0, accI);
+    if (BWD) {
+        const f32x2 a1 = mul2(r, horner2<coef::A1>(v));
+        const f32x2 th1 = fma2(q, horner2<coef::F1>(v), add2(x, pk1(-k3PiO4)));
+        accB = fma2(mul2(w, m), amp_cos2(a1, th1), accB);
+    }
+}
+
 // x >= 0.  Per-lane branches: uniform within a warp pass except for the (at most two) passes per
 // column that straddle a range boundary (lanes hold consecutive quadrature nodes, x is monotone in lane).
 template <bool WANT_J1>

@@ -266,15 +266,35 @@ __device__ __forceinline__ float node0_value(const QboldParams& P, float a) {
 // [column][lane] at the phase end (first visit stores, later visits add -- no per-voxel clearing).
 enum QuadPath { kSched = 0, kCols = 1, kColsMulti = 2 };
 
+// Which argument ranges evaluate two schedule entries per instruction with packed FP32 (FFMA2).
+#ifndef QB_PACK_SMALL
+#define QB_PACK_SMALL 1
+#endif
+#ifndef QB_PACK_MID
+#define QB_PACK_MID 1
+#endif
+#ifndef QB_PACK_BIG
+#define QB_PACK_BIG 1
+#endif
+
 struct SchedSmem {
-    float2 mw[QBOLD_SCHED_MAX_ENTRIES];                  // (m, weight) per [phase][pass][lane]
+    // packed entries [phase][pair][lane] = (m_a, m_b, w_a, w_b): passes 2*pair and 2*pair+1 of the host schedule,
+    // evaluated together with packed FP32 (one LDS.128 per lane feeds two Bessel-pair evaluations)
+    float4 mw[QBOLD_SCHED_MAX_ENTRIES / 2];
     unsigned char col[QBOLD_SCHED_MAX_PHASES * 32];
     float slots[8 /*warps*/][2][8][32];                  // [warp][I|D][column][lane]
 };
 
 __device__ __forceinline__ void load_sched(const QboldParams& P, SchedSmem& s) {
+    static_assert(QBOLD_SCHED_PHASE_LEN % 2 == 0, "packed evaluation pairs up the passes of a phase");
     const int n = P.sched_phases * QBOLD_SCHED_PHASE_LEN * 32;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s.mw[i] = make_float2(P.sched_m[i], P.sched_w[i]);
+    float* mw = reinterpret_cast<float*>(s.mw);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int lane = i & 31, pass = i >> 5, pair = pass >> 1, half = pass & 1;
+        float* e = mw + (pair * 32 + lane) * 4;
+        e[half] = P.sched_m[i];
+        e[2 + half] = P.sched_w[i];
+    }
     for (int i = threadIdx.x; i < P.sched_phases * 32; i += blockDim.x) s.col[i] = P.sched_col[i];
     float* z = &s.slots[0][0][0][0];
     for (int i = threadIdx.x; i < 8 * 2 * 8 * 32; i += blockDim.x) z[i] = 0.f;
@@ -339,24 +359,33 @@ struct SchedAddr {
     unsigned redD;
 };
 
+// The addresses go through an empty asm so that the compiler keeps them in registers: left to itself it
+// re-derives them from %tid / the CTA's shared window at every phase flush (~10 instructions per phase).
+__device__ __forceinline__ unsigned pinned(unsigned a) {
+    asm volatile("" : "+r"(a));
+    return a;
+}
+
 __device__ __forceinline__ SchedAddr sched_addr(const SchedSmem& s, int lane, int warp_in_cta) {
     SchedAddr a;
-    a.mw = smem_addr(&s.mw[lane]);
-    a.col = smem_addr(&s.col[lane]);
-    a.slotI = smem_addr(&s.slots[warp_in_cta][0][0][lane]);
-    a.slotD = smem_addr(&s.slots[warp_in_cta][1][0][lane]);
-    a.redI = smem_addr(&s.slots[warp_in_cta][0][lane >> 2][(lane & 3) * 8]);
-    a.redD = smem_addr(&s.slots[warp_in_cta][1][lane >> 2][(lane & 3) * 8]);
+    a.mw = pinned(smem_addr(&s.mw[lane]));
+    a.col = pinned(smem_addr(&s.col[lane]));
+    a.slotI = pinned(smem_addr(&s.slots[warp_in_cta][0][0][lane]));
+    a.slotD = a.slotI + (unsigned)sizeof(float) * 8 * 32;
+    a.redI = pinned(smem_addr(&s.slots[warp_in_cta][0][lane >> 2][(lane & 3) * 8]));
+    a.redD = a.redI + (unsigned)sizeof(float) * 8 * 32;
     return a;
 }
 
 // Returns for lane t < n_tau: I = sum_{k>=1} c_k (1 - J0(a_t u_k)) and
 // Dm = sum_{k>=1} c_k m_tk J1(a_t u_k)  (m = |tau_t|/tau_ref * u_k), so dI/dA = Dm with a_t u_k = A m.
 // ph_lo / ph_hi: this lane's phase bounds (lane p < sched_phases holds phase p), hoisted by the caller.
+// Every pass evaluates TWO schedule entries per lane with packed FP32 (FFMA2): the kernels are issue-bound, and the
+// Horner chains of two entries cost one instruction slot per step instead of two.
 template <bool BWD>
 __device__ __forceinline__ void tissue_sched(int nph, const SchedAddr& sa, float A, int lane, float ph_lo, float ph_hi,
                                              int my_col, float& I_out, float& Dm_out) {
-    constexpr int kPassBytes = 32 * 8, kPhaseBytes = QBOLD_SCHED_PHASE_LEN * kPassBytes;
+    constexpr int kPairBytes = 32 * 16, kPairs = QBOLD_SCHED_PHASE_LEN / 2, kPhaseBytes = kPairs * kPairBytes;
     const bool is_ph = lane < nph;
     const float lo = A * ph_lo, hi = A * ph_hi;
     // one kernel for the whole phase whenever its argument span fits the kernel's validity range
@@ -365,47 +394,91 @@ __device__ __forceinline__ void tissue_sched(int nph, const SchedAddr& sa, float
     const unsigned PM = __ballot_sync(kFull, is_ph && lo >= coef::kMidLo && hi <= coef::kX2);
     const unsigned PB = __ballot_sync(kFull, is_ph && lo >= coef::kBigLo);
     const float invA = A > 0.f ? 1.0f / A : 0.f;
-    float accI = 0.f, accS = 0.f, accB = 0.f;
+    const f32x2 A2 = pk1(A);
+    f32x2 accI = pk1(0.f), accS = pk1(0.f), accB = pk1(0.f);
     unsigned ea = sa.mw, ca = sa.col;
 #pragma unroll 1
     for (int ph = 0; ph < nph; ++ph, ea += kPhaseBytes, ca += 32) {
         const unsigned bit = 1u << ph;
         if (PS & bit) {
 #pragma unroll
-            for (int c = 0; c < QBOLD_SCHED_PHASE_LEN; ++c) {
-                const float2 e = lds_f2(ea + c * kPassBytes);
-                acc_small<BWD>(A * e.x, e.y, accI, accS);
+            for (int c = 0; c < kPairs; ++c) {
+                const float4 e = lds_f4(ea + c * kPairBytes);
+                if (QB_PACK_SMALL) {
+                    acc_small2<BWD>(mul2(A2, pk2(e.x, e.y)), pk2(e.z, e.w), accI, accS);
+                } else {
+                    float i0, i1, s0, s1;
+                    upk2(accI, i0, i1);
+                    upk2(accS, s0, s1);
+                    acc_small<BWD>(A * e.x, e.z, i0, s0);
+                    acc_small<BWD>(A * e.y, e.w, i1, s1);
+                    accI = pk2(i0, i1);
+                    accS = pk2(s0, s1);
+                }
             }
         } else if (PM & bit) {
 #pragma unroll
-            for (int c = 0; c < QBOLD_SCHED_PHASE_LEN; ++c) {
-                const float2 e = lds_f2(ea + c * kPassBytes);
-                acc_mid<BWD>(A * e.x, e, accI, accB);
+            for (int c = 0; c < kPairs; ++c) {
+                const float4 e = lds_f4(ea + c * kPairBytes);
+                if (QB_PACK_MID) {
+                    const f32x2 m = pk2(e.x, e.y);
+                    acc_mid2<BWD>(mul2(A2, m), m, pk2(e.z, e.w), accI, accB);
+                } else {
+                    float i0, i1, b0, b1;
+                    upk2(accI, i0, i1);
+                    upk2(accB, b0, b1);
+                    acc_mid<BWD>(A * e.x, make_float2(e.x, e.z), i0, b0);
+                    acc_mid<BWD>(A * e.y, make_float2(e.y, e.w), i1, b1);
+                    accI = pk2(i0, i1);
+                    accB = pk2(b0, b1);
+                }
             }
         } else if (PB & bit) {
 #pragma unroll
-            for (int c = 0; c < QBOLD_SCHED_PHASE_LEN; ++c) {
-                const float2 e = lds_f2(ea + c * kPassBytes);
-                acc_big<BWD>(A * e.x, e, accI, accB);
+            for (int c = 0; c < kPairs; ++c) {
+                const float4 e = lds_f4(ea + c * kPairBytes);
+                if (QB_PACK_BIG) {
+                    const f32x2 m = pk2(e.x, e.y);
+                    acc_big2<BWD>(mul2(A2, m), m, pk2(e.z, e.w), accI, accB);
+                } else {
+                    float i0, i1, b0, b1;
+                    upk2(accI, i0, i1);
+                    upk2(accB, b0, b1);
+                    acc_big<BWD>(A * e.x, make_float2(e.x, e.z), i0, b0);
+                    acc_big<BWD>(A * e.y, make_float2(e.y, e.w), i1, b1);
+                    accI = pk2(i0, i1);
+                    accB = pk2(b0, b1);
+                }
             }
         } else {
-            // phase straddles a range boundary: decide per pass with warp votes (uniform branches); only the
-            // one pass that really straddles it takes the per-lane path
+            // phase straddles a range boundary: decide per packed pass with warp votes (uniform branches); only
+            // the pass that really straddles it takes the per-lane scalar path
 #pragma unroll 1
-            for (int c = 0; c < QBOLD_SCHED_PHASE_LEN; ++c) {
-                const float2 e = lds_f2(ea + c * kPassBytes);
-                const float x = A * e.x;
-                const bool le1 = x <= coef::kX1, le2 = x <= coef::kX2;
-                if (__all_sync(kFull, le1)) {
-                    acc_small<BWD>(x, e.y, accI, accS);
-                } else if (__all_sync(kFull, x >= coef::kMidLo && le2)) {
-                    acc_mid<BWD>(x, e, accI, accB);
-                } else if (__all_sync(kFull, x >= coef::kBigLo)) {
-                    acc_big<BWD>(x, e, accI, accB);
+            for (int c = 0; c < kPairs; ++c) {
+                const float4 e = lds_f4(ea + c * kPairBytes);
+                const float x0 = A * e.x, x1 = A * e.y;
+                const float xlo = fminf(x0, x1), xhi = fmaxf(x0, x1);
+                const f32x2 m = pk2(e.x, e.y), w = pk2(e.z, e.w), x = pk2(x0, x1);
+                if (__all_sync(kFull, xhi <= coef::kX1)) {
+                    acc_small2<BWD>(x, w, accI, accS);
+                } else if (__all_sync(kFull, xlo >= coef::kMidLo && xhi <= coef::kX2)) {
+                    acc_mid2<BWD>(x, m, w, accI, accB);
+                } else if (__all_sync(kFull, xlo >= coef::kBigLo)) {
+                    acc_big2<BWD>(x, m, w, accI, accB);
                 } else {
-                    if (le1) acc_small<BWD>(x, e.y, accI, accS);
-                    else if (le2) acc_mid<BWD>(x, e, accI, accB);
-                    else acc_big<BWD>(x, e, accI, accB);
+                    float i0, i1, s0, s1, b0, b1;
+                    upk2(accI, i0, i1);
+                    upk2(accS, s0, s1);
+                    upk2(accB, b0, b1);
+                    if (x0 <= coef::kX1) acc_small<BWD>(x0, e.z, i0, s0);
+                    else if (x0 <= coef::kX2) acc_mid<BWD>(x0, make_float2(e.x, e.z), i0, b0);
+                    else acc_big<BWD>(x0, make_float2(e.x, e.z), i0, b0);
+                    if (x1 <= coef::kX1) acc_small<BWD>(x1, e.w, i1, s1);
+                    else if (x1 <= coef::kX2) acc_mid<BWD>(x1, make_float2(e.y, e.w), i1, b1);
+                    else acc_big<BWD>(x1, make_float2(e.y, e.w), i1, b1);
+                    accI = pk2(i0, i1);
+                    accS = pk2(s0, s1);
+                    accB = pk2(b0, b1);
                 }
             }
         }
@@ -418,11 +491,11 @@ __device__ __forceinline__ void tissue_sched(int nph, const SchedAddr& sa, float
             oldI = lds_f1(sa.slotI + off);
             if (BWD) oldD = lds_f1(sa.slotD + off);
         }
-        sts_f1(sa.slotI + off, oldI + accI);
-        accI = 0.f;
+        sts_f1(sa.slotI + off, oldI + hsum2(accI));
+        accI = pk1(0.f);
         if (BWD) {
-            sts_f1(sa.slotD + off, oldD + fmaf(accS, invA, accB));
-            accS = accB = 0.f;
+            sts_f1(sa.slotD + off, oldD + fmaf(hsum2(accS), invA, hsum2(accB)));
+            accS = accB = pk1(0.f);
         }
     }
     __syncwarp();
