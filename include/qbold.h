@@ -129,6 +129,22 @@ int qbold_forward(const QboldParams* p, const float* oef_dbv, int32_t width, int
 int qbold_forward_backward(const QboldParams* p, const float* oef_dbv, const float* g_signal,
                            int64_t n, float* signal, float* g_oef_dbv, void* stream);
 
+/* variable_hct=True (signals.py:64-70): rows are (OEF, DBV, Hct); g_oef_dbv_hct[n,3] also carries
+ * d/dHct (through dw = (4/3) pi gamma B0 dchi Hct OEF, signals.py:142-144, and the blood term's
+ * G0 ~ Hct (1 - Hct), signals.py:239). */
+int qbold_forward_backward_hct(const QboldParams* p, const float* oef_dbv_hct, const float* g_signal,
+                               int64_t n, float* signal, float* g_oef_dbv_hct, void* stream);
+
+/* Misalignment augmentation of SignalGenerationLayer.call (signals.py:80-96), applied to `signal`
+ * [n,n_tau] = the noise-free forward model of oef_dbv [n,width]: voxels with sel_u01 < prob get, for
+ * the images after from_index (in [4, n_tau-1)), the signal of OEF + 0.15 eps[.,0] clipped to
+ * [0.05,0.8] and DBV + 0.05 eps[.,1] clipped to [0.002,0.3].  sel_u01 [n], from_index [n] (int32),
+ * eps [n,2]: the reference's draws (all three or none); NULL = Philox (seed, offset + voxel,
+ * stream 0x20000).  QBOLD_EUNSUPPORTED when n_tau <= 5 (the reference's randint range is empty). */
+int qbold_misalign(const QboldParams* p, const float* oef_dbv, int32_t width, int64_t n, float prob,
+                   const float* sel_u01, const int32_t* from_index, const float* eps, uint64_t seed,
+                   uint64_t offset, float* signal, void* stream);
+
 /* Same call with HOST buffers: chunked, double-buffered H2D -> kernel -> D2H on
  * internal streams of the current device; returns after the results are in host memory. */
 int qbold_forward_backward_host(const QboldParams* p, const float* h_oef_dbv, const float* h_g_signal,
@@ -224,6 +240,23 @@ int qbold_smoothness(const float* q, int32_t n_ch, const float* mask, int64_t n_
 int qbold_synth_nll(const float* labels, int32_t label_stride, const float* pred, int32_t use_mvg,
                     double inv_gamma_alpha, double inv_gamma_beta, int64_t n, float grad_scale, float* nll_rows,
                     float* grad_pred, double* loss_sum, void* stream);
+
+/* synthetic_data_loss with infer_inv_gamma=True (model.py:454-455,493-496): the InverseGamma parameters are
+ * LEARNED.  inv_gamma_params (DEVICE pointer, 4 floats: alpha_oef, beta_oef, alpha_dbv, beta_dbv -- the exp() of the
+ * encoder's hyper-prior variables, model.py:201-205).  pred rows have stride pred_stride (the reference layout is
+ * [q | 4 hyper-prior channels]); grad_pred is [n, 5|4] dense.  ig_sums (double[4], caller zeroes, may be NULL) +=
+ * (sum log v_oef, sum 1/v_oef, sum log v_dbv, sum 1/v_dbv), from which d loss / d(alpha, beta) follow in closed
+ * form: d/dalpha = -(n (log beta - digamma(alpha)) - sum log v), d/dbeta = -(n alpha / beta - sum 1/v). */
+int qbold_synth_nll_inferred(const float* labels, int32_t label_stride, const float* pred, int32_t pred_stride,
+                             int32_t use_mvg, const float* inv_gamma_params, int64_t n, float grad_scale,
+                             float* nll_rows, float* grad_pred, double* loss_sum, double* ig_sums, void* stream);
+
+/* Mixture-of-Gaussians population prior of kl_loss (model.py:666-684; use_mvg=False, mog_components = M > 1):
+ * pred [n, 4 (M+1)] = q then M components (mean, raw std of OEF and DBV each); single-sample estimate with the
+ * draws eps [n,2] (NULL = Philox (seed, offset + voxel, stream 0)).  kl_map [n] (0 where mask <= 0; mask may be
+ * NULL), grad_pred [n, 4 (M+1)] (may be NULL) = d kl_map[v] / d pred[v,:]. */
+int qbold_mog_kl(const float* pred, int32_t n_components, const float* mask, const float* eps, uint64_t seed,
+                 uint64_t offset, int64_t n, float* kl_map, float* grad_pred, void* stream);
 
 /* KL of the diagonal (use_mvg=False) branch of kl_loss (model.py:685-708): tfp LogitNormal.kl_divergence for OEF
  * plus DBV, zero where mask <= 0 (mask may be NULL).  pred / prior rows = [mean_o, raw_std_o, mean_d, raw_std_d]

@@ -163,6 +163,72 @@ def main():
                  dbv_tn_u01=log[3][1].numpy(), uniform_prop=uprop, sample_size=23)
         print('dataset[%s]: x %s y %s' % (tag, tuple(tx.shape), tuple(ty.shape)))
 
+    # ------------------------------------------------------------------ D2. dataset with misalignment / variable Hct
+    def small_params():
+        p2 = configparser.ConfigParser()
+        p2.read(os.path.join(args.ref, 'config'))
+        p2 = p2['DEFAULT']
+        p2['sample_size'] = '23'
+        return p2
+
+    tf.random.set_seed(8)
+    tf.random.LOG.clear()
+    prob = 0.3
+    tx, ty = ref_signals.create_synthetic_dataset(small_params(), True, True, prob, uniform_prop=0.1)
+    log = tf.random.LOG
+    kinds = [k for k, _ in log]
+    assert kinds[:5] == ['uniform', 'normal', 'uniform', 'truncnorm_u', 'perm'], kinds[:5]
+    assert kinds[5:11] == ['uniform', 'uniform_int', 'normal', 'normal', 'uniform', 'normal'], kinds[5:11]
+    cat = lambda j: np.concatenate([log[5 + 6 * i + j][1].numpy() for i in range(10)], 0)
+    np.savez(os.path.join(args.out, 'ref_shim_dataset_misalign.npz'),
+             train_x=tx.numpy(), train_y=ty.numpy(), perm=log[4][1].numpy(), prob=prob,
+             mis_u01=cat(0).reshape(-1), mis_index=cat(1).reshape(-1).astype(np.int32),
+             mis_eps=np.concatenate([cat(2), cat(3)], -1), snr_u01=cat(4), noise_eps=cat(5), sample_size=23)
+    print('dataset[misalign]: x %s, %d of %d rows misaligned' % (tuple(tx.shape), int((cat(0) < prob).sum()), tx.shape[0]))
+
+    tf.random.set_seed(9)
+    tf.random.LOG.clear()
+    tx, ty = ref_signals.create_synthetic_dataset(small_params(), True, True, 0.0, variable_hct=True, uniform_prop=0.1)
+    log = tf.random.LOG
+    kinds = [k for k, _ in log]
+    assert kinds[:6] == ['uniform', 'normal', 'uniform', 'truncnorm_u', 'uniform', 'perm'], kinds[:6]
+    np.savez(os.path.join(args.out, 'ref_shim_dataset_hct.npz'),
+             train_x=tx.numpy(), train_y=ty.numpy(), perm=log[5][1].numpy(),
+             snr_u01=np.concatenate([log[6 + 2 * i][1].numpy() for i in range(10)], 0),
+             noise_eps=np.concatenate([log[7 + 2 * i][1].numpy() for i in range(10)], 0), sample_size=23)
+    print('dataset[variable_hct]: x %s y %s' % (tuple(tx.shape), tuple(ty.shape)))
+
+    # ------------------------------------------------------------------ A2. variable Hct: forward + tape.gradient
+    n3 = 96
+    x3 = np.stack([rng.uniform(0.04, 0.84, n3), rng.uniform(0.001, 0.201, n3), rng.uniform(0.2, 0.55, n3)], -1)
+    x3 = x3.astype(np.float32)
+    x3[:2] = [[0.4, 0.12, 0.34], [0.4, 0.03, 0.45]]
+    g3 = rng.standard_normal((n3, 11)).astype(np.float32)
+    out3 = {'oef_dbv_hct': x3, 'g_rand': g3}
+    for full in (True, False):
+        for blood in (True, False):
+            layer = ref_signals.SignalGenerationLayer(params, full, blood, variable_hct=True)
+            key = 'f%d_b%d' % (int(full), int(blood))
+            inp = tf.convert_to_tensor(x3.reshape(n3, 1, 1, 1, 3))
+            with tf.GradientTape(persistent=True) as tape:
+                tape.watch(inp)
+                o3 = layer(inp)
+                o3_w = o3 * tf.convert_to_tensor(g3.reshape(n3, 1, 1, 1, 11))
+            out3['signal_' + key] = o3.detach().numpy().reshape(n3, 11)
+            out3['grad_ones_' + key] = tape.gradient(o3, inp).numpy().reshape(n3, 3)
+            out3['grad_rand_' + key] = tape.gradient(o3_w, inp).numpy().reshape(n3, 3)
+    # misalignment on the layer itself with a variable-Hct input (signals.py:80-96 with hct [N,1])
+    tf.random.set_seed(10)
+    tf.random.LOG.clear()
+    layer = ref_signals.SignalGenerationLayer(params, True, True, misaligned_prob=0.4, variable_hct=True)
+    o3 = layer(tf.convert_to_tensor(x3))
+    lg = tf.random.LOG
+    assert [k for k, _ in lg] == ['uniform', 'uniform_int', 'normal', 'normal']
+    out3.update(mis_prob=0.4, mis_u01=lg[0][1].numpy().reshape(-1), mis_index=lg[1][1].numpy().reshape(-1).astype(np.int32),
+                mis_eps=np.concatenate([lg[2][1].numpy(), lg[3][1].numpy()], -1), signal_misaligned=o3.numpy())
+    np.savez(os.path.join(args.out, 'ref_shim_forward_hct.npz'), **out3)
+    print('forward[variable_hct]: demo input ->', out3['signal_f1_b1'][0])
+
     # ------------------------------------------------------------------ F. losses either side of the path
     def make_trainer(**kw):
         base = dict(system_params=params, no_units=60, no_intermediate_layers=2, student_t_df=200,
@@ -218,6 +284,19 @@ def main():
         adj['synth_%s' % tag] = loss.detach().numpy()
         adj['synth_%s_grad' % tag] = torch.autograd.grad(loss, [q_t])[0].numpy().reshape(nv, c)
         adj['synth_%s_labels' % tag] = lab
+    # F2a' infer_inv_gamma (model.py:454-455,493-496): learned InverseGamma parameters ride in 4 extra channels
+    tr_i = make_trainer(use_mvg=False, infer_inv_gamma=True)
+    lab = labels.copy()
+    lab[0, :2] = [0.3, 0.05]
+    ig = np.array([18.0, 2.2, 23.0, 2.9], np.float32)
+    q8 = np.concatenate([q5[:, :4], np.tile(ig[None, :], (nv, 1))], -1).astype(np.float32)
+    q_t = tf.convert_to_tensor(q8.reshape(nv, 1, 1, 1, 8))
+    q_t.requires_grad_(True)
+    loss = tr_i.synthetic_data_loss(tf.convert_to_tensor(lab.reshape(nv, 1, 1, 1, 3)), q_t, False, 0.0, 0.0)
+    adj['synth_iginf'] = loss.detach().numpy()
+    adj['synth_iginf_grad'] = torch.autograd.grad(loss, [q_t])[0].numpy().reshape(nv, 8)
+    adj['synth_iginf_pred'] = q8
+    adj['synth_iginf_labels'] = lab
     # F2b r2p term (10 recorded reparam draws, model.py:480-494)
     tf.random.set_seed(21)
     tf.random.LOG.clear()

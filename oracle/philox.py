@@ -10,7 +10,7 @@ import numpy as np
 
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
-STREAM_REPARAM, STREAM_KL, STREAM_SNR, STREAM_NOISE = 0, 0x100, 0x10000, 0x10001
+STREAM_REPARAM, STREAM_KL, STREAM_SNR, STREAM_NOISE, STREAM_MISALIGN = 0, 0x100, 0x10000, 0x10001, 0x20000
 _MASK32 = np.uint64(0xFFFFFFFF)
 
 
@@ -92,6 +92,17 @@ def noise_eps(seed, index, n_tau):
     for t in range(0, n_tau, 2):
         out[:, t], out[:, t + 1] = normal_pair(seed, index, STREAM_NOISE + (t >> 1))
     return out[:, :n_tau]
+
+
+def misalign_draws(seed, index, n_tau):
+    """Misalignment draws of a voxel (forward.cu k_misalign): one Philox call (index, STREAM_MISALIGN); x -> selection
+    uniform, y -> first misaligned image in [4, n_tau - 1), (z, w) -> the OEF / DBV normals."""
+    lo, hi, k0, k1 = _words(index, seed)
+    r = philox4x32_10(lo, hi, np.uint32(STREAM_MISALIGN), np.uint32(0), k0, k1)
+    span = n_tau - 1 - 4
+    idx = 4 + np.minimum((u01(r[1]) * np.float32(span)).astype(np.int32), span - 1)
+    e0, e1 = box_muller(r[2], r[3])
+    return u01(r[0]), idx.astype(np.int32), np.stack([e0, e1], -1)
 
 
 def _feistel_round(r, key):

@@ -178,7 +178,7 @@ def m_bld(ph: Physics, dt):
 
 
 def calc_tissue(ph: Physics, oef, dbv, hct=None, full_model=True, dtype=F32, chunk=4096,
-                want_grad=False, g_out=None):
+                want_grad=False, g_out=None, want_hct=False):
     """calc_tissue (signals.py:152-209).
 
     oef, dbv: [N] arrays.  Returns S_t [N, n_tau]; with ``want_grad`` also the
@@ -199,6 +199,8 @@ def calc_tissue(ph: Physics, oef, dbv, hct=None, full_model=True, dtype=F32, chu
     out = np.empty((n, nt), dtype=dt)
     g_oef = np.zeros(n, dtype=dt) if want_grad else None
     g_dbv = np.zeros(n, dtype=dt) if want_grad else None
+    g_hct = np.zeros(n, dtype=dt) if want_grad else None          # d/d hct through dw = K0 * hct * oef (:142-144)
+    K0 = dt(dw_const(ph, 1.0))
 
     if not full_model:
         # log-linear branch, signals.py:194-207
@@ -226,7 +228,10 @@ def calc_tissue(ph: Physics, oef, dbv, hct=None, full_model=True, dtype=F32, chu
             g_r2p = (g_rt * taus[None, :]).sum(-1)
             g_dbv[:] = g_dbv_a + g_dbv_b + g_r2p * dw
             g_oef[:] = g_r2p * dbv * K
-        return (out, g_oef, g_dbv) if want_grad else out
+            g_hct[:] = g_r2p * dbv * (K0 * oef)
+        if want_grad:
+            return (out, g_oef, g_dbv, g_hct) if want_hct else (out, g_oef, g_dbv)
+        return out
 
     u32 = quad_nodes()
     u = u32.astype(dt)
@@ -262,10 +267,13 @@ def calc_tissue(ph: Physics, oef, dbv, hct=None, full_model=True, dtype=F32, chu
             g_t = (g_arg * (dt(1.5) * u)[None, None, :]).sum(-1, dtype=dt)
             g_dw = (g_t * taus[None, :]).sum(-1, dtype=dt)
             g_oef[sl] = g_dw * Ks
-    return (out, g_oef, g_dbv) if want_grad else out
+            g_hct[sl] = g_dw * (K0 * oef[sl])
+    if want_grad:
+        return (out, g_oef, g_dbv, g_hct) if want_hct else (out, g_oef, g_dbv)
+    return out
 
 
-def calc_blood(ph: Physics, oef, hct=None, dtype=F32, want_grad=False, g_out=None):
+def calc_blood(ph: Physics, oef, hct=None, dtype=F32, want_grad=False, g_out=None, want_hct=False):
     """calc_blood, live branch (signals.py:233-247)."""
     dt = dtype
     hct = ph.hct if hct is None else hct
@@ -287,6 +295,9 @@ def calc_blood(ph: Physics, oef, hct=None, dtype=F32, want_grad=False, g_out=Non
     g_G = (g * sb * (-B[None, :])).sum(-1)
     g_g0 = g_G * dt(0.5 * (ph.gamma ** 2)) * dt(td ** 2)
     g_base = g_g0 * c0 * dt(2.0) * base
+    if want_hct:                                                  # c0 = (4/45) hct (1 - hct)
+        g_hct = (g_g0 * base ** 2) * (dt(4 / 45) * (dt(1.0) - dt(2.0) * np.asarray(hct, dtype=dt).reshape(-1)))
+        return sb, g_base * dt(c1), g_hct
     return sb, g_base * dt(c1)
 
 
@@ -313,12 +324,28 @@ def forward(ph: Physics, oef_dbv, full_model=True, include_blood=True, dtype=F32
 
 
 def forward_backward(ph: Physics, oef_dbv, g_signal, full_model=True, include_blood=True,
-                     dtype=F32, chunk=4096):
+                     dtype=F32, chunk=4096, variable_hct=False):
     """Forward plus the TF-autodiff-consistent vector-Jacobian product.
 
-    Returns (S [N,n_tau], g_oef_dbv [N,2]) for upstream gradient g_signal [N,n_tau].
+    Returns (S [N,n_tau], g_oef_dbv [N,2]) for upstream gradient g_signal [N,n_tau];
+    with ``variable_hct`` rows are (OEF, DBV, Hct) and the gradient is [N,3] (signals.py:64-70).
     Chain (what tape.gradient would do for signals.py:98-114): mix -> tissue / blood."""
     dt = dtype
+    if variable_hct:
+        flat = np.asarray(oef_dbv).reshape(-1, 3).astype(dt)
+        g = np.asarray(g_signal).reshape(-1, ph.n_tau).astype(dt)
+        oef, dbv, hct = flat[:, 0], flat[:, 1], flat[:, 2]
+        kappa = m_bld(ph, dt) * dt(NB) if include_blood else dt(1.0)
+        bw = kappa * dbv
+        tw = dt(1.0) - bw
+        st, go_t, gd_t, gh_t = calc_tissue(ph, oef, dbv, hct, full_model, dt, chunk, True, g * tw[:, None], True)
+        if include_blood:
+            sb, go_b, gh_b = calc_blood(ph, oef, hct, dt, True, g * bw[:, None], True)
+        else:
+            sb, go_b, gh_b = np.zeros_like(st), np.zeros_like(oef), np.zeros_like(oef)
+        sig = tw[:, None] * st + bw[:, None] * sb
+        g_dbv = gd_t + kappa * (g * (sb - st)).sum(-1)
+        return sig, np.stack([go_t + go_b, g_dbv, gh_t + gh_b], -1).astype(dt)
     flat = np.asarray(oef_dbv).reshape(-1, 2).astype(dt)
     g = np.asarray(g_signal).reshape(-1, ph.n_tau).astype(dt)
     oef, dbv = flat[:, 0], flat[:, 1]
@@ -341,6 +368,26 @@ def forward_backward(ph: Physics, oef_dbv, g_signal, full_model=True, include_bl
     g_dbv = gd_t + kappa * g_bw
     g_oef = go_t + go_b
     return sig, np.stack([g_oef, g_dbv], -1).astype(dt)
+
+
+def forward_misaligned(ph: Physics, oef_dbv, prob, sel_u01, from_index, eps, full_model=True, include_blood=True,
+                       dtype=F32, variable_hct=False):
+    """SignalGenerationLayer.call with misaligned_prob > 0, noise off (signals.py:80-96), explicit draws:
+    sel_u01 [N] (uniform of :82), from_index [N] (randint of :84-85), eps [N,2] (the normals of :92-93).
+    The reference turns OEF/DBV into per-image [N,n_tau] tensors; each image's signal depends on its own pair only,
+    so the result is the per-image selection between the forward model of the original and the perturbed pair."""
+    dt = dtype
+    x = np.asarray(oef_dbv).astype(dt)
+    x = x.reshape(-1, x.shape[-1])
+    base = forward(ph, x, full_model, include_blood, dt, variable_hct)
+    mis = np.asarray(sel_u01, dtype=dt).reshape(-1) < dt(prob)                                    # :82
+    late = (np.arange(ph.n_tau)[None, :] > np.asarray(from_index).reshape(-1, 1)) & mis[:, None]  # :86-88
+    e = np.asarray(eps, dtype=dt).reshape(-1, 2)
+    pert = x.copy()
+    pert[:, 0] = np.clip(e[:, 0] * dt(0.15) + x[:, 0], dt(0.05), dt(0.8))                        # :92
+    pert[:, 1] = np.clip(e[:, 1] * dt(0.05) + x[:, 1], dt(0.002), dt(0.3))                       # :93
+    alt = forward(ph, pert, full_model, include_blood, dt, variable_hct)
+    return np.where(late, alt, base)                                                              # :95-96
 
 
 def add_noise(signal, snr_u, eps, dtype=F32):
@@ -532,7 +579,7 @@ def elbo_and_grads(ph: Physics, q, sigma, y, mask, prior, eps, eps_kl, dt=F32,
     Follows build_fine_tuner (model.py:239-286): sample -> forward model -> loss.
     Gradients are TF-autodiff-consistent: stop_gradient on q inside log q
     (model.py:596), identity gradient through the clip (model.py:395), bessel_j0'=-j1.
-    Returns dict(nll, kl, grad_q, grad_sigma, nll_map, kl_map)."""
+    Returns dict(nll, kl, grad_q, grad_sigma, nll_map, kl_map, grad_q_nll, grad_q_kl)."""
     q = np.asarray(q, dtype=dt).reshape(-1, 5)
     n = q.shape[0]
     nt = ph.n_tau
@@ -644,7 +691,8 @@ def elbo_and_grads(ph: Physics, q, sigma, y, mask, prior, eps, eps_kl, dt=F32,
     kl = kl_map.sum(dtype=dt) / msum
     return dict(nll=dt(nll), kl=dt(kl), elbo=dt(nll + dt(kl_weight) * kl),
                 grad_q=(grad_q + dt(kl_weight) * grad_q_kl).astype(dt), grad_sigma=g_sigma.astype(dt),
-                nll_map=nll_map, kl_map=kl_map, pred=pred)
+                nll_map=nll_map, kl_map=kl_map, pred=pred,
+                grad_q_nll=grad_q.astype(dt), grad_q_kl=grad_q_kl.astype(dt))
 
 
 # --------------------------------------------------------------------------
@@ -669,25 +717,38 @@ def posterior_stats(ph: Physics, q, eps_s, dt=F32):
 # synthetic data generation (signals.py:251-300) with explicit draws
 # --------------------------------------------------------------------------
 def synthetic_dataset_from_draws(ph: Physics, oefs, dbvs, perm, snr_u=None, noise_eps=None,
-                                 full_model=True, use_blood=True, dt=F32, n_chunks=10):
-    """create_synthetic_dataset after the random draws: meshgrid ('ij') -> shuffle
-    (explicit permutation) -> 10 chunked forward calls (noise std is a per-chunk
-    statistic, signals.py:126,282-285) -> labels [OEF, DBV, R2']."""
+                                 full_model=True, use_blood=True, dt=F32, n_chunks=10, misalign=None,
+                                 variable_hct=False):
+    """create_synthetic_dataset after the random draws: meshgrid ('ij') -> [constant Hct column 0.34 with
+    variable_hct, signals.py:273-276] -> shuffle (explicit permutation) -> 10 chunked layer calls (misalignment
+    :80-96 with ``misalign`` = (prob, sel_u01 [n], from_index [n], eps [n,2]) concatenated over the chunks, then the
+    noise, whose std is a per-chunk statistic :126,282-285) -> labels [OEF, DBV, R2']."""
     oefs = np.asarray(oefs, dtype=dt)
     dbvs = np.asarray(dbvs, dtype=dt)
     xx, yy = np.meshgrid(oefs, dbvs, indexing='ij')                  # :270
-    train_y = np.stack([xx.reshape(-1), yy.reshape(-1)], 1)[np.asarray(perm)]   # :271,279
+    train_y = np.stack([xx.reshape(-1), yy.reshape(-1)], 1)
+    if variable_hct:
+        train_y = np.concatenate([train_y, np.full((train_y.shape[0], 1), 0.34, dtype=dt)], -1)   # :273-276
+    train_y = train_y[np.asarray(perm)]                              # :279
     n = train_y.shape[0]
     chunk = n // n_chunks                                            # :283
     xs = []
     for i in range(n_chunks):
         sl = slice(i * chunk, (i + 1) * chunk)
-        s = forward(ph, train_y[sl], full_model, use_blood, dt)
+        if misalign is not None:
+            prob, mu, mi, me = misalign
+            s = forward_misaligned(ph, train_y[sl], prob, mu[sl], mi[sl], me[sl], full_model, use_blood, dt,
+                                   variable_hct)
+        else:
+            s = forward(ph, train_y[sl], full_model, use_blood, dt, variable_hct)
         if ph.simulate_noise:
             s = add_noise(s, snr_u[sl], noise_eps[sl], dt)
         xs.append(s)
     train_x = np.concatenate(xs, 0)                                  # rows beyond 10*chunk are dropped (:283-287)
-    r2p = calculate_r2p(ph, train_y[:, 0], train_y[:, 1], None, dt)  # :296
+    if variable_hct:
+        r2p = (dt(dw_const(ph, 1.0)) * train_y[:, 2] * train_y[:, 0]) * train_y[:, 1]             # :293-294
+    else:
+        r2p = calculate_r2p(ph, train_y[:, 0], train_y[:, 1], None, dt)  # :296
     return train_x, np.concatenate([train_y[:, :2], r2p[:, None]], -1).astype(dt)
 
 

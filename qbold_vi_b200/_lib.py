@@ -61,6 +61,9 @@ _SIGNATURES = {
     'qbold_params_set_likelihood': (C.c_int, [_P(QboldParams), _P(QboldLikelihood)]),
     'qbold_forward': (C.c_int, [_P(QboldParams), _f, C.c_int32, C.c_int64, _f, C.c_void_p]),
     'qbold_forward_backward': (C.c_int, [_P(QboldParams), _f, _f, C.c_int64, _f, _f, C.c_void_p]),
+    'qbold_forward_backward_hct': (C.c_int, [_P(QboldParams), _f, _f, C.c_int64, _f, _f, C.c_void_p]),
+    'qbold_misalign': (C.c_int, [_P(QboldParams), _f, C.c_int32, C.c_int64, C.c_float, _f, _f, _f, C.c_uint64, C.c_uint64,
+                                 _f, C.c_void_p]),
     'qbold_forward_backward_host': (C.c_int, [_P(QboldParams), _f, _f, C.c_int64, _f, _f]),
     'qbold_reparam_sample': (C.c_int, [_f, _f, C.c_uint64, C.c_uint64, C.c_int64, _f, C.c_void_p]),
     'qbold_column_mean': (C.c_int, [_f, C.c_int64, C.c_int32, _f, _f, C.c_void_p]),
@@ -81,6 +84,9 @@ _SIGNATURES = {
                                    C.c_void_p]),
     'qbold_synth_nll': (C.c_int, [_f, C.c_int32, _f, C.c_int32, C.c_double, C.c_double, C.c_int64, C.c_float, _f, _f,
                                   _f, C.c_void_p]),
+    'qbold_synth_nll_inferred': (C.c_int, [_f, C.c_int32, _f, C.c_int32, C.c_int32, _f, C.c_int64, C.c_float, _f, _f, _f,
+                                           _f, C.c_void_p]),
+    'qbold_mog_kl': (C.c_int, [_f, C.c_int32, _f, _f, C.c_uint64, C.c_uint64, C.c_int64, _f, _f, C.c_void_p]),
     'qbold_diag_kl': (C.c_int, [_f, C.c_int32, _f, C.c_int32, _f, C.c_int64, _f, _f, C.c_int32, _f, C.c_int32,
                                 C.c_void_p]),
     'qbold_encoder_mlp_blob_floats': (C.c_int, [C.c_int32]),

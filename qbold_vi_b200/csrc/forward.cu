@@ -3,6 +3,7 @@
 // tape.gradient does through it (bessel_j0' = -bessel_j1, node 0 value-dead / gradient-live).
 #include "qbold_core.cuh"
 #include "launch.h"
+#include "rng.cuh"
 
 #ifndef QB_FWD_MIN_BLOCKS
 #define QB_FWD_MIN_BLOCKS 5
@@ -55,8 +56,72 @@ __global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward(const _
             float gd = live ? gs * ts.dS_ddbv : 0.f;
             go = warp_sum(go);
             gd = warp_sum(gd);
-            if (lane == 0) *reinterpret_cast<float2*>(g_oef_dbv + v * 2) = make_float2(go, gd);
+            if (HCT) {
+                const float gh = warp_sum(live ? gs * ts.dS_dhct : 0.f);
+                if (lane < 3) g_oef_dbv[v * 3 + lane] = lane == 0 ? go : (lane == 1 ? gd : gh);
+            } else if (lane == 0) {
+                *reinterpret_cast<float2*>(g_oef_dbv + v * 2) = make_float2(go, gd);
+            }
         }
+    }
+}
+
+// Misalignment augmentation (reference signals.py:80-96).  A Bernoulli(prob) subset of the voxels is "misaligned":
+// the images after a random index in [4, n_tau - 1) see perturbed parameters, OEF + N(0, 0.15) clipped to
+// [0.05, 0.8] and DBV + N(0, 0.05) clipped to [0.002, 0.3].  The reference makes OEF/DBV per-image tensors and runs
+// the whole forward model on them; every image's signal depends on its own parameters only, so this kernel
+// recomputes the forward model of the selected voxels with the perturbed pair and overwrites the late images of
+// `signal` (which holds the unperturbed forward model).  Voxels come from the work counter: the ~90 % that are not
+// selected cost one Philox call.  Draws: explicit arrays (parity tests feed the reference's recorded draws) or
+// Philox call (seed, global voxel index, kStreamMisalign): x -> selection, y -> index, (z, w) -> the two normals.
+template <bool HCT, int PATH>
+__global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_misalign(
+    const __grid_constant__ QboldParams P, const float* __restrict__ oef_dbv, int64_t n, float prob,
+    const float* __restrict__ sel_u01, const int32_t* __restrict__ from_index, const float* __restrict__ eps,
+    uint64_t seed, uint64_t offset, float* __restrict__ signal, unsigned long long* __restrict__ work) {
+    __shared__ QuadSmem s;
+    __shared__ SchedSmem ss;
+    if (P.full_model) {
+        if (PATH == kSched) load_sched(P, ss);
+        else load_quad_tables(P, s);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nt = P.n_tau;
+    const bool live = lane < nt;
+    const int my_col = live ? P.col_of_tau[lane] : -1;
+    const float my_tau = live ? P.tau[lane] : 0.f;
+    const float my_b = live ? P.blood_b[lane] : 0.f;
+    constexpr int W = HCT ? 3 : 2;
+    const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
+    const int span = nt - 1 - 4;                               // tf.random.uniform(minval=4, maxval=n_tau-1, int32)
+
+    for (int64_t v = next_unit(work, lane), nxt_unit; v < n; v = nxt_unit) {
+        nxt_unit = next_unit(work, lane);
+        float u, e0, e1;
+        int idx;
+        if (sel_u01 != nullptr && from_index != nullptr && eps != nullptr) {
+            u = __ldg(sel_u01 + v);
+            idx = __ldg(from_index + v);
+            e0 = __ldg(eps + v * 2);
+            e1 = __ldg(eps + v * 2 + 1);
+        } else {
+            const uint64_t g = offset + (uint64_t)v;
+            const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), kStreamMisalign, 0u, (uint32_t)seed,
+                                       (uint32_t)(seed >> 32));
+            u = u01(r.x);
+            idx = 4 + min((int)(u01(r.y) * (float)span), span - 1);
+            box_muller(r.z, r.w, e0, e1);
+        }
+        if (!(u < prob)) continue;                             // warp-uniform
+        const float oef = fminf(fmaxf(__fadd_rn(__fmul_rn(e0, 0.15f), __ldg(oef_dbv + v * W)), 0.05f), 0.8f);
+        const float dbv = fminf(fmaxf(__fadd_rn(__fmul_rn(e1, 0.05f), __ldg(oef_dbv + v * W + 1)), 0.002f), 0.3f);
+        const float hct = HCT ? __ldg(oef_dbv + v * W + 2) : P.hct;
+        const VoxelPhys vp = voxel_phys<HCT>(P, oef, dbv, hct);
+        float I = 0.f, dI = 0.f;
+        if (P.full_model) tissue_eval<false, PATH>(P, s, ss, qc, vp.dw, vp.dw_k, I, dI);
+        const TauSignal ts = tau_signal<false>(P, vp, my_tau, my_b, I, dI);
+        if (live && lane > idx) signal[v * nt + lane] = ts.S;
     }
 }
 
@@ -237,9 +302,69 @@ static int launch_forward(const QboldParams* p, const float* oef_dbv, const floa
                                  : launch_forward_t<BWD, HCT, kCols>(p, oef_dbv, g, signal, grad, n, st);
 }
 
+template <bool HCT, int PATH>
+static int launch_misalign_t(const QboldParams* p, const float* oef_dbv, int64_t n, float prob, const float* u,
+                             const int32_t* idx, const float* eps, uint64_t seed, uint64_t offset, float* signal,
+                             cudaStream_t st) {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_misalign<HCT, PATH>, kThreads, 0) !=
+                cudaSuccess || blocks_per_sm < 1)
+            blocks_per_sm = 1;
+    }
+    const int64_t want = (n + (kThreads / 32) - 1) / (kThreads / 32);
+    int64_t grid = (int64_t)sm_count() * blocks_per_sm;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    unsigned long long* work = next_work_counter(st);
+    if (!work) return fail(QBOLD_ECUDA, "qbold_misalign: work counter unavailable");
+    k_misalign<HCT, PATH><<<(unsigned)grid, kThreads, 0, st>>>(*p, oef_dbv, n, prob, u, idx, eps, seed, offset, signal,
+                                                              work);
+    return after_launch("k_misalign");
+}
+
+template <bool HCT>
+static int launch_misalign(const QboldParams* p, const float* oef_dbv, int64_t n, float prob, const float* u,
+                           const int32_t* idx, const float* eps, uint64_t seed, uint64_t offset, float* signal,
+                           cudaStream_t st) {
+    if (p->sched_phases > 0) return launch_misalign_t<HCT, kSched>(p, oef_dbv, n, prob, u, idx, eps, seed, offset, signal, st);
+    return p->n_cols > kColGroup
+               ? launch_misalign_t<HCT, kColsMulti>(p, oef_dbv, n, prob, u, idx, eps, seed, offset, signal, st)
+               : launch_misalign_t<HCT, kCols>(p, oef_dbv, n, prob, u, idx, eps, seed, offset, signal, st);
+}
+
 }  // namespace qb
 
 using namespace qb;
+
+extern "C" int qbold_misalign(const QboldParams* p, const float* oef_dbv, int32_t width, int64_t n, float prob,
+                              const float* sel_u01, const int32_t* from_index, const float* eps, uint64_t seed,
+                              uint64_t offset, float* signal, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_misalign: bad params block");
+    if (width != 2 && width != 3)
+        return fail(QBOLD_EINVAL, "Input should have 2 (OEF, DBV) or 3 (OEF, DBV, hct) elements in last dimension");
+    if (n < 0 || (n > 0 && (!oef_dbv || !signal))) return fail(QBOLD_EINVAL, "qbold_misalign: null pointer");
+    const bool any = sel_u01 || from_index || eps, all = sel_u01 && from_index && eps;
+    if (any && !all)
+        return fail(QBOLD_EINVAL, "qbold_misalign: pass all of sel_u01, from_index and eps, or none of them");
+    if (p->n_tau - 1 <= 4)
+        return fail(QBOLD_EUNSUPPORTED, "misalignment draws the first misaligned image from [4, n_tau - 1): needs "
+                                        "n_tau > 5 (signals.py:84-85), got %d", p->n_tau);
+    if (n == 0 || !(prob > 0.f)) return QBOLD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    return width == 3 ? launch_misalign<true>(p, oef_dbv, n, prob, sel_u01, from_index, eps, seed, offset, signal, st)
+                      : launch_misalign<false>(p, oef_dbv, n, prob, sel_u01, from_index, eps, seed, offset, signal, st);
+}
+
+extern "C" int qbold_forward_backward_hct(const QboldParams* p, const float* oef_dbv_hct, const float* g_signal,
+                                          int64_t n, float* signal, float* g_oef_dbv_hct, void* stream) {
+    if (!p || p->abi_version != QBOLD_ABI_VERSION)
+        return fail(QBOLD_EINVAL, "qbold_forward_backward_hct: bad params block");
+    if (n < 0 || (n > 0 && (!oef_dbv_hct || !g_oef_dbv_hct)))
+        return fail(QBOLD_EINVAL, "qbold_forward_backward_hct: null pointer");
+    if (n == 0) return QBOLD_OK;
+    return launch_forward<true, true>(p, oef_dbv_hct, g_signal, signal, g_oef_dbv_hct, n, (cudaStream_t)stream);
+}
 
 extern "C" int qbold_forward(const QboldParams* p, const float* oef_dbv, int32_t width, int64_t n,
                              float* signal, void* stream) {

@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "launch.h"
+#include "rng.cuh"
 
 namespace qb {
 
@@ -102,6 +103,7 @@ struct SynthOpts {
     int use_mvg;
     int inv_gamma;          // 1: subtract the inverse-gamma log-prior of the predicted variances
     float ig_alpha, ig_beta, ig_const;   // ig_const = alpha*log(beta) - lgamma(alpha)
+    int pred_stride;        // row stride of pred (>= 5 | 4): the infer_inv_gamma layout carries 4 extra channels
 };
 
 // One thread per label row.  labels [n, label_stride >= 2] (OEF, DBV, ...), pred [n, 5 | 4] raw.
@@ -109,11 +111,21 @@ __global__ void __launch_bounds__(kThreads) k_synth_nll(const float* __restrict_
                                                         const float* __restrict__ pred, SynthOpts opt, int64_t n,
                                                         float grad_scale, float* __restrict__ nll_rows,
                                                         float* __restrict__ grad_pred,
-                                                        double* __restrict__ loss_sum) {
+                                                        double* __restrict__ loss_sum,
+                                                        const float* __restrict__ ig4,
+                                                        double* __restrict__ ig_sums) {
     const int nc = opt.use_mvg ? 5 : 4;
     double acc = 0.0;
+    // infer_inv_gamma (model.py:493-496): learned (alpha_oef, beta_oef, alpha_dbv, beta_dbv), read from device memory
+    float a_o = opt.ig_alpha, b_o = opt.ig_beta, c_o = opt.ig_const, a_d = a_o, b_d = b_o, c_d = c_o;
+    float s_lo = 0.f, s_io = 0.f, s_ld = 0.f, s_id = 0.f;     // sums of log v and 1/v: the gradients of the 4 parameters
+    if (ig4 != nullptr) {
+        a_o = __ldg(ig4 + 0), b_o = __ldg(ig4 + 1), a_d = __ldg(ig4 + 2), b_d = __ldg(ig4 + 3);
+        c_o = a_o * logf(b_o) - lgammaf(a_o);
+        c_d = a_d * logf(b_d) - lgammaf(a_d);
+    }
     for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += (int64_t)gridDim.x * kThreads) {
-        const float* q = pred + v * nc;
+        const float* q = pred + v * opt.pred_stride;
         const float mu_o = __ldg(q + 0), mu_d = __ldg(q + 2);
         const float th1 = tanhf(__ldg(q + 1)), th3 = tanhf(__ldg(q + 3));
         const float ls_o = th1 * 3.0f - 1.0f, ls_d = th3 * 3.0f - 1.0f;              // transform_std, model.py:288-290
@@ -143,13 +155,14 @@ __global__ void __launch_bounds__(kThreads) k_synth_nll(const float* __restrict_
         float d_ls_d = 1.0f - w_d * w_d;
         float d_raw4 = (-w_d * r_o * e_neg) * kExpM2 * (1.0f - th4 * th4);
         if (opt.inv_gamma) {                                                         // model.py:495-507
-            const float a1 = opt.ig_alpha + 1.0f, b = opt.ig_beta;
             const float e_o = expf(ls_o), e_d = expf(ls_d);
             const float v_o = opt.use_mvg ? e_o * e_o : expf(ls_o * 2.0f);
             const float vd0 = opt.use_mvg ? e_d * e_d : expf(ls_d * 2.0f);
             const float v_d = opt.use_mvg ? vd0 + raw4 * raw4 : vd0;                 // raw channel 4 (model.py:500)
-            loss -= (opt.ig_const - a1 * logf(v_o) - b / v_o) + (opt.ig_const - a1 * logf(v_d) - b / v_d);
-            const float dl_o = a1 / v_o - b / (v_o * v_o), dl_d = a1 / v_d - b / (v_d * v_d);
+            const float lv_o = logf(v_o), lv_d = logf(v_d);
+            loss -= (c_o - (a_o + 1.0f) * lv_o - b_o / v_o) + (c_d - (a_d + 1.0f) * lv_d - b_d / v_d);
+            const float dl_o = (a_o + 1.0f) / v_o - b_o / (v_o * v_o), dl_d = (a_d + 1.0f) / v_d - b_d / (v_d * v_d);
+            s_lo += lv_o, s_io += 1.0f / v_o, s_ld += lv_d, s_id += 1.0f / v_d;
             d_ls_o += dl_o * 2.0f * v_o;
             d_ls_d += dl_d * 2.0f * vd0;
             d_raw4 += dl_d * 2.0f * raw4;
@@ -167,6 +180,75 @@ __global__ void __launch_bounds__(kThreads) k_synth_nll(const float* __restrict_
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0 && loss_sum != nullptr) atomicAdd(loss_sum, acc);
+    if (ig_sums != nullptr) {
+        s_lo = warp_sum(s_lo), s_io = warp_sum(s_io), s_ld = warp_sum(s_ld), s_id = warp_sum(s_id);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(ig_sums + 0, (double)s_lo);
+            atomicAdd(ig_sums + 1, (double)s_io);
+            atomicAdd(ig_sums + 2, (double)s_ld);
+            atomicAdd(ig_sums + 3, (double)s_id);
+        }
+    }
+}
+
+// Mixture-of-Gaussians population prior of kl_loss (reference model.py:666-684), use_mvg=False: a single-sample
+// estimate  -entropy(q) + (1/M) sum_i [nll(s_oef; comp_i) + nll(s_dbv; comp_i)]  with s = mean + eps * exp(log_std)
+// in logit space and nll(s; m, raw) = ls + 0.5 ((s - m) / exp(ls))^2, ls = transform_std(raw).  pred rows are
+// [q (4) | M components (4 each)]; value + analytic gradient w.r.t. all 4 (M + 1) channels (the sample carries the
+// reparameterisation gradient).  One thread per voxel, HBM-bound (16 (M+1) B in + 16 (M+1) B out).
+__global__ void __launch_bounds__(kThreads) k_mog_kl(const float* __restrict__ pred, int n_comp,
+                                                     const float* __restrict__ mask, const float* __restrict__ eps,
+                                                     uint64_t seed, uint64_t offset, int64_t n,
+                                                     float* __restrict__ kl_map, float* __restrict__ grad_pred) {
+    const int width = 4 * (n_comp + 1);
+    const float inv_m = 1.0f / (float)n_comp;
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += (int64_t)gridDim.x * kThreads) {
+        const float* q = pred + v * width;
+        float* g = grad_pred != nullptr ? grad_pred + v * width : nullptr;
+        const bool live = mask == nullptr || __ldg(mask + v) > 0.f;                  // model.py:717
+        if (!live) {
+            kl_map[v] = 0.f;
+            if (g != nullptr)
+                for (int c = 0; c < width; ++c) g[c] = 0.f;
+            continue;
+        }
+        float e0, e1;
+        if (eps != nullptr) {
+            e0 = __ldg(eps + v * 2), e1 = __ldg(eps + v * 2 + 1);
+        } else {
+            normal_pair(seed, offset + (uint64_t)v, kStreamReparam, e0, e1);
+        }
+        const float th_o = tanhf(__ldg(q + 1)), th_d = tanhf(__ldg(q + 3));
+        const float ls_o = th_o * 3.0f - 1.0f, ls_d = th_d * 3.0f - 1.0f;
+        const float sd_o = expf(ls_o), sd_d = expf(ls_d);
+        const float s_o = __ldg(q + 0) + e0 * sd_o, s_d = __ldg(q + 2) + e1 * sd_d;  // :670-673
+        float kl = (ls_o + ls_d) * -1.0f;                                            // :677
+        float gs_o = 0.f, gs_d = 0.f;                                                // d kl / d sample
+        for (int i = 0; i < n_comp; ++i) {
+            const float* c = q + 4 * (i + 1);
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+                const float th = tanhf(__ldg(c + k + 1));
+                const float ls = th * 3.0f - 1.0f;
+                const float w = ((k == 0 ? s_o : s_d) - __ldg(c + k)) / expf(ls);
+                kl += (ls + 0.5f * (w * w)) * inv_m;                                 // :675-682
+                const float dw = w / expf(ls) * inv_m;                               // d/d sample = -d/d mean
+                if (k == 0) gs_o += dw;
+                else gs_d += dw;
+                if (g != nullptr) {
+                    g[4 * (i + 1) + k] = -dw;
+                    g[4 * (i + 1) + k + 1] = (1.0f - w * w) * inv_m * (3.0f * (1.0f - th * th));
+                }
+            }
+        }
+        kl_map[v] = kl;
+        if (g != nullptr) {
+            g[0] = gs_o;
+            g[1] = (gs_o * e0 * sd_o - 1.0f) * (3.0f * (1.0f - th_o * th_o));
+            g[2] = gs_d;
+            g[3] = (gs_d * e1 * sd_d - 1.0f) * (3.0f * (1.0f - th_d * th_d));
+        }
+    }
 }
 
 // KL(LogitNormal q || LogitNormal p) = KL of the underlying Normals, OEF + DBV (tfp, reference model.py:695-708).
@@ -233,6 +315,7 @@ extern "C" int qbold_synth_nll(const float* labels, int32_t label_stride, const 
         return fail(QBOLD_EINVAL, "qbold_synth_nll: null pointer");
     SynthOpts opt{};
     opt.use_mvg = use_mvg ? 1 : 0;
+    opt.pred_stride = use_mvg ? 5 : 4;
     if (inv_gamma_alpha * inv_gamma_beta > 0.0) {
         opt.inv_gamma = 1;
         opt.ig_alpha = (float)inv_gamma_alpha;
@@ -241,8 +324,38 @@ extern "C" int qbold_synth_nll(const float* labels, int32_t label_stride, const 
     }
     k_synth_nll<<<(unsigned)stream_grid(n), kThreads, 0, (cudaStream_t)stream>>>(labels, label_stride, pred, opt, n,
                                                                                  grad_scale, nll_rows, grad_pred,
-                                                                                 loss_sum);
+                                                                                 loss_sum, nullptr, nullptr);
     return after_launch("k_synth_nll");
+}
+
+extern "C" int qbold_synth_nll_inferred(const float* labels, int32_t label_stride, const float* pred,
+                                        int32_t pred_stride, int32_t use_mvg, const float* inv_gamma_params,
+                                        int64_t n, float grad_scale, float* nll_rows, float* grad_pred,
+                                        double* loss_sum, double* ig_sums, void* stream) {
+    const int nc = use_mvg ? 5 : 4;
+    if (n < 0 || label_stride < 2 || pred_stride < nc)
+        return fail(QBOLD_EINVAL, "qbold_synth_nll_inferred: bad argument");
+    if (n == 0) return QBOLD_OK;
+    if (!labels || !pred || !inv_gamma_params || (!nll_rows && !grad_pred && !loss_sum))
+        return fail(QBOLD_EINVAL, "qbold_synth_nll_inferred: null pointer");
+    SynthOpts opt{};
+    opt.use_mvg = use_mvg ? 1 : 0;
+    opt.pred_stride = pred_stride;
+    opt.inv_gamma = 1;
+    k_synth_nll<<<(unsigned)stream_grid(n), kThreads, 0, (cudaStream_t)stream>>>(
+        labels, label_stride, pred, opt, n, grad_scale, nll_rows, grad_pred, loss_sum, inv_gamma_params, ig_sums);
+    return after_launch("k_synth_nll");
+}
+
+extern "C" int qbold_mog_kl(const float* pred, int32_t n_components, const float* mask, const float* eps,
+                            uint64_t seed, uint64_t offset, int64_t n, float* kl_map, float* grad_pred,
+                            void* stream) {
+    if (n < 0 || n_components < 1 || n_components > 64) return fail(QBOLD_EINVAL, "qbold_mog_kl: bad argument");
+    if (n == 0) return QBOLD_OK;
+    if (!pred || !kl_map) return fail(QBOLD_EINVAL, "qbold_mog_kl: null pointer");
+    k_mog_kl<<<(unsigned)stream_grid(n), kThreads, 0, (cudaStream_t)stream>>>(pred, n_components, mask, eps, seed,
+                                                                              offset, n, kl_map, grad_pred);
+    return after_launch("k_mog_kl");
 }
 
 extern "C" int qbold_diag_kl(const float* pred, int32_t pred_stride, const float* prior, int32_t prior_stride,

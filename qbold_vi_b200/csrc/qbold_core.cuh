@@ -154,6 +154,8 @@ struct VoxelPhys {
     float dG_doef;
     float bw;        // blood weight                     signals.py:107/110
     float kappa;     // d bw / d dbv
+    float hratio;    // (d dw / d hct) / (d dw / d oef) = oef / hct      (variable_hct only)
+    float dG_dhct;   //                                                 (variable_hct only)
 };
 
 template <bool HCT>
@@ -169,12 +171,15 @@ __device__ __forceinline__ VoxelPhys voxel_phys(const QboldParams& P, float oef,
         const float g0 = c0 * (base * base);
         v.G = (P.blood_hg * g0) * P.blood_td2;
         v.dG_doef = ((P.blood_hg * (c0 * (2.0f * base * P.blood_c1))) * P.blood_td2);
+        v.dG_dhct = HCT ? (P.blood_hg * (((4.0f / 45.0f) * (1.0f - 2.0f * hct)) * (base * base))) * P.blood_td2 : 0.f;
         v.kappa = P.kappa;
     } else {
         v.G = 0.f;
         v.dG_doef = 0.f;
+        v.dG_dhct = 0.f;
         v.kappa = 1.0f;
     }
+    v.hratio = (HCT && hct != 0.f) ? oef / hct : 0.f;
     v.bw = v.kappa * dbv;
     return v;
 }
@@ -205,6 +210,8 @@ struct TauSignal {
     float S;         // mixed signal
     float dS_doef;   // partials of S (BWD)
     float dS_ddbv;
+    float dS_dhct;   // variable_hct: the tissue term depends on Hct through dw only (dw = k hct oef), the blood
+                     // term through G0 ~ hct (1 - hct)   (signals.py:142-144, 239)
 };
 
 // I = tissue integral of this tau, dI_doef = its derivative w.r.t. OEF (BWD).
@@ -232,8 +239,9 @@ __device__ __forceinline__ TauSignal tau_signal(const QboldParams& P, const Voxe
     if (BWD) {
         r.dS_doef = tw * dst_doef + v.bw * dsb_doef;
         r.dS_ddbv = tw * dst_ddbv + v.kappa * (sb - st);
+        r.dS_dhct = (tw * dst_doef) * v.hratio + v.bw * (-blood_b * sb * v.dG_dhct);
     } else {
-        r.dS_doef = r.dS_ddbv = 0.f;
+        r.dS_doef = r.dS_ddbv = r.dS_dhct = 0.f;
     }
     return r;
 }

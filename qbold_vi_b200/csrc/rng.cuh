@@ -16,6 +16,7 @@ constexpr uint32_t kStreamReparam = 0;        // ReparamTrickLayer draw of the l
 constexpr uint32_t kStreamKl = 0x100;         // + (sample index >> 1): Monte-Carlo samples, see mc_normal_pair
 constexpr uint32_t kStreamSnr = 0x10000;      // noise model: per-voxel SNR
 constexpr uint32_t kStreamNoise = 0x10001;    // + pair index: noise normals
+constexpr uint32_t kStreamMisalign = 0x20000; // misalignment: x selection, y first misaligned image, (z, w) normals
 
 struct U4 {
     uint32_t x, y, z, w;

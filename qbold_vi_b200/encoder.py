@@ -237,8 +237,11 @@ class Encoder(nn.Module):
 
     def __init__(self, no_units=60, no_intermediate_layers=2, activation='relu', initial_im_sigma=0.05,
                  multi_image_normalisation=False, channelwise_gating=True, gate_offset=-3.0, resid_init_std=0.05,
-                 no_ip_images=11, se_idx=2, use_mvg=True):
+                 no_ip_images=11, se_idx=2, use_mvg=True, infer_inv_gamma=False):
         super().__init__()
+        # infer_inv_gamma (model.py:201-205): a learned 4-vector exp(v), v initialised to log([20, 2.5, 20, 2.5]), is
+        # broadcast onto output 0 as 4 extra channels (alpha_oef, beta_oef, alpha_dbv, beta_dbv)
+        self.hyper_prior = nn.Parameter(torch.log(torch.tensor([20.0, 2.5, 20.0, 2.5]))) if infer_inv_gamma else None
         self.act = {'relu': F.relu, 'gelu': F.gelu, 'tanh': torch.tanh}[activation]
         self.se_idx = se_idx
         self.multi_image_normalisation = multi_image_normalisation
@@ -313,7 +316,12 @@ class Encoder(nn.Module):
         h = dense(self.first, x, True) if fuse else self.act(dense(self.first, x))
         for blk in self.blocks:
             h = dense(blk.pointwise, h, True) if fuse else self.act(dense(blk.pointwise, h))
-        return dense(self.final, h)
+        return self._with_hyper_prior(dense(self.final, h))
+
+    def _with_hyper_prior(self, out):
+        if self.hyper_prior is None:
+            return out
+        return torch.cat([out, torch.exp(self.hyper_prior).expand(out.shape[:-1] + (4,))], -1)     # model.py:205
 
     def forward(self, data):
         x = self.normalise_data(data)
@@ -321,14 +329,18 @@ class Encoder(nn.Module):
         net1 = net2 = h
         for blk in self.blocks:
             net1, net2 = blk(net1, net2)
-        return dense(self.final, net1), dense(self.final, net2), torch.exp(dense(self.im_sigma, net2))
+        return (self._with_hyper_prior(dense(self.final, net1)), dense(self.final, net2),
+                torch.exp(dense(self.im_sigma, net2)))
 
 
 def create_encoder_from_args(args, no_ip_images=11, se_idx=2):
     """train.py:430-451 with an argparse/yaml namespace (config.load_arguments)."""
+    if getattr(args, 'use_layer_norm', False) or float(getattr(args, 'dropout_rate', 0.0) or 0.0) > 0.0:
+        raise NotImplementedError('use_layer_norm / dropout_rate > 0 (model.py:136-147) are not provided by this encoder; '
+                                  'optimal.yaml uses neither')
     return Encoder(no_units=max(1, args.no_units), no_intermediate_layers=max(1, args.no_intermediate_layers),
                    activation=args.activation, initial_im_sigma=args.im_loss_sigma,
                    multi_image_normalisation=args.multi_image_normalisation,
                    channelwise_gating=args.channelwise_gating, gate_offset=args.gate_offset,
                    resid_init_std=args.resid_init_std, no_ip_images=no_ip_images, se_idx=se_idx,
-                   use_mvg=args.use_mvg)
+                   use_mvg=args.use_mvg, infer_inv_gamma=bool(getattr(args, 'infer_inv_gamma', False)))

@@ -36,6 +36,16 @@ def _as_mvg(params, use_mvg):
     return torch.cat([params[..., :4], torch.zeros_like(params[..., :1])], -1)
 
 
+def _check_mvg_operands(pred, prior):
+    """The kernels take raw pointers: refuse anything but [...,5] operands with equal voxel counts (a reference-style
+    10-channel 'predictions' tensor with an appended population prior would otherwise be read as 2N rows)."""
+    if pred.shape[-1] != 5 or prior.shape[-1] != 5:
+        raise ValueError('mvg KL: predicted and prior must have 5 channels (mean, raw std, mean, raw std, raw '
+                         'off-diagonal); got %d and %d' % (pred.shape[-1], prior.shape[-1]))
+    if pred.numel() != prior.numel():
+        raise ValueError('mvg KL: %d predicted voxels but %d prior voxels' % (pred.numel() // 5, prior.numel() // 5))
+
+
 def _next_seed(obj):
     obj._calls += 1
     return (obj._seed + 0x9E3779B97F4A7C15 * obj._calls) & 0xFFFFFFFFFFFFFFFF
@@ -190,6 +200,55 @@ class _DiagKlFn(torch.autograd.Function):
         return ctx.saved_tensors[0] * g[:, None], None, None
 
 
+class _MogKlFn(torch.autograd.Function):
+    """Per-voxel single-sample KL against the mixture-of-Gaussians population prior (qbold_mog_kl)."""
+
+    @staticmethod
+    def forward(ctx, pred, mask, eps, seed, n_comp, offset):
+        n = pred.shape[0]
+        kl = torch.empty(n, dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred)
+        with torch.cuda.device(pred.device):
+            check(_lib.lib().qbold_mog_kl(dptr(pred), n_comp, dptr(mask, allow_none=True), dptr(eps, allow_none=True),
+                                          seed, int(offset), n, dptr(kl), dptr(grad), stream_ptr(pred.device)))
+        ctx.save_for_backward(grad)
+        return kl
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.saved_tensors[0] * g[:, None], None, None, None, None, None
+
+
+class _SynthNllInferredFn(torch.autograd.Function):
+    """Pre-training NLL with LEARNED InverseGamma parameters (qbold_synth_nll_inferred): gradients for the q channels
+    come from the kernel, those of the 4 hyper-parameters from its 4 reduced sums."""
+
+    @staticmethod
+    def forward(ctx, pred, ig, labels, use_mvg):
+        n, dev = pred.shape[0], pred.device
+        nc = 5 if use_mvg else 4
+        grad = torch.empty((n, nc), dtype=torch.float32, device=dev)
+        acc = torch.zeros(5, dtype=torch.float64, device=dev)                 # loss sum | 4 hyper-parameter sums
+        with torch.cuda.device(dev):
+            check(_lib.lib().qbold_synth_nll_inferred(dptr(labels), labels.shape[1], dptr(pred), pred.shape[1],
+                                                      int(use_mvg), dptr(ig), n, 1.0 / n, None, dptr(grad),
+                                                      C.c_void_p(acc.data_ptr()), C.c_void_p(acc.data_ptr() + 8),
+                                                      stream_ptr(dev)))
+        a, b = ig.double()[0::2], ig.double()[1::2]
+        g_alpha = -((torch.log(b) - torch.digamma(a)) - acc[1::2][:2] / n)    # d mean(loss) / d alpha_(oef, dbv)
+        g_beta = -(a / b - acc[2::2][:2] / n)
+        ctx.save_for_backward(grad, torch.stack([g_alpha[0], g_beta[0], g_alpha[1], g_beta[1]]).float())
+        ctx.width = pred.shape[1]
+        return (acc[0] / n).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        grad, g_ig = ctx.saved_tensors
+        gp = torch.zeros((grad.shape[0], ctx.width), dtype=torch.float32, device=grad.device)
+        gp[:, :grad.shape[1]] = grad * g
+        return gp, g_ig * g, None, None
+
+
 class _FusedElboFn(torch.autograd.Function):
     """loss = nll + kl_weight * kl of one (local) batch; gradients come from the same launch."""
 
@@ -257,7 +316,6 @@ class EncoderTrainer:
         self._se_idx = int(abs(float(system_params['tau_start']) / float(system_params['tau_step'])))   # model.py:95
         self._seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self._calls = 0
-        self._param_cache = {}
 
     # ------------------------------------------------------------------ transforms (model.py:288-316)
     def transform_std(self, pred_stds):
@@ -293,16 +351,20 @@ class EncoderTrainer:
 
     # ------------------------------------------------------------------ parameter block with likelihood options
     def _params_for(self, layer):
-        key = id(layer)
-        if key not in self._param_cache:
+        """The layer's parameter block with this trainer's likelihood options.  Cached ON the layer object (it dies with
+        it -- an id()-keyed dict would hand a recycled id the block of a dead layer) under the current option values, so
+        later changes of the trainer's flags are seen."""
+        df = self._student_t_df
+        key = (self._se_idx, bool(self._multi_image_normalisation), bool(self._predict_log_data),
+               float(df) if df is not None else 0.0)
+        cache = layer.__dict__.setdefault('_likelihood_blocks', {})
+        if key not in cache:
             p = QboldParams()
             C.memmove(C.byref(p), C.byref(layer.params), C.sizeof(QboldParams))
-            df = self._student_t_df
-            lik = QboldLikelihood(self._se_idx, int(bool(self._multi_image_normalisation)),
-                                  int(bool(self._predict_log_data)), 0, float(df) if df is not None else 0.0)
+            lik = QboldLikelihood(key[0], int(key[1]), int(key[2]), 0, key[3])
             check(_lib.lib().qbold_params_set_likelihood(C.byref(p), C.byref(lik)))
-            self._param_cache[key] = p
-        return self._param_cache[key]
+            cache[key] = p
+        return cache[key]
 
     # ------------------------------------------------------------------ sampling helpers (model.py:318-343)
     def create_samples(self, predicted_params, mask, no_samples):
@@ -395,6 +457,7 @@ class EncoderTrainer:
     # ------------------------------------------------------------------ KL (model.py:592-665)
     def mvg_kl_samples(self, prior, pred, no_samples=50, eps=None):
         prior_dist, mask = prior[..., :5], prior[..., 5:6]
+        _check_mvg_operands(pred, prior_dist)
         lead = tuple(pred.shape[:-1])
         kl = _KlFn.apply(pred.reshape(-1, 5).float().contiguous(), prior_dist.reshape(-1, 5).float().contiguous(),
                          None, None if eps is None else eps.reshape(-1, no_samples, 2).float().contiguous(),
@@ -408,6 +471,7 @@ class EncoderTrainer:
         true = torch.cat([true for _ in range(self._no_samples)], 0)
         if self._use_mvg:
             prior_dist, mask = true[..., :5], true[..., 5:6]
+            _check_mvg_operands(predicted, prior_dist)
             lead = tuple(predicted.shape[:-1])
             m = mask.reshape(-1).float().contiguous()
             kl = _KlFn.apply(predicted.reshape(-1, 5).float().contiguous(),
@@ -419,7 +483,7 @@ class EncoderTrainer:
             return kl.reshape(lead + (1,))
         mask = true[..., 4:5]
         if self._use_population_prior and self._mog_components > 1:
-            return self._mog_kl(predicted, mask, return_mean, eps)
+            return self._mog_kl(predicted, mask, return_mean, eps, offset)
 
         lead = tuple(predicted.shape[:-1])
         m = mask.reshape(-1).float().contiguous()
@@ -443,31 +507,26 @@ class EncoderTrainer:
             return (torch.sum(kl) + prior_cost) / torch.sum(mask)
         return kl.reshape(lead + (1,))
 
-    def _mog_kl(self, predicted, mask, return_mean, eps=None):
-        """Mixture-of-Gaussians population prior (model.py:666-684), a non-default branch kept as tensor ops:
-        single-sample estimate -entropy(q) + mean over components of the Gaussian NLL of one logit-space draw.
-        ``predicted`` [...,4*(M+1)]: q then M components; ``eps`` [...,2] pins the (OEF, DBV) draws."""
+    def _mog_kl(self, predicted, mask, return_mean, eps=None, offset=0):
+        """Mixture-of-Gaussians population prior (model.py:666-684) in one kernel (``qbold_mog_kl``): single-sample
+        estimate -entropy(q) + mean over components of the Gaussian NLL of one logit-space draw, with its gradient for
+        q and every component.  ``predicted`` [...,4*(M+1)]: q then M components; ``eps`` [...,2] pins the (OEF, DBV)
+        draws (default: in-kernel Philox)."""
         m_comp = self._mog_components
-        parts = torch.split(predicted, 4, -1)
-        q = parts[0]
-        ls_o, ls_d = self.transform_std(q[..., 1]), self.transform_std(q[..., 3])
-        if eps is None:
-            eps = torch.randn(q.shape[:-1] + (2,), dtype=q.dtype, device=q.device)
-        s_o = q[..., 0] + eps[..., 0] * torch.exp(ls_o)
-        s_d = q[..., 2] + eps[..., 1] * torch.exp(ls_d)
-
-        def nll(sample, mean, raw_std):
-            ls = self.transform_std(raw_std)
-            return -(-ls - 0.5 * ((sample - mean) / torch.exp(ls)) ** 2)
-
-        kl = (ls_o + ls_d) * -1.0
-        for i in range(m_comp):
-            c = parts[i + 1]
-            kl = kl + nll(s_o, c[..., 0], c[..., 1]) / float(m_comp) + nll(s_d, c[..., 2], c[..., 3]) / float(m_comp)
-        kl = torch.where(mask > 0, kl.unsqueeze(-1), torch.zeros_like(mask))
+        width = 4 * (m_comp + 1)
+        if predicted.shape[-1] != width:
+            raise ValueError('kl_loss: expected %d channels (q + %d mixture components), got %d'
+                             % (width, m_comp, predicted.shape[-1]))
+        lead = tuple(predicted.shape[:-1])
+        pred = predicted.reshape(-1, width).float().contiguous()
+        m = mask.reshape(-1).float().contiguous()
+        if m.shape[0] != pred.shape[0]:
+            raise ValueError('kl_loss: %d mask voxels for %d predicted voxels' % (m.shape[0], pred.shape[0]))
+        e = None if eps is None else eps.reshape(-1, 2).float().contiguous()
+        kl = _MogKlFn.apply(pred, m, e, _next_seed(self), m_comp, int(offset))
         if return_mean:
             return torch.sum(kl) / torch.sum(mask)
-        return kl
+        return kl.reshape(lead + (1,))
 
     # ------------------------------------------------------------------ fused training objective
     def fused_elbo(self, signal_layer, q_params, im_sigma, data, mask, prior, kl_samples=70, kl_weight=1.0,
@@ -483,8 +542,13 @@ class EncoderTrainer:
         if not self._use_mvg:
             q_params, kl_samples = _as_mvg(q_params, False), 0          # analytic KL, as the reference (model.py:695-708)
             prior = None if prior is None else _as_mvg(prior, False)
+        if q_params.shape[-1] != 5 or (prior is not None and prior.shape[-1] != 5):
+            raise ValueError('fused_elbo: q_params / prior must have %d channels' % (5 if self._use_mvg else 4))
         q = q_params.reshape(-1, 5).float().contiguous()
         n = q.shape[0]
+        for name, t, width in (('im_sigma', im_sigma, nt), ('data', data, nt), ('mask', mask, 1), ('prior', prior, 5)):
+            if t is not None and t.numel() != n * width:
+                raise ValueError('fused_elbo: %s holds %d values, expected %d voxels x %d' % (name, t.numel(), n, width))
         sg = im_sigma.reshape(n, nt).float().contiguous()
         y = data.reshape(n, nt).float().contiguous()
         m = mask.reshape(n).float().contiguous()
@@ -642,13 +706,21 @@ class EncoderTrainer:
         inputs and then averages to mean(nll) + mean(extra); that is what is returned here for any shape.
         ``use_r2p_loss``: Gaussian NLL of the R2' label under 10 reparameterised draws (:480-494; ``eps``
         [N,10,2] pins the draws)."""
-        if self._infer_inv_gamma:
-            raise NotImplementedError('infer_inv_gamma (learned InverseGamma parameters, model.py:497-500) is not '
-                                      'provided')
         c = 5 if self._use_mvg else 4
         labels = y_true_orig.reshape(-1, 3).float().contiguous()
-        pred = y_pred_orig.reshape(-1, c).float().contiguous()
-        loss = _SynthNllFn.apply(pred, labels, self._use_mvg, float(inv_gamma_alpha), float(inv_gamma_beta))
+        if self._infer_inv_gamma:
+            # model.py:454-455 splits the prediction into two equal halves [q | hyper-prior], which only exists for the
+            # diagonal layout (4 + 4 channels); the hyper-parameters are read from voxel 0 (:494)
+            if y_pred_orig.shape[-1] != 2 * c or self._use_mvg:
+                raise ValueError('infer_inv_gamma needs an 8-channel diagonal prediction [q(4) | alpha_oef, beta_oef, '
+                                 'alpha_dbv, beta_dbv] (tf.split(y_pred, 2, -1), model.py:455); got %d channels, use_mvg=%s'
+                                 % (y_pred_orig.shape[-1], self._use_mvg))
+            both = y_pred_orig.reshape(-1, 2 * c).float().contiguous()
+            pred = both[:, :c]
+            loss = _SynthNllInferredFn.apply(both, both[0, c:], labels, False)
+        else:
+            pred = y_pred_orig.reshape(-1, c).float().contiguous()
+            loss = _SynthNllFn.apply(pred, labels, self._use_mvg, float(inv_gamma_alpha), float(inv_gamma_beta))
         if use_r2p_loss:
             n_samples = 10
             rpl = ReparamTrickLayer(self)
@@ -663,12 +735,33 @@ class EncoderTrainer:
 
 class FineTuner(torch.nn.Module):
     """build_fine_tuner (model.py:239-286) as a module; the encoder is any callable returning
-    (q_voxelwise, q_spatial, sigma) like qbold_vi_b200.encoder.Encoder."""
+    (q_voxelwise, q_spatial, sigma) like qbold_vi_b200.encoder.Encoder.
+
+    ``use_population_prior`` (diagonal layout): a trainable prior vector (model.py:252-271; [-0.97, 0.4, -1.14, 0.6], or
+    N(0,1) draws for a mixture of ``mog_components`` Gaussians) is broadcast over the voxels and appended to
+    'predictions', as the reference does, so ``kl_loss`` on that output trains it.  With ``use_mvg`` the reference appends
+    5 more channels that its own mvg ``kl_loss`` then mis-splits (ReparamTrickLayer splits 10 channels into 5 pairs,
+    model.py:24,594): that combination is refused here instead of being reproduced."""
 
     def __init__(self, trainer, encoder_model, signal_generation_layer):
         super().__init__()
         self.trainer, self.encoder, self.layer = trainer, encoder_model, signal_generation_layer
         self.reparam = ReparamTrickLayer(trainer)
+        self.pop_prior = None
+        if trainer._use_population_prior:
+            if trainer._use_mvg:
+                raise NotImplementedError(
+                    'use_population_prior with use_mvg: the reference concatenates a 5-channel prior onto the predictions '
+                    '(model.py:254-271) but its mvg kl_loss never reads it as a prior (model.py:594 samples from the '
+                    '10-channel tensor instead); use use_mvg=False for a trainable population prior')
+            m = trainer._mog_components
+            init = torch.randn(4 * m) if m > 1 else torch.tensor([-0.97, 0.4, -1.14, 0.6])     # model.py:261-264
+            self.pop_prior = torch.nn.Parameter(init.float())
+
+    def _with_pop_prior(self, q):
+        if self.pop_prior is None:
+            return q
+        return torch.cat([q, self.pop_prior.to(q.device).expand(q.shape[:-1] + (self.pop_prior.numel(),))], -1)
 
     def forward(self, data, mask, eps=None):
         _, q, sigma = self.encoder(data)
@@ -676,8 +769,20 @@ class FineTuner(torch.nn.Module):
         q_rep, sigma_rep = torch.cat([q] * k, 0), torch.cat([sigma] * k, 0)               # model.py:245-246
         sampled = self.reparam((q_rep, mask), eps=eps)                                    # :248
         pred = self.layer(sampled)                                                        # :273
-        return {'predictions': q_rep, 'predicted_images': torch.cat([pred, sigma_rep], -1)}   # :276,284-285
+        return {'predictions': self._with_pop_prior(q_rep),                               # :268-271
+                'predicted_images': torch.cat([pred, sigma_rep], -1)}                     # :276,284-285
 
     def fused_loss(self, data, mask, prior, **kw):
+        """One-launch training objective.  With a population prior the KL runs against the trainable prior
+        (``kl_loss`` on the appended channels, which carries its gradient) and the fused kernel does the likelihood."""
         _, q, sigma = self.encoder(data)
-        return self.trainer.fused_elbo(self.layer, q, sigma, data, mask, prior, **kw)
+        if self.pop_prior is None:
+            return self.trainer.fused_elbo(self.layer, q, sigma, data, mask, prior, **kw)
+        kl_weight = float(kw.pop('kl_weight', 1.0))
+        for k in ('kl_samples', 'eps_kl'):
+            kw.pop(k, None)
+        nll, info = self.trainer.fused_elbo(self.layer, q, sigma, data, mask, None, **kw)
+        true = torch.cat([torch.zeros_like(q[..., :4]), mask.reshape(q.shape[:-1] + (1,))], -1)
+        kl = self.trainer.kl_loss(true, self._with_pop_prior(q))
+        info['kl'] = kl.detach()
+        return nll + kl_weight * kl, info

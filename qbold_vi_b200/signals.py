@@ -51,9 +51,7 @@ class _ForwardFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (flat,) = ctx.saved_tensors
-        if flat.shape[-1] != 2:
-            raise NotImplementedError('gradients with variable_hct=True are not provided')
-        _, grad = ctx.layer.forward_backward(flat, g.contiguous())
+        _, grad = ctx.layer.forward_backward(flat, g.contiguous())          # [N,2], or [N,3] with variable_hct
         return grad, None
 
 
@@ -83,8 +81,6 @@ class SignalGenerationLayer:
         self._include_blood = _as_bool(include_blood)
         self._misaligned_prob = float(misaligned_prob)
         self._variable_hct = bool(variable_hct)
-        if self._misaligned_prob > 0.0 and self._variable_hct:
-            raise NotImplementedError('misalignment augmentation with variable_hct is not provided')
         self._seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self._calls = 0
 
@@ -121,16 +117,46 @@ class SignalGenerationLayer:
         else:
             signal = self._forward_raw(flat)
         if self._misaligned_prob > 0.0:
-            signal = self._misalign(flat, signal)
+            if signal.requires_grad:
+                signal = self._misalign_autograd(flat, signal)
+            else:
+                signal = self.misalign(flat, signal, inplace=True)
         if self._simulate_noise:
-            signal = self.add_noise(signal)
+            noisy = self.add_noise(signal)
+            # the noise is additive with unit Jacobian (signals.py:128); the reference's std_dev also depends on the
+            # batch-mean signal (:126) -- that second-order path is not followed
+            signal = signal + (noisy - signal.detach()) if signal.requires_grad else noisy
         return signal.reshape(tuple(input.shape[:-1]) + (self.n_tau,))
 
-    def _misalign(self, flat, signal):
-        """Misalignment augmentation (signals.py:80-96): a Bernoulli(p) subset of voxels gets, for the images after a
-        random index in [4, n_tau-1), the signal of perturbed parameters (OEF + N(0,0.15) clipped to [0.05,0.8],
-        DBV + N(0,0.05) clipped to [0.002,0.3]).  The perturbed signals come from a second forward launch on the
-        selected voxels only; the per-image blend is the reference's mask arithmetic."""
+    def misalign(self, oef_dbv, signal, sel_u01=None, from_index=None, eps=None, seed=None, offset=0, inplace=False):
+        """Misalignment augmentation (signals.py:80-96) in one launch (``qbold_misalign``): a Bernoulli(p) subset of
+        voxels gets, for the images after a random index in [4, n_tau-1), the signal of perturbed parameters
+        (OEF + N(0,0.15) clipped to [0.05,0.8], DBV + N(0,0.05) clipped to [0.002,0.3]).  ``signal`` is the noise-free
+        forward model of ``oef_dbv``.  ``sel_u01`` [N], ``from_index`` [N] int32 and ``eps`` [N,2] pin the reference's
+        draws (uniform, randint, the two normals); by default they come from the in-kernel Philox stream."""
+        flat = oef_dbv.reshape(-1, oef_dbv.shape[-1]).float().contiguous()
+        n = flat.shape[0]
+        sig = signal.detach().reshape(n, self.n_tau)
+        sig = sig if (inplace and sig.is_contiguous()) else sig.clone().contiguous()
+        if n == 0:
+            return sig
+        if seed is None:
+            seed = (self._seed + 0x9E3779B97F4A7C15 * (self._calls + 1)) & 0xFFFFFFFFFFFFFFFF
+            self._calls += 1
+        fi = None if from_index is None else from_index.reshape(n).to(torch.int32).contiguous()
+        with torch.cuda.device(flat.device):
+            check(_lib.lib().qbold_misalign(C.byref(self.params), dptr(flat), flat.shape[1], n, self._misaligned_prob,
+                                            dptr(None if sel_u01 is None else sel_u01.reshape(n).float().contiguous(),
+                                                 allow_none=True),
+                                            dptr(fi, torch.int32, allow_none=True),
+                                            dptr(None if eps is None else eps.reshape(n, 2).float().contiguous(),
+                                                 allow_none=True),
+                                            seed, int(offset), dptr(sig), stream_ptr(flat.device)))
+        return sig
+
+    def _misalign_autograd(self, flat, signal):
+        """The same augmentation as differentiable tensor ops (only taken when the input requires grad): gradients reach
+        OEF/DBV through the unperturbed images and, inside the clip range, through the perturbed ones (:92-96)."""
         n, nt = flat.shape[0], self.n_tau
         dev = flat.device
         misaligned = torch.rand(n, device=dev) < self._misaligned_prob                               # :82
@@ -138,14 +164,14 @@ class SignalGenerationLayer:
         idx = torch.nonzero(misaligned).reshape(-1)
         if idx.numel() == 0:
             return signal
-        sel = flat.detach()[idx]
-        pert = torch.stack([(torch.randn(idx.numel(), device=dev) * 0.15 + sel[:, 0]).clamp(0.05, 0.8),   # :92
-                            (torch.randn(idx.numel(), device=dev) * 0.05 + sel[:, 1]).clamp(0.002, 0.3)], -1)  # :93
-        s2 = self._forward_raw(pert.contiguous())
+        sel = flat[idx]
+        cols = [(torch.randn(idx.numel(), device=dev) * 0.15 + sel[:, 0]).clamp(0.05, 0.8),          # :92
+                (torch.randn(idx.numel(), device=dev) * 0.05 + sel[:, 1]).clamp(0.002, 0.3)]         # :93
+        if flat.shape[1] == 3:
+            cols.append(sel[:, 2])
+        s2 = _ForwardFn.apply(torch.stack(cols, -1).contiguous(), self)
         late = torch.arange(nt, device=dev)[None, :] > from_index[idx, None]                         # :86-88
-        out = signal.clone()
-        out[idx] = torch.where(late, s2, signal[idx])                                                # :95-96
-        return out
+        return signal.index_copy(0, idx, torch.where(late, s2, signal[idx]))                         # :95-96
 
     @staticmethod
     def calculate_dw_static(oef, hct, gamma, b0, dchi):
@@ -167,18 +193,21 @@ class SignalGenerationLayer:
         return out
 
     def forward_backward(self, oef_dbv, g_signal=None, want_signal=True):
-        """Forward + VJP in one fused launch: returns (signal [N,n_tau] or None, grad [N,2])."""
+        """Forward + VJP in one fused launch: returns (signal [N,n_tau] or None, grad [N,2]); with variable_hct the rows
+        are (OEF, DBV, Hct) and grad is [N,3]."""
         if not oef_dbv.is_cuda:
             raise QboldError('qbold_vi_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path'
                              % oef_dbv.device)
-        flat = oef_dbv.reshape(-1, 2).contiguous()
+        width = 3 if self._variable_hct else 2
+        flat = oef_dbv.reshape(-1, width).contiguous()
         n = flat.shape[0]
         sig = torch.empty((n, self.n_tau), dtype=torch.float32, device=flat.device) if want_signal else None
-        grad = torch.empty((n, 2), dtype=torch.float32, device=flat.device)
+        grad = torch.empty((n, width), dtype=torch.float32, device=flat.device)
         g = None if g_signal is None else g_signal.reshape(n, self.n_tau).contiguous()
+        fn = _lib.lib().qbold_forward_backward_hct if self._variable_hct else _lib.lib().qbold_forward_backward
         with torch.cuda.device(flat.device):
-            check(_lib.lib().qbold_forward_backward(C.byref(self.params), dptr(flat), dptr(g, allow_none=True), n,
-                                                    dptr(sig, allow_none=True), dptr(grad), stream_ptr(flat.device)))
+            check(fn(C.byref(self.params), dptr(flat), dptr(g, allow_none=True), n, dptr(sig, allow_none=True),
+                     dptr(grad), stream_ptr(flat.device)))
         return sig, grad
 
     def forward_backward_host(self, oef_dbv, g_signal, signal_out, grad_out):
@@ -233,9 +262,6 @@ def create_synthetic_dataset(params, full_model, use_blood, misaligned_prob, var
 
     ``shuffle='perm'`` materialises an explicit permutation (torch.randperm, as tf.random.shuffle does);
     ``shuffle='feistel'`` uses the in-kernel keyed bijection (no permutation array; large S)."""
-    if variable_hct:
-        raise NotImplementedError('variable_hct generation draws a constant Hct 0.34 (signals.py:273-276); '
-                                  'use variable_hct=False')
     device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
     sig_layer = SignalGenerationLayer(params, full_model, use_blood, misaligned_prob=misaligned_prob,
                                       variable_hct=variable_hct, seed=seed)
@@ -259,9 +285,12 @@ def create_synthetic_dataset(params, full_model, use_blood, misaligned_prob, var
 
 
 def generate_from_marginals(sig_layer, oefs, dbvs, perm=None, n_chunks=10, snr_u01=None, noise_eps=None,
-                            seed=None):
-    """signals.py:270-299 after the random draws.  Noise (if the layer simulates it) is applied per chunk
-    because its std is the per-call batch mean (signals.py:126, 282-285)."""
+                            seed=None, misalign_u01=None, misalign_index=None, misalign_eps=None):
+    """signals.py:270-299 after the random draws.  Per chunk the reference calls the layer once: misalignment
+    (if the layer's misaligned_prob > 0, signals.py:80-96) on the clean signal, then the noise, whose std is the
+    per-call batch mean (signals.py:126, 282-285).  ``misalign_*``: the reference's recorded draws, concatenated
+    over the chunks ([n_x], [n_x] int, [n_x,2]); default = the in-kernel Philox stream (chunk-invariant).
+    With ``variable_hct`` every row carries the constant Hct 0.34 the reference draws (signals.py:273-276)."""
     lib = _lib.lib()
     dev = oefs.device
     nt = sig_layer.n_tau
@@ -274,12 +303,27 @@ def generate_from_marginals(sig_layer, oefs, dbvs, perm=None, n_chunks=10, snr_u
     pptr = None if perm is None else dptr(perm, torch.int64)
     with torch.cuda.device(dev):
         st = stream_ptr(dev)
-        if n_x > 0:                 # rows are independent: the reference's chunking (:282-285) only matters for the noise
+        if sig_layer._variable_hct:                                 # labels only; the signals follow below
+            check(lib.qbold_generate(C.byref(sig_layer.params), dptr(oefs), oefs.numel(), dptr(dbvs), dbvs.numel(),
+                                     pptr, seed, 0, total, None, dptr(train_y), st))
+        elif n_x > 0:               # rows are independent: the reference's chunking (:282-285) only matters for the noise
             check(lib.qbold_generate(C.byref(sig_layer.params), dptr(oefs), oefs.numel(), dptr(dbvs), dbvs.numel(),
                                      pptr, seed, 0, n_x, dptr(train_x), dptr(train_y), st))
-        if total > n_x:
+        if total > n_x and not sig_layer._variable_hct:
             check(lib.qbold_generate(C.byref(sig_layer.params), dptr(oefs), oefs.numel(), dptr(dbvs), dbvs.numel(),
                                      pptr, seed, n_x, total - n_x, None, dptr(train_y[n_x:]), st))
+    if sig_layer._variable_hct and total > 0:
+        # rows (OEF, DBV, 0.34) through the variable-Hct forward kernel; R2' label with the float32 Hct (:293-294)
+        hct = torch.full((total, 1), 0.34, dtype=torch.float32, device=dev)
+        rows = torch.cat([train_y[:, :2], hct], -1).contiguous()
+        if n_x > 0:
+            train_x = sig_layer._forward_raw(rows[:n_x].contiguous())
+        k = (4.0 / 3.0) * math.pi * sig_layer._gamma * sig_layer._b0 * sig_layer._dchi
+        train_y[:, 2] = (k * rows[:, 2] * rows[:, 0]) * rows[:, 1]
+    if sig_layer._misaligned_prob > 0.0 and n_x > 0:
+        rows = rows[:n_x] if sig_layer._variable_hct else train_y[:n_x, :2].contiguous()
+        train_x = sig_layer.misalign(rows, train_x, misalign_u01, misalign_index, misalign_eps,
+                                     seed=(seed ^ 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF, inplace=True)
     if sig_layer._simulate_noise and chunk > 0:
         # every chunk is one forward call in the reference, so its noise std uses that chunk's column means (:126)
         if sig_layer.params.norm_snr[0] == 0.0:

@@ -15,6 +15,29 @@ pytestmark = pytest.mark.gpu
 
 SIG_TOL = 1e-5
 GRAD_TOL = 1e-4
+ELEM_TOL = 1e-4            # element-wise, against max(|ref|, 1e-3 * max|ref|); see _elem_check
+
+
+def _rel_elem_floor(got, want, floor_frac=1e-3):
+    """Element-wise relative error with a floor: max |got - want| / max(|want|, floor_frac * max|want|).  A voxel whose
+    gradient is 0.1 % of the batch maximum still has to be right to ELEM_TOL of its own size."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    floor = floor_frac * float(np.max(np.abs(want)))
+    return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), floor)))
+
+
+def _elem_check(got, want64, ref32):
+    """Element-wise gradient bar.  Every element must agree with the float64 oracle to ELEM_TOL of max(|element|,
+    0.1 % of the batch maximum) -- or, where float32 arithmetic itself cannot deliver that, to within twice the distance
+    of the REFERENCE's own float32 evaluation (``ref32``: the reference-source fixture or the float32-emulated oracle)
+    from the same float64 values.  Measured: the reference's float32 gradients sit 1.4e-3 from float64 in this metric
+    (absolute error 2e-5 on gradients of size 13), so a flat 1e-4 would fail the reference itself."""
+    e = _rel_elem_floor(got, want64)
+    bar = max(ELEM_TOL, 2.0 * _rel_elem_floor(ref32, want64))
+    assert e < bar, 'element-wise error %.3g exceeds %.3g (reference float32 vs float64: %.3g)' % (
+        e, bar, _rel_elem_floor(ref32, want64))
+    # entries of at least 10 % of the batch maximum meet the flat tolerance unconditionally
+    assert _rel_elem_floor(got, want64, 1e-1) < ELEM_TOL
 
 
 @pytest.fixture(scope='module')
@@ -178,6 +201,11 @@ def test_fused_elbo_matches_reference_source(qb, dev, cfg_noise_off, tag):
     assert rel_max(info['nll_map'].cpu().numpy(), e['nll_map']) < GRAD_TOL
     assert rel_max(q.grad.cpu().numpy(), e['grad_q_nll'] + e['grad_q_kl']) < GRAD_TOL
     assert rel_max(sg.grad.cpu().numpy(), e['grad_sigma']) < GRAD_TOL
+    if tag != 'studentt':                                     # the oracle's analytic backward covers the Gaussian likelihood
+        r64 = o.elbo_and_grads(o.parse_params(cfg_noise_off), e['q'], e['sigma'], e['data'], e['mask'], e['prior'], e['eps'],
+                               e['eps_kl'], np.float64, multi_image_normalisation=bool(e['multi_image_normalisation']))
+        _elem_check(q.grad.cpu().numpy(), r64['grad_q'], e['grad_q_nll'] + e['grad_q_kl'])
+        _elem_check(sg.grad.cpu().numpy(), r64['grad_sigma'], e['grad_sigma'])
     assert float(info['mask_sum']) == e['mask'].sum() and float(info['non_finite']) == 0
     # masked voxels: exactly zero loss and gradient (model.py:564,661)
     dead = e['mask'] == 0
@@ -208,6 +236,9 @@ def test_fused_elbo_matches_oracle_on_random_batch(qb, dev, cfg_noise_off, physi
     assert rel_max(info['kl_map'].cpu().numpy(), ref['kl_map']) < GRAD_TOL
     assert rel_max(qt.grad.cpu().numpy(), ref['grad_q']) < GRAD_TOL
     assert rel_max(st.grad.cpu().numpy(), ref['grad_sigma']) < GRAD_TOL
+    ref32 = o.elbo_and_grads(physics, q, sigma, data, mask, prior, eps, eps_kl, np.float32)
+    _elem_check(qt.grad.cpu().numpy(), ref['grad_q'], ref32['grad_q'])
+    _elem_check(st.grad.cpu().numpy(), ref['grad_sigma'], ref32['grad_sigma'])
     # sharding invariance: the same batch in two halves with the global mask sum gives the same gradients
     h = n // 2
     parts = []
@@ -219,6 +250,59 @@ def test_fused_elbo_matches_oracle_on_random_batch(qb, dev, cfg_noise_off, physi
         parts.append((l.item(), qh.grad))
     assert abs(parts[0][0] + parts[1][0] - loss.item()) < 1e-5 * abs(loss.item())
     assert torch.equal(torch.cat([parts[0][1], parts[1][1]]), qt.grad)
+
+
+def _elbo_batch(physics, n, seed, spread=0.7):
+    r = np.random.default_rng(seed)
+    q = np.stack([r.normal(-0.3, spread, n), r.normal(0, 0.6, n), r.normal(-1.2, spread, n), r.normal(0, 0.6, n),
+                  r.normal(0, 0.8, n)], -1).astype(np.float32)
+    prior = (q + r.normal(0, 0.3, (n, 5))).astype(np.float32)
+    sigma = np.exp(r.normal(np.log(0.05), 0.2, (n, 11))).astype(np.float32)
+    truth = np.stack([r.uniform(0.1, 0.7, n), r.uniform(0.005, 0.15, n)], -1)
+    data = (o.forward(physics, truth, dtype=np.float64) * 100 * (1 + 0.02 * r.standard_normal((n, 11)))).astype(np.float32)
+    return q, prior, sigma, data
+
+
+def test_production_rng_path_matches_oracle(qb, dev, cfg_noise_off, physics):
+    """The calls as users make them -- fused_elbo(seed=...) and kl_loss() with NO explicit draws, i.e. in-kernel
+    Philox4x32-10 + Box-Muller -- against the oracle fed oracle/philox.py draws for the same (seed, global index)."""
+    n, S, seed, off = 2048, 70, 99, 1_234_567
+    q, prior, sigma, data = _elbo_batch(physics, n, 31)
+    mask = (np.random.default_rng(32).uniform(size=n) > 0.3).astype(np.float32)
+    data *= mask[:, None]
+    idx = np.arange(n, dtype=np.uint64) + np.uint64(off)
+    eps, eps_kl = philox.reparam_eps(seed, idx), philox.kl_eps(seed, idx, S)
+    ref = o.elbo_and_grads(physics, q, sigma, data, mask, prior, eps, eps_kl, np.float64)
+    tr = _trainer(qb, cfg_noise_off)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    qt, st = _t(q, dev).requires_grad_(True), _t(sigma, dev).requires_grad_(True)
+    loss, info = tr.fused_elbo(layer, qt, st, _t(data, dev), _t(mask, dev), _t(prior, dev), kl_samples=S, seed=seed,
+                               offset=off, return_maps=True)
+    loss.backward()
+    assert rel_elem(info['nll'].item(), ref['nll']) < GRAD_TOL and rel_elem(info['kl'].item(), ref['kl']) < GRAD_TOL
+    assert rel_elem(loss.item(), ref['nll'] + ref['kl']) < GRAD_TOL
+    assert rel_max(info['nll_map'].cpu().numpy(), ref['nll_map']) < GRAD_TOL
+    assert rel_max(info['kl_map'].cpu().numpy(), ref['kl_map']) < GRAD_TOL
+    ref32 = o.elbo_and_grads(physics, q, sigma, data, mask, prior, eps, eps_kl, np.float32)
+    for got, key in ((qt.grad, 'grad_q'), (st.grad, 'grad_sigma')):
+        assert rel_max(got.cpu().numpy(), ref[key]) < GRAD_TOL
+        _elem_check(got.cpu().numpy(), ref[key], ref32[key])
+    # kl_loss() with its defaults: the trainer's own call counter seeds the draws
+    tr2 = _trainer(qb, cfg_noise_off, seed=77)
+    seed2 = (77 + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF                           # first call of this trainer
+    true = torch.cat([_t(prior, dev), _t(mask, dev)[:, None]], -1)
+    pred = _t(q, dev).requires_grad_(True)
+    kl = tr2.kl_loss(true, pred)
+    kl.backward()
+    eps_kl2 = philox.kl_eps(seed2, np.arange(n, dtype=np.uint64), 70)
+    want = float(np.sum(o.mc_kl(prior, q, eps_kl2, np.float64) * mask) / mask.sum())
+    assert rel_elem(kl.item(), want) < GRAD_TOL
+    ref2 = o.elbo_and_grads(physics, q, sigma, data, mask, prior, np.zeros((n, 2), np.float32), eps_kl2, np.float64)
+    assert rel_elem(kl.item(), ref2['kl']) < GRAD_TOL
+    g_kl = pred.grad.cpu().numpy()
+    assert rel_max(g_kl, ref2['grad_q_kl']) < GRAD_TOL
+    ref2_32 = o.elbo_and_grads(physics, q, sigma, data, mask, prior, np.zeros((n, 2), np.float32), eps_kl2, np.float32)
+    _elem_check(g_kl, ref2['grad_q_kl'], ref2_32['grad_q_kl'])
 
 
 def test_kl_loss_mc_and_closed_form(qb, dev, cfg_noise_off):
@@ -342,6 +426,14 @@ def test_full_size_properties_16M(qb, dev, cfg_noise_off):
     s_full, g1 = layer.forward_backward(x, w1)
     s_part, g_part = layer.forward_backward(x[sl].contiguous(), w1[sl].contiguous())
     assert torch.equal(s_full[sl], s_part) and torch.equal(g1[sl], g_part)          # shard invariance, bit-exact
+    # oracle parity AT full size: a random 100 000-voxel subsample of the 16 M outputs vs the float64 oracle
+    pick = torch.randperm(n, device=dev, generator=g)[:100_000]
+    ph = o.parse_params(cfg_noise_off)
+    s64, g64 = o.forward_backward(ph, x[pick].cpu().numpy(), w1[pick].cpu().numpy(), dtype=np.float64)
+    assert rel_elem(s_full[pick].cpu().numpy(), s64) < SIG_TOL
+    assert rel_max(g1[pick].cpu().numpy(), g64) < GRAD_TOL
+    _, g32 = o.forward_backward(ph, x[pick[:20_000]].cpu().numpy(), w1[pick[:20_000]].cpu().numpy(), dtype=np.float32)
+    _elem_check(g1[pick[:20_000]].cpu().numpy(), g64[:20_000], g32)
     del s, s_full
     _, g_ones = layer.forward_backward(x, None, want_signal=False)
     _, g2 = layer.forward_backward(x, w1 + 1.0, want_signal=False)
@@ -350,6 +442,41 @@ def test_full_size_properties_16M(qb, dev, cfg_noise_off):
 
 
 # ---------------------------------------------------------------------------------- training glue
+def test_config3_volume_elbo_matches_oracle(qb, dev, cfg_noise_off, physics):
+    """BASELINE config 3 shape: one 64^3 volume, sphere mask r = 28 (92 k live voxels of 262 144), 70-sample KL with
+    the in-kernel Philox draws, against the float64 oracle fed the same draws."""
+    side, S, seed = 64, 70, 2026
+    n = side ** 3
+    q, prior, sigma, data = _elbo_batch(physics, n, 64, spread=0.5)
+    zz, yy, xx = np.meshgrid(*(np.arange(side) - (side - 1) / 2.0,) * 3, indexing='ij')
+    mask = ((xx ** 2 + yy ** 2 + zz ** 2) <= 28.0 ** 2).astype(np.float32).reshape(n)
+    data *= mask[:, None]
+    idx = np.arange(n, dtype=np.uint64)
+    ref = o.elbo_and_grads(physics, q, sigma, data, mask, prior, philox.reparam_eps(seed, idx),
+                           philox.kl_eps(seed, idx, S), np.float64)
+    tr = _trainer(qb, cfg_noise_off)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    shp = (1, side, side, side)
+    qt = _t(q, dev).reshape(shp + (5,)).requires_grad_(True)
+    st = _t(sigma, dev).reshape(shp + (11,)).requires_grad_(True)
+    loss, info = tr.fused_elbo(layer, qt, st, _t(data, dev).reshape(shp + (11,)), _t(mask, dev).reshape(shp + (1,)),
+                               _t(prior, dev).reshape(shp + (5,)), kl_samples=S, seed=seed, return_maps=True)
+    loss.backward()
+    assert float(info['mask_sum']) == mask.sum()
+    assert rel_elem(info['nll'].item(), ref['nll']) < GRAD_TOL and rel_elem(info['kl'].item(), ref['kl']) < GRAD_TOL
+    assert rel_max(info['nll_map'].cpu().numpy().reshape(-1), ref['nll_map']) < GRAD_TOL
+    assert rel_max(info['kl_map'].cpu().numpy().reshape(-1), ref['kl_map']) < GRAD_TOL
+    gq, gs = qt.grad.cpu().numpy().reshape(n, 5), st.grad.cpu().numpy().reshape(n, 11)
+    assert rel_max(gq, ref['grad_q']) < GRAD_TOL and rel_max(gs, ref['grad_sigma']) < GRAD_TOL
+    sub = np.flatnonzero(mask > 0)[::5]                                              # float32 reference on 18 k live voxels
+    ref32 = o.elbo_and_grads(physics, q[sub], sigma[sub], data[sub], mask[sub], prior[sub],
+                             philox.reparam_eps(seed, idx[sub]), philox.kl_eps(seed, idx[sub], S), np.float32)
+    scale = float(mask[sub].sum() / mask.sum())                                      # the oracle divides by ITS sum(mask)
+    _elem_check(gq[sub], ref['grad_q'][sub], ref32['grad_q'] * scale)
+    _elem_check(gs[sub], ref['grad_sigma'][sub], ref32['grad_sigma'] * scale)
+    assert np.all(gq[mask == 0] == 0) and np.all(gs[mask == 0] == 0)
+
+
 def test_fused_step_equals_unfused_layer_composition(qb, dev, cfg_noise_off):
     """One fused launch == the reference's graph built from the separate layers (build_fine_tuner,
     model.py:239-286 + loss closures train.py:315-320), gradients w.r.t. the encoder parameters included."""
@@ -454,6 +581,106 @@ def test_misalignment_augmentation(qb, dev, cfg_noise_off):
     aug = qb.SignalGenerationLayer(cfg_noise_off, True, True, misaligned_prob=0.25)(x)
     frac = float((aug != clean).any(-1).float().mean())
     assert 0.2 < frac < 0.3 and torch.isfinite(aug).all()
+
+
+def _marginals_from_labels(d):
+    grid = np.empty((529, 2), np.float32)
+    grid[d['perm']] = d['train_y'][:, :2]
+    g = grid.reshape(23, 23, 2)
+    return g[:, 0, 0].copy(), g[0, :, 1].copy()
+
+
+def test_generation_with_misalignment_matches_reference_source(qb, dev, physics):
+    """create_synthetic_dataset(..., misaligned_prob=0.3) of the reference source, its recorded draws replayed through
+    generate_from_marginals -> qbold_generate + qbold_misalign + the chunked noise (signals.py:80-96 inside :282-285)."""
+    d = golden('ref_shim_dataset_misalign.npz')
+    cfg = o.default_config()                                                         # noise ON, as in the INI
+    oefs, dbvs = _marginals_from_labels(d)
+    layer = qb.SignalGenerationLayer(cfg, True, True, misaligned_prob=float(d['prob']))
+    x, y = qb.generate_from_marginals(layer, _t(oefs, dev), _t(dbvs, dev),
+                                      torch.as_tensor(d['perm'], device=dev).contiguous(), n_chunks=10,
+                                      snr_u01=_t(d['snr_u01'].reshape(-1), dev), noise_eps=_t(d['noise_eps'], dev),
+                                      misalign_u01=_t(d['mis_u01'], dev),
+                                      misalign_index=torch.as_tensor(d['mis_index'], device=dev),
+                                      misalign_eps=_t(d['mis_eps'], dev))
+    assert tuple(x.shape) == (520, 11)
+    assert rel_elem(y.cpu().numpy(), d['train_y']) < 1e-6
+    assert rel_elem(x.cpu().numpy(), d['train_x']) < 2 * SIG_TOL
+    # the production path: in-kernel Philox draws == oracle/philox.py draws, through the public entry point's layer
+    ph = o.parse_params(dict(cfg, simulate_noise='False'))
+    clean = qb.SignalGenerationLayer(dict(cfg, simulate_noise='False'), True, True, misaligned_prob=0.1, seed=5)
+    xv = _rand_voxels(6000, 14)
+    got = clean.misalign(_t(xv, dev), clean._forward_raw(_t(xv, dev)), seed=1234, offset=777)
+    u, idx, eps = philox.misalign_draws(1234, np.arange(6000, dtype=np.uint64) + np.uint64(777), 11)
+    want = o.forward_misaligned(ph, xv, 0.1, u, idx, eps, dtype=np.float64)
+    assert rel_elem(got.cpu().numpy(), want) < SIG_TOL
+    assert 0.07 < float((u < 0.1).mean()) < 0.13 and idx.min() == 4 and idx.max() == 9
+    # create_synthetic_dataset honours misaligned_prob (the reference CLI passes 0.1, signals.py:330)
+    cfg2 = dict(cfg, sample_size='100', simulate_noise='False')
+    x0, y0 = qb.create_synthetic_dataset(cfg2, True, True, 0.0, device=dev, seed=3)
+    x1, y1 = qb.create_synthetic_dataset(cfg2, True, True, 0.1, device=dev, seed=3)
+    assert torch.equal(y0, y1) and torch.equal(x0[:, :5], x1[:, :5])
+    frac = float((x0 != x1).any(-1).float().mean())
+    assert 0.08 < frac < 0.12
+    with pytest.raises(qb.QboldError):                                               # randint(4, 4) in the reference
+        cfg5 = dict(cfg2, tau_start='0.0', tau_end='0.05', tau_step='0.01')
+        qb.SignalGenerationLayer(cfg5, True, True, misaligned_prob=0.5)(_t(xv[:8], dev))
+
+
+@pytest.mark.parametrize('full', [True, False])
+@pytest.mark.parametrize('blood', [True, False])
+def test_variable_hct_forward_and_gradient(qb, dev, cfg_noise_off, physics, full, blood):
+    """variable_hct=True (signals.py:64-70): rows (OEF, DBV, Hct); value and the 3-column VJP (d/dHct through dw and
+    the blood term) against the reference-source fixture and the float64 oracle; autograd through the layer."""
+    g = golden('ref_shim_forward_hct.npz')
+    key = 'f%d_b%d' % (int(full), int(blood))
+    layer = qb.SignalGenerationLayer(cfg_noise_off, full, blood, variable_hct=True)
+    x = _t(g['oef_dbv_hct'], dev)
+    s, g2 = layer.forward_backward(x, _t(g['g_rand'], dev))
+    _, g1 = layer.forward_backward(x, None, want_signal=False)
+    assert tuple(g2.shape) == (96, 3)
+    assert rel_elem(s.cpu().numpy(), g['signal_' + key]) < SIG_TOL
+    for j in range(3):
+        assert rel_max(g1.cpu().numpy()[:, j], g['grad_ones_' + key][:, j]) < GRAD_TOL
+        assert rel_max(g2.cpu().numpy()[:, j], g['grad_rand_' + key][:, j]) < GRAD_TOL
+    r = np.random.default_rng(17)
+    xv = _rand_voxels(3000, 15)
+    # Hct up to 0.6, but OEF * Hct <= 0.38: beyond 1.5 tau dw u_0 = 3.45e-4 the float32 reference's node 0 stops being
+    # exactly dead (1 - j0f(x0) becomes one ulp = 6e-8, times a weight of 1.7e7) and float64 is no longer its oracle
+    hct = np.minimum(r.uniform(0.2, 0.6, 3000), 0.38 / xv[:, 0]).astype(np.float32)
+    xv = np.concatenate([xv, hct[:, None]], -1)
+    gs = r.standard_normal((3000, 11)).astype(np.float32)
+    s, gg = layer.forward_backward(_t(xv, dev), _t(gs, dev))
+    s64, g64 = o.forward_backward(physics, xv, gs, full, blood, np.float64, variable_hct=True)
+    assert rel_elem(s.cpu().numpy(), s64) < SIG_TOL
+    for j in range(3):
+        assert rel_max(gg.cpu().numpy()[:, j], g64[:, j]) < GRAD_TOL
+    xa = _t(xv[:257], dev).reshape(257, 1, 3).requires_grad_(True)
+    w = _t(gs[:257], dev).reshape(257, 1, 11)
+    (layer(xa) * w).sum().backward()
+    assert torch.equal(xa.grad.reshape(-1, 3), gg[:257])
+
+
+def test_variable_hct_generation_and_misalignment(qb, dev, cfg_noise_off):
+    d = golden('ref_shim_dataset_hct.npz')
+    cfg = o.default_config()
+    oefs, dbvs = _marginals_from_labels(d)
+    layer = qb.SignalGenerationLayer(cfg, True, True, variable_hct=True)
+    x, y = qb.generate_from_marginals(layer, _t(oefs, dev), _t(dbvs, dev),
+                                      torch.as_tensor(d['perm'], device=dev).contiguous(), n_chunks=10,
+                                      snr_u01=_t(d['snr_u01'].reshape(-1), dev), noise_eps=_t(d['noise_eps'], dev))
+    assert tuple(x.shape) == (520, 11) and tuple(y.shape) == (529, 3)
+    assert rel_elem(y.cpu().numpy(), d['train_y']) < 1e-6
+    assert rel_elem(x.cpu().numpy(), d['train_x']) < 2 * SIG_TOL
+    tx, ty = qb.create_synthetic_dataset(dict(cfg, sample_size='40'), True, True, 0.0, variable_hct=True, device=dev)
+    assert tuple(tx.shape) == (1600, 11) and tuple(ty.shape) == (1600, 3) and torch.isfinite(tx).all()
+    # misalignment with a per-voxel Hct column (signals.py:80-96 broadcasts hct [N,1] over the images)
+    g = golden('ref_shim_forward_hct.npz')
+    lay = qb.SignalGenerationLayer(cfg_noise_off, True, True, misaligned_prob=float(g['mis_prob']), variable_hct=True)
+    xh = _t(g['oef_dbv_hct'], dev)
+    got = lay.misalign(xh, lay._forward_raw(xh), _t(g['mis_u01'], dev), torch.as_tensor(g['mis_index'], device=dev),
+                       _t(g['mis_eps'], dev))
+    assert rel_elem(got.cpu().numpy(), g['signal_misaligned']) < SIG_TOL
 
 
 def test_diagonal_posterior_variant(qb, dev, cfg_noise_off):
@@ -911,6 +1138,64 @@ def test_mog_population_prior_kl_matches_reference_source(qb, dev, cfg_noise_off
     assert rel_elem(kl.item(), a['kl_mog']) < GRAD_TOL
     kl.backward()
     assert rel_max(q16.grad.cpu().numpy().reshape(-1, 16), a['kl_mog_grad']) < GRAD_TOL
+
+
+def test_infer_inv_gamma_pretraining_loss_matches_reference_source(qb, dev, cfg_noise_off):
+    """synthetic_data_loss with infer_inv_gamma=True (model.py:454-455,493-496): the learned InverseGamma parameters
+    ride in channels 4..7; value and the gradient of all 8 channels (the hyper-parameter gradient lands on voxel 0)."""
+    a, _ = _adj()
+    tr = _trainer(qb, cfg_noise_off, use_mvg=False, infer_inv_gamma=True)
+    q8 = _t(a['synth_iginf_pred'], dev).reshape(-1, 1, 1, 1, 8).requires_grad_(True)
+    loss = tr.synthetic_data_loss(_t(a['synth_iginf_labels'], dev).reshape(-1, 1, 1, 1, 3), q8)
+    loss.backward()
+    assert rel_elem(loss.item(), a['synth_iginf']) < GRAD_TOL
+    g = q8.grad.cpu().numpy().reshape(-1, 8)
+    assert rel_max(g[:, :4], a['synth_iginf_grad'][:, :4]) < GRAD_TOL
+    assert rel_elem(g[0, 4:], a['synth_iginf_grad'][0, 4:]) < GRAD_TOL and np.all(g[1:, 4:] == 0)
+    with pytest.raises(ValueError):                                                  # tf.split(y_pred, 2, -1) of 9 channels
+        _trainer(qb, cfg_noise_off, use_mvg=True, infer_inv_gamma=True).synthetic_data_loss(
+            _t(a['synth_iginf_labels'], dev), torch.zeros(a['labels'].shape[0], 9, device=dev))
+    # the encoder carries the hyper-prior variable (model.py:201-205)
+    from qbold_vi_b200.encoder import Encoder
+    enc = Encoder(no_units=16, no_intermediate_layers=1, use_mvg=False, infer_inv_gamma=True).to(dev)
+    out0, out1, _ = enc(torch.rand(1, 4, 4, 2, 11, device=dev) + 0.5)
+    assert out0.shape[-1] == 8 and out1.shape[-1] == 4
+    assert torch.allclose(out0[0, 0, 0, 0, 4:], torch.tensor([20.0, 2.5, 20.0, 2.5], device=dev))
+
+
+def test_population_prior_is_trainable_and_operands_are_validated(qb, dev, cfg_noise_off):
+    from qbold_vi_b200.encoder import Encoder
+    torch.manual_seed(0)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    data = layer(_t(_rand_voxels(2 * 6 * 6 * 2, 4), dev)).reshape(2, 6, 6, 2, 11) * 100.0
+    mask = (torch.rand(2, 6, 6, 2, 1, device=dev) > 0.2).float()
+    for m_comp in (1, 3):
+        tr = _trainer(qb, cfg_noise_off, use_mvg=False, use_population_prior=True, mog_components=m_comp)
+        enc = Encoder(no_units=16, no_intermediate_layers=1, use_mvg=False).to(dev)
+        ft = tr.build_fine_tuner(enc, layer)
+        assert ft.pop_prior.numel() == 4 * m_comp and ft.pop_prior.requires_grad
+        out = ft(data * mask, mask)
+        assert out['predictions'].shape[-1] == 4 * (m_comp + 1)                      # model.py:268-271
+        loss, info = ft.fused_loss(data * mask, mask, None)
+        loss.backward()
+        assert torch.isfinite(loss) and ft.pop_prior.grad is not None and float(ft.pop_prior.grad.abs().sum()) > 0
+        assert enc.final.weight.grad is not None and float(enc.final.weight.grad.abs().sum()) > 0
+    with pytest.raises(NotImplementedError):
+        _trainer(qb, cfg_noise_off, use_mvg=True, use_population_prior=True).build_fine_tuner(enc, layer)
+    tr = _trainer(qb, cfg_noise_off)
+    q10 = torch.zeros(8, 10, device=dev)
+    true = torch.zeros(8, 6, device=dev)
+    with pytest.raises(ValueError):
+        tr.kl_loss(true, q10)                                                        # 10-channel 'predictions'
+    with pytest.raises(ValueError):
+        tr.fused_elbo(layer, torch.zeros(8, 5, device=dev), torch.ones(8, 11, device=dev), torch.ones(8, 11, device=dev),
+                      torch.ones(8, 1, device=dev), torch.zeros(4, 5, device=dev))   # prior of another voxel count
+    # the parameter block follows the trainer's flags and the layer's lifetime (no id()-keyed cache)
+    tr._student_t_df = 4.0
+    p1 = tr._params_for(layer)
+    tr._student_t_df = 200
+    p2 = tr._params_for(layer)
+    assert p1 is not p2 and float(p1.student_t_df) == 4.0 and tr._params_for(layer) is p2
 
 
 def test_fused_elbo_full_size_properties(qb, dev, cfg_noise_off):

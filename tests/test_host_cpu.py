@@ -75,8 +75,11 @@ def test_layer_argument_handling(qb):
     assert qb.SignalGenerationLayer(cfg, 'True', 'False')._include_blood is False
     with pytest.raises(ValueError):
         qb.SignalGenerationLayer(cfg, 'yes', True)
-    with pytest.raises(NotImplementedError):
-        qb.SignalGenerationLayer(cfg, True, True, misaligned_prob=0.1, variable_hct=True)
+    both = qb.SignalGenerationLayer(cfg, True, True, misaligned_prob=0.1, variable_hct=True)   # signals.py:64-96
+    assert both._variable_hct and both._misaligned_prob == 0.1
+    import torch as _torch
+    with pytest.raises(AssertionError):
+        both(_torch.zeros(4, 2))                                            # needs (OEF, DBV, Hct) rows
     import torch
     layer = qb.SignalGenerationLayer(cfg, True, True)
     with pytest.raises(AssertionError):

@@ -109,6 +109,57 @@ def test_synthetic_dataset_vs_reference_source(tag):
     assert rel_elem(x, d['train_x']) < 5e-6
 
 
+def _marginals_from_labels(d):
+    """Un-shuffle the labels of a dataset fixture to recover the 23 OEF / 23 DBV marginals the reference drew."""
+    grid = np.empty((529, 2), np.float32)
+    grid[d['perm']] = d['train_y'][:, :2]
+    g = grid.reshape(23, 23, 2)
+    return g[:, 0, 0].copy(), g[0, :, 1].copy()
+
+
+def test_synthetic_dataset_with_misalignment_vs_reference_source():
+    """create_synthetic_dataset(..., misaligned_prob=0.3): the reference's own draws (uniform, randint, two normals per
+    chunk, then the noise draws) replayed through the restatement of signals.py:80-96."""
+    d = golden('ref_shim_dataset_misalign.npz')
+    ph = o.parse_params(o.default_config())
+    oefs, dbvs = _marginals_from_labels(d)
+    f32 = np.float32
+    snr_u = (d['snr_u01'] * f32(120 - 50) + f32(50)).astype(f32)
+    mis = (float(d['prob']), d['mis_u01'], d['mis_index'], d['mis_eps'])
+    x, y = o.synthetic_dataset_from_draws(ph, oefs, dbvs, d['perm'], snr_u, d['noise_eps'], misalign=mis)
+    assert rel_elem(y, d['train_y']) < 1e-6
+    assert rel_elem(x, d['train_x']) < 5e-6
+    assert 100 < int((d['mis_u01'] < d['prob']).sum()) < 220 and d['mis_index'].min() >= 4 and d['mis_index'].max() <= 9
+    x0, _ = o.synthetic_dataset_from_draws(ph, oefs, dbvs, d['perm'], snr_u, d['noise_eps'])
+    assert rel_elem(x0, d['train_x']) > 1e-2                   # the augmentation is visible
+
+
+def test_variable_hct_vs_reference_source(physics):
+    g = golden('ref_shim_forward_hct.npz')
+    x = g['oef_dbv_hct']
+    for full in (1, 0):
+        for blood in (1, 0):
+            key = 'f%d_b%d' % (full, blood)
+            for dt, tol in ((np.float32, 2e-6), (np.float64, 1e-5)):
+                S = o.forward(physics, x, bool(full), bool(blood), dt, variable_hct=True)
+                assert rel_elem(S, g['signal_' + key]) < tol
+                _, g1 = o.forward_backward(physics, x, np.ones((x.shape[0], 11)), bool(full), bool(blood), dt,
+                                           variable_hct=True)
+                _, g2 = o.forward_backward(physics, x, g['g_rand'], bool(full), bool(blood), dt, variable_hct=True)
+                for j in range(3):                              # OEF, DBV and Hct columns on their own scales
+                    assert rel_max(g1[:, j], g['grad_ones_' + key][:, j]) < tol
+                    assert rel_max(g2[:, j], g['grad_rand_' + key][:, j]) < 5 * tol
+    sm = o.forward_misaligned(physics, x, float(g['mis_prob']), g['mis_u01'], g['mis_index'], g['mis_eps'],
+                              dtype=np.float32, variable_hct=True)
+    assert rel_elem(sm, g['signal_misaligned']) < 2e-6
+    d = golden('ref_shim_dataset_hct.npz')
+    ph = o.parse_params(o.default_config())
+    oefs, dbvs = _marginals_from_labels(d)
+    snr_u = (d['snr_u01'] * np.float32(70) + np.float32(50)).astype(np.float32)
+    xs, ys = o.synthetic_dataset_from_draws(ph, oefs, dbvs, d['perm'], snr_u, d['noise_eps'], variable_hct=True)
+    assert rel_elem(ys, d['train_y']) < 1e-6 and rel_elem(xs, d['train_x']) < 5e-6
+
+
 # ------------------------------------------------------------------ structural identities (SURVEY.md 8c)
 def test_tau_symmetry_and_tau0_column(physics):
     rng = np.random.default_rng(3)
