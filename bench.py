@@ -160,7 +160,7 @@ def fused_elbo_leg(qb, layer, cfg, x, sig, dev, f_alg_forward, fma_tf, voxels=1 
     return out
 
 
-def streaming_leg(qb, cfg, x, dev, hbm_peak, reps=5):
+def streaming_leg(qb, cfg, x, dev, hbm_peak, fma_tf, f_big, n_cols, reps=5):
     """Secondary line: the streaming synthetic-data path (qbold_generate: shuffled OEF x DBV meshgrid -> signals +
     labels, nothing read but the two marginals) and the HBM-bound log-linear forward (full_model=False), each with
     its achieved HBM GB/s (algorithmic bytes: 44 B signal + 12 B labels written; 8 B read + 44 B written)."""
@@ -186,14 +186,114 @@ def streaming_leg(qb, cfg, x, dev, hbm_peak, reps=5):
     dbvs = torch.rand(n // 4096, device=dev, generator=g) * 0.192 + 0.003
     ms_gen = timed(lambda: qb.generate_from_marginals(full, oefs, dbvs, None, n_chunks=1))
     ms_ll = timed(lambda: loglin(x))
+    # forward-only FLOP convention of SURVEY.md 8(d): 127 live nodes x columns x (15 small / 56 asymptotic)
+    f_fwd = 127 * n_cols * (15 * (1 - f_big) + 56 * f_big) + 200.0
+    tf_gen = n * f_fwd / (ms_gen * 1e-3) / 1e12
     return {'generate_full_model': {'voxels': n, 'ms': ms_gen, 'voxels_per_s': n / (ms_gen * 1e-3),
                                     'hbm_gbs': n * 56 / (ms_gen * 1e-3) / 1e9,
                                     'hbm_frac': n * 56 / (ms_gen * 1e-3) / 1e9 / hbm_peak,
-                                    'bound': 'fp32 (same quadrature as the headline kernel, forward only)'},
+                                    'alg_flops_per_voxel': f_fwd, 'achieved_tflops': tf_gen, 'fp32_peak_tflops': fma_tf,
+                                    'fp32_frac': tf_gen / fma_tf,
+                                    'bound': 'fp32 (same quadrature as the headline kernel, forward only): the streaming '
+                                             'path is ~650 FLOP/B, far above the HBM ridge'},
             'forward_loglinear': {'voxels': n, 'ms': ms_ll, 'voxels_per_s': n / (ms_ll * 1e-3),
                                   'hbm_gbs': n * 52 / (ms_ll * 1e-3) / 1e9,
                                   'hbm_frac': n * 52 / (ms_ll * 1e-3) / 1e9 / hbm_peak, 'bound': 'hbm'},
             'hbm_peak_gbs': hbm_peak}
+
+
+def training_and_inference_legs(qb, dev, rank, world, steps=10, volumes_per_gpu=2, size=64):
+    """BASELINE configs 3-5 on every N: the amortized-VI training step (encoder forward + backward, fused ELBO kernel
+    with the 70-sample KL, TV stencil, NCCL all-reduce of the flat encoder gradient, AdamW) on `volumes_per_gpu`
+    synthetic 64^3 volumes per GPU (sphere mask r = 28), and whole-volume posterior inference with 64 samples per
+    voxel.  Weak scaling: per-GPU work is fixed; times are CUDA events, max over ranks.  Run by ALL ranks."""
+    import torch
+    import torch.distributed as dist
+    from qbold_vi_b200 import distributed as D
+    from qbold_vi_b200.encoder import create_encoder_from_args
+
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    args = qb.optimal_arguments()
+    cfg = qb.load_system_parameters(qb.config.DEFAULT_CONFIG_PATH)
+    cfg['simulate_noise'] = 'False'
+    layer = qb.SignalGenerationLayer(cfg, args.full_model, args.use_blood)
+    tr = qb.EncoderTrainer(cfg, no_units=args.no_units, no_intermediate_layers=args.no_intermediate_layers,
+                           student_t_df=args.student_t_df, initial_im_sigma=args.im_loss_sigma,
+                           multi_image_normalisation=args.multi_image_normalisation,
+                           channelwise_gating=args.channelwise_gating, use_mvg=args.use_mvg,
+                           use_population_prior=args.use_population_prior, predict_log_data=args.predict_log_data, seed=1)
+    torch.manual_seed(1)
+    enc = create_encoder_from_args(args).to(dev)
+    B, S = volumes_per_gpu, size
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    truth = torch.stack([torch.rand((B, S, S, S), device=dev, generator=g) * 0.5 + 0.15,
+                         torch.rand((B, S, S, S), device=dev, generator=g) * 0.1 + 0.01], -1)
+    ax = torch.arange(S, device=dev, dtype=torch.float32) - (S - 1) / 2
+    r2 = ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2
+    mask = (r2 <= (28.0 * S / 64) ** 2).float()[None, ..., None].expand(B, S, S, S, 1).contiguous()
+    noisy = qb.SignalGenerationLayer(dict(cfg, simulate_noise='True'), True, True, seed=7 + rank)
+    data = (noisy(truth.reshape(-1, 2)).reshape(B, S, S, S, 11) * 100.0 * mask).contiguous()
+    with torch.no_grad():
+        prior = enc(data)[0].clone()
+    dp = D.DataParallelTrainer(enc, tr, layer, ft_lr=args.ft_lr, adamw_decay=args.adamw_decay,
+                               smoothness_weight=args.smoothness_weight)
+    voxels = B * S ** 3
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k, warm=3):
+        for _ in range(warm):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1) / k], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    last = {}
+    launches0 = qb.launch_count()
+    ms_train = timed(lambda: last.update(s=dp.step(data, mask, prior)), steps)
+    own_launches = (qb.launch_count() - launches0) / (steps + 3)
+    loss = float(last['s']['loss'])                                       # the only host read, after the timed region
+    ms_ar = timed(lambda: dp.bucket.all_reduce_(), 20) if world > 1 else 0.0
+
+    def enc_only():
+        dp.bucket.zero_()
+        _, q, s_ = enc(data)
+        (q.sum() + s_.sum()).backward()
+    ms_enc = timed(enc_only, steps)
+    with torch.no_grad():
+        _, q, sigma = enc(data)
+    q, sigma = q.contiguous(), sigma.contiguous()
+    msum = mask.sum(dtype=torch.float64)
+    ms_fused = timed(lambda: tr.fused_elbo(layer, q, sigma, data, mask, prior, kl_samples=70, mask_sum=msum), steps)
+    ms_inf = timed(lambda: tr.posterior_inference(layer, q, sigma, data, mask, prior, no_samples=64), max(3, steps // 2))
+    common = {'volumes_per_gpu': B, 'volume': '%d^3' % S, 'voxels_per_gpu': voxels, 'masked_fraction': float(mask.mean()),
+              'encoder_params': sum(p.numel() for p in enc.parameters()),
+              'precision': 'qBOLD kernels fp32; encoder convolutions / Dense layers TF32 tensor cores'}
+    train = dict(common, config='BASELINE config 3 / 5: amortized-VI training step (encoder fwd+bwd, fused ELBO kernel '
+                 'with 70-sample KL, TV, NCCL all-reduce of the encoder gradient, AdamW), weak scaling',
+                 ms_per_step=ms_train, steps=steps, voxel_signals_per_s=world * voxels * 11 / (ms_train * 1e-3),
+                 ms_allreduce_alone=ms_ar, allreduce_floats=int(dp.bucket.flat.numel()),
+                 ms_encoder_fwd_bwd=ms_enc, ms_fused_elbo_kernel=ms_fused, own_kernel_launches_per_step=own_launches,
+                 host_syncs_per_step=0, loss=loss,
+                 limiter='encoder forward + backward (3x3x1 convolutions and Dense GEMMs): %.0f %% of the step'
+                         % (100.0 * ms_enc / ms_train))
+    infer = dict(common, config='BASELINE config 4: whole-volume posterior inference, 64 samples per voxel (means / '
+                 'variances of OEF, DBV, R2prime, likelihood map, KL map)', ms_per_volume_batch=ms_inf,
+                 voxels_per_s=world * voxels / (ms_inf * 1e-3), samples_per_voxel=64)
+    return train, infer
 
 
 def workload_config(voxels, gpus):
@@ -214,6 +314,7 @@ def main():
     ap.add_argument('--voxels', type=int, default=1 << 24)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--train-steps', type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -294,7 +395,18 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * N_TAU * args.e2e_steps / float(e2e_s.item())
-    e2e_ok = bool(torch.equal(hs[:4096], sig[:4096].cpu()))
+    e2e_ok = bool(torch.equal(hs, sig.cpu()) and torch.equal(hgr, grad.cpu()))      # every element of both outputs
+    # what this box's host <-> device link sustains for the same copy pattern with no kernel (all ranks at once)
+    gbps = (C.c_double * 2)()
+    barrier()
+    qb._lib.check(lib.qbold_host_copy_ceiling(hg.data_ptr(), hs.data_ptr(), hg.numel() * 4, 3, gbps))
+    ceil_t = torch.tensor([gbps[0]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ceil_t, op=dist.ReduceOp.MIN)
+    ceiling_gbs = float(ceil_t.item())
+    e2e_gbs = n * (8 + 4 * N_TAU) * args.e2e_steps / float(e2e_s.item()) / 1e9      # per direction, per GPU
+    del hx, hg, hs, hgr
+    train_leg, infer_leg = training_and_inference_legs(qb, dev, rank, world, steps=args.train_steps)
 
     if rank == 0:
         # ---- roofline of the dominant (only) kernel: FP32 CUDA-core bound, HBM reported as secondary
@@ -332,8 +444,14 @@ def main():
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n * (8 + 4 * N_TAU),
                     'd2h_bytes_per_step': n * (8 + 4 * N_TAU), 'steps': args.e2e_steps,
-                    'path': 'qbold_forward_backward_host: pinned host buffers, 4-slot H2D/kernel/D2H pipeline, 512k-voxel chunks',
-                    'matches_device_path': e2e_ok},
+                    'path': 'qbold_forward_backward_host: pinned host buffers, 6-slot H2D/kernel/D2H pipeline, 128k-voxel chunks',
+                    'matches_device_path': e2e_ok, 'compared': 'every element of signal and gradient',
+                    'gbs_per_direction_per_gpu': e2e_gbs,
+                    'host_ceiling': {'gbs_per_direction_per_gpu': ceiling_gbs,
+                                     'how': 'qbold_host_copy_ceiling: the same pinned buffers, chunk size and stream count, '
+                                            'H2D and D2H concurrently, no kernel, all ranks at once (min over ranks)'},
+                    'frac_of_host_ceiling': e2e_gbs / ceiling_gbs if ceiling_gbs > 0 else None},
+            'training_step': train_leg, 'inference_64': infer_leg,
             'gpu_launches': launches,
             'roofline': {'bound': 'fp32', 'bound_note': 'FP32 CUDA-core issue (not HBM, not tensor): ~570 FLOP/B, see '
                                                         'SURVEY.md 8(d); HBM fraction reported under "hbm"',
@@ -352,7 +470,7 @@ def main():
         }
         if world == 1:
             line['fused_elbo'] = fused_elbo_leg(qb, layer, cfg, x, sig, dev, f_alg, fma_tf)
-            line['streaming'] = streaming_leg(qb, cfg, x, dev, hbm_peak)
+            line['streaming'] = streaming_leg(qb, cfg, x, dev, hbm_peak, fma_tf, f_big, layer.params.n_cols)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cpu_port_run(8192, threads)

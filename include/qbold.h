@@ -150,6 +150,11 @@ int qbold_misalign(const QboldParams* p, const float* oef_dbv, int32_t width, in
 int qbold_forward_backward_host(const QboldParams* p, const float* h_oef_dbv, const float* h_g_signal,
                                 int64_t n, float* h_signal, float* h_g_oef_dbv);
 
+/* The host <-> device ceiling of this box for the copy pattern of qbold_forward_backward_host (same chunk size,
+ * same number of streams, H2D and D2H concurrently, no kernel).  h_src, h_dst: host buffers of `bytes` each
+ * (pinned); gbps[0] = H2D GB/s, gbps[1] = D2H GB/s while both directions run (best of `reps`). */
+int qbold_host_copy_ceiling(const void* h_src, void* h_dst, int64_t bytes, int32_t reps, double* gbps);
+
 /* Replaces ReparamTrickLayer.call (model.py:21-50), use_mvg branch: q [n,5] raw encoder
  * outputs; eps [n,2] explicit N(0,1) draws, or NULL -> Philox4x32-10 keyed (seed, voxel). */
 int qbold_reparam_sample(const float* q, const float* eps, uint64_t seed, uint64_t offset,
@@ -197,6 +202,14 @@ int qbold_elbo_fused(const QboldParams* p, const float* q, const float* sigma, c
                      float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
                      float* kl_map, double* sums, void* stream);
 
+/* Same kernel with 1/sum(mask) read from DEVICE memory (one float): the data-parallel trainer all-reduces the mask
+ * count on the device and never brings it to the host, so a training step has no host synchronisation. */
+int qbold_elbo_fused_dev(const QboldParams* p, const float* q, const float* sigma, const float* y,
+                         const float* mask, const float* prior, const float* eps, const float* eps_kl,
+                         uint64_t seed, uint64_t offset, int32_t kl_samples, const float* inv_mask_sum_dev,
+                         float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
+                         float* kl_map, double* sums, void* stream);
+
 /* fine_tune_loss_fn alone (model.py:527-568) for predictions already in HBM: nll_map[n] = mask * sum_tau NLL,
  * and (optional) d_pred / d_sigma [n,n_tau] = d nll_map[v] / d pred[v,:], d sigma[v,:].  mask may be NULL. */
 int qbold_nll(const QboldParams* p, const float* y, const float* pred, const float* sigma, const float* mask,
@@ -231,6 +244,9 @@ int qbold_nll_map(const QboldParams* p, const float* q, const float* sigma, cons
  * grad_q (same shape as q, may be NULL) = scale * d(sum |d|)/dq, so scale = weight / sum(mask). */
 int qbold_smoothness(const float* q, int32_t n_ch, const float* mask, int64_t n_vol, int32_t nx, int32_t ny,
                      int32_t nz, float scale, double* tv_sum, float* grad_q, void* stream);
+/* Same kernel with `scale` read from device memory (see qbold_elbo_fused_dev). */
+int qbold_smoothness_dev(const float* q, int32_t n_ch, const float* mask, int64_t n_vol, int32_t nx, int32_t ny,
+                         int32_t nz, const float* scale_dev, double* tv_sum, float* grad_q, void* stream);
 
 /* synthetic_data_loss (model.py:449-514) per label row: logit-MVN NLL of (OEF, DBV) under the predicted
  * distribution (use_mvg: logit_gaussian_mvg_log_prob :376-400, pred [n,5]; else logit_gaussian_log_prob :406-421,

@@ -65,6 +65,7 @@ _SIGNATURES = {
     'qbold_misalign': (C.c_int, [_P(QboldParams), _f, C.c_int32, C.c_int64, C.c_float, _f, _f, _f, C.c_uint64, C.c_uint64,
                                  _f, C.c_void_p]),
     'qbold_forward_backward_host': (C.c_int, [_P(QboldParams), _f, _f, C.c_int64, _f, _f]),
+    'qbold_host_copy_ceiling': (C.c_int, [_f, _f, C.c_int64, C.c_int32, _P(C.c_double)]),
     'qbold_reparam_sample': (C.c_int, [_f, _f, C.c_uint64, C.c_uint64, C.c_int64, _f, C.c_void_p]),
     'qbold_column_mean': (C.c_int, [_f, C.c_int64, C.c_int32, _f, _f, C.c_void_p]),
     'qbold_add_noise': (C.c_int, [_P(QboldParams), _f, C.c_int64, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -74,6 +75,8 @@ _SIGNATURES = {
                                  _f, _f, C.c_void_p]),
     'qbold_elbo_fused': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32,
                                    C.c_float, C.c_float, C.c_int64, _f, _f, _f, _f, _f, C.c_void_p]),
+    'qbold_elbo_fused_dev': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32,
+                                       _f, C.c_float, C.c_int64, _f, _f, _f, _f, _f, C.c_void_p]),
     'qbold_nll': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, C.c_int64, _f, _f, _f, C.c_void_p]),
     'qbold_kl': (C.c_int, [_f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f, _f, C.c_void_p]),
     'qbold_posterior_stats': (C.c_int, [_P(QboldParams), _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f, _f,
@@ -82,6 +85,8 @@ _SIGNATURES = {
                                 C.c_void_p]),
     'qbold_smoothness': (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, _f, _f,
                                    C.c_void_p]),
+    'qbold_smoothness_dev': (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _f, _f, _f,
+                                       C.c_void_p]),
     'qbold_synth_nll': (C.c_int, [_f, C.c_int32, _f, C.c_int32, C.c_double, C.c_double, C.c_int64, C.c_float, _f, _f,
                                   _f, C.c_void_p]),
     'qbold_synth_nll_inferred': (C.c_int, [_f, C.c_int32, _f, C.c_int32, C.c_int32, _f, C.c_int64, C.c_float, _f, _f, _f,

@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
                                                    const float* __restrict__ y, const float* __restrict__ mask,
                                                    const float* __restrict__ prior, const float* __restrict__ eps,
                                                    const float* __restrict__ eps_kl, uint64_t seed, uint64_t offset,
-                                                   int kl_samples, float inv_mask_sum, float kl_weight, int64_t n,
+                                                   int kl_samples, float inv_mask_sum,
+                                                   const float* __restrict__ inv_mask_sum_dev, float kl_weight, int64_t n,
                                                    float* __restrict__ grad_q, float* __restrict__ grad_sigma,
                                                    float* __restrict__ nll_map, float* __restrict__ kl_map,
                                                    double* __restrict__ sums, unsigned long long* __restrict__ work) {
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
     const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
     const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
     const float df = P.student_t_df;
+    if (inv_mask_sum_dev != nullptr) inv_mask_sum = __ldg(inv_mask_sum_dev);   // 1 / global sum(mask), left on the device
     const bool wide = nt > 16;
 
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
@@ -463,6 +465,7 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
                                                            const float* __restrict__ prior, const float* __restrict__ eps,
                                                            const float* __restrict__ eps_kl, uint64_t seed,
                                                            uint64_t offset, int kl_samples, float inv_mask_sum,
+                                                           const float* __restrict__ inv_mask_sum_dev,
                                                            float kl_weight, int64_t n, float* __restrict__ grad_q,
                                                            float* __restrict__ grad_sigma, float* __restrict__ nll_map,
                                                            float* __restrict__ kl_map, double* __restrict__ sums,
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
     const float norm_w = multi ? (1.0f / 3.0f) : 1.0f;
     const float df = P.student_t_df;
     const QuadCtx qc = make_quad_ctx<kSched>(P, ss, lane, my_col, my_tau);
+    if (inv_mask_sum_dev != nullptr) inv_mask_sum = __ldg(inv_mask_sum_dev);   // 1 / global sum(mask), left on the device
     const int64_t npairs = (n + 1) >> 1;
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
     int bad = 0;
@@ -993,11 +997,11 @@ static int64_t persistent_grid(K kernel, int64_t n_warp_items) {
 
 using namespace qb;
 
-extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const float* sigma, const float* y,
-                                const float* mask, const float* prior, const float* eps, const float* eps_kl,
-                                uint64_t seed, uint64_t offset, int32_t kl_samples, float inv_mask_sum,
-                                float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
-                                float* kl_map, double* sums, void* stream) {
+static int elbo_fused_impl(const QboldParams* p, const float* q, const float* sigma, const float* y,
+                           const float* mask, const float* prior, const float* eps, const float* eps_kl,
+                           uint64_t seed, uint64_t offset, int32_t kl_samples, float inv_mask_sum,
+                           const float* inv_mask_sum_dev, float kl_weight, int64_t n, float* grad_q,
+                           float* grad_sigma, float* nll_map, float* kl_map, double* sums, void* stream) {
     if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_elbo_fused: bad params block");
     if (n < 0 || kl_samples < 0) return fail(QBOLD_EINVAL, "qbold_elbo_fused: negative size");
     if (n == 0) return QBOLD_OK;
@@ -1015,7 +1019,7 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
         const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo<HP, MU>, INT64_MAX / 64)); \
         k_elbo<HP, MU><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(                                  \
             *p, q, sigma, y, mask, HP ? prior : nullptr, eps, HP ? eps_kl : nullptr, seed, offset,                    \
-            HP ? kl_samples : 0, inv_mask_sum, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, work);        \
+            HP ? kl_samples : 0, inv_mask_sum, inv_mask_sum_dev, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, work);        \
     } while (0)
     if (path == kSched && p->full_model && p->n_tau <= 16) {
         const int64_t wantp = ((n + 1) / 2 + 7) / 8;
@@ -1023,13 +1027,13 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
             static int64_t grid_cache = 0;
             const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<true>, INT64_MAX / 64));
             k_elbo_pair<true><<<(unsigned)(wantp < grid ? wantp : grid), kThreads, 0, st>>>(
-                *p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, kl_weight, n, grad_q,
+                *p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, inv_mask_sum_dev, kl_weight, n, grad_q,
                 grad_sigma, nll_map, kl_map, sums, work);
         } else {
             static int64_t grid_cache = 0;
             const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<false>, INT64_MAX / 64));
             k_elbo_pair<false><<<(unsigned)(wantp < grid ? wantp : grid), kThreads, 0, st>>>(
-                *p, q, sigma, y, mask, nullptr, eps, nullptr, seed, offset, 0, inv_mask_sum, kl_weight, n, grad_q,
+                *p, q, sigma, y, mask, nullptr, eps, nullptr, seed, offset, 0, inv_mask_sum, inv_mask_sum_dev, kl_weight, n, grad_q,
                 grad_sigma, nll_map, kl_map, sums, work);
         }
     } else if (prior) {
@@ -1043,6 +1047,25 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
     }
 #undef QB_LAUNCH_ELBO
     return after_launch("k_elbo");
+}
+
+extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const float* sigma, const float* y,
+                                const float* mask, const float* prior, const float* eps, const float* eps_kl,
+                                uint64_t seed, uint64_t offset, int32_t kl_samples, float inv_mask_sum,
+                                float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
+                                float* kl_map, double* sums, void* stream) {
+    return elbo_fused_impl(p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, nullptr,
+                           kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, stream);
+}
+
+extern "C" int qbold_elbo_fused_dev(const QboldParams* p, const float* q, const float* sigma, const float* y,
+                                    const float* mask, const float* prior, const float* eps, const float* eps_kl,
+                                    uint64_t seed, uint64_t offset, int32_t kl_samples,
+                                    const float* inv_mask_sum_dev, float kl_weight, int64_t n, float* grad_q,
+                                    float* grad_sigma, float* nll_map, float* kl_map, double* sums, void* stream) {
+    if (!inv_mask_sum_dev) return fail(QBOLD_EINVAL, "qbold_elbo_fused_dev: inv_mask_sum_dev is NULL");
+    return elbo_fused_impl(p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, 0.f, inv_mask_sum_dev,
+                           kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, stream);
 }
 
 extern "C" int qbold_kl(const float* q, const float* prior, const float* mask, const float* eps_kl, uint64_t seed,

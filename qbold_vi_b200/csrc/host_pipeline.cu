@@ -9,8 +9,9 @@
 
 namespace qb {
 
-constexpr int kSlots = 4;
-constexpr int64_t kChunk = 1 << 19;   // voxels per chunk: 4 MB in, 46 MB g+S, 4 MB grad (short pipeline fill/drain)
+constexpr int kSlots = 6;
+constexpr int64_t kChunk = 1 << 17;   // voxels per chunk: 1 MB in, 11.5 MB g+S, 1 MB grad: the pipeline fill + drain (one chunk each of H2D,
+                                      // kernel, D2H) is 2 % of a 16 M-voxel call; with 512 k-voxel chunks it was 8 %
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -98,4 +99,65 @@ extern "C" int qbold_forward_backward_host(const QboldParams* p, const float* h_
         if (!rc) rc = rc2;
     }
     return rc;
+}
+
+// What the box's host <-> device link sustains with the SAME copy pattern as qbold_forward_backward_host (pinned
+// buffers, kChunk-voxel pieces cycling over the slot streams, both directions at once), without any kernel: the
+// ceiling the end-to-end figure is judged against.  h_src / h_dst: host buffers of `bytes` each (pinned for a
+// meaningful number); gbps[0] = H2D, gbps[1] = D2H, each direction's bytes / wall time of the concurrent run.
+extern "C" int qbold_host_copy_ceiling(const void* h_src, void* h_dst, int64_t bytes, int32_t reps, double* gbps) {
+    if (!h_src || !h_dst || !gbps || bytes <= 0 || reps < 1)
+        return fail(QBOLD_EINVAL, "qbold_host_copy_ceiling: bad argument");
+    std::lock_guard<std::mutex> lock(g_pipe_mu);
+    int dev = 0;
+    int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    const int64_t piece = (int64_t)sizeof(float) * 13 * kChunk;          // one chunk's bytes per direction (8 + 44 B/voxel)
+    void* d_in[kSlots] = {};
+    void* d_out[kSlots] = {};
+    cudaStream_t st[kSlots] = {};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    for (int i = 0; i < kSlots && !rc; ++i) {
+        rc = cuda_check(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!rc) rc = cuda_check(cudaMalloc(&d_in[i], piece), "cudaMalloc");
+        if (!rc) rc = cuda_check(cudaMalloc(&d_out[i], piece), "cudaMalloc");
+        if (!rc) rc = cuda_check(cudaMemsetAsync(d_out[i], 0, piece, st[i]), "cudaMemset");
+    }
+    if (!rc) rc = cuda_check(cudaEventCreate(&e0), "cudaEventCreate");
+    if (!rc) rc = cuda_check(cudaEventCreate(&e1), "cudaEventCreate");
+    float best_ms = 0.f;
+    for (int r = 0; r <= reps && !rc; ++r) {                              // first pass is the warm-up
+        rc = cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+        if (!rc) rc = cuda_check(cudaEventRecord(e0, st[0]), "cudaEventRecord");
+        for (int i = 1; i < kSlots && !rc; ++i) rc = cuda_check(cudaStreamWaitEvent(st[i], e0, 0), "cudaStreamWaitEvent");
+        int64_t c = 0;
+        for (int64_t off = 0; off < bytes && !rc; off += piece, ++c) {
+            const int64_t m = bytes - off < piece ? bytes - off : piece;
+            const int i = (int)(c % kSlots);
+            rc = cuda_check(cudaMemcpyAsync(d_in[i], (const char*)h_src + off, m, cudaMemcpyHostToDevice, st[i]), "H2D");
+            if (!rc) rc = cuda_check(cudaMemcpyAsync((char*)h_dst + off, d_out[i], m, cudaMemcpyDeviceToHost, st[i]), "D2H");
+        }
+        for (int i = 1; i < kSlots && !rc; ++i) {
+            cudaEvent_t done;
+            rc = cuda_check(cudaEventCreateWithFlags(&done, cudaEventDisableTiming), "cudaEventCreate");
+            if (!rc) rc = cuda_check(cudaEventRecord(done, st[i]), "cudaEventRecord");
+            if (!rc) rc = cuda_check(cudaStreamWaitEvent(st[0], done, 0), "cudaStreamWaitEvent");
+            cudaEventDestroy(done);
+        }
+        if (!rc) rc = cuda_check(cudaEventRecord(e1, st[0]), "cudaEventRecord");
+        if (!rc) rc = cuda_check(cudaEventSynchronize(e1), "cudaEventSynchronize");
+        float ms = 0.f;
+        if (!rc) rc = cuda_check(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+        if (r > 0 && (best_ms == 0.f || ms < best_ms)) best_ms = ms;
+    }
+    for (int i = 0; i < kSlots; ++i) {
+        if (st[i]) cudaStreamDestroy(st[i]);
+        cudaFree(d_in[i]);
+        cudaFree(d_out[i]);
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (rc) return rc;
+    gbps[0] = gbps[1] = (double)bytes / (best_ms * 1e-3) / 1e9;
+    return QBOLD_OK;
 }

@@ -50,8 +50,9 @@ __device__ __forceinline__ Pq rescaled(const float* __restrict__ q, int64_t v, i
 // edges that touch it (sign(0) = 0 like tf.abs; an edge counts only when both ends are inside the mask).
 __global__ void __launch_bounds__(kThreads) k_smoothness(const float* __restrict__ q, int n_ch,
                                                          const float* __restrict__ mask, int64_t n, int X, int Y,
-                                                         int Z, float scale, double* __restrict__ tv_sum,
-                                                         float* __restrict__ grad_q) {
+                                                         int Z, float scale, const float* __restrict__ scale_dev,
+                                                         double* __restrict__ tv_sum, float* __restrict__ grad_q) {
+    if (scale_dev != nullptr) scale = __ldg(scale_dev);       // weight / global sum(mask), left on the device
     const int64_t sy = Z, sx = (int64_t)Y * Z;
     double acc = 0.0;
     for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += (int64_t)gridDim.x * kThreads) {
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(kThreads) k_diag_kl(const float* __restrict__ 
 
 using namespace qb;
 
-extern "C" int qbold_smoothness(const float* q, int32_t n_ch, const float* mask, int64_t n_vol, int32_t nx,
-                                int32_t ny, int32_t nz, float scale, double* tv_sum, float* grad_q, void* stream) {
+static int smoothness_impl(const float* q, int32_t n_ch, const float* mask, int64_t n_vol, int32_t nx, int32_t ny,
+                           int32_t nz, float scale, const float* scale_dev, double* tv_sum, float* grad_q,
+                           void* stream) {
     if ((n_ch != 4 && n_ch != 5) || n_vol < 0 || nx <= 0 || ny <= 0 || nz <= 0)
         return fail(QBOLD_EINVAL, "qbold_smoothness: bad shape (n_ch=%d, volumes=%lld, %d x %d x %d)", n_ch,
                     (long long)n_vol, nx, ny, nz);
@@ -302,8 +304,20 @@ extern "C" int qbold_smoothness(const float* q, int32_t n_ch, const float* mask,
     if (n == 0) return QBOLD_OK;
     if (!q || !mask || (!tv_sum && !grad_q)) return fail(QBOLD_EINVAL, "qbold_smoothness: null pointer");
     k_smoothness<<<(unsigned)stream_grid(n), kThreads, 0, (cudaStream_t)stream>>>(q, n_ch, mask, n, nx, ny, nz, scale,
-                                                                                  tv_sum, grad_q);
+                                                                                  scale_dev, tv_sum, grad_q);
     return after_launch("k_smoothness");
+}
+
+extern "C" int qbold_smoothness(const float* q, int32_t n_ch, const float* mask, int64_t n_vol, int32_t nx,
+                                int32_t ny, int32_t nz, float scale, double* tv_sum, float* grad_q, void* stream) {
+    return smoothness_impl(q, n_ch, mask, n_vol, nx, ny, nz, scale, nullptr, tv_sum, grad_q, stream);
+}
+
+extern "C" int qbold_smoothness_dev(const float* q, int32_t n_ch, const float* mask, int64_t n_vol, int32_t nx,
+                                    int32_t ny, int32_t nz, const float* scale_dev, double* tv_sum, float* grad_q,
+                                    void* stream) {
+    if (!scale_dev) return fail(QBOLD_EINVAL, "qbold_smoothness_dev: scale_dev is NULL");
+    return smoothness_impl(q, n_ch, mask, n_vol, nx, ny, nz, 0.f, scale_dev, tv_sum, grad_q, stream);
 }
 
 extern "C" int qbold_synth_nll(const float* labels, int32_t label_stride, const float* pred, int32_t use_mvg,

@@ -54,14 +54,51 @@ def all_reduce_sum_(t):
 
 def global_mask_sum(mask):
     """sum(mask) over all ranks, as a Python float (one tiny all-reduce; the mask is an input, so this can
-    be issued before the step)."""
-    s = mask.sum(dtype=torch.float64).reshape(1)
-    return float(all_reduce_sum_(s).item())
+    be issued before the step).  Synchronises with the host: the training step uses global_mask_sum_device."""
+    return float(global_mask_sum_device(mask).item())
+
+
+def global_mask_sum_device(mask):
+    """sum(mask) over all ranks as a 1-element float64 DEVICE tensor: the all-reduce is enqueued on the stream and
+    the value is consumed by the kernels through a device pointer (qbold_elbo_fused_dev / qbold_smoothness_dev),
+    so the step never waits for it on the host."""
+    return all_reduce_sum_(mask.sum(dtype=torch.float64).reshape(1))
+
+
+class LazyStats(dict):
+    """Per-step statistics that stay on the device until somebody reads them: ``stats['loss']`` converts (and thereby
+    synchronises) on access, so a training loop that logs every k-th step has no host sync on the others."""
+
+    def __init__(self, names, values, **host_items):
+        super().__init__(host_items)
+        self._names, self._values, self._host = list(names), values, None
+
+    def _fetch(self):
+        if self._host is None:
+            self._host = self._values.tolist()
+        return self._host
+
+    def __getitem__(self, key):
+        if key in self._names:
+            return self._fetch()[self._names.index(key)]
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        return self[key] if (key in self._names or key in self.keys()) else default
+
+    def __contains__(self, key):
+        return key in self._names or super().__contains__(key)
+
+    def as_dict(self):
+        d = dict(self)
+        d.update(zip(self._names, self._fetch()))
+        return d
 
 
 def _adam(params, **kw):
     """Adam with the single-kernel (fused) update on CUDA parameters; the multi-tensor default elsewhere (CPU tests)."""
     params = list(params)
+    kw.setdefault('eps', 1e-7)                       # tf.keras / tfa Adam(W) epsilon (train.py:309-311), not torch's 1e-8
     if params and all(p.is_cuda for p in params):
         try:
             return torch.optim.Adam(params, fused=True, **kw)
@@ -81,6 +118,13 @@ class FlatGradBucket:
         off = 0
         for p in self.params:
             # same (dense, possibly permuted) strides as the parameter, e.g. channels_last_3d conv weights
+            p.grad = self.flat[off:off + p.numel()].as_strided(p.size(), p.stride())
+            off += p.numel()
+
+    def realias(self):
+        """Point every parameter's .grad back into the flat buffer (after load_state_dict / anything that replaced it)."""
+        off = 0
+        for p in self.params:
             p.grad = self.flat[off:off + p.numel()].as_strided(p.size(), p.stride())
             off += p.numel()
 
@@ -121,6 +165,7 @@ class DataParallelTrainer:
         self.opt = _adam(self.bucket.params, lr=ft_lr, betas=(0.9, 0.9))                 # beta_2 = 0.9 (train.py:310)
         self.decay = adamw_decay > 0.0
         self.step_no = 0
+        self._comm_stream = None
         self.loss_fn = loss_fn or self._fused_loss
         self.tv_fn = tv_fn or self._tv
 
@@ -134,15 +179,19 @@ class DataParallelTrainer:
                                        kl_weight=self.kl_weight, mask_sum=mask_sum, offset=rank * mask.numel())
 
     def step(self, data, mask, prior):
-        """data [B,X,Y,Z,n_tau] (pre-masked), mask [B,X,Y,Z,1], prior [B,X,Y,Z,5]: this rank's volumes."""
-        msum = global_mask_sum(mask)
+        """data [B,X,Y,Z,n_tau] (pre-masked), mask [B,X,Y,Z,1], prior [B,X,Y,Z,5]: this rank's volumes.
+
+        No host synchronisation: the global mask count stays on the device (its all-reduce is enqueued ahead of the
+        encoder), the gradient all-reduce runs on a side stream as soon as backward has produced it, and the returned
+        statistics are read lazily (LazyStats)."""
+        msum = global_mask_sum_device(mask)
         self.bucket.zero_()
         _, q, sigma = self.encoder(data)
         loss, info = self.loss_fn(q, sigma, data, mask, prior, msum)
         tv = self.tv_fn(q, prior, mask, msum)
         total = loss + self.smoothness_weight * tv
         total.backward()
-        self.bucket.all_reduce_()
+        self._reduce_gradients()
         lr = self.lr(self.step_no)
         for g in self.opt.param_groups:
             g['lr'] = lr
@@ -151,15 +200,55 @@ class DataParallelTrainer:
                 self.bucket_params_mul_(1.0 - self.wd(self.step_no))
         self.opt.step()
         self.step_no += 1
-        zero = total.detach().double() * 0
-        stats = torch.stack([total.detach().double(), info['nll'].detach().double() if 'nll' in info else zero,
-                             info['kl'].detach().double() if 'kl' in info else zero, tv.detach().double()])
+        sc = lambda t: t.detach().double().reshape(())                      # noqa: E731
+        zero = sc(total) * 0
+        stats = torch.stack([sc(total), sc(info['nll']) if 'nll' in info else zero,
+                             sc(info['kl']) if 'kl' in info else zero, sc(tv), sc(msum) / max(world_size(), 1)])
         all_reduce_sum_(stats)
-        return {'loss': float(stats[0]), 'nll': float(stats[1]), 'kl': float(stats[2]), 'smoothness': float(stats[3]),
-                'mask_sum': msum, 'lr': lr}
+        return LazyStats(['loss', 'nll', 'kl', 'smoothness', 'mask_sum'], stats, lr=lr)
+
+    def _reduce_gradients(self):
+        """SUM all-reduce of the flat gradient bucket on a side stream (NCCL over NVLink): it is ordered after the
+        backward kernels by an event and the optimiser waits for it by an event, so the host thread keeps enqueuing
+        (LR schedule, weight decay) while the 585 KB reduction is in flight."""
+        if world_size() <= 1:
+            return
+        if not self.bucket.flat.is_cuda:
+            self.bucket.all_reduce_()
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.bucket.flat.device)
+        cur = torch.cuda.current_stream(self.bucket.flat.device)
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            self.bucket.all_reduce_()
+        cur.wait_stream(self._comm_stream)
 
     def bucket_params_mul_(self, factor):
         torch._foreach_mul_(self.bucket.params, factor)
+
+    # ---- checkpoint / resume (the reference saves pt_model.h5 / final_model.h5 and skips finished phases,
+    # train.py:193-202,260-270; here: one torch file with everything the step depends on)
+    def state_dict(self):
+        return {'encoder': self.encoder.state_dict(), 'optimizer': self.opt.state_dict(), 'step_no': self.step_no,
+                'trainer_calls': self.trainer._calls, 'trainer_seed': self.trainer._seed,
+                'layer_calls': getattr(self.layer, '_calls', 0)}
+
+    def load_state_dict(self, state):
+        self.encoder.load_state_dict(state['encoder'])
+        self.opt.load_state_dict(state['optimizer'])
+        self.step_no = int(state['step_no'])                      # position on the LR / weight-decay schedule
+        self.trainer._calls = int(state.get('trainer_calls', 0))  # Philox call counter: resumed draws continue the stream
+        self.trainer._seed = int(state.get('trainer_seed', self.trainer._seed))
+        if hasattr(self.layer, '_calls'):
+            self.layer._calls = int(state.get('layer_calls', 0))
+        self.bucket.realias()
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path, map_location=None):
+        self.load_state_dict(torch.load(path, map_location=map_location, weights_only=False))
 
 
 class StreamingPretrainer:
@@ -197,6 +286,17 @@ class StreamingPretrainer:
         self.opt = _adam(self.bucket.params, lr=lr)
         self.weight_decay = weight_decay
         self._C = C
+
+    def state_dict(self):
+        return {'encoder': self.encoder.state_dict(), 'optimizer': self.opt.state_dict(), 'cursor': self.cursor,
+                'trainer_calls': self.trainer._calls}
+
+    def load_state_dict(self, state):
+        self.encoder.load_state_dict(state['encoder'])
+        self.opt.load_state_dict(state['optimizer'])
+        self.cursor = int(state['cursor'])                        # position in the shuffled OEF x DBV grid
+        self.trainer._calls = int(state.get('trainer_calls', 0))
+        self.bucket.realias()
 
     def next_batch(self):
         """(x [batch, n_tau] noisy signals, y [batch, 3] labels) for this rank's next slice of the shuffled grid."""

@@ -145,6 +145,12 @@ class _TvFn(torch.autograd.Function):
         grad = torch.empty_like(q)
         tv = torch.zeros(1, dtype=torch.float64, device=q.device)
         with torch.cuda.device(q.device):
+            if torch.is_tensor(mask_sum):                       # global sum(mask) left on the device: no host sync
+                inv = (1.0 / mask_sum.reshape(1).to(q.device, torch.float64)).float().contiguous()
+                check(_lib.lib().qbold_smoothness_dev(dptr(q), c, dptr(mask), b, x, y, z, dptr(inv),
+                                                      dptr(tv, torch.float64), dptr(grad), stream_ptr(q.device)))
+                ctx.save_for_backward(grad)
+                return (tv[0] * inv[0].double()).float()
             check(_lib.lib().qbold_smoothness(dptr(q), c, dptr(mask), b, x, y, z, 1.0 / mask_sum,
                                               dptr(tv, torch.float64), dptr(grad), stream_ptr(q.device)))
         ctx.save_for_backward(grad)
@@ -264,15 +270,18 @@ class _FusedElboFn(torch.autograd.Function):
         nll_map = torch.empty(n, dtype=torch.float32, device=dev) if want_maps else None
         kl_map = torch.empty(n, dtype=torch.float32, device=dev) if want_maps else None
         with torch.cuda.device(dev):
-            check(_lib.lib().qbold_elbo_fused(
+            fn = _lib.lib().qbold_elbo_fused_dev if torch.is_tensor(inv_mask_sum) else _lib.lib().qbold_elbo_fused
+            check(fn(
                 C.byref(trainer._params_for(layer)), dptr(q), dptr(sigma), dptr(y), dptr(mask),
                 dptr(prior, allow_none=True), dptr(eps, allow_none=True), dptr(eps_kl, allow_none=True), seed,
-                int(offset), kl_samples, inv_mask_sum, kl_weight, n, dptr(grad_q), dptr(grad_sigma),
+                int(offset), kl_samples, dptr(inv_mask_sum) if torch.is_tensor(inv_mask_sum) else inv_mask_sum,
+                kl_weight, n, dptr(grad_q), dptr(grad_sigma),
                 dptr(nll_map, allow_none=True), dptr(kl_map, allow_none=True), dptr(sums, torch.float64),
                 stream_ptr(dev)))
         ctx.save_for_backward(grad_q, grad_sigma)
         s = sums.float()
-        nll, kl = s[0] * inv_mask_sum, s[1] * inv_mask_sum
+        ims = inv_mask_sum[0] if torch.is_tensor(inv_mask_sum) else inv_mask_sum
+        nll, kl = s[0] * ims, s[1] * ims
         ctx.mark_non_differentiable(sums)
         if want_maps:
             ctx.mark_non_differentiable(nll_map, kl_map)
@@ -556,13 +565,17 @@ class EncoderTrainer:
         e = None if eps is None else eps.reshape(n, 2).float().contiguous()
         ek = None if eps_kl is None else eps_kl.reshape(n, kl_samples, 2).float().contiguous()
         if mask_sum is None:
-            mask_sum = float(m.sum().item())
-        inv = 1.0 / float(mask_sum)
+            mask_sum = m.sum(dtype=torch.float64)                # stays on the device: no host synchronisation
+        if torch.is_tensor(mask_sum):
+            inv = (1.0 / mask_sum.reshape(1).to(q.device, torch.float64)).float().contiguous()
+        else:
+            inv = 1.0 / float(mask_sum)
         out = _FusedElboFn.apply(q, sg, self, signal_layer, y, m, pr, e, ek,
                                  _next_seed(self) if seed is None else seed, kl_samples if pr is not None else 0,
                                  inv, float(kl_weight), return_maps, int(offset))
         loss, sums = out[0], out[1]
-        info = {'nll': (sums[0] * inv).float(), 'kl': (sums[1] * inv).float(), 'mask_sum': sums[2],
+        ims = inv[0] if torch.is_tensor(inv) else inv
+        info = {'nll': (sums[0] * ims).float(), 'kl': (sums[1] * ims).float(), 'mask_sum': sums[2],
                 'non_finite': sums[3]}
         if return_maps:
             info['nll_map'], info['kl_map'] = out[2], out[3]
@@ -660,8 +673,8 @@ class EncoderTrainer:
         if pred_params.dim() != 5 or pred_params.shape[-1] != c:
             raise ValueError('smoothness_loss: pred_params must be [B,X,Y,Z,%d]' % c)
         if mask_sum is None:
-            mask_sum = float(mask.sum().item())
-        return _TvFn.apply(pred_params, mask, float(mask_sum))
+            mask_sum = mask.sum(dtype=torch.float64)             # stays on the device: no host synchronisation
+        return _TvFn.apply(pred_params, mask, mask_sum if torch.is_tensor(mask_sum) else float(mask_sum))
 
     def oef_dbv_metrics(self, y_true, y_pred, oef_dbv_r2p=0, eps=None):
         """MSE of the 20-sample posterior means against the labels (model.py:345-364)."""

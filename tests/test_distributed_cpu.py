@@ -65,7 +65,7 @@ def _worker(rank, world, port, out):
     data, mask, prior = _batch()
     lo, hi = D.shard_range(data.shape[0], rank, world)
     stats = dp.step(data[lo:hi], mask[lo:hi], prior[lo:hi])
-    out.put((rank, dp.bucket.flat.clone().numpy(), stats,
+    out.put((rank, dp.bucket.flat.clone().numpy(), stats.as_dict(),
              torch.cat([p.detach().reshape(-1) for p in enc.parameters()]).numpy()))
     dist.barrier()
     dist.destroy_process_group()
