@@ -100,6 +100,8 @@ class SignalGenerationLayer:
         return self.call(input, *args, **kwargs)
 
     def call(self, input, *args, **kwargs):
+        if not torch.is_tensor(input) and (hasattr(input, '__dlpack__') or type(input).__name__ == 'PyCapsule'):
+            input = torch.from_dlpack(input)                # zero-copy hand-off (tf.experimental.dlpack, CuPy, JAX, ...)
         width = 3 if self._variable_hct else 2
         if self._variable_hct:
             assert input.shape[-1] == 3, 'Input should have 3 elements in last dimension, OEF, DBV and hct'

@@ -1394,3 +1394,35 @@ def test_c_abi_from_plain_c(qb, dev, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'max relative deviation' in out.stdout
+
+
+def test_dlpack_hand_off_without_torch_tensors(qb, dev, cfg_noise_off):
+    """north_star: "ctypes, with DLPack for tensor hand-off".  A foreign producer (here: a minimal object exposing only
+    __dlpack__ / __dlpack_device__, and a raw capsule) reaches qbold_forward / qbold_forward_backward as raw pointers."""
+    from torch.utils import dlpack as tdl
+
+    class Foreign:                                                   # what a tf / cupy / jax array looks like to us
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None):
+            return self._t.__dlpack__(stream=stream)
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    x = _t(_rand_voxels(3001, 23), dev)
+    want_s, want_g = layer.forward_backward(x, None)
+    out = torch.empty((3001, 11), device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    qb.forward_dlpack(layer, Foreign(x), tdl.to_dlpack(out), stream=st)
+    assert torch.equal(out, want_s)
+    sig, grad = torch.zeros((3001, 11), device=dev), torch.zeros((3001, 2), device=dev)
+    qb.forward_backward_dlpack(layer, tdl.to_dlpack(x), None, Foreign(sig), Foreign(grad), stream=st)
+    assert torch.equal(sig, want_s) and torch.equal(grad, want_g)
+    assert torch.equal(layer(Foreign(x)), want_s)                    # the layer call itself takes producers too
+    with pytest.raises(qb.dlpack.DLPackError):
+        qb.forward_dlpack(layer, Foreign(x), Foreign(torch.empty((7, 11), device=dev)))
+    with pytest.raises(qb.dlpack.DLPackError, match='CUDA device memory only'):
+        qb.forward_dlpack(layer, x.cpu(), Foreign(out))

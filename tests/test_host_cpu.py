@@ -276,3 +276,29 @@ def test_bench_fails_loudly_without_a_gpu():
                          timeout=300, cwd=root)
     assert out.returncode != 0 and 'no CPU fallback' in (out.stderr + out.stdout)
     assert '"value"' not in out.stdout
+
+
+def test_dlpack_unpacking_without_a_gpu(qb):
+    """The ctypes DLPack consumer: capsule and __dlpack__ producers, shape / dtype / contiguity checks, single use,
+    and the loud refusal of host memory (there is no CPU path)."""
+    import torch
+    from torch.utils import dlpack as tdl
+    t = torch.arange(24, dtype=torch.float32).reshape(4, 3, 2)
+    with qb.DLPackView(tdl.to_dlpack(t), allow_host=True) as v:
+        assert v.shape == (4, 3, 2) and v.dtype == 'f4' and v.numel == 24 and v.ptr == t.data_ptr()
+    with qb.DLPackView(t[1:], allow_host=True) as v:                         # __dlpack__ protocol, offset view
+        assert v.shape == (3, 3, 2) and v.ptr == t[1:].data_ptr()
+    cap = tdl.to_dlpack(t)
+    qb.DLPackView(cap, allow_host=True).release()
+    with pytest.raises(qb.dlpack.DLPackError, match='already consumed'):
+        qb.DLPackView(cap, allow_host=True)
+    with pytest.raises(qb.dlpack.DLPackError, match='C-contiguous'):
+        qb.DLPackView(t.transpose(0, 1), allow_host=True)
+    with pytest.raises(qb.dlpack.DLPackError, match='unsupported DLPack dtype'):
+        qb.DLPackView(t.double(), allow_host=True)
+    with pytest.raises(qb.dlpack.DLPackError, match='expected a f4'):
+        qb.DLPackView(t.int(), allow_host=True)
+    with pytest.raises(qb.dlpack.DLPackError, match='CUDA device memory only'):
+        qb.DLPackView(t)
+    with pytest.raises(qb.dlpack.DLPackError):
+        qb.DLPackView(object())

@@ -25,4 +25,4 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
     for _ in range(3): dp.step(data, mask, prior)
     torch.cuda.synchronize()
-print(p.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+print(p.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
