@@ -27,6 +27,8 @@ def main():
     ap.add_argument('--ft-steps', type=int, default=60)
     ap.add_argument('--size', type=int, default=32)
     ap.add_argument('--volumes-per-gpu', type=int, default=2)
+    ap.add_argument('--save-directory', default=None,
+                    help='checkpoints: pt_model.pt / final_model.pt; finished phases are skipped (train.py:193-202,260-270)')
     a = ap.parse_args()
     rank, world, dev = D.init_distributed()
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
@@ -48,10 +50,19 @@ def main():
     pt = D.StreamingPretrainer(model, trainer, params, args.full_model, args.use_blood, uniform_prop=args.uniform_prop,
                                lr=args.pt_lr, weight_decay=args.pt_adamw_decay, batch_blocks=128, seed=1 + rank, device=dev)
     log = []
-    for i in range(a.pt_steps):
-        st = pt.step()
-        if i % 25 == 0 or i == a.pt_steps - 1:
-            log.append(('pt', i, st))
+    ckpt = (lambda name: os.path.join(a.save_directory, name)) if a.save_directory else None
+    if ckpt:
+        os.makedirs(a.save_directory, exist_ok=True)
+    if ckpt and os.path.exists(ckpt('pt_model.pt')):            # the reference loads pt_model.h5 instead of pre-training again
+        pt.load_state_dict(torch.load(ckpt('pt_model.pt'), map_location=dev, weights_only=False))
+        log.append(('pt', 'resumed', {'cursor': pt.cursor}))
+    else:
+        for i in range(a.pt_steps):
+            st = pt.step()
+            if i % 25 == 0 or i == a.pt_steps - 1:
+                log.append(('pt', i, st))
+        if ckpt and rank == 0:
+            torch.save(pt.state_dict(), ckpt('pt_model.pt'))
 
     # ---- synthetic "scans": smooth OEF/DBV maps inside a sphere, forward model + noise
     S, B = a.size, a.volumes_per_gpu
@@ -72,10 +83,15 @@ def main():
         prior = model(data)[0][..., :5].contiguous()
     ft = D.DataParallelTrainer(model, trainer, sig_gen_layer, ft_lr=args.ft_lr, adamw_decay=args.adamw_decay,
                                smoothness_weight=args.smoothness_weight, kl_weight=1.0)
-    for i in range(a.ft_steps):
+    if ckpt and os.path.exists(ckpt('final_model.pt')):         # resume: weights, Adam moments, schedule position, RNG counters
+        ft.load(ckpt('final_model.pt'), map_location=dev)
+        log.append(('ft', 'resumed', {'step_no': ft.step_no}))
+    for i in range(ft.step_no, a.ft_steps):
         st = ft.step(data, mask, prior)
         if i % 10 == 0 or i == a.ft_steps - 1:
-            log.append(('ft', i, st))
+            log.append(('ft', i, st.as_dict()))                 # reading the lazy statistics is the only host sync
+    if ckpt and rank == 0:
+        ft.save(ckpt('final_model.pt'))
 
     # ---- inference: 64 posterior samples per voxel
     with torch.no_grad():

@@ -337,6 +337,25 @@ int qbold_gate_mix_forward(const float* skip, const float* r, const float* z, fl
 int qbold_gate_mix_backward(const float* go, const float* skip, const float* r, const float* z, float offset, int64_t n,
                             int32_t channels, int32_t z_channels, float* d_skip, float* d_r, float* d_z, void* stream);
 
+/* Fused elementwise steps of the encoder block's training path (create_block, model.py:142-174; see
+ * csrc/encoder_block.cu).  channels: a multiple of 4 up to 64, channel-wise gating; operands 16-byte aligned.
+ *   forward : out = skip (1-g) + (r0 + r_bias) g, g = sigmoid(z + offset); r_bias [channels] may be NULL (r0 is
+ *             the second 3x3x1 convolution without its bias); out_relu (may be NULL) = relu(out), the next block's
+ *             convolution input (model.py:150).
+ *   backward: d_r, d_z as qbold_gate_mix_backward; d_skip is multiplied by [skip > 0] when skip_is_relu != 0 (the
+ *             skip branch ends in a ReLU). */
+int qbold_block_mix_forward(const float* skip, const float* r0, const float* r_bias, const float* z, float offset,
+                            int64_t n, int32_t channels, float* out, float* out_relu, void* stream);
+int qbold_block_mix_backward(const float* go, const float* skip, const float* r0, const float* r_bias, const float* z,
+                             float offset, int64_t n, int32_t channels, int32_t skip_is_relu, float* d_skip, float* d_r,
+                             float* d_z, void* stream);
+/* ReLU backward fused with the bias gradient: out[n,channels] = g * [y > 0] (+ addend, may be NULL) (y NULL: no mask,
+ * out unused) and colsum[channels] (+)= column sums of that (colsum may be NULL; deterministic two-stage reduction
+ * through `workspace`, qbold_colsum_workspace_floats() floats of device scratch). */
+int64_t qbold_colsum_workspace_floats(void);
+int qbold_relu_bwd_colsum(const float* g, const float* y, const float* addend, int64_t n, int32_t channels, float* out,
+                          float* colsum, int32_t accumulate, float* workspace, void* stream);
+
 /* FP32 FMA micro-benchmark (roofline denominator measured in the same run): launches
  * `iters` dependent-chain FFMA sweeps, returns achieved TFLOP/s through *tflops. */
 int qbold_fma_peak(int32_t iters, double* tflops);

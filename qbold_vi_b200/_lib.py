@@ -109,6 +109,11 @@ _SIGNATURES = {
     'qbold_gate_mix_forward': (C.c_int, [_f, _f, _f, C.c_float, C.c_int64, C.c_int32, C.c_int32, _f, C.c_void_p]),
     'qbold_gate_mix_backward': (C.c_int, [_f, _f, _f, _f, C.c_float, C.c_int64, C.c_int32, C.c_int32, _f, _f, _f,
                                           C.c_void_p]),
+    'qbold_block_mix_forward': (C.c_int, [_f, _f, _f, _f, C.c_float, C.c_int64, C.c_int32, _f, _f, C.c_void_p]),
+    'qbold_block_mix_backward': (C.c_int, [_f, _f, _f, _f, _f, C.c_float, C.c_int64, C.c_int32, C.c_int32, _f, _f, _f,
+                                           C.c_void_p]),
+    'qbold_colsum_workspace_floats': (C.c_int64, []),
+    'qbold_relu_bwd_colsum': (C.c_int, [_f, _f, _f, C.c_int64, C.c_int32, _f, _f, C.c_int32, _f, C.c_void_p]),
     'qbold_fma_peak': (C.c_int, [C.c_int32, _P(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

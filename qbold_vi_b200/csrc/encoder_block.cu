@@ -1,0 +1,223 @@
+// Streaming kernels of the fused encoder block (reference create_block, model.py:142-174) used by the training
+// path of qbold_vi_b200/encoder.py (_BlockFn).  The block's convolutions and 60x60 GEMMs run in the libraries; every
+// elementwise step between them is fused here so that an activation tensor ([voxels, 60] floats, 126 MB for
+// 2 x 64^3 volumes) is read and written as few times as the data flow allows:
+//
+//   k_block_mix_fwd    out = skip (1 - g) + (r0 + b_r) g,  g = sigmoid(z + offset)     (model.py:160-172)
+//                      r0 is the second 3x3x1 convolution WITHOUT its bias (cuDNN adds a bias in a separate pass);
+//                      optionally also writes relu(out), the next block's convolution input (model.py:150).
+//   k_block_mix_bwd    d_r, d_z and d_skip * [skip > 0] (the skip branch ends in a ReLU: its derivative is applied
+//                      here instead of in a pass of its own).
+//   k_relu_bwd_colsum  g * [y > 0] and, in the same pass, its column sums (= the bias gradient of the layer that
+//                      produced y); deterministic two-stage reduction.
+//   k_colsum           column sums alone (bias gradient of a convolution without ReLU).
+// All HBM-bound: 16-byte accesses, grid = a multiple of the SM count.
+#include "launch.h"
+
+namespace qb {
+
+namespace {
+
+constexpr int kColTile = 256;                  // threads per CTA of the column-sum kernels
+constexpr int kMaxC4 = 16;                     // up to 64 channels (16 float4 per row)
+
+__device__ __forceinline__ float gate(float z, float offset) { return 1.0f / (1.0f + expf(-(z + offset))); }
+
+__device__ __forceinline__ float4 ld4(const float4* p) { return __ldg(p); }
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads) k_block_mix_fwd(const float4* __restrict__ skip, const float4* __restrict__ r0,
+                                                            const float4* __restrict__ r_bias,
+                                                            const float4* __restrict__ z, float offset, int64_t total4,
+                                                            int c4, float4* __restrict__ out,
+                                                            float4* __restrict__ out_relu) {
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total4; e += (int64_t)gridDim.x * kThreads) {
+        const float4 zz = ld4(z + e), s = ld4(skip + e);
+        float4 rr = ld4(r0 + e);
+        if (r_bias != nullptr) {
+            const float4 b = ld4(r_bias + (int)(e % c4));
+            rr = make_float4(rr.x + b.x, rr.y + b.y, rr.z + b.z, rr.w + b.w);
+        }
+        const float g0 = gate(zz.x, offset), g1 = gate(zz.y, offset), g2 = gate(zz.z, offset), g3 = gate(zz.w, offset);
+        const float4 o = make_float4(s.x * (1.0f - g0) + rr.x * g0, s.y * (1.0f - g1) + rr.y * g1,
+                                     s.z * (1.0f - g2) + rr.z * g2, s.w * (1.0f - g3) + rr.w * g3);
+        out[e] = o;
+        if (out_relu != nullptr)
+            out_relu[e] = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_block_mix_bwd(const float4* __restrict__ go, const float4* __restrict__ skip,
+                                                            const float4* __restrict__ r0,
+                                                            const float4* __restrict__ r_bias,
+                                                            const float4* __restrict__ z, float offset, int64_t total4,
+                                                            int c4, int skip_is_relu, float4* __restrict__ d_skip,
+                                                            float4* __restrict__ d_r, float4* __restrict__ d_z) {
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total4; e += (int64_t)gridDim.x * kThreads) {
+        const float4 zz = ld4(z + e), s = ld4(skip + e), o = ld4(go + e);
+        float4 rr = ld4(r0 + e);
+        if (r_bias != nullptr) {
+            const float4 b = ld4(r_bias + (int)(e % c4));
+            rr = make_float4(rr.x + b.x, rr.y + b.y, rr.z + b.z, rr.w + b.w);
+        }
+        const float g0 = gate(zz.x, offset), g1 = gate(zz.y, offset), g2 = gate(zz.z, offset), g3 = gate(zz.w, offset);
+        float4 ds = make_float4(o.x * (1.0f - g0), o.y * (1.0f - g1), o.z * (1.0f - g2), o.w * (1.0f - g3));
+        if (skip_is_relu)                                            // skip = relu(.): threshold_backward(ds, skip, 0)
+            ds = make_float4(s.x > 0.f ? ds.x : 0.f, s.y > 0.f ? ds.y : 0.f, s.z > 0.f ? ds.z : 0.f,
+                             s.w > 0.f ? ds.w : 0.f);
+        d_skip[e] = ds;
+        d_r[e] = make_float4(o.x * g0, o.y * g1, o.z * g2, o.w * g3);
+        d_z[e] = make_float4(o.x * (rr.x - s.x) * (g0 * (1.0f - g0)), o.y * (rr.y - s.y) * (g1 * (1.0f - g1)),
+                             o.z * (rr.z - s.z) * (g2 * (1.0f - g2)), o.w * (rr.w - s.w) * (g3 * (1.0f - g3)));
+    }
+}
+
+// Rows [row0, row1) of this CTA: thread (lane-in-row-group) owns one float4 column chunk of every (kColTile / c4)-th
+// row.  MASK: out = g * [y > 0] is written as well.  partial [gridDim.x, 4 c4] receives the CTA's column sums.
+template <bool MASK>
+__global__ void __launch_bounds__(kColTile) k_relu_bwd_colsum(const float4* __restrict__ g, const float4* __restrict__ y,
+                                                              const float4* __restrict__ addend, int64_t n, int c4,
+                                                              float4* __restrict__ out, float* __restrict__ partial) {
+    __shared__ float4 red[kColTile];
+    const int rows_per_pass = kColTile / c4;                     // threads beyond rows_per_pass * c4 idle
+    const int rr = threadIdx.x / c4, cc = threadIdx.x % c4;
+    const bool active = rr < rows_per_pass;
+    const int64_t rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        for (int64_t row = row0 + rr; row < row1; row += rows_per_pass) {
+            const int64_t e = row * c4 + cc;
+            float4 v = ld4(g + e);
+            if (MASK) {
+                const float4 m = ld4(y + e);
+                v = make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f,
+                                m.w > 0.f ? v.w : 0.f);
+                if (addend != nullptr) {
+                    const float4 a = ld4(addend + e);
+                    v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
+                }
+                if (out != nullptr) out[e] = v;
+            }
+            acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (partial != nullptr && threadIdx.x < c4) {                // fixed order: deterministic
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < rows_per_pass; ++r) {
+            const float4 v = red[r * c4 + threadIdx.x];
+            s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+        }
+        reinterpret_cast<float4*>(partial)[(int64_t)blockIdx.x * c4 + threadIdx.x] = s;
+    }
+}
+
+// Second stage: column j of the [n_parts, c] partial sums, summed in a FIXED order (16 strided slices per column, then
+// the 16 slice totals in order) so the result does not depend on scheduling.  One CTA of 16 x 64 threads.
+__global__ void __launch_bounds__(1024) k_colsum_finish(const float* __restrict__ partial, int n_parts, int c,
+                                                        float* __restrict__ out, int accumulate) {
+    __shared__ float red[16][64];
+    const int j = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    float s = 0.f;
+    if (j < c)
+        for (int p = slice; p < n_parts; p += 16) s += partial[(int64_t)p * c + j];
+    red[slice][j] = s;
+    __syncthreads();
+    if (slice == 0 && j < c) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t += red[k][j];
+        out[j] = accumulate ? out[j] + t : t;
+    }
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int64_t stream_grid4(int64_t total4) {
+    const int64_t want = (total4 + kThreads - 1) / kThreads, cap = (int64_t)sm_count() * 16;
+    return want < cap ? (want < 1 ? 1 : want) : cap;
+}
+
+extern "C" int qbold_block_mix_forward(const float* skip, const float* r0, const float* r_bias, const float* z,
+                                       float offset, int64_t n, int32_t channels, float* out, float* out_relu,
+                                       void* stream) {
+    if (n < 0 || channels < 4 || (channels & 3) || channels > 4 * kMaxC4)
+        return fail(QBOLD_EUNSUPPORTED, "qbold_block_mix_forward: channels must be a multiple of 4 in [4, 64]");
+    if (n == 0) return QBOLD_OK;
+    if (!skip || !r0 || !z || !out) return fail(QBOLD_EINVAL, "qbold_block_mix_forward: null pointer");
+    if (!aligned16(skip) || !aligned16(r0) || !aligned16(z) || !aligned16(out) || (r_bias && !aligned16(r_bias)) ||
+        (out_relu && !aligned16(out_relu)))
+        return fail(QBOLD_EINVAL, "qbold_block_mix_forward: operands must be 16-byte aligned");
+    const int64_t total4 = n * (channels / 4);
+    k_block_mix_fwd<<<(unsigned)stream_grid4(total4), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(skip), reinterpret_cast<const float4*>(r0),
+        reinterpret_cast<const float4*>(r_bias), reinterpret_cast<const float4*>(z), offset, total4, channels / 4,
+        reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_relu));
+    return after_launch("k_block_mix_fwd");
+}
+
+extern "C" int qbold_block_mix_backward(const float* go, const float* skip, const float* r0, const float* r_bias,
+                                        const float* z, float offset, int64_t n, int32_t channels,
+                                        int32_t skip_is_relu, float* d_skip, float* d_r, float* d_z, void* stream) {
+    if (n < 0 || channels < 4 || (channels & 3) || channels > 4 * kMaxC4)
+        return fail(QBOLD_EUNSUPPORTED, "qbold_block_mix_backward: channels must be a multiple of 4 in [4, 64]");
+    if (n == 0) return QBOLD_OK;
+    if (!go || !skip || !r0 || !z || !d_skip || !d_r || !d_z)
+        return fail(QBOLD_EINVAL, "qbold_block_mix_backward: null pointer");
+    const void* ptrs[] = {go, skip, r0, z, d_skip, d_r, d_z};
+    for (const void* p : ptrs)
+        if (!aligned16(p)) return fail(QBOLD_EINVAL, "qbold_block_mix_backward: operands must be 16-byte aligned");
+    if (r_bias && !aligned16(r_bias)) return fail(QBOLD_EINVAL, "qbold_block_mix_backward: r_bias must be 16-byte aligned");
+    const int64_t total4 = n * (channels / 4);
+    k_block_mix_bwd<<<(unsigned)stream_grid4(total4), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(go), reinterpret_cast<const float4*>(skip), reinterpret_cast<const float4*>(r0),
+        reinterpret_cast<const float4*>(r_bias), reinterpret_cast<const float4*>(z), offset, total4, channels / 4,
+        skip_is_relu, reinterpret_cast<float4*>(d_skip), reinterpret_cast<float4*>(d_r), reinterpret_cast<float4*>(d_z));
+    return after_launch("k_block_mix_bwd");
+}
+
+extern "C" int64_t qbold_colsum_workspace_floats(void) { return (int64_t)sm_count() * 8 * 4 * kMaxC4; }
+
+// out = g * [y > 0] (+ addend) (y NULL: no mask, out unused) and colsum[channels] (+)= its column sums (may be NULL).
+extern "C" int qbold_relu_bwd_colsum(const float* g, const float* y, const float* addend, int64_t n, int32_t channels,
+                                     float* out, float* colsum, int32_t accumulate, float* workspace, void* stream) {
+    if (n < 0 || channels < 4 || (channels & 3) || channels > 4 * kMaxC4)
+        return fail(QBOLD_EUNSUPPORTED, "qbold_relu_bwd_colsum: channels must be a multiple of 4 in [4, 64]");
+    if (!g || (y && !out && !colsum) || (!y && !colsum) || (colsum && !workspace))
+        return fail(QBOLD_EINVAL, "qbold_relu_bwd_colsum: null pointer");
+    if (addend && !y) return fail(QBOLD_EINVAL, "qbold_relu_bwd_colsum: addend needs the masked form (y != NULL)");
+    if (!aligned16(g) || (y && !aligned16(y)) || (out && !aligned16(out)) || (workspace && !aligned16(workspace)) ||
+        (addend && !aligned16(addend)))
+        return fail(QBOLD_EINVAL, "qbold_relu_bwd_colsum: operands must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int c4 = channels / 4;
+    int64_t grid = (int64_t)sm_count() * 8;
+    const int64_t rows_per_pass = kColTile / c4;
+    const int64_t want = (n + rows_per_pass * 4 - 1) / (rows_per_pass * 4);
+    if (want < grid) grid = want < 1 ? 1 : want;
+    if (n > 0) {
+        if (y)
+            k_relu_bwd_colsum<true><<<(unsigned)grid, kColTile, 0, st>>>(
+                reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(y),
+                reinterpret_cast<const float4*>(addend), n, c4, reinterpret_cast<float4*>(out),
+                colsum ? workspace : nullptr);
+        else
+            k_relu_bwd_colsum<false><<<(unsigned)grid, kColTile, 0, st>>>(reinterpret_cast<const float4*>(g), nullptr, nullptr,
+                                                                          n, c4, nullptr, workspace);
+        int rc = after_launch("k_relu_bwd_colsum");
+        if (rc) return rc;
+    }
+    if (colsum) {
+        k_colsum_finish<<<1, 1024, 0, st>>>(workspace, n > 0 ? (int)grid : 0, channels, colsum, accumulate);
+        return after_launch("k_colsum_finish");
+    }
+    return QBOLD_OK;
+}

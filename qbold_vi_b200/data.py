@@ -61,9 +61,17 @@ class FineTuneDataset:
         data = d[..., :-1] * mask                                               # train.py:56
         return data, mask, torch.cat([p, mask], -1), torch.cat([data, mask], -1)
 
+    def _subjects(self):
+        """Endless stream of subject indices: shuffled passes over ALL subjects (tf.data shuffle + repeat, train.py:64-70),
+        not independent draws -- every subject is visited once per pass."""
+        while True:
+            for s in torch.randperm(self.real.shape[0], generator=self.gen).tolist():
+                yield s
+
     def __iter__(self):
+        stream = self._subjects()
         while True:                                                             # .repeat(-1), shuffled
-            subj = torch.randint(0, self.real.shape[0], (self.batch,), generator=self.gen).tolist()
+            subj = [next(stream) for _ in range(self.batch)]
             parts = [self._crop(s) for s in subj]
             data, mask, pred, img = (torch.stack(t) for t in zip(*parts))
             yield (data, mask), {'predictions': pred, 'predicted_images': img}

@@ -121,6 +121,9 @@ class _DenseFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 gx = g @ weight
         lib = _lib.lib()
+        if not torch.backends.cuda.matmul.allow_tf32:         # strict float32 requested: qbold_dense_wgrad is TF32 mma
+            gm = g if mask is None else torch.ops.aten.threshold_backward(g, mask, 0.0)
+            return gx, gm.t() @ x, gm.sum(0), None
         # per-call scratch from the caching allocator (stream-ordered, so concurrent backward passes cannot share it)
         ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
         dw = torch.empty_like(weight)
@@ -232,6 +235,175 @@ class _Block(nn.Module):
         return out1, gate_mix(skip, r, dense(self.gate, r), self.gate_offset)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Fused training path of the gated residual block (create_block, model.py:142-174).
+#
+# Internally the encoder keeps its activations as [B, Z, X, Y, C] ("z-outer"): the reference's 3x3x1 convolutions never
+# mix z slices, so in this layout they are plain 3x3 2-D convolutions over a batch of B*Z channels-last images -- the
+# shape cuDNN's 2-D NHWC kernels are tuned for (76 us against 152 us for the 3-D NDHWC form at 2 x 64^3 x 60, TF32) --
+# and the per-voxel Dense layers do not care.  Only the 11-channel input and the 5 / 5 / 11-channel outputs are
+# transposed.  One autograd node per block runs: the shared pointwise Dense (+ReLU, cuBLASLt epilogue), conv + bias +
+# ReLU fused in cuDNN, the second conv WITHOUT its bias (its bias is folded into the gate Dense and the mix kernel:
+# cuDNN would add it in a separate 86 us pass), the gate Dense and the mix kernel; the backward uses the fused
+# streaming kernels of csrc/encoder_block.cu (ReLU' + bias gradient in one pass, ReLU' of the skip branch inside the
+# mix backward), in-place accumulating GEMMs (beta = 1) instead of separate gradient additions, and qbold_dense_wgrad.
+_FAST_BLOCK = os.environ.get('QBOLD_FAST_BLOCK', '1') == '1'
+
+
+def _ws(dev):
+    from . import _lib
+    return torch.empty(int(_lib.lib().qbold_colsum_workspace_floats()), dtype=torch.float32, device=dev)
+
+
+def _relu_bwd(g, y, addend=None, colsum=None):
+    """g * [y > 0] (+ addend), optionally with the column sums of the result (a bias gradient) from the same pass."""
+    from . import _lib
+    from ._lib import check, dptr, stream_ptr
+    n, c = g.shape
+    out = torch.empty_like(g)
+    ws = _ws(g.device) if colsum is not None else None
+    with torch.cuda.device(g.device):
+        check(_lib.lib().qbold_relu_bwd_colsum(dptr(g), dptr(y), dptr(addend, allow_none=True), n, c, dptr(out),
+                                               dptr(colsum, allow_none=True), 0, dptr(ws, allow_none=True),
+                                               stream_ptr(g.device)))
+    return out
+
+
+def _colsum(g):
+    from . import _lib
+    from ._lib import check, dptr, stream_ptr
+    n, c = g.shape
+    out = torch.empty(c, dtype=torch.float32, device=g.device)
+    ws = _ws(g.device)
+    with torch.cuda.device(g.device):
+        check(_lib.lib().qbold_relu_bwd_colsum(dptr(g), None, None, n, c, None, dptr(out), 0, dptr(ws), stream_ptr(g.device)))
+    return out
+
+
+def _wgrad(g, x, accumulate_into=None):
+    """dW [n_out, n_in] = g^T x and db = column sums of g (qbold_dense_wgrad); optionally added to an earlier pair."""
+    from . import _lib
+    from ._lib import check, dptr, stream_ptr
+    lib = _lib.lib()
+    n_out, n_in = g.shape[1], x.shape[1]
+    dev = g.device
+    if not torch.backends.cuda.matmul.allow_tf32 or n_in > 63:      # strict float32 requested: the kernel is TF32 mma
+        dw, db = g.t() @ x, g.sum(0)
+        if accumulate_into is not None:
+            accumulate_into[0].add_(dw)
+            accumulate_into[1].add_(db)
+            return accumulate_into
+        return dw, db
+    ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
+    if accumulate_into is None:
+        dw = torch.empty((n_out, n_in), dtype=torch.float32, device=dev)
+        db = torch.empty(n_out, dtype=torch.float32, device=dev)
+    else:
+        dw, db = accumulate_into
+    with torch.cuda.device(dev):
+        check(lib.qbold_dense_wgrad(dptr(g), None, n_out, dptr(x), n_in, x.shape[0], dptr(dw), dptr(db),
+                                    0 if accumulate_into is None else 1, dptr(ws), stream_ptr(dev)))
+    return dw, db
+
+
+def _as_images(flat, dims):
+    """[N, C] z-outer activations as the [B*Z, C, X, Y] channels-last view cuDNN's 2-D kernels take (no copy)."""
+    bz, x, y = dims
+    return flat.view(bz, x, y, flat.shape[1]).permute(0, 3, 1, 2)
+
+
+def _as_flat(img):
+    """Back to [N, C]; a copy only if the library returned a non-channels-last tensor."""
+    return img.permute(0, 2, 3, 1).reshape(-1, img.shape[1])
+
+
+_CONV_ARGS = ((1, 1), (1, 1), (1, 1))                 # stride, padding, dilation
+
+
+class _BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net1, net2, a0, w_p, b_p, w_a, b_a, w_b, b_b, w_g, b_g, dims, offset, same_input, a0_is_net2,
+                want_relu_out):
+        from . import _lib
+        from ._lib import check, dptr, stream_ptr
+        n, c = net2.shape
+        dev = net2.device
+        skip = torch._addmm_activation(b_p, net2, w_p.t(), use_gelu=False)
+        out1 = skip if same_input else torch._addmm_activation(b_p, net1, w_p.t(), use_gelu=False)
+        wa2 = w_a.squeeze(-1).contiguous(memory_format=torch.channels_last)
+        wb2 = w_b.squeeze(-1).contiguous(memory_format=torch.channels_last)
+        c1 = torch.cudnn_convolution_relu(_as_images(a0, dims), wa2, b_a, *_CONV_ARGS, 1)          # conv + bias + ReLU
+        r0 = F.conv2d(c1, wb2, None, padding=1)                                                    # bias folded below
+        c1f, r0f = _as_flat(c1), _as_flat(r0)
+        z = torch.addmm(torch.addmv(b_g, w_g, b_b), r0f, w_g.t())                                  # W_g (r0 + b_b) + b_g
+        out2 = torch.empty_like(r0f)
+        out2_relu = torch.empty_like(r0f) if want_relu_out else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().qbold_block_mix_forward(dptr(skip), dptr(r0f), dptr(b_b.contiguous()), dptr(z), float(offset), n,
+                                                     c, dptr(out2), dptr(out2_relu, allow_none=True), stream_ptr(dev)))
+        ctx.save_for_backward(net1, net2, a0, out1, skip, c1f, r0f, z, w_p, w_a, w_b, w_g, b_b)
+        ctx.dims, ctx.offset, ctx.same_input, ctx.a0_is_net2 = dims, float(offset), same_input, a0_is_net2
+        if want_relu_out:
+            ctx.mark_non_differentiable(out2_relu)
+            return out1, out2, out2_relu
+        return out1, out2, None
+
+    @staticmethod
+    def backward(ctx, d_out1, d_out2, _unused):
+        from . import _lib
+        from ._lib import check, dptr, stream_ptr
+        net1, net2, a0, out1, skip, c1f, r0f, z, w_p, w_a, w_b, w_g, b_b = ctx.saved_tensors
+        n, c = net2.shape
+        dev = net2.device
+        dims = ctx.dims
+        d_out2 = d_out2.contiguous()
+        d_skip, d_r, d_z = torch.empty_like(skip), torch.empty_like(skip), torch.empty_like(skip)
+        with torch.cuda.device(dev):
+            check(_lib.lib().qbold_block_mix_backward(dptr(d_out2), dptr(skip), dptr(r0f), dptr(b_b.contiguous()), dptr(z),
+                                                      ctx.offset, n, c, 1, dptr(d_skip), dptr(d_r), dptr(d_z),
+                                                      stream_ptr(dev)))
+        # gate Dense: z = W_g (r0 + b_b) + b_g
+        dw_g, db_g = _wgrad(d_z, r0f)
+        dw_g = torch.addr(dw_g, db_g, b_b)                                   # + colsum(d_z) (x) b_b
+        d_r.addmm_(d_z, w_g)                                                 # total gradient of r = r0 + b_b, in place
+        db_b = _colsum(d_r)
+        # second convolution (no bias of its own): input gradient + weight gradient
+        wa2 = w_a.squeeze(-1).contiguous(memory_format=torch.channels_last)
+        wb2 = w_b.squeeze(-1).contiguous(memory_format=torch.channels_last)
+        d_c1, dw_b, _ = torch.ops.aten.convolution_backward(_as_images(d_r, dims), _as_images(c1f, dims), wb2, None,
+                                                            (1, 1), (1, 1), (1, 1), False, (0, 0), 1, (True, True, False))
+        db_a = torch.empty(c, dtype=torch.float32, device=dev)
+        d_c1m = _relu_bwd(_as_flat(d_c1), c1f, colsum=db_a)                  # ReLU' and the bias gradient in one pass
+        d_a0, dw_a, _ = torch.ops.aten.convolution_backward(_as_images(d_c1m, dims), _as_images(a0, dims), wa2, None,
+                                                            (1, 1), (1, 1), (1, 1), False, (0, 0), 1, (True, True, False))
+        d_net2 = _as_flat(d_a0)
+        if not ctx.a0_is_net2:                                               # a0 = relu(net2): apply its derivative
+            d_net2 = _relu_bwd(d_net2, net2)
+        elif not d_net2.is_contiguous():
+            d_net2 = d_net2.contiguous()
+        # shared pointwise Dense: skip = relu(W_p net2 + b_p) (d_skip is already masked), out1 = relu(W_p net1 + b_p)
+        if ctx.same_input:
+            g_p = _relu_bwd(d_out1.contiguous(), out1, addend=d_skip)        # both uses of the same activation
+            dw_p, db_p = _wgrad(g_p, net2)
+            d_net2.addmm_(g_p, w_p)
+            d_net1 = None
+        else:
+            g_1 = _relu_bwd(d_out1.contiguous(), out1)
+            dw_p, db_p = _wgrad(d_skip, net2)
+            _wgrad(g_1, net1, accumulate_into=(dw_p, db_p))
+            d_net2.addmm_(d_skip, w_p)
+            d_net1 = g_1 @ w_p
+        return (d_net1, d_net2, None, dw_p, db_p, dw_a.unsqueeze(-1), db_a, dw_b.unsqueeze(-1), db_b, dw_g, db_g,
+                None, None, None, None, None)
+
+
+def _fast_block_ok(blk, net2):
+    u = blk.pointwise.out_features
+    return (_FAST_BLOCK and net2.is_cuda and net2.dtype == torch.float32 and blk.act is F.relu and u % 4 == 0 and u <= 64
+            and blk.gate.out_features == u and torch.backends.cudnn.is_available() and not torch.is_autocast_enabled() and torch.is_grad_enabled()
+            and hasattr(torch, 'cudnn_convolution_relu'))
+
+
 class Encoder(nn.Module):
     """outer_model of create_encoder: data [B,X,Y,Z,n_tau] -> (q_voxelwise [...,5], q_spatial [...,5], sigma [...,n_tau])."""
 
@@ -325,12 +497,45 @@ class Encoder(nn.Module):
 
     def forward(self, data):
         x = self.normalise_data(data)
+        if x.dim() == 5 and _fast_block_ok(self.blocks[0], x):
+            return self._forward_fused_blocks(x)
         h = dense(self.first, x, True) if self.act is F.relu else self.act(dense(self.first, x))
         net1 = net2 = h
         for blk in self.blocks:
             net1, net2 = blk(net1, net2)
         return (self._with_hyper_prior(dense(self.final, net1)), dense(self.final, net2),
                 torch.exp(dense(self.im_sigma, net2)))
+
+    def _forward_fused_blocks(self, x):
+        """Training path on CUDA (TF32, ReLU, channel-wise gating): z-outer layout + one fused autograd node per block."""
+        b, nx, ny, nz, _ = x.shape
+        dims = (b * nz, nx, ny)
+        xt = x.permute(0, 3, 1, 2, 4).reshape(b * nz * nx * ny, x.shape[-1])          # [B,Z,X,Y,n_tau]: 44 B/voxel copy
+        h = dense(self.first, xt, True)
+        net1 = net2 = a0 = h
+        for i, blk in enumerate(self.blocks):
+            last = i + 1 == len(self.blocks)
+            net1, net2, nxt = _BlockFn.apply(net1, net2, a0, blk.pointwise.weight, blk.pointwise.bias, blk.conv_a.conv.weight,
+                                             blk.conv_a.conv.bias, blk.conv_b.conv.weight, blk.conv_b.conv.bias,
+                                             blk.gate.weight, blk.gate.bias, dims, blk.gate_offset, i == 0, i == 0,
+                                             not last)
+            a0 = nxt
+
+        def back(t):                                                                  # [B,Z,X,Y,c] -> [B,X,Y,Z,c]
+            return t.view(b, nz, nx, ny, t.shape[-1]).permute(0, 2, 3, 1, 4).contiguous()
+
+        q1 = dense(self.final, net1)
+        # the two heads that read net2 (posterior parameters and sigmas) as ONE skinny Dense: one pass over net2 forward,
+        # one input-gradient pass backward
+        n_q = self.final.out_features
+        w_cat = torch.cat([self.final.weight, self.im_sigma.weight], 0)
+        b_cat = torch.cat([self.final.bias, self.im_sigma.bias], 0)
+        if w_cat.shape[0] <= 16 and net2.is_cuda:
+            both = _DenseFn.apply(net2, w_cat, b_cat, False)
+            q2, sg = both[:, :n_q], torch.exp(both[:, n_q:])
+        else:
+            q2, sg = dense(self.final, net2), torch.exp(dense(self.im_sigma, net2))
+        return self._with_hyper_prior(back(q1)), back(q2), back(sg)
 
 
 def create_encoder_from_args(args, no_ip_images=11, se_idx=2):

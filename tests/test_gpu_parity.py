@@ -1426,3 +1426,37 @@ def test_dlpack_hand_off_without_torch_tensors(qb, dev, cfg_noise_off):
         qb.forward_dlpack(layer, Foreign(x), Foreign(torch.empty((7, 11), device=dev)))
     with pytest.raises(qb.dlpack.DLPackError, match='CUDA device memory only'):
         qb.forward_dlpack(layer, x.cpu(), Foreign(out))
+
+
+def test_fused_encoder_block_path_matches_the_layer_by_layer_path(qb, dev, monkeypatch):
+    """The training path of the encoder (z-outer layout, one fused autograd node per gated residual block, bias of the
+    second convolution folded into the gate Dense / mix kernel, fused ReLU' + bias-gradient kernels) against the plain
+    layer-by-layer module: outputs and every parameter gradient, in strict float32 (TF32 off) so the bar can be tight."""
+    import qbold_vi_b200.encoder as E
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(3)
+        enc = E.Encoder(no_units=60, no_intermediate_layers=2, gate_offset=-1.0, resid_init_std=0.1).to(dev)
+        data = torch.rand(2, 10, 12, 6, 11, device=dev) * 50.0 + 20.0
+        w = [torch.randn(2, 10, 12, 6, c, device=dev) for c in (5, 5, 11)]
+
+        def run(fast):
+            monkeypatch.setattr(E, '_FAST_BLOCK', fast)
+            for p in enc.parameters():
+                p.grad = None
+            outs = enc(data)
+            sum((o * wi).sum() for o, wi in zip(outs, w)).backward()
+            return [o.detach().clone() for o in outs], [p.grad.detach().clone() for p in enc.parameters()]
+
+        o_ref, g_ref = run(False)
+        o_fast, g_fast = run(True)
+        for a, b in zip(o_fast, o_ref):
+            assert a.shape == b.shape and float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
+        names = [n for n, _ in enc.named_parameters()]
+        for n, a, b in zip(names, g_fast, g_ref):
+            assert a.shape == b.shape, n
+            assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-6, n
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
