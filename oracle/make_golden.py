@@ -340,6 +340,44 @@ def main():
     print('adjacent: tv=%.6f synth=%.6f kl_diag=%.6f kl_pop=%.6f' % (float(adj['tv_mvg']), float(adj['synth_mvg']),
                                                                    float(adj['kl_diag']), float(adj['kl_pop'])))
 
+    # ------------------------------------------------------------------ G. the amortization network itself
+    # EncoderTrainer.create_encoder (model.py:122-223) executed over the shim's minimal Keras functional API: outputs
+    # of the outer model and the gradient of a weighted sum of them w.r.t. every kernel / bias.
+    tr_e = ref_model.EncoderTrainer(system_params=params, no_units=60, no_intermediate_layers=2, student_t_df=200,
+                                    initial_im_sigma=0.05, activation_type='relu', multi_image_normalisation=False,
+                                    channelwise_gating=True, infer_inv_gamma=False, use_population_prior=False,
+                                    use_mvg=True, predict_log_data=False)
+    torch.manual_seed(2026)
+    del tf.keras.layers.created[:]
+    outer, _inner = tr_e.create_encoder(gate_offset=-1.0, resid_init_std=0.1, no_ip_images=11)
+    r = np.random.default_rng(99)
+    vol = (2, 6, 5, 3)
+    e_data = (r.uniform(20.0, 70.0, vol + (11,))).astype(np.float32)
+    outer(tf.convert_to_tensor(e_data))                                   # builds the weights (creation order below)
+    layers = list(tf.keras.layers.created)
+    assert len(layers) == 11, len(layers)            # first | (pointwise, conv_a, conv_b, gate) x 2 | final | im_sigma
+    for lay in layers:
+        lay.bias = (lay.bias + 0.05 * torch.randn_like(lay.bias))         # non-trivial biases
+        lay.kernel.requires_grad_(True)
+        lay.bias.requires_grad_(True)
+    o0, o1, o2 = outer(tf.convert_to_tensor(e_data))
+    e_w = [r.standard_normal(tuple(o.shape)).astype(np.float32) for o in (o0, o1, o2)]
+    total = sum((o * torch.as_tensor(w)).sum() for o, w in zip((o0, o1, o2), e_w))
+    grads = torch.autograd.grad(total, [t for lay in layers for t in (lay.kernel, lay.bias)])
+    enc_fix = {'data': e_data, 'out_voxelwise': o0.detach().numpy(), 'out_spatial': o1.detach().numpy(),
+               'out_sigma': o2.detach().numpy(), 'gate_offset': -1.0, 'n_layers': len(layers)}
+    for i, w in enumerate(e_w):
+        enc_fix['w_out%d' % i] = w
+    for i, lay in enumerate(layers):
+        enc_fix['kernel%d' % i] = lay.kernel.detach().numpy()              # keras layout [kx, ky, kz, C_in, C_out]
+        enc_fix['bias%d' % i] = lay.bias.detach().numpy()
+        enc_fix['grad_kernel%d' % i] = grads[2 * i].numpy()
+        enc_fix['grad_bias%d' % i] = grads[2 * i + 1].numpy()
+    np.savez(os.path.join(args.out, 'ref_shim_encoder.npz'), **enc_fix)
+    print('encoder: %d layers, %d parameters, sigma mean %.4f' % (
+        len(layers), sum(int(np.prod(lay.kernel.shape)) + int(lay.bias.numel()) for lay in layers),
+        float(o2.detach().mean())))
+
     # ------------------------------------------------------------------ E. Appendix B KATs
     np.savez(os.path.join(args.out, 'kat_appendix_b.npz'),
              oef_dbv=np.array([[0.4, 0.12], [0.4, 0.03]]),

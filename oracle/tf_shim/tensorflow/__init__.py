@@ -346,7 +346,157 @@ class _Layer:
 
 
 keras.layers.Layer = _Layer
+
+
+# ---- a minimal functional API: what EncoderTrainer.create_encoder (model.py:122-223) touches.  Layers applied to the
+# symbolic tensors of keras.layers.Input build a graph; keras.Model(inputs, outputs) replays it on real tensors.
+class _Sym:
+    """Symbolic tensor: `layer` applied to `parents` (output `index` of it), or a placeholder (layer None)."""
+
+    def __init__(self, layer=None, parents=(), index=None, last_dim=None):
+        self.layer, self.parents, self.index = layer, tuple(parents), index
+        self.shape = (None, None, None, None, last_dim)
+
+
+def _is_sym(x):
+    return isinstance(x, _Sym) or (isinstance(x, (list, tuple)) and len(x) > 0 and all(isinstance(v, _Sym) for v in x))
+
+
+class _GraphLayer:
+    """Base of the functional-API layers: symbolic inputs defer, real inputs compute."""
+    created = []                                       # creation order, so a test can install known weights
+
+    def __call__(self, inputs):
+        if _is_sym(inputs):
+            parents = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+            return _Sym(self, parents, None, self._out_dim(parents))
+        return self.compute(inputs)
+
+    def _out_dim(self, parents):
+        return parents[0].shape[-1]
+
+
+class _Conv3D(_GraphLayer):
+    """keras.layers.Conv3D on channels-last [B,X,Y,Z,C]: kernel [kx,ky,kz,C_in,C_out], padding 'valid' | 'same'
+    (odd kernels), optional activation ('relu', None or a callable)."""
+
+    def __init__(self, filters, kernel_size, padding='valid', kernel_initializer=None, bias_initializer=None,
+                 activation=None):
+        self.filters, self.kernel_size, self.padding = int(filters), tuple(kernel_size), padding
+        self.kernel_initializer, self.bias_initializer, self.activation = kernel_initializer, bias_initializer, activation
+        self.kernel = self.bias = None
+        _GraphLayer.created.append(self)
+
+    def _out_dim(self, parents):
+        return self.filters
+
+    def build(self, c_in):
+        shape = self.kernel_size + (c_in, self.filters)
+        init = self.kernel_initializer or (lambda shp: torch.zeros(shp))
+        self.kernel = init(shape).float()
+        self.bias = (self.bias_initializer((self.filters,)) if self.bias_initializer else torch.zeros(self.filters)).float()
+
+    def compute(self, x):
+        x = _t(x)
+        if self.kernel is None:
+            self.build(x.shape[-1])
+        w = self.kernel.permute(4, 3, 0, 1, 2)                       # [C_out, C_in, kx, ky, kz]
+        pad = tuple(k // 2 for k in self.kernel_size) if self.padding == 'same' else 0
+        y = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3), w, self.bias, padding=pad).permute(0, 2, 3, 4, 1)
+        act = self.activation
+        if act is None or act == 'linear':
+            return y
+        if callable(act):
+            return act(y)
+        return {'relu': torch.relu, 'gelu': torch.nn.functional.gelu, 'tanh': torch.tanh}[act](y)
+
+
+class _Activation(_GraphLayer):
+    def __init__(self, activation):
+        self.activation = activation
+
+    def compute(self, x):
+        return {'relu': torch.relu, 'gelu': torch.nn.functional.gelu, 'tanh': torch.tanh}[self.activation](_t(x))
+
+
+class _Lambda(_GraphLayer):
+    def __init__(self, fn):
+        self.fn = fn
+
+    def compute(self, x):
+        return self.fn(x)
+
+
+def _Input(shape=None, ragged=False, **kw):
+    return _Sym(None, (), None, shape[-1] if shape else None)
+
+
+class _Model(_GraphLayer):
+    """keras.Model(inputs, outputs): callable on real tensors (list or single), or on symbolic tensors (nesting)."""
+
+    def __init__(self, inputs=None, outputs=None):
+        self.inputs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+        self.single_output = not isinstance(outputs, (list, tuple))
+        self.outputs = [outputs] if self.single_output else list(outputs)
+
+    def __call__(self, inputs):
+        if _is_sym(inputs):
+            parents = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+            outs = [_Sym(self, parents, i, o.shape[-1]) for i, o in enumerate(self.outputs)]
+            return outs[0] if self.single_output else outs
+        return self.compute(inputs)
+
+    def compute(self, inputs):
+        vals = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        memo = {id(s): _t(v) for s, v in zip(self.inputs, vals)}
+        nested = {}
+
+        def ev(sym):
+            if id(sym) in memo:
+                return memo[id(sym)]
+            if sym.layer is None:
+                raise ValueError('unbound keras Input')
+            args = [ev(p) for p in sym.parents]
+            if isinstance(sym.layer, _Model):
+                key = (id(sym.layer), tuple(id(p) for p in sym.parents))
+                if key not in nested:
+                    res = sym.layer.compute(args)
+                    nested[key] = res if isinstance(res, (list, tuple)) else [res]
+                out = nested[key][sym.index]
+            else:
+                out = sym.layer.compute(args[0] if len(args) == 1 else args)
+            memo[id(sym)] = out
+            return out
+
+        outs = [ev(o) for o in self.outputs]
+        return outs[0] if self.single_output else outs
+
+    predict = compute
+
+
+keras.layers.Conv3D = _Conv3D
+keras.layers.Activation = _Activation
+keras.layers.Lambda = _Lambda
+keras.layers.Input = _Input
+keras.layers.created = _GraphLayer.created
+keras.Model = _Model
 keras.backend = types.SimpleNamespace(print_tensor=lambda x, *a, **k: print(x))
-keras.initializers = types.SimpleNamespace()
+
+
+def _he_normal():
+    def init(shape):                                   # fan_in = receptive field x C_in; truncated normal, as keras
+        fan_in = 1
+        for d in shape[:-1]:
+            fan_in *= d
+        std = (2.0 / fan_in) ** 0.5 / 0.87962566103423978
+        return torch.nn.init.trunc_normal_(torch.empty(shape), 0.0, std, -2 * std, 2 * std)
+    return init
+
+
+keras.initializers = types.SimpleNamespace(
+    HeNormal=_he_normal,
+    RandomNormal=lambda stddev=0.05, mean=0.0: (lambda shape: torch.randn(shape) * stddev + mean),
+    Constant=lambda value: (lambda shape: torch.full(shape, float(value))),
+    constant=lambda value: (lambda shape: torch.as_tensor(np.asarray(value, dtype=np.float32)).reshape(shape)))
 sys.modules['tensorflow.keras'] = keras
 sys.modules['tensorflow.keras.layers'] = keras.layers

@@ -56,3 +56,30 @@ def cfg_noise_off():
 def physics(cfg_noise_off):
     from oracle import qbold_oracle as o
     return o.parse_params(cfg_noise_off)
+
+
+def load_reference_encoder_weights(enc, fix):
+    """Install the kernels / biases of the reference-source encoder fixture (keras layout [kx,ky,kz,C_in,C_out], creation
+    order: first | (pointwise, conv_a, conv_b, gate) per block | final | im_sigma) into a qbold_vi_b200 Encoder; returns
+    the parameters in the same order as the fixture's gradients [(weight, bias, kind), ...]."""
+    import torch
+    mods = [(enc.first, 'dense')]
+    for blk in enc.blocks:
+        mods += [(blk.pointwise, 'dense'), (blk.conv_a.conv, 'conv'), (blk.conv_b.conv, 'conv'), (blk.gate, 'dense')]
+    mods += [(enc.final, 'dense'), (enc.im_sigma, 'dense')]
+    assert len(mods) == int(fix['n_layers'])
+    out = []
+    with torch.no_grad():
+        for i, (m, kind) in enumerate(mods):
+            k = torch.as_tensor(fix['kernel%d' % i])
+            w = k.permute(4, 3, 0, 1, 2) if kind == 'conv' else k[0, 0, 0].t()
+            m.weight.copy_(w.to(m.weight.device))
+            m.bias.copy_(torch.as_tensor(fix['bias%d' % i]).to(m.bias.device))
+            out.append((m.weight, m.bias, kind))
+    return out
+
+
+def reference_encoder_grad(fix, i, kind):
+    import torch
+    k = torch.as_tensor(fix['grad_kernel%d' % i])
+    return (k.permute(4, 3, 0, 1, 2) if kind == 'conv' else k[0, 0, 0].t()), torch.as_tensor(fix['grad_bias%d' % i])

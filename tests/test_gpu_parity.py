@@ -1460,3 +1460,28 @@ def test_fused_encoder_block_path_matches_the_layer_by_layer_path(qb, dev, monke
             assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-6, n
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_fused_encoder_path_matches_the_reference_source_network(qb, dev):
+    """The GPU training path (fused blocks, z-outer layout) against the reference-source encoder fixture, strict float32."""
+    from conftest import load_reference_encoder_weights, reference_encoder_grad
+    from qbold_vi_b200.encoder import Encoder
+    fix = golden('ref_shim_encoder.npz')
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        enc = Encoder(no_units=60, no_intermediate_layers=2, activation='relu', initial_im_sigma=0.05,
+                      multi_image_normalisation=False, channelwise_gating=True, gate_offset=float(fix['gate_offset']),
+                      resid_init_std=0.1, no_ip_images=11, se_idx=2, use_mvg=True).to(dev)
+        params = load_reference_encoder_weights(enc, fix)
+        outs = enc(_t(fix['data'], dev))
+        for o, key in zip(outs, ('out_voxelwise', 'out_spatial', 'out_sigma')):
+            assert rel_max(o.detach().cpu().numpy(), fix[key]) < 5e-5, key
+        sum((o * _t(fix['w_out%d' % i], dev)).sum() for i, o in enumerate(outs)).backward()
+        for i, (w, b, kind) in enumerate(params):
+            gw, gb = reference_encoder_grad(fix, i, kind)
+            assert rel_max(w.grad.cpu().numpy(), gw.numpy()) < 2e-4, ('kernel', i)
+            assert rel_max(b.grad.cpu().numpy(), gb.numpy()) < 2e-4, ('bias', i)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old

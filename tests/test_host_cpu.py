@@ -302,3 +302,26 @@ def test_dlpack_unpacking_without_a_gpu(qb):
         qb.DLPackView(t)
     with pytest.raises(qb.dlpack.DLPackError):
         qb.DLPackView(object())
+
+
+def test_encoder_matches_the_reference_source_network(qb):
+    """EncoderTrainer.create_encoder (model.py:122-223), executed from the reference's own source over the Keras shim
+    (oracle/make_golden.py, fixture ref_shim_encoder.npz): same weights -> same three outputs and the same gradient for
+    every kernel and bias.  Pins normalise_data, the shared pointwise layer, the gated residual blocks, both heads."""
+    import torch
+    from conftest import golden, load_reference_encoder_weights, reference_encoder_grad
+    from qbold_vi_b200.encoder import Encoder
+    fix = golden('ref_shim_encoder.npz')
+    enc = Encoder(no_units=60, no_intermediate_layers=2, activation='relu', initial_im_sigma=0.05,
+                  multi_image_normalisation=False, channelwise_gating=True, gate_offset=float(fix['gate_offset']),
+                  resid_init_std=0.1, no_ip_images=11, se_idx=2, use_mvg=True)
+    params = load_reference_encoder_weights(enc, fix)
+    outs = enc(torch.as_tensor(fix['data']))
+    for o, key in zip(outs, ('out_voxelwise', 'out_spatial', 'out_sigma')):
+        ref = torch.as_tensor(fix[key])
+        assert o.shape == ref.shape and float((o - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), key
+    sum((o * torch.as_tensor(fix['w_out%d' % i])).sum() for i, o in enumerate(outs)).backward()
+    for i, (w, b, kind) in enumerate(params):
+        gw, gb = reference_encoder_grad(fix, i, kind)
+        assert float((w.grad - gw).abs().max()) <= 1e-4 * float(gw.abs().max()) + 1e-7, ('kernel', i)
+        assert float((b.grad - gb).abs().max()) <= 1e-4 * float(gb.abs().max()) + 1e-7, ('bias', i)
