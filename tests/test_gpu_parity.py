@@ -531,6 +531,15 @@ def test_single_gpu_training_steps_reduce_the_loss(qb, dev, cfg_noise_off):
     losses = [dp.step(data, mask, prior) for _ in range(12)]
     assert all(np.isfinite(s['loss']) for s in losses)
     assert np.mean([s['nll'] for s in losses[-3:]]) < np.mean([s['nll'] for s in losses[:3]])
+    # the step itself never synchronises with the host: torch raises on any synchronising call in this mode (the mask
+    # count, the losses and the statistics stay on the device until somebody reads them)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode('error')
+    try:
+        lazy = [dp.step(data, mask, prior) for _ in range(3)]
+    finally:
+        torch.cuda.set_sync_debug_mode('default')
+    assert np.isfinite(lazy[-1]['loss']) and lazy[-1]['mask_sum'] == float(mask.sum())
 
 
 # ---------------------------------------------------------------------------------- whole-volume inference (config 4)
@@ -1485,3 +1494,73 @@ def test_fused_encoder_path_matches_the_reference_source_network(qb, dev):
             assert rel_max(b.grad.cpu().numpy(), gb.numpy()) < 2e-4, ('bias', i)
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize('n,c', [(1, 4), (257, 60), (100003, 60), (4096, 64)])
+def test_encoder_block_kernels_match_torch(qb, dev, n, c):
+    """csrc/encoder_block.cu against plain float32 torch: gated mix with the folded convolution bias (+ ReLU copy), its
+    backward with the skip branch's ReLU' applied in place, and ReLU' + column sums in one pass; ragged sizes."""
+    import ctypes as C
+    from qbold_vi_b200._lib import check, dptr, lib, stream_ptr
+    g = torch.Generator(device=dev).manual_seed(n + c)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)                       # noqa: E731
+    skip, r0, z, go = torch.relu(rnd(n, c)), rnd(n, c), rnd(n, c), rnd(n, c)
+    rb = rnd(c)
+    off = -0.7
+    out, out_relu = torch.empty_like(r0), torch.empty_like(r0)
+    st = stream_ptr(dev)
+    check(lib().qbold_block_mix_forward(dptr(skip), dptr(r0), dptr(rb), dptr(z), off, n, c, dptr(out), dptr(out_relu), st))
+    gate = torch.sigmoid(z + off)
+    want = skip * (1 - gate) + (r0 + rb) * gate
+    assert torch.allclose(out, want, rtol=1e-6, atol=1e-6) and torch.allclose(out_relu, torch.relu(want), rtol=1e-6, atol=1e-6)
+    ds, dr, dz = torch.empty_like(r0), torch.empty_like(r0), torch.empty_like(r0)
+    check(lib().qbold_block_mix_backward(dptr(go), dptr(skip), dptr(r0), dptr(rb), dptr(z), off, n, c, 1, dptr(ds), dptr(dr),
+                                         dptr(dz), st))
+    assert torch.allclose(ds, go * (1 - gate) * (skip > 0), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(dr, go * gate, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(dz, go * ((r0 + rb) - skip) * gate * (1 - gate), rtol=1e-5, atol=1e-6)
+    # ReLU' (+ addend) with the bias gradient from the same pass
+    y, add = rnd(n, c), rnd(n, c)
+    ws = torch.empty(int(lib().qbold_colsum_workspace_floats()), device=dev)
+    o, cs = torch.empty_like(y), torch.empty(c, device=dev)
+    check(lib().qbold_relu_bwd_colsum(dptr(go), dptr(y), dptr(add), n, c, dptr(o), dptr(cs), 0, dptr(ws), st))
+    want = go * (y > 0) + add
+    assert torch.equal(o, want)
+    ref = want.double().sum(0)
+    assert float((cs.double() - ref).abs().max()) <= 1e-5 * float(want.abs().double().sum(0).max()) + 1e-6
+    cs2 = cs.clone()
+    check(lib().qbold_relu_bwd_colsum(dptr(go), None, None, n, c, None, dptr(cs2), 1, dptr(ws), st))     # accumulate
+    ref2 = ref + go.double().sum(0)
+    assert float((cs2.double() - ref2).abs().max()) <= 1e-5 * float(go.abs().double().sum(0).max() + ref.abs().max()) + 1e-6
+    with pytest.raises(qb.QboldError):
+        check(lib().qbold_block_mix_forward(dptr(skip), dptr(r0), None, dptr(z), off, n, 6, dptr(out), None, st))   # c % 4
+
+
+def test_new_entry_points_edge_cases(qb, dev, cfg_noise_off):
+    """Empty and degenerate inputs of the round-2 entry points (the reference's behaviour for empty tensors is 'empty in,
+    empty out'; bad shapes raise)."""
+    from qbold_vi_b200._lib import check, dptr, lib, stream_ptr
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True, misaligned_prob=0.5)
+    empty = torch.empty((0, 2), device=dev)
+    assert tuple(layer.misalign(empty, torch.empty((0, 11), device=dev)).shape) == (0, 11)
+    x = _t(_rand_voxels(64, 9), dev)
+    s = layer._forward_raw(x)
+    layer._misaligned_prob = 0.0
+    assert torch.equal(layer.misalign(x, s), s)                                      # prob 0: untouched
+    layer._misaligned_prob = 0.5
+    with pytest.raises(qb.QboldError):                                               # all three draw arrays or none
+        layer.misalign(x, s, sel_u01=torch.rand(64, device=dev))
+    hl = qb.SignalGenerationLayer(cfg_noise_off, True, True, variable_hct=True)
+    sig, g = hl.forward_backward(torch.empty((0, 3), device=dev), None)
+    assert tuple(sig.shape) == (0, 11) and tuple(g.shape) == (0, 3)
+    one = torch.tensor([[0.4, 0.12, 0.34]], device=dev)
+    s1, g1 = hl.forward_backward(one, None)
+    s2, g2 = qb.SignalGenerationLayer(cfg_noise_off, True, True).forward_backward(one[:, :2].contiguous(), None)
+    assert torch.allclose(s1, s2, rtol=2e-6, atol=0) and torch.allclose(g1[:, :2], g2, rtol=1e-5, atol=0)
+    tr = _trainer(qb, cfg_noise_off, use_mvg=False, use_population_prior=True, mog_components=2)
+    q12 = torch.randn(5, 12, device=dev)
+    dead = torch.zeros(5, 5, device=dev)                                             # mask channel (index 4) all zero
+    kl = tr.kl_loss(dead, q12, return_mean=False)
+    assert tuple(kl.shape) == (5, 1) and float(kl.abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        tr.kl_loss(dead, torch.randn(5, 8, device=dev))                              # wrong channel count for M = 2
