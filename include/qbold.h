@@ -356,6 +356,16 @@ int64_t qbold_colsum_workspace_floats(void);
 int qbold_relu_bwd_colsum(const float* g, const float* y, const float* addend, int64_t n, int32_t channels, float* out,
                           float* colsum, int32_t accumulate, float* workspace, void* stream);
 
+/* Weight gradient of the encoder's 3x3x1 convolutions (create_block, model.py:152,156; padding 'same') on tcgen05
+ * tensor cores (kind::tf32, fp32 accumulate in TMEM): dw[cg, cx, 3, 3] (+)= sum_v g[v, :]^T x[v + (kx-1, ky-1), :]
+ * for activations laid out [n_images, nx, ny, channels] (the encoder's z-outer layout: n_images = B * Z).
+ * cg, cx: multiples of 4 up to 64; g, x 16-byte aligned.  workspace: qbold_conv_wgrad_workspace_floats() floats of
+ * device scratch (per-SM partials, summed in a fixed order).  status (may be NULL) is set non-zero if a tensor-core
+ * completion barrier timed out. */
+int64_t qbold_conv_wgrad_workspace_floats(void);
+int qbold_conv_wgrad(const float* g, int32_t cg, const float* x, int32_t cx, int64_t n_images, int32_t nx, int32_t ny,
+                     float* dw, int32_t accumulate, float* workspace, int32_t* status, void* stream);
+
 /* FP32 FMA micro-benchmark (roofline denominator measured in the same run): launches
  * `iters` dependent-chain FFMA sweeps, returns achieved TFLOP/s through *tflops. */
 int qbold_fma_peak(int32_t iters, double* tflops);

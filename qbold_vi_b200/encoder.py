@@ -318,6 +318,35 @@ def _as_flat(img):
 
 
 _CONV_ARGS = ((1, 1), (1, 1), (1, 1))                 # stride, padding, dilation
+# weight gradient of the 3x3 convolutions on tcgen05 (qbold_conv_wgrad) instead of cuDNN's wgrad kernel; TF32, so only
+# when TF32 convolutions are allowed
+_CONV_WGRAD_TC = os.environ.get('QBOLD_CONV_WGRAD_TC', '0') == '1'
+
+
+def _conv_backward(g_flat, x_flat, w2, dims):
+    """(input gradient [N, C_in] flat, weight gradient [C_out, C_in, 3, 3]) of a 3x3 'same' convolution on z-outer
+    activations: the input gradient is cuDNN's, the weight gradient the tcgen05 kernel (or cuDNN's in strict float32)."""
+    from . import _lib
+    from ._lib import check, dptr, stream_ptr
+    bz, nx, ny = dims
+    c_out, c_in = g_flat.shape[1], x_flat.shape[1]
+    use_tc = (_CONV_WGRAD_TC and torch.backends.cudnn.allow_tf32 and c_out % 4 == 0 and c_in % 4 == 0 and c_out <= 64
+              and c_in <= 64 and g_flat.is_contiguous() and x_flat.is_contiguous())
+    mask = (True, not use_tc, False)
+    d_in, dw, _ = torch.ops.aten.convolution_backward(_as_images(g_flat, dims), _as_images(x_flat, dims), w2, None,
+                                                      (1, 1), (1, 1), (1, 1), False, (0, 0), 1, mask)
+    if use_tc:
+        lib = _lib.lib()
+        dev = g_flat.device
+        dw = torch.empty((c_out, c_in, 3, 3), dtype=torch.float32, device=dev)
+        ws = torch.empty(int(lib.qbold_conv_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
+        status = _TC_STATUS.get(dev)
+        if status is None:
+            status = _TC_STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.qbold_conv_wgrad(dptr(g_flat), c_out, dptr(x_flat), c_in, bz, nx, ny, dptr(dw), 0, dptr(ws),
+                                       dptr(status, torch.int32), stream_ptr(dev)))
+    return _as_flat(d_in), dw
 
 
 class _BlockFn(torch.autograd.Function):
@@ -370,13 +399,10 @@ class _BlockFn(torch.autograd.Function):
         # second convolution (no bias of its own): input gradient + weight gradient
         wa2 = w_a.squeeze(-1).contiguous(memory_format=torch.channels_last)
         wb2 = w_b.squeeze(-1).contiguous(memory_format=torch.channels_last)
-        d_c1, dw_b, _ = torch.ops.aten.convolution_backward(_as_images(d_r, dims), _as_images(c1f, dims), wb2, None,
-                                                            (1, 1), (1, 1), (1, 1), False, (0, 0), 1, (True, True, False))
+        d_c1, dw_b = _conv_backward(d_r, c1f, wb2, dims)
         db_a = torch.empty(c, dtype=torch.float32, device=dev)
-        d_c1m = _relu_bwd(_as_flat(d_c1), c1f, colsum=db_a)                  # ReLU' and the bias gradient in one pass
-        d_a0, dw_a, _ = torch.ops.aten.convolution_backward(_as_images(d_c1m, dims), _as_images(a0, dims), wa2, None,
-                                                            (1, 1), (1, 1), (1, 1), False, (0, 0), 1, (True, True, False))
-        d_net2 = _as_flat(d_a0)
+        d_c1m = _relu_bwd(d_c1, c1f, colsum=db_a)                            # ReLU' and the bias gradient in one pass
+        d_net2, dw_a = _conv_backward(d_c1m, a0, wa2, dims)
         if not ctx.a0_is_net2:                                               # a0 = relu(net2): apply its derivative
             d_net2 = _relu_bwd(d_net2, net2)
         elif not d_net2.is_contiguous():

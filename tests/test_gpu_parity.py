@@ -1564,3 +1564,33 @@ def test_new_entry_points_edge_cases(qb, dev, cfg_noise_off):
     assert tuple(kl.shape) == (5, 1) and float(kl.abs().max()) == 0.0
     with pytest.raises(ValueError):
         tr.kl_loss(dead, torch.randn(5, 8, device=dev))                              # wrong channel count for M = 2
+
+
+@pytest.mark.parametrize('bz,nx,ny,cg,cx', [(3, 5, 7, 60, 60), (2, 64, 64, 60, 60), (1, 1, 1, 4, 8), (4, 9, 33, 12, 8),
+                                           (130, 16, 16, 64, 64)])
+def test_conv_weight_gradient_tensor_core_kernel(qb, dev, bz, nx, ny, cg, cx):
+    """qbold_conv_wgrad (tcgen05 kind::tf32, voxel-contraction GEMM with nine shifted operands) against the float64
+    weight gradient of a 3x3 'same' convolution; TF32 operand rounding sets the bar (1e-3 of the largest entry)."""
+    from qbold_vi_b200._lib import check, dptr, lib, stream_ptr
+    gen = torch.Generator(device=dev).manual_seed(bz * 1000 + nx)
+    x = torch.randn(bz, nx, ny, cx, device=dev, generator=gen)
+    g = torch.randn(bz, nx, ny, cg, device=dev, generator=gen)
+    w = torch.zeros(cg, cx, 3, 3, device=dev, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w, None, padding=1)
+    (y * g.double().permute(0, 3, 1, 2)).sum().backward()
+    dw = torch.full((cg, cx, 3, 3), float('nan'), device=dev)
+    ws = torch.empty(int(lib().qbold_conv_wgrad_workspace_floats()), device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib().qbold_conv_wgrad(dptr(g.reshape(-1, cg)), cg, dptr(x.reshape(-1, cx)), cx, bz, nx, ny, dptr(dw), 0, dptr(ws),
+                                 dptr(status, torch.int32), stream_ptr(dev)))
+    assert int(status.item()) == 0
+    ref = w.grad
+    scale = float(ref.abs().max()) + float((bz * nx * ny) ** 0.5) * 1e-3
+    assert float((dw.double() - ref).abs().max()) <= 1.5e-3 * scale
+    dw2 = dw.clone()
+    check(lib().qbold_conv_wgrad(dptr(g.reshape(-1, cg)), cg, dptr(x.reshape(-1, cx)), cx, bz, nx, ny, dptr(dw2), 1, dptr(ws),
+                                 dptr(status, torch.int32), stream_ptr(dev)))
+    assert torch.allclose(dw2, 2 * dw, rtol=1e-6, atol=1e-6)                          # accumulate, deterministic
+    with pytest.raises(qb.QboldError):
+        check(lib().qbold_conv_wgrad(dptr(g.reshape(-1, cg)), 6, dptr(x.reshape(-1, cx)), cx, bz, nx, ny, dptr(dw), 0, dptr(ws),
+                                     None, stream_ptr(dev)))
