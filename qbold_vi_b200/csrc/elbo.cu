@@ -163,6 +163,24 @@ struct KlOut {
     float g[5];
 };
 
+__device__ __forceinline__ KlOut kl_closed_form(const Dist& dq, const QExtra& ex, const Dist& dp) {
+    KlOut o;
+    const float m00 = ex.sd_o * dp.inv_o;
+    const float m10 = (dq.cov - dp.cov * m00) * dp.inv_d;
+    const float m11 = ex.sd_d * dp.inv_d;
+    const float d_o = dp.mu_o - dq.mu_o, d_d = dp.mu_d - dq.mu_d;
+    const float w_o = d_o * dp.inv_o;
+    const float w_d = (d_d - dp.cov * w_o) * dp.inv_d;
+    o.kl = 0.5f * ((m00 * m00 + m10 * m10 + m11 * m11) + (w_o * w_o + w_d * w_d) - 2.0f +
+                   2.0f * ((dp.ls_o + dp.ls_d) - (dq.ls_o + dq.ls_d)));
+    o.g[0] = -w_o * dp.inv_o + w_d * dp.cov * dp.inv_o * dp.inv_d;
+    o.g[1] = (m00 * m00 - m10 * dp.cov * m00 * dp.inv_d - 1.0f) * ex.dls_o;
+    o.g[2] = -w_d * dp.inv_d;
+    o.g[3] = (m11 * m11 - 1.0f) * ex.dls_d;
+    o.g[4] = (m10 * dp.inv_d) * ex.dcov;
+    return o;
+}
+
 template <int W = 32>
 __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const Dist& dp,
                                          const float* __restrict__ eps_v, uint64_t seed, uint64_t index,
@@ -241,35 +259,166 @@ __device__ __forceinline__ KlOut kl_term(const Dist& dq, const QExtra& ex, const
         o.g[4] = a[4] * inv_s * ex.dcov;
         o.kl = a[5] * inv_s;
     } else {
-        const float m00 = ex.sd_o * dp.inv_o;
-        const float m10 = (dq.cov - dp.cov * m00) * dp.inv_d;
-        const float m11 = ex.sd_d * dp.inv_d;
-        const float d_o = dp.mu_o - dq.mu_o, d_d = dp.mu_d - dq.mu_d;
-        const float w_o = d_o * dp.inv_o;
-        const float w_d = (d_d - dp.cov * w_o) * dp.inv_d;
-        o.kl = 0.5f * ((m00 * m00 + m10 * m10 + m11 * m11) + (w_o * w_o + w_d * w_d) - 2.0f +
-                       2.0f * ((dp.ls_o + dp.ls_d) - (dq.ls_o + dq.ls_d)));
-        o.g[0] = -w_o * dp.inv_o + w_d * dp.cov * dp.inv_o * dp.inv_d;
-        o.g[1] = (m00 * m00 - m10 * dp.cov * m00 * dp.inv_d - 1.0f) * ex.dls_o;
-        o.g[2] = -w_d * dp.inv_d;
-        o.g[3] = (m11 * m11 - 1.0f) * ex.dls_d;
-        o.g[4] = (m10 * dp.inv_d) * ex.dcov;
+        o = kl_closed_form(dq, ex, dp);
     }
     return o;
 }
 
-// kl_loss alone (model.py:654-665): per-voxel KL map and d kl_map[v] / d q[v,:].
+// ---- thread-per-voxel KL --------------------------------------------------------------------------------------
+// The same estimator as kl_term with ONE LANE per voxel (no shuffles, no idle sample slots, both samples of every
+// Philox call used).  While every sample stays inside |z| < kRoundTripZ the round trip is the identity, so
+//     zh = mu_q + L k,   log q - log p = C + 1/2 (|b + B k|^2 - |k|^2),   d(log q - log p)/d zh = c + D k
+// are polynomials of degree <= 2 in the draw k = (k0, k1): the sums over those samples follow exactly from their five
+// moments S0 = sum k0, S1 = sum k1, S00 = sum k0^2, S01 = sum k0 k1, S11 = sum k1^2, and the loop is
+// Philox + Box-Muller + 5 FMA + the |z| range check.  A sample at |z| >= kRoundTripZ stays out of the moments and is
+// evaluated on its own with the reference's literal float32 round trip (kl_sample_literal, cold).
+__device__ __forceinline__ void dists_of_thread(const float* __restrict__ q, const float* __restrict__ prior, Dist& dq,
+                                                QExtra& ex, Dist& dp) {
+    const float q0 = __ldg(q + 0), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, p4 = 0.f;
+    if (prior != nullptr) {
+        p0 = __ldg(prior + 0);
+        p1 = __ldg(prior + 1);
+        p2 = __ldg(prior + 2);
+        p3 = __ldg(prior + 3);
+        p4 = __ldg(prior + 4);
+    }
+    const float th1 = tanhf(q1), th3 = tanhf(q3), th4 = tanhf(q4);
+    const float ph1 = tanhf(p1), ph3 = tanhf(p3), ph4 = tanhf(p4);
+    dq.mu_o = q0;
+    dq.mu_d = q2;
+    dq.ls_o = th1 * 3.0f - 1.0f;                             // transform_std, model.py:288-290
+    dq.ls_d = th3 * 3.0f - 1.0f;
+    dq.cov = th4 * kExpM2;                                   // transform_offdiag, model.py:292-294
+    dq.inv_o = expf(dq.ls_o * -1.0f);                        // model.py:432-433
+    dq.inv_d = expf(dq.ls_d * -1.0f);
+    dq.inv_bl = (expf(dq.ls_o * -1.0f + dq.ls_d * -1.0f) * dq.cov) * -1.0f;     // model.py:434
+    ex.sd_o = expf(dq.ls_o);
+    ex.sd_d = expf(dq.ls_d);
+    ex.dls_o = 3.0f * (1.0f - th1 * th1);
+    ex.dls_d = 3.0f * (1.0f - th3 * th3);
+    ex.dcov = kExpM2 * (1.0f - th4 * th4);
+    dp.mu_o = p0;
+    dp.mu_d = p2;
+    dp.ls_o = ph1 * 3.0f - 1.0f;
+    dp.ls_d = ph3 * 3.0f - 1.0f;
+    dp.cov = ph4 * kExpM2;
+    dp.inv_o = expf(dp.ls_o * -1.0f);
+    dp.inv_d = expf(dp.ls_d * -1.0f);
+    dp.inv_bl = (expf(dp.ls_o * -1.0f + dp.ls_d * -1.0f) * dp.cov) * -1.0f;
+}
+
+// One sample outside |z| < kRoundTripZ, evaluated as in kl_term with the reference's literal float32 round trip and
+// added to a[0..5]; cold and out of line (Dist / a[] live on the stack only for this call).
+__device__ __noinline__ void kl_sample_literal(const Dist& dq, const QExtra& ex, const Dist& dp, float k0, float k1,
+                                               float* __restrict__ a) {
+    const float z_o = dq.mu_o + k0 * ex.sd_o;                                // model.py:26-27
+    const float z_d = (dq.mu_d + k0 * dq.cov) + k1 * ex.sd_d;                // model.py:29-31
+    const float4 rt = roundtrip_literal(z_o, z_d);
+    float gq_o, gq_d, gp_o, gp_d;
+    const float nq = mvn_nll(dq, rt.x, rt.y, gq_o, gq_d);
+    const float np = mvn_nll(dp, rt.x, rt.y, gp_o, gp_d);
+    const float hz_o = (gp_o - gq_o) * rt.z, hz_d = (gp_d - gq_d) * rt.w;
+    a[0] += hz_o;
+    a[1] += hz_o * k0;
+    a[2] += hz_d;
+    a[3] += hz_d * k1;
+    a[4] += hz_d * k0;
+    a[5] += np - nq;                                                         // log q - log p (model.py:603)
+}
+
+// KL(q || prior) of voxel `index` and its gradient w.r.t. the raw q parameters, computed by the calling lane alone.
+// eps_v: this voxel's explicit draws [n_samples, 2] or nullptr (Philox draws of mc_normal_pair).
+__device__ __forceinline__ KlOut kl_voxel(const Dist& dq, const QExtra& ex, const Dist& dp,
+                                          const float* __restrict__ eps_v, uint64_t seed, uint64_t index,
+                                          int n_samples) {
+    if (n_samples <= 0) return kl_closed_form(dq, ex, dp);
+    float s0 = 0.f, s1 = 0.f, s00 = 0.f, s01 = 0.f, s11 = 0.f;
+    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};              // the literally evaluated samples
+    int n_in = 0;                                             // samples inside the range: they enter through the moments
+#pragma unroll 1
+    for (int s = 0; s < n_samples; s += 2) {
+        const bool two = s + 1 < n_samples;
+        float k0, k1, k2 = 0.f, k3 = 0.f;
+        if (eps_v) {
+            const float2 e = __ldg(reinterpret_cast<const float2*>(eps_v) + s);
+            k0 = e.x;
+            k1 = e.y;
+            if (two) {
+                const float2 e2 = __ldg(reinterpret_cast<const float2*>(eps_v) + s + 1);
+                k2 = e2.x;
+                k3 = e2.y;
+            }
+        } else {
+            const U4 r = mc_words(seed, index, s);
+            mc_box_muller(r.x, r.y, k0, k1);
+            mc_box_muller(r.z, r.w, k2, k3);
+        }
+        const float za = dq.mu_o + k0 * ex.sd_o, zb = (dq.mu_d + k0 * dq.cov) + k1 * ex.sd_d;
+        const float zc = dq.mu_o + k2 * ex.sd_o, zd = (dq.mu_d + k2 * dq.cov) + k3 * ex.sd_d;
+        if (!(fmaxf(fabsf(za), fabsf(zb)) < kRoundTripZ)) {
+            kl_sample_literal(dq, ex, dp, k0, k1, a);
+            k0 = k1 = 0.f;
+        } else {
+            ++n_in;
+        }
+        if (!two) {
+            k2 = k3 = 0.f;
+        } else if (!(fmaxf(fabsf(zc), fabsf(zd)) < kRoundTripZ)) {
+            kl_sample_literal(dq, ex, dp, k2, k3, a);
+            k2 = k3 = 0.f;
+        } else {
+            ++n_in;
+        }
+        s0 += k0;
+        s1 += k1;
+        s00 = fmaf(k0, k0, s00);
+        s01 = fmaf(k0, k1, s01);
+        s11 = fmaf(k1, k1, s11);
+        s0 += k2;
+        s1 += k3;
+        s00 = fmaf(k2, k2, s00);
+        s01 = fmaf(k2, k3, s01);
+        s11 = fmaf(k3, k3, s11);
+    }
+    const float ns = (float)n_samples;
+    {
+        // the n_in samples inside the range: w_p = b + B k, w_q = k (inverse Cholesky factor of q times its factor)
+        const float ni = (float)n_in;
+        const float del_o = dq.mu_o - dp.mu_o, del_d = dq.mu_d - dp.mu_d;
+        const float b0 = del_o * dp.inv_o, b1 = del_d * dp.inv_d + del_o * dp.inv_bl;
+        const float B00 = dp.inv_o * ex.sd_o, B10 = dp.inv_bl * ex.sd_o + dp.inv_d * dq.cov, B11 = dp.inv_d * ex.sd_d;
+        const float u0 = B00 * b0 + B10 * b1, u1 = B11 * b1;
+        const float sum_wp = ni * (b0 * b0 + b1 * b1) + 2.0f * (u0 * s0 + u1 * s1) + (B00 * B00 + B10 * B10) * s00 +
+                             2.0f * (B10 * B11) * s01 + (B11 * B11) * s11;
+        a[5] += ni * ((dp.ls_o + dp.ls_d) - (dq.ls_o + dq.ls_d)) + 0.5f * (sum_wp - (s00 + s11));
+        // d(log q - log p)/d zh = c + D k
+        const float c0 = dp.inv_o * b0 + dp.inv_bl * b1, c1 = dp.inv_d * b1;
+        const float D00 = (dp.inv_o * B00 + dp.inv_bl * B10) - dq.inv_o, D01 = dp.inv_bl * B11 - dq.inv_bl;
+        const float D10 = dp.inv_d * B10, D11 = dp.inv_d * B11 - dq.inv_d;
+        a[0] += ni * c0 + D00 * s0 + D01 * s1;
+        a[1] += c0 * s0 + D00 * s00 + D01 * s01;
+        a[2] += ni * c1 + D10 * s0 + D11 * s1;
+        a[3] += c1 * s1 + D10 * s01 + D11 * s11;
+        a[4] += c1 * s0 + D10 * s00 + D11 * s01;
+    }
+    KlOut o;
+    const float inv_s = 1.0f / ns;
+    o.g[0] = a[0] * inv_s;
+    o.g[1] = a[1] * inv_s * ex.sd_o * ex.dls_o;
+    o.g[2] = a[2] * inv_s;
+    o.g[3] = a[3] * inv_s * ex.sd_d * ex.dls_d;
+    o.g[4] = a[4] * inv_s * ex.dcov;
+    o.kl = a[5] * inv_s;
+    return o;
+}
+
+// kl_loss alone (model.py:654-665): per-voxel KL map and d kl_map[v] / d q[v,:]; one thread per voxel (kl_voxel).
 __global__ void __launch_bounds__(kThreads) k_kl(const float* __restrict__ q, const float* __restrict__ prior,
                                                  const float* __restrict__ mask, const float* __restrict__ eps_kl,
                                                  uint64_t seed, uint64_t offset, int n_samples, int64_t n,
-                                                 float* __restrict__ kl_map, float* __restrict__ grad_q,
-                                                 unsigned long long* __restrict__ work) {
-    const int lane = threadIdx.x & 31;
-    // four voxels per grab from the device work counter (see next_unit)
-    for (int64_t b = next_unit(work, lane), nb; b * 4 < n; b = nb) {
-      nb = next_unit(work, lane);
-      const int64_t v_end = (b + 1) * 4 < n ? (b + 1) * 4 : n;
-      for (int64_t v = b * 4; v < v_end; ++v) {
+                                                 float* __restrict__ kl_map, float* __restrict__ grad_q) {
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += (int64_t)gridDim.x * kThreads) {
         KlOut ko;
         ko.kl = 0.f;
 #pragma unroll
@@ -277,15 +426,15 @@ __global__ void __launch_bounds__(kThreads) k_kl(const float* __restrict__ q, co
         if (mask == nullptr || __ldg(mask + v) > 0.f) {                          // model.py:661
             Dist dq, dp;
             QExtra ex;
-            load_dists(q + v * 5, prior + v * 5, lane, dq, ex, dp);
-            ko = kl_term(dq, ex, dp, eps_kl ? eps_kl + v * n_samples * 2 : nullptr, seed, offset + (uint64_t)v,
-                         n_samples, lane);
+            dists_of_thread(q + v * 5, prior + v * 5, dq, ex, dp);
+            ko = kl_voxel(dq, ex, dp, eps_kl ? eps_kl + v * n_samples * 2 : nullptr, seed, offset + (uint64_t)v,
+                          n_samples);
         }
-        if (lane == 0) kl_map[v] = ko.kl;
-        if (grad_q != nullptr && lane < 5)
-            grad_q[v * 5 + lane] = lane == 0 ? ko.g[0] : lane == 1 ? ko.g[1] : lane == 2 ? ko.g[2]
-                                   : lane == 3 ? ko.g[3] : ko.g[4];
-      }
+        kl_map[v] = ko.kl;
+        if (grad_q != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) grad_q[v * 5 + i] = ko.g[i];
+        }
     }
 }
 
@@ -458,6 +607,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
 // two quadratures run on all 32 lanes (one after the other); the parameter transforms, the sample, the per-tau
 // likelihood, its reductions, the KL (lanes = samples, 16 per pass) and all loads / stores are done once for both
 // voxels, voxel 0 on lanes 0-15 and voxel 1 on lanes 16-31.
+//
+// Work unit = 32 consecutive voxels per warp, in two phases.  Phase A, lanes = voxels: every lane does the per-voxel
+// scalar work of ONE voxel by itself -- parameter transforms, the reparameterised draw (Philox + accurate Box-Muller),
+// sigmoid / OEF / DBV, and the whole KL term (kl_voxel: a compact Philox / Box-Muller / five-moment loop that all lanes
+// of the warp run in lock step) -- and parks 14 floats in the warp's shared-memory slot.  Phase B, the 16 pairs of
+// the unit: quadrature, likelihood, reductions and stores as described above, fed from the slot.
 template <bool HAS_PRIOR>
 __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(const __grid_constant__ QboldParams P,
                                                            const float* __restrict__ q, const float* __restrict__ sigma,
@@ -471,9 +626,13 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
                                                            float* __restrict__ kl_map, double* __restrict__ sums,
                                                            unsigned long long* __restrict__ work) {
     __shared__ SchedSmem ss;
+    // [warp][voxel of the unit][kl, kl gradient 0..4, oef, dbv, d oef/d z_o, d dbv/d z_d, d z_o/d raw1, d z_d/d raw3,
+    //                             d z_d/d raw4, mask, -, -]
+    __shared__ __align__(16) float vox_slot[kThreads / 32][32][16];
     load_sched(P, ss);
     __syncthreads();
     const int lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15, gb = lane & 16;
+    const int wslot = threadIdx.x >> 5;
     const int nt = P.n_tau;
     const bool live = t < nt;
     const int my_col = live ? P.col_of_tau[t] : -1;
@@ -490,13 +649,57 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
     int bad = 0;
 
-    // pairs come from the device work counter (masked volumes: see next_unit); the next index is fetched early
-    for (int64_t pr = next_unit(work, lane), nxt; pr < npairs; pr = nxt) {
-        nxt = next_unit(work, lane);
-        int64_t v = pr * 2 + half;
-        const bool valid = v < n;
-        if (!valid) v = n - 1;                               // odd tail: mirror the last voxel, store nothing
-        const float m = valid ? __ldg(mask + v) : 0.f;
+    // units of 16 pairs come from the device work counter (masked volumes: see next_unit); the next index is fetched early
+    for (int64_t un = next_unit(work, lane), nxt; un * 16 < npairs; un = nxt) {
+      nxt = next_unit(work, lane);
+      {
+          // ---- phase A: voxel un * 32 + lane on this lane
+          const int64_t va = un * 32 + lane;
+          const float ma = va < n ? __ldg(mask + va) : 0.f;
+          float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.4f, 0.05f);
+          float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f), s3 = make_float4(0.f, ma, 0.f, 0.f);
+          if (ma != 0.0f) {
+              Dist dq, dp;
+              QExtra ex;
+              dists_of_thread(q + va * 5, HAS_PRIOR ? prior + va * 5 : nullptr, dq, ex, dp);
+              float e0, e1;
+              if (eps) {
+                  e0 = __ldg(eps + va * 2);
+                  e1 = __ldg(eps + va * 2 + 1);
+              } else {
+                  normal_pair(seed, offset + (uint64_t)va, kStreamReparam, e0, e1);
+              }
+              const Sample sm = draw(dq, ex, e0, e1);
+              s1.z = sm.oef;
+              s1.w = sm.dbv;
+              s2.x = kOefRange * sm.s_o * (1.0f - sm.s_o);
+              s2.y = kDbvRange * sm.s_d * (1.0f - sm.s_d);
+              s2.z = e0 * ex.sd_o * ex.dls_o;
+              s2.w = e1 * ex.sd_d * ex.dls_d;
+              s3.x = e0 * ex.dcov;
+              if (HAS_PRIOR && ma > 0.f) {                   // model.py:661: KL only where mask > 0
+                  const KlOut ko = kl_voxel(dq, ex, dp, eps_kl ? eps_kl + va * kl_samples * 2 : nullptr, seed,
+                                            offset + (uint64_t)va, kl_samples);
+                  s0 = make_float4(ko.kl, ko.g[0], ko.g[1], ko.g[2]);
+                  s1.x = ko.g[3];
+                  s1.y = ko.g[4];
+              }
+          }
+          __syncwarp();                                      // phase B of the previous unit has read the slot
+          float4* slot = reinterpret_cast<float4*>(&vox_slot[wslot][lane][0]);
+          slot[0] = s0;
+          slot[1] = s1;
+          slot[2] = s2;
+          slot[3] = s3;
+          __syncwarp();
+      }
+      const int64_t pr_end = (un + 1) * 16 < npairs ? (un + 1) * 16 : npairs;
+#pragma unroll 1
+      for (int64_t pr = un * 16; pr < pr_end; ++pr) {
+        const int64_t v = pr * 2 + half;
+        const bool valid = v < n;                            // odd tail: the slot holds mask 0 and harmless OEF / DBV
+        const float* slot = &vox_slot[wslot][(int)(pr - un * 16) * 2 + half][0];
+        const float m = slot[13];
         const bool on = (m != 0.0f);
         if (!__any_sync(kFull, on)) {
             // both voxels masked: nll * 0 and where(mask > 0, kl, 0) (model.py:564,661) -> zero loss and gradient
@@ -510,18 +713,7 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
             }
             continue;
         }
-        Dist dq, dp;
-        QExtra ex;
-        load_dists<16>(q + v * 5, HAS_PRIOR ? prior + v * 5 : nullptr, lane, dq, ex, dp);
-        float e0, e1;
-        if (eps) {
-            e0 = __ldg(eps + v * 2);
-            e1 = __ldg(eps + v * 2 + 1);
-        } else {
-            normal_pair(seed, offset + (uint64_t)v, kStreamReparam, e0, e1);
-        }
-        const Sample sm = draw(dq, ex, e0, e1);
-        const VoxelPhys vp = voxel_phys<false>(P, sm.oef, sm.dbv, P.hct);
+        const VoxelPhys vp = voxel_phys<false>(P, slot[6], slot[7], P.hct);
         const float A_mine = qc.tau_ref15 * vp.dw;
         const unsigned on_mask = __ballot_sync(kFull, on);
         float I = 0.f, Dm = 0.f;
@@ -588,30 +780,19 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
         const float g_npd = -s_gp * (inv_npd * inv_npd);
         const float go = s_go * inv_npd + g_npd * n_o;
         const float gd = s_gd * inv_npd + g_npd * n_d;
-        const float gz_o = go * kOefRange * sm.s_o * (1.0f - sm.s_o);
-        const float gz_d = gd * kDbvRange * sm.s_d * (1.0f - sm.s_d);
-        float g0 = gz_o, g1 = gz_o * e0 * ex.sd_o * ex.dls_o, g2 = gz_d;
-        float g3 = gz_d * e1 * ex.sd_d * ex.dls_d, g4 = gz_d * e0 * ex.dcov;
-
-        // ---- KL(q || prior): lanes of the half = samples
-        float kl_v = 0.f;
-        if (HAS_PRIOR) {
-            const KlOut ko = kl_term<16>(dq, ex, dp, eps_kl ? eps_kl + v * kl_samples * 2 : nullptr, seed,
-                                         offset + (uint64_t)v, kl_samples, lane);
-            if (m > 0.f) {                                   // model.py:661
-                kl_v = ko.kl;
-                const float w = kl_weight * inv_mask_sum;
-                g0 += w * ko.g[0];
-                g1 += w * ko.g[1];
-                g2 += w * ko.g[2];
-                g3 += w * ko.g[3];
-                g4 += w * ko.g[4];
-            }
+        const float gz_o = go * slot[8], gz_d = gd * slot[9];
+        // gradient w.r.t. raw q[t], t < 5: likelihood part through the sample + KL part left by phase A
+        float g_mine = 0.f;
+        if (t < 5) {
+            const float gz = t < 2 ? gz_o : gz_d;
+            g_mine = (t == 0 || t == 2) ? gz : gz * slot[9 + t - (t > 1)];   // t = 1, 3, 4 -> slot[10], [11], [12]
+            if (HAS_PRIOR) g_mine += (kl_weight * inv_mask_sum) * slot[1 + t];
         }
+        float kl_v = HAS_PRIOR ? slot[0] : 0.f;
         if (valid) {
-            if (!on) g0 = g1 = g2 = g3 = g4 = 0.f;
+            if (!on) g_mine = 0.f;
             if (live) grad_sigma[v * nt + t] = on ? dnll_dsg * scale : 0.f;
-            if (t < 5) grad_q[v * 5 + t] = t == 0 ? g0 : t == 1 ? g1 : t == 2 ? g2 : t == 3 ? g3 : g4;
+            if (t < 5) grad_q[v * 5 + t] = g_mine;
             if (t == 0) {
                 const float nm = on ? nll_v * m : 0.f;
                 if (!on) kl_v = 0.f;
@@ -623,6 +804,7 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
                 if (!isfinite(nm + kl_v)) bad = 1;
             }
         }
+      }
     }
     if (t == 0 && sums != nullptr && (acc_mask != 0.0 || bad)) {
         atomicAdd(sums + 0, acc_nll);
@@ -1022,7 +1204,7 @@ static int elbo_fused_impl(const QboldParams* p, const float* q, const float* si
             HP ? kl_samples : 0, inv_mask_sum, inv_mask_sum_dev, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, work);        \
     } while (0)
     if (path == kSched && p->full_model && p->n_tau <= 16) {
-        const int64_t wantp = ((n + 1) / 2 + 7) / 8;
+        const int64_t wantp = ((n + 31) / 32 + 7) / 8;                      // a warp takes units of 32 voxels
         if (prior) {
             static int64_t grid_cache = 0;
             const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<true>, INT64_MAX / 64));
@@ -1073,14 +1255,12 @@ extern "C" int qbold_kl(const float* q, const float* prior, const float* mask, c
     if (n < 0 || n_samples < 0 || (n > 0 && (!q || !prior || !kl_map)))
         return fail(QBOLD_EINVAL, "qbold_kl: bad argument");
     if (n == 0) return QBOLD_OK;
-    static int64_t grid_cache = 0;
-    const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_kl, INT64_MAX / 64));
-    const int64_t want = (n + 7) / 8;
-    unsigned long long* work = next_work_counter((cudaStream_t)stream);
-    if (!work) return fail(QBOLD_ECUDA, "qbold_kl: work counter unavailable");
-    k_kl<<<(unsigned)(want < grid ? want : grid), kThreads, 0, (cudaStream_t)stream>>>(q, prior, mask, eps_kl, seed,
-                                                                                      offset, n_samples, n, kl_map,
-                                                                                      grad_q, work);
+    // one thread per voxel; 64-thread granularity spreads a small (masked) batch over all SMs
+    const int64_t blocks = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 64;
+    k_kl<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(q, prior, mask, eps_kl, seed,
+                                                                                        offset, n_samples, n, kl_map,
+                                                                                        grad_q);
     return after_launch("k_kl");
 }
 
