@@ -1098,70 +1098,76 @@ __global__ void __launch_bounds__(kThreads) k_reparam(const float* __restrict__ 
         make_float2(sigmoidf(z_o) * kOefRange + kMinOef, sigmoidf(z_d) * kDbvRange + kMinDbv);
 }
 
-// calculate_means(include_r2p=True, return_stds=True) (model.py:326-343): one warp per voxel,
-// lanes = samples; two-pass mean / mean((s-mean)^2) exactly as the reference forms them.
-__global__ void __launch_bounds__(kThreads) k_posterior_stats(const __grid_constant__ QboldParams P,
-                                                              const float* __restrict__ q,
+// calculate_means(include_r2p=True, return_stds=True) (model.py:326-343): one THREAD per voxel loops over the samples
+// (both samples of every Philox call used, no shuffles).  The reference's two-pass mean / mean((s - mean)^2) is formed
+// in one pass around a pivot (the voxel's first sample): var = mean(d^2) - mean(d)^2 with d = s - pivot, which keeps
+// the cancellation at the level of the two-pass form since |mean(d)| is of the order of the standard deviation.
+__global__ void __launch_bounds__(kThreads) k_posterior_stats(const float dw_k, const float* __restrict__ q,
                                                               const float* __restrict__ eps, uint64_t seed,
                                                               uint64_t offset, int n_samples, int64_t n,
-                                                              float* __restrict__ mean3, float* __restrict__ var3,
-                                                              unsigned long long* __restrict__ work) {
-    const int lane = threadIdx.x & 31;
-    constexpr int kMaxPer = 8;   // up to 256 samples per voxel held in registers
+                                                              float* __restrict__ mean3, float* __restrict__ var3) {
     const float inv_n = 1.0f / (float)n_samples;
-    for (int64_t bt = next_unit(work, lane), nbt; bt * 4 < n; bt = nbt) {        // four voxels per grab
-      nbt = next_unit(work, lane);
-      const int64_t v_end = (bt + 1) * 4 < n ? (bt + 1) * 4 : n;
-      for (int64_t v = bt * 4; v < v_end; ++v) {
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += (int64_t)gridDim.x * kThreads) {
         Dist dq, dp;
         QExtra ex;
-        load_dists(q + v * 5, nullptr, lane, dq, ex, dp);
-        float so[kMaxPer], sd[kMaxPer], sr[kMaxPer];
-        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < kMaxPer; ++i) {
-            const int sidx = lane + 32 * i;
-            so[i] = sd[i] = sr[i] = 0.f;
-            if (sidx < n_samples) {
-                float k0, k1;
-                if (eps) {
-                    const float2 e = __ldg(reinterpret_cast<const float2*>(eps) + (v * n_samples + sidx));
-                    k0 = e.x;
-                    k1 = e.y;
-                } else {
-                    mc_normal_pair(seed, offset + (uint64_t)v, sidx, k0, k1);
+        dists_of_thread(q + v * 5, nullptr, dq, ex, dp);
+        float p_o = 0.f, p_d = 0.f, p_r = 0.f;                                   // pivots
+        float a_o = 0.f, a_d = 0.f, a_r = 0.f, b_o = 0.f, b_d = 0.f, b_r = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < n_samples; s += 2) {
+            float k0, k1, k2 = 0.f, k3 = 0.f;
+            const bool two = s + 1 < n_samples;
+            if (eps) {
+                const float2 e = __ldg(reinterpret_cast<const float2*>(eps) + (v * n_samples + s));
+                k0 = e.x;
+                k1 = e.y;
+                if (two) {
+                    const float2 e2 = __ldg(reinterpret_cast<const float2*>(eps) + (v * n_samples + s + 1));
+                    k2 = e2.x;
+                    k3 = e2.y;
                 }
-                const Sample ks = draw(dq, ex, k0, k1);
-                so[i] = ks.oef;
-                sd[i] = ks.dbv;
-                sr[i] = (P.dw_k * ks.oef) * ks.dbv;                              // model.py:516-525
-                a[0] += so[i];
-                a[1] += sd[i];
-                a[2] += sr[i];
+            } else {
+                const U4 r = mc_words(seed, offset + (uint64_t)v, s);
+                mc_box_muller(r.x, r.y, k0, k1);
+                mc_box_muller(r.z, r.w, k2, k3);
+            }
+            const Sample sa = draw(dq, ex, k0, k1);
+            const float ra = (dw_k * sa.oef) * sa.dbv;                           // model.py:516-525
+            if (s == 0) {
+                p_o = sa.oef;
+                p_d = sa.dbv;
+                p_r = ra;
+            }
+            float d = sa.oef - p_o;
+            a_o += d;
+            b_o = fmaf(d, d, b_o);
+            d = sa.dbv - p_d;
+            a_d += d;
+            b_d = fmaf(d, d, b_d);
+            d = ra - p_r;
+            a_r += d;
+            b_r = fmaf(d, d, b_r);
+            if (two) {
+                const Sample sb = draw(dq, ex, k2, k3);
+                const float rb = (dw_k * sb.oef) * sb.dbv;
+                d = sb.oef - p_o;
+                a_o += d;
+                b_o = fmaf(d, d, b_o);
+                d = sb.dbv - p_d;
+                a_d += d;
+                b_d = fmaf(d, d, b_d);
+                d = rb - p_r;
+                a_r += d;
+                b_r = fmaf(d, d, b_r);
             }
         }
-        float tot = butterfly8(a, lane);
-        const float m_o = __shfl_sync(kFull, tot, butterfly8_src_lane(0)) * inv_n;
-        const float m_d = __shfl_sync(kFull, tot, butterfly8_src_lane(1)) * inv_n;
-        const float m_r = __shfl_sync(kFull, tot, butterfly8_src_lane(2)) * inv_n;
-        float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < kMaxPer; ++i) {
-            if (lane + 32 * i < n_samples) {
-                b[0] += (so[i] - m_o) * (so[i] - m_o);
-                b[1] += (sd[i] - m_d) * (sd[i] - m_d);
-                b[2] += (sr[i] - m_r) * (sr[i] - m_r);
-            }
-        }
-        tot = butterfly8(b, lane);
-        const float v_o = __shfl_sync(kFull, tot, butterfly8_src_lane(0)) * inv_n;
-        const float v_d = __shfl_sync(kFull, tot, butterfly8_src_lane(1)) * inv_n;
-        const float v_r = __shfl_sync(kFull, tot, butterfly8_src_lane(2)) * inv_n;
-        if (lane < 3) {
-            mean3[v * 3 + lane] = lane == 0 ? m_o : lane == 1 ? m_d : m_r;
-            var3[v * 3 + lane] = lane == 0 ? v_o : lane == 1 ? v_d : v_r;
-        }
-      }
+        const float m_o = a_o * inv_n, m_d = a_d * inv_n, m_r = a_r * inv_n;
+        mean3[v * 3 + 0] = p_o + m_o;
+        mean3[v * 3 + 1] = p_d + m_d;
+        mean3[v * 3 + 2] = p_r + m_r;
+        var3[v * 3 + 0] = fmaxf(b_o * inv_n - m_o * m_o, 0.f);
+        var3[v * 3 + 1] = fmaxf(b_d * inv_n - m_d * m_d, 0.f);
+        var3[v * 3 + 2] = fmaxf(b_r * inv_n - m_r * m_r, 0.f);
     }
 }
 
@@ -1330,12 +1336,9 @@ extern "C" int qbold_posterior_stats(const QboldParams* p, const float* q, const
     if (n_samples < 1 || n_samples > 256) return fail(QBOLD_EINVAL, "qbold_posterior_stats: n_samples must be in [1,256]");
     if (n < 0 || (n > 0 && (!q || !mean3 || !var3))) return fail(QBOLD_EINVAL, "qbold_posterior_stats: null pointer");
     if (n == 0) return QBOLD_OK;
-    static int64_t grid_cache = 0;
-    const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_posterior_stats, INT64_MAX / 64));
-    const int64_t want = (n + 7) / 8;
-    unsigned long long* work = next_work_counter((cudaStream_t)stream);
-    if (!work) return fail(QBOLD_ECUDA, "qbold_posterior_stats: work counter unavailable");
-    k_posterior_stats<<<(unsigned)(want < grid ? want : grid), kThreads, 0, (cudaStream_t)stream>>>(
-        *p, q, eps, seed, offset, n_samples, n, mean3, var3, work);
+    const int64_t blocks = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 64;
+    k_posterior_stats<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(
+        p->dw_k, q, eps, seed, offset, n_samples, n, mean3, var3);
     return after_launch("k_posterior_stats");
 }

@@ -320,7 +320,7 @@ def _as_flat(img):
 _CONV_ARGS = ((1, 1), (1, 1), (1, 1))                 # stride, padding, dilation
 # weight gradient of the 3x3 convolutions on tcgen05 (qbold_conv_wgrad) instead of cuDNN's wgrad kernel; TF32, so only
 # when TF32 convolutions are allowed
-_CONV_WGRAD_TC = os.environ.get('QBOLD_CONV_WGRAD_TC', '0') == '1'
+_CONV_WGRAD_TC = os.environ.get('QBOLD_CONV_WGRAD_TC', '1') == '1'
 
 
 def _conv_backward(g_flat, x_flat, w2, dims):
