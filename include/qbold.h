@@ -356,6 +356,24 @@ int64_t qbold_colsum_workspace_floats(void);
 int qbold_relu_bwd_colsum(const float* g, const float* y, const float* addend, int64_t n, int32_t channels, float* out,
                           float* colsum, int32_t accumulate, float* workspace, void* stream);
 
+/* One Dense layer as a persistent TMA -> tcgen05 (kind::tf32, fp32 accumulate in TMEM) -> TMA pipeline, for the
+ * encoder's training passes (reference create_layer, model.py:115-120):
+ *     y[n, n_out] = act(x[n, n_in] B + bias) (+ addend[n, n_out])
+ * transpose = 0: B = w^T with w [n_out, n_in] (forward); transpose = 1: B = w with w [n_in, n_out] (input gradient: the
+ * stored weight is read MN-major, no transposed copy).  bias, addend may be NULL; addend may alias y (beta = 1
+ * accumulation in place).  n_in, n_out: multiples of 4 in [4, 64]; all matrices dense row-major, 16-byte aligned.
+ * status (may be NULL) is set non-zero if a completion barrier timed out. */
+int qbold_dense_tma(const float* x, const float* w, const float* bias, const float* addend, int32_t n_in, int32_t n_out,
+                    int32_t transpose, int32_t relu, int64_t n, float* y, int32_t* status, void* stream);
+
+/* Weight / bias gradient of a Dense layer on the same machinery: dw[n_out, n_in] (+)= g^T x, db[n_out] (+)= column sums
+ * of g (db may be NULL); g [n, n_out], x [n, n_in] read MN-major straight from memory by TMA (the contraction runs over
+ * the rows), one TMEM accumulator per SM, per-SM partials in `workspace` (qbold_dense_wgrad_tma_workspace_floats()
+ * floats) summed in a fixed order.  n_in, n_out: multiples of 4 in [4, 64]. */
+int64_t qbold_dense_wgrad_tma_workspace_floats(void);
+int qbold_dense_wgrad_tma(const float* g, int32_t n_out, const float* x, int32_t n_in, int64_t n, float* dw, float* db,
+                          int32_t accumulate, float* workspace, int32_t* status, void* stream);
+
 /* Weight gradient of the encoder's 3x3x1 convolutions (create_block, model.py:152,156; padding 'same') on tcgen05
  * tensor cores (kind::tf32, fp32 accumulate in TMEM): dw[cg, cx, 3, 3] (+)= sum_v g[v, :]^T x[v + (kx-1, ky-1), :]
  * for activations laid out [n_images, nx, ny, channels] (the encoder's z-outer layout: n_images = B * Z).

@@ -58,6 +58,64 @@ def _dense_tc(x, mask, w, bias, n_in, n_out, transpose, relu):
     return y
 
 
+# The TMA-fed pipeline kernel (qbold_dense_tma): 48 us per 524 288 x 60 layer against 67 us for cuBLAS, 67 us against
+# 114 us with the in-place accumulation of the backward pass -- the default for the training passes in TF32 mode.
+USE_DENSE_TMA = os.environ.get('QBOLD_DENSE_TMA', '1') == '1'
+
+
+def _tma_ok(n_in, n_out, *tensors):
+    return (USE_DENSE_TMA and torch.backends.cuda.matmul.allow_tf32 and n_in % 4 == 0 and n_out % 4 == 0
+            and 4 <= n_in <= 64 and 4 <= n_out <= 64
+            and all(t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0)
+                    for t in tensors))
+
+
+def _dense_tma(x, w, bias=None, addend=None, transpose=False, relu=False):
+    """act(x w^T + bias) (transpose=False, w [n_out, n_in]) or x w (+ addend, in place into addend) (transpose=True,
+    w [n_in, n_out]) through qbold_dense_tma.  Callers check _tma_ok first."""
+    from . import _lib
+    from ._lib import check, dptr, stream_ptr
+    n = x.shape[0]
+    n_in = x.shape[1]
+    n_out = w.shape[1] if transpose else w.shape[0]
+    dev = x.device
+    y = addend if addend is not None else torch.empty((n, n_out), dtype=torch.float32, device=dev)
+    status = _TC_STATUS.get(dev)
+    if status is None:
+        status = _TC_STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().qbold_dense_tma(dptr(x), dptr(w), dptr(bias, allow_none=True), dptr(addend, allow_none=True), n_in,
+                                         n_out, int(transpose), int(relu), n, dptr(y), dptr(status, torch.int32),
+                                         stream_ptr(dev)))
+    return y
+
+
+def _linear_relu(x, w, b):
+    """relu(x w^T + b) for the block's shared pointwise layer."""
+    if _tma_ok(w.shape[1], w.shape[0], x, w, b):
+        return _dense_tma(x, w, b, relu=True)
+    return torch._addmm_activation(b, x, w.t(), use_gelu=False)
+
+
+def _linear(x, w, b):
+    if _tma_ok(w.shape[1], w.shape[0], x, w, b):
+        return _dense_tma(x, w, b)
+    return torch.addmm(b, x, w.t())
+
+
+def _addmm_(acc, g, w):
+    """acc += g w (w [n_out, n_in], the stored weight: an input gradient accumulated in place)."""
+    if _tma_ok(w.shape[0], w.shape[1], acc, g, w):
+        return _dense_tma(g, w, addend=acc, transpose=True)
+    return acc.addmm_(g, w)
+
+
+def _mm(g, w):
+    if _tma_ok(w.shape[0], w.shape[1], g, w):
+        return _dense_tma(g, w, transpose=True)
+    return g @ w
+
+
 def tensor_core_status(device):
     """Non-zero if a tcgen05 completion barrier of the Dense kernels ever timed out on `device` (checked lazily: the
     training loop never synchronises on it)."""
@@ -83,6 +141,8 @@ class _DenseFn(torch.autograd.Function):
                                                            dptr(y), stream_ptr(x.device)))
         elif USE_DENSE_TC and _tc_ok(n_in, n_out, x):
             y = _dense_tc(x, None, weight, bias, n_in, n_out, False, relu)
+        elif _tma_ok(n_in, n_out, x, weight, bias):
+            y = _dense_tma(x, weight, bias, relu=relu)
         elif relu:                                            # bias + ReLU in the GEMM epilogue (cuBLASLt)
             y = torch._addmm_activation(bias, x, weight.t(), use_gelu=False)
         else:
@@ -119,7 +179,7 @@ class _DenseFn(torch.autograd.Function):
             if y is not None:                                 # library path: materialise g * relu' once for both uses
                 g, mask = torch.ops.aten.threshold_backward(g, y, 0.0), None
             if ctx.needs_input_grad[0]:
-                gx = g @ weight
+                gx = _mm(g, weight)
         lib = _lib.lib()
         if not torch.backends.cuda.matmul.allow_tf32:         # strict float32 requested: qbold_dense_wgrad is TF32 mma
             gm = g if mask is None else torch.ops.aten.threshold_backward(g, mask, 0.0)
@@ -294,12 +354,22 @@ def _wgrad(g, x, accumulate_into=None):
             accumulate_into[1].add_(db)
             return accumulate_into
         return dw, db
-    ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
     if accumulate_into is None:
         dw = torch.empty((n_out, n_in), dtype=torch.float32, device=dev)
         db = torch.empty(n_out, dtype=torch.float32, device=dev)
     else:
         dw, db = accumulate_into
+    if _tma_ok(n_in, n_out, g, x):                          # TMA-fed tcgen05 kernel (MN-major operands)
+        ws = torch.empty(int(lib.qbold_dense_wgrad_tma_workspace_floats()), dtype=torch.float32, device=dev)
+        status = _TC_STATUS.get(dev)
+        if status is None:
+            status = _TC_STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.qbold_dense_wgrad_tma(dptr(g), n_out, dptr(x), n_in, x.shape[0], dptr(dw), dptr(db),
+                                            0 if accumulate_into is None else 1, dptr(ws), dptr(status, torch.int32),
+                                            stream_ptr(dev)))
+        return dw, db
+    ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.qbold_dense_wgrad(dptr(g), None, n_out, dptr(x), n_in, x.shape[0], dptr(dw), dptr(db),
                                     0 if accumulate_into is None else 1, dptr(ws), stream_ptr(dev)))
@@ -357,14 +427,14 @@ class _BlockFn(torch.autograd.Function):
         from ._lib import check, dptr, stream_ptr
         n, c = net2.shape
         dev = net2.device
-        skip = torch._addmm_activation(b_p, net2, w_p.t(), use_gelu=False)
-        out1 = skip if same_input else torch._addmm_activation(b_p, net1, w_p.t(), use_gelu=False)
+        skip = _linear_relu(net2, w_p, b_p)
+        out1 = skip if same_input else _linear_relu(net1, w_p, b_p)
         wa2 = w_a.squeeze(-1).contiguous(memory_format=torch.channels_last)
         wb2 = w_b.squeeze(-1).contiguous(memory_format=torch.channels_last)
         c1 = torch.cudnn_convolution_relu(_as_images(a0, dims), wa2, b_a, *_CONV_ARGS, 1)          # conv + bias + ReLU
         r0 = F.conv2d(c1, wb2, None, padding=1)                                                    # bias folded below
         c1f, r0f = _as_flat(c1), _as_flat(r0)
-        z = torch.addmm(torch.addmv(b_g, w_g, b_b), r0f, w_g.t())                                  # W_g (r0 + b_b) + b_g
+        z = _linear(r0f, w_g, torch.addmv(b_g, w_g, b_b))                                          # W_g (r0 + b_b) + b_g
         out2 = torch.empty_like(r0f)
         out2_relu = torch.empty_like(r0f) if want_relu_out else None
         with torch.cuda.device(dev):
@@ -394,7 +464,7 @@ class _BlockFn(torch.autograd.Function):
         # gate Dense: z = W_g (r0 + b_b) + b_g
         dw_g, db_g = _wgrad(d_z, r0f)
         dw_g = torch.addr(dw_g, db_g, b_b)                                   # + colsum(d_z) (x) b_b
-        d_r.addmm_(d_z, w_g)                                                 # total gradient of r = r0 + b_b, in place
+        _addmm_(d_r, d_z, w_g)                                               # total gradient of r = r0 + b_b, in place
         db_b = _colsum(d_r)
         # second convolution (no bias of its own): input gradient + weight gradient
         wa2 = w_a.squeeze(-1).contiguous(memory_format=torch.channels_last)
@@ -411,14 +481,14 @@ class _BlockFn(torch.autograd.Function):
         if ctx.same_input:
             g_p = _relu_bwd(d_out1.contiguous(), out1, addend=d_skip)        # both uses of the same activation
             dw_p, db_p = _wgrad(g_p, net2)
-            d_net2.addmm_(g_p, w_p)
+            _addmm_(d_net2, g_p, w_p)
             d_net1 = None
         else:
             g_1 = _relu_bwd(d_out1.contiguous(), out1)
             dw_p, db_p = _wgrad(d_skip, net2)
             _wgrad(g_1, net1, accumulate_into=(dw_p, db_p))
-            d_net2.addmm_(d_skip, w_p)
-            d_net1 = g_1 @ w_p
+            _addmm_(d_net2, d_skip, w_p)
+            d_net1 = _mm(g_1, w_p)
         return (d_net1, d_net2, None, dw_p, db_p, dw_a.unsqueeze(-1), db_a, dw_b.unsqueeze(-1), db_b, dw_g, db_g,
                 None, None, None, None, None)
 

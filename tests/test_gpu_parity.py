@@ -1594,3 +1594,57 @@ def test_conv_weight_gradient_tensor_core_kernel(qb, dev, bz, nx, ny, cg, cx):
     with pytest.raises(qb.QboldError):
         check(lib().qbold_conv_wgrad(dptr(g.reshape(-1, cg)), 6, dptr(x.reshape(-1, cx)), cx, bz, nx, ny, dptr(dw), 0, dptr(ws),
                                      None, stream_ptr(dev)))
+
+
+@pytest.mark.parametrize('n,n_in,n_out,transpose,relu,add', [(1000, 60, 60, 0, 1, 0), (4097, 60, 60, 1, 0, 1), (129, 32, 64, 0, 0, 1),
+                                                            (1, 64, 60, 1, 1, 0), (70000, 60, 60, 0, 0, 0), (300, 8, 12, 0, 1, 0),
+                                                            (555, 12, 44, 1, 0, 1)])
+def test_dense_tma_pipeline_kernel(qb, dev, n, n_in, n_out, transpose, relu, add):
+    """qbold_dense_tma (TMA -> tcgen05 kind::tf32 -> TMA store; forward with the stored weight K-major, input gradient
+    with the same rows read MN-major; bias, ReLU and the in-place beta = 1 addend fused) against float64; TF32 operand
+    rounding sets the bar."""
+    from qbold_vi_b200._lib import check, dptr, lib, stream_ptr
+    gen = torch.Generator(device=dev).manual_seed(n + n_in)
+    x = torch.randn(n, n_in, device=dev, generator=gen)
+    w = torch.randn((n_in, n_out) if transpose else (n_out, n_in), device=dev, generator=gen) * 0.3
+    bias = None if transpose else torch.randn(n_out, device=dev, generator=gen)
+    y = torch.randn(n, n_out, device=dev, generator=gen) if add else torch.full((n, n_out), float('nan'), device=dev)
+    ref = x.double() @ (w.double() if transpose else w.double().t())
+    if bias is not None:
+        ref = ref + bias.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    if add:
+        ref = ref + y.double()
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib().qbold_dense_tma(dptr(x), dptr(w), dptr(bias, allow_none=True), dptr(y) if add else None, n_in, n_out, transpose,
+                                relu, n, dptr(y), dptr(status, torch.int32), stream_ptr(dev)))
+    assert int(status.item()) == 0
+    scale = float(ref.abs().max()) + 1e-6
+    assert float((y.double() - ref).abs().max()) <= 2e-3 * scale
+    with pytest.raises(qb.QboldError):
+        check(lib().qbold_dense_tma(dptr(x), dptr(w), None, None, 6, n_out, 0, 0, n, dptr(y), None, stream_ptr(dev)))
+
+
+@pytest.mark.parametrize('n,n_in,n_out', [(1000, 60, 60), (70001, 60, 60), (1, 64, 64), (129, 12, 44), (5000, 32, 8)])
+def test_dense_weight_gradient_tma_kernel(qb, dev, n, n_in, n_out):
+    """qbold_dense_wgrad_tma (g and x read MN-major by TMA, contraction over the rows on tcgen05, bias gradient from an
+    MMA against a tile of ones) against float64, plus accumulation and determinism."""
+    from qbold_vi_b200._lib import check, dptr, lib, stream_ptr
+    gen = torch.Generator(device=dev).manual_seed(n + n_out)
+    x = torch.randn(n, n_in, device=dev, generator=gen)
+    g = torch.randn(n, n_out, device=dev, generator=gen)
+    dw = torch.full((n_out, n_in), float('nan'), device=dev)
+    db = torch.full((n_out,), float('nan'), device=dev)
+    ws = torch.empty(int(lib().qbold_dense_wgrad_tma_workspace_floats()), device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    args = (dptr(g), n_out, dptr(x), n_in, n)
+    check(lib().qbold_dense_wgrad_tma(*args, dptr(dw), dptr(db), 0, dptr(ws), dptr(status, torch.int32), stream_ptr(dev)))
+    assert int(status.item()) == 0
+    ref_w, ref_b = g.double().t() @ x.double(), g.double().sum(0)
+    scale = float(ref_w.abs().max()) + float(n ** 0.5) * 1e-3
+    assert float((dw.double() - ref_w).abs().max()) <= 1.5e-3 * scale
+    assert float((db.double() - ref_b).abs().max()) <= 1.5e-3 * (float(ref_b.abs().max()) + float(n ** 0.5) * 1e-3)
+    dw2, db2 = dw.clone(), db.clone()
+    check(lib().qbold_dense_wgrad_tma(*args, dptr(dw2), dptr(db2), 1, dptr(ws), dptr(status, torch.int32), stream_ptr(dev)))
+    assert torch.allclose(dw2, 2 * dw, rtol=1e-6, atol=1e-6) and torch.allclose(db2, 2 * db, rtol=1e-6, atol=1e-6)
