@@ -356,6 +356,12 @@ int64_t qbold_colsum_workspace_floats(void);
 int qbold_relu_bwd_colsum(const float* g, const float* y, const float* addend, int64_t n, int32_t channels, float* out,
                           float* colsum, int32_t accumulate, float* workspace, void* stream);
 
+/* normalise_data (model.py:97-113) fused with the training path's layout change: raw images data [b, nx, ny, nz, n_tau]
+ * -> out [b, nz, nx, ny, tp] = log(clip(d, 1e-2, 1e8) / reference), tp = n_tau rounded up to a multiple of 4, padding
+ * columns zero.  reference = the clipped tau = 0 image (se_idx) or the mean of the three clipped images around it. */
+int qbold_normalise_zouter(const float* data, int64_t b, int32_t nx, int32_t ny, int32_t nz, int32_t n_tau, int32_t se_idx,
+                           int32_t multi_image_normalisation, float* out, void* stream);
+
 /* One Dense layer as a persistent TMA -> tcgen05 (kind::tf32, fp32 accumulate in TMEM) -> TMA pipeline, for the
  * encoder's training passes (reference create_layer, model.py:115-120):
  *     y[n, n_out] = act(x[n, n_in] B + bias) (+ addend[n, n_out])

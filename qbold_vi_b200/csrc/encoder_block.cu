@@ -135,6 +135,43 @@ __global__ void __launch_bounds__(1024) k_colsum_finish(const float* __restrict_
     }
 }
 
+// normalise_data (model.py:97-113) fused with the layout change of the training path: raw images [B, X, Y, Z, T] ->
+// log(clip(d, 1e-2, 1e8) / reference) as z-outer rows [B, Z, X, Y, Tp], Tp = T rounded up to a multiple of 4 (zero
+// padded, so the rows are 16-byte aligned operands of the TMA-fed first Dense layer).  A CTA transposes a 32 (y) x 32 (z)
+// tile through shared memory: reads run along z (the input's fastest spatial axis), writes along y (the output's).
+__global__ void __launch_bounds__(256) k_normalise_zouter(const float* __restrict__ data, int X, int Y, int Z, int T,
+                                                         int Tp, int se, int multi, float* __restrict__ out) {
+    extern __shared__ float tile[];                                         // [32 y][32 T + 1]
+    const int zt = (Z + 31) / 32, yt = (Y + 31) / 32;
+    int blk = blockIdx.x;
+    const int z0 = (blk % zt) * 32;
+    blk /= zt;
+    const int y0 = (blk % yt) * 32;
+    blk /= yt;
+    const int x = blk % X, b = blk / X;
+    const int nz = min(32, Z - z0), ny = min(32, Y - y0);
+    const int run = nz * T, pitch = 32 * T + 1;
+    for (int e = threadIdx.x; e < ny * run; e += blockDim.x) {
+        const int y = e / run, r = e - y * run;
+        tile[y * pitch + r] = __ldg(data + ((((int64_t)b * X + x) * Y + (y0 + y)) * Z + z0) * T + r);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= ny) return;
+    for (int z = warp; z < nz; z += 8) {
+        const float* src = tile + lane * pitch + z * T;
+        float ref;
+        if (multi) {
+            ref = (fminf(fmaxf(src[se - 1], 1e-2f), 1e8f) + fminf(fmaxf(src[se], 1e-2f), 1e8f) +
+                   fminf(fmaxf(src[se + 1], 1e-2f), 1e8f)) / 3.0f;
+        } else {
+            ref = fminf(fmaxf(src[se], 1e-2f), 1e8f);
+        }
+        float* dst = out + ((((int64_t)b * Z + (z0 + z)) * X + x) * Y + (y0 + lane)) * Tp;
+        for (int t = 0; t < Tp; ++t) dst[t] = t < T ? logf(fminf(fmaxf(src[t], 1e-2f), 1e8f) / ref) : 0.f;
+    }
+}
+
 }  // namespace qb
 
 using namespace qb;
@@ -220,4 +257,25 @@ extern "C" int qbold_relu_bwd_colsum(const float* g, const float* y, const float
         return after_launch("k_colsum_finish");
     }
     return QBOLD_OK;
+}
+
+extern "C" int qbold_normalise_zouter(const float* data, int64_t b, int32_t nx, int32_t ny, int32_t nz, int32_t n_tau,
+                                      int32_t se_idx, int32_t multi_image_normalisation, float* out, void* stream) {
+    if (b < 0 || nx < 1 || ny < 1 || nz < 1 || n_tau < 1 || n_tau > 64 || se_idx < 0 || se_idx >= n_tau ||
+        (multi_image_normalisation && (se_idx < 1 || se_idx + 1 >= n_tau)))
+        return fail(QBOLD_EINVAL, "qbold_normalise_zouter: bad shape or se_idx");
+    if (b == 0) return QBOLD_OK;
+    if (!data || !out) return fail(QBOLD_EINVAL, "qbold_normalise_zouter: null pointer");
+    const int64_t blocks = b * nx * ((ny + 31) / 32) * ((nz + 31) / 32);
+    if (blocks > 0x7fffffffLL) return fail(QBOLD_EUNSUPPORTED, "qbold_normalise_zouter: volume too large for one launch");
+    const int tp = (n_tau + 3) & ~3;
+    const size_t smem = (size_t)32 * (32 * n_tau + 1) * sizeof(float);
+    if (smem > 48 * 1024) {
+        int rc = cuda_check(cudaFuncSetAttribute(k_normalise_zouter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(k_normalise_zouter)");
+        if (rc) return rc;
+    }
+    k_normalise_zouter<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(data, nx, ny, nz, n_tau, tp, se_idx,
+                                                                              multi_image_normalisation, out);
+    return after_launch("k_normalise_zouter");
 }

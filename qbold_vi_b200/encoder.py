@@ -132,7 +132,9 @@ class _DenseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu=False):
         n_out, n_in = weight.shape
-        if not relu and _small_ok(n_in, n_out, x, weight):
+        if not relu and n_out >= 8 and _tma_ok(n_in, n_out, x, weight, bias):      # e.g. the 16-output double head
+            y = _dense_tma(x, weight, bias)
+        elif not relu and _small_ok(n_in, n_out, x, weight):
             from . import _lib
             from ._lib import check, dptr, stream_ptr
             y = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=x.device)
@@ -166,7 +168,10 @@ class _DenseFn(torch.autograd.Function):
         n_out, n_in = weight.shape
         dev = x.device
         gx, mask = None, y
-        if y is None and _small_ok(n_in, n_out, weight):
+        if y is None and n_out >= 8 and _tma_ok(n_out, n_in, g, weight):
+            if ctx.needs_input_grad[0]:
+                gx = _dense_tma(g, weight, transpose=True)
+        elif y is None and _small_ok(n_in, n_out, weight):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty((x.shape[0], n_in), dtype=torch.float32, device=dev)
                 with torch.cuda.device(dev):
@@ -184,6 +189,9 @@ class _DenseFn(torch.autograd.Function):
         if not torch.backends.cuda.matmul.allow_tf32:         # strict float32 requested: qbold_dense_wgrad is TF32 mma
             gm = g if mask is None else torch.ops.aten.threshold_backward(g, mask, 0.0)
             return gx, gm.t() @ x, gm.sum(0), None
+        if mask is None and _tma_ok(n_in, n_out, g, x):
+            dw, db = _wgrad(g, x)
+            return gx, dw, db, None
         # per-call scratch from the caching allocator (stream-ordered, so concurrent backward passes cannot share it)
         ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
         dw = torch.empty_like(weight)
@@ -592,9 +600,9 @@ class Encoder(nn.Module):
         return torch.cat([out, torch.exp(self.hyper_prior).expand(out.shape[:-1] + (4,))], -1)     # model.py:205
 
     def forward(self, data):
+        if data.dim() == 5 and _fast_block_ok(self.blocks[0], data):
+            return self._forward_fused_blocks(data)
         x = self.normalise_data(data)
-        if x.dim() == 5 and _fast_block_ok(self.blocks[0], x):
-            return self._forward_fused_blocks(x)
         h = dense(self.first, x, True) if self.act is F.relu else self.act(dense(self.first, x))
         net1 = net2 = h
         for blk in self.blocks:
@@ -602,12 +610,28 @@ class Encoder(nn.Module):
         return (self._with_hyper_prior(dense(self.final, net1)), dense(self.final, net2),
                 torch.exp(dense(self.im_sigma, net2)))
 
-    def _forward_fused_blocks(self, x):
+    def _forward_fused_blocks(self, data):
         """Training path on CUDA (TF32, ReLU, channel-wise gating): z-outer layout + one fused autograd node per block."""
-        b, nx, ny, nz, _ = x.shape
+        b, nx, ny, nz, n_tau = data.shape
         dims = (b * nz, nx, ny)
-        xt = x.permute(0, 3, 1, 2, 4).reshape(b * nz * nx * ny, x.shape[-1])          # [B,Z,X,Y,n_tau]: 44 B/voxel copy
-        h = dense(self.first, xt, True)
+        tp = (n_tau + 3) & ~3
+        if (not data.requires_grad and n_tau <= 64 and data.numel() > 0
+                and _tma_ok(tp, self.first.out_features, self.first.weight, self.first.bias)):
+            # normalise_data + the move to z-outer rows in ONE pass (rows padded to a multiple of 4 images: 16-byte
+            # aligned operands), then the first Dense layer on the TMA-fed tensor-core kernel with zero-padded weights
+            from . import _lib
+            from ._lib import check, dptr, stream_ptr
+            src = data.contiguous()
+            xt = torch.empty((b * nz * nx * ny, tp), dtype=torch.float32, device=data.device)
+            with torch.cuda.device(data.device):
+                check(_lib.lib().qbold_normalise_zouter(dptr(src), b, nx, ny, nz, n_tau, self.se_idx,
+                                                        int(self.multi_image_normalisation), dptr(xt),
+                                                        stream_ptr(data.device)))
+            h = _DenseFn.apply(xt, F.pad(self.first.weight, (0, tp - n_tau)), self.first.bias, True)
+        else:
+            x = self.normalise_data(data)
+            xt = x.permute(0, 3, 1, 2, 4).reshape(b * nz * nx * ny, n_tau)            # [B,Z,X,Y,n_tau]: 44 B/voxel copy
+            h = dense(self.first, xt, True)
         net1 = net2 = a0 = h
         for i, blk in enumerate(self.blocks):
             last = i + 1 == len(self.blocks)

@@ -1648,3 +1648,21 @@ def test_dense_weight_gradient_tma_kernel(qb, dev, n, n_in, n_out):
     dw2, db2 = dw.clone(), db.clone()
     check(lib().qbold_dense_wgrad_tma(*args, dptr(dw2), dptr(db2), 1, dptr(ws), dptr(status, torch.int32), stream_ptr(dev)))
     assert torch.allclose(dw2, 2 * dw, rtol=1e-6, atol=1e-6) and torch.allclose(db2, 2 * db, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('shape,multi', [((2, 5, 7, 9, 11), False), ((1, 3, 40, 33, 11), True), ((1, 2, 64, 64, 24), False)])
+def test_normalise_zouter_kernel(qb, dev, shape, multi):
+    """qbold_normalise_zouter = Encoder.normalise_data (model.py:97-113) + the permute to z-outer rows, zero padded to a
+    multiple of 4 images."""
+    from qbold_vi_b200._lib import check, dptr, lib, stream_ptr
+    from qbold_vi_b200.encoder import Encoder
+    b, nx, ny, nz, t = shape
+    gen = torch.Generator(device=dev).manual_seed(sum(shape))
+    data = torch.rand(shape, device=dev, generator=gen) * 3.0 - 0.2              # some values below the 1e-2 clip
+    enc = Encoder(no_ip_images=t, se_idx=2, multi_image_normalisation=multi)
+    ref = enc.normalise_data(data).permute(0, 3, 1, 2, 4).reshape(-1, t)
+    tp = (t + 3) & ~3
+    out = torch.full((ref.shape[0], tp), float('nan'), device=dev)
+    check(lib().qbold_normalise_zouter(dptr(data), b, nx, ny, nz, t, 2, int(multi), dptr(out), stream_ptr(dev)))
+    assert torch.allclose(out[:, :t], ref, rtol=1e-6, atol=2e-6)
+    assert float(out[:, t:].abs().sum()) == 0.0
