@@ -17,9 +17,38 @@ __device__ __forceinline__ void ct_mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void ct_mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait (a descriptor or byte-count mistake must not wedge the GPU); false on timeout.
+// Bounded wait (a descriptor or byte-count mistake must not wedge the GPU); false on timeout.  The polling loop lives
+// inside ONE asm statement: a C-level loop that branches on the (per-thread) try_wait result makes everything after it
+// look divergent to the compiler, which then refuses to keep the MMA descriptors in uniform registers.
 __device__ __forceinline__ bool ct_mbar_wait(unsigned bar, unsigned parity) {
-    for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+    unsigned done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "CT_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "@p bra CT_WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 0x1000000;\n\t"
+        "@p bra CT_WAIT_LOOP;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "bra CT_WAIT_EXIT;\n\t"
+        "CT_WAIT_DONE:\n\t"
+        "mov.u32 %0, 1;\n\t"
+        "CT_WAIT_EXIT:\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// The same for threads that are NOT on the critical path (epilogue warps parked until the accumulators are final, a
+// producer several stages ahead): sleep between polls so the polling does not compete with the tensor pipe's operand
+// fetches for shared-memory bandwidth.
+__device__ __forceinline__ bool ct_mbar_wait_relaxed(unsigned bar, unsigned parity, unsigned sleep_ns) {
+    for (unsigned spin = 0; spin < (1u << 22); ++spin) {
         unsigned done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -29,8 +58,18 @@ __device__ __forceinline__ bool ct_mbar_wait(unsigned bar, unsigned parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return true;
+        __nanosleep(sleep_ns);
     }
     return false;
+}
+// One lane of a converged warp.  The MMA / TMA issue loops are run by ALL lanes of their warp with warp-uniform values and
+// only the instruction itself sits under this predicate: tcgen05.mma and the TMA instructions take their operands from
+// uniform registers, and a loop that runs on a single lane (inside `if (lane == 0)`) makes the compiler move every
+// descriptor through an ELECT / R2UR.BROADCAST "waterfall" -- ~90 clk per MMA instead of the 48 the tensor pipe needs.
+__device__ __forceinline__ bool ct_elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void ct_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

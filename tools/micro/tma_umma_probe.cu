@@ -137,6 +137,8 @@ int main() {
     const unsigned LA = 2048, LB = 1024;
     std::vector<Variant> vs;
     vs.push_back({0, 1024, 0, 1024, 0, 0, 0, 0, 2});               // K-major both (harness check)
+    vs.push_back({128, 512, LB, 512, 0, 0, 1, 1, 1});            // M atoms = the same 32 channels moved by 0..3 rows (LBO = one row)
+    vs.push_back({128, 512, LB, 512, 1, 0, 1, 1, 1});
     for (int ro = 0; ro < 3; ++ro)
         for (int bo = 0; bo < 2; ++bo) {
             if (ro == 0 && bo) continue;
@@ -176,7 +178,7 @@ int main() {
         // (the swizzle XOR uses the absolute row, so a start moved by row_off rows reads row k + row_off)
         auto elem = [&](int base_bytes, int mn_major, unsigned lbo, unsigned sbo, int idx, int k, int row_off) -> double {
             long off;
-            if (mn_major) { const int kr = k + row_off; off = (long)(idx / 32) * lbo + (long)kr * 128 + ((((idx % 32) / 8) ^ (kr % 4)) * 32) + (idx % 8) * 4; }
+            if (mn_major) { const int kr = k + row_off + (lbo == 128 ? idx / 32 : 0); off = (lbo == 128 ? 0 : (long)(idx / 32) * lbo) + (long)kr * 128 + ((((idx % 32) / 8) ^ (kr % 4)) * 32) + (idx % 8) * 4; }
             else { const int r = idx + row_off; off = (long)(r / 8) * sbo + (r % 8) * 128 + ((((k / 4) ^ (r % 8))) * 16) + (k % 4) * 4; }
             off += base_bytes;
             if (off < 0 || off / 4 >= (long)hs.size()) return 0.0;

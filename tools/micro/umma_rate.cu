@@ -14,13 +14,13 @@ __device__ __forceinline__ uint64_t mk_desc(unsigned addr, unsigned lbo, unsigne
            ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
 
-__global__ void __launch_bounds__(128) k_rate(int M, int N, int mn_major, int iters, int distinct, long long* cycles) {
+__global__ void __launch_bounds__(128) k_rate(int M, int N, int mn_major, int iters, int a_shift, int a_lbo, int random_data, int n_acc, long long* cycles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;
     __shared__ uint64_t bar;
     __shared__ unsigned tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem_raw + (base - s32(smem_raw)))[i] = 1.0f;
+    for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem_raw + (base - s32(smem_raw)))[i] = random_data ? (float)((int)((i * 2654435761u) >> 20) - 2048) * 0.001f : 1.0f;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128) k_rate(int M, int N, int mn_major, int it
         for (int w = 0; w < 4; ++w) {
             // four different operand windows, so the operands are really re-fetched
             if (mn_major) {
-                da[w] = mk_desc(base + (unsigned)w * 1024u, 16384u, 512u, 1u);
+                da[w] = mk_desc(base + (unsigned)w * 1024u + (unsigned)a_shift, (unsigned)a_lbo, 512u, 1u);
                 db[w] = mk_desc(base + 65536u + (unsigned)w * 1024u, 16384u, 512u, 1u);
             } else {
                 da[w] = mk_desc(base + (unsigned)w * 32u, 0u, 1024u, 2u);
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) k_rate(int M, int N, int mn_major, int it
 #pragma unroll
             for (int w = 0; w < 4; ++w)
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(tmem + (unsigned)(w & 1) * 256u), "l"(da[w]), "l"(db[w]), "r"(idesc), "r"(it > 0 ? 1u : 0u) : "memory");
+                             ::"r"(tmem + (unsigned)((it + w) % n_acc) * (n_acc > 2 ? 64u : 256u)), "l"(da[w]), "l"(db[w]), "r"(idesc), "r"(it > 0 ? 1u : 0u) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar)) : "memory");
         unsigned done = 0;
@@ -75,19 +75,32 @@ int main() {
     cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 4096;
     const int shapes[][2] = {{128, 64}, {64, 64}, {128, 128}, {64, 128}, {128, 192}, {128, 256}, {64, 256}, {128, 16}};
-    printf("%-10s %-9s %12s %14s %16s\n", "M x N x 8", "major", "clk / MMA", "MAC / clk / SM", "smem B / clk");
+    printf("%-10s %-34s %12s %14s %16s\n", "M x N x 8", "operands", "clk / MMA", "MAC / clk / SM", "smem B / clk");
+    auto run = [&](int M, int N, int mn, int a_shift, int a_lbo, const char* label, int random_data = 0, int n_acc = 2) {
+        k_rate<<<sms, 128, 200 * 1024>>>(M, N, mn, iters, a_shift, a_lbo, random_data, n_acc, d);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); exit(1); }
+        long long h[256];
+        cudaMemcpy(h, d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+        double mean = 0;
+        for (int i = 0; i < sms; ++i) mean += (double)h[i];
+        mean /= sms;
+        const double clk = mean / iters;
+        printf("%3dx%3dx8  %-34s %12.1f %14.0f %16.1f\n", M, N, label, clk, M * N * 8.0 / clk, (M + N) * 32.0 / clk);
+    };
     for (int mn = 0; mn < 2; ++mn)
-        for (auto& sh : shapes) {
-            k_rate<<<sms, 128, 200 * 1024>>>(sh[0], sh[1], mn, iters, 4, d);
-            if (cudaDeviceSynchronize() != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
-            long long h[256];
-            cudaMemcpy(h, d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
-            double mean = 0;
-            for (int i = 0; i < sms; ++i) mean += (double)h[i];
-            mean /= sms;
-            const double clk = mean / iters;
-            printf("%3dx%3dx8  %-9s %12.1f %14.0f %16.1f\n", sh[0], sh[1], mn ? "MN-major" : "K-major", clk, sh[0] * sh[1] * 8.0 / clk,
-                   (sh[0] + sh[1]) * 32.0 / clk);
-        }
+        for (auto& sh : shapes) run(sh[0], sh[1], mn, 0, 16384, mn ? "MN-major" : "K-major");
+    // MN-major A whose start address is moved by whole 128-byte rows / whose four M atoms are one row apart
+    run(128, 64, 1, 128, 16384, "MN-major, A start + 1 row");
+    run(128, 64, 1, 256, 16384, "MN-major, A start + 2 rows");
+    run(128, 64, 1, 512, 16384, "MN-major, A start + 4 rows");
+    run(128, 64, 1, 0, 128, "MN-major, A atoms 1 row apart");
+    run(128, 64, 1, 0, 512, "MN-major, A atoms 4 rows apart");
+    run(128, 128, 1, 128, 16384, "MN-major, A start + 1 row");
+    run(128, 128, 1, 0, 128, "MN-major, A atoms 1 row apart");
+    run(128, 64, 1, 0, 128, "MN-major, random data", 1, 2);
+    run(128, 64, 1, 0, 128, "MN-major, random data, 6 accum.", 1, 6);
+    run(128, 64, 1, 0, 128, "MN-major, ones, 6 accumulators", 0, 6);
+    run(128, 128, 0, 0, 16384, "K-major, random data", 1, 2);
+    run(128, 256, 0, 0, 16384, "K-major, random data", 1, 2);
     return 0;
 }

@@ -26,3 +26,10 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
     for _ in range(3): dp.step(data, mask, prior)
     torch.cuda.synchronize()
 print(p.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+# GPU-busy time per step against the wall time of a step (launch gaps show up as the difference)
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(10): dp.step(data, mask, prior)
+torch.cuda.synchronize(); wall = (time.perf_counter() - t0) / 10 * 1e3
+busy = sum(e.self_device_time_total for e in p.key_averages()) / 3 / 1e3
+print('wall ms/step %.3f   GPU-busy ms/step (sum of kernel times) %.3f' % (wall, busy))
