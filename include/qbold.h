@@ -316,6 +316,12 @@ int qbold_dense_small_forward(const float* x, const float* w, const float* bias,
 int qbold_dense_small_dgrad(const float* g, const float* w, int32_t n_in, int32_t n_out, int64_t n, float* dx,
                             void* stream);
 
+/* dx[n,n_in] = [relu_mask > 0] * (g[n,n_out] w): the skinny input gradient with the ReLU' of the activation the head
+ * read applied to the result (relu_mask [n,n_in], may be NULL); warp-cooperative coalesced stores.  n_out <= 16,
+ * n_in <= 64. */
+int qbold_dense_small_dgrad_masked(const float* g, const float* w, const float* relu_mask, int32_t n_in, int32_t n_out,
+                                   int64_t n, float* dx, void* stream);
+
 /* One Dense layer on the tensor cores (tcgen05 kind::tf32, fp32 accumulate) for the encoder's training passes:
  * y[n,n_out] = act((x[n,n_in] * [relu_mask > 0]) B^T + bias).  qbold_dense_tc_pack builds the operand image
  * (qbold_dense_tc_packed_floats() floats, device) from a row-major matrix: transpose = 0: B = w [rows, cols] with

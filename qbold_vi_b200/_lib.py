@@ -115,6 +115,7 @@ _SIGNATURES = {
     'qbold_colsum_workspace_floats': (C.c_int64, []),
     'qbold_relu_bwd_colsum': (C.c_int, [_f, _f, _f, C.c_int64, C.c_int32, _f, _f, C.c_int32, _f, C.c_void_p]),
     'qbold_normalise_zouter': (C.c_int, [_f, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, C.c_void_p]),
+    'qbold_dense_small_dgrad_masked': (C.c_int, [_f, _f, _f, C.c_int32, C.c_int32, C.c_int64, _f, C.c_void_p]),
     'qbold_dense_tma': (C.c_int, [_f, _f, _f, _f, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _f, _f, C.c_void_p]),
     'qbold_dense_wgrad_tma_workspace_floats': (C.c_int64, []),
     'qbold_dense_wgrad_tma': (C.c_int, [_f, C.c_int32, _f, C.c_int32, C.c_int64, _f, _f, C.c_int32, _f, _f, C.c_void_p]),

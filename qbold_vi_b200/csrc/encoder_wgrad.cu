@@ -264,6 +264,57 @@ __global__ void __launch_bounds__(256) k_dense_small_dgrad(const float* __restri
     }
 }
 
+// The same input gradient with warp-cooperative, coalesced stores and an optional ReLU' mask on the RESULT:
+//     dx[v, i] = [relu_mask[v, i] > 0] * sum_o g[v, o] W[o, i]
+// A warp takes 32 voxels: lane l loads the gradient row of voxel l (n_out <= 16 floats), then for each voxel the row
+// is broadcast by shuffles and lane l produces inputs i = l and l + 32, so a voxel's 240-byte row is written (and
+// its mask row read) by consecutive lanes.  With the mask this also replaces the separate ReLU' pass over the
+// activation that the head reads (the last block's stream-1 output).
+__global__ void __launch_bounds__(256) k_dense_small_dgrad_coop(const float* __restrict__ g, const float* __restrict__ w,
+                                                                const float* __restrict__ relu_mask, int n_in, int n_out,
+                                                                int64_t n, float* __restrict__ dx) {
+    __shared__ float sw[kSmallOut][kSmallIn];
+    for (int e = threadIdx.x; e < kSmallOut * kSmallIn; e += blockDim.x) {
+        const int o = e / kSmallIn, i = e % kSmallIn;
+        sw[o][i] = (o < n_out && i < n_in) ? __ldg(w + o * n_in + i) : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int i0 = lane, i1 = lane + 32;
+    float w0[kSmallOut], w1[kSmallOut];
+#pragma unroll
+    for (int o = 0; o < kSmallOut; ++o) {
+        w0[o] = sw[o][i0];
+        w1[o] = sw[o][i1];
+    }
+    for (int64_t base = warp0 * 32; base < n; base += nwarps * 32) {
+        const int64_t mine = base + lane;
+        float gv[kSmallOut];
+#pragma unroll
+        for (int o = 0; o < kSmallOut; ++o) gv[o] = (o < n_out && mine < n) ? __ldg(g + mine * n_out + o) : 0.f;
+        const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+        for (int t = 0; t < cnt; ++t) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int o = 0; o < kSmallOut; ++o) {
+                if (o < n_out) {
+                    const float gg = __shfl_sync(0xffffffffu, gv[o], t);
+                    a0 = fmaf(gg, w0[o], a0);
+                    a1 = fmaf(gg, w1[o], a1);
+                }
+            }
+            const int64_t row = (base + t) * n_in;
+            if (relu_mask != nullptr) {
+                if (i0 < n_in && !(__ldg(relu_mask + row + i0) > 0.f)) a0 = 0.f;
+                if (i1 < n_in && !(__ldg(relu_mask + row + i1) > 0.f)) a1 = 0.f;
+            }
+            if (i0 < n_in) dx[row + i0] = a0;
+            if (i1 < n_in) dx[row + i1] = a1;
+        }
+    }
+}
+
 }  // namespace qb
 
 static int small_dense_args_ok(const void* a, const void* w, const void* out, int n_in, int n_out, int64_t n) {
@@ -296,4 +347,16 @@ extern "C" int qbold_dense_small_dgrad(const float* g, const float* w, int32_t n
     if (grid > cap) grid = cap;
     k_dense_small_dgrad<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(g, w, n_in, n_out, n, dx);
     return after_launch("k_dense_small_dgrad");
+}
+
+extern "C" int qbold_dense_small_dgrad_masked(const float* g, const float* w, const float* relu_mask, int32_t n_in,
+                                              int32_t n_out, int64_t n, float* dx, void* stream) {
+    if (!g || !w || !dx || n < 0 || n_out < 1 || n_out > kSmallOut || n_in < 1 || n_in > kSmallIn)
+        return fail(QBOLD_EUNSUPPORTED, "qbold_dense_small_dgrad_masked: needs n_out <= 16, n_in <= 64");
+    if (n == 0) return QBOLD_OK;
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    k_dense_small_dgrad_coop<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(g, w, relu_mask, n_in, n_out, n, dx);
+    return after_launch("k_dense_small_dgrad_coop");
 }

@@ -130,7 +130,11 @@ class _DenseFn(torch.autograd.Function):
     qbold_dense_wgrad (TF32 mma, HBM-bound, deterministic)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu=False):
+    def forward(ctx, x, weight, bias, relu=False, input_is_relu=False):
+        # input_is_relu: x is itself a ReLU output with this layer as its ONLY consumer; the input gradient is then
+        # returned already multiplied by [x > 0] (fused into the skinny kernel's stores), and the producer skips its
+        # own ReLU' pass (_BlockFn's premasked_out1)
+        ctx.input_is_relu = bool(input_is_relu)
         n_out, n_in = weight.shape
         if not relu and n_out >= 8 and _tma_ok(n_in, n_out, x, weight, bias):      # e.g. the 16-output double head
             y = _dense_tma(x, weight, bias)
@@ -175,23 +179,24 @@ class _DenseFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty((x.shape[0], n_in), dtype=torch.float32, device=dev)
                 with torch.cuda.device(dev):
-                    check(_lib.lib().qbold_dense_small_dgrad(dptr(g), dptr(weight), n_in, n_out, x.shape[0], dptr(gx),
-                                                             stream_ptr(dev)))
+                    check(_lib.lib().qbold_dense_small_dgrad_masked(dptr(g), dptr(weight),
+                                                                    dptr(x) if ctx.input_is_relu else None, n_in, n_out,
+                                                                    x.shape[0], dptr(gx), stream_ptr(dev)))
         elif USE_DENSE_TC and _tc_ok(n_out, n_in, g) and (y is None or y.data_ptr() % 16 == 0):
             if ctx.needs_input_grad[0]:
                 gx = _dense_tc(g, y, weight, None, n_out, n_in, True, False)          # (g * relu') W, relu' fused
         else:
-            if y is not None:                                 # library path: materialise g * relu' once for both uses
+            if y is not None and ctx.needs_input_grad[0]:     # materialise g * relu' once for both uses
                 g, mask = torch.ops.aten.threshold_backward(g, y, 0.0), None
             if ctx.needs_input_grad[0]:
                 gx = _mm(g, weight)
         lib = _lib.lib()
         if not torch.backends.cuda.matmul.allow_tf32:         # strict float32 requested: qbold_dense_wgrad is TF32 mma
             gm = g if mask is None else torch.ops.aten.threshold_backward(g, mask, 0.0)
-            return gx, gm.t() @ x, gm.sum(0), None
+            return gx, gm.t() @ x, gm.sum(0), None, None
         if mask is None and _tma_ok(n_in, n_out, g, x):
             dw, db = _wgrad(g, x)
-            return gx, dw, db, None
+            return gx, dw, db, None, None
         # per-call scratch from the caching allocator (stream-ordered, so concurrent backward passes cannot share it)
         ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
         dw = torch.empty_like(weight)
@@ -199,7 +204,7 @@ class _DenseFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib.qbold_dense_wgrad(dptr(g), dptr(mask, allow_none=True), n_out, dptr(x), n_in, x.shape[0], dptr(dw),
                                         dptr(db), 0, dptr(ws), stream_ptr(dev)))
-        return gx, dw, db, None
+        return gx, dw, db, None, None
 
 
 class _GateMixFn(torch.autograd.Function):
@@ -430,7 +435,7 @@ def _conv_backward(g_flat, x_flat, w2, dims):
 class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net1, net2, a0, w_p, b_p, w_a, b_a, w_b, b_b, w_g, b_g, dims, offset, same_input, a0_is_net2,
-                want_relu_out):
+                want_relu_out, premasked_out1=False):
         from . import _lib
         from ._lib import check, dptr, stream_ptr
         n, c = net2.shape
@@ -450,6 +455,7 @@ class _BlockFn(torch.autograd.Function):
                                                      c, dptr(out2), dptr(out2_relu, allow_none=True), stream_ptr(dev)))
         ctx.save_for_backward(net1, net2, a0, out1, skip, c1f, r0f, z, w_p, w_a, w_b, w_g, b_b)
         ctx.dims, ctx.offset, ctx.same_input, ctx.a0_is_net2 = dims, float(offset), same_input, a0_is_net2
+        ctx.premasked_out1 = bool(premasked_out1)       # the gradient of out1 arrives already times [out1 > 0]
         if want_relu_out:
             ctx.mark_non_differentiable(out2_relu)
             return out1, out2, out2_relu
@@ -492,13 +498,13 @@ class _BlockFn(torch.autograd.Function):
             _addmm_(d_net2, g_p, w_p)
             d_net1 = None
         else:
-            g_1 = _relu_bwd(d_out1.contiguous(), out1)
+            g_1 = d_out1.contiguous() if ctx.premasked_out1 else _relu_bwd(d_out1.contiguous(), out1)
             dw_p, db_p = _wgrad(d_skip, net2)
             _wgrad(g_1, net1, accumulate_into=(dw_p, db_p))
             _addmm_(d_net2, d_skip, w_p)
             d_net1 = _mm(g_1, w_p)
         return (d_net1, d_net2, None, dw_p, db_p, dw_a.unsqueeze(-1), db_a, dw_b.unsqueeze(-1), db_b, dw_g, db_g,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def _fast_block_ok(blk, net2):
@@ -633,18 +639,24 @@ class Encoder(nn.Module):
             xt = x.permute(0, 3, 1, 2, 4).reshape(b * nz * nx * ny, n_tau)            # [B,Z,X,Y,n_tau]: 44 B/voxel copy
             h = dense(self.first, xt, True)
         net1 = net2 = a0 = h
+        # the stream-1 head is the only reader of the last block's out1 (a ReLU output): its skinny input-gradient kernel
+        # applies [out1 > 0] itself, so the block skips a ReLU' pass (needs the float32 skinny path: <= 16 outputs)
+        head_masks = _small_ok(self.final.in_features, self.final.out_features, self.final.weight)
         for i, blk in enumerate(self.blocks):
             last = i + 1 == len(self.blocks)
             net1, net2, nxt = _BlockFn.apply(net1, net2, a0, blk.pointwise.weight, blk.pointwise.bias, blk.conv_a.conv.weight,
                                              blk.conv_a.conv.bias, blk.conv_b.conv.weight, blk.conv_b.conv.bias,
                                              blk.gate.weight, blk.gate.bias, dims, blk.gate_offset, i == 0, i == 0,
-                                             not last)
+                                             not last, last and i > 0 and head_masks)
             a0 = nxt
 
         def back(t):                                                                  # [B,Z,X,Y,c] -> [B,X,Y,Z,c]
             return t.view(b, nz, nx, ny, t.shape[-1]).permute(0, 2, 3, 1, 4).contiguous()
 
-        q1 = dense(self.final, net1)
+        if head_masks and len(self.blocks) > 1:
+            q1 = _DenseFn.apply(net1, self.final.weight, self.final.bias, False, True)
+        else:
+            q1 = dense(self.final, net1)
         # the two heads that read net2 (posterior parameters and sigmas) as ONE skinny Dense: one pass over net2 forward,
         # one input-gradient pass backward
         n_q = self.final.out_features

@@ -1666,3 +1666,20 @@ def test_normalise_zouter_kernel(qb, dev, shape, multi):
     check(lib().qbold_normalise_zouter(dptr(data), b, nx, ny, nz, t, 2, int(multi), dptr(out), stream_ptr(dev)))
     assert torch.allclose(out[:, :t], ref, rtol=1e-6, atol=2e-6)
     assert float(out[:, t:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('n,n_in,n_out,masked', [(1000, 60, 5, True), (33, 60, 16, False), (70001, 60, 5, True), (1, 12, 3, True)])
+def test_skinny_input_gradient_with_relu_mask(qb, dev, n, n_in, n_out, masked):
+    """qbold_dense_small_dgrad_masked: dx = [mask > 0] * (g W) in float32 (warp-cooperative stores)."""
+    from qbold_vi_b200._lib import check, dptr, lib, stream_ptr
+    gen = torch.Generator(device=dev).manual_seed(n + n_out)
+    g = torch.randn(n, n_out, device=dev, generator=gen)
+    w = torch.randn(n_out, n_in, device=dev, generator=gen)
+    act = torch.relu(torch.randn(n, n_in, device=dev, generator=gen))
+    dx = torch.full((n, n_in), float('nan'), device=dev)
+    check(lib().qbold_dense_small_dgrad_masked(dptr(g), dptr(w), dptr(act) if masked else None, n_in, n_out, n, dptr(dx),
+                                               stream_ptr(dev)))
+    ref = g.double() @ w.double()
+    if masked:
+        ref = ref * (act > 0)
+    assert float((dx.double() - ref).abs().max()) <= 1e-5 * (float(ref.abs().max()) + 1.0)
