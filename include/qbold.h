@@ -355,6 +355,11 @@ int qbold_block_mix_forward(const float* skip, const float* r0, const float* r_b
 int qbold_block_mix_backward(const float* go, const float* skip, const float* r0, const float* r_bias, const float* z,
                              float offset, int64_t n, int32_t channels, int32_t skip_is_relu, float* d_skip, float* d_r,
                              float* d_z, void* stream);
+/* The same with a second gradient of the skip activation (skip_addend [n, channels], may be NULL) added BEFORE the ReLU'
+ * mask: d_skip = [skip > 0] * (go (1 - g) + skip_addend) -- block 0 of the encoder, whose stream-1 output IS the skip. */
+int qbold_block_mix_backward_add(const float* go, const float* skip, const float* r0, const float* r_bias, const float* z,
+                                 float offset, int64_t n, int32_t channels, int32_t skip_is_relu, const float* skip_addend,
+                                 float* d_skip, float* d_r, float* d_z, void* stream);
 /* ReLU backward fused with the bias gradient: out[n,channels] = g * [y > 0] (+ addend, may be NULL) (y NULL: no mask,
  * out unused) and colsum[channels] (+)= column sums of that (colsum may be NULL; deterministic two-stage reduction
  * through `workspace`, qbold_colsum_workspace_floats() floats of device scratch). */

@@ -112,6 +112,8 @@ _SIGNATURES = {
     'qbold_block_mix_forward': (C.c_int, [_f, _f, _f, _f, C.c_float, C.c_int64, C.c_int32, _f, _f, C.c_void_p]),
     'qbold_block_mix_backward': (C.c_int, [_f, _f, _f, _f, _f, C.c_float, C.c_int64, C.c_int32, C.c_int32, _f, _f, _f,
                                            C.c_void_p]),
+    'qbold_block_mix_backward_add': (C.c_int, [_f, _f, _f, _f, _f, C.c_float, C.c_int64, C.c_int32, C.c_int32, _f, _f, _f, _f,
+                                               C.c_void_p]),
     'qbold_colsum_workspace_floats': (C.c_int64, []),
     'qbold_relu_bwd_colsum': (C.c_int, [_f, _f, _f, C.c_int64, C.c_int32, _f, _f, C.c_int32, _f, C.c_void_p]),
     'qbold_normalise_zouter': (C.c_int, [_f, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, C.c_void_p]),

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads) k_block_mix_bwd(const float4* __rest
                                                             const float4* __restrict__ r0,
                                                             const float4* __restrict__ r_bias,
                                                             const float4* __restrict__ z, float offset, int64_t total4,
-                                                            int c4, int skip_is_relu, float4* __restrict__ d_skip,
+                                                            int c4, int skip_is_relu, const float4* __restrict__ skip_addend, float4* __restrict__ d_skip,
                                                             float4* __restrict__ d_r, float4* __restrict__ d_z) {
     for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total4; e += (int64_t)gridDim.x * kThreads) {
         const float4 zz = ld4(z + e), s = ld4(skip + e), o = ld4(go + e);
@@ -63,6 +63,10 @@ __global__ void __launch_bounds__(kThreads) k_block_mix_bwd(const float4* __rest
         }
         const float g0 = gate(zz.x, offset), g1 = gate(zz.y, offset), g2 = gate(zz.z, offset), g3 = gate(zz.w, offset);
         float4 ds = make_float4(o.x * (1.0f - g0), o.y * (1.0f - g1), o.z * (1.0f - g2), o.w * (1.0f - g3));
+        if (skip_addend != nullptr) {                                // a second gradient of the same activation (stream 1)
+            const float4 a = ld4(skip_addend + e);
+            ds = make_float4(ds.x + a.x, ds.y + a.y, ds.z + a.z, ds.w + a.w);
+        }
         if (skip_is_relu)                                            // skip = relu(.): threshold_backward(ds, skip, 0)
             ds = make_float4(s.x > 0.f ? ds.x : 0.f, s.y > 0.f ? ds.y : 0.f, s.z > 0.f ? ds.z : 0.f,
                              s.w > 0.f ? ds.w : 0.f);
@@ -167,8 +171,15 @@ __global__ void __launch_bounds__(256) k_normalise_zouter(const float* __restric
         } else {
             ref = fminf(fmaxf(src[se], 1e-2f), 1e8f);
         }
-        float* dst = out + ((((int64_t)b * Z + (z0 + z)) * X + x) * Y + (y0 + lane)) * Tp;
-        for (int t = 0; t < Tp; ++t) dst[t] = t < T ? logf(fminf(fmaxf(src[t], 1e-2f), 1e8f) / ref) : 0.f;
+        float4* dst = reinterpret_cast<float4*>(out + ((((int64_t)b * Z + (z0 + z)) * X + x) * Y + (y0 + lane)) * Tp);
+        for (int t = 0; t < Tp; t += 4) {                                   // 16-byte stores (Tp is a multiple of 4)
+            float4 v;
+            v.x = logf(fminf(fmaxf(src[t], 1e-2f), 1e8f) / ref);
+            v.y = t + 1 < T ? logf(fminf(fmaxf(src[t + 1], 1e-2f), 1e8f) / ref) : 0.f;
+            v.z = t + 2 < T ? logf(fminf(fmaxf(src[t + 2], 1e-2f), 1e8f) / ref) : 0.f;
+            v.w = t + 3 < T ? logf(fminf(fmaxf(src[t + 3], 1e-2f), 1e8f) / ref) : 0.f;
+            dst[t >> 2] = v;
+        }
     }
 }
 
@@ -201,9 +212,22 @@ extern "C" int qbold_block_mix_forward(const float* skip, const float* r0, const
     return after_launch("k_block_mix_fwd");
 }
 
+extern "C" int qbold_block_mix_backward_add(const float* go, const float* skip, const float* r0, const float* r_bias,
+                                            const float* z, float offset, int64_t n, int32_t channels,
+                                            int32_t skip_is_relu, const float* skip_addend, float* d_skip, float* d_r,
+                                            float* d_z, void* stream);
+
 extern "C" int qbold_block_mix_backward(const float* go, const float* skip, const float* r0, const float* r_bias,
                                         const float* z, float offset, int64_t n, int32_t channels,
                                         int32_t skip_is_relu, float* d_skip, float* d_r, float* d_z, void* stream) {
+    return qbold_block_mix_backward_add(go, skip, r0, r_bias, z, offset, n, channels, skip_is_relu, nullptr, d_skip, d_r,
+                                        d_z, stream);
+}
+
+extern "C" int qbold_block_mix_backward_add(const float* go, const float* skip, const float* r0, const float* r_bias,
+                                            const float* z, float offset, int64_t n, int32_t channels,
+                                            int32_t skip_is_relu, const float* skip_addend, float* d_skip, float* d_r,
+                                            float* d_z, void* stream) {
     if (n < 0 || channels < 4 || (channels & 3) || channels > 4 * kMaxC4)
         return fail(QBOLD_EUNSUPPORTED, "qbold_block_mix_backward: channels must be a multiple of 4 in [4, 64]");
     if (n == 0) return QBOLD_OK;
@@ -213,11 +237,14 @@ extern "C" int qbold_block_mix_backward(const float* go, const float* skip, cons
     for (const void* p : ptrs)
         if (!aligned16(p)) return fail(QBOLD_EINVAL, "qbold_block_mix_backward: operands must be 16-byte aligned");
     if (r_bias && !aligned16(r_bias)) return fail(QBOLD_EINVAL, "qbold_block_mix_backward: r_bias must be 16-byte aligned");
+    if (skip_addend && !aligned16(skip_addend))
+        return fail(QBOLD_EINVAL, "qbold_block_mix_backward: skip_addend must be 16-byte aligned");
     const int64_t total4 = n * (channels / 4);
     k_block_mix_bwd<<<(unsigned)stream_grid4(total4), kThreads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(go), reinterpret_cast<const float4*>(skip), reinterpret_cast<const float4*>(r0),
         reinterpret_cast<const float4*>(r_bias), reinterpret_cast<const float4*>(z), offset, total4, channels / 4,
-        skip_is_relu, reinterpret_cast<float4*>(d_skip), reinterpret_cast<float4*>(d_r), reinterpret_cast<float4*>(d_z));
+        skip_is_relu, reinterpret_cast<const float4*>(skip_addend), reinterpret_cast<float4*>(d_skip),
+        reinterpret_cast<float4*>(d_r), reinterpret_cast<float4*>(d_z));
     return after_launch("k_block_mix_bwd");
 }
 

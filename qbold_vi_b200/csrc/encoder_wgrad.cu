@@ -200,71 +200,53 @@ namespace qb {
 
 constexpr int kSmallOut = 16, kSmallIn = 64;
 
-__global__ void __launch_bounds__(256) k_dense_small_fwd(const float* __restrict__ x, const float* __restrict__ w,
-                                                         const float* __restrict__ b, int n_in, int n_out, int64_t n,
-                                                         float* __restrict__ y) {
-    __shared__ float4 sw[kSmallOut][kSmallIn / 4];
+// Forward with coalesced loads: a warp copies 32 consecutive rows of x (one contiguous 32 * n_in float run) into its
+// shared-memory tile with a row pitch of n_in + 1 floats, then lane l multiplies row l (bank-conflict free: the pitch is
+// odd) with the weights broadcast from shared memory.  58 -> ~25 us for the 60 -> 5 head on 524 288 voxels.
+__global__ void __launch_bounds__(128) k_dense_small_fwd_coop(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ b, int n_in, int n_out, int64_t n,
+                                                              float* __restrict__ y) {
+    __shared__ float sw[kSmallOut][kSmallIn];
     __shared__ float sb[kSmallOut];
-    const int chunks = n_in >> 2;
-    for (int e = threadIdx.x; e < kSmallOut * (kSmallIn / 4); e += blockDim.x) {
-        const int o = e / (kSmallIn / 4), c = e % (kSmallIn / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < n_out && c < chunks) v = *reinterpret_cast<const float4*>(w + o * n_in + c * 4);
-        sw[o][c] = v;
+    __shared__ float tile[4][32 * (kSmallIn + 1)];
+    for (int e = threadIdx.x; e < kSmallOut * kSmallIn; e += blockDim.x) {
+        const int o = e / kSmallIn, i = e % kSmallIn;
+        sw[o][i] = (o < n_out && i < n_in) ? __ldg(w + o * n_in + i) : 0.f;
     }
     if (threadIdx.x < kSmallOut) sb[threadIdx.x] = threadIdx.x < n_out ? b[threadIdx.x] : 0.f;
     __syncthreads();
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        float acc[kSmallOut];
-#pragma unroll
-        for (int o = 0; o < kSmallOut; ++o) acc[o] = sb[o];
-        const float4* row = reinterpret_cast<const float4*>(x + v * n_in);
-        for (int c = 0; c < chunks; ++c) {
-            const float4 a = __ldg(row + c);
-#pragma unroll
-            for (int o = 0; o < kSmallOut; ++o) {
-                const float4 ww = sw[o][c];
-                acc[o] = fmaf(a.x, ww.x, fmaf(a.y, ww.y, fmaf(a.z, ww.z, fmaf(a.w, ww.w, acc[o]))));
-            }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, pitch = n_in + 1;
+    float* t = tile[wid];
+    const int64_t warp0 = (int64_t)blockIdx.x * 4 + wid, nwarps = (int64_t)gridDim.x * 4;
+    for (int64_t base = warp0 * 32; base < n; base += nwarps * 32) {
+        const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+        const int run = cnt * n_in;
+        const float* src = x + base * n_in;
+        for (int e = lane; e < run; e += 32) {
+            const int r = e / n_in, c = e - r * n_in;
+            t[r * pitch + c] = __ldg(src + e);
         }
+        __syncwarp();
+        if (lane < cnt) {
+            float acc[kSmallOut];
 #pragma unroll
-        for (int o = 0; o < kSmallOut; ++o)
-            if (o < n_out) y[v * n_out + o] = acc[o];
+            for (int o = 0; o < kSmallOut; ++o) acc[o] = sb[o];
+            const float* row = t + lane * pitch;
+            for (int i = 0; i < n_in; ++i) {
+                const float a = row[i];
+#pragma unroll
+                for (int o = 0; o < kSmallOut; ++o)
+                    if (o < n_out) acc[o] = fmaf(a, sw[o][i], acc[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < kSmallOut; ++o)
+                if (o < n_out) y[(base + lane) * n_out + o] = acc[o];
+        }
+        __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(256) k_dense_small_dgrad(const float* __restrict__ g, const float* __restrict__ w,
-                                                           int n_in, int n_out, int64_t n, float* __restrict__ dx) {
-    __shared__ float4 sw[kSmallOut][kSmallIn / 4];
-    const int chunks = n_in >> 2;
-    for (int e = threadIdx.x; e < kSmallOut * (kSmallIn / 4); e += blockDim.x) {
-        const int o = e / (kSmallIn / 4), c = e % (kSmallIn / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < n_out && c < chunks) v = *reinterpret_cast<const float4*>(w + o * n_in + c * 4);
-        sw[o][c] = v;
-    }
-    __syncthreads();
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        float gv[kSmallOut];
-#pragma unroll
-        for (int o = 0; o < kSmallOut; ++o) gv[o] = o < n_out ? __ldg(g + v * n_out + o) : 0.f;
-        float4* row = reinterpret_cast<float4*>(dx + v * n_in);
-        for (int c = 0; c < chunks; ++c) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int o = 0; o < kSmallOut; ++o) {
-                const float4 ww = sw[o][c];
-                a.x = fmaf(gv[o], ww.x, a.x);
-                a.y = fmaf(gv[o], ww.y, a.y);
-                a.z = fmaf(gv[o], ww.z, a.z);
-                a.w = fmaf(gv[o], ww.w, a.w);
-            }
-            row[c] = a;
-        }
-    }
-}
-
-// The same input gradient with warp-cooperative, coalesced stores and an optional ReLU' mask on the RESULT:
+// Input gradient with warp-cooperative, coalesced stores and an optional ReLU' mask on the RESULT:
 //     dx[v, i] = [relu_mask[v, i] > 0] * sum_o g[v, o] W[o, i]
 // A warp takes 32 voxels: lane l loads the gradient row of voxel l (n_out <= 16 floats), then for each voxel the row
 // is broadcast by shuffles and lane l produces inputs i = l and l + 32, so a voxel's 240-byte row is written (and
@@ -329,11 +311,11 @@ extern "C" int qbold_dense_small_forward(const float* x, const float* w, const f
         return fail(QBOLD_EUNSUPPORTED, "qbold_dense_small_forward: needs n_out <= 16, n_in a multiple of 4 up to 64, "
                                         "16-byte aligned x / w / y");
     if (n == 0) return QBOLD_OK;
-    int64_t grid = (n + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 8;
+    int64_t grid = (n + 127) / 128;
+    const int64_t cap = (int64_t)sm_count() * 6;
     if (grid > cap) grid = cap;
-    k_dense_small_fwd<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, n_in, n_out, n, y);
-    return after_launch("k_dense_small_fwd");
+    k_dense_small_fwd_coop<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(x, w, bias, n_in, n_out, n, y);
+    return after_launch("k_dense_small_fwd_coop");
 }
 
 extern "C" int qbold_dense_small_dgrad(const float* g, const float* w, int32_t n_in, int32_t n_out, int64_t n, float* dx,
@@ -345,8 +327,8 @@ extern "C" int qbold_dense_small_dgrad(const float* g, const float* w, int32_t n
     int64_t grid = (n + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;
-    k_dense_small_dgrad<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(g, w, n_in, n_out, n, dx);
-    return after_launch("k_dense_small_dgrad");
+    k_dense_small_dgrad_coop<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(g, w, nullptr, n_in, n_out, n, dx);
+    return after_launch("k_dense_small_dgrad_coop");
 }
 
 extern "C" int qbold_dense_small_dgrad_masked(const float* g, const float* w, const float* relu_mask, int32_t n_in,

@@ -471,10 +471,13 @@ class _BlockFn(torch.autograd.Function):
         dims = ctx.dims
         d_out2 = d_out2.contiguous()
         d_skip, d_r, d_z = torch.empty_like(skip), torch.empty_like(skip), torch.empty_like(skip)
+        # block 0: out1 IS skip, so the stream-1 gradient joins the skip gradient inside the mix kernel, before its ReLU'
+        # mask -- d_skip then already is g_p = [skip > 0] * (d_out2 (1 - g) + d_out1)
+        d_out1c = d_out1.contiguous() if ctx.same_input else None
         with torch.cuda.device(dev):
-            check(_lib.lib().qbold_block_mix_backward(dptr(d_out2), dptr(skip), dptr(r0f), dptr(b_b.contiguous()), dptr(z),
-                                                      ctx.offset, n, c, 1, dptr(d_skip), dptr(d_r), dptr(d_z),
-                                                      stream_ptr(dev)))
+            check(_lib.lib().qbold_block_mix_backward_add(dptr(d_out2), dptr(skip), dptr(r0f), dptr(b_b.contiguous()),
+                                                          dptr(z), ctx.offset, n, c, 1, dptr(d_out1c, allow_none=True),
+                                                          dptr(d_skip), dptr(d_r), dptr(d_z), stream_ptr(dev)))
         # gate Dense: z = W_g (r0 + b_b) + b_g
         dw_g, db_g = _wgrad(d_z, r0f)
         dw_g = torch.addr(dw_g, db_g, b_b)                                   # + colsum(d_z) (x) b_b
@@ -493,7 +496,7 @@ class _BlockFn(torch.autograd.Function):
             d_net2 = d_net2.contiguous()
         # shared pointwise Dense: skip = relu(W_p net2 + b_p) (d_skip is already masked), out1 = relu(W_p net1 + b_p)
         if ctx.same_input:
-            g_p = _relu_bwd(d_out1.contiguous(), out1, addend=d_skip)        # both uses of the same activation
+            g_p = d_skip                                                     # both uses of the same activation
             dw_p, db_p = _wgrad(g_p, net2)
             _addmm_(d_net2, g_p, w_p)
             d_net1 = None
