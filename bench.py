@@ -281,19 +281,95 @@ def training_and_inference_legs(qb, dev, rank, world, steps=10, volumes_per_gpu=
     ms_inf = timed(lambda: tr.posterior_inference(layer, q, sigma, data, mask, prior, no_samples=64), max(3, steps // 2))
     common = {'volumes_per_gpu': B, 'volume': '%d^3' % S, 'voxels_per_gpu': voxels, 'masked_fraction': float(mask.mean()),
               'encoder_params': sum(p.numel() for p in enc.parameters()),
-              'precision': 'qBOLD kernels fp32; encoder convolutions / Dense layers TF32 tensor cores'}
+              'precision': 'qBOLD kernels fp32; encoder in TF32: Dense layers (forward, input and weight gradients) and the '
+                           'convolution weight gradients on hand-written TMA + tcgen05 kernels, convolution forward / '
+                           'input gradient in cuDNN'}
     train = dict(common, config='BASELINE config 3 / 5: amortized-VI training step (encoder fwd+bwd, fused ELBO kernel '
                  'with 70-sample KL, TV, NCCL all-reduce of the encoder gradient, AdamW), weak scaling',
                  ms_per_step=ms_train, steps=steps, voxel_signals_per_s=world * voxels * 11 / (ms_train * 1e-3),
                  ms_allreduce_alone=ms_ar, allreduce_floats=int(dp.bucket.flat.numel()),
                  ms_encoder_fwd_bwd=ms_enc, ms_fused_elbo_kernel=ms_fused, own_kernel_launches_per_step=own_launches,
                  host_syncs_per_step=0, loss=loss,
-                 limiter='encoder forward + backward (3x3x1 convolutions and Dense GEMMs): %.0f %% of the step'
+                 limiter='encoder forward + backward (HBM passes over the [voxels, 60] activations): %.0f %% of the step'
                          % (100.0 * ms_enc / ms_train))
     infer = dict(common, config='BASELINE config 4: whole-volume posterior inference, 64 samples per voxel (means / '
                  'variances of OEF, DBV, R2prime, likelihood map, KL map)', ms_per_volume_batch=ms_inf,
                  voxels_per_s=world * voxels / (ms_inf * 1e-3), samples_per_voxel=64)
     return train, infer
+
+
+def encoder_kernels_leg(qb, dev, hbm_peak):
+    """The encoder's hand-written tensor-core kernels on the training shape (2 x 64^3 voxels, 60
+    channels), each beside the library kernel it replaces: the Dense kernels are HBM-bound (achieved / measured copy
+    bandwidth), the convolution weight gradient is bound by the shared-memory operand fetch of tcgen05 (TFLOP/s given)."""
+    import torch
+    from qbold_vi_b200._lib import check, dptr, lib, stream_ptr
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+    L = lib()
+    bz, nx, ny, c = 128, 64, 64, 60
+    n = bz * nx * ny
+    gen = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(n, c, device=dev, generator=gen)
+    g = torch.randn(n, c, device=dev, generator=gen)
+    w = torch.randn(c, c, device=dev, generator=gen) * 0.2
+    b = torch.randn(c, device=dev, generator=gen)
+    y, acc = torch.empty(n, c, device=dev), torch.randn(n, c, device=dev, generator=gen)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = stream_ptr(dev)
+    dw, db = torch.empty(c, c, device=dev), torch.empty(c, device=dev)
+    ws_d = torch.empty(int(L.qbold_dense_wgrad_tma_workspace_floats()), device=dev)
+    w4 = torch.randn(c, c, 3, 3, device=dev, generator=gen).contiguous(memory_format=torch.channels_last)
+    dw4 = torch.empty(c, c, 3, 3, device=dev)
+    ws_c = torch.empty(int(L.qbold_conv_wgrad_workspace_floats()), device=dev)
+    xi, gi = x.view(bz, nx, ny, c).permute(0, 3, 1, 2), g.view(bz, nx, ny, c).permute(0, 3, 1, 2)
+
+    def timed(fn, k=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k * 1e3                              # us
+
+    def dense(transpose, relu, add):
+        check(L.qbold_dense_tma(dptr(x), dptr(w), None if transpose else dptr(b), dptr(acc) if add else None, c, c,
+                                transpose, relu, n, dptr(acc) if add else dptr(y), dptr(status, torch.int32), st))
+
+    rows = {}
+
+    def row(name, ours, library, library_name, moved_bytes=None, flops=None):
+        t_o, t_l = timed(ours), timed(library)
+        r = {'us': t_o, 'library_us': t_l, 'library': library_name}
+        if moved_bytes:
+            r.update(bound='hbm', achieved_gbs=moved_bytes / t_o / 1e3, peak_gbs=hbm_peak,
+                     frac=moved_bytes / t_o / 1e3 / hbm_peak)
+        if flops:
+            r.update(bound='tcgen05 tf32 operand fetch from shared memory (128 B/clk/SM: 48 clk per 128x64x8 MMA, '
+                           'tools/micro/umma_rate.cu)', achieved_tflops=flops / t_o / 1e6)
+        rows[name] = r
+
+    row('k_dense_tma forward (bias + ReLU)', lambda: dense(0, 1, 0),
+        lambda: torch._addmm_activation(b, x, w.t(), use_gelu=False), 'cuBLASLt addmm + ReLU epilogue', 2 * n * c * 4)
+    row('k_dense_tma input gradient, in-place accumulate', lambda: dense(1, 0, 1), lambda: acc.addmm_(x, w),
+        'cuBLAS addmm_ (beta = 1)', 3 * n * c * 4)
+    row('k_dense_wgrad_tma (weight + bias gradient)',
+        lambda: check(L.qbold_dense_wgrad_tma(dptr(g), c, dptr(x), c, n, dptr(dw), dptr(db), 0, dptr(ws_d),
+                                              dptr(status, torch.int32), st)),
+        lambda: (g.t() @ x, g.sum(0)), 'cuBLAS g^T x + column sum', 2 * n * c * 4)
+    row('k_conv_wgrad_tma (3x3 weight gradient)',
+        lambda: check(L.qbold_conv_wgrad(dptr(g), c, dptr(x), c, bz, nx, ny, dptr(dw4), 0, dptr(ws_c),
+                                         dptr(status, torch.int32), st)),
+        lambda: torch.ops.aten.convolution_backward(gi, xi, w4, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
+                                                    (False, True, False)),
+        'cuDNN wgrad (cutlass3x sm100 implicit GEMM)', flops=2.0 * n * c * c * 9)
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return {'shape': '%d voxels (2 x 64^3), %d channels, TF32 operands, fp32 accumulate' % (n, c),
+            'tensor_core_timeouts': int(status.item()), 'kernels': rows}
 
 
 def workload_config(voxels, gpus):
@@ -471,6 +547,7 @@ def main():
         if world == 1:
             line['fused_elbo'] = fused_elbo_leg(qb, layer, cfg, x, sig, dev, f_alg, fma_tf)
             line['streaming'] = streaming_leg(qb, cfg, x, dev, hbm_peak, fma_tf, f_big, layer.params.n_cols)
+            line['encoder_kernels'] = encoder_kernels_leg(qb, dev, hbm_peak)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cpu_port_run(8192, threads)
