@@ -1683,3 +1683,51 @@ def test_skinny_input_gradient_with_relu_mask(qb, dev, n, n_in, n_out, masked):
     if masked:
         ref = ref * (act > 0)
     assert float((dx.double() - ref).abs().max()) <= 1e-5 * (float(ref.abs().max()) + 1.0)
+
+
+def test_fused_encoder_production_path_in_tf32(qb, dev, monkeypatch):
+    """The encoder as training runs it (TF32 on: normalise + z-outer kernel, Dense layers and weight gradients on the
+    TMA / tcgen05 kernels, masked head gradient, cuDNN TF32 convolutions) against the layer-by-layer module in strict
+    float32: outputs within 1e-2, every parameter gradient within twice the deviation the layer-by-layer module shows when
+    the libraries run it in TF32."""
+    import qbold_vi_b200.encoder as E
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.manual_seed(5)
+        enc = E.Encoder(no_units=60, no_intermediate_layers=2, gate_offset=-1.0, resid_init_std=0.1).to(dev)
+        data = torch.rand(2, 18, 20, 7, 11, device=dev) * 50.0 + 20.0
+        w = [torch.randn(2, 18, 20, 7, c, device=dev) for c in (5, 5, 11)]
+
+        def run(fast, tf32):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            monkeypatch.setattr(E, '_FAST_BLOCK', fast)
+            for p in enc.parameters():
+                p.grad = None
+            outs = enc(data)
+            sum((o * wi).sum() for o, wi in zip(outs, w)).backward()
+            return [o.detach().clone() for o in outs], [p.grad.detach().clone() for p in enc.parameters()]
+
+        o_ref, g_ref = run(False, False)
+        o_lib, g_lib = run(False, True)                                 # the library's own TF32 error on the same network
+        launches = qb.launch_count()
+        o_fast, g_fast = run(True, True)
+        assert qb.launch_count() - launches >= 30                      # the hand-written kernels ran, not a library fallback
+        assert E.tensor_core_status(dev) == 0
+        o_fast[2], o_ref[2] = torch.log(o_fast[2]), torch.log(o_ref[2])      # sigma = exp(.): compare the exponent
+        errs = [float((a - b).abs().max()) / float(b.abs().max()) for a, b in zip(o_fast, o_ref)]
+        gerrs = {n: float((a - b).abs().max()) / (float(b.abs().max()) + 1e-6)
+                 for (n, _), a, b in zip(enc.named_parameters(), g_fast, g_ref)}
+        lerrs = {n: float((a - b).abs().max()) / (float(b.abs().max()) + 1e-6)
+                 for (n, _), a, b in zip(enc.named_parameters(), g_lib, g_ref)}
+        print('tf32 path: output errors', errs, 'worst gradient', max(gerrs.items(), key=lambda kv: kv[1]),
+              'library TF32 worst gradient', max(lerrs.items(), key=lambda kv: kv[1]))
+        for a, b in zip(o_fast, o_ref):
+            assert a.shape == b.shape
+        assert max(errs) <= 1e-2, errs
+        # gradients: random cotangents make them sums of cancelling terms, so TF32 rounding shows up at the per-cent
+        # level in ANY TF32 implementation; the bar is the library path's own deviation from float32 on the same network
+        for n in gerrs:
+            assert gerrs[n] <= 2.0 * lerrs[n] + 1e-2, (n, gerrs[n], lerrs[n])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
