@@ -520,7 +520,7 @@ def main():
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n * (8 + 4 * N_TAU),
                     'd2h_bytes_per_step': n * (8 + 4 * N_TAU), 'steps': args.e2e_steps,
-                    'path': 'qbold_forward_backward_host: pinned host buffers, 6-slot H2D/kernel/D2H pipeline, 128k-voxel chunks',
+                    'path': 'qbold_forward_backward_host: pinned host buffers, 6-slot H2D/kernel/D2H pipeline, 256k-voxel chunks, OEF/DBV and its gradient per 1M-voxel super-chunk',
                     'matches_device_path': e2e_ok, 'compared': 'every element of signal and gradient',
                     'gbs_per_direction_per_gpu': e2e_gbs,
                     'host_ceiling': {'gbs_per_direction_per_gpu': ceiling_gbs,

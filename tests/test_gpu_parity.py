@@ -1731,3 +1731,20 @@ def test_fused_encoder_production_path_in_tf32(qb, dev, monkeypatch):
             assert gerrs[n] <= 2.0 * lerrs[n] + 1e-2, (n, gerrs[n], lerrs[n])
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize('n', [1, 300001, (1 << 20) + (1 << 18) + 777])
+def test_host_buffer_pipeline_matches_the_device_path(qb, dev, cfg_noise_off, n):
+    """qbold_forward_backward_host (pinned host buffers, chunked H2D / kernel / D2H pipeline with super-chunked OEF/DBV
+    and gradient copies) gives bit for bit what the device entry point gives, across chunk and super-chunk boundaries
+    and on a second call that reuses the pipeline's buffers."""
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    gen = torch.Generator().manual_seed(n)
+    hx = (torch.rand(n, 2, generator=gen) * torch.tensor([0.8, 0.2]) + torch.tensor([0.04, 0.001])).pin_memory()
+    hg = torch.randn(n, 11, generator=gen).pin_memory()
+    s_ref, g_ref = layer.forward_backward(hx.to(dev), hg.to(dev))
+    for _ in range(2):
+        hs = torch.full((n, 11), float('nan')).pin_memory()
+        hgr = torch.full((n, 2), float('nan')).pin_memory()
+        layer.forward_backward_host(hx, hg, hs, hgr)
+        assert torch.equal(hs, s_ref.cpu()) and torch.equal(hgr, g_ref.cpu())
