@@ -264,7 +264,17 @@ def training_and_inference_legs(qb, dev, rank, world, steps=10, volumes_per_gpu=
     last = {}
     launches0 = qb.launch_count()
     ms_train = timed(lambda: last.update(s=dp.step(data, mask, prior)), steps)
-    own_launches = (qb.launch_count() - launches0) / (steps + 3)
+    # host cost of enqueuing one step: three steps issued into an EMPTY queue (no back-pressure from the device)
+    sync()
+    t_h = time.perf_counter()
+    for _ in range(3):
+        dp.step(data, mask, prior)
+    ms_host = torch.tensor([(time.perf_counter() - t_h) / 3 * 1e3], device=dev, dtype=torch.float64)
+    sync()
+    if world > 1:
+        dist.all_reduce(ms_host, op=dist.ReduceOp.MAX)
+    ms_host = float(ms_host)
+    own_launches = (qb.launch_count() - launches0) / (steps + 6)
     loss = float(last['s']['loss'])                                       # the only host read, after the timed region
     ms_ar = timed(lambda: dp.bucket.all_reduce_(), 20) if world > 1 else 0.0
 
@@ -289,7 +299,7 @@ def training_and_inference_legs(qb, dev, rank, world, steps=10, volumes_per_gpu=
                  ms_per_step=ms_train, steps=steps, voxel_signals_per_s=world * voxels * 11 / (ms_train * 1e-3),
                  ms_allreduce_alone=ms_ar, allreduce_floats=int(dp.bucket.flat.numel()),
                  ms_encoder_fwd_bwd=ms_enc, ms_fused_elbo_kernel=ms_fused, own_kernel_launches_per_step=own_launches,
-                 host_syncs_per_step=0, loss=loss,
+                 host_syncs_per_step=0, ms_host_enqueue_per_step=ms_host, host_cores=len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else None, loss=loss,
                  limiter='encoder forward + backward (HBM passes over the [voxels, 60] activations): %.0f %% of the step'
                          % (100.0 * ms_enc / ms_train))
     infer = dict(common, config='BASELINE config 4: whole-volume posterior inference, 64 samples per voxel (means / '
@@ -409,6 +419,8 @@ def main():
         raise SystemExit('bench.py needs a CUDA device: the qBOLD hot path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    from qbold_vi_b200.distributed import pin_cores
+    pin_cores(local_rank, int(os.environ.get('LOCAL_WORLD_SIZE', world)))    # disjoint host cores per rank
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)

@@ -14,6 +14,8 @@ import math
 import os
 
 import torch
+
+from ._lib import on_device as _on_device
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -50,7 +52,7 @@ def _dense_tc(x, mask, w, bias, n_in, n_out, transpose, relu):
     status = _TC_STATUS.get(dev)
     if status is None:
         status = _TC_STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         st = stream_ptr(dev)
         check(lib.qbold_dense_tc_pack(dptr(w), dptr(bias, allow_none=True), n_out, n_in, int(transpose), dptr(packed), st))
         check(lib.qbold_dense_tc(dptr(x), dptr(mask, allow_none=True), dptr(packed), n_in, n_out, int(relu), x.shape[0],
@@ -83,7 +85,7 @@ def _dense_tma(x, w, bias=None, addend=None, transpose=False, relu=False):
     status = _TC_STATUS.get(dev)
     if status is None:
         status = _TC_STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         check(_lib.lib().qbold_dense_tma(dptr(x), dptr(w), dptr(bias, allow_none=True), dptr(addend, allow_none=True), n_in,
                                          n_out, int(transpose), int(relu), n, dptr(y), dptr(status, torch.int32),
                                          stream_ptr(dev)))
@@ -142,7 +144,7 @@ class _DenseFn(torch.autograd.Function):
             from . import _lib
             from ._lib import check, dptr, stream_ptr
             y = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=x.device)
-            with torch.cuda.device(x.device):
+            with _on_device(x.device):
                 check(_lib.lib().qbold_dense_small_forward(dptr(x), dptr(weight), dptr(bias), n_in, n_out, x.shape[0],
                                                            dptr(y), stream_ptr(x.device)))
         elif USE_DENSE_TC and _tc_ok(n_in, n_out, x):
@@ -178,7 +180,7 @@ class _DenseFn(torch.autograd.Function):
         elif y is None and _small_ok(n_in, n_out, weight):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty((x.shape[0], n_in), dtype=torch.float32, device=dev)
-                with torch.cuda.device(dev):
+                with _on_device(dev):
                     check(_lib.lib().qbold_dense_small_dgrad_masked(dptr(g), dptr(weight),
                                                                     dptr(x) if ctx.input_is_relu else None, n_in, n_out,
                                                                     x.shape[0], dptr(gx), stream_ptr(dev)))
@@ -197,11 +199,10 @@ class _DenseFn(torch.autograd.Function):
         if mask is None and _tma_ok(n_in, n_out, g, x):
             dw, db = _wgrad(g, x)
             return gx, dw, db, None, None
-        # per-call scratch from the caching allocator (stream-ordered, so concurrent backward passes cannot share it)
-        ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
+        ws = _workspace('dense_wgrad', dev)
         dw = torch.empty_like(weight)
         db = torch.empty(n_out, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(lib.qbold_dense_wgrad(dptr(g), dptr(mask, allow_none=True), n_out, dptr(x), n_in, x.shape[0], dptr(dw),
                                         dptr(db), 0, dptr(ws), stream_ptr(dev)))
         return gx, dw, db, None, None
@@ -218,7 +219,7 @@ class _GateMixFn(torch.autograd.Function):
         c, zc = r.shape[-1], z.shape[-1]
         n = r.numel() // c
         out = torch.empty_like(r)
-        with torch.cuda.device(r.device):
+        with _on_device(r.device):
             check(_lib.lib().qbold_gate_mix_forward(dptr(skip), dptr(r), dptr(z), float(offset), n, c, zc, dptr(out),
                                                     stream_ptr(r.device)))
         ctx.save_for_backward(skip, r, z)
@@ -234,7 +235,7 @@ class _GateMixFn(torch.autograd.Function):
         c, zc = r.shape[-1], z.shape[-1]
         n = r.numel() // c
         d_skip, d_r, d_z = torch.empty_like(skip), torch.empty_like(r), torch.empty_like(z)
-        with torch.cuda.device(r.device):
+        with _on_device(r.device):
             check(_lib.lib().qbold_gate_mix_backward(dptr(go), dptr(skip), dptr(r), dptr(z), ctx.offset, n, c, zc,
                                                      dptr(d_skip), dptr(d_r), dptr(d_z), stream_ptr(r.device)))
         return d_skip, d_r, d_z, None
@@ -323,9 +324,26 @@ class _Block(nn.Module):
 _FAST_BLOCK = os.environ.get('QBOLD_FAST_BLOCK', '1') == '1'
 
 
-def _ws(dev):
+_WORKSPACES = {}
+
+
+def _workspace(kind, dev):
+    """Device scratch of one of the reduction kernels, allocated once per (kind, device, stream): launches on one stream
+    are ordered, so consecutive calls can share it; a different stream (a concurrent backward pass) gets its own."""
     from . import _lib
-    return torch.empty(int(_lib.lib().qbold_colsum_workspace_floats()), dtype=torch.float32, device=dev)
+    key = (kind, dev.index, _lib.stream_ptr(dev).value)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        lib = _lib.lib()
+        n = {'colsum': lib.qbold_colsum_workspace_floats, 'dense_wgrad': lib.qbold_dense_wgrad_workspace_floats,
+             'dense_wgrad_tma': lib.qbold_dense_wgrad_tma_workspace_floats,
+             'conv_wgrad': lib.qbold_conv_wgrad_workspace_floats}[kind]()
+        ws = _WORKSPACES[key] = torch.empty(int(n), dtype=torch.float32, device=dev)
+    return ws
+
+
+def _ws(dev):
+    return _workspace('colsum', dev)
 
 
 def _relu_bwd(g, y, addend=None, colsum=None):
@@ -335,7 +353,7 @@ def _relu_bwd(g, y, addend=None, colsum=None):
     n, c = g.shape
     out = torch.empty_like(g)
     ws = _ws(g.device) if colsum is not None else None
-    with torch.cuda.device(g.device):
+    with _on_device(g.device):
         check(_lib.lib().qbold_relu_bwd_colsum(dptr(g), dptr(y), dptr(addend, allow_none=True), n, c, dptr(out),
                                                dptr(colsum, allow_none=True), 0, dptr(ws, allow_none=True),
                                                stream_ptr(g.device)))
@@ -348,7 +366,7 @@ def _colsum(g):
     n, c = g.shape
     out = torch.empty(c, dtype=torch.float32, device=g.device)
     ws = _ws(g.device)
-    with torch.cuda.device(g.device):
+    with _on_device(g.device):
         check(_lib.lib().qbold_relu_bwd_colsum(dptr(g), None, None, n, c, None, dptr(out), 0, dptr(ws), stream_ptr(g.device)))
     return out
 
@@ -373,17 +391,17 @@ def _wgrad(g, x, accumulate_into=None):
     else:
         dw, db = accumulate_into
     if _tma_ok(n_in, n_out, g, x):                          # TMA-fed tcgen05 kernel (MN-major operands)
-        ws = torch.empty(int(lib.qbold_dense_wgrad_tma_workspace_floats()), dtype=torch.float32, device=dev)
+        ws = _workspace('dense_wgrad_tma', dev)
         status = _TC_STATUS.get(dev)
         if status is None:
             status = _TC_STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(lib.qbold_dense_wgrad_tma(dptr(g), n_out, dptr(x), n_in, x.shape[0], dptr(dw), dptr(db),
                                             0 if accumulate_into is None else 1, dptr(ws), dptr(status, torch.int32),
                                             stream_ptr(dev)))
         return dw, db
-    ws = torch.empty(int(lib.qbold_dense_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    ws = _workspace('dense_wgrad', dev)
+    with _on_device(dev):
         check(lib.qbold_dense_wgrad(dptr(g), None, n_out, dptr(x), n_in, x.shape[0], dptr(dw), dptr(db),
                                     0 if accumulate_into is None else 1, dptr(ws), stream_ptr(dev)))
     return dw, db
@@ -422,11 +440,11 @@ def _conv_backward(g_flat, x_flat, w2, dims):
         lib = _lib.lib()
         dev = g_flat.device
         dw = torch.empty((c_out, c_in, 3, 3), dtype=torch.float32, device=dev)
-        ws = torch.empty(int(lib.qbold_conv_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
+        ws = _workspace('conv_wgrad', dev)
         status = _TC_STATUS.get(dev)
         if status is None:
             status = _TC_STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(lib.qbold_conv_wgrad(dptr(g_flat), c_out, dptr(x_flat), c_in, bz, nx, ny, dptr(dw), 0, dptr(ws),
                                        dptr(status, torch.int32), stream_ptr(dev)))
     return _as_flat(d_in), dw
@@ -450,11 +468,12 @@ class _BlockFn(torch.autograd.Function):
         z = _linear(r0f, w_g, torch.addmv(b_g, w_g, b_b))                                          # W_g (r0 + b_b) + b_g
         out2 = torch.empty_like(r0f)
         out2_relu = torch.empty_like(r0f) if want_relu_out else None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(_lib.lib().qbold_block_mix_forward(dptr(skip), dptr(r0f), dptr(b_b.contiguous()), dptr(z), float(offset), n,
                                                      c, dptr(out2), dptr(out2_relu, allow_none=True), stream_ptr(dev)))
         ctx.save_for_backward(net1, net2, a0, out1, skip, c1f, r0f, z, w_p, w_a, w_b, w_g, b_b)
         ctx.dims, ctx.offset, ctx.same_input, ctx.a0_is_net2 = dims, float(offset), same_input, a0_is_net2
+        ctx.wa2, ctx.wb2 = wa2, wb2                      # channels-last copies of the 3x3 weights, reused by backward
         ctx.premasked_out1 = bool(premasked_out1)       # the gradient of out1 arrives already times [out1 > 0]
         if want_relu_out:
             ctx.mark_non_differentiable(out2_relu)
@@ -474,7 +493,7 @@ class _BlockFn(torch.autograd.Function):
         # block 0: out1 IS skip, so the stream-1 gradient joins the skip gradient inside the mix kernel, before its ReLU'
         # mask -- d_skip then already is g_p = [skip > 0] * (d_out2 (1 - g) + d_out1)
         d_out1c = d_out1.contiguous() if ctx.same_input else None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(_lib.lib().qbold_block_mix_backward_add(dptr(d_out2), dptr(skip), dptr(r0f), dptr(b_b.contiguous()),
                                                           dptr(z), ctx.offset, n, c, 1, dptr(d_out1c, allow_none=True),
                                                           dptr(d_skip), dptr(d_r), dptr(d_z), stream_ptr(dev)))
@@ -484,8 +503,7 @@ class _BlockFn(torch.autograd.Function):
         _addmm_(d_r, d_z, w_g)                                               # total gradient of r = r0 + b_b, in place
         db_b = _colsum(d_r)
         # second convolution (no bias of its own): input gradient + weight gradient
-        wa2 = w_a.squeeze(-1).contiguous(memory_format=torch.channels_last)
-        wb2 = w_b.squeeze(-1).contiguous(memory_format=torch.channels_last)
+        wa2, wb2 = ctx.wa2, ctx.wb2
         d_c1, dw_b = _conv_backward(d_r, c1f, wb2, dims)
         db_a = torch.empty(c, dtype=torch.float32, device=dev)
         d_c1m = _relu_bwd(d_c1, c1f, colsum=db_a)                            # ReLU' and the bias gradient in one pass
@@ -582,7 +600,7 @@ class Encoder(nn.Module):
         b_arr = (C.c_void_p * n_mid)(*[b.data_ptr() for b in bs])
         w_in, b_in = self.first.weight.detach().float().contiguous(), self.first.bias.detach().float().contiguous()
         w_out, b_out = self.final.weight.detach().float().contiguous(), self.final.bias.detach().float().contiguous()
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = stream_ptr(dev)
             check(lib.qbold_encoder_mlp_pack(dptr(w_in), dptr(b_in), w_arr, b_arr, dptr(w_out), dptr(b_out), n_in, hidden,
                                              n_mid, n_out, dptr(blob), st))
@@ -632,7 +650,7 @@ class Encoder(nn.Module):
             from ._lib import check, dptr, stream_ptr
             src = data.contiguous()
             xt = torch.empty((b * nz * nx * ny, tp), dtype=torch.float32, device=data.device)
-            with torch.cuda.device(data.device):
+            with _on_device(data.device):
                 check(_lib.lib().qbold_normalise_zouter(dptr(src), b, nx, ny, nz, n_tau, self.se_idx,
                                                         int(self.multi_image_normalisation), dptr(xt),
                                                         stream_ptr(data.device)))

@@ -19,6 +19,8 @@ import math
 import numpy as np
 import torch
 
+from ._lib import on_device as _on_device
+
 from . import _lib
 from ._lib import QboldLikelihood, QboldParams, check, dptr, stream_ptr
 from .signals import SignalGenerationLayer
@@ -56,7 +58,7 @@ class _ReparamFn(torch.autograd.Function):
     def forward(ctx, q, eps):
         n = q.shape[0]
         out = torch.empty((n, 2), dtype=torch.float32, device=q.device)
-        with torch.cuda.device(q.device):
+        with _on_device(q.device):
             check(_lib.lib().qbold_reparam_sample(dptr(q), dptr(eps), 0, 0, n, dptr(out), stream_ptr(q.device)))
         ctx.save_for_backward(q, eps, out)
         return out
@@ -100,7 +102,7 @@ class _KlFn(torch.autograd.Function):
         n = pred.shape[0]
         kl_map = torch.empty(n, dtype=torch.float32, device=pred.device)
         grad = torch.empty((n, 5), dtype=torch.float32, device=pred.device)
-        with torch.cuda.device(pred.device):
+        with _on_device(pred.device):
             check(_lib.lib().qbold_kl(dptr(pred), dptr(prior), dptr(mask, allow_none=True),
                                       dptr(eps_kl, allow_none=True), seed, int(offset), n_samples, n, dptr(kl_map),
                                       dptr(grad),
@@ -123,7 +125,7 @@ class _NllFn(torch.autograd.Function):
         n, nt = pred.shape
         nll = torch.empty(n, dtype=torch.float32, device=pred.device)
         d_pred, d_sigma = torch.empty_like(pred), torch.empty_like(sigma)
-        with torch.cuda.device(pred.device):
+        with _on_device(pred.device):
             check(_lib.lib().qbold_nll(C.byref(params), dptr(y), dptr(pred), dptr(sigma), dptr(mask), n, dptr(nll),
                                        dptr(d_pred), dptr(d_sigma), stream_ptr(pred.device)))
         ctx.save_for_backward(d_pred, d_sigma)
@@ -144,7 +146,7 @@ class _TvFn(torch.autograd.Function):
         b, x, y, z, c = q.shape
         grad = torch.empty_like(q)
         tv = torch.zeros(1, dtype=torch.float64, device=q.device)
-        with torch.cuda.device(q.device):
+        with _on_device(q.device):
             if torch.is_tensor(mask_sum):                       # global sum(mask) left on the device: no host sync
                 inv = (1.0 / mask_sum.reshape(1).to(q.device, torch.float64)).float().contiguous()
                 check(_lib.lib().qbold_smoothness_dev(dptr(q), c, dptr(mask), b, x, y, z, dptr(inv),
@@ -169,7 +171,7 @@ class _SynthNllFn(torch.autograd.Function):
         n = pred.shape[0]
         grad = torch.empty_like(pred)
         total = torch.zeros(1, dtype=torch.float64, device=pred.device)
-        with torch.cuda.device(pred.device):
+        with _on_device(pred.device):
             check(_lib.lib().qbold_synth_nll(dptr(labels), labels.shape[1], dptr(pred), int(use_mvg), float(ig_alpha),
                                              float(ig_beta), n, 1.0 / n, None, dptr(grad),
                                              dptr(total, torch.float64), stream_ptr(pred.device)))
@@ -190,7 +192,7 @@ class _DiagKlFn(torch.autograd.Function):
         n, width = pred.shape
         kl = torch.empty(n, dtype=torch.float32, device=pred.device)
         grad = torch.empty_like(pred)
-        with torch.cuda.device(pred.device):
+        with _on_device(pred.device):
             if prior is None:                                   # population prior inside `pred`
                 p, g = pred.data_ptr(), grad.data_ptr()
                 check(_lib.lib().qbold_diag_kl(p, 8, p + 16, 8, dptr(mask, allow_none=True), n, dptr(kl), g, 8, g + 16,
@@ -214,7 +216,7 @@ class _MogKlFn(torch.autograd.Function):
         n = pred.shape[0]
         kl = torch.empty(n, dtype=torch.float32, device=pred.device)
         grad = torch.empty_like(pred)
-        with torch.cuda.device(pred.device):
+        with _on_device(pred.device):
             check(_lib.lib().qbold_mog_kl(dptr(pred), n_comp, dptr(mask, allow_none=True), dptr(eps, allow_none=True),
                                           seed, int(offset), n, dptr(kl), dptr(grad), stream_ptr(pred.device)))
         ctx.save_for_backward(grad)
@@ -235,7 +237,7 @@ class _SynthNllInferredFn(torch.autograd.Function):
         nc = 5 if use_mvg else 4
         grad = torch.empty((n, nc), dtype=torch.float32, device=dev)
         acc = torch.zeros(5, dtype=torch.float64, device=dev)                 # loss sum | 4 hyper-parameter sums
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(_lib.lib().qbold_synth_nll_inferred(dptr(labels), labels.shape[1], dptr(pred), pred.shape[1],
                                                       int(use_mvg), dptr(ig), n, 1.0 / n, None, dptr(grad),
                                                       C.c_void_p(acc.data_ptr()), C.c_void_p(acc.data_ptr() + 8),
@@ -269,7 +271,7 @@ class _FusedElboFn(torch.autograd.Function):
         sums = torch.zeros(4, dtype=torch.float64, device=dev)
         nll_map = torch.empty(n, dtype=torch.float32, device=dev) if want_maps else None
         kl_map = torch.empty(n, dtype=torch.float32, device=dev) if want_maps else None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             fn = _lib.lib().qbold_elbo_fused_dev if torch.is_tensor(inv_mask_sum) else _lib.lib().qbold_elbo_fused
             check(fn(
                 C.byref(trainer._params_for(layer)), dptr(q), dptr(sigma), dptr(y), dptr(mask),
@@ -390,7 +392,7 @@ class EncoderTrainer:
         var3 = torch.empty((n, 3), dtype=torch.float32, device=q.device)
         layer = signal_layer or self._default_layer()
         e = None if eps is None else eps.reshape(n, no_samples, 2).float().contiguous()
-        with torch.cuda.device(q.device):
+        with _on_device(q.device):
             check(_lib.lib().qbold_posterior_stats(C.byref(layer.params), dptr(q), dptr(e, allow_none=True),
                                                    _next_seed(self), int(offset), no_samples, n, dptr(mean3), dptr(var3),
                                                    stream_ptr(q.device)))
@@ -600,7 +602,7 @@ class EncoderTrainer:
         m = None if mask is None else mask.reshape(n).float().contiguous()
         e = None if eps is None else eps.reshape(n, no_samples, 2).float().contiguous()
         out = torch.empty(n, dtype=torch.float32, device=q.device)
-        with torch.cuda.device(q.device):
+        with _on_device(q.device):
             check(_lib.lib().qbold_nll_map(C.byref(self._params_for(signal_layer)), dptr(q), dptr(sg), dptr(y),
                                            dptr(m, allow_none=True), dptr(e, allow_none=True), _next_seed(self),
                                            int(offset),

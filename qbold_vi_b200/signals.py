@@ -18,6 +18,8 @@ import math
 import numpy as np
 import torch
 
+from ._lib import on_device as _on_device
+
 from . import _lib
 from ._lib import QboldError, QboldLikelihood, QboldParams, QboldPhysics, check, dptr, stream_ptr
 
@@ -146,7 +148,7 @@ class SignalGenerationLayer:
             seed = (self._seed + 0x9E3779B97F4A7C15 * (self._calls + 1)) & 0xFFFFFFFFFFFFFFFF
             self._calls += 1
         fi = None if from_index is None else from_index.reshape(n).to(torch.int32).contiguous()
-        with torch.cuda.device(flat.device):
+        with _on_device(flat.device):
             check(_lib.lib().qbold_misalign(C.byref(self.params), dptr(flat), flat.shape[1], n, self._misaligned_prob,
                                             dptr(None if sel_u01 is None else sel_u01.reshape(n).float().contiguous(),
                                                  allow_none=True),
@@ -189,7 +191,7 @@ class SignalGenerationLayer:
     def _forward_raw(self, flat):
         n, width = flat.shape
         out = torch.empty((n, self.n_tau), dtype=torch.float32, device=flat.device)
-        with torch.cuda.device(flat.device):
+        with _on_device(flat.device):
             check(_lib.lib().qbold_forward(C.byref(self.params), dptr(flat), width, n, dptr(out),
                                            stream_ptr(flat.device)))
         return out
@@ -207,7 +209,7 @@ class SignalGenerationLayer:
         grad = torch.empty((n, width), dtype=torch.float32, device=flat.device)
         g = None if g_signal is None else g_signal.reshape(n, self.n_tau).contiguous()
         fn = _lib.lib().qbold_forward_backward_hct if self._variable_hct else _lib.lib().qbold_forward_backward
-        with torch.cuda.device(flat.device):
+        with _on_device(flat.device):
             check(fn(C.byref(self.params), dptr(flat), dptr(g, allow_none=True), n, dptr(sig, allow_none=True),
                      dptr(grad), stream_ptr(flat.device)))
         return sig, grad
@@ -236,7 +238,7 @@ class SignalGenerationLayer:
         if seed is None:
             seed = (self._seed + 0x9E3779B97F4A7C15 * (self._calls + 1)) & 0xFFFFFFFFFFFFFFFF
             self._calls += 1
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(_lib.lib().qbold_column_mean(dptr(sig), n, self.n_tau, dptr(mean), dptr(scratch, torch.float64),
                                                stream_ptr(dev)))
             if self.params.norm_snr[0] == 0.0:
@@ -303,7 +305,7 @@ def generate_from_marginals(sig_layer, oefs, dbvs, perm=None, n_chunks=10, snr_u
     train_x = torch.empty((n_x, nt), dtype=torch.float32, device=dev)
     train_y = torch.empty((total, 3), dtype=torch.float32, device=dev)
     pptr = None if perm is None else dptr(perm, torch.int64)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         st = stream_ptr(dev)
         if sig_layer._variable_hct:                                 # labels only; the signals follow below
             check(lib.qbold_generate(C.byref(sig_layer.params), dptr(oefs), oefs.numel(), dptr(dbvs), dbvs.numel(),
@@ -332,7 +334,7 @@ def generate_from_marginals(sig_layer, oefs, dbvs, perm=None, n_chunks=10, snr_u
             raise UnboundLocalError("local variable 'norm_snr' referenced before assignment "
                                     "(only 11 or 24 taus are supported, signals.py:117-121)")
         scratch = torch.empty(32 * n_chunks, dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(lib.qbold_add_noise_chunked(C.byref(sig_layer.params), dptr(train_x), chunk, n_chunks,
                                               dptr(None if snr_u01 is None else snr_u01[:n_x].contiguous(),
                                                    allow_none=True),
