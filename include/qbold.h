@@ -210,6 +210,15 @@ int qbold_elbo_fused_dev(const QboldParams* p, const float* q, const float* sigm
                          float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
                          float* kl_map, double* sums, void* stream);
 
+/* Same kernel for a CAPTURED training step (CUDA graph): every per-step scalar comes from device memory, so the
+ * launch replays with fresh draws.  seed_dev: one uint64, the Philox key (the trainer's per-call seed,
+ * qbold_elbo_fused's `seed`), advanced on the device between replays; draws are always in-kernel (no eps / eps_kl). */
+int qbold_elbo_fused_graph(const QboldParams* p, const float* q, const float* sigma, const float* y,
+                           const float* mask, const float* prior, const uint64_t* seed_dev, uint64_t offset,
+                           int32_t kl_samples, const float* inv_mask_sum_dev, float kl_weight, int64_t n,
+                           float* grad_q, float* grad_sigma, float* nll_map, float* kl_map, double* sums,
+                           void* stream);
+
 /* fine_tune_loss_fn alone (model.py:527-568) for predictions already in HBM: nll_map[n] = mask * sum_tau NLL,
  * and (optional) d_pred / d_sigma [n,n_tau] = d nll_map[v] / d pred[v,:], d sigma[v,:].  mask may be NULL. */
 int qbold_nll(const QboldParams* p, const float* y, const float* pred, const float* sigma, const float* mask,

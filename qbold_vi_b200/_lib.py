@@ -77,6 +77,8 @@ _SIGNATURES = {
                                    C.c_float, C.c_float, C.c_int64, _f, _f, _f, _f, _f, C.c_void_p]),
     'qbold_elbo_fused_dev': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32,
                                        _f, C.c_float, C.c_int64, _f, _f, _f, _f, _f, C.c_void_p]),
+    'qbold_elbo_fused_graph': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, _f, C.c_void_p, C.c_uint64, C.c_int32, _f,
+                                         C.c_float, C.c_int64, _f, _f, _f, _f, _f, C.c_void_p]),
     'qbold_nll': (C.c_int, [_P(QboldParams), _f, _f, _f, _f, C.c_int64, _f, _f, _f, C.c_void_p]),
     'qbold_kl': (C.c_int, [_f, _f, _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f, _f, C.c_void_p]),
     'qbold_posterior_stats': (C.c_int, [_P(QboldParams), _f, _f, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _f, _f,

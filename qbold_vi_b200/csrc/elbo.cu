@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
                                                    const float* __restrict__ q, const float* __restrict__ sigma,
                                                    const float* __restrict__ y, const float* __restrict__ mask,
                                                    const float* __restrict__ prior, const float* __restrict__ eps,
-                                                   const float* __restrict__ eps_kl, uint64_t seed, uint64_t offset,
+                                                   const float* __restrict__ eps_kl, uint64_t seed,
+                                                   const uint64_t* __restrict__ seed_dev, uint64_t offset,
                                                    int kl_samples, float inv_mask_sum,
                                                    const float* __restrict__ inv_mask_sum_dev, float kl_weight, int64_t n,
                                                    float* __restrict__ grad_q, float* __restrict__ grad_sigma,
@@ -472,6 +473,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_elbo(const __grid_constant__ Qb
     const QuadCtx qc = make_quad_ctx<PATH>(P, ss, lane, my_col, my_tau);
     const float df = P.student_t_df;
     if (inv_mask_sum_dev != nullptr) inv_mask_sum = __ldg(inv_mask_sum_dev);   // 1 / global sum(mask), left on the device
+    if (seed_dev != nullptr) seed = __ldg(seed_dev);   // Philox key kept on the device: a captured launch replays with fresh draws
     const bool wide = nt > 16;
 
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
@@ -619,7 +621,8 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
                                                            const float* __restrict__ y, const float* __restrict__ mask,
                                                            const float* __restrict__ prior, const float* __restrict__ eps,
                                                            const float* __restrict__ eps_kl, uint64_t seed,
-                                                           uint64_t offset, int kl_samples, float inv_mask_sum,
+                                                           const uint64_t* __restrict__ seed_dev, uint64_t offset,
+                                                           int kl_samples, float inv_mask_sum,
                                                            const float* __restrict__ inv_mask_sum_dev,
                                                            float kl_weight, int64_t n, float* __restrict__ grad_q,
                                                            float* __restrict__ grad_sigma, float* __restrict__ nll_map,
@@ -645,6 +648,7 @@ __global__ void __launch_bounds__(kThreads, QB_ELBO_MIN_BLOCKS) k_elbo_pair(cons
     const float df = P.student_t_df;
     const QuadCtx qc = make_quad_ctx<kSched>(P, ss, lane, my_col, my_tau);
     if (inv_mask_sum_dev != nullptr) inv_mask_sum = __ldg(inv_mask_sum_dev);   // 1 / global sum(mask), left on the device
+    if (seed_dev != nullptr) seed = __ldg(seed_dev);   // Philox key kept on the device: a captured launch replays with fresh draws
     const int64_t npairs = (n + 1) >> 1;
     double acc_nll = 0.0, acc_kl = 0.0, acc_mask = 0.0;
     int bad = 0;
@@ -1187,9 +1191,10 @@ using namespace qb;
 
 static int elbo_fused_impl(const QboldParams* p, const float* q, const float* sigma, const float* y,
                            const float* mask, const float* prior, const float* eps, const float* eps_kl,
-                           uint64_t seed, uint64_t offset, int32_t kl_samples, float inv_mask_sum,
-                           const float* inv_mask_sum_dev, float kl_weight, int64_t n, float* grad_q,
-                           float* grad_sigma, float* nll_map, float* kl_map, double* sums, void* stream) {
+                           uint64_t seed, const uint64_t* seed_dev, uint64_t offset, int32_t kl_samples,
+                           float inv_mask_sum, const float* inv_mask_sum_dev, float kl_weight, int64_t n,
+                           float* grad_q, float* grad_sigma, float* nll_map, float* kl_map, double* sums,
+                           void* stream) {
     if (!p || p->abi_version != QBOLD_ABI_VERSION) return fail(QBOLD_EINVAL, "qbold_elbo_fused: bad params block");
     if (n < 0 || kl_samples < 0) return fail(QBOLD_EINVAL, "qbold_elbo_fused: negative size");
     if (n == 0) return QBOLD_OK;
@@ -1206,7 +1211,7 @@ static int elbo_fused_impl(const QboldParams* p, const float* q, const float* si
         static int64_t grid_cache = 0;                                                                                \
         const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo<HP, MU>, INT64_MAX / 64)); \
         k_elbo<HP, MU><<<(unsigned)(want < grid ? want : grid), kThreads, 0, st>>>(                                  \
-            *p, q, sigma, y, mask, HP ? prior : nullptr, eps, HP ? eps_kl : nullptr, seed, offset,                    \
+            *p, q, sigma, y, mask, HP ? prior : nullptr, eps, HP ? eps_kl : nullptr, seed, seed_dev, offset,          \
             HP ? kl_samples : 0, inv_mask_sum, inv_mask_sum_dev, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, work);        \
     } while (0)
     if (path == kSched && p->full_model && p->n_tau <= 16) {
@@ -1215,13 +1220,15 @@ static int elbo_fused_impl(const QboldParams* p, const float* q, const float* si
             static int64_t grid_cache = 0;
             const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<true>, INT64_MAX / 64));
             k_elbo_pair<true><<<(unsigned)(wantp < grid ? wantp : grid), kThreads, 0, st>>>(
-                *p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, inv_mask_sum_dev, kl_weight, n, grad_q,
+                *p, q, sigma, y, mask, prior, eps, eps_kl, seed, seed_dev, offset, kl_samples, inv_mask_sum, inv_mask_sum_dev,
+                kl_weight, n, grad_q,
                 grad_sigma, nll_map, kl_map, sums, work);
         } else {
             static int64_t grid_cache = 0;
             const int64_t grid = grid_cache ? grid_cache : (grid_cache = persistent_grid(k_elbo_pair<false>, INT64_MAX / 64));
             k_elbo_pair<false><<<(unsigned)(wantp < grid ? wantp : grid), kThreads, 0, st>>>(
-                *p, q, sigma, y, mask, nullptr, eps, nullptr, seed, offset, 0, inv_mask_sum, inv_mask_sum_dev, kl_weight, n, grad_q,
+                *p, q, sigma, y, mask, nullptr, eps, nullptr, seed, seed_dev, offset, 0, inv_mask_sum, inv_mask_sum_dev, kl_weight,
+                n, grad_q,
                 grad_sigma, nll_map, kl_map, sums, work);
         }
     } else if (prior) {
@@ -1242,7 +1249,7 @@ extern "C" int qbold_elbo_fused(const QboldParams* p, const float* q, const floa
                                 uint64_t seed, uint64_t offset, int32_t kl_samples, float inv_mask_sum,
                                 float kl_weight, int64_t n, float* grad_q, float* grad_sigma, float* nll_map,
                                 float* kl_map, double* sums, void* stream) {
-    return elbo_fused_impl(p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, inv_mask_sum, nullptr,
+    return elbo_fused_impl(p, q, sigma, y, mask, prior, eps, eps_kl, seed, nullptr, offset, kl_samples, inv_mask_sum, nullptr,
                            kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, stream);
 }
 
@@ -1252,8 +1259,19 @@ extern "C" int qbold_elbo_fused_dev(const QboldParams* p, const float* q, const 
                                     const float* inv_mask_sum_dev, float kl_weight, int64_t n, float* grad_q,
                                     float* grad_sigma, float* nll_map, float* kl_map, double* sums, void* stream) {
     if (!inv_mask_sum_dev) return fail(QBOLD_EINVAL, "qbold_elbo_fused_dev: inv_mask_sum_dev is NULL");
-    return elbo_fused_impl(p, q, sigma, y, mask, prior, eps, eps_kl, seed, offset, kl_samples, 0.f, inv_mask_sum_dev,
+    return elbo_fused_impl(p, q, sigma, y, mask, prior, eps, eps_kl, seed, nullptr, offset, kl_samples, 0.f, inv_mask_sum_dev,
                            kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, stream);
+}
+
+extern "C" int qbold_elbo_fused_graph(const QboldParams* p, const float* q, const float* sigma, const float* y,
+                                      const float* mask, const float* prior, const uint64_t* seed_dev, uint64_t offset,
+                                      int32_t kl_samples, const float* inv_mask_sum_dev, float kl_weight, int64_t n,
+                                      float* grad_q, float* grad_sigma, float* nll_map, float* kl_map, double* sums,
+                                      void* stream) {
+    if (!inv_mask_sum_dev || !seed_dev)
+        return fail(QBOLD_EINVAL, "qbold_elbo_fused_graph: seed_dev / inv_mask_sum_dev is NULL");
+    return elbo_fused_impl(p, q, sigma, y, mask, prior, nullptr, nullptr, 0, seed_dev, offset, kl_samples, 0.f,
+                           inv_mask_sum_dev, kl_weight, n, grad_q, grad_sigma, nll_map, kl_map, sums, stream);
 }
 
 extern "C" int qbold_kl(const float* q, const float* prior, const float* mask, const float* eps_kl, uint64_t seed,

@@ -128,6 +128,14 @@ def _adam(params, **kw):
     return torch.optim.Adam(params, **kw)
 
 
+_GOLDEN = 0x9E3779B97F4A7C15                     # per-call seed stride of EncoderTrainer (model._next_seed)
+
+
+def _as_i64(u):
+    """The int64 with the bit pattern of the uint64 `u` (torch has no uint64 arithmetic; the kernel reads uint64)."""
+    return u - (1 << 64) if u >= (1 << 63) else u
+
+
 class FlatGradBucket:
     """One contiguous float32 buffer aliasing every parameter's .grad: a single all-reduce per step."""
 
@@ -178,26 +186,48 @@ class DataParallelTrainer:
     (EncoderTrainer.smoothness_loss); tests of the host logic inject stand-ins."""
 
     def __init__(self, encoder, trainer, signal_layer, ft_lr=5e-3, adamw_decay=2e-4, smoothness_weight=5.0,
-                 kl_weight=1.0, kl_samples=70, loss_fn=None, tv_fn=None):
+                 kl_weight=1.0, kl_samples=70, loss_fn=None, tv_fn=None, cuda_graph=False, graph_warmup=3):
         self.encoder, self.trainer, self.layer = encoder, trainer, signal_layer
         self.smoothness_weight, self.kl_weight, self.kl_samples = smoothness_weight, kl_weight, kl_samples
         self.bucket = FlatGradBucket(encoder.parameters())
         self.lr, self.wd = LinearSchedule(ft_lr), LinearSchedule(adamw_decay)
-        self.opt = _adam(self.bucket.params, lr=ft_lr, betas=(0.9, 0.9))                 # beta_2 = 0.9 (train.py:310)
         self.decay = adamw_decay > 0.0
         self.step_no = 0
         self._comm_stream = None
         self.loss_fn = loss_fn or self._fused_loss
         self.tv_fn = tv_fn or self._tv
+        # cuda_graph=True: the whole step (encoder, fused ELBO, TV, backward, the three NCCL all-reduces, AdamW) is
+        # captured once and replayed with ONE cudaGraphLaunch per step.  Everything that changes from step to step
+        # lives on the device: the Philox key, the schedule position (learning rate, weight decay), Adam's counter.
+        self.cuda_graph = bool(cuda_graph)
+        self._g = None
+        if self.cuda_graph:
+            dev = self.bucket.flat.device
+            if dev.type != 'cuda':
+                raise ValueError('cuda_graph=True needs the encoder on a CUDA device')
+            if loss_fn is not None:
+                raise ValueError('cuda_graph=True runs the fused sm_100a loss; a custom loss_fn cannot be captured safely')
+            f32 = dict(dtype=torch.float32, device=dev)
+            self._g = {'warmup': int(graph_warmup), 'calls': 0, 'graph': None, 'shapes': None,
+                       'seed': torch.zeros(1, dtype=torch.int64, device=dev),
+                       'golden': torch.tensor([_as_i64(_GOLDEN)], dtype=torch.int64, device=dev),
+                       't': torch.zeros(2, **f32),                                   # schedule position, twice
+                       'sched0': torch.tensor([self.lr.initial, 1.0 - self.wd.initial], **f32),
+                       'rates': torch.tensor([self.lr.rate, -self.wd.rate], **f32),
+                       'sched': torch.tensor([self.lr.initial, 1.0 - self.wd.initial], **f32),   # lr_t | 1 - wd_t
+                       'dev_calls': None, 'dev_step': None}
+            self.opt = _adam(self.bucket.params, lr=self._g['sched'][0], betas=(0.9, 0.9), capturable=True)
+        else:
+            self.opt = _adam(self.bucket.params, lr=ft_lr, betas=(0.9, 0.9))             # beta_2 = 0.9 (train.py:310)
 
     def _tv(self, q, prior, mask, mask_sum):
         return self.trainer.smoothness_loss(torch.cat([prior, mask], -1), q, mask_sum=mask_sum)
 
-    def _fused_loss(self, q, sigma, data, mask, prior, mask_sum):
+    def _fused_loss(self, q, sigma, data, mask, prior, mask_sum, seed=None):
         # equal-size shards (weak scaling): this rank's first global voxel, so ranks draw disjoint Philox counters
         rank = dist.get_rank() if world_size() > 1 else 0
         return self.trainer.fused_elbo(self.layer, q, sigma, data, mask, prior, kl_samples=self.kl_samples,
-                                       kl_weight=self.kl_weight, mask_sum=mask_sum, offset=rank * mask.numel())
+                                       kl_weight=self.kl_weight, mask_sum=mask_sum, offset=rank * mask.numel(), seed=seed)
 
     def step(self, data, mask, prior):
         """data [B,X,Y,Z,n_tau] (pre-masked), mask [B,X,Y,Z,1], prior [B,X,Y,Z,5]: this rank's volumes.
@@ -205,6 +235,8 @@ class DataParallelTrainer:
         No host synchronisation: the global mask count stays on the device (its all-reduce is enqueued ahead of the
         encoder), the gradient all-reduce runs on a side stream as soon as backward has produced it, and the returned
         statistics are read lazily (LazyStats)."""
+        if self.cuda_graph:
+            return self._graph_step(data, mask, prior)
         msum = global_mask_sum_device(mask)
         self.bucket.zero_()
         _, q, sigma = self.encoder(data)
@@ -226,6 +258,79 @@ class DataParallelTrainer:
         stats = torch.stack([sc(total), sc(info['nll']) if 'nll' in info else zero,
                              sc(info['kl']) if 'kl' in info else zero, sc(tv), sc(msum) / max(world_size(), 1)])
         all_reduce_sum_(stats)
+        return LazyStats(['loss', 'nll', 'kl', 'smoothness', 'mask_sum'], stats, lr=lr)
+
+    # ---- captured step -------------------------------------------------------------------------------------------
+    def static_inputs(self):
+        """The (data, mask, prior) buffers the captured step reads, or None before the first step: a loader that
+        writes the next batch straight into them saves the three device copies step() otherwise makes."""
+        g = self._g
+        return None if not g or g['shapes'] is None else (g['data'], g['mask'], g['prior'])
+
+    def _sync_device_scalars(self):
+        """Device copies of the Philox call counter and the schedule position follow the host mirrors (they only
+        diverge after load_state_dict or when other code drew from the trainer's stream between two steps)."""
+        g, tr = self._g, self.trainer
+        if g['dev_calls'] != tr._calls:
+            g['seed'].fill_(_as_i64((tr._seed + _GOLDEN * tr._calls) & 0xFFFFFFFFFFFFFFFF))
+            g['dev_calls'] = tr._calls
+        if g['dev_step'] != self.step_no:
+            g['t'].fill_(float(self.step_no))
+            g['dev_step'] = self.step_no
+
+    def _graph_body(self):
+        """One step on the static buffers; identical whether it runs eagerly (warm-up) or under capture."""
+        g = self._g
+        data, mask, prior = g['data'], g['mask'], g['prior']
+        g['seed'].add_(g['golden'])                                   # the key of call number _calls + 1 (uint64 wrap)
+        torch.addcmul(g['sched0'], g['t'], g['rates'], out=g['sched'])  # lr_t, 1 - wd_t (LinearSchedule)
+        g['t'].add_(1.0)
+        msum = global_mask_sum_device(mask)
+        self.bucket.zero_()
+        _, q, sigma = self.encoder(data)
+        loss, info = self._fused_loss(q, sigma, data, mask, prior, msum, seed=g['seed'])
+        tv = self.tv_fn(q, prior, mask, msum)
+        total = loss + self.smoothness_weight * tv
+        total.backward()
+        self._reduce_gradients()
+        if self.decay:
+            with torch.no_grad():
+                torch._foreach_mul_(self.bucket.params, g['sched'][1])
+        self.opt.step()
+        sc = lambda t: t.detach().double().reshape(())                      # noqa: E731
+        stats = torch.stack([sc(total), sc(info['nll']), sc(info['kl']), sc(tv), sc(msum) / max(world_size(), 1)])
+        all_reduce_sum_(stats)
+        return stats
+
+    def _graph_step(self, data, mask, prior):
+        g = self._g
+        shapes = (tuple(data.shape), tuple(mask.shape), tuple(prior.shape))
+        if g['shapes'] != shapes:                          # first call, or a new batch shape: new buffers, new capture
+            g['shapes'], g['graph'], g['calls'] = shapes, None, 0
+            g['data'], g['mask'], g['prior'] = (torch.empty_like(t, dtype=torch.float32).contiguous()
+                                                for t in (data, mask, prior))
+        for name, src in (('data', data), ('mask', mask), ('prior', prior)):
+            if src.data_ptr() != g[name].data_ptr():
+                g[name].copy_(src, non_blocking=True)
+        self._sync_device_scalars()
+        lr = self.lr(self.step_no)
+        if g['graph'] is None and g['calls'] >= g['warmup']:
+            # capture (nothing executes): cuDNN algorithm search, workspaces, the NCCL communicator and the library's
+            # lazy state were all set up by the eager warm-up steps
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g['stats'] = self._graph_body()
+            g['graph'] = graph
+        if g['graph'] is not None:
+            g['graph'].replay()
+            stats = g['stats'].clone()
+        else:
+            stats = self._graph_body()
+        g['calls'] += 1
+        self.step_no += 1
+        self.trainer._calls += 1
+        g['dev_step'], g['dev_calls'] = self.step_no, self.trainer._calls
         return LazyStats(['loss', 'nll', 'kl', 'smoothness', 'mask_sum'], stats, lr=lr)
 
     def _reduce_gradients(self):
@@ -264,6 +369,12 @@ class DataParallelTrainer:
         if hasattr(self.layer, '_calls'):
             self.layer._calls = int(state.get('layer_calls', 0))
         self.bucket.realias()
+        if self._g is not None:
+            # the optimiser's moments are new tensors and its learning rate a loaded copy: re-alias the device schedule
+            # and capture again (the device counters follow the host mirrors at the next step)
+            for group in self.opt.param_groups:
+                group['lr'] = self._g['sched'][0]
+            self._g.update(graph=None, calls=0, dev_calls=None, dev_step=None)
 
     def save(self, path):
         torch.save(self.state_dict(), path)

@@ -272,14 +272,25 @@ class _FusedElboFn(torch.autograd.Function):
         nll_map = torch.empty(n, dtype=torch.float32, device=dev) if want_maps else None
         kl_map = torch.empty(n, dtype=torch.float32, device=dev) if want_maps else None
         with _on_device(dev):
-            fn = _lib.lib().qbold_elbo_fused_dev if torch.is_tensor(inv_mask_sum) else _lib.lib().qbold_elbo_fused
-            check(fn(
-                C.byref(trainer._params_for(layer)), dptr(q), dptr(sigma), dptr(y), dptr(mask),
-                dptr(prior, allow_none=True), dptr(eps, allow_none=True), dptr(eps_kl, allow_none=True), seed,
-                int(offset), kl_samples, dptr(inv_mask_sum) if torch.is_tensor(inv_mask_sum) else inv_mask_sum,
-                kl_weight, n, dptr(grad_q), dptr(grad_sigma),
-                dptr(nll_map, allow_none=True), dptr(kl_map, allow_none=True), dptr(sums, torch.float64),
-                stream_ptr(dev)))
+            if torch.is_tensor(seed):       # Philox key on the device (int64 bit pattern of the uint64): captured steps
+                if not torch.is_tensor(inv_mask_sum) or eps is not None or eps_kl is not None:
+                    raise ValueError('fused_elbo: a device seed needs a device mask_sum and in-kernel draws (no eps)')
+                check(_lib.lib().qbold_elbo_fused_graph(
+                    C.byref(trainer._params_for(layer)), dptr(q), dptr(sigma), dptr(y), dptr(mask),
+                    dptr(prior, allow_none=True), dptr(seed, torch.int64), int(offset), kl_samples, dptr(inv_mask_sum),
+                    kl_weight, n, dptr(grad_q), dptr(grad_sigma), dptr(nll_map, allow_none=True),
+                    dptr(kl_map, allow_none=True), dptr(sums, torch.float64), stream_ptr(dev)))
+                fn = None
+            else:
+                fn = _lib.lib().qbold_elbo_fused_dev if torch.is_tensor(inv_mask_sum) else _lib.lib().qbold_elbo_fused
+            if fn is not None:
+                check(fn(
+                    C.byref(trainer._params_for(layer)), dptr(q), dptr(sigma), dptr(y), dptr(mask),
+                    dptr(prior, allow_none=True), dptr(eps, allow_none=True), dptr(eps_kl, allow_none=True), seed,
+                    int(offset), kl_samples, dptr(inv_mask_sum) if torch.is_tensor(inv_mask_sum) else inv_mask_sum,
+                    kl_weight, n, dptr(grad_q), dptr(grad_sigma),
+                    dptr(nll_map, allow_none=True), dptr(kl_map, allow_none=True), dptr(sums, torch.float64),
+                    stream_ptr(dev)))
         ctx.save_for_backward(grad_q, grad_sigma)
         s = sums.float()
         ims = inv_mask_sum[0] if torch.is_tensor(inv_mask_sum) else inv_mask_sum

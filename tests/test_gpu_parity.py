@@ -542,6 +542,62 @@ def test_single_gpu_training_steps_reduce_the_loss(qb, dev, cfg_noise_off):
     assert np.isfinite(lazy[-1]['loss']) and lazy[-1]['mask_sum'] == float(mask.sum())
 
 
+def test_captured_training_step_matches_the_eager_step(qb, dev, cfg_noise_off, tmp_path):
+    """cuda_graph=True: the step is captured after three eager warm-up steps and replayed; the Philox key, the
+    schedule position and Adam's counter advance on the device.  Same seeds, same data -> the statistics of every
+    step (warm-up, first replay, later replays, after a checkpoint round trip) equal the eager trainer's."""
+    import copy
+    from qbold_vi_b200.encoder import Encoder
+    from qbold_vi_b200.distributed import DataParallelTrainer
+    torch.manual_seed(1)
+    enc_e = Encoder().to(dev)
+    enc_g = copy.deepcopy(enc_e)
+    layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
+    dp_e = DataParallelTrainer(enc_e, _trainer(qb, cfg_noise_off, seed=11), layer, ft_lr=2e-3)
+    dp_g = DataParallelTrainer(enc_g, _trainer(qb, cfg_noise_off, seed=11), layer, ft_lr=2e-3, cuda_graph=True)
+    g = torch.Generator(device=dev).manual_seed(9)
+    shape = (2, 16, 16, 4)
+    truth = torch.stack([torch.rand(shape, device=dev, generator=g) * 0.4 + 0.2,
+                         torch.rand(shape, device=dev, generator=g) * 0.06 + 0.01], -1)
+    mask = (torch.rand(shape + (1,), device=dev, generator=g) > 0.2).float()
+    data = layer(truth) * 100.0 * mask
+    with torch.no_grad():
+        prior = enc_e(data)[0].clone()
+
+    def close(a, b, what):
+        for k in ('loss', 'nll', 'kl', 'smoothness', 'mask_sum'):
+            assert abs(a[k] - b[k]) <= 2e-4 * max(abs(a[k]), 1e-3), (what, k, a[k], b[k])
+        assert abs(a['lr'] - b['lr']) < 1e-12
+
+    for i in range(7):                                     # 3 eager warm-up steps, the capture, 3 more replays
+        close(dp_e.step(data, mask, prior), dp_g.step(data, mask, prior), 'step %d' % i)
+    assert dp_g._g['graph'] is not None and dp_g.step_no == dp_e.step_no == 7
+    assert dp_g.trainer._calls == dp_e.trainer._calls
+    for a, b in zip(enc_e.parameters(), enc_g.parameters()):
+        assert float((a - b).abs().max()) <= 2e-3 * float(a.abs().max()) + 1e-6
+    # a replay is one graph launch: no kernel of this library is launched from the host during it
+    before = qb.launch_count()
+    torch.cuda.set_sync_debug_mode('error')
+    try:
+        s_g = dp_g.step(data, mask, prior)
+    finally:
+        torch.cuda.set_sync_debug_mode('default')
+    assert qb.launch_count() == before
+    close(dp_e.step(data, mask, prior), s_g, 'replay under sync-debug')
+    # new batch contents go through the static buffers
+    data2 = data * 1.01
+    close(dp_e.step(data2, mask, prior), dp_g.step(data2, mask, prior), 'second batch')
+    # checkpoint round trip into a fresh captured trainer: counters, schedule position and moments carry over
+    path = str(tmp_path / 'dp.pt')
+    dp_g.save(path)
+    enc_r = copy.deepcopy(enc_g)
+    dp_r = DataParallelTrainer(enc_r, _trainer(qb, cfg_noise_off, seed=11), layer, ft_lr=2e-3, cuda_graph=True)
+    dp_r.load(path)
+    for i in range(5):
+        close(dp_e.step(data, mask, prior), dp_r.step(data, mask, prior), 'resumed step %d' % i)
+    assert dp_r._g['graph'] is not None
+
+
 # ---------------------------------------------------------------------------------- whole-volume inference (config 4)
 def test_likelihood_map_and_posterior_inference(qb, dev, cfg_noise_off, physics):
     e = golden('ref_shim_elbo_optimal.npz')
