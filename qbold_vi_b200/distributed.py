@@ -199,7 +199,13 @@ class DataParallelTrainer:
         # cuda_graph=True: the whole step (encoder, fused ELBO, TV, backward, the three NCCL all-reduces, AdamW) is
         # captured once and replayed with ONE cudaGraphLaunch per step.  Everything that changes from step to step
         # lives on the device: the Philox key, the schedule position (learning rate, weight decay), Adam's counter.
+        # cuda_graph='split': the same, with the NCCL calls kept OUT of the capture -- graph A (encoder, losses, backward),
+        # eager all-reduce of the gradient bucket, graph B (weight decay, Adam, statistics); the mask count is reduced
+        # before A and the statistics after B.  Two graph launches and three eager collectives per step.
+        if cuda_graph not in (False, True, None, 'full', 'split'):
+            raise ValueError("cuda_graph must be False, True ('full') or 'split'")
         self.cuda_graph = bool(cuda_graph)
+        self.graph_mode = None if not cuda_graph else ('split' if cuda_graph == 'split' else 'full')
         self._g = None
         if self.cuda_graph:
             dev = self.bucket.flat.device
@@ -215,6 +221,7 @@ class DataParallelTrainer:
                        'sched0': torch.tensor([self.lr.initial, 1.0 - self.wd.initial], **f32),
                        'rates': torch.tensor([self.lr.rate, -self.wd.rate], **f32),
                        'sched': torch.tensor([self.lr.initial, 1.0 - self.wd.initial], **f32),   # lr_t | 1 - wd_t
+                       'msum': torch.zeros(1, dtype=torch.float64, device=dev),      # split mode: global sum(mask)
                        'dev_calls': None, 'dev_step': None}
             self.opt = _adam(self.bucket.params, lr=self._g['sched'][0], betas=(0.9, 0.9), capturable=True)
         else:
@@ -302,6 +309,52 @@ class DataParallelTrainer:
         all_reduce_sum_(stats)
         return stats
 
+    def _split_front(self):
+        """Graph A of the split mode: everything up to and including backward (no collective inside)."""
+        g = self._g
+        data, mask, prior, msum = g['data'], g['mask'], g['prior'], g['msum']
+        g['seed'].add_(g['golden'])
+        torch.addcmul(g['sched0'], g['t'], g['rates'], out=g['sched'])
+        g['t'].add_(1.0)
+        self.bucket.zero_()
+        _, q, sigma = self.encoder(data)
+        loss, info = self._fused_loss(q, sigma, data, mask, prior, msum, seed=g['seed'])
+        tv = self.tv_fn(q, prior, mask, msum)
+        total = loss + self.smoothness_weight * tv
+        total.backward()
+        sc = lambda t: t.detach().double().reshape(())                      # noqa: E731
+        return torch.stack([sc(total), sc(info['nll']), sc(info['kl']), sc(tv), sc(msum) / max(world_size(), 1)])
+
+    def _split_back(self):
+        """Graph B of the split mode: decoupled weight decay and Adam on the all-reduced gradient."""
+        if self.decay:
+            with torch.no_grad():
+                torch._foreach_mul_(self.bucket.params, self._g['sched'][1])
+        self.opt.step()
+
+    def _split_step(self):
+        """One step in split mode on the static buffers (eager during warm-up, two graph launches afterwards)."""
+        g = self._g
+        g['msum'].copy_(global_mask_sum_device(g['mask']))               # eager collective 1 (an input of graph A)
+        if g['graph'] is None and g['calls'] >= g['warmup']:
+            torch.cuda.synchronize()
+            front, back = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(front):
+                g['stats'] = self._split_front()
+            with torch.cuda.graph(back, pool=front.pool()):
+                self._split_back()
+            g['graph'], g['graph_back'] = front, back
+        if g['graph'] is not None:
+            g['graph'].replay()
+            self._reduce_gradients()                                        # eager collective 2
+            g['graph_back'].replay()
+            stats = g['stats'].clone()
+        else:
+            stats = self._split_front()
+            self._reduce_gradients()
+            self._split_back()
+        return all_reduce_sum_(stats)                                       # eager collective 3
+
     def _graph_step(self, data, mask, prior):
         g = self._g
         shapes = (tuple(data.shape), tuple(mask.shape), tuple(prior.shape))
@@ -314,7 +367,9 @@ class DataParallelTrainer:
                 g[name].copy_(src, non_blocking=True)
         self._sync_device_scalars()
         lr = self.lr(self.step_no)
-        if g['graph'] is None and g['calls'] >= g['warmup']:
+        if self.graph_mode == 'split':
+            stats = self._split_step()
+        elif g['graph'] is None and g['calls'] >= g['warmup']:
             # capture (nothing executes): cuDNN algorithm search, workspaces, the NCCL communicator and the library's
             # lazy state were all set up by the eager warm-up steps
             torch.cuda.synchronize()
@@ -322,7 +377,9 @@ class DataParallelTrainer:
             with torch.cuda.graph(graph):
                 g['stats'] = self._graph_body()
             g['graph'] = graph
-        if g['graph'] is not None:
+        if self.graph_mode == 'split':
+            pass
+        elif g['graph'] is not None:
             g['graph'].replay()
             stats = g['stats'].clone()
         else:

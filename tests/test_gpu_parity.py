@@ -542,10 +542,15 @@ def test_single_gpu_training_steps_reduce_the_loss(qb, dev, cfg_noise_off):
     assert np.isfinite(lazy[-1]['loss']) and lazy[-1]['mask_sum'] == float(mask.sum())
 
 
-def test_captured_training_step_matches_the_eager_step(qb, dev, cfg_noise_off, tmp_path):
+@pytest.mark.parametrize('graph_mode', [
+    True,
+    pytest.param('split', marks=pytest.mark.xfail(strict=False, reason='split mode (collectives outside the capture) was '
+                 'written after the GPU budget of round 2 was spent: not yet run on hardware'))])
+def test_captured_training_step_matches_the_eager_step(qb, dev, cfg_noise_off, tmp_path, graph_mode):
     """cuda_graph=True: the step is captured after three eager warm-up steps and replayed; the Philox key, the
     schedule position and Adam's counter advance on the device.  Same seeds, same data -> the statistics of every
-    step (warm-up, first replay, later replays, after a checkpoint round trip) equal the eager trainer's."""
+    step (warm-up, first replay, later replays, after a checkpoint round trip) equal the eager trainer's.
+    'split': two graphs with the (here absent) collectives enqueued eagerly between them."""
     import copy
     from qbold_vi_b200.encoder import Encoder
     from qbold_vi_b200.distributed import DataParallelTrainer
@@ -554,7 +559,7 @@ def test_captured_training_step_matches_the_eager_step(qb, dev, cfg_noise_off, t
     enc_g = copy.deepcopy(enc_e)
     layer = qb.SignalGenerationLayer(cfg_noise_off, True, True)
     dp_e = DataParallelTrainer(enc_e, _trainer(qb, cfg_noise_off, seed=11), layer, ft_lr=2e-3)
-    dp_g = DataParallelTrainer(enc_g, _trainer(qb, cfg_noise_off, seed=11), layer, ft_lr=2e-3, cuda_graph=True)
+    dp_g = DataParallelTrainer(enc_g, _trainer(qb, cfg_noise_off, seed=11), layer, ft_lr=2e-3, cuda_graph=graph_mode)
     g = torch.Generator(device=dev).manual_seed(9)
     shape = (2, 16, 16, 4)
     truth = torch.stack([torch.rand(shape, device=dev, generator=g) * 0.4 + 0.2,
@@ -591,7 +596,7 @@ def test_captured_training_step_matches_the_eager_step(qb, dev, cfg_noise_off, t
     path = str(tmp_path / 'dp.pt')
     dp_g.save(path)
     enc_r = copy.deepcopy(enc_g)
-    dp_r = DataParallelTrainer(enc_r, _trainer(qb, cfg_noise_off, seed=11), layer, ft_lr=2e-3, cuda_graph=True)
+    dp_r = DataParallelTrainer(enc_r, _trainer(qb, cfg_noise_off, seed=11), layer, ft_lr=2e-3, cuda_graph=graph_mode)
     dp_r.load(path)
     for i in range(5):
         close(dp_e.step(data, mask, prior), dp_r.step(data, mask, prior), 'resumed step %d' % i)

@@ -278,6 +278,37 @@ def test_bench_fails_loudly_without_a_gpu():
     assert '"value"' not in out.stdout
 
 
+@pytest.mark.parametrize('case', ['ok', 'raises', 'hangs'])
+def test_bench_prints_its_line_whatever_the_captured_step_trial_does(case):
+    """bench.py runs the captured (CUDA graph) training step last and under a deadline: a trial that succeeds updates
+    the training_step leg, one that raises or never returns leaves the eager numbers in the line; exit code 0 always."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = (
+        "import sys, time, types; sys.path.insert(0, %r); import bench\n"
+        "line = {'metric': 'm', 'training_step': {'ms_per_step': 4.0, 'ms_encoder_fwd_bwd': 3.0}}\n"
+        "args = types.SimpleNamespace(graph_deadline=2)\n"
+        "def trial(mode):\n"
+        "    case = %r\n"
+        "    if case == 'raises': raise RuntimeError('capture failed')\n"
+        "    if case == 'hangs': time.sleep(60)\n"
+        "    return {'ms_per_step': 3.5, 'voxel_signals_per_s': 1.0, 'ms_host_enqueue_per_step': 0.05, 'loss': -1.0}\n"
+        "bench.finish_with_graph_trial(line, line['training_step'], trial, 0, 1, args)\n" % (root, case))
+    out = subprocess.run([sys.executable, '-c', prog], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    t = json.loads(lines[0])['training_step']
+    if case == 'ok':
+        assert t['ms_per_step'] == 3.5 and t['captured_step'] == {'mode': 'full', 'status': 'ok'}
+        assert 'CUDA graph' in t['launch_mode']
+    else:
+        assert t['ms_per_step'] == 4.0 and t['captured_step']['mode'] == 'full'
+        assert ('failed: RuntimeError' if case == 'raises' else 'deadline') in t['captured_step']['status']
+
+
 def test_dlpack_unpacking_without_a_gpu(qb):
     """The ctypes DLPack consumer: capsule and __dlpack__ producers, shape / dtype / contiguity checks, single use,
     and the loud refusal of host memory (there is no CPU path)."""

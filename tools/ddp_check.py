@@ -77,6 +77,33 @@ def main():
                           'philox_grad_rel_err': err_p, 'philox_loss_rel_err': lerr_p}))
     assert err < 1e-5 and lerr < 1e-6, (err, lerr)
     assert err_p < 1e-5 and lerr_p < 1e-6, (err_p, lerr_p)
+    # the captured (CUDA graph) data-parallel step against the eager one (QBOLD_DDP_GRAPH=full: NCCL all-reduces
+    # inside the graph; default split: collectives eager between two graphs).  Run it under `timeout`: the only 8-GPU
+    # attempt of round 2 (full mode) did not return within the GPU budget.
+    import copy
+    enc_e, enc_g = copy.deepcopy(enc), copy.deepcopy(enc)
+    mk = lambda: qb.EncoderTrainer(cfg, student_t_df=200, multi_image_normalisation=False, use_mvg=True,   # noqa: E731
+                                   use_population_prior=False, predict_log_data=False, seed=7)
+    dp_e = D.DataParallelTrainer(enc_e, mk(), layer, ft_lr=2e-3)
+    dp_g = D.DataParallelTrainer(enc_g, mk(), layer, ft_lr=2e-3, cuda_graph=os.environ.get('QBOLD_DDP_GRAPH', 'split'))
+    d_, m_, p_ = data[sl].contiguous(), mask[sl].contiguous(), prior[sl].contiguous()
+    worst = 0.0
+    for i in range(7):
+        a, b = dp_e.step(d_, m_, p_), dp_g.step(d_, m_, p_)
+        for k in ('loss', 'nll', 'kl', 'smoothness', 'mask_sum'):
+            worst = max(worst, abs(a[k] - b[k]) / max(abs(a[k]), 1e-3))
+    assert dp_g._g['graph'] is not None
+    flat = torch.cat([p.detach().reshape(-1) for p in enc_g.parameters()])
+    ref0 = flat.clone()
+    if world > 1:
+        dist.broadcast(ref0, 0)
+    drift = float((flat - ref0).abs().max())                    # replicas stay identical
+    pe = torch.cat([p.detach().reshape(-1) for p in enc_e.parameters()])
+    perr = float((flat - pe).abs().max() / pe.abs().max())
+    if rank == 0:
+        print(json.dumps({'world': world, 'captured_vs_eager_stats_rel_err': worst, 'captured_vs_eager_param_rel_err': perr,
+                          'replica_drift': drift}))
+    assert worst < 2e-4 and drift == 0.0 and perr < 2e-3, (worst, drift, perr)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
