@@ -542,15 +542,14 @@ def test_single_gpu_training_steps_reduce_the_loss(qb, dev, cfg_noise_off):
     assert np.isfinite(lazy[-1]['loss']) and lazy[-1]['mask_sum'] == float(mask.sum())
 
 
-@pytest.mark.parametrize('graph_mode', [
-    True,
-    pytest.param('split', marks=pytest.mark.xfail(strict=False, reason='split mode (collectives outside the capture) was '
-                 'written after the GPU budget of round 2 was spent: not yet run on hardware'))])
-def test_captured_training_step_matches_the_eager_step(qb, dev, cfg_noise_off, tmp_path, graph_mode):
+def test_captured_training_step_matches_the_eager_step(qb, dev, cfg_noise_off, tmp_path):
     """cuda_graph=True: the step is captured after three eager warm-up steps and replayed; the Philox key, the
     schedule position and Adam's counter advance on the device.  Same seeds, same data -> the statistics of every
-    step (warm-up, first replay, later replays, after a checkpoint round trip) equal the eager trainer's.
-    'split': two graphs with the (here absent) collectives enqueued eagerly between them."""
+    step (warm-up, first replay, later replays, after a checkpoint round trip) equal the eager trainer's."""
+    _captured_step_against_eager(qb, dev, cfg_noise_off, tmp_path, True)
+
+
+def _captured_step_against_eager(qb, dev, cfg_noise_off, tmp_path, graph_mode):
     import copy
     from qbold_vi_b200.encoder import Encoder
     from qbold_vi_b200.distributed import DataParallelTrainer
@@ -1809,3 +1808,11 @@ def test_host_buffer_pipeline_matches_the_device_path(qb, dev, cfg_noise_off, n)
         hgr = torch.full((n, 2), float('nan')).pin_memory()
         layer.forward_backward_host(hx, hg, hs, hgr)
         assert torch.equal(hs, s_ref.cpu()) and torch.equal(hgr, g_ref.cpu())
+
+
+@pytest.mark.xfail(strict=False, reason='split mode (collectives outside the capture) was written after the GPU budget of '
+                   'round 2 was spent: not yet run on hardware')
+def test_split_captured_training_step_matches_the_eager_step(qb, dev, cfg_noise_off, tmp_path):
+    """cuda_graph='split': two graphs (encoder + losses + backward | weight decay + Adam) with the collectives enqueued
+    eagerly around them -- the multi-GPU form of the captured step.  Last in the file on purpose."""
+    _captured_step_against_eager(qb, dev, cfg_noise_off, tmp_path, 'split')
