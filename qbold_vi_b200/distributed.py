@@ -208,13 +208,15 @@ class DataParallelTrainer:
         self.graph_mode = None if not cuda_graph else ('split' if cuda_graph == 'split' else 'full')
         self._g = None
         if self.cuda_graph:
+            # (a custom loss_fn must take ``seed=`` -- the device Philox key -- and launch nothing that cannot be captured)
             dev = self.bucket.flat.device
-            if dev.type != 'cuda':
-                raise ValueError('cuda_graph=True needs the encoder on a CUDA device')
-            if loss_fn is not None:
-                raise ValueError('cuda_graph=True runs the fused sm_100a loss; a custom loss_fn cannot be captured safely')
+            if dev.type != 'cuda' and graph_warmup is not None:
+                raise ValueError('cuda_graph needs the encoder on a CUDA device (graph_warmup=None never captures: the '
+                                 'step then runs eagerly on the device-resident scalars, which is what the CPU tests of '
+                                 'the host logic use)')
             f32 = dict(dtype=torch.float32, device=dev)
-            self._g = {'warmup': int(graph_warmup), 'calls': 0, 'graph': None, 'shapes': None,
+            self._g = {'warmup': float('inf') if graph_warmup is None else int(graph_warmup), 'calls': 0, 'graph': None,
+                       'shapes': None,
                        'seed': torch.zeros(1, dtype=torch.int64, device=dev),
                        'golden': torch.tensor([_as_i64(_GOLDEN)], dtype=torch.int64, device=dev),
                        't': torch.zeros(2, **f32),                                   # schedule position, twice
@@ -223,7 +225,11 @@ class DataParallelTrainer:
                        'sched': torch.tensor([self.lr.initial, 1.0 - self.wd.initial], **f32),   # lr_t | 1 - wd_t
                        'msum': torch.zeros(1, dtype=torch.float64, device=dev),      # split mode: global sum(mask)
                        'dev_calls': None, 'dev_step': None}
-            self.opt = _adam(self.bucket.params, lr=self._g['sched'][0], betas=(0.9, 0.9), capturable=True)
+            if dev.type == 'cuda':
+                self.opt = _adam(self.bucket.params, lr=self._g['sched'][0], betas=(0.9, 0.9), capturable=True)
+            else:
+                self.opt = torch.optim.Adam(self.bucket.params, lr=self._g['sched'][0], betas=(0.9, 0.9), eps=1e-7,
+                                            foreach=False)
         else:
             self.opt = _adam(self.bucket.params, lr=ft_lr, betas=(0.9, 0.9))             # beta_2 = 0.9 (train.py:310)
 
@@ -295,7 +301,7 @@ class DataParallelTrainer:
         msum = global_mask_sum_device(mask)
         self.bucket.zero_()
         _, q, sigma = self.encoder(data)
-        loss, info = self._fused_loss(q, sigma, data, mask, prior, msum, seed=g['seed'])
+        loss, info = self.loss_fn(q, sigma, data, mask, prior, msum, seed=g['seed'])
         tv = self.tv_fn(q, prior, mask, msum)
         total = loss + self.smoothness_weight * tv
         total.backward()
@@ -318,7 +324,7 @@ class DataParallelTrainer:
         g['t'].add_(1.0)
         self.bucket.zero_()
         _, q, sigma = self.encoder(data)
-        loss, info = self._fused_loss(q, sigma, data, mask, prior, msum, seed=g['seed'])
+        loss, info = self.loss_fn(q, sigma, data, mask, prior, msum, seed=g['seed'])
         tv = self.tv_fn(q, prior, mask, msum)
         total = loss + self.smoothness_weight * tv
         total.backward()

@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _standin_loss(q, sigma, data, mask, prior, mask_sum):
+def _standin_loss(q, sigma, data, mask, prior, mask_sum, seed=None):
     m = mask.reshape(-1)
     per_voxel = ((q.reshape(-1, 5) - prior.reshape(-1, 5)) ** 2).sum(-1) + \
         ((torch.log(sigma.reshape(m.shape[0], -1)) + 2.0) ** 2).sum(-1)
@@ -35,7 +35,7 @@ def _standin_tv(q, prior, mask, mask_sum):
     return ((p[:, :-1] - p[:, 1:]).abs() * both).sum() / mask_sum
 
 
-def _make(seed=3):
+def _make(seed=3, **kw):
     import qbold_vi_b200 as qb
     from qbold_vi_b200.encoder import Encoder
     from qbold_vi_b200.distributed import DataParallelTrainer
@@ -44,7 +44,7 @@ def _make(seed=3):
     enc = Encoder(no_units=12, no_intermediate_layers=2)
     tr = qb.EncoderTrainer(cfg, student_t_df=200, multi_image_normalisation=False, use_mvg=True,
                            use_population_prior=False, predict_log_data=False, seed=1)
-    return enc, DataParallelTrainer(enc, tr, None, loss_fn=_standin_loss, tv_fn=_standin_tv)
+    return enc, DataParallelTrainer(enc, tr, None, loss_fn=_standin_loss, tv_fn=_standin_tv, **kw)
 
 
 def _batch():
@@ -106,6 +106,77 @@ def test_two_rank_step_equals_single_rank_step():
         assert abs(st['loss'] - stats['loss']) <= 1e-5 * abs(stats['loss'])
         assert st['mask_sum'] == stats['mask_sum'] == float(mask.sum())
     assert np.array_equal(res[0][3], res[1][3])                                 # replicas stay bit-identical
+
+
+def _graph_mode_worker(rank, world, port, out, tmp):
+    """Host logic of the captured step (DataParallelTrainer(cuda_graph=...)) with the capture itself left out
+    (graph_warmup=None): Philox key, schedule position and learning rate live in tensors and advance inside the step
+    body; 'split' issues the collectives around the two halves."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from qbold_vi_b200 import distributed as D
+    D.init_distributed('gloo')
+    data, mask, prior = _batch()
+    lo, hi = D.shard_range(data.shape[0], rank, world)
+    d_, m_, p_ = data[lo:hi].contiguous(), mask[lo:hi].contiguous(), prior[lo:hi].contiguous()
+    rows = []
+    for mode in (True, 'split'):
+        enc_e, dp_e = _make()
+        enc_g, dp_g = _make(cuda_graph=mode, graph_warmup=None)
+        worst = 0.0
+        for i in range(4):
+            a, b = dp_e.step(d_, m_, p_), dp_g.step(d_, m_, p_)
+            for k in ('loss', 'nll', 'kl', 'smoothness', 'mask_sum'):
+                worst = max(worst, abs(a[k] - b[k]) / max(abs(a[k]), 1e-6))
+            assert abs(a['lr'] - b['lr']) < 1e-15
+        # the device-resident scalars followed the host mirrors
+        tr = dp_g.trainer
+        want_seed = D._as_i64((tr._seed + D._GOLDEN * tr._calls) & 0xFFFFFFFFFFFFFFFF)
+        seed_ok = int(dp_g._g['seed']) == want_seed and tr._calls == 4 and dp_g.step_no == 4
+        sched_ok = abs(float(dp_g._g['sched'][0]) - dp_g.lr(3)) < 1e-9 and \
+            abs(float(dp_g._g['sched'][1]) - (1.0 - dp_g.wd(3))) < 1e-7 and float(dp_g._g['t'][0]) == 4.0
+        # checkpoint round trip into a fresh trainer of the same mode, then one more step on both
+        path = os.path.join(tmp, 'g_%s_%d.pt' % (mode, rank))
+        dp_g.save(path)
+        enc_r, dp_r = _make(cuda_graph=mode, graph_warmup=None)
+        dp_r.load(path)
+        a, b = dp_e.step(d_, m_, p_), dp_r.step(d_, m_, p_)
+        resumed = max(abs(a[k] - b[k]) / max(abs(a[k]), 1e-6) for k in ('loss', 'nll', 'smoothness'))
+        w_e = torch.cat([p.detach().reshape(-1) for p in enc_e.parameters()])
+        w_r = torch.cat([p.detach().reshape(-1) for p in enc_r.parameters()])
+        rows.append((str(mode), worst, bool(seed_ok), bool(sched_ok), resumed, float((w_e - w_r).abs().max()),
+                     w_r.numpy()))
+    out.put((rank, rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_captured_step_host_logic_on_two_ranks(tmp_path):
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_graph_mode_worker, args=(r, 2, port, out, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([out.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, rows in res:
+        for mode, worst, seed_ok, sched_ok, resumed, w_err, _ in rows:
+            assert worst < 1e-5 and resumed < 1e-5 and w_err < 1e-5, (rank, mode, worst, resumed, w_err)
+            assert seed_ok and sched_ok, (rank, mode)
+    for i in range(2):                                                          # replicas stay bit-identical
+        assert np.array_equal(res[0][1][i][6], res[1][1][i][6])
+
+
+def test_uint64_key_as_int64_bit_pattern():
+    from qbold_vi_b200.distributed import _GOLDEN, _as_i64
+    for u in (0, 1, (1 << 63) - 1, 1 << 63, (1 << 64) - 1, _GOLDEN):
+        assert -(1 << 63) <= _as_i64(u) < (1 << 63) and _as_i64(u) % (1 << 64) == u
+    t = torch.tensor([_as_i64((1 << 64) - 5)], dtype=torch.int64)
+    t.add_(torch.tensor([_as_i64(_GOLDEN)], dtype=torch.int64))                  # wraps like the uint64 the kernel reads
+    assert int(t) % (1 << 64) == ((1 << 64) - 5 + _GOLDEN) % (1 << 64)
 
 
 def test_encoder_parameter_count_matches_the_reference():
