@@ -411,7 +411,8 @@ def finish_with_graph_trial(line, train_leg, graph_trial, rank, world, args):
     The captured step is verified on one GPU (tests, profiles/r02s_bench_n1.json).  Its multi-GPU form could not be
     confirmed inside the round's GPU budget, so a trial that raises, or that does not finish before the deadline (a rank
     stuck in a collective cannot be recovered in-process), leaves the eager numbers in the line and ends the process
-    with os._exit(0): a hung trial never costs the rest of the bench line."""
+    through leave() (exit hooks, then os._exit(0)): a hung trial never costs the rest of the bench line.  A trial that
+    succeeds exits the normal way."""
     import torch.distributed as dist
     mode = os.environ.get('QBOLD_BENCH_GRAPH', 'full' if world == 1 else 'split')
     lock, state = threading.Lock(), {'printed': False}
@@ -425,10 +426,23 @@ def finish_with_graph_trial(line, train_leg, graph_trial, rank, world, args):
                 line['training_step']['captured_step'] = status
                 print(json.dumps(line), flush=True)
 
+    def leave():
+        # A stuck main thread cannot exit normally.  Registered exit hooks (a harness may record loaded libraries there)
+        # still get to run, for at most 10 s, before the process is ended without the CUDA / NCCL teardown that would hang.
+        sys.stdout.flush()
+        hard = threading.Timer(10, lambda: os._exit(0))
+        hard.daemon = True
+        hard.start()
+        try:
+            import atexit
+            atexit._run_exitfuncs()
+        except BaseException:
+            pass
+        os._exit(0)
+
     def watchdog():
         emit({'mode': mode, 'status': 'no result within %d s (deadline); the eager step is reported' % args.graph_deadline})
-        sys.stdout.flush()
-        os._exit(0)
+        leave()
 
     if mode in ('0', 'off', 'none'):
         emit({'mode': None, 'status': 'disabled (QBOLD_BENCH_GRAPH)'})
@@ -440,8 +454,7 @@ def finish_with_graph_trial(line, train_leg, graph_trial, rank, world, args):
             res = graph_trial(True if mode == 'full' else mode)
         except Exception as exc:                         # other ranks may now be stuck in a collective: no more of those
             emit({'mode': mode, 'status': 'failed: %s: %s' % (type(exc).__name__, str(exc)[:300])})
-            sys.stdout.flush()
-            os._exit(0)
+            leave()
         timer.cancel()
         if rank == 0 and not state['printed']:
             t = line['training_step']
@@ -455,13 +468,13 @@ def finish_with_graph_trial(line, train_leg, graph_trial, rank, world, args):
             t['limiter'] = ('encoder forward + backward (HBM passes over the [voxels, 60] activations): %.0f %% of the step'
                             % (100.0 * t['ms_encoder_fwd_bwd'] / t['ms_per_step']))
         emit({'mode': mode, 'status': 'ok'})
-    bye = threading.Timer(30, lambda: os._exit(0))       # the line is out: a teardown that hangs must not keep the job
+    # the line is out; normal interpreter exit from here (exit hooks run).  Only a teardown that hangs is cut short.
+    bye = threading.Timer(60, lambda: os._exit(0))
     bye.daemon = True
     bye.start()
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()
-    os._exit(0)
 
 
 def workload_config(voxels, gpus):

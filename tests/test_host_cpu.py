@@ -287,7 +287,8 @@ def test_bench_prints_its_line_whatever_the_captured_step_trial_does(case):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     prog = (
-        "import sys, time, types; sys.path.insert(0, %r); import bench\n"
+        "import sys, time, types, atexit; sys.path.insert(0, %r); import bench\n"
+        "atexit.register(lambda: sys.stderr.write('EXIT-HOOK-RAN\\n'))\n"
         "line = {'metric': 'm', 'training_step': {'ms_per_step': 4.0, 'ms_encoder_fwd_bwd': 3.0}}\n"
         "args = types.SimpleNamespace(graph_deadline=2)\n"
         "def trial(mode):\n"
@@ -298,6 +299,7 @@ def test_bench_prints_its_line_whatever_the_captured_step_trial_does(case):
         "bench.finish_with_graph_trial(line, line['training_step'], trial, 0, 1, args)\n" % (root, case))
     out = subprocess.run([sys.executable, '-c', prog], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr[-800:]
+    assert 'EXIT-HOOK-RAN' in out.stderr                  # exit hooks of the harness run on every way out
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
     assert len(lines) == 1
     t = json.loads(lines[0])['training_step']
