@@ -179,6 +179,42 @@ def test_uint64_key_as_int64_bit_pattern():
     assert int(t) % (1 << 64) == ((1 << 64) - 5 + _GOLDEN) % (1 << 64)
 
 
+def test_ranks_get_disjoint_host_cores():
+    """pin_cores: every local rank takes its own slice of the cores this process may run on (QBOLD_PIN_CORES=0: off)."""
+    import subprocess
+    import sys
+    if not hasattr(os, 'sched_getaffinity') or len(os.sched_getaffinity(0)) < 2:
+        pytest.skip('needs sched_setaffinity and two cores')
+    prog = ("import os, sys, json; sys.path.insert(0, %r)\n"
+            "from qbold_vi_b200.distributed import pin_cores\n"
+            "before = sorted(os.sched_getaffinity(0)); mine = pin_cores(int(sys.argv[1]), 2)\n"
+            "print(json.dumps([before, mine, sorted(os.sched_getaffinity(0))]))\n"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import json
+    got = []
+    for rank in (0, 1):
+        out = subprocess.run([sys.executable, '-c', prog, str(rank)], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-500:]
+        got.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    (b0, m0, a0), (b1, m1, a1) = got
+    assert m0 == a0 and m1 == a1 and not set(a0) & set(a1) and set(a0) | set(a1) <= set(b0)
+    assert len(a0) == len(a1) == len(b0) // 2
+    env = dict(os.environ, QBOLD_PIN_CORES='0')
+    out = subprocess.run([sys.executable, '-c', prog, '0'], capture_output=True, text=True, timeout=300, env=env)
+    before, mine, after = json.loads(out.stdout.strip().splitlines()[-1])
+    assert mine is None and before == after
+
+
+def test_lazy_stats_convert_on_access_only():
+    from qbold_vi_b200.distributed import LazyStats
+    vals = torch.tensor([1.5, 2.5], dtype=torch.float64)
+    st = LazyStats(['loss', 'kl'], vals, lr=0.1)
+    assert st._host is None and st['lr'] == 0.1 and st._host is None              # host items never touch the tensor
+    assert 'loss' in st and 'lr' in st and 'nll' not in st and st.get('nll', 7) == 7
+    assert st['kl'] == 2.5 and st._host == [1.5, 2.5]
+    assert st.as_dict() == {'lr': 0.1, 'loss': 1.5, 'kl': 2.5}
+
+
 def test_encoder_parameter_count_matches_the_reference():
     from qbold_vi_b200.encoder import Encoder
     enc = Encoder()                                   # optimal.yaml: 60 units, 2 blocks, channel-wise gating
