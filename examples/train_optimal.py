@@ -29,6 +29,9 @@ def main():
     ap.add_argument('--volumes-per-gpu', type=int, default=2)
     ap.add_argument('--save-directory', default=None,
                     help='checkpoints: pt_model.pt / final_model.pt; finished phases are skipped (train.py:193-202,260-270)')
+    ap.add_argument('--cuda-graph', default='off', choices=['off', 'full', 'split'],
+                    help="fine-tuning step replayed from a CUDA graph: 'full' (one graph, measured on one GPU) or 'split' "
+                         "(collectives outside the capture, for several GPUs)")
     a = ap.parse_args()
     rank, world, dev = D.init_distributed()
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
@@ -82,7 +85,8 @@ def main():
     with torch.no_grad():
         prior = model(data)[0][..., :5].contiguous()
     ft = D.DataParallelTrainer(model, trainer, sig_gen_layer, ft_lr=args.ft_lr, adamw_decay=args.adamw_decay,
-                               smoothness_weight=args.smoothness_weight, kl_weight=1.0)
+                               smoothness_weight=args.smoothness_weight, kl_weight=1.0,
+                               cuda_graph=False if a.cuda_graph == 'off' else a.cuda_graph)
     if ckpt and os.path.exists(ckpt('final_model.pt')):         # resume: weights, Adam moments, schedule position, RNG counters
         ft.load(ckpt('final_model.pt'), map_location=dev)
         log.append(('ft', 'resumed', {'step_no': ft.step_no}))
