@@ -235,3 +235,27 @@ def test_diag_kl_oracle_vs_reference_source():
     m = a['mask']
     assert rel_elem((kl * (m > 0)).sum() / m.sum(), a['kl_diag']) < 1e-5
     assert rel_max(gq * (m > 0)[:, None] / m.sum(), a['kl_diag_grad']) < 1e-4
+
+
+def test_single_precision_bessel_restatement_against_scipy():
+    """oracle/cephes_f32.py restates the Cephes j0f / j1f routines TensorFlow's float32 bessel_j0 / bessel_j1 dispatch to
+    (signals.py:170 and its registered gradient).  Pinned here against scipy's double-precision J0 / J1: the arguments
+    of the qBOLD path, 1.5 * tau * dw * u, stay below ~25; the asymptotic branch is checked far beyond that."""
+    import scipy.special as sp
+    from oracle import cephes_f32 as c
+    x = np.linspace(0.0, 30.0, 300001).astype(np.float32)
+    assert c.j0f(x).dtype == np.float32 and c.j1f(x).dtype == np.float32
+    assert np.abs(c.j0f(x).astype(np.float64) - sp.j0(x.astype(np.float64))).max() < 2.5e-7
+    assert np.abs(c.j1f(x).astype(np.float64) - sp.j1(x.astype(np.float64))).max() < 2.5e-7
+    x = np.linspace(30.0, 400.0, 300001).astype(np.float32)
+    assert np.abs(c.j0f(x).astype(np.float64) - sp.j0(x.astype(np.float64))).max() < 1e-6
+    assert np.abs(c.j1f(x).astype(np.float64) - sp.j1(x.astype(np.float64))).max() < 1e-6
+    # known answers: J0(0) = 1, J1(0) = 0, the first zeros of J0 and J1, and J0' = -J1 by central differences
+    assert c.j0f(np.float32([0.0]))[0] == 1.0 and c.j1f(np.float32([0.0]))[0] == 0.0
+    assert np.abs(c.j0f(np.float32([2.404825557695773, 5.520078110286311, 8.653727912911013]))).max() < 2e-7
+    assert np.abs(c.j1f(np.float32([3.8317059702075125, 7.015586669815619]))).max() < 2e-7
+    xm = np.linspace(0.5, 25.0, 2001)
+    h = 1e-2
+    d = (c.j0f((xm + h).astype(np.float32)).astype(np.float64) - c.j0f((xm - h).astype(np.float32)).astype(np.float64)) / \
+        ((xm + h).astype(np.float32).astype(np.float64) - (xm - h).astype(np.float32).astype(np.float64))
+    assert np.abs(d + c.j1f(xm.astype(np.float32))).max() < 5e-5
