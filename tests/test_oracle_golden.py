@@ -259,3 +259,29 @@ def test_single_precision_bessel_restatement_against_scipy():
     d = (c.j0f((xm + h).astype(np.float32)).astype(np.float64) - c.j0f((xm - h).astype(np.float32)).astype(np.float64)) / \
         ((xm + h).astype(np.float32).astype(np.float64) - (xm - h).astype(np.float32).astype(np.float64))
     assert np.abs(d + c.j1f(xm.astype(np.float32))).max() < 5e-5
+
+
+def test_cpu_baseline_port_computes_the_reference_path():
+    """oracle/torch_port.py is what `bench.py --impl reference` and the `cpu_baseline` leg time.  It must be the same
+    computation: signal and autodiff gradient against the fixture recorded from the reference's own signals.py, and
+    against the float64 oracle on random voxels of the bench workload (float32 program: 2e-5 element-wise)."""
+    import torch
+    from oracle import torch_port as tp
+    cfg = o.default_config()
+    cfg['simulate_noise'] = 'False'
+    ph = o.parse_params(cfg)
+    d = golden('ref_shim_forward.npz')
+    x = d['oef_dbv'].reshape(-1, 2).astype(np.float32)
+    g = d['g_rand'].reshape(-1, 11).astype(np.float32)
+    s, gr = tp.forward_backward(ph, torch.from_numpy(x), torch.from_numpy(g))
+    want_s, want_g = d['signal_f1_b1'].reshape(-1, 11), d['grad_rand_f1_b1'].reshape(-1, 2)
+    assert np.max(np.abs(s.numpy() - want_s) / np.abs(want_s)) < 2e-5
+    assert np.abs(gr.numpy() - want_g).max() < 2e-5 * np.abs(want_g).max()
+    rng = np.random.default_rng(0)
+    n = 3000
+    x = np.stack([rng.uniform(0.04, 0.84, n), rng.uniform(0.001, 0.201, n)], -1).astype(np.float32)
+    g = rng.standard_normal((n, 11)).astype(np.float32)
+    s, gr = tp.forward_backward(ph, torch.from_numpy(x), torch.from_numpy(g), chunk=1024)
+    s64, g64 = o.forward_backward(ph, x, g, dtype=np.float64)
+    assert np.max(np.abs(s.numpy() - s64) / np.abs(s64)) < 2e-5
+    assert np.abs(gr.numpy() - g64).max() < 2e-5 * np.abs(g64).max()
