@@ -117,6 +117,7 @@ def run_reference(args, rank, world):
                                    'CPU path (TensorFlow unavailable offline): oracle/torch_port.py' % sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'sample_voxels_per_step': sample,     # what one timed step covers (config names the full workload it samples)
     }
     print(json.dumps(line), flush=True)
 
