@@ -311,6 +311,31 @@ def test_bench_prints_its_line_whatever_the_captured_step_trial_does(case):
         assert ('failed: RuntimeError' if case == 'raises' else 'deadline') in t['captured_step']['status']
 
 
+def test_header_is_plain_c_and_the_c_demo_links(qb, tmp_path):
+    """The boundary is a C ABI: include/qbold.h must parse as strict C99 and as C++, and examples/c_abi_demo.c must
+    compile with a C compiler and link against libqbold.so (it is RUN by the GPU suite: test_c_abi_from_plain_c)."""
+    import shutil
+    import subprocess
+    gcc, gxx = shutil.which('gcc'), shutil.which('g++')
+    if not gcc or not gxx:
+        pytest.skip('gcc / g++ not available')
+    hdr = os.path.join(ROOT, 'include', 'qbold.h')
+    subprocess.run([gcc, '-std=c99', '-pedantic', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c', hdr], check=True,
+                   capture_output=True, timeout=120)
+    subprocess.run([gxx, '-std=c++11', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c++', hdr], check=True,
+                   capture_output=True, timeout=120)
+    cuda = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    if not os.path.exists(os.path.join(cuda, 'include', 'cuda_runtime.h')):
+        pytest.skip('CUDA toolkit headers not available')
+    qb._lib.lib()                                                    # the library exists (built in-tree)
+    libdir = os.path.join(ROOT, 'qbold_vi_b200')
+    res = subprocess.run([gcc, '-std=c99', '-Wall', '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(cuda, 'include'),
+                          os.path.join(ROOT, 'examples', 'c_abi_demo.c'), '-L', libdir, '-lqbold', '-L',
+                          os.path.join(cuda, 'lib64'), '-lcudart', '-lm', '-o', str(tmp_path / 'c_abi_demo')],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-1500:]
+
+
 def test_dlpack_unpacking_without_a_gpu(qb):
     """The ctypes DLPack consumer: capsule and __dlpack__ producers, shape / dtype / contiguity checks, single use,
     and the loud refusal of host memory (there is no CPU path)."""
