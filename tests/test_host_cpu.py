@@ -311,6 +311,42 @@ def test_bench_prints_its_line_whatever_the_captured_step_trial_does(case):
         assert ('failed: RuntimeError' if case == 'raises' else 'deadline') in t['captured_step']['status']
 
 
+def test_ctypes_signatures_match_the_header_prototypes(qb):
+    """Every prototype of include/qbold.h against the ctypes signature the Python side binds it with: same number of
+    parameters, pointer / int32 / int64 / uint64 / float / double in the same positions (a drift here is a silent
+    ABI bug, not a link error)."""
+    hdr = re.sub(r'/\*.*?\*/', '', open(os.path.join(ROOT, 'include', 'qbold.h')).read(), flags=re.S)
+    protos = re.findall(r'\b([A-Za-z_][\w\s\*]*?)\b(qbold_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', hdr)
+    assert len(protos) == len(qb._lib._SIGNATURES) >= 50
+
+    def kind(decl):
+        d = decl.strip()
+        if d in ('void', ''):
+            return None
+        if '*' in d:
+            return 'ptr'
+        for k, v in (('uint64_t', 'u64'), ('int64_t', 'i64'), ('int32_t', 'i32'), ('double', 'f64'), ('float', 'f32'),
+                     ('int', 'i32')):
+            if re.search(r'\b%s\b' % k, d):
+                return v
+        raise AssertionError('unhandled parameter type: %r' % d)
+
+    def ckind(a):
+        for t, v in ((C.c_uint64, 'u64'), (C.c_int64, 'i64'), (C.c_int32, 'i32'), (C.c_double, 'f64'), (C.c_float, 'f32'),
+                     (C.c_void_p, 'ptr'), (C.c_char_p, 'ptr')):
+            if a is t:
+                return v
+        assert hasattr(a, '_type_') and not isinstance(a._type_, str), a          # POINTER(struct) / POINTER(c_float)
+        return 'ptr'
+
+    for ret, name, args in protos:
+        res, argtypes = qb._lib._SIGNATURES[name]
+        want = [k for k in (kind(a) for a in args.split(',')) if k]
+        assert [ckind(a) for a in argtypes] == want, name
+        want_ret = 'ptr' if '*' in ret else kind(ret)
+        assert (None if res is None else ckind(res)) == want_ret, name
+
+
 def test_header_is_plain_c_and_the_c_demo_links(qb, tmp_path):
     """The boundary is a C ABI: include/qbold.h must parse as strict C99 and as C++, and examples/c_abi_demo.c must
     compile with a C compiler and link against libqbold.so (it is RUN by the GPU suite: test_c_abi_from_plain_c)."""
