@@ -170,6 +170,32 @@ def test_captured_step_host_logic_on_two_ranks(tmp_path):
         assert np.array_equal(res[0][1][i][6], res[1][1][i][6])
 
 
+def test_checkpoints_move_between_the_eager_and_the_captured_trainer(tmp_path):
+    """A checkpoint written by the eager trainer resumes in the captured-step trainer and the other way round: the
+    learning rate is re-aliased to the device schedule, counters and moments carry over (capture left out on CPU)."""
+    data, mask, prior = _batch()
+    enc_a, dp_a = _make()
+    for _ in range(3):
+        dp_a.step(data, mask, prior)
+    path = str(tmp_path / 'eager.pt')
+    dp_a.save(path)
+    enc_b, dp_b = _make(seed=5, cuda_graph='split', graph_warmup=None)
+    dp_b.load(path)
+    assert dp_b.step_no == 3 and dp_b.opt.param_groups[0]['lr'].data_ptr() == dp_b._g['sched'].data_ptr()
+    for _ in range(2):
+        a, b = dp_a.step(data, mask, prior), dp_b.step(data, mask, prior)
+        assert abs(a['loss'] - b['loss']) <= 1e-5 * abs(a['loss']) and abs(a['lr'] - b['lr']) < 1e-15
+    path2 = str(tmp_path / 'captured.pt')
+    dp_b.save(path2)
+    enc_c, dp_c = _make(seed=7)
+    dp_c.load(path2)
+    a, c = dp_a.step(data, mask, prior), dp_c.step(data, mask, prior)
+    assert dp_c.step_no == 6 and abs(a['loss'] - c['loss']) <= 1e-5 * abs(a['loss'])
+    w_a = torch.cat([p.detach().reshape(-1) for p in enc_a.parameters()])
+    w_c = torch.cat([p.detach().reshape(-1) for p in enc_c.parameters()])
+    assert float((w_a - w_c).abs().max()) < 1e-5
+
+
 def test_uint64_key_as_int64_bit_pattern():
     from qbold_vi_b200.distributed import _GOLDEN, _as_i64
     for u in (0, 1, (1 << 63) - 1, 1 << 63, (1 << 64) - 1, _GOLDEN):
