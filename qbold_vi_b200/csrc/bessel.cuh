@@ -51,11 +51,15 @@ __device__ __forceinline__ float amp_cos(float amp, float theta) {
 }
 
 // MUFU.RSQ without the subnormal-input fix-up rsqrtf() carries (x > 9 here); same 2-ulp unit.
+#ifndef QB_HOST_EMU
 __device__ __forceinline__ float rsqrt_pos(float x) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+#else   // tests/host_emu: this header compiled for the host, every PTX statement replaced by its IEEE meaning
+__device__ __forceinline__ float rsqrt_pos(float x) { return 1.0f / sqrtf(x); }
+#endif
 
 template <bool WANT_J1>
 __device__ __forceinline__ void bessel_small(float x, float& omj0, float& j1) {
@@ -95,12 +99,31 @@ __device__ __forceinline__ void bessel_big(float x, float& omj0, float& j1) {
 // Same IEEE round-to-nearest arithmetic per half as the scalar kernels above.
 typedef unsigned long long f32x2;
 
+#ifdef QB_HOST_EMU
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    return (f32x2)__float_as_uint(lo) | ((f32x2)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+    lo = __uint_as_float((unsigned)(v & 0xffffffffull));
+    hi = __uint_as_float((unsigned)(v >> 32));
+}
+#define QB_EMU_OP2(NAME, EXPR)                                                        \
+    __device__ __forceinline__ f32x2 NAME {                                           \
+        float a0, a1, b0, b1, c0 = 0.f, c1 = 0.f;                                     \
+        upk2(a, a0, a1);                                                              \
+        upk2(b, b0, b1);                                                              \
+        EXPR;                                                                         \
+    }
+QB_EMU_OP2(fma2(f32x2 a, f32x2 b, f32x2 c), upk2(c, c0, c1); return pk2(fmaf(a0, b0, c0), fmaf(a1, b1, c1)))
+QB_EMU_OP2(mul2(f32x2 a, f32x2 b), (void)c0; (void)c1; return pk2(a0 * b0, a1 * b1))
+QB_EMU_OP2(add2(f32x2 a, f32x2 b), (void)c0; (void)c1; return pk2(a0 + b0, a1 + b1))
+#undef QB_EMU_OP2
+#else
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
     f32x2 r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
-__device__ __forceinline__ f32x2 pk1(float v) { return pk2(v, v); }
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
@@ -119,6 +142,8 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+#endif   // QB_HOST_EMU
+__device__ __forceinline__ f32x2 pk1(float v) { return pk2(v, v); }
 __device__ __forceinline__ float hsum2(f32x2 v) {
     float lo, hi;
     upk2(v, lo, hi);

@@ -311,6 +311,76 @@ def test_bench_prints_its_line_whatever_the_captured_step_trial_does(case):
         assert ('failed: RuntimeError' if case == 'raises' else 'deadline') in t['captured_step']['status']
 
 
+@pytest.fixture(scope='module')
+def bessel_emu(tmp_path_factory):
+    """csrc/bessel.cuh compiled for the host (tests/host_emu/bessel_host.cpp, -DQB_HOST_EMU)."""
+    import shutil
+    import subprocess
+    gxx = shutil.which('g++')
+    if not gxx:
+        pytest.skip('g++ not available')
+    out = str(tmp_path_factory.mktemp('emu') / 'libbessel_emu.so')
+    subprocess.run([gxx, '-O2', '-std=c++17', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared',
+                    '-fPIC', os.path.join(ROOT, 'tests', 'host_emu', 'bessel_host.cpp'), '-o', out], check=True,
+                   capture_output=True, timeout=300)
+    return C.CDLL(out)
+
+
+def _emu_bessel(lib, x, which):
+    x = np.ascontiguousarray(x, np.float32)
+    a, b = np.empty_like(x), np.empty_like(x)
+    lib.qb_emu_bessel(x.ctypes.data_as(C.c_void_p), C.c_int(x.size), C.c_int(which), a.ctypes.data_as(C.c_void_p),
+                      b.ctypes.data_as(C.c_void_p))
+    return a, b
+
+
+def test_device_bessel_source_on_the_host_against_scipy(bessel_emu):
+    """The Bessel kernels of the hot path (csrc/bessel.cuh, the source the GPU kernels are built from) evaluated on the
+    host: (1 - J0, J1) against scipy in each range INCLUDING the overlap a straddling warp pass uses (mid on [2, 9],
+    big from 6.5), at the error bars the header states; the reference's own float32 Bessel (Cephes j0f, 1.9e-7) is the
+    yardstick -- the signal tolerance of 1e-5 leaves a factor of 20."""
+    import scipy.special as sp
+    bars = {'production selection': (0.0, 40.0, 0, 6e-7, 4.5e-7), 'small': (0.0, 3.0, 1, 2.5e-7, 2.5e-7),
+            'mid': (2.0, 9.0, 2, 5e-7, 4e-7), 'big': (6.5, 40.0, 3, 6e-7, 4.5e-7), 'big, far': (40.0, 400.0, 3, 1.2e-6, 1.5e-6)}
+    for name, (lo, hi, which, bar0, bar1) in bars.items():
+        x = np.linspace(lo, hi, 200001).astype(np.float32)
+        omj0, j1 = _emu_bessel(bessel_emu, x, which)
+        x64 = x.astype(np.float64)
+        assert np.abs(omj0 - (1.0 - sp.j0(x64))).max() < bar0, name
+        assert np.abs(j1 - sp.j1(x64)).max() < bar1, name
+    # small arguments carry the largest quadrature weights (~ 1 / u^2): RELATIVE accuracy there, no cancellation
+    x = np.linspace(1e-6, 0.05, 2001).astype(np.float32)
+    omj0, j1 = _emu_bessel(bessel_emu, x, 0)
+    z = x.astype(np.float64) ** 2
+    series = z / 4 - z * z / 64 + z ** 3 / 2304
+    assert np.max(np.abs(omj0 - series) / series) < 2.5e-7
+    assert np.max(np.abs(j1 - sp.j1(x.astype(np.float64))) / sp.j1(x.astype(np.float64))) < 2.5e-7
+    x = np.linspace(0.05, 3.0, 20001).astype(np.float32)
+    omj0, _ = _emu_bessel(bessel_emu, x, 0)
+    want = 1.0 - sp.j0(x.astype(np.float64))
+    assert np.max(np.abs(omj0 - want) / want) < 4e-7
+    assert _emu_bessel(bessel_emu, np.zeros(1, np.float32), 0)[0][0] == 0.0       # node 0 of a dead voxel stays exactly 0
+
+
+def test_packed_quadrature_steps_equal_the_scalar_kernels(bessel_emu):
+    """acc_small2 / acc_mid2 / acc_big2 (fma.rn.f32x2 on register pairs; emulated per half on the host) accumulate
+    w (1 - J0) and (w m) J1 -- the same values the scalar kernels give, to the last float32 rounding of the products."""
+    import scipy.special as sp
+    w, A = np.float32(0.37), np.float32(13.0)
+    for which, lo, hi in ((1, 0.0, 3.0), (2, 2.0, 9.0), (3, 6.5, 40.0)):
+        x = np.linspace(lo, hi, 100000).astype(np.float32)
+        acc_i, acc_b = np.empty_like(x), np.empty_like(x)
+        bessel_emu.qb_emu_acc2(x.ctypes.data_as(C.c_void_p), C.c_int(x.size // 2), C.c_int(which), C.c_float(w), C.c_float(A),
+                               acc_i.ctypes.data_as(C.c_void_p), acc_b.ctypes.data_as(C.c_void_p))
+        omj0, j1 = _emu_bessel(bessel_emu, x, which)
+        assert np.abs(acc_i - w * omj0).max() <= 1.2e-7                          # one rounding of the product
+        x64 = x.astype(np.float64)
+        m = (x / A).astype(np.float64)
+        want_b = float(w) * x64 * sp.j1(x64) if which == 1 else float(w) * m * sp.j1(x64)
+        assert np.abs(acc_b - want_b).max() < 6e-7
+        assert np.abs(acc_i - float(w) * (1.0 - sp.j0(x64))).max() < 3e-7
+
+
 def test_ctypes_signatures_match_the_header_prototypes(qb):
     """Every prototype of include/qbold.h against the ctypes signature the Python side binds it with: same number of
     parameters, pointer / int32 / int64 / uint64 / float / double in the same positions (a drift here is a silent
