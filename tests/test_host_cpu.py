@@ -138,6 +138,46 @@ def test_philox_known_answers_and_streams():
         assert x.min() >= 0 and x.max() < n and len(np.unique(x)) == len(x)
 
 
+def test_device_rng_source_on_the_host_matches_the_oracle_bit_for_bit(tmp_path):
+    """csrc/rng.cuh (Philox4x32-10 and the 24-bit uniform, __host__ __device__ in the source) compiled for the host:
+    the Random123 known answers, and word-for-word equality with oracle/philox.py for the counter layout the kernels use
+    (index_lo, index_hi, stream, 0 | seed_lo, seed_hi), incl. indices beyond 2^32 and the stream ids."""
+    import shutil
+    import subprocess
+    gxx = shutil.which('g++')
+    if not gxx:
+        pytest.skip('g++ not available')
+    so = str(tmp_path / 'librng_emu.so')
+    subprocess.run([gxx, '-O2', '-std=c++17', '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'rng_host.cpp'), '-o', so], check=True, capture_output=True,
+                   timeout=300)
+    lib = C.CDLL(so)
+    lib.qb_emu_stream_id.restype = C.c_uint32
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        out = (C.c_uint32 * 4)()
+        lib.qb_emu_philox_raw((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        assert tuple(out) == want
+    assert [lib.qb_emu_stream_id(i) for i in range(5)] == [philox.STREAM_REPARAM, philox.STREAM_KL, philox.STREAM_SNR,
+                                                            philox.STREAM_NOISE, philox.STREAM_MISALIGN]
+    rng = np.random.default_rng(3)
+    index = np.concatenate([np.arange(4096, dtype=np.uint64), rng.integers(0, 1 << 40, 4096, dtype=np.uint64),
+                            np.uint64(1 << 32) + np.arange(-2, 3).astype(np.uint64)])
+    for seed, stream in ((0, philox.STREAM_REPARAM), (0x9E3779B97F4A7C15, philox.STREAM_KL + 17),
+                         (0xFFFFFFFFFFFFFFFF, philox.STREAM_MISALIGN)):
+        words = np.empty((index.size, 4), np.uint32)
+        u = np.empty((index.size, 4), np.float32)
+        lib.qb_emu_philox(index.ctypes.data_as(C.c_void_p), C.c_int(index.size), C.c_uint32(stream), C.c_uint64(seed),
+                          words.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
+        lo, hi, k0, k1 = philox._words(index, seed)
+        want = np.stack(philox.philox4x32_10(lo, hi, np.uint32(stream), np.uint32(0), k0, k1), -1)
+        assert np.array_equal(words, want)
+        assert np.array_equal(u, philox.u01(want)) and u.min() > 0.0 and u.max() < 1.0
+
+
 def test_static_lane_schedule_covers_every_node_once(qb):
     """QboldParams::sched_*: every (column, node>=1) pair is dealt to exactly one (pass, lane) with its Simpson
     weight, a lane keeps one column per phase, and the first-visit flags are consistent."""
