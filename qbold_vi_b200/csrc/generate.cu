@@ -10,37 +10,7 @@
 
 namespace qb {
 
-// Keyed bijection of [0, n): 4-round balanced Feistel network on 2*half_bits bits with
-// cycle walking.  Stands in for tf.random.shuffle (signals.py:279) without materialising a
-// permutation array in HBM (1e9-voxel generation, BASELINE config 5).  oracle/philox.py
-// implements the identical function.
-__host__ __device__ __forceinline__ uint32_t feistel_round(uint32_t r, uint32_t key) {
-    uint32_t h = r * 0x9E3779B1u + key;
-    h ^= h >> 15;
-    h *= 0x85EBCA77u;
-    h ^= h >> 13;
-    h *= 0xC2B2AE3Du;
-    h ^= h >> 16;
-    return h;
-}
-
-__host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t i, uint64_t n, int half_bits, uint64_t seed) {
-    const uint32_t mask = (half_bits >= 32) ? 0xffffffffu : ((1u << half_bits) - 1u);
-    uint64_t x = i;
-    do {
-        uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t key = (uint32_t)(seed >> (16 * (k & 1))) + 0x7F4A7C15u * (uint32_t)(k + 1) +
-                                 (uint32_t)(seed >> 32);
-            const uint32_t t = l ^ (feistel_round(r, key) & mask);
-            l = r;
-            r = t;
-        }
-        x = ((uint64_t)l << half_bits) | r;
-    } while (x >= n);
-    return x;
-}
+// (the keyed Feistel bijection that stands in for tf.random.shuffle lives in rng.cuh: feistel_permute)
 
 template <int PATH>
 __global__ void __launch_bounds__(kThreads) k_generate(const __grid_constant__ QboldParams P,

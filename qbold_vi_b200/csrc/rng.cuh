@@ -44,6 +44,38 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, u
 // 24-bit uniform in (0, 1): (top 24 bits + 0.5) * 2^-24 -- never 0 or 1.
 __host__ __device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-08f; }
 
+// Keyed bijection of [0, n): 4-round balanced Feistel network on 2*half_bits bits with
+// cycle walking.  Stands in for tf.random.shuffle (signals.py:279) without materialising a
+// permutation array in HBM (1e9-voxel generation, BASELINE config 5).  oracle/philox.py
+// implements the identical function.
+__host__ __device__ __forceinline__ uint32_t feistel_round(uint32_t r, uint32_t key) {
+    uint32_t h = r * 0x9E3779B1u + key;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    h ^= h >> 13;
+    h *= 0xC2B2AE3Du;
+    h ^= h >> 16;
+    return h;
+}
+
+__host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t i, uint64_t n, int half_bits, uint64_t seed) {
+    const uint32_t mask = (half_bits >= 32) ? 0xffffffffu : ((1u << half_bits) - 1u);
+    uint64_t x = i;
+    do {
+        uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t key = (uint32_t)(seed >> (16 * (k & 1))) + 0x7F4A7C15u * (uint32_t)(k + 1) +
+                                 (uint32_t)(seed >> 32);
+            const uint32_t t = l ^ (feistel_round(r, key) & mask);
+            l = r;
+            r = t;
+        }
+        x = ((uint64_t)l << half_bits) | r;
+    } while (x >= n);
+    return x;
+}
+
 #ifdef __CUDACC__
 // Two independent N(0,1) draws from two words (Box-Muller, accurate logf/sincospif).
 __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {

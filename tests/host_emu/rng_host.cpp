@@ -42,3 +42,11 @@ extern "C" uint32_t qb_emu_stream_id(int which) {
         default: return qb::kStreamMisalign;
     }
 }
+
+// the keyed Feistel bijection of [0, n) that stands in for tf.random.shuffle (half_bits as qbold_generate derives it)
+extern "C" void qb_emu_feistel(const uint64_t* i, int count, uint64_t n, uint64_t seed, uint64_t* out) {
+    int bits = 1;
+    while (bits < 64 && (1ull << bits) < n) ++bits;
+    const int half_bits = (bits + 1) / 2;
+    for (int k = 0; k < count; ++k) out[k] = qb::feistel_permute(i[k], n, half_bits, seed);
+}

@@ -176,6 +176,16 @@ def test_device_rng_source_on_the_host_matches_the_oracle_bit_for_bit(tmp_path):
         want = np.stack(philox.philox4x32_10(lo, hi, np.uint32(stream), np.uint32(0), k0, k1), -1)
         assert np.array_equal(words, want)
         assert np.array_equal(u, philox.u01(want)) and u.min() > 0.0 and u.max() < 1.0
+    # the Feistel shuffle of the streaming generator: a bijection of [0, n), identical to the oracle's
+    for n, seed in ((1, 5), (2, 5), (529, 99), (6250000, 1), (1000003, 0xFEDCBA9876543210), ((1 << 33) + 7, 3)):
+        m = int(min(n, 4000))
+        i = np.arange(m, dtype=np.uint64) if n <= 4000 else rng.integers(0, n, m, dtype=np.uint64)
+        out = np.empty(m, np.uint64)
+        lib.qb_emu_feistel(i.ctypes.data_as(C.c_void_p), C.c_int(m), C.c_uint64(n), C.c_uint64(seed),
+                           out.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(out, philox.feistel_permute(i, n, seed).astype(np.uint64)) and int(out.max()) < n
+        if n <= 4000:
+            assert len(np.unique(out)) == n
 
 
 def test_static_lane_schedule_covers_every_node_once(qb):
