@@ -310,6 +310,17 @@ __device__ __forceinline__ void load_sched(const QboldParams& P, SchedSmem& s) {
 
 // Shared-memory accesses of the scheduled path use explicit 32-bit shared addresses: one LDS/STS with a
 // register base + immediate offset, no generic-to-shared address arithmetic inside the voxel loop.
+#ifdef QB_HOST_EMU
+// tests/host_emu: the same code on the host.  A "shared address" is the 32-bit offset of the object from the
+// emulator's anchor (qb_emu::smem_anchor, same module), so the register-base + immediate-offset arithmetic of the
+// scheduled path runs unchanged; the ld/st.shared statements become plain loads and stores.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return qb_emu::to_shared(p); }
+__device__ __forceinline__ float2 lds_f2(unsigned a) { return *static_cast<const float2*>(qb_emu::from_shared(a)); }
+__device__ __forceinline__ float4 lds_f4(unsigned a) { return *static_cast<const float4*>(qb_emu::from_shared(a)); }
+__device__ __forceinline__ float lds_f1(unsigned a) { return *static_cast<const float*>(qb_emu::from_shared(a)); }
+__device__ __forceinline__ unsigned lds_u8(unsigned a) { return *static_cast<const unsigned char*>(qb_emu::from_shared(a)); }
+__device__ __forceinline__ void sts_f1(unsigned a, float v) { *static_cast<float*>(qb_emu::from_shared(a)) = v; }
+#else
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float2 lds_f2(unsigned a) {
     float2 v;
@@ -332,6 +343,7 @@ __device__ __forceinline__ unsigned lds_u8(unsigned a) {
     return v;
 }
 __device__ __forceinline__ void sts_f1(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+#endif   // QB_HOST_EMU
 
 template <bool BWD>
 __device__ __forceinline__ void acc_small(float x, float w, float& accI, float& accS) {
