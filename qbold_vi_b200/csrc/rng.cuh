@@ -76,7 +76,7 @@ __host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t i, uint64_
     return x;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(QB_HOST_EMU)
 // Two independent N(0,1) draws from two words (Box-Muller, accurate logf/sincospif).
 __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {
     const float rad = sqrtf(-2.0f * logf(u01(r0)));
