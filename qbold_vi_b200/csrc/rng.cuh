@@ -99,6 +99,12 @@ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t index, uint3
 // draws with radius < 0.04, where the 2^-22 absolute error of lg2.approx near 1 dominates) -- far below the
 // estimators' sampling noise; four MUFU + ~8 FP32 instructions instead of ~75.  The likelihood's own reparameterisation draw and the dataset noise keep the
 // accurate logf / sincospif path above.
+#ifdef QB_HOST_EMU   // tests/host_emu: the SFU approximations replaced by the functions they approximate
+__device__ __forceinline__ float lg2_approx(float x) { return log2f(x); }
+__device__ __forceinline__ float sqrt_approx(float x) { return sqrtf(x); }
+__device__ __forceinline__ float sin_approx(float x) { return sinf(x); }
+__device__ __forceinline__ float cos_approx(float x) { return cosf(x); }
+#else
 __device__ __forceinline__ float lg2_approx(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -119,6 +125,7 @@ __device__ __forceinline__ float cos_approx(float x) {
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif   // QB_HOST_EMU
 
 __device__ __forceinline__ void mc_box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {
     const float rad = sqrt_approx(fmaxf(lg2_approx(u01(r0)) * -1.3862943611198906f, 0.f));   // sqrt(-2 ln u)
