@@ -24,7 +24,7 @@
 #define __shared__ static
 #define __grid_constant__
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct float2 {
     float x, y;
@@ -184,3 +184,59 @@ static inline size_t __cvta_generic_to_shared(const void* p) { return qb_emu::to
 
 // host-API names the launch helpers mention (never called in the emulator)
 constexpr cudaError_t cudaSuccess = 0;
+
+// ---- additions for the ELBO kernels
+using std::isfinite;
+using std::isnan;
+using std::isinf;
+#define __noinline__ __attribute__((noinline))
+struct float3 {
+    float x, y, z;
+};
+static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
+static inline double atomicAdd(double* p, double v) {
+    uint64_t o = __atomic_load_n(reinterpret_cast<uint64_t*>(p), __ATOMIC_RELAXED), w;
+    double old;
+    do {
+        std::memcpy(&old, &o, 8);
+        const double want = old + v;
+        std::memcpy(&w, &want, 8);
+    } while (!__atomic_compare_exchange_n(reinterpret_cast<uint64_t*>(p), &o, w, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return old;
+}
+static inline float atomicAdd(float* p, float v) {
+    float old;
+    uint32_t o = __atomic_load_n(reinterpret_cast<uint32_t*>(p), __ATOMIC_RELAXED), w;
+    do {
+        std::memcpy(&old, &o, 4);
+        const float want = old + v;
+        std::memcpy(&w, &want, 4);
+    } while (!__atomic_compare_exchange_n(reinterpret_cast<uint32_t*>(p), &o, w, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return old;
+}
+static inline int __shfl_xor_sync(unsigned, int v, int lane_mask) {
+    return (int)qb_emu::exchange((uint32_t)v, qb_emu::my_lane() ^ lane_mask);
+}
+static inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
+    uint64_t u;
+    std::memcpy(&u, &v, 8);
+    const uint64_t lo = qb_emu::exchange((uint32_t)u, qb_emu::my_lane() ^ lane_mask);
+    const uint64_t hi = qb_emu::exchange((uint32_t)(u >> 32), qb_emu::my_lane() ^ lane_mask);
+    u = lo | (hi << 32);
+    std::memcpy(&v, &u, 8);
+    return v;
+}
+static inline double __shfl_sync(unsigned, double v, int src) {
+    uint64_t u;
+    std::memcpy(&u, &v, 8);
+    const uint64_t lo = qb_emu::exchange((uint32_t)u, src);
+    const uint64_t hi = qb_emu::exchange((uint32_t)(u >> 32), src);
+    u = lo | (hi << 32);
+    std::memcpy(&v, &u, 8);
+    return v;
+}
+static inline float __shfl_down_sync(unsigned, float v, unsigned delta) {
+    const int src = qb_emu::my_lane() + (int)delta;
+    const float got = __uint_as_float(qb_emu::exchange(__float_as_uint(v), src & 31));
+    return src < 32 ? got : v;
+}

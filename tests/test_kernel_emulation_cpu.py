@@ -177,3 +177,148 @@ def test_misalignment_kernel_with_recorded_and_philox_draws(emu, qb):
     assert rel_elem(got, want) < SIG_TOL
     hit = u < prob
     assert 0.2 < hit.mean() < 0.5 and np.array_equal(got[~hit], clean[~hit]) and np.array_equal(got[:, :5], clean[:, :5])
+
+
+# ------------------------------------------------------------------------------------------- likelihood-side kernels (K2)
+@pytest.fixture(scope='module')
+def emu_elbo(tmp_path_factory):
+    gxx = shutil.which('g++')
+    if not gxx:
+        pytest.skip('g++ not available')
+    out = str(tmp_path_factory.mktemp('emu_elbo') / 'libelbo_emu.so')
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+                    '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'elbo_host.cpp'), '-o', out], check=True, capture_output=True,
+                   timeout=900)
+    return C.CDLL(out)
+
+
+def _trainer(qb, **kw):
+    args = dict(student_t_df=200, multi_image_normalisation=False, use_mvg=True, use_population_prior=False,
+                predict_log_data=False, seed=1234)
+    args.update(kw)
+    return qb.EncoderTrainer(_cfg(), **args)
+
+
+def _elbo(lib, params, q, sigma, y, mask, prior, eps=None, eps_kl=None, kl_samples=70, seed=0, offset=0, pair=1, path=0,
+          grid=2, seed_dev=None, kl_weight=1.0, mask_sum=None, inv_dev=False):
+    n, nt = q.shape[0], sigma.shape[1]
+    arrs = [None if a is None else np.ascontiguousarray(a, np.float32) for a in (q, sigma, y, mask, prior, eps, eps_kl)]
+    gq, gs = np.full((n, 5), np.nan, np.float32), np.full((n, nt), np.nan, np.float32)
+    nm, km, sums = np.full(n, np.nan, np.float32), np.full(n, np.nan, np.float32), np.zeros(4, np.float64)
+    inv = np.float32(1.0 / float(mask.sum() if mask_sum is None else mask_sum))
+    inv_arr = np.array([inv], np.float32)
+    sd = None if seed_dev is None else np.array([seed_dev], np.uint64)
+    rc = lib.qb_emu_elbo(C.byref(params), *[_p(a) for a in arrs], C.c_uint64(seed), _p(sd), C.c_uint64(offset), kl_samples,
+                         C.c_float(0.0 if inv_dev else inv), _p(inv_arr) if inv_dev else None, C.c_float(kl_weight),
+                         C.c_int64(n), _p(gq), _p(gs), _p(nm), _p(km), _p(sums), pair, path, grid)
+    assert rc == 0
+    return dict(grad_q=gq, grad_sigma=gs, nll_map=nm, kl_map=km, nll=sums[0] * float(inv), kl=sums[1] * float(inv),
+                mask_sum=sums[2], non_finite=sums[3])
+
+
+def _elbo_batch(ph, n, seed):
+    r = np.random.default_rng(seed)
+    q = np.stack([r.normal(-0.3, 0.7, n), r.normal(0, 0.6, n), r.normal(-1.2, 0.7, n), r.normal(0, 0.6, n),
+                  r.normal(0, 0.8, n)], -1).astype(np.float32)
+    prior = (q + r.normal(0, 0.3, (n, 5))).astype(np.float32)
+    sigma = np.exp(r.normal(np.log(0.05), 0.2, (n, 11))).astype(np.float32)
+    truth = np.stack([r.uniform(0.1, 0.7, n), r.uniform(0.005, 0.15, n)], -1)
+    data = (o.forward(ph, truth, dtype=np.float64) * 100 * (1 + 0.02 * r.standard_normal((n, 11)))).astype(np.float32)
+    mask = (r.uniform(size=n) > 0.3).astype(np.float32)
+    return q, prior, sigma, data * mask[:, None], mask
+
+
+@pytest.mark.parametrize('tag', ['optimal', 'multinorm', 'studentt'])
+def test_fused_elbo_kernels_on_the_host_match_the_reference_fixture(emu_elbo, qb, tag):
+    """k_elbo_pair<HAS_PRIOR> (production) and the generic k_elbo on the scheduled and the column-group path: loss terms,
+    maps and both gradients against the fixture recorded from the reference's model.py + signals.py."""
+    e = golden('ref_shim_elbo_%s.npz' % tag)
+    tr = _trainer(qb, student_t_df=float(e['student_t_df']), multi_image_normalisation=bool(e['multi_image_normalisation']))
+    layer = qb.SignalGenerationLayer(_cfg(), True, True)
+    params = tr._params_for(layer)
+    plain = type(params)()
+    C.memmove(C.byref(plain), C.byref(params), C.sizeof(plain))
+    plain.sched_phases = 0
+    for P, pair, path in ((params, 1, 0), (params, 0, 0), (plain, 0, 1)):
+        r = _elbo(emu_elbo, P, e['q'], e['sigma'], e['data'], e['mask'], e['prior'], e['eps'], e['eps_kl'], pair=pair, path=path)
+        assert rel_elem(r['nll'], e['nll']) < GRAD_TOL and rel_elem(r['kl'], e['kl']) < GRAD_TOL
+        assert rel_max(r['nll_map'], e['nll_map']) < GRAD_TOL
+        assert rel_max(r['grad_q'], e['grad_q_nll'] + e['grad_q_kl']) < GRAD_TOL
+        assert rel_max(r['grad_sigma'], e['grad_sigma']) < GRAD_TOL
+        assert r['mask_sum'] == e['mask'].sum() and r['non_finite'] == 0
+        dead = e['mask'] == 0
+        assert np.all(r['grad_q'][dead] == 0) and np.all(r['grad_sigma'][dead] == 0)     # model.py:564,661
+    # no prior: likelihood term only
+    r = _elbo(emu_elbo, params, e['q'], e['sigma'], e['data'], e['mask'], None, e['eps'], None, kl_samples=0)
+    assert rel_elem(r['nll'], e['nll']) < GRAD_TOL and r['kl'] == 0.0
+    assert rel_max(r['grad_q'], e['grad_q_nll']) < GRAD_TOL
+
+
+def test_in_kernel_philox_draws_and_the_device_resident_key(emu_elbo, qb):
+    """No explicit draws: in-kernel Philox + Box-Muller against the oracle fed oracle/philox.py draws for the same
+    (seed, global voxel index).  The Philox key read through a pointer (qbold_elbo_fused_graph, the captured training
+    step) and 1/sum(mask) read through a pointer give the same bits as the by-value launch; so does any launch shape."""
+    ph = o.parse_params(_cfg())
+    n, S, seed, off = 384, 70, 0x9E3779B97F4A7C15 + 99, (1 << 32) + 1_234_567
+    q, prior, sigma, data, mask = _elbo_batch(ph, n, 31)
+    idx = np.arange(n, dtype=np.uint64) + np.uint64(off)
+    eps, eps_kl = philox.reparam_eps(seed, idx), philox.kl_eps(seed, idx, S)
+    ref = o.elbo_and_grads(ph, q, sigma, data, mask, prior, eps, eps_kl, np.float64)
+    layer = qb.SignalGenerationLayer(_cfg(), True, True)
+    params = _trainer(qb)._params_for(layer)
+    r = _elbo(emu_elbo, params, q, sigma, data, mask, prior, kl_samples=S, seed=seed, offset=off)
+    assert rel_elem(r['nll'], ref['nll']) < GRAD_TOL and rel_elem(r['kl'], ref['kl']) < GRAD_TOL
+    assert rel_max(r['nll_map'], ref['nll_map']) < GRAD_TOL and rel_max(r['kl_map'], ref['kl_map']) < GRAD_TOL
+    assert rel_max(r['grad_q'], ref['grad_q']) < GRAD_TOL and rel_max(r['grad_sigma'], ref['grad_sigma']) < GRAD_TOL
+    by_ptr = _elbo(emu_elbo, params, q, sigma, data, mask, prior, kl_samples=S, seed=12345, seed_dev=seed, offset=off,
+                   inv_dev=True, grid=3)
+    for k in ('grad_q', 'grad_sigma', 'nll_map', 'kl_map'):
+        assert np.array_equal(by_ptr[k], r[k]), k
+    # explicit draws equal to the Philox draws reproduce the likelihood side bit for bit; the KL differs only by the
+    # SFU-approximation Box-Muller of the sampling loop (emulated with the exact functions here)
+    ex = _elbo(emu_elbo, params, q, sigma, data, mask, prior, eps, eps_kl, kl_samples=S)
+    assert rel_max(ex['nll_map'], r['nll_map']) < 1e-6 and rel_max(ex['kl_map'], r['kl_map']) < 1e-4
+    # shards of the batch with the global mask count and the shard's global offset: same per-voxel results
+    h = 192
+    parts = [_elbo(emu_elbo, params, q[s], sigma[s], data[s], mask[s], prior[s], kl_samples=S, seed=seed,
+                   offset=off + s.start, mask_sum=mask.sum()) for s in (slice(0, h), slice(h, n))]
+    assert np.array_equal(np.concatenate([p['grad_q'] for p in parts]), r['grad_q'])
+    assert abs(parts[0]['nll'] + parts[1]['nll'] - r['nll']) < 1e-6 * abs(r['nll'])
+
+
+def test_kl_reparam_and_posterior_statistics_kernels(emu_elbo, qb):
+    """k_kl (70-sample Monte Carlo with recorded draws, and the closed form), k_reparam and k_posterior_stats against
+    the reference-source fixtures and the oracle."""
+    e = golden('ref_shim_elbo_optimal.npz')
+    n = e['q'].shape[0]
+    q, prior, mask = (np.ascontiguousarray(e[k], np.float32) for k in ('q', 'prior', 'mask'))
+    eps_kl = np.ascontiguousarray(e['eps_kl'], np.float32)
+    kl_map, grad = np.full(n, np.nan, np.float32), np.full((n, 5), np.nan, np.float32)
+    emu_elbo.qb_emu_kl(_p(q), _p(prior), _p(mask), _p(eps_kl), C.c_uint64(0), C.c_uint64(0), 70, C.c_int64(n), _p(kl_map),
+                       _p(grad), 1)
+    assert rel_elem(kl_map.sum() / mask.sum(), e['kl']) < GRAD_TOL
+    assert rel_max(grad / mask.sum(), e['grad_q_kl']) < GRAD_TOL
+    emu_elbo.qb_emu_kl(_p(q), _p(prior), _p(mask), None, C.c_uint64(0), C.c_uint64(0), 0, C.c_int64(n), _p(kl_map), _p(grad), 1)
+    assert rel_max(kl_map, np.where(mask > 0, o.closed_form_kl(prior, q), 0)) < 1e-5
+    # reparameterised sample (model.py:21-50)
+    eps = np.ascontiguousarray(e['eps'], np.float32)
+    out = np.full((n, 2), np.nan, np.float32)
+    emu_elbo.qb_emu_reparam(_p(q), _p(eps), C.c_uint64(0), C.c_uint64(0), C.c_int64(n), _p(out))
+    want, _ = o.reparam_sample(q, eps, True, np.float64)
+    assert rel_max(out, want) < 1e-6
+    seed, off = 77, 5000
+    emu_elbo.qb_emu_reparam(_p(q), None, C.c_uint64(seed), C.c_uint64(off), C.c_int64(n), _p(out))
+    want, _ = o.reparam_sample(q, philox.reparam_eps(seed, np.arange(n, dtype=np.uint64) + np.uint64(off)), True, np.float64)
+    assert rel_max(out, want) < 1e-5
+    # posterior statistics (model.py:326-343): in-kernel draws, 64 samples per voxel, against explicit oracle samples
+    layer = qb.SignalGenerationLayer(_cfg(), True, True)
+    S = 64
+    mean3, var3 = np.full((n, 3), np.nan, np.float32), np.full((n, 3), np.nan, np.float32)
+    emu_elbo.qb_emu_posterior_stats(C.c_float(layer.params.dw_k), _p(q), None, C.c_uint64(seed), C.c_uint64(off), S,
+                                    C.c_int64(n), _p(mean3), _p(var3), 1)
+    draws = philox.kl_eps(seed, np.arange(n, dtype=np.uint64) + np.uint64(off), S)               # [n, S, 2]
+    smp = np.stack([o.reparam_sample(q, draws[:, s], True, np.float64)[0] for s in range(S)], 1)  # [n, S, 2]
+    r2p = float(layer.params.dw_k) * smp[..., 0] * smp[..., 1]
+    vals = np.concatenate([smp, r2p[..., None]], -1)
+    assert rel_max(mean3, vals.mean(1)) < 1e-4 and rel_max(var3, vals.var(1)) < 2e-3
