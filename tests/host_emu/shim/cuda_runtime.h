@@ -95,11 +95,14 @@ inline unsigned ballot(bool pred) {
     return m;
 }
 
-// Runs kernel(args...) as a grid of `grid` CTAs of `block` threads (block a multiple of 32, <= 256), one CTA at a time.
-inline void launch(int grid, int block, const std::function<void()>& kernel) {
+// Runs kernel(args...) as a grid of `grid` x `grid_y` CTAs of `block` threads (block a multiple of 32, <= 256), one CTA
+// at a time.
+inline void launch(int grid, int block, const std::function<void()>& kernel, int grid_y = 1) {
     Cta& c = cta();
     blockDim.x = (unsigned)block;
     gridDim.x = (unsigned)grid;
+    gridDim.y = (unsigned)grid_y;
+    for (int by = 0; by < grid_y; ++by)
     for (int b = 0; b < grid; ++b) {
         c.n_threads = block;
         pthread_barrier_init(&c.bar, nullptr, (unsigned)block);
@@ -107,9 +110,10 @@ inline void launch(int grid, int block, const std::function<void()>& kernel) {
         std::vector<std::thread> threads;
         threads.reserve((size_t)block);
         for (int t = 0; t < block; ++t)
-            threads.emplace_back([&kernel, b, t]() {
+            threads.emplace_back([&kernel, b, by, t]() {
                 threadIdx.x = (unsigned)t;
                 blockIdx.x = (unsigned)b;
+                blockIdx.y = (unsigned)by;
                 kernel();
             });
         for (auto& th : threads) th.join();

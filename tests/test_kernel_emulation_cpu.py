@@ -322,3 +322,81 @@ def test_kl_reparam_and_posterior_statistics_kernels(emu_elbo, qb):
     r2p = float(layer.params.dw_k) * smp[..., 0] * smp[..., 1]
     vals = np.concatenate([smp, r2p[..., None]], -1)
     assert rel_max(mean3, vals.mean(1)) < 1e-4 and rel_max(var3, vals.var(1)) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------- streaming generation (K3)
+@pytest.fixture(scope='module')
+def emu_gen(tmp_path_factory):
+    gxx = shutil.which('g++')
+    if not gxx:
+        pytest.skip('g++ not available')
+    out = str(tmp_path_factory.mktemp('emu_gen') / 'libgen_emu.so')
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+                    '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'generate_host.cpp'), '-o', out], check=True, capture_output=True,
+                   timeout=900)
+    return C.CDLL(out)
+
+
+def _generate(lib, layer, oefs, dbvs, perm, seed, n_chunks, snr_u01=None, noise_eps=None, pair=1, path=0):
+    """generate_from_marginals (qbold_vi_b200/signals.py) on the emulated kernels."""
+    oefs, dbvs = np.ascontiguousarray(oefs, np.float32), np.ascontiguousarray(dbvs, np.float32)
+    perm = None if perm is None else np.ascontiguousarray(perm, np.int64)
+    nt, total = layer.n_tau, oefs.size * dbvs.size
+    chunk = total // n_chunks
+    n_x = chunk * n_chunks
+    x = np.full((n_x, nt), np.nan, np.float32)
+    y = np.full((total, 3), np.nan, np.float32)
+    rc = lib.qb_emu_generate(C.byref(layer.params), _p(oefs), C.c_int64(oefs.size), _p(dbvs), C.c_int64(dbvs.size), _p(perm),
+                             C.c_uint64(seed), C.c_int64(0), C.c_int64(n_x), _p(x), _p(y), pair, path, 2)
+    assert rc == 0
+    if total > n_x:
+        tail = np.full((total - n_x, 3), np.nan, np.float32)
+        lib.qb_emu_generate(C.byref(layer.params), _p(oefs), C.c_int64(oefs.size), _p(dbvs), C.c_int64(dbvs.size), _p(perm),
+                            C.c_uint64(seed), C.c_int64(n_x), C.c_int64(total - n_x), None, _p(tail), pair, path, 1)
+        y[n_x:] = tail
+    clean = x.copy()
+    if snr_u01 is not None or noise_eps is None:
+        s = None if snr_u01 is None else np.ascontiguousarray(snr_u01[:n_x], np.float32)
+        e = None if noise_eps is None else np.ascontiguousarray(noise_eps[:n_x], np.float32)
+        lib.qb_emu_add_noise_chunked(C.byref(layer.params), _p(x), C.c_int64(chunk), n_chunks, _p(s), _p(e),
+                                     C.c_uint64((seed ^ 0x5DEECE66D) & 0xFFFFFFFFFFFFFFFF), C.c_uint64(0), 2)
+    return x, y, clean
+
+
+@pytest.mark.parametrize('tag', ['u10', 'u0'])
+def test_dataset_generation_kernels_match_the_reference_source(emu_gen, qb, tag):
+    """k_generate_pair / k_generate + the chunked noise kernels against create_synthetic_dataset of the reference
+    (recorded permutation and draws; the S^2 % 10 trailing rows are dropped from x only, signals.py:283-287)."""
+    d = golden('ref_shim_dataset_%s.npz' % tag)
+    ty = d['train_y']
+    grid = np.empty((529, 2), np.float32)
+    grid[d['perm']] = ty[:, :2]
+    oefs, dbvs = grid.reshape(23, 23, 2)[:, 0, 0].copy(), grid.reshape(23, 23, 2)[0, :, 1].copy()
+    layer = qb.SignalGenerationLayer(o.default_config(), True, True)                       # noise ON, as in the INI
+    for pair, path in ((1, 0), (0, 0)):
+        x, y, _ = _generate(emu_gen, layer, oefs, dbvs, d['perm'], 0, 10, d['snr_u01'].reshape(-1), d['noise_eps'],
+                            pair=pair, path=path)
+        assert x.shape == (520, 11) and y.shape == (529, 3)
+        assert rel_elem(y, ty) < 1e-6
+        assert rel_elem(x, d['train_x']) < 2 * SIG_TOL
+
+
+def test_dataset_generation_with_the_feistel_shuffle_and_philox_noise(emu_gen, qb):
+    """No recorded draws: the keyed Feistel shuffle and the Philox noise streams, against the oracle fed
+    oracle/philox.py's permutation and draws."""
+    cfg = o.default_config()
+    ph = o.parse_params(cfg)
+    layer = qb.SignalGenerationLayer(cfg, True, True, seed=4242)
+    r = np.random.default_rng(8)
+    oefs = r.uniform(0.05, 0.8, 40).astype(np.float32)
+    dbvs = r.uniform(0.003, 0.195, 30).astype(np.float32)
+    x, y, clean = _generate(emu_gen, layer, oefs, dbvs, None, 4242, 10)
+    perm = philox.feistel_permute(np.arange(1200), 1200, 4242)
+    assert sorted(perm.tolist()) == list(range(1200))
+    snr = np.concatenate([philox.snr_u01(4242 ^ 0x5DEECE66D, np.arange(i * 120, (i + 1) * 120)) for i in range(10)])
+    eps = np.concatenate([philox.noise_eps(4242 ^ 0x5DEECE66D, np.arange(i * 120, (i + 1) * 120), 11) for i in range(10)])
+    xo, yo = o.synthetic_dataset_from_draws(ph, oefs, dbvs, perm, snr * np.float32(70) + np.float32(50), eps)
+    assert rel_elem(y, yo) < 1e-6
+    assert rel_elem(clean, o.forward(ph, yo[:, :2], dtype=np.float64)) < SIG_TOL
+    assert rel_elem(x, xo) < 2 * SIG_TOL
