@@ -400,3 +400,75 @@ def test_dataset_generation_with_the_feistel_shuffle_and_philox_noise(emu_gen, q
     assert rel_elem(y, yo) < 1e-6
     assert rel_elem(clean, o.forward(ph, yo[:, :2], dtype=np.float64)) < SIG_TOL
     assert rel_elem(x, xo) < 2 * SIG_TOL
+
+
+# ------------------------------------------------------------------------------------------- losses either side (8f-1/2)
+@pytest.fixture(scope='module')
+def emu_losses(tmp_path_factory):
+    gxx = shutil.which('g++')
+    if not gxx:
+        pytest.skip('g++ not available')
+    out = str(tmp_path_factory.mktemp('emu_losses') / 'liblosses_emu.so')
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+                    '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'losses_host.cpp'), '-o', out], check=True, capture_output=True,
+                   timeout=900)
+    return C.CDLL(out)
+
+
+def test_tv_pretraining_and_population_kl_kernels_match_the_reference_source(emu_losses):
+    """k_smoothness, k_synth_nll (mvg / diagonal, fixed and learned InverseGamma), k_diag_kl, k_mog_kl: value and gradient
+    against the fixture recorded from the reference's model.py."""
+    a = golden('ref_shim_adjacent.npz')
+    shp = tuple(int(v) for v in a['shape'])
+    n = int(np.prod(shp))
+    mask = np.ascontiguousarray(a['mask'], np.float32)
+    msum = float(mask.sum())
+    # total variation (model.py:726-754): x / y neighbours inside the mask
+    for tag, c in (('mvg', 5), ('diag', 4)):
+        q = np.ascontiguousarray(a['q5'][:, :c], np.float32)
+        tv, grad = np.zeros(1, np.float64), np.full((n, c), np.nan, np.float32)
+        emu_losses.qb_emu_smoothness(_p(q), c, _p(mask), C.c_int64(shp[0]), shp[1], shp[2], shp[3], C.c_float(1.0 / msum),
+                                     None, _p(tv), _p(grad), 2)
+        assert rel_elem(tv[0] / msum, a['tv_' + tag]) < GRAD_TOL
+        assert rel_max(grad, a['tv_%s_grad' % tag]) < GRAD_TOL
+        scale = np.array([1.0 / msum], np.float32)                                       # the same through a pointer
+        tv2, grad2 = np.zeros(1, np.float64), np.full((n, c), np.nan, np.float32)
+        emu_losses.qb_emu_smoothness(_p(q), c, _p(mask), C.c_int64(shp[0]), shp[1], shp[2], shp[3], C.c_float(0.0),
+                                     _p(scale), _p(tv2), _p(grad2), 1)
+        assert np.array_equal(grad2, grad) and abs(tv2[0] - tv[0]) < 1e-9 * abs(tv[0])
+    # pre-training NLL (model.py:449-514)
+    for tag, use_mvg, ig in (('mvg', 1, (0.0, 0.0)), ('mvg_ig', 1, (3.0, 0.15)), ('diag', 0, (0.0, 0.0)),
+                             ('diag_ig', 0, (3.0, 0.15))):
+        c = 5 if use_mvg else 4
+        pred = np.ascontiguousarray(a['q5'][:, :c], np.float32)
+        labels = np.ascontiguousarray(a['synth_%s_labels' % tag], np.float32)
+        total, grad = np.zeros(1, np.float64), np.full((n, c), np.nan, np.float32)
+        emu_losses.qb_emu_synth_nll(_p(labels), 3, _p(pred), c, use_mvg, C.c_double(ig[0]), C.c_double(ig[1]), None,
+                                    C.c_int64(n), C.c_float(1.0 / n), None, _p(grad), _p(total), None, 1)
+        assert rel_elem(total[0] / n, a['synth_' + tag]) < GRAD_TOL
+        assert rel_max(grad, a['synth_%s_grad' % tag]) < GRAD_TOL
+    # infer_inv_gamma (model.py:454-455,493-496): the 4 hyper-prior channels of voxel 0 (:494), read through a pointer
+    pred8 = np.ascontiguousarray(a['synth_iginf_pred'], np.float32)
+    labels = np.ascontiguousarray(a['synth_iginf_labels'], np.float32)
+    ig4 = np.ascontiguousarray(pred8[0, 4:8])
+    total, grad, igs = np.zeros(1, np.float64), np.full((n, 4), np.nan, np.float32), np.zeros(4, np.float64)
+    emu_losses.qb_emu_synth_nll(_p(labels), 3, _p(pred8), 8, 0, C.c_double(0.0), C.c_double(0.0), _p(ig4), C.c_int64(n),
+                                C.c_float(1.0 / n), None, _p(grad), _p(total), _p(igs), 2)
+    assert rel_elem(total[0] / n, a['synth_iginf']) < GRAD_TOL
+    assert rel_max(grad, a['synth_iginf_grad'][:, :4]) < GRAD_TOL
+    # diagonal KL (model.py:685-708) against a fixed prior
+    q4, p4 = np.ascontiguousarray(a['q5'][:, :4], np.float32), np.ascontiguousarray(a['prior5'][:, :4], np.float32)
+    kl, grad = np.full(n, np.nan, np.float32), np.full((n, 4), np.nan, np.float32)
+    emu_losses.qb_emu_diag_kl(_p(q4), 4, _p(p4), 4, _p(mask), C.c_int64(n), _p(kl), _p(grad), 4, None, 0, 1)
+    assert rel_elem(kl.sum() / msum, a['kl_diag']) < GRAD_TOL
+    assert rel_max(grad / msum, a['kl_diag_grad']) < GRAD_TOL
+    ref, _, _ = o.diag_kl(a['prior5'][:, :4], a['q5'][:, :4])
+    assert rel_max(kl, ref * (mask > 0)) < 1e-5
+    # mixture-of-Gaussians population prior (model.py:666-684), the reference's recorded draw per voxel
+    pred16 = np.ascontiguousarray(a['kl_mog_pred'], np.float32)
+    eps = np.ascontiguousarray(a['kl_mog_eps'], np.float32)
+    kl, grad = np.full(n, np.nan, np.float32), np.full((n, 16), np.nan, np.float32)
+    emu_losses.qb_emu_mog_kl(_p(pred16), 3, _p(mask), _p(eps), C.c_uint64(0), C.c_uint64(0), C.c_int64(n), _p(kl), _p(grad), 2)
+    assert rel_elem(kl.sum() / msum, a['kl_mog']) < GRAD_TOL
+    assert rel_max(grad / msum, a['kl_mog_grad']) < GRAD_TOL
