@@ -52,3 +52,38 @@ extern "C" void qb_emu_posterior_stats(float dw_k, const float* q, const float* 
     qb_emu::launch(grid, qb::kThreads,
                    [&]() { qb::k_posterior_stats(dw_k, q, eps, seed, offset, n_samples, n, mean3, var3); });
 }
+
+// likelihood map of save_predictions (model.py:808-817): pair != 0 -> k_nll_map_pair, else k_nll_map<path>
+extern "C" int qb_emu_nll_map(const QboldParams* P, const float* q, const float* sigma, const float* y, const float* mask,
+                              const float* eps, uint64_t seed, uint64_t offset, int n_samples, int64_t n, float* nll_map,
+                              int pair, int path, int grid) {
+    g_work = 0;
+    const QboldParams params = *P;
+    if (pair) {
+        qb_emu::launch(grid, qb::kThreads, [&]() {
+            qb::k_nll_map_pair(params, q, sigma, y, mask, eps, seed, offset, n_samples, n, nll_map, &g_work);
+        });
+        return 0;
+    }
+#define QB_CASE(PA)                                                                                               \
+    if (path == PA) {                                                                                             \
+        qb_emu::launch(grid, qb::kThreads, [&]() {                                                                \
+            qb::k_nll_map<PA>(params, q, sigma, y, mask, eps, seed, offset, n_samples, n, nll_map, &g_work);      \
+        });                                                                                                       \
+        return 0;                                                                                                 \
+    }
+    QB_CASE(0) QB_CASE(1) QB_CASE(2)
+#undef QB_CASE
+    return -1;
+}
+
+// fine_tune_loss_fn alone on predictions that already exist (model.py:527-568): W = 16 (two voxels per warp) for
+// n_tau <= 16, else 32 -- as qbold_nll picks it
+extern "C" void qb_emu_nll(const QboldParams* P, const float* y, const float* pred, const float* sigma, const float* mask,
+                           int64_t n, float* nll_map, float* d_pred, float* d_sigma, int grid) {
+    const QboldParams params = *P;
+    if (params.n_tau <= 16)
+        qb_emu::launch(grid, qb::kThreads, [&]() { qb::k_nll<16>(params, y, pred, sigma, mask, n, nll_map, d_pred, d_sigma); });
+    else
+        qb_emu::launch(grid, qb::kThreads, [&]() { qb::k_nll<32>(params, y, pred, sigma, mask, n, nll_map, d_pred, d_sigma); });
+}

@@ -472,3 +472,47 @@ def test_tv_pretraining_and_population_kl_kernels_match_the_reference_source(emu
     emu_losses.qb_emu_mog_kl(_p(pred16), 3, _p(mask), _p(eps), C.c_uint64(0), C.c_uint64(0), C.c_int64(n), _p(kl), _p(grad), 2)
     assert rel_elem(kl.sum() / msum, a['kl_mog']) < GRAD_TOL
     assert rel_max(grad / msum, a['kl_mog_grad']) < GRAD_TOL
+
+
+@pytest.mark.parametrize('tag', ['optimal', 'multinorm', 'studentt'])
+def test_standalone_likelihood_and_likelihood_map_kernels(emu_elbo, qb, tag):
+    """k_nll (fine_tune_loss_fn on predictions that already exist: value, d/dsigma) against the reference fixture, and
+    k_nll_map_pair / k_nll_map (likelihood map of save_predictions, model.py:808-817: one forward pass per sample)
+    against the oracle, with explicit draws and with in-kernel Philox draws."""
+    e = golden('ref_shim_elbo_%s.npz' % tag)
+    tr = _trainer(qb, student_t_df=float(e['student_t_df']), multi_image_normalisation=bool(e['multi_image_normalisation']))
+    layer = qb.SignalGenerationLayer(_cfg(), True, True)
+    params = tr._params_for(layer)
+    n = e['q'].shape[0]
+    y, pred, sigma, mask = (np.ascontiguousarray(e[k], np.float32) for k in ('data', 'pred', 'sigma', 'mask'))
+    nll, d_pred, d_sigma = np.full(n, np.nan, np.float32), np.full((n, 11), np.nan, np.float32), np.full((n, 11), np.nan, np.float32)
+    emu_elbo.qb_emu_nll(C.byref(params), _p(y), _p(pred), _p(sigma), _p(mask), C.c_int64(n), _p(nll), _p(d_pred), _p(d_sigma), 1)
+    assert rel_max(nll, e['nll_map']) < GRAD_TOL and rel_elem(nll.sum() / mask.sum(), e['nll']) < GRAD_TOL
+    assert rel_max(d_sigma / mask.sum(), e['grad_sigma']) < GRAD_TOL
+    if tag == 'studentt':
+        return                                              # the oracle's per-sample likelihood covers the Gaussian case
+    ph = o.parse_params(_cfg())
+    q = np.ascontiguousarray(e['q'], np.float32)
+    S, se = 6, 2
+    eps = np.random.default_rng(4).standard_normal((n, S, 2)).astype(np.float32)
+    yt = np.concatenate([e['data'], e['mask'][:, None]], -1)
+
+    def oracle_map(draws):
+        ref = np.zeros(n)
+        for s in range(S):
+            smp, _ = o.reparam_sample(e['q'], draws[:, s], True, np.float64)
+            ref += o.fine_tune_nll(yt, o.forward(ph, smp, dtype=np.float64), e['sigma'], se, np.float64, return_mean=False,
+                                   multi_image_normalisation=bool(e['multi_image_normalisation'])).reshape(-1)
+        return ref / S
+
+    for pair, path in ((1, 0), (0, 0)):
+        got = np.full(n, np.nan, np.float32)
+        rc = emu_elbo.qb_emu_nll_map(C.byref(params), _p(q), _p(sigma), _p(y), _p(mask), _p(eps), C.c_uint64(0), C.c_uint64(0),
+                                     S, C.c_int64(n), _p(got), pair, path, 1)
+        assert rc == 0 and rel_max(got, oracle_map(eps)) < GRAD_TOL
+    seed, off = 31, 1 << 20
+    got = np.full(n, np.nan, np.float32)
+    emu_elbo.qb_emu_nll_map(C.byref(params), _p(q), _p(sigma), _p(y), _p(mask), None, C.c_uint64(seed), C.c_uint64(off), S,
+                            C.c_int64(n), _p(got), 1, 0, 2)
+    draws = philox.kl_eps(seed, np.arange(n, dtype=np.uint64) + np.uint64(off), S)
+    assert rel_max(got, oracle_map(draws)) < GRAD_TOL
