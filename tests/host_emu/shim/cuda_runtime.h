@@ -42,7 +42,7 @@ typedef int cudaError_t;
 
 namespace qb_emu {
 
-constexpr int kMaxWarps = 8;
+constexpr int kMaxWarps = 32;
 
 struct Warp {
     pthread_barrier_t bar;
@@ -95,10 +95,17 @@ inline unsigned ballot(bool pred) {
     return m;
 }
 
-// Runs kernel(args...) as a grid of `grid` x `grid_y` CTAs of `block` threads (block a multiple of 32, <= 256), one CTA
-// at a time.
-inline void launch(int grid, int block, const std::function<void()>& kernel, int grid_y = 1) {
+// Runs kernel(args...) as a grid of `grid` x `grid_y` CTAs of `block` threads (block a multiple of 32, <= 1024), one
+// CTA at a time; smem_bytes = the dynamic shared memory of the launch.
+inline std::vector<float>& dynamic_window() {
+    static std::vector<float> w;
+    return w;
+}
+inline float* dynamic_smem() { return dynamic_window().data(); }       // `extern __shared__` of the running launch
+
+inline void launch(int grid, int block, const std::function<void()>& kernel, int grid_y = 1, size_t smem_bytes = 0) {
     Cta& c = cta();
+    dynamic_window().assign(smem_bytes / sizeof(float) + 4, 0.f);
     blockDim.x = (unsigned)block;
     gridDim.x = (unsigned)grid;
     gridDim.y = (unsigned)grid_y;

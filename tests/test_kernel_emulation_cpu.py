@@ -516,3 +516,63 @@ def test_standalone_likelihood_and_likelihood_map_kernels(emu_elbo, qb, tag):
                             C.c_int64(n), _p(got), 1, 0, 2)
     draws = philox.kl_eps(seed, np.arange(n, dtype=np.uint64) + np.uint64(off), S)
     assert rel_max(got, oracle_map(draws)) < GRAD_TOL
+
+
+# ------------------------------------------------------------------------------------------- encoder block streaming (8f-3)
+@pytest.fixture(scope='module')
+def emu_enc(tmp_path_factory):
+    gxx = shutil.which('g++')
+    if not gxx:
+        pytest.skip('g++ not available')
+    out = str(tmp_path_factory.mktemp('emu_enc') / 'libenc_emu.so')
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+                    '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'encoder_block_host.cpp'), '-o', out], check=True,
+                   capture_output=True, timeout=900)
+    return C.CDLL(out)
+
+
+def test_encoder_block_streaming_kernels(emu_enc):
+    """The elementwise kernels of the fused encoder block (create_block, model.py:142-174) against the formulas in
+    float64 NumPy: gated mix forward (+ the ReLU copy) and backward (incl. the stream-1 addend and the ReLU' of the skip
+    branch), ReLU' + bias-gradient column sums (two-stage fixed-order reduction, accumulate flag), and normalise_data
+    (model.py:97-113) fused with the move to the z-outer layout (ragged tiles, single- and multi-image reference)."""
+    r = np.random.default_rng(12)
+    n, c = 777, 60
+    skip, r0, z, go, add = (r.standard_normal((n, c)).astype(np.float32) for _ in range(5))
+    skip = np.maximum(skip, 0)                                                    # the skip branch ends in a ReLU
+    b_r = r.standard_normal(c).astype(np.float32)
+    off = np.float32(-1.0)
+    out, out_relu = np.full((n, c), np.nan, np.float32), np.full((n, c), np.nan, np.float32)
+    emu_enc.qb_emu_block_mix_forward(_p(skip), _p(r0), _p(b_r), _p(z), C.c_float(off), C.c_int64(n), c, _p(out), _p(out_relu), 3)
+    g = 1.0 / (1.0 + np.exp(-(z.astype(np.float64) + float(off))))
+    rr = r0.astype(np.float64) + b_r
+    want = skip * (1 - g) + rr * g
+    assert rel_max(out, want) < 1e-6 and np.array_equal(out_relu, np.maximum(out, 0))
+    d_skip, d_r, d_z = (np.full((n, c), np.nan, np.float32) for _ in range(3))
+    emu_enc.qb_emu_block_mix_backward(_p(go), _p(skip), _p(r0), _p(b_r), _p(z), C.c_float(off), C.c_int64(n), c, 1, _p(add),
+                                      _p(d_skip), _p(d_r), _p(d_z), 2)
+    assert rel_max(d_skip, (go * (1 - g) + add) * (skip > 0)) < 1e-6
+    assert rel_max(d_r, go * g) < 1e-6 and rel_max(d_z, go * (rr - skip) * g * (1 - g)) < 1e-5
+    emu_enc.qb_emu_block_mix_backward(_p(go), _p(skip), _p(r0), None, _p(z), C.c_float(off), C.c_int64(n), c, 0, None,
+                                      _p(d_skip), _p(d_r), _p(d_z), 1)
+    assert rel_max(d_skip, go * (1 - g)) < 1e-6 and rel_max(d_z, go * (r0.astype(np.float64) - skip) * g * (1 - g)) < 1e-5
+    # ReLU' + column sums
+    y = r.standard_normal((n, c)).astype(np.float32)
+    masked, colsum = np.full((n, c), np.nan, np.float32), np.full(c, 7.0, np.float32)
+    emu_enc.qb_emu_relu_bwd_colsum(_p(go), _p(y), _p(add), C.c_int64(n), c, _p(masked), _p(colsum), 0, 5)
+    want = go * (y > 0) + add
+    assert np.array_equal(masked, want.astype(np.float32)) and rel_max(colsum, want.astype(np.float64).sum(0)) < 1e-5
+    again = colsum.copy()
+    emu_enc.qb_emu_relu_bwd_colsum(_p(go), None, None, C.c_int64(n), c, None, _p(again), 1, 4)     # plain sums, accumulated
+    assert rel_max(again, colsum + go.astype(np.float64).sum(0)) < 1e-5
+    # normalise_data + z-outer transpose
+    for (B, X, Y, Z, T, se, multi) in ((2, 3, 37, 5, 11, 2, 1), (1, 2, 33, 40, 11, 2, 0), (1, 1, 4, 3, 24, 7, 1)):
+        data = (r.uniform(0.0, 3.0, (B, X, Y, Z, T)) * (r.uniform(size=(B, X, Y, Z, 1)) > 0.1)).astype(np.float32)
+        tp = (T + 3) & ~3
+        got = np.full((B, Z, X, Y, tp), np.nan, np.float32)
+        emu_enc.qb_emu_normalise_zouter(_p(data), C.c_int64(B), X, Y, Z, T, se, multi, _p(got))
+        d = np.clip(data.astype(np.float64), 1e-2, 1e8)
+        ref = d[..., se - 1:se + 2].mean(-1, keepdims=True) if multi else d[..., se:se + 1]
+        want = np.log(d / ref).transpose(0, 3, 1, 2, 4)
+        assert rel_max(got[..., :T], want) < 1e-5 and np.all(got[..., T:] == 0)
