@@ -191,4 +191,62 @@ __global__ void __launch_bounds__(kThreads, QB_FWD_MIN_BLOCKS) k_forward_pair(co
     }
 }
 
+
+// Log-linear branch (full_model = False, reference signals.py:194-207): ~30 FLOP per 52-104 B, i.e. HBM-bound.
+// One thread per voxel; the [256 x n_tau] signal / upstream-gradient tiles go through shared memory so that
+// every global access is a coalesced 16-byte vector (a CTA's rows are one contiguous 256*n_tau*4-byte span).
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) k_loglinear(const __grid_constant__ QboldParams P,
+                                                        const float2* __restrict__ oef_dbv,
+                                                        const float* __restrict__ g_signal, float* __restrict__ signal,
+                                                        float2* __restrict__ g_oef_dbv, int64_t n) {
+#ifdef QB_HOST_EMU
+    float4* tile4 = reinterpret_cast<float4*>(qb_emu::dynamic_smem());   // tests/host_emu: the launch's dynamic window
+#else
+    extern __shared__ float4 tile4[];
+#endif
+    float* tile = reinterpret_cast<float*>(tile4);
+    const int nt = P.n_tau;
+    const int64_t v0 = (int64_t)blockIdx.x * kThreads;
+    const int rows = (int)((n - v0 < kThreads) ? (n - v0) : kThreads);
+    const int64_t base = v0 * nt;
+    const int count = rows * nt;
+    const bool vec = ((count & 3) == 0);                       // only the last CTA can be ragged
+    const bool vec_g = vec && ((reinterpret_cast<uintptr_t>(g_signal + base) & 15) == 0);
+    const bool vec_s = vec && ((reinterpret_cast<uintptr_t>(signal + base) & 15) == 0);
+    if (BWD && g_signal != nullptr) {
+        if (vec_g) {
+            const float4* src = reinterpret_cast<const float4*>(g_signal + base);
+            for (int i = threadIdx.x; i < count / 4; i += kThreads) tile4[i] = __ldg(src + i);
+        } else {
+            for (int i = threadIdx.x; i < count; i += kThreads) tile[i] = __ldg(g_signal + base + i);
+        }
+        __syncthreads();
+    }
+    const int r = threadIdx.x;
+    float go = 0.f, gd = 0.f;
+    if (r < rows) {
+        const float2 x = __ldg(oef_dbv + v0 + r);
+        const VoxelPhys vp = voxel_phys<false>(P, x.x, x.y, P.hct);
+        for (int t = 0; t < nt; ++t) {
+            const TauSignal ts = tau_signal<BWD>(P, vp, P.tau[t], P.blood_b[t], 0.f, 0.f);
+            if (BWD) {
+                const float gs = (g_signal != nullptr) ? tile[r * nt + t] : 1.0f;
+                go = fmaf(gs, ts.dS_doef, go);
+                gd = fmaf(gs, ts.dS_ddbv, gd);
+            }
+            tile[r * nt + t] = ts.S;                           // row stride n_tau (odd for 11): conflict-free
+        }
+        if (BWD) g_oef_dbv[v0 + r] = make_float2(go, gd);
+    }
+    if (signal == nullptr) return;
+    __syncthreads();
+    if (vec_s) {
+        float4* dst = reinterpret_cast<float4*>(signal + base);
+        for (int i = threadIdx.x; i < count / 4; i += kThreads) dst[i] = tile4[i];
+    } else {
+        for (int i = threadIdx.x; i < count; i += kThreads) signal[base + i] = tile[i];
+    }
+}
+
 }  // namespace qb

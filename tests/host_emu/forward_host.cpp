@@ -57,3 +57,22 @@ extern "C" void qb_emu_misalign(const QboldParams* P, const float* oef_dbv, int6
             qb::k_misalign<false, qb::kSched>(params, oef_dbv, n, prob, sel_u01, from_index, eps, seed, offset, signal, &g_work);
         });
 }
+
+// k_loglinear<BWD> (full_model = False, signals.py:194-207): one CTA of 256 rows per block, [256 x n_tau] tile in
+// dynamic shared memory -- launch arithmetic of launch_loglinear (forward.cu)
+extern "C" void qb_emu_loglinear(const QboldParams* P, const float* oef_dbv, const float* g_signal, float* signal,
+                                 float* g_oef_dbv, int64_t n, int bwd) {
+    const QboldParams params = *P;
+    const size_t smem = sizeof(float) * qb::kThreads * params.n_tau;
+    const int grid = (int)((n + qb::kThreads - 1) / qb::kThreads);
+    if (bwd)
+        qb_emu::launch(grid, qb::kThreads, [&]() {
+            qb::k_loglinear<true>(params, reinterpret_cast<const float2*>(oef_dbv), g_signal, signal,
+                                  reinterpret_cast<float2*>(g_oef_dbv), n);
+        }, 1, smem);
+    else
+        qb_emu::launch(grid, qb::kThreads, [&]() {
+            qb::k_loglinear<false>(params, reinterpret_cast<const float2*>(oef_dbv), g_signal, signal,
+                                   reinterpret_cast<float2*>(g_oef_dbv), n);
+        }, 1, smem);
+}

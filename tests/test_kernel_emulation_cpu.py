@@ -138,6 +138,35 @@ def test_one_voxel_per_warp_kernel_all_model_variants(emu, qb, full, blood):
         assert rel_max(grad[:, j], h['grad_rand_' + key][:, j]) < GRAD_TOL
 
 
+@pytest.mark.parametrize('blood', [True, False])
+def test_log_linear_kernel(emu, qb, blood):
+    """k_loglinear (full_model = False, the HBM-bound branch): tiles through dynamic shared memory, 16-byte and ragged
+    stores; against the reference-source fixture and, on a ragged batch, the float64 oracle."""
+    key = 'f0_b%d' % int(blood)
+    d = golden('ref_shim_forward.npz')
+    layer = qb.SignalGenerationLayer(_cfg(), False, blood)
+    ph = o.parse_params(_cfg())
+
+    def run(x, g, bwd=True):
+        n = x.shape[0]
+        x = np.ascontiguousarray(x, np.float32)
+        g = None if g is None else np.ascontiguousarray(g, np.float32)
+        sig, grad = np.full((n, 11), np.nan, np.float32), np.full((n, 2), np.nan, np.float32)
+        emu.qb_emu_loglinear(C.byref(layer.params), _p(x), _p(g), _p(sig), _p(grad), C.c_int64(n), int(bwd))
+        return sig, grad
+
+    sig, grad = run(d['oef_dbv'], d['g_rand'])
+    assert rel_elem(sig, d['signal_' + key]) < SIG_TOL and rel_max(grad, d['grad_rand_' + key]) < GRAD_TOL
+    _, grad1 = run(d['oef_dbv'], None)
+    assert rel_max(grad1, d['grad_ones_' + key]) < GRAD_TOL
+    x = _voxels(600 + 3, 21)                                       # three CTAs, the last one ragged (count % 4 != 0)
+    g = np.random.default_rng(21).standard_normal((603, 11)).astype(np.float32)
+    sig, grad = run(x, g)
+    s64, g64 = o.forward_backward(ph, x, g, False, blood, np.float64)
+    assert rel_elem(sig, s64) < SIG_TOL and rel_max(grad, g64) < GRAD_TOL
+    assert np.array_equal(run(x, None, bwd=False)[0], sig)
+
+
 def test_24_tau_grid_on_the_multi_group_path(emu, qb):
     """16 distinct |tau| columns (the 24-tau protocol): column groups beyond the first are read from the parameter block."""
     cfg = dict(_cfg(), tau_start='-0.028', tau_end='0.065', tau_step='0.004')
