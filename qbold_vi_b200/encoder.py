@@ -319,7 +319,7 @@ class _Block(nn.Module):
 # transposed.  One autograd node per block runs: the shared pointwise Dense (+ReLU, cuBLASLt epilogue), conv + bias +
 # ReLU fused in cuDNN, the second conv WITHOUT its bias (its bias is folded into the gate Dense and the mix kernel:
 # cuDNN would add it in a separate 86 us pass), the gate Dense and the mix kernel; the backward uses the fused
-# streaming kernels of csrc/encoder_block.cu (ReLU' + bias gradient in one pass, ReLU' of the skip branch inside the
+# streaming kernels of csrc/encoder_block_kernels.cuh (ReLU' + bias gradient in one pass, ReLU' of the skip branch inside the
 # mix backward), in-place accumulating GEMMs (beta = 1) instead of separate gradient additions, and qbold_dense_wgrad.
 _FAST_BLOCK = os.environ.get('QBOLD_FAST_BLOCK', '1') == '1'
 

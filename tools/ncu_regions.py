@@ -1,3 +1,10 @@
+"""Executed instructions / stall samples of one kernel of an .ncu-rep, grouped into source regions.
+
+    python tools/ncu_regions.py <report.ncu-rep> <kernel substring> <voxels per launch>
+
+The line ranges below describe the source as it stood when profiles/r02m_* were captured (commit a9463eb: the ELBO
+kernels were still inside elbo.cu).  Since then the kernel bodies moved to *_kernels.cuh; re-derive the ranges before
+using this on a new capture."""
 import csv, io, subprocess, sys, collections
 rep=sys.argv[1]; sub=sys.argv[2]; nvox=float(sys.argv[3])
 out = subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass'],capture_output=True,text=True).stdout
