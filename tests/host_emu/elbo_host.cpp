@@ -11,7 +11,7 @@ unsigned long long g_work;
 
 // k_elbo_pair<HAS_PRIOR> (the production kernel for n_tau <= 16, full model) or, pair == 0, k_elbo<HAS_PRIOR, PATH>.
 // seed_dev non-NULL: the Philox key is read from memory (qbold_elbo_fused_graph); inv_mask_sum_dev likewise.
-extern "C" int qb_emu_elbo(const QboldParams* P, const float* q, const float* sigma, const float* y, const float* mask,
+QB_EMU_API int qb_emu_elbo(const QboldParams* P, const float* q, const float* sigma, const float* y, const float* mask,
                            const float* prior, const float* eps, const float* eps_kl, uint64_t seed,
                            const uint64_t* seed_dev, uint64_t offset, int kl_samples, float inv_mask_sum,
                            const float* inv_mask_sum_dev, float kl_weight, int64_t n, float* grad_q, float* grad_sigma,
@@ -37,24 +37,24 @@ extern "C" int qb_emu_elbo(const QboldParams* P, const float* q, const float* si
     return -1;
 }
 
-extern "C" void qb_emu_kl(const float* q, const float* prior, const float* mask, const float* eps_kl, uint64_t seed,
+QB_EMU_API void qb_emu_kl(const float* q, const float* prior, const float* mask, const float* eps_kl, uint64_t seed,
                           uint64_t offset, int n_samples, int64_t n, float* kl_map, float* grad_q, int grid) {
     qb_emu::launch(grid, qb::kThreads, [&]() { qb::k_kl(q, prior, mask, eps_kl, seed, offset, n_samples, n, kl_map, grad_q); });
 }
 
-extern "C" void qb_emu_reparam(const float* q, const float* eps, uint64_t seed, uint64_t offset, int64_t n, float* out) {
+QB_EMU_API void qb_emu_reparam(const float* q, const float* eps, uint64_t seed, uint64_t offset, int64_t n, float* out) {
     const int grid = (int)((n + qb::kThreads - 1) / qb::kThreads);
     qb_emu::launch(grid, qb::kThreads, [&]() { qb::k_reparam(q, eps, seed, offset, n, out); });
 }
 
-extern "C" void qb_emu_posterior_stats(float dw_k, const float* q, const float* eps, uint64_t seed, uint64_t offset,
+QB_EMU_API void qb_emu_posterior_stats(float dw_k, const float* q, const float* eps, uint64_t seed, uint64_t offset,
                                        int n_samples, int64_t n, float* mean3, float* var3, int grid) {
     qb_emu::launch(grid, qb::kThreads,
                    [&]() { qb::k_posterior_stats(dw_k, q, eps, seed, offset, n_samples, n, mean3, var3); });
 }
 
 // likelihood map of save_predictions (model.py:808-817): pair != 0 -> k_nll_map_pair, else k_nll_map<path>
-extern "C" int qb_emu_nll_map(const QboldParams* P, const float* q, const float* sigma, const float* y, const float* mask,
+QB_EMU_API int qb_emu_nll_map(const QboldParams* P, const float* q, const float* sigma, const float* y, const float* mask,
                               const float* eps, uint64_t seed, uint64_t offset, int n_samples, int64_t n, float* nll_map,
                               int pair, int path, int grid) {
     g_work = 0;
@@ -79,7 +79,7 @@ extern "C" int qb_emu_nll_map(const QboldParams* P, const float* q, const float*
 
 // fine_tune_loss_fn alone on predictions that already exist (model.py:527-568): W = 16 (two voxels per warp) for
 // n_tau <= 16, else 32 -- as qbold_nll picks it
-extern "C" void qb_emu_nll(const QboldParams* P, const float* y, const float* pred, const float* sigma, const float* mask,
+QB_EMU_API void qb_emu_nll(const QboldParams* P, const float* y, const float* pred, const float* sigma, const float* mask,
                            int64_t n, float* nll_map, float* d_pred, float* d_sigma, int grid) {
     const QboldParams params = *P;
     if (params.n_tau <= 16)

@@ -9,7 +9,7 @@
 
 using namespace qb;
 
-extern "C" void qb_emu_block_mix_forward(const float* skip, const float* r0, const float* r_bias, const float* z, float offset,
+QB_EMU_API void qb_emu_block_mix_forward(const float* skip, const float* r0, const float* r_bias, const float* z, float offset,
                                          int64_t n, int channels, float* out, float* out_relu, int grid) {
     const int64_t total4 = n * (channels / 4);
     qb_emu::launch(grid, kThreads, [&]() {
@@ -19,7 +19,7 @@ extern "C" void qb_emu_block_mix_forward(const float* skip, const float* r0, con
     });
 }
 
-extern "C" void qb_emu_block_mix_backward(const float* go, const float* skip, const float* r0, const float* r_bias,
+QB_EMU_API void qb_emu_block_mix_backward(const float* go, const float* skip, const float* r0, const float* r_bias,
                                           const float* z, float offset, int64_t n, int channels, int skip_is_relu,
                                           const float* skip_addend, float* d_skip, float* d_r, float* d_z, int grid) {
     const int64_t total4 = n * (channels / 4);
@@ -33,7 +33,7 @@ extern "C" void qb_emu_block_mix_backward(const float* go, const float* skip, co
 }
 
 // out = g * [y > 0] (+ addend) and colsum (+)= its column sums: two-stage fixed-order reduction (qbold_relu_bwd_colsum)
-extern "C" void qb_emu_relu_bwd_colsum(const float* g, const float* y, const float* addend, int64_t n, int channels,
+QB_EMU_API void qb_emu_relu_bwd_colsum(const float* g, const float* y, const float* addend, int64_t n, int channels,
                                        float* out, float* colsum, int accumulate, int grid) {
     const int c4 = channels / 4;
     std::vector<float> ws((size_t)grid * 4 * kMaxC4 + 4, 0.f);
@@ -51,7 +51,7 @@ extern "C" void qb_emu_relu_bwd_colsum(const float* g, const float* y, const flo
     if (colsum) qb_emu::launch(1, 1024, [&]() { k_colsum_finish(workspace, grid, channels, colsum, accumulate); });
 }
 
-extern "C" void qb_emu_normalise_zouter(const float* data, int64_t b, int nx, int ny, int nz, int n_tau, int se_idx, int multi,
+QB_EMU_API void qb_emu_normalise_zouter(const float* data, int64_t b, int nx, int ny, int nz, int n_tau, int se_idx, int multi,
                                         float* out) {
     const int64_t blocks = b * nx * ((ny + 31) / 32) * ((nz + 31) / 32);
     const int tp = (n_tau + 3) & ~3;

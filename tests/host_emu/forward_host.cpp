@@ -14,7 +14,7 @@ unsigned long long g_work;
 }
 
 // k_forward_pair<BWD> (the headline kernel): grid x block threads, block a multiple of 32.
-extern "C" void qb_emu_forward_pair(const QboldParams* P, const float* oef_dbv, const float* g_signal, float* signal,
+QB_EMU_API void qb_emu_forward_pair(const QboldParams* P, const float* oef_dbv, const float* g_signal, float* signal,
                                     float* g_oef_dbv, int64_t n, int bwd, int grid, int block) {
     g_work = 0;
     const QboldParams params = *P;
@@ -26,7 +26,7 @@ extern "C" void qb_emu_forward_pair(const QboldParams* P, const float* oef_dbv, 
 
 // k_forward<BWD, HCT, PATH>: one warp per voxel; path 0 = static lane schedule, 1 = column groups (<= 8 columns),
 // 2 = column groups (> 8 columns, the 24-tau grid)
-extern "C" int qb_emu_forward(const QboldParams* P, const float* oef_dbv, const float* g_signal, float* signal,
+QB_EMU_API int qb_emu_forward(const QboldParams* P, const float* oef_dbv, const float* g_signal, float* signal,
                               float* g_oef_dbv, int64_t n, int bwd, int hct, int path, int grid, int block) {
     g_work = 0;
     const QboldParams params = *P;
@@ -43,7 +43,7 @@ extern "C" int qb_emu_forward(const QboldParams* P, const float* oef_dbv, const 
 }
 
 // k_misalign<HCT, kSched>: overwrites the late images of the selected voxels in `signal` (recorded draws or Philox)
-extern "C" void qb_emu_misalign(const QboldParams* P, const float* oef_dbv, int64_t n, float prob, const float* sel_u01,
+QB_EMU_API void qb_emu_misalign(const QboldParams* P, const float* oef_dbv, int64_t n, float prob, const float* sel_u01,
                                 const int32_t* from_index, const float* eps, uint64_t seed, uint64_t offset, float* signal,
                                 int hct, int grid, int block) {
     g_work = 0;
@@ -60,7 +60,7 @@ extern "C" void qb_emu_misalign(const QboldParams* P, const float* oef_dbv, int6
 
 // k_loglinear<BWD> (full_model = False, signals.py:194-207): one CTA of 256 rows per block, [256 x n_tau] tile in
 // dynamic shared memory -- launch arithmetic of launch_loglinear (forward.cu)
-extern "C" void qb_emu_loglinear(const QboldParams* P, const float* oef_dbv, const float* g_signal, float* signal,
+QB_EMU_API void qb_emu_loglinear(const QboldParams* P, const float* oef_dbv, const float* g_signal, float* signal,
                                  float* g_oef_dbv, int64_t n, int bwd) {
     const QboldParams params = *P;
     const size_t smem = sizeof(float) * qb::kThreads * params.n_tau;

@@ -12,7 +12,7 @@ unsigned long long g_work;
 }
 
 // pair != 0: k_generate_pair (n_tau <= 16, full model, scheduled path); else k_generate<path>
-extern "C" int qb_emu_generate(const QboldParams* P, const float* oefs, int64_t n_oef, const float* dbvs, int64_t n_dbv,
+QB_EMU_API int qb_emu_generate(const QboldParams* P, const float* oefs, int64_t n_oef, const float* dbvs, int64_t n_dbv,
                                const int64_t* perm, uint64_t seed, int64_t first, int64_t count, float* x, float* y3,
                                int pair, int path, int grid) {
     g_work = 0;
@@ -41,7 +41,7 @@ extern "C" int qb_emu_generate(const QboldParams* P, const float* oefs, int64_t 
 }
 
 // noise of create_synthetic_dataset's chunk loop (signals.py:116-128, 282-285): per-chunk column sums, then the noise pass
-extern "C" void qb_emu_add_noise_chunked(const QboldParams* P, float* signal, int64_t chunk_rows, int n_chunks,
+QB_EMU_API void qb_emu_add_noise_chunked(const QboldParams* P, float* signal, int64_t chunk_rows, int n_chunks,
                                          const float* snr_u01, const float* eps, uint64_t seed, uint64_t offset, int gx) {
     const QboldParams params = *P;
     const int64_t n = chunk_rows * n_chunks;

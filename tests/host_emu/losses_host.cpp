@@ -7,14 +7,14 @@
 
 #include "losses_kernels.cuh"
 
-extern "C" void qb_emu_smoothness(const float* q, int n_ch, const float* mask, int64_t n_vol, int X, int Y, int Z,
+QB_EMU_API void qb_emu_smoothness(const float* q, int n_ch, const float* mask, int64_t n_vol, int X, int Y, int Z,
                                   float scale, const float* scale_dev, double* tv_sum, float* grad_q, int grid) {
     const int64_t n = n_vol * X * Y * Z;
     qb_emu::launch(grid, qb::kThreads,
                    [&]() { qb::k_smoothness(q, n_ch, mask, n, X, Y, Z, scale, scale_dev, tv_sum, grad_q); });
 }
 
-extern "C" void qb_emu_synth_nll(const float* labels, int label_stride, const float* pred, int pred_stride, int use_mvg,
+QB_EMU_API void qb_emu_synth_nll(const float* labels, int label_stride, const float* pred, int pred_stride, int use_mvg,
                                  double ig_alpha, double ig_beta, const float* ig4, int64_t n, float grad_scale,
                                  float* nll_rows, float* grad_pred, double* loss_sum, double* ig_sums, int grid) {
     qb::SynthOpts opt{};
@@ -33,7 +33,7 @@ extern "C" void qb_emu_synth_nll(const float* labels, int label_stride, const fl
     });
 }
 
-extern "C" void qb_emu_diag_kl(const float* pred, int pred_stride, const float* prior, int prior_stride, const float* mask,
+QB_EMU_API void qb_emu_diag_kl(const float* pred, int pred_stride, const float* prior, int prior_stride, const float* mask,
                                int64_t n, float* kl_map, float* grad_pred, int gpred_stride, float* grad_prior,
                                int gprior_stride, int grid) {
     qb_emu::launch(grid, qb::kThreads, [&]() {
@@ -42,7 +42,7 @@ extern "C" void qb_emu_diag_kl(const float* pred, int pred_stride, const float* 
     });
 }
 
-extern "C" void qb_emu_mog_kl(const float* pred, int n_comp, const float* mask, const float* eps, uint64_t seed,
+QB_EMU_API void qb_emu_mog_kl(const float* pred, int n_comp, const float* mask, const float* eps, uint64_t seed,
                               uint64_t offset, int64_t n, float* kl_map, float* grad_pred, int grid) {
     qb_emu::launch(grid, qb::kThreads,
                    [&]() { qb::k_mog_kl(pred, n_comp, mask, eps, seed, offset, n, kl_map, grad_pred); });

@@ -17,6 +17,12 @@
 #error "the cuda_runtime.h shim is for -DQB_HOST_EMU builds only"
 #endif
 
+// Entry points of a harness library.  Everything else is built with hidden visibility and without GNU unique symbols
+// (-fvisibility=hidden -fno-gnu-unique): several harness libraries live in one test process, and each must keep its OWN
+// emulator state, kernel statics (__shared__ objects) and shared-window anchor -- a process-wide unified inline variable
+// would put the anchor of one library gigabytes away from the statics of another.
+#define QB_EMU_API extern "C" __attribute__((visibility("default")))
+
 #define __global__
 #define __device__
 #define __host__

@@ -32,7 +32,8 @@ def emu(tmp_path_factory):
     if not gxx:
         pytest.skip('g++ not available')
     out = str(tmp_path_factory.mktemp('emu') / 'libforward_emu.so')
-    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-fvisibility=hidden', '-fno-gnu-unique', '-I',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
                     '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
                     os.path.join(ROOT, 'tests', 'host_emu', 'forward_host.cpp'), '-o', out], check=True, capture_output=True,
                    timeout=600)
@@ -215,7 +216,8 @@ def emu_elbo(tmp_path_factory):
     if not gxx:
         pytest.skip('g++ not available')
     out = str(tmp_path_factory.mktemp('emu_elbo') / 'libelbo_emu.so')
-    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-fvisibility=hidden', '-fno-gnu-unique', '-I',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
                     '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
                     os.path.join(ROOT, 'tests', 'host_emu', 'elbo_host.cpp'), '-o', out], check=True, capture_output=True,
                    timeout=900)
@@ -360,7 +362,8 @@ def emu_gen(tmp_path_factory):
     if not gxx:
         pytest.skip('g++ not available')
     out = str(tmp_path_factory.mktemp('emu_gen') / 'libgen_emu.so')
-    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-fvisibility=hidden', '-fno-gnu-unique', '-I',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
                     '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
                     os.path.join(ROOT, 'tests', 'host_emu', 'generate_host.cpp'), '-o', out], check=True, capture_output=True,
                    timeout=900)
@@ -438,7 +441,8 @@ def emu_losses(tmp_path_factory):
     if not gxx:
         pytest.skip('g++ not available')
     out = str(tmp_path_factory.mktemp('emu_losses') / 'liblosses_emu.so')
-    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-fvisibility=hidden', '-fno-gnu-unique', '-I',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
                     '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
                     os.path.join(ROOT, 'tests', 'host_emu', 'losses_host.cpp'), '-o', out], check=True, capture_output=True,
                    timeout=900)
@@ -554,7 +558,8 @@ def emu_enc(tmp_path_factory):
     if not gxx:
         pytest.skip('g++ not available')
     out = str(tmp_path_factory.mktemp('emu_enc') / 'libenc_emu.so')
-    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
+    subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-fvisibility=hidden', '-fno-gnu-unique', '-I',
+                    os.path.join(ROOT, 'tests', 'host_emu', 'shim'),
                     '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'), '-shared', '-fPIC',
                     os.path.join(ROOT, 'tests', 'host_emu', 'encoder_block_host.cpp'), '-o', out], check=True,
                    capture_output=True, timeout=900)
