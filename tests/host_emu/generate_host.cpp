@@ -53,3 +53,17 @@ QB_EMU_API void qb_emu_add_noise_chunked(const QboldParams* P, float* signal, in
         qb::k_add_noise_chunked(params, signal, n, chunk_rows, sums, snr_u01, eps, seed, offset);
     });
 }
+
+// noise of one SignalGenerationLayer.call (signals.py:116-128): column means of the whole batch (qbold_column_mean:
+// Kahan partial sums per warp, double totals), then one noise pass (qbold_add_noise).  mean_out receives the means.
+QB_EMU_API void qb_emu_add_noise(const QboldParams* P, float* signal, int64_t n, const float* snr_u01, const float* eps,
+                                 uint64_t seed, uint64_t offset, float* mean_out, int grid) {
+    const QboldParams params = *P;
+    const int nt = params.n_tau;
+    std::vector<double> scratch(32, 0.0);
+    double* sums = scratch.data();
+    qb_emu::launch(grid, qb::kThreads, [&]() { qb::k_column_sum(signal, n, nt, sums); });
+    qb_emu::launch(1, 32, [&]() { qb::k_finish_mean(sums, n, nt, mean_out); });
+    qb_emu::launch((int)((n + qb::kThreads - 1) / qb::kThreads), qb::kThreads,
+                   [&]() { qb::k_add_noise(params, signal, n, mean_out, snr_u01, eps, seed, offset); });
+}

@@ -610,3 +610,30 @@ def test_encoder_block_streaming_kernels(emu_enc):
         ref = d[..., se - 1:se + 2].mean(-1, keepdims=True) if multi else d[..., se:se + 1]
         want = np.log(d / ref).transpose(0, 3, 1, 2, 4)
         assert rel_max(got[..., :T], want) < 1e-5 and np.all(got[..., T:] == 0)
+
+
+def test_noise_model_of_one_layer_call(emu_gen, qb):
+    """k_column_sum + k_finish_mean + k_add_noise (signals.py:116-128: the noise std is the batch mean of each image
+    over the SNR): explicit draws against the oracle, and the Philox streams against oracle/philox.py's draws."""
+    cfg = o.default_config()
+    ph = o.parse_params(cfg)
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    r = np.random.default_rng(6)
+    n = 1500
+    clean = o.forward(ph, _voxels(n, 6), dtype=np.float64).astype(np.float32)
+    u = r.uniform(size=n).astype(np.float32)
+    eps = r.standard_normal((n, 11)).astype(np.float32)
+    sig, mean = clean.copy(), np.full(11, np.nan, np.float32)
+    emu_gen.qb_emu_add_noise(C.byref(layer.params), _p(sig), C.c_int64(n), _p(u), _p(eps), C.c_uint64(0), C.c_uint64(0),
+                             _p(mean), 3)
+    assert rel_max(mean, clean.astype(np.float64).mean(0)) < 1e-6
+    want = o.add_noise(clean, u * np.float32(70) + np.float32(50), eps, np.float64)
+    assert rel_elem(sig, want) < SIG_TOL
+    seed, off = 0xABCDEF0123, 7_000_000_000
+    sig2 = clean.copy()
+    emu_gen.qb_emu_add_noise(C.byref(layer.params), _p(sig2), C.c_int64(n), None, None, C.c_uint64(seed), C.c_uint64(off),
+                             _p(mean), 2)
+    idx = np.arange(n, dtype=np.uint64) + np.uint64(off)
+    want2 = o.add_noise(clean, philox.snr_u01(seed, idx) * np.float32(70) + np.float32(50), philox.noise_eps(seed, idx, 11),
+                        np.float64)
+    assert rel_elem(sig2, want2) < SIG_TOL
