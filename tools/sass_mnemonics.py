@@ -36,7 +36,13 @@ def main():
             name = re.sub(r'\(.*', '', name).replace('void ', '')
             rows.append((name, sum(c.values()), [c.get(k, 0) for k in KEYS]))
     rows.sort()
+    import hashlib
+    body = '\n'.join(ln for ln in sass.splitlines()
+                     if not ln.startswith(('Fatbin', '=')) and not any(k in ln for k in ('arch =', 'code version', 'host =',
+                                                                                         'compile_size', 'identifier')))
     print('# cuobjdump -sass %s (sm_100a): instruction counts per kernel' % os.path.relpath(lib, ROOT))
+    print('# md5 of the SASS text (headers stripped): %s -- compare two builds with it: refactors that must not touch the '
+          'device code leave it unchanged' % hashlib.md5((body + '\n').encode()).hexdigest())
     print('# tcgen05 = UTCHMMA (MMA) / UTCBAR (commit) / LDTM (tcgen05.ld); TMA = UTMALDG / UTMASTG; mbarrier = SYNCS; '
           'packed FP32 = FFMA2 / FMUL2 / FADD2')
     print('%-58s %7s ' % ('kernel', 'total') + ' '.join('%8s' % k for k in KEYS))
