@@ -467,6 +467,33 @@ def test_ctypes_signatures_match_the_header_prototypes(qb):
         assert (None if res is None else ckind(res)) == want_ret, name
 
 
+def test_every_entry_point_rejects_garbage_before_touching_the_device(qb):
+    """NULL pointers, negative sizes and zero scalars into every int-returning entry point: a negative QBOLD_E* code and
+    a message that names the function -- decided on the host, so it holds (and is tested) without a GPU.  The launch
+    counter does not move."""
+    lib = qb._lib.lib()
+    sizes = {'qbold_abi_version', 'qbold_params_sizeof', 'qbold_encoder_mlp_blob_floats', 'qbold_dense_tc_packed_floats'}
+    before = qb.launch_count()
+    checked = 0
+    for name, (restype, argtypes) in qb._lib._SIGNATURES.items():
+        if restype is not C.c_int or name in sizes:
+            continue
+        args = []
+        for a in argtypes:
+            if a in (C.c_void_p, C.c_char_p) or (hasattr(a, '_type_') and not isinstance(a._type_, str)):
+                args.append(None)
+            elif a in (C.c_float, C.c_double):
+                args.append(0.0)
+            else:
+                args.append(-1)
+        rc = getattr(lib, name)(*args)
+        msg = lib.qbold_last_error().decode()
+        assert rc in (-1, -3), (name, rc, msg)                                   # QBOLD_EINVAL / QBOLD_EUNSUPPORTED
+        assert msg.startswith(name) or (name.endswith('_add') and msg.startswith(name[:-4])), (name, msg)
+        checked += 1
+    assert checked >= 40 and qb.launch_count() == before
+
+
 def test_header_is_plain_c_and_the_c_demo_links(qb, tmp_path):
     """The boundary is a C ABI: include/qbold.h must parse as strict C99 and as C++, and examples/c_abi_demo.c must
     compile with a C compiler and link against libqbold.so (it is RUN by the GPU suite: test_c_abi_from_plain_c)."""
