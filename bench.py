@@ -497,7 +497,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--train-steps', type=int, default=10)
-    ap.add_argument('--graph-deadline', type=int, default=90,
+    ap.add_argument('--graph-deadline', type=int, default=60,
                     help='seconds the captured-training-step trial may take before the line is printed without it')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
