@@ -663,3 +663,29 @@ def test_wide_posteriors_take_the_literal_fallback_of_the_kl(emu_elbo, qb):
     floor = max(rel_max(ref32['kl_map'], ref64['kl_map']), rel_max(ref32['grad_q'], ref64['grad_q']))
     assert floor > 1e-4                                     # the float32 reference itself misses the 1e-4 bar here ...
     assert rel_max(got['kl_map'], ref64['kl_map']) < 1.5 * floor and rel_max(got['grad_q'], ref64['grad_q']) < 1.5 * floor
+
+
+def test_forward_kernel_at_and_beyond_the_edges_of_the_domain(emu, qb):
+    """OEF = 0 (dw = 0: every Bessel argument 0), DBV = 0, the corners of the sampling box, OEF / DBV up to 1 and a negative
+    DBV: value and gradient against the float64 oracle.  OEF = 2 (OEF x Hct > 0.40, not reachable with Hct 0.34): node 0
+    of the float32 reference stops being exactly dead (domain note) -- the kernel follows the
+    reference's float32 arithmetic there, not float64."""
+    layer = qb.SignalGenerationLayer(_cfg(), True, True)
+    ph = o.parse_params(_cfg())
+    x = np.array([[0.0, 0.05], [1e-8, 0.05], [1e-4, 0.05], [0.84, 0.0], [0.04, 0.001], [0.84, 0.201], [1.0, 0.3], [0.5, 1.0],
+                  [0.4, -0.05]], np.float32)
+    g = np.random.default_rng(2).standard_normal((x.shape[0], 11)).astype(np.float32)
+    sig, grad = _pair(emu, layer, x, g, grid=1, block=32)
+    s64, g64 = o.forward_backward(ph, x, g, dtype=np.float64)
+    assert np.isfinite(sig).all() and np.isfinite(grad).all()
+    assert rel_elem(sig, s64) < 2e-6
+    for i in range(x.shape[0]):
+        assert rel_max(grad[i], g64[i]) < 2e-6, x[i]
+    beyond = np.array([[2.0, 0.05], [1.5, 0.1]], np.float32)
+    gb = np.ones((2, 11), np.float32)
+    sig, grad = _pair(emu, layer, beyond, gb, grid=1, block=32)
+    with np.errstate(all='ignore'):
+        s32, g32 = o.forward_backward(ph, beyond, gb, dtype=np.float32)
+        s64, _ = o.forward_backward(ph, beyond, gb, dtype=np.float64)
+    assert rel_elem(sig, s32) < 2e-6 and rel_max(grad, g32) < 2e-6
+    assert rel_elem(sig, s64) > 1e-3                        # ... where float64 is no longer the reference's oracle
