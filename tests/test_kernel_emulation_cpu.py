@@ -689,3 +689,26 @@ def test_forward_kernel_at_and_beyond_the_edges_of_the_domain(emu, qb):
         s64, _ = o.forward_backward(ph, beyond, gb, dtype=np.float64)
     assert rel_elem(sig, s32) < 2e-6 and rel_max(grad, g32) < 2e-6
     assert rel_elem(sig, s64) > 1e-3                        # ... where float64 is no longer the reference's oracle
+
+
+@pytest.mark.parametrize('n', [1, 3, 33, 65])
+def test_fused_elbo_ragged_batches(emu_elbo, qb, n):
+    """A warp of k_elbo_pair takes units of 32 voxels, a lane pair two: batches that end inside a unit / inside a pair,
+    with a masked voxel in the middle, against the float64 oracle (production and generic kernel)."""
+    ph = o.parse_params(_cfg())
+    layer = qb.SignalGenerationLayer(_cfg(), True, True)
+    params = _trainer(qb)._params_for(layer)
+    q, prior, sigma, data, mask = _elbo_batch(ph, n, 100 + n)
+    mask[:] = 1
+    if n > 2:
+        mask[n // 2] = 0
+    data = data * mask[:, None]
+    r = np.random.default_rng(n)
+    eps, eps_kl = r.standard_normal((n, 2)).astype(np.float32), r.standard_normal((n, 70, 2)).astype(np.float32)
+    ref = o.elbo_and_grads(ph, q, sigma, data, mask, prior, eps, eps_kl, np.float64)
+    for pair in (1, 0):
+        got = _elbo(emu_elbo, params, q, sigma, data, mask, prior, eps, eps_kl, pair=pair, grid=1)
+        assert rel_elem(got['nll'], ref['nll']) < GRAD_TOL and rel_elem(got['kl'], ref['kl']) < GRAD_TOL
+        assert rel_max(got['grad_q'], ref['grad_q']) < GRAD_TOL and rel_max(got['grad_sigma'], ref['grad_sigma']) < GRAD_TOL
+        assert not np.isnan(got['nll_map']).any() and not np.isnan(got['kl_map']).any()       # every voxel was written
+        assert got['mask_sum'] == mask.sum()
