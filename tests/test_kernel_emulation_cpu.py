@@ -712,3 +712,17 @@ def test_fused_elbo_ragged_batches(emu_elbo, qb, n):
         assert rel_max(got['grad_q'], ref['grad_q']) < GRAD_TOL and rel_max(got['grad_sigma'], ref['grad_sigma']) < GRAD_TOL
         assert not np.isnan(got['nll_map']).any() and not np.isnan(got['kl_map']).any()       # every voxel was written
         assert got['mask_sum'] == mask.sum()
+
+
+def test_non_finite_inputs_stay_inside_their_voxel(emu, qb):
+    """Two voxels share a warp in k_forward_pair (ballots over both halves pick the Bessel range): a NaN / Inf voxel must
+    not change a single bit of its partner or of any other voxel (the reference relies on TerminateOnNaN)."""
+    layer = qb.SignalGenerationLayer(_cfg(), True, True)
+    x, g = _voxels(64, 5), np.ones((64, 11), np.float32)
+    ref_s, ref_g = _pair(emu, layer, x, g, grid=1, block=32)
+    xb = x.copy()
+    xb[10], xb[21], xb[33] = [np.nan, 0.05], [0.4, np.inf], [np.inf, 0.05]
+    s, gr = _pair(emu, layer, xb, g, grid=1, block=32)
+    ok = [i for i in range(64) if i not in (10, 21, 33)]
+    assert np.array_equal(s[ok], ref_s[ok]) and np.array_equal(gr[ok], ref_g[ok])
+    assert np.isnan(s[10]).all() and np.isnan(s[21]).all() and np.isnan(gr[[10, 21, 33]]).all()
