@@ -726,3 +726,32 @@ def test_non_finite_inputs_stay_inside_their_voxel(emu, qb):
     ok = [i for i in range(64) if i not in (10, 21, 33)]
     assert np.array_equal(s[ok], ref_s[ok]) and np.array_equal(gr[ok], ref_g[ok])
     assert np.isnan(s[10]).all() and np.isnan(s[21]).all() and np.isnan(gr[[10, 21, 33]]).all()
+
+
+@pytest.mark.parametrize('multi', [False, True])
+def test_fused_elbo_on_the_24_tau_grid(emu_elbo, qb, multi):
+    """24 images, 16 distinct |tau| columns, spin echo at index 7: the generic k_elbo on the multi-group path (a lane per
+    image, n_tau > 16) against the float64 oracle, single- and multi-image normalisation."""
+    cfg = dict(_cfg(), tau_start='-0.028', tau_end='0.065', tau_step='0.004')
+    ph = o.parse_params(cfg)
+    layer = qb.SignalGenerationLayer(cfg, True, True)
+    tr = qb.EncoderTrainer(cfg, student_t_df=200, multi_image_normalisation=multi, use_mvg=True, use_population_prior=False,
+                           predict_log_data=False, seed=1)
+    assert layer.n_tau == 24 and tr._se_idx == 7 and layer.params.n_cols == 16
+    n, S = 48, 70
+    r = np.random.default_rng(4)
+    q = np.stack([r.normal(-0.3, 0.7, n), r.normal(0, 0.6, n), r.normal(-1.2, 0.7, n), r.normal(0, 0.6, n),
+                  r.normal(0, 0.8, n)], -1).astype(np.float32)
+    prior = (q + r.normal(0, 0.3, (n, 5))).astype(np.float32)
+    sigma = np.exp(r.normal(np.log(0.05), 0.2, (n, 24))).astype(np.float32)
+    truth = np.stack([r.uniform(0.1, 0.7, n), r.uniform(0.005, 0.15, n)], -1)
+    data = (o.forward(ph, truth, dtype=np.float64) * 100 * (1 + 0.02 * r.standard_normal((n, 24)))).astype(np.float32)
+    mask = (r.uniform(size=n) > 0.3).astype(np.float32)
+    data *= mask[:, None]
+    eps, eps_kl = r.standard_normal((n, 2)).astype(np.float32), r.standard_normal((n, S, 2)).astype(np.float32)
+    ref = o.elbo_and_grads(ph, q, sigma, data, mask, prior, eps, eps_kl, np.float64, se_idx=7, multi_image_normalisation=multi)
+    path = 0 if layer.params.sched_phases > 0 else 2
+    got = _elbo(emu_elbo, tr._params_for(layer), q, sigma, data, mask, prior, eps, eps_kl, kl_samples=S, pair=0, path=path,
+                grid=1)
+    assert rel_elem(got['nll'], ref['nll']) < GRAD_TOL and rel_elem(got['kl'], ref['kl']) < GRAD_TOL
+    assert rel_max(got['grad_q'], ref['grad_q']) < GRAD_TOL and rel_max(got['grad_sigma'], ref['grad_sigma']) < GRAD_TOL
