@@ -196,6 +196,105 @@ def test_checkpoints_move_between_the_eager_and_the_captured_trainer(tmp_path):
     assert float((w_a - w_c).abs().max()) < 1e-5
 
 
+class _SkipBody(Exception):
+    pass
+
+
+def _fake_cuda_graphs(monkeypatch, bodies):
+    """torch.cuda.CUDAGraph / torch.cuda.graph stand-ins with the one property of a capture that matters to the host
+    logic: the body of ``with torch.cuda.graph(g):`` is NOT executed (a trace function raises at its first line and
+    __exit__ swallows it); ``g.replay()`` executes the body registered for the i-th graph created."""
+    import sys
+    created = []
+
+    class FakeGraph:
+        def __init__(self):
+            self.index = len(created)
+            created.append(self)
+
+        def pool(self):
+            return ('pool', self.index)
+
+        def replay(self):
+            bodies[self.index % len(bodies)]()
+
+    class fake_graph:
+        def __init__(self, graph, pool=None, **kw):
+            self.graph, self.pool = graph, pool
+
+        def __enter__(self):
+            def tracer(frame, event, arg):
+                raise _SkipBody()
+            self._old = sys.gettrace()
+            sys.settrace(lambda *a: None)                       # enable tracing, then trap the caller's next line
+            sys._getframe(1).f_trace = tracer
+            return self
+
+        def __exit__(self, exc_type, exc, tb):
+            sys.settrace(self._old)
+            return exc_type is _SkipBody
+
+    monkeypatch.setattr(torch.cuda, 'CUDAGraph', FakeGraph)
+    monkeypatch.setattr(torch.cuda, 'graph', fake_graph)
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+    return created
+
+
+@pytest.mark.parametrize('mode', [True, 'split'])
+def test_capture_and_replay_control_flow_with_stand_in_graphs(monkeypatch, tmp_path, mode):
+    """The capture / replay branches of DataParallelTrainer on CPU, with graph objects that behave like a capture on the
+    host side (body skipped at capture, executed at replay): three eager warm-up steps, the capture call, replays, a new
+    batch through the static buffers, a new batch SHAPE (new buffers, new capture), a checkpoint round trip (capture
+    again) -- every step against the eager trainer."""
+    data, mask, prior = _batch()
+    enc_e, dp_e = _make()
+    enc_g, dp_g = _make(cuda_graph=mode, graph_warmup=None)
+    dp_g._g['warmup'] = 3                                       # capture after three eager steps, as on a GPU
+
+    def front_full():
+        dp_g._g['stats'] = dp_g._graph_body()
+
+    def front_split():
+        dp_g._g['stats'] = dp_g._split_front()
+
+    bodies = [front_full] if mode is True else [front_split, dp_g._split_back]
+    created = _fake_cuda_graphs(monkeypatch, bodies)
+
+    def both(d, m, p, what):
+        a, b = dp_e.step(d, m, p), dp_g.step(d, m, p)
+        for k in ('loss', 'nll', 'smoothness', 'mask_sum'):
+            assert abs(a[k] - b[k]) <= 1e-5 * max(abs(a[k]), 1e-6), (what, k, a[k], b[k])
+        assert abs(a['lr'] - b['lr']) < 1e-15 and dp_g.step_no == dp_e.step_no
+
+    for i in range(3):
+        both(data, mask, prior, 'warm-up %d' % i)
+    assert dp_g._g['graph'] is None and not created
+    both(data, mask, prior, 'capture + first replay')
+    assert dp_g._g['graph'] is not None and len(created) == (1 if mode is True else 2)
+    if mode == 'split':
+        assert dp_g._g['graph_back'] is created[1]
+    for i in range(2):
+        both(data, mask, prior, 'replay %d' % i)
+    both(data * 1.02, mask, prior, 'new batch, same shape')
+    assert len(created) == (1 if mode is True else 2)           # no new capture
+    sd, sm, sp = dp_g.static_inputs()
+    assert sd.data_ptr() != data.data_ptr() and torch.equal(sd, data * 1.02) and torch.equal(sm, mask)
+    half = slice(0, 2)
+    for i in range(5):                                          # new shape: three eager steps, capture, replay
+        both(data[half].contiguous(), mask[half].contiguous(), prior[half].contiguous(), 'new shape %d' % i)
+    assert len(created) == (2 if mode is True else 4)
+    path = str(tmp_path / 'g.pt')
+    dp_g.save(path)
+    dp_g.load(path)
+    assert dp_g._g['graph'] is None                             # moments are new tensors: capture again
+    for i in range(5):
+        both(data[half].contiguous(), mask[half].contiguous(), prior[half].contiguous(), 'after load %d' % i)
+    assert len(created) == (3 if mode is True else 6)
+    w_e = torch.cat([p.detach().reshape(-1) for p in enc_e.parameters()])
+    w_g = torch.cat([p.detach().reshape(-1) for p in enc_g.parameters()])
+    assert float((w_e - w_g).abs().max()) < 1e-5
+
+
 def test_uint64_key_as_int64_bit_pattern():
     from qbold_vi_b200.distributed import _GOLDEN, _as_i64
     for u in (0, 1, (1 << 63) - 1, 1 << 63, (1 << 64) - 1, _GOLDEN):
