@@ -58,3 +58,16 @@ QB_EMU_API void qb_emu_normalise_zouter(const float* data, int64_t b, int nx, in
     const size_t smem = (size_t)32 * (32 * n_tau + 1) * sizeof(float);
     qb_emu::launch((int)blocks, 256, [&]() { k_normalise_zouter(data, nx, ny, nz, n_tau, tp, se_idx, multi, out); }, 1, smem);
 }
+
+// ---- skinny Dense layers of the heads (encoder_small_kernels.cuh), launch arithmetic of qbold_dense_small_*
+#include "encoder_small_kernels.cuh"
+
+QB_EMU_API void qb_emu_dense_small_forward(const float* x, const float* w, const float* bias, int n_in, int n_out, int64_t n,
+                                           float* y, int grid) {
+    qb_emu::launch(grid, 128, [&]() { k_dense_small_fwd_coop(x, w, bias, n_in, n_out, n, y); });
+}
+
+QB_EMU_API void qb_emu_dense_small_dgrad(const float* g, const float* w, const float* relu_mask, int n_in, int n_out,
+                                         int64_t n, float* dx, int grid) {
+    qb_emu::launch(grid, 256, [&]() { k_dense_small_dgrad_coop(g, w, relu_mask, n_in, n_out, n, dx); });
+}

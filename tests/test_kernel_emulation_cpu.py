@@ -755,3 +755,25 @@ def test_fused_elbo_on_the_24_tau_grid(emu_elbo, qb, multi):
                 grid=1)
     assert rel_elem(got['nll'], ref['nll']) < GRAD_TOL and rel_elem(got['kl'], ref['kl']) < GRAD_TOL
     assert rel_max(got['grad_q'], ref['grad_q']) < GRAD_TOL and rel_max(got['grad_sigma'], ref['grad_sigma']) < GRAD_TOL
+
+
+def test_skinny_dense_kernels_of_the_heads(emu_enc):
+    """k_dense_small_fwd_coop / k_dense_small_dgrad_coop (the 60 -> 5 and 60 -> 11 heads, model.py:176-223): coalesced
+    row tiles through shared memory, shuffle-broadcast gradient rows, optional ReLU' mask on the result; ragged row
+    counts; against float64 matrix products."""
+    r = np.random.default_rng(14)
+    for n, n_in, n_out, grid in ((1, 60, 5, 1), (95, 60, 11, 2), (300, 12, 16, 3), (257, 64, 1, 2)):
+        x = r.standard_normal((n, n_in)).astype(np.float32)
+        w = (r.standard_normal((n_out, n_in)) * 0.3).astype(np.float32)
+        b = r.standard_normal(n_out).astype(np.float32)
+        y = np.full((n, n_out), np.nan, np.float32)
+        emu_enc.qb_emu_dense_small_forward(_p(x), _p(w), _p(b), n_in, n_out, C.c_int64(n), _p(y), grid)
+        assert rel_max(y, x.astype(np.float64) @ w.astype(np.float64).T + b) < 1e-6
+        g = r.standard_normal((n, n_out)).astype(np.float32)
+        dx = np.full((n, n_in), np.nan, np.float32)
+        emu_enc.qb_emu_dense_small_dgrad(_p(g), _p(w), None, n_in, n_out, C.c_int64(n), _p(dx), grid)
+        want = g.astype(np.float64) @ w.astype(np.float64)
+        assert rel_max(dx, want) < 1e-6
+        act = r.standard_normal((n, n_in)).astype(np.float32)
+        emu_enc.qb_emu_dense_small_dgrad(_p(g), _p(w), _p(act), n_in, n_out, C.c_int64(n), _p(dx), grid)
+        assert rel_max(dx, want * (act > 0)) < 1e-6 and np.all(dx[act <= 0] == 0)
