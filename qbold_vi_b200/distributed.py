@@ -10,6 +10,7 @@
 from __future__ import annotations
 
 import os
+import time
 
 import torch
 
@@ -344,10 +345,18 @@ class DataParallelTrainer:
         g['msum'].copy_(global_mask_sum_device(g['mask']))               # eager collective 1 (an input of graph A)
         if g['graph'] is None and g['calls'] >= g['warmup']:
             torch.cuda.synchronize()
+            kw = {}
+            if world_size() > 1:
+                # Other threads of this process make CUDA calls of their own -- the NCCL watchdog polls the events of the
+                # collectives issued so far (cudaEventQuery, not allowed while a global-mode capture is under way).  Give
+                # it time to retire them (they are complete: the device is idle), and let the capture only police the
+                # capturing thread; the kernels the autograd thread adds to the stream are captured either way.
+                time.sleep(0.5)
+                kw['capture_error_mode'] = 'thread_local'
             front, back = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(front):
+            with torch.cuda.graph(front, **kw):
                 g['stats'] = self._split_front()
-            with torch.cuda.graph(back, pool=front.pool()):
+            with torch.cuda.graph(back, pool=front.pool(), **kw):
                 self._split_back()
             g['graph'], g['graph_back'] = front, back
         if g['graph'] is not None:
