@@ -120,8 +120,8 @@ int qbold_params_set_likelihood(QboldParams* p, const QboldLikelihood* lik);
 /* Replaces SignalGenerationLayer.call with noise off (signals.py:55-114,137-140).
  * oef_dbv [n,width], width 2 (OEF,DBV) or 3 (+Hct, variable_hct); signal [n,n_tau].
  * Domain: OEF >= 0 (every caller of the reference produces OEF in [0.04, 0.84]).  A negative OEF is outside what the
- * scheduled quadrature handles: the signal stays right while |1.5 tau dw| <= 3, the OEF gradient
- * of qbold_forward_backward does not.  NaN / Inf rows give NaN / Inf in that row only. */
+ * scheduled quadrature handles (the build option QB_SIGNED_OEF lifts this): results for such rows
+ * are not meaningful and may be non-finite.  NaN / Inf rows give NaN / Inf in that row only. */
 int qbold_forward(const QboldParams* p, const float* oef_dbv, int32_t width, int64_t n,
                   float* signal, void* stream);
 

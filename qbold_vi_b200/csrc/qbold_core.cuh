@@ -102,7 +102,12 @@ __device__ __forceinline__ void tissue_group(const QuadSmem& s, const TauCols& t
 #pragma unroll
         for (int j = 0; j < kColGroup; ++j) {
             float f0, f1 = 0.f;
+#ifdef QB_SIGNED_OEF
+            bessel_pair<BWD>(fabsf(a[j] * u), f0, f1);              // see tissue_sched: even / odd continuation
+            if (a[j] < 0.f) f1 = -f1;
+#else
             bessel_pair<BWD>(a[j] * u, f0, f1);
+#endif
             accI[j] = fmaf(c, f0, accI[j]);
             if (BWD) accD[j] = fmaf(d, f1, accD[j]);
         }
@@ -407,6 +412,13 @@ __device__ __forceinline__ void tissue_sched(int nph, const SchedAddr& sa, float
                                              int my_col, float& I_out, float& Dm_out) {
     constexpr int kPairBytes = 32 * 16, kPairs = QBOLD_SCHED_PHASE_LEN / 2, kPhaseBytes = kPairs * kPairBytes;
     const bool is_ph = lane < nph;
+#ifdef QB_SIGNED_OEF
+    // Negative OEF (outside the reference's callers): 1 - J0 is even and J1 odd in A, so the
+    // quadrature runs on |A| and Dm takes the sign of A.  Off by default: verified in the host emulator only, to be
+    // switched on together with a GPU measurement of the kernels it touches.
+    const float a_sign = A < 0.f ? -1.0f : 1.0f;
+    A = fabsf(A);
+#endif
     const float lo = A * ph_lo, hi = A * ph_hi;
     // one kernel for the whole phase whenever its argument span fits the kernel's validity range
     // (small: x <= 3, mid: [2, 9], big: x >= 6.5 -- the ranges overlap on purpose, see bessel.cuh)
@@ -537,6 +549,9 @@ __device__ __forceinline__ void tissue_sched(int nph, const SchedAddr& sa, float
     const float vd = BWD ? __shfl_sync(kFull, td, src) : 0.f;
     I_out = (my_col >= 0) ? vi : 0.f;
     Dm_out = (my_col >= 0) ? vd : 0.f;
+#ifdef QB_SIGNED_OEF
+    Dm_out *= a_sign;
+#endif
 }
 
 // One entry point for the three quadrature paths: returns (I, dI/dOEF) of this lane's tau.

@@ -777,3 +777,39 @@ def test_skinny_dense_kernels_of_the_heads(emu_enc):
         act = r.standard_normal((n, n_in)).astype(np.float32)
         emu_enc.qb_emu_dense_small_dgrad(_p(g), _p(w), _p(act), n_in, n_out, C.c_int64(n), _p(dx), grid)
         assert rel_max(dx, want * (act > 0)) < 1e-6 and np.all(dx[act <= 0] == 0)
+
+
+def test_signed_oef_option_restores_the_odd_continuation(tmp_path, qb):
+    """-DQB_SIGNED_OEF (off in the library: the kernels it touches were not re-measured): with it the quadrature runs on
+    |A| and the derivative sum takes the sign of A, so a NEGATIVE OEF -- which the reference's callers never produce --
+    gives what TensorFlow's even 1 - J0 / odd J1 give; positive inputs keep their bits.  Without it the gradient of such a
+    voxel is wrong (the known limitation stated in include/qbold.h and DESIGN.md section 4)."""
+    gxx = shutil.which('g++')
+    if not gxx:
+        pytest.skip('g++ not available')
+    libs = {}
+    for tag, extra in (('plain', []), ('signed', ['-DQB_SIGNED_OEF'])):
+        out = str(tmp_path / ('libforward_%s.so' % tag))
+        subprocess.run([gxx, '-O1', '-std=c++17', '-pthread', '-DQB_HOST_EMU', '-fvisibility=hidden', '-fno-gnu-unique'] + extra +
+                       ['-I', os.path.join(ROOT, 'tests', 'host_emu', 'shim'), '-I', os.path.join(ROOT, 'qbold_vi_b200', 'csrc'),
+                        '-shared', '-fPIC', os.path.join(ROOT, 'tests', 'host_emu', 'forward_host.cpp'), '-o', out], check=True,
+                       capture_output=True, timeout=900)
+        libs[tag] = C.CDLL(out)
+    layer = qb.SignalGenerationLayer(_cfg(), True, True)
+    plain = type(layer.params)()
+    C.memmove(C.byref(plain), C.byref(layer.params), C.sizeof(plain))
+    plain.sched_phases = 0                                                           # -> column-group path
+    ph = o.parse_params(_cfg())
+    r = np.random.default_rng(3)
+    neg = np.stack([-r.uniform(0.01, 0.84, 40), r.uniform(0.001, 0.2, 40)], -1).astype(np.float32)
+    pos = _voxels(41, 9)
+    g = r.standard_normal((41, 11)).astype(np.float32)
+    s64, g64 = o.forward_backward(ph, neg, g[:40], dtype=np.float64)
+    for run in (lambda lib, x, gg: _pair(lib, layer, x, gg), lambda lib, x, gg: _generic(lib, layer.params, x, gg, 11, path=0),
+                lambda lib, x, gg: _generic(lib, plain, x, gg, 11, path=1)):
+        sig, grad = run(libs['signed'], neg, g[:40])
+        assert rel_elem(sig, s64) < SIG_TOL and rel_max(grad, g64) < GRAD_TOL
+        a, b = run(libs['signed'], pos, g), run(libs['plain'], pos, g)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])             # positive OEF: not a bit changes
+    _, grad_plain = _pair(libs['plain'], layer, neg, g[:40])
+    assert not rel_max(grad_plain, g64) < 1e-2                                       # the limitation, as documented: wrong or non-finite
